@@ -1,0 +1,198 @@
+/* msim.h — C ABI of the B200 engine for the microsimulation hot path.
+ *
+ * This is the drop-in boundary: an R-free restatement of the entry points the
+ * reference registers with R in src/init.c:32-62 (its .Call and .C tables).
+ * Every function below names the reference interface it replaces.  The R glue
+ * a maintainer adds on top (SEXP <-> these structs) is shown in
+ * INTEGRATION.md.  No torch, CUDA or C++ types appear in any signature.
+ *
+ * Conventions
+ *   - every function that can fail returns MSIM_OK (0) or a negative code and
+ *     records a message readable through msim_last_error(); nothing throws
+ *     across this boundary;
+ *   - one call at a time per process (the reference is single-threaded with
+ *     static state, src/ssim.cc:35-79, 154-156);
+ *   - tables are column-major (each column is one R numeric vector), live in
+ *     page-locked host memory owned by the library, and are released with
+ *     msim_table_free / msim_report_free;
+ *   - there is NO CPU fallback: without a CUDA device every simulation entry
+ *     returns MSIM_ERR_NO_DEVICE.
+ */
+#ifndef MSIM_H
+#define MSIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSIM_OK 0
+#define MSIM_ERR_NO_DEVICE (-1)   /* no CUDA device / driver */
+#define MSIM_ERR_CUDA (-2)        /* a CUDA call failed (message has the detail) */
+#define MSIM_ERR_ARG (-3)         /* invalid argument */
+#define MSIM_ERR_HEAP (-4)        /* a person needed more pending events than the device heap holds */
+#define MSIM_ERR_SEED (-5)        /* illegal MRG32k3a seed (RngStream.cpp:234-268) */
+#define MSIM_ERR_STREAM (-6)      /* sequential-stream model drew more uniforms per person than planned for */
+#define MSIM_ERR_STATE (-7)       /* call order error (e.g. no current stream) */
+
+/* ---- tables --------------------------------------------------------- */
+
+typedef struct msim_table {
+  int64_t nrow;
+  int32_t ncol;
+  const char *const *colnames; /* ncol static strings, the reference's R column names */
+  double *data;                /* column j = data[j*nrow .. (j+1)*nrow) */
+} msim_table;
+
+/* EventReport::wrap() (microsimulation.h:974-986) / SummaryReport::asList()
+ * (microsimulation.h:1125-1145): sparse, key-sorted tables.
+ *   pt     : Key, age, pt            ut    : Key, age, utility
+ *   events : Key, event, age, number prev  : Key, age, number
+ *   costs  : Key, age, cost          (SummaryReport only, else nrow = 0)
+ *   indiv  : utilities, costs        (SummaryReport with indivp, else nrow = 0)  */
+typedef struct msim_report {
+  msim_table pt, ut, events, prev, costs, indiv;
+} msim_report;
+
+/* callCalibrationSimulation's named list (calibperson-r.cc:176-200):
+ * occupancy is 10 x 4 column-major, columns DiseaseFree, Precursor,
+ * PreClinical, Clinical; `present[j]` says whether the reference's list would
+ * contain column j at all (it only has stages that were ever counted).
+ * TimeAtRisk has n_time_at_risk (<= 4) valid entries. */
+typedef struct msim_calibration {
+  double occupancy[40];
+  int32_t present[4];
+  double time_at_risk[4];
+  int32_t n_time_at_risk;
+} msim_calibration;
+
+void msim_table_free(msim_table *t);
+void msim_report_free(msim_report *r);
+
+/* ---- library state --------------------------------------------------- */
+
+const char *msim_last_error(void);
+const char *msim_version(void);
+/* Bind the calling process to a CUDA device (default: device 0 on first use). */
+int msim_init(int device);
+void msim_shutdown(void);
+/* Number of kernels this library has launched since it was loaded. */
+int64_t msim_launch_count(void);
+
+/* ---- RNG state (replaces the .C table, src/init.c:11-30) ------------- */
+
+/* src/microsimulation.cc:33-42 — default RngStream that serves unif_rand()
+ * under RNGkind("user"); created in .onLoad, removed in .onUnload. */
+void msim_r_create_current_stream(void);
+void msim_r_remove_current_stream(void);
+/* src/microsimulation.cc:44-51: package seed AND default-stream seed. */
+int msim_r_set_user_random_seed(const double seed[6]);
+/* src/microsimulation.cc:53-59 */
+int msim_r_get_user_random_seed(double seed[6]);
+/* src/microsimulation.cc:61-63 */
+int msim_r_next_rng_substream(void);
+/* src/microsimulation.cc:65-75: seed <- seed advanced by *n substreams
+ * (side effect kept: it constructs an RngStream, advancing the package seed). */
+int msim_r_rng_advance_substream(double seed[6], const int *n);
+
+/* R's own generator, which the wrappers select with
+ * RNGkind("Mersenne-Twister"); set.seed(12345) before the .Call
+ * (R/rcpp_hello_world.R:325-336, 346-353, 374-381).  R glue copies
+ * .Random.seed in before the call and back out after it (Rcpp::RNGScope,
+ * illness-death.cpp:75). State = R's 625 words: position, then mt[624]. */
+int msim_mt_set_state(const uint32_t state[625]);
+int msim_mt_get_state(uint32_t state[625]);
+int msim_mt_set_seed(uint32_t seed); /* == RNGkind("Mersenne-Twister"); set.seed(seed) */
+
+/* ---- the five model entry points (replace the .Call table) ----------- */
+
+/* callPersonSimulation(inseed, parms$n)   src/person-r.cc:195-226
+ * Row log columns (std::map key order): endTime, event, id, startTime, state. */
+int msim_callPersonSimulation(const int32_t inseed[6], int32_t n, msim_table *out);
+
+/* callSimplePerson(parms$n)               src/simple-example.cc:72-83
+ * Columns: endtime, event, id, startTime, state.  Draws from the MT state. */
+int msim_callSimplePerson(int32_t n, msim_table *out);
+
+/* callSimplePerson2(parms$n)              src/simple-example2.cc:62-83 */
+int msim_callSimplePerson2(int32_t n, msim_report *out);
+
+/* callIllnessDeath(parms$n, $cure, $zsd)  src/illness-death.cpp:73-94 */
+int msim_callIllnessDeath(int32_t n, double cure, double zsd, msim_report *out);
+
+/* callCalibrationSimulation(parms$n, $runpar)  src/calibperson-r.cc:176-200
+ * Uses the package seed last set with msim_r_set_user_random_seed. */
+int msim_callCalibrationSimulation(int32_t n, const double runpar[6], msim_calibration *out);
+
+/* ---- sharded / device-resident forms (multi-GPU, benchmarks) --------- */
+
+#define MSIM_OUT_ROWLOG 1u   /* life-history rows */
+#define MSIM_OUT_REPORT 2u   /* EventReport attached to every handled event */
+#define MSIM_OUT_COUNTS 4u   /* per-kind event counts + sum of end times */
+
+/* Dense report geometry (states x events x age bins over the partition
+ * {0,1,..,100,1e6} used by every built model). */
+typedef struct msim_dense_dims {
+  int32_t n_state, n_event, n_bin;
+  int64_t n_doubles; /* length of the dense accumulator vector */
+} msim_dense_dims;
+
+typedef struct msim_person_shard {
+  double seed[6];        /* package seed (stream "NH" = first stream made from it) */
+  int64_t first_person;  /* person i uses substream i+1 of that stream */
+  int64_t n;
+  uint32_t outputs;      /* MSIM_OUT_* */
+  double discount_rate;  /* EventReport utility discounting (0 = none) */
+} msim_person_shard;
+
+typedef struct msim_person_device_result {
+  int64_t n_rows;        /* rows written to the device row log */
+  int64_t capacity;      /* rows the device row log can hold */
+  const double *d_rowlog;   /* DEVICE pointer, 5 columns, column stride = capacity */
+  const double *d_dense;    /* DEVICE pointer, dims.n_doubles accumulators (or NULL) */
+  const double *d_counts;   /* DEVICE pointer: 8 per-kind counts, then sum(endTime) */
+  msim_dense_dims dims;
+} msim_person_device_result;
+
+/* Run persons [first_person, first_person+n) of callPersonSimulation on the
+ * current device and leave the results in device memory owned by the library
+ * (valid until the next call).  Synchronous on return. */
+int msim_person_run_device(const msim_person_shard *shard, msim_person_device_result *res);
+/* Same, but asynchronous: only enqueues work on the library stream. */
+int msim_person_enqueue(const msim_person_shard *shard, msim_person_device_result *res);
+int msim_sync(void);
+/* Average device time (ms) of the last enqueue/run, measured with CUDA events
+ * on the library's stream around the simulation kernel. */
+int msim_last_kernel_ms(float *ms);
+/* Copy results of the last run to the host. */
+int msim_person_fetch_rowlog(msim_table *out);
+int msim_person_fetch_counts(double counts[9]);
+/* Dense accumulators (e.g. after an all-reduce done by the caller on the
+ * device buffer) -> sparse report tables in the reference's layout. */
+int msim_dense_to_report(const double *host_dense, const msim_dense_dims *dims, msim_report *out);
+/* Writable device pointer to the dense accumulators of the last run, for an
+ * in-place NCCL all-reduce by the host layer. */
+int msim_dense_device_ptr(double **d_ptr, int64_t *n_doubles);
+int msim_dense_fetch(double *host_dense, int64_t n_doubles);
+
+/* Calibration sweep: n_sets parameter vectors (row-major n_sets x 6), every
+ * set run on persons [first_person, first_person+n) with the same seed
+ * (common random numbers, R/calibSim.R:12-14). out has n_sets entries. */
+int msim_calibration_sweep(const double seed[6], int64_t first_person, int64_t n, int32_t n_sets,
+                           const double *runpar, msim_calibration *out);
+
+/* K1 parity hook: uniforms[j*draws + k] = k-th uniform of substream
+ * first_substream+j of the stream whose state is `seed` (substream 0 = seed). */
+int msim_rng_uniforms(const double seed[6], int64_t first_substream, int64_t n_substreams, int32_t draws,
+                      double *uniforms_host);
+/* MT19937 parity hook: the first n uniforms R's unif_rand() would return from
+ * the current MT state (state is NOT advanced). */
+int msim_mt_uniforms(int64_t n, double *uniforms_host);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* MSIM_H */

@@ -1,0 +1,256 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Never linked into the product library.
+//
+// C entry points of the CPU oracle.  They mirror include/msim.h one for one
+// (same structs, `oracle_` prefix) so a parity test calls both sides with the
+// same arguments.  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load this library.
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "cprocess_lite.h"
+#include "models.h"
+
+using namespace orc;
+
+namespace {
+
+const char *const ROWLOG_COLS_PERSON[5] = {"endTime", "event", "id", "startTime", "state"};
+const char *const ROWLOG_COLS_SIMPLE[5] = {"endtime", "event", "id", "startTime", "state"};
+const char *const PT_COLS[3] = {"Key", "age", "pt"};
+const char *const UT_COLS[3] = {"Key", "age", "utility"};
+const char *const EV_COLS[4] = {"Key", "event", "age", "number"};
+const char *const PREV_COLS[3] = {"Key", "age", "number"};
+const char *const COST_COLS[3] = {"Key", "age", "cost"};
+const char *const INDIV_COLS[2] = {"utilities", "costs"};
+
+void fill_rowlog(const RowLog &log, const char *const *cols, msim_table *t) {
+  int64_t n = (int64_t)log.id.size();
+  t->nrow = n;
+  t->ncol = 5;
+  t->colnames = cols;
+  t->data = (double *)malloc(sizeof(double) * 5 * (n ? n : 1));
+  const std::vector<double> *src[5] = {&log.endTime, &log.event, &log.id, &log.startTime, &log.state};
+  for (int j = 0; j < 5; j++)
+    if (n) memcpy(t->data + j * n, src[j]->data(), sizeof(double) * n);
+}
+
+// row-major rows -> column-major table
+void fill_table(const std::vector<double> &rows, int64_t n, int ncol, const char *const *cols, msim_table *t) {
+  t->nrow = n;
+  t->ncol = ncol;
+  t->colnames = cols;
+  t->data = (double *)malloc(sizeof(double) * ncol * (n ? n : 1));
+  for (int64_t i = 0; i < n; i++)
+    for (int j = 0; j < ncol; j++) t->data[j * n + i] = rows[i * ncol + j];
+}
+
+void fill_report(const ReportTables &r, msim_report *out) {
+  fill_table(r.pt, r.n_pt, 3, PT_COLS, &out->pt);
+  fill_table(r.ut, r.n_ut, 3, UT_COLS, &out->ut);
+  fill_table(r.events, r.n_events, 4, EV_COLS, &out->events);
+  fill_table(r.prev, r.n_prev, 3, PREV_COLS, &out->prev);
+  fill_table(r.costs, r.n_costs, 3, COST_COLS, &out->costs);
+  fill_table(r.indiv, r.n_indiv, 2, INDIV_COLS, &out->indiv);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *oracle_flavour(void) {
+#ifdef MSIM_ORACLE_USE_REFERENCE
+  return "reference";  // reference's ssim.cc + RngStream.cpp + heap.h compiled where they lie
+#else
+  return "port";  // restated engine + integer RngStream
+#endif
+}
+
+void oracle_table_free(msim_table *t) {
+  free(t->data);
+  t->data = 0;
+  t->nrow = 0;
+}
+void oracle_report_free(msim_report *r) {
+  oracle_table_free(&r->pt);
+  oracle_table_free(&r->ut);
+  oracle_table_free(&r->events);
+  oracle_table_free(&r->prev);
+  oracle_table_free(&r->costs);
+  oracle_table_free(&r->indiv);
+}
+
+uint64_t oracle_events_handled(void) { return g_events_handled; }
+uint64_t oracle_draws_taken(void) { return rlite::draws_taken(); }
+void oracle_reset_counters(void) {
+  g_events_handled = 0;
+  rlite::reset_draw_counter();
+}
+
+// ---- RNG state
+void oracle_r_create_current_stream(void) { ssim::r_create_current_stream(); }
+void oracle_r_remove_current_stream(void) { ssim::r_remove_current_stream(); }
+int oracle_r_set_user_random_seed(const double seed[6]) {
+  double s[6];
+  memcpy(s, seed, sizeof s);
+  ssim::r_set_user_random_seed(s);
+  return 0;
+}
+int oracle_r_get_user_random_seed(double seed[6]) {
+  ssim::r_get_user_random_seed(seed);
+  return 0;
+}
+int oracle_r_next_rng_substream(void) {
+  ssim::r_next_rng_substream();
+  return 0;
+}
+int oracle_r_rng_advance_substream(double seed[6], const int *n) {
+  int nn = *n;
+  ssim::r_rng_advance_substream(seed, &nn);
+  return 0;
+}
+int oracle_mt_set_seed(uint32_t seed) {
+  rlite::RNGkind(rlite::MERSENNE_TWISTER);
+  rlite::set_seed(seed);
+  return 0;
+}
+
+// uniforms[j*draws+k]: k-th uniform of substream first_substream+j of the
+// stream whose start state is `seed` (substream 0 = seed itself)
+int oracle_rng_uniforms(const double seed[6], int64_t first_substream, int64_t n_substreams, int32_t draws,
+                        double *uniforms) {
+  ssim::RngStream g;
+  if (!g.SetSeed(seed)) return MSIM_ERR_SEED;
+  if (first_substream > 0) g.AdvanceSubstream(0, (int32_t)first_substream);
+  for (int64_t j = 0; j < n_substreams; j++) {
+    for (int k = 0; k < draws; k++) uniforms[j * draws + k] = g.RandU01();
+    g.ResetNextSubstream();
+  }
+  return 0;
+}
+
+int oracle_mt_uniforms(int64_t n, double *uniforms) {
+  for (int64_t i = 0; i < n; i++) uniforms[i] = unif_rand();
+  return 0;
+}
+
+// nmath samplers driven by the current generator, for sampler-level parity
+// which: 0 runif(a,b) 1 rweibull(a,b) 2 rexp(a) 3 rnorm(a,b) 4 exp_rand 5 norm_rand
+int oracle_sample(int which, double a, double b, int64_t n, double *out) {
+  for (int64_t i = 0; i < n; i++) {
+    switch (which) {
+      case 0: out[i] = R::runif(a, b); break;
+      case 1: out[i] = R::rweibull(a, b); break;
+      case 2: out[i] = R::rexp(a); break;
+      case 3: out[i] = R::rnorm(a, b); break;
+      case 4: out[i] = exp_rand(); break;
+      case 5: out[i] = norm_rand(); break;
+      default: return MSIM_ERR_ARG;
+    }
+  }
+  return 0;
+}
+double oracle_qnorm(double p) { return R::qnorm(p, 0.0, 1.0, 1, 0); }
+double oracle_gammafn(double x) { return R::gammafn(x); }
+double oracle_discountedInterval(double y, double start, double end, double rate) {
+  return ssim::discountedInterval(y, start, end, rate);
+}
+
+// ---- models
+int oracle_callPersonSimulation(const int32_t inseed[6], int32_t n, msim_table *out) {
+  double seed[6];
+  for (int i = 0; i < 6; i++) seed[i] = inseed[i];
+  RowLog log;
+  run_person_r(seed, 0, n, true, &log, 0, 0, 0.0);
+  fill_rowlog(log, ROWLOG_COLS_PERSON, out);
+  return 0;
+}
+
+// sharded form: counts[0..7] events by kind, counts[8] = sum(endTime)
+int oracle_person_run(const msim_person_shard *sh, msim_table *rowlog, double counts[9], msim_report *report) {
+  RowLog log;
+  ReportTables rt;
+  run_person_r(sh->seed, sh->first_person, sh->n, rowlog != 0, &log, counts, report ? &rt : 0, sh->discount_rate);
+  if (rowlog) fill_rowlog(log, ROWLOG_COLS_PERSON, rowlog);
+  if (report) fill_report(rt, report);
+  return 0;
+}
+
+int oracle_callSimplePerson(int32_t n, msim_table *out) {
+  RowLog log;
+  run_simple_person(n, &log);
+  fill_rowlog(log, ROWLOG_COLS_SIMPLE, out);
+  return 0;
+}
+int oracle_callSimplePerson2(int32_t n, msim_report *out) {
+  ReportTables rt;
+  run_simple_person2(n, &rt);
+  fill_report(rt, out);
+  return 0;
+}
+int oracle_callIllnessDeath(int32_t n, double cure, double zsd, msim_report *out) {
+  ReportTables rt;
+  run_illness_death(n, cure, zsd, &rt);
+  fill_report(rt, out);
+  return 0;
+}
+int oracle_callCalibrationSimulation(int32_t n, const double runpar[6], msim_calibration *out) {
+  run_calibration(0, n, runpar, out);
+  return 0;
+}
+int oracle_calibration_sweep(const double seed[6], int64_t first_person, int64_t n, int32_t n_sets,
+                             const double *runpar, msim_calibration *out) {
+  for (int s = 0; s < n_sets; s++) {
+    double sd[6];
+    memcpy(sd, seed, sizeof sd);
+    if (!ssim::RngStream::SetPackageSeed(sd)) return MSIM_ERR_SEED;
+    run_calibration(first_person, n, runpar + 6 * s, out + s);
+  }
+  return 0;
+}
+
+// Sick-Sicker (README.org:214-301). par = the 17 SickSickerParam fields in
+// declaration order. trace (optional) receives 5 doubles per handled event:
+// id, state, kind, previous, now — the README's debug print.
+int oracle_sick_sicker(int64_t n, const double par[17], int indivp, int substreams, int64_t first_person,
+                       msim_report *out, double *trace, int64_t trace_cap, int64_t *trace_len) {
+  SickSickerParam p;
+  p.r_HS1 = par[0]; p.r_HD = par[1]; p.r_S1H = par[2]; p.r_S1S2 = par[3]; p.r_S1D = par[4]; p.r_S2D = par[5];
+  p.c_H = par[6]; p.c_S1 = par[7]; p.c_S2 = par[8]; p.c_Trt = par[9];
+  p.u_H = par[10]; p.u_S1 = par[11]; p.u_S2 = par[12]; p.u_Trt = par[13];
+  p.discountRate = par[14]; p.partitionBy = par[15]; p.Trt = (int)par[16];
+  ReportTables rt;
+  std::vector<double> tr;
+  run_sick_sicker(n, &p, indivp != 0, substreams != 0, first_person, &rt, trace ? &tr : 0);
+  fill_report(rt, out);
+  if (trace) {
+    int64_t m = (int64_t)tr.size() < trace_cap ? (int64_t)tr.size() : trace_cap;
+    memcpy(trace, tr.data(), sizeof(double) * m);
+    *trace_len = (int64_t)tr.size();
+  }
+  return 0;
+}
+
+// doc examples: return event times; tick_tock's finish time is the last one
+int64_t oracle_tick_tock(double *times, int64_t cap) {
+  std::vector<double> t;
+  run_tick_tock(&t);
+  for (size_t i = 0; i < t.size() && (int64_t)i < cap; i++) times[i] = t[i];
+  return (int64_t)t.size();
+}
+int64_t oracle_doc_illness_death(int n, double *times, int64_t cap, double *qaly_cost) {
+  std::vector<double> t, qc;
+  run_doc_illness_death(n, &t, &qc);
+  for (size_t i = 0; i < t.size() && (int64_t)i < cap; i++) times[i] = t[i];
+  for (size_t i = 0; i < qc.size(); i++) qaly_cost[i] = qc[i];
+  return (int64_t)t.size();
+}
+int oracle_priority_demo(double order[4]) {
+  std::vector<double> o;
+  run_priority_demo(&o);
+  for (size_t i = 0; i < o.size() && i < 4; i++) order[i] = o[i];
+  return (int)o.size();
+}
+
+}  // extern "C"
