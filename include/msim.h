@@ -171,7 +171,8 @@ int msim_person_fetch_rowlog(msim_table *out);
 int msim_person_fetch_counts(double counts[9]);
 /* Dense accumulators (e.g. after an all-reduce done by the caller on the
  * device buffer) -> sparse report tables in the reference's layout. */
-int msim_dense_to_report(const double *host_dense, const msim_dense_dims *dims, msim_report *out);
+int msim_dense_to_report(const double *host_dense, const msim_dense_dims *dims, double discount_rate,
+                         msim_report *out);
 /* Writable device pointer to the dense accumulators of the last run, for an
  * in-place NCCL all-reduce by the host layer. */
 int msim_dense_device_ptr(double **d_ptr, int64_t *n_doubles);

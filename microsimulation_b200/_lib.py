@@ -1,0 +1,114 @@
+"""ctypes binding of include/msim.h (the C ABI of libmsim_b200.so)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+MSIM_OUT_ROWLOG, MSIM_OUT_REPORT, MSIM_OUT_COUNTS = 1, 2, 4
+
+ERRORS = {-1: "MSIM_ERR_NO_DEVICE", -2: "MSIM_ERR_CUDA", -3: "MSIM_ERR_ARG", -4: "MSIM_ERR_HEAP", -5: "MSIM_ERR_SEED",
+          -6: "MSIM_ERR_STREAM", -7: "MSIM_ERR_STATE"}
+
+
+class MsimError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s (%d): %s" % (ERRORS.get(code, "error"), code, msg))
+        self.code = code
+
+
+class Table(C.Structure):
+    _fields_ = [("nrow", C.c_int64), ("ncol", C.c_int32), ("colnames", C.POINTER(C.c_char_p)),
+                ("data", C.POINTER(C.c_double))]
+
+    def to_dict(self, copy=True):
+        out = {}
+        for j in range(self.ncol):
+            name = self.colnames[j].decode()
+            if self.nrow:
+                base = C.addressof(self.data.contents) + 8 * j * self.nrow
+                col = np.ctypeslib.as_array((C.c_double * self.nrow).from_address(base))
+                out[name] = col.copy() if copy else col
+            else:
+                out[name] = np.zeros(0)
+        return out
+
+
+class Report(C.Structure):
+    _fields_ = [(k, Table) for k in ("pt", "ut", "events", "prev", "costs", "indiv")]
+
+    def to_dict(self):
+        return {k: getattr(self, k).to_dict() for k in ("pt", "ut", "events", "prev", "costs", "indiv")}
+
+
+class Calibration(C.Structure):
+    _fields_ = [("occupancy", C.c_double * 40), ("present", C.c_int32 * 4), ("time_at_risk", C.c_double * 4),
+                ("n_time_at_risk", C.c_int32)]
+
+    def to_dict(self):
+        names = ["DiseaseFree", "Precursor", "PreClinical", "Clinical"]
+        out = {"TimeAtRisk": np.array(self.time_at_risk[:self.n_time_at_risk])}
+        for s, nm in enumerate(names):
+            if self.present[s]:
+                out[nm] = np.array(self.occupancy[s * 10:(s + 1) * 10])
+        return out
+
+
+class DenseDims(C.Structure):
+    _fields_ = [("n_state", C.c_int32), ("n_event", C.c_int32), ("n_bin", C.c_int32), ("n_doubles", C.c_int64)]
+
+
+class PersonShard(C.Structure):
+    _fields_ = [("seed", C.c_double * 6), ("first_person", C.c_int64), ("n", C.c_int64), ("outputs", C.c_uint32),
+                ("discount_rate", C.c_double)]
+
+
+class PersonDeviceResult(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("capacity", C.c_int64), ("d_rowlog", C.c_void_p), ("d_dense", C.c_void_p),
+                ("d_counts", C.c_void_p), ("dims", DenseDims)]
+
+
+# every symbol include/msim.h declares (tests check that the library exports them all)
+SYMBOLS = [
+    "msim_table_free", "msim_report_free", "msim_last_error", "msim_version", "msim_init", "msim_shutdown",
+    "msim_launch_count", "msim_r_create_current_stream", "msim_r_remove_current_stream",
+    "msim_r_set_user_random_seed", "msim_r_get_user_random_seed", "msim_r_next_rng_substream",
+    "msim_r_rng_advance_substream", "msim_mt_set_state", "msim_mt_get_state", "msim_mt_set_seed",
+    "msim_callPersonSimulation", "msim_callSimplePerson", "msim_callSimplePerson2", "msim_callIllnessDeath",
+    "msim_callCalibrationSimulation", "msim_person_run_device", "msim_person_enqueue", "msim_sync",
+    "msim_last_kernel_ms", "msim_person_fetch_rowlog", "msim_person_fetch_counts", "msim_dense_to_report",
+    "msim_dense_device_ptr", "msim_dense_fetch", "msim_calibration_sweep", "msim_rng_uniforms", "msim_mt_uniforms",
+]
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load libmsim_b200.so (building it if sources changed).  Fails loudly if it cannot."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build()
+    L = C.CDLL(path)
+    L.msim_last_error.restype = C.c_char_p
+    L.msim_version.restype = C.c_char_p
+    L.msim_launch_count.restype = C.c_int64
+    L.msim_r_create_current_stream.restype = None
+    L.msim_r_remove_current_stream.restype = None
+    L.msim_table_free.restype = None
+    L.msim_report_free.restype = None
+    L.msim_shutdown.restype = None
+    L.msim_callIllnessDeath.argtypes = [C.c_int32, C.c_double, C.c_double, C.POINTER(Report)]
+    L.msim_dense_to_report.argtypes = [C.POINTER(C.c_double), C.POINTER(DenseDims), C.c_double, C.POINTER(Report)]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise MsimError(rc, load().msim_last_error().decode())

@@ -1,0 +1,256 @@
+"""Host-side mirror of the reference's R wrappers, over the C ABI.
+
+Same names, arguments and defaults as the R functions a user of the reference
+calls (R/rcpp_hello_world.R:104-152, 300-390; R/calibSim.R:10-40), so parity
+tests read like the reference's own tests (tests/testthat/*.R).  Everything
+here is thin: seeds in, tables out; all simulation work happens in
+libmsim_b200.so on the GPU.  There is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (MSIM_OUT_COUNTS, MSIM_OUT_REPORT, MSIM_OUT_ROWLOG, Calibration, DenseDims, PersonDeviceResult,
+                   PersonShard, Report, Table, check, load)
+
+_stream_created = False
+
+
+def _ensure_stream():
+    """.onLoad of the R package calls r_create_current_stream (R/zzz.R)."""
+    global _stream_created
+    if not _stream_created:
+        load().msim_r_create_current_stream()
+        _stream_created = True
+
+
+def _seed6(seed):
+    """set.user.Random.seed's recycling rule (R/rcpp_hello_world.R:104-110)."""
+    if np.isscalar(seed):
+        seed = [seed] * 6
+    seed = [float(x) + (2.0 ** 32 if x < 0 else 0.0) for x in seed]  # unsigned()
+    if len(seed) == 7:
+        seed = seed[1:]
+    if len(seed) != 6:
+        raise ValueError("seed must have length 1, 6 or 7")
+    return seed
+
+
+def init(device=0):
+    check(load().msim_init(device))
+
+
+def launch_count():
+    return int(load().msim_launch_count())
+
+
+# ---- RNG utilities (R/rcpp_hello_world.R:104-152)
+
+def set_user_random_seed(seed):
+    _ensure_stream()
+    s = (C.c_double * 6)(*_seed6(seed))
+    check(load().msim_r_set_user_random_seed(s))
+    return list(s)
+
+
+def user_random_seed():
+    _ensure_stream()
+    s = (C.c_double * 6)()
+    check(load().msim_r_get_user_random_seed(s))
+    return [407] + [int(x) for x in s]
+
+
+def next_user_random_substream():
+    _ensure_stream()
+    check(load().msim_r_next_rng_substream())
+
+
+def advance_substream(seed, n):
+    s = (C.c_double * 6)(*_seed6(seed))
+    nn = C.c_int(int(n))
+    check(load().msim_r_rng_advance_substream(s, C.byref(nn)))
+    return list(s)
+
+
+def set_seed(seed=12345):
+    """RNGkind("Mersenne-Twister"); set.seed(seed)."""
+    check(load().msim_mt_set_seed(C.c_uint32(seed)))
+
+
+def mt_state():
+    st = (C.c_uint32 * 625)()
+    check(load().msim_mt_get_state(st))
+    return np.array(st[:], dtype=np.uint32)
+
+
+def set_mt_state(state):
+    st = (C.c_uint32 * 625)(*[int(x) for x in state])
+    check(load().msim_mt_set_state(st))
+
+
+def rng_uniforms(seed, first_substream, n_substreams, draws):
+    s = (C.c_double * 6)(*_seed6(seed))
+    out = np.empty(n_substreams * draws)
+    check(load().msim_rng_uniforms(s, C.c_int64(first_substream), C.c_int64(n_substreams), C.c_int32(draws),
+                                   out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out.reshape(n_substreams, draws)
+
+
+def mt_uniforms(n):
+    out = np.empty(n)
+    check(load().msim_mt_uniforms(C.c_int64(n), out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+# ---- the model wrappers
+
+def _table(fn, *args):
+    t = Table()
+    check(fn(*args, C.byref(t)))
+    d = t.to_dict()
+    load().msim_table_free(C.byref(t))
+    return d
+
+
+def _report(fn, *args):
+    r = Report()
+    check(fn(*args, C.byref(r)))
+    d = r.to_dict()
+    load().msim_report_free(C.byref(r))
+    return d
+
+
+def callPersonSimulation(n=20, seed=(12345,) * 6):
+    """R/rcpp_hello_world.R:300-315 -> src/person-r.cc:195-226."""
+    s6 = _seed6(list(seed) if not np.isscalar(seed) else seed)
+    set_user_random_seed(s6)
+    ints = (C.c_int32 * 6)(*[int(x) for x in s6])
+    return _table(load().msim_callPersonSimulation, ints, C.c_int32(n))
+
+
+def callSimplePerson(n=10):
+    """R/rcpp_hello_world.R:325-336 -> src/simple-example.cc:72-83."""
+    set_seed(12345)
+    return _table(load().msim_callSimplePerson, C.c_int32(n))
+
+
+def callSimplePerson2(n=10):
+    """R/rcpp_hello_world.R:346-364 -> src/simple-example2.cc:62-83."""
+    set_seed(12345)
+    return _report(load().msim_callSimplePerson2, C.c_int32(n))
+
+
+def callIllnessDeath(n=10, cure=0.1, zsd=0.0):
+    """R/rcpp_hello_world.R:374-390 -> src/illness-death.cpp:73-94."""
+    set_seed(12345)
+    return _report(load().msim_callIllnessDeath, C.c_int32(n), C.c_double(cure), C.c_double(zsd))
+
+
+def callCalibrationPerson(seed=12345, n=500, runpar=(4, 0.5, 0.05, 10, 3, 0.5), mc_cores=1):
+    """R/calibSim.R:10-40 with mc.cores = 1 (more cores change the random numbers in the reference too)."""
+    if mc_cores != 1:
+        raise ValueError("mc_cores > 1 uses different streams per chunk in the reference; shard with calibration_sweep")
+    set_user_random_seed(seed)
+    par = (C.c_double * 6)(*[float(x) for x in runpar])
+    c = Calibration()
+    check(load().msim_callCalibrationSimulation(C.c_int32(n), par, C.byref(c)))
+    d = c.to_dict()
+    states = ["DiseaseFree", "Precursor", "PreClinical", "Clinical"]
+    mat = np.zeros((10, 4))
+    for j, nm in enumerate(states):
+        if nm in d:
+            mat[:, j] = d[nm]
+    return {"StateOccupancy": mat, "TimeAtRisk": d["TimeAtRisk"], "raw": d}
+
+
+def calibration_sweep(seed, runpars, n, first_person=0):
+    """n_sets parameter vectors x persons [first_person, first_person+n), one seed (common random numbers)."""
+    runpars = np.ascontiguousarray(runpars, dtype=np.float64).reshape(-1, 6)
+    ns = runpars.shape[0]
+    arr = (Calibration * ns)()
+    s = (C.c_double * 6)(*_seed6(seed))
+    check(load().msim_calibration_sweep(s, C.c_int64(first_person), C.c_int64(n), C.c_int32(ns),
+                                        runpars.ctypes.data_as(C.POINTER(C.c_double)), arr))
+    return [arr[i].to_dict() for i in range(ns)]
+
+
+# ---- sharded / device-resident person-r runs (multi-GPU, benchmarks)
+
+def person_shard(seed, first_person, n, outputs, discount_rate=0.0):
+    return PersonShard((C.c_double * 6)(*_seed6(seed)), int(first_person), int(n), int(outputs), float(discount_rate))
+
+
+def person_run_device(seed, first_person, n, outputs, discount_rate=0.0):
+    """Runs a shard and leaves results on the device; returns the result struct."""
+    sh = person_shard(seed, first_person, n, outputs, discount_rate)
+    res = PersonDeviceResult()
+    check(load().msim_person_run_device(C.byref(sh), C.byref(res)))
+    return res
+
+
+def person_enqueue(seed, first_person, n, outputs, discount_rate=0.0):
+    sh = person_shard(seed, first_person, n, outputs, discount_rate)
+    res = PersonDeviceResult()
+    check(load().msim_person_enqueue(C.byref(sh), C.byref(res)))
+    return res
+
+
+def sync():
+    check(load().msim_sync())
+
+
+def last_kernel_ms():
+    ms = C.c_float()
+    check(load().msim_last_kernel_ms(C.byref(ms)))
+    return ms.value
+
+
+def person_fetch_rowlog(copy=True):
+    t = Table()
+    check(load().msim_person_fetch_rowlog(C.byref(t)))
+    d = t.to_dict(copy=copy)
+    if copy:
+        load().msim_table_free(C.byref(t))
+        return d
+    return d, t  # caller frees with free_table(t)
+
+
+def free_table(t):
+    load().msim_table_free(C.byref(t))
+
+
+def person_fetch_counts():
+    c = (C.c_double * 9)()
+    check(load().msim_person_fetch_counts(c))
+    return np.array(c[:])
+
+
+def dense_fetch(n_doubles):
+    out = np.empty(n_doubles)
+    check(load().msim_dense_fetch(out.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(n_doubles)))
+    return out
+
+
+def dense_device_ptr():
+    p = C.POINTER(C.c_double)()
+    n = C.c_int64()
+    check(load().msim_dense_device_ptr(C.byref(p), C.byref(n)))
+    return C.cast(p, C.c_void_p).value, n.value
+
+
+def dense_to_report(dense, dims, discount_rate=0.0):
+    dense = np.ascontiguousarray(dense, dtype=np.float64)
+    r = Report()
+    check(load().msim_dense_to_report(dense.ctypes.data_as(C.POINTER(C.c_double)), C.byref(dims),
+                                      C.c_double(discount_rate), C.byref(r)))
+    d = r.to_dict()
+    load().msim_report_free(C.byref(r))
+    return d
+
+
+def person_report(seed, first_person, n, discount_rate=0.0):
+    """Single-GPU person-r run with the EventReport attached; returns (report tables, counts)."""
+    res = person_run_device(seed, first_person, n, MSIM_OUT_REPORT | MSIM_OUT_COUNTS, discount_rate)
+    dense = dense_fetch(res.dims.n_doubles)
+    return dense_to_report(dense, res.dims, discount_rate), person_fetch_counts()

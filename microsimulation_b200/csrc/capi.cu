@@ -1,0 +1,799 @@
+// C ABI of the B200 engine (include/msim.h): host-side orchestration in C++,
+// every simulation step on the GPU.  There is no CPU execution path: without
+// a CUDA device each simulation entry returns MSIM_ERR_NO_DEVICE.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/msim.h"
+#include "host_state.h"
+#include "report_host.h"
+#include "kernels.cuh"
+
+using namespace msim;
+
+namespace {
+
+// ---------------------------------------------------------------- context
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+};
+
+struct Ctx {
+  bool inited = false;
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  MrgJump *d_lo = nullptr, *d_hi = nullptr;
+  DevBuf rowlog, tiles, dense, small, mt_words, len, starts, chain_exit, chain_count, chain_entry, chain_base, calib_out,
+      calib_par, uniforms;
+  HostRngState rng;
+  // last cohort run
+  int64_t last_n_rows = 0, last_capacity = 0;
+  ReportGeom last_geom;
+  unsigned last_outputs = 0;
+  bool last_simple_names = false;
+  bool have_last = false;
+  float last_ms = 0.f;
+  bool timing_pending = false;
+  int64_t launches = 0;
+  // pinned host cache (one buffer) so steady-state row-log fetches do not re-pin
+  void *pin_cache = nullptr;
+  size_t pin_cache_bytes = 0;
+  std::unordered_map<void *, size_t> pinned;  // live pinned allocations -> bytes
+};
+
+Ctx g;
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(MSIM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));             \
+  } while (0)
+
+int ensure(DevBuf &b, size_t bytes) {
+  if (b.bytes >= bytes && b.p) return MSIM_OK;
+  if (b.p) CK(cudaFree(b.p));
+  b.p = nullptr;
+  b.bytes = 0;
+  size_t want = bytes < 256 ? 256 : bytes;
+  CK(cudaMalloc(&b.p, want));
+  b.bytes = want;
+  return MSIM_OK;
+}
+
+int ensure_init() {
+  if (g.inited) return MSIM_OK;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(MSIM_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0"));
+  if (g.device >= ndev) return fail(MSIM_ERR_ARG, "device index out of range");
+  CK(cudaSetDevice(g.device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, g.device));
+  g.sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&g.ev0));
+  CK(cudaEventCreate(&g.ev1));
+  // per-thread start tables: lo[j] = M^j, hi[j] = M^(JUMP_TAB*j)
+  std::vector<MrgJump> lo(JUMP_TAB), hi(JUMP_TAB);
+  const MrgJump &M = mrg_substream_jump();
+  lo[0] = mrg_jump_identity();
+  for (int j = 1; j < JUMP_TAB; j++) lo[j] = mrg_jump_mul(M, lo[j - 1]);
+  MrgJump Mt = mrg_jump_mul(M, lo[JUMP_TAB - 1]);  // M^JUMP_TAB
+  hi[0] = mrg_jump_identity();
+  for (int j = 1; j < JUMP_TAB; j++) hi[j] = mrg_jump_mul(Mt, hi[j - 1]);
+  CK(cudaMalloc(&g.d_lo, sizeof(MrgJump) * JUMP_TAB));
+  CK(cudaMalloc(&g.d_hi, sizeof(MrgJump) * JUMP_TAB));
+  CK(cudaMemcpy(g.d_lo, lo.data(), sizeof(MrgJump) * JUMP_TAB, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(g.d_hi, hi.data(), sizeof(MrgJump) * JUMP_TAB, cudaMemcpyHostToDevice));
+  g.inited = true;
+  return MSIM_OK;
+}
+
+// substream state of person `first_person` of the stream that starts at `state`
+void stream_start(const uint32_t state[6], int64_t first_person, int grid, StreamStart *st) {
+  Mrg32k3a b;
+  memcpy(b.s, state, sizeof b.s);
+  b.jump(mrg_jump_pow(mrg_substream_jump(), (uint64_t)first_person + 1));
+  memcpy(st->base, b.s, sizeof b.s);
+  st->lo = g.d_lo;
+  st->hi = g.d_hi;
+  st->stride = mrg_jump_pow(mrg_substream_jump(), (uint64_t)grid * BLOCK);
+}
+
+// ---------------------------------------------------------------- host memory
+
+int pinned_alloc(size_t bytes, double **out) {
+  if (bytes == 0) bytes = 8;
+  if (g.pin_cache && g.pin_cache_bytes >= bytes) {
+    *out = (double *)g.pin_cache;
+    g.pinned[g.pin_cache] = g.pin_cache_bytes;
+    g.pin_cache = nullptr;
+    g.pin_cache_bytes = 0;
+    return MSIM_OK;
+  }
+  void *p = nullptr;
+  CK(cudaMallocHost(&p, bytes));
+  g.pinned[p] = bytes;
+  *out = (double *)p;
+  return MSIM_OK;
+}
+
+void host_free(double *p) {
+  if (!p) return;
+  auto it = g.pinned.find(p);
+  if (it == g.pinned.end()) {
+    free(p);
+    return;
+  }
+  size_t bytes = it->second;
+  g.pinned.erase(it);
+  if (bytes > g.pin_cache_bytes) {  // keep the largest buffer for the next call
+    if (g.pin_cache) cudaFreeHost(g.pin_cache);
+    g.pin_cache = p;
+    g.pin_cache_bytes = bytes;
+  } else {
+    cudaFreeHost(p);
+  }
+}
+
+ReportGeom geom_from_dims(const msim_dense_dims *dims, double discount_rate) {
+  return ages_geom(dims->n_state, dims->n_event, discount_rate);
+}
+
+// ---------------------------------------------------------------- cohort launch
+
+// `small` buffer layout (doubles / 8-byte cells): [0..8] counts, [9] n_rows (u64), [10] error (int), [11] end_word (i64)
+struct SmallView {
+  double *counts;
+  unsigned long long *n_rows;
+  int *error;
+  int64_t *end_word;
+};
+SmallView small_view() {
+  SmallView v;
+  double *b = (double *)g.small.p;
+  v.counts = b;
+  v.n_rows = (unsigned long long *)(b + 9);
+  v.error = (int *)(b + 10);
+  v.end_word = (int64_t *)(b + 11);
+  return v;
+}
+
+template <class Traits, bool STREAM>
+int cohort_grid(size_t smem, int64_t n, int *grid) {
+  auto kern = cohort_kernel<Traits, STREAM>;
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem));
+  if (per_sm < 1) return fail(MSIM_ERR_CUDA, "cohort kernel does not fit on an SM");
+  int64_t tiles = (n + BLOCK - 1) / BLOCK;
+  int64_t gmax = (int64_t)per_sm * g.sm_count;
+  if (gmax > JUMP_TAB * (int64_t)JUMP_TAB / BLOCK) gmax = JUMP_TAB * (int64_t)JUMP_TAB / BLOCK;
+  *grid = (int)std::max<int64_t>(1, std::min<int64_t>(gmax, tiles));
+  return MSIM_OK;
+}
+
+// Allocates and zeroes the accumulators a run needs and fills the pointers in p.
+template <class Traits, bool STREAM>
+int cohort_prepare(CohortParams<typename Traits::Consts> &p, const uint32_t stream_state[6], int *grid_out,
+                   size_t *smem_out) {
+  int rc;
+  size_t smem = cohort_kernel_smem<Traits>(p.geom, p.outputs);
+  int grid = 1;
+  if ((rc = cohort_grid<Traits, STREAM>(smem, p.n, &grid))) return rc;
+  if (!STREAM) stream_start(stream_state, p.first_person, grid, &p.st);
+  if ((rc = ensure(g.small, 16 * sizeof(double)))) return rc;
+  CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
+  SmallView sv = small_view();
+  p.counts = sv.counts;
+  p.n_rows = sv.n_rows;
+  p.error = sv.error;
+  if (p.outputs & OUT_REPORT) {
+    if ((rc = ensure(g.dense, sizeof(double) * p.geom.total))) return rc;
+    CK(cudaMemsetAsync(g.dense.p, 0, sizeof(double) * p.geom.total, g.stream));
+    p.dense = (double *)g.dense.p;
+  }
+  if (p.outputs & OUT_ROWLOG) {
+    int64_t tiles = (p.n + BLOCK - 1) / BLOCK;
+    if ((rc = ensure(g.tiles, sizeof(unsigned long long) * (size_t)std::max<int64_t>(tiles, 1)))) return rc;
+    CK(cudaMemsetAsync(g.tiles.p, 0, sizeof(unsigned long long) * (size_t)std::max<int64_t>(tiles, 1), g.stream));
+    p.tile_status = (unsigned long long *)g.tiles.p;
+    if ((rc = ensure(g.rowlog, sizeof(double) * 5 * (size_t)std::max<int64_t>(p.capacity, 1)))) return rc;
+    p.rowlog = (double *)g.rowlog.p;
+  }
+  *grid_out = grid;
+  *smem_out = smem;
+  return MSIM_OK;
+}
+
+template <class Traits, bool STREAM>
+int cohort_fire(CohortParams<typename Traits::Consts> &p, int grid, size_t smem) {
+  if (p.n > 0) {
+    auto kern = cohort_kernel<Traits, STREAM>;
+    if (p.outputs & OUT_ROWLOG) {
+      // the tile look-back needs every block of the grid resident: a cooperative launch enforces it
+      void *args[] = {(void *)&p};
+      CK(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(BLOCK), args, smem, g.stream));
+    } else {
+      kern<<<grid, BLOCK, smem, g.stream>>>(p);
+      CK(cudaGetLastError());
+    }
+    g.launches++;
+  }
+  g.last_geom = p.geom;
+  g.last_outputs = p.outputs;
+  g.last_capacity = p.capacity;
+  g.have_last = true;
+  return MSIM_OK;
+}
+
+int finish_run(int64_t *n_rows_out) {
+  CK(cudaStreamSynchronize(g.stream));
+  if (g.timing_pending) {
+    CK(cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1));
+    g.timing_pending = false;
+  }
+  double small[16];
+  CK(cudaMemcpy(small, g.small.p, sizeof small, cudaMemcpyDeviceToHost));
+  int err = *(int *)(small + 10);
+  unsigned long long nr = *(unsigned long long *)(small + 9);
+  g.last_n_rows = (int64_t)nr;
+  if (n_rows_out) *n_rows_out = (int64_t)nr;
+  if (err == MSIM_ERR_HEAP) return fail(MSIM_ERR_HEAP, "a person scheduled more pending events / rows than the device capacity");
+  if (err == MSIM_ERR_STREAM) return fail(MSIM_ERR_STREAM, "a person drew more uniforms than the sequential-stream plan allows");
+  if (err) return fail(err, "device-side error");
+  return MSIM_OK;
+}
+
+int64_t rowlog_capacity_guess(int64_t n, int max_rows, double mean_rows) {
+  if (n <= 65536) return n * max_rows + 1;
+  int64_t c = (int64_t)((double)n * mean_rows) + 65536;
+  return std::min<int64_t>(c, n * max_rows + 1);
+}
+
+int fetch_rowlog(const char *const *cols, msim_table *out) {
+  int64_t n = g.last_n_rows, cap = g.last_capacity;
+  out->nrow = n;
+  out->ncol = 5;
+  out->colnames = cols;
+  out->data = nullptr;
+  int rc;
+  if ((rc = pinned_alloc(sizeof(double) * 5 * (size_t)std::max<int64_t>(n, 1), &out->data))) return rc;
+  if (n > 0) {
+    CK(cudaMemcpy2DAsync(out->data, sizeof(double) * n, g.rowlog.p, sizeof(double) * cap, sizeof(double) * n, 5,
+                         cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+  }
+  return MSIM_OK;
+}
+
+int fetch_report(msim_report *out) {
+  std::vector<double> d(g.last_geom.total);
+  CK(cudaMemcpy(d.data(), g.dense.p, sizeof(double) * d.size(), cudaMemcpyDeviceToHost));
+  dense_to_report_impl(d.data(), g.last_geom, out);
+  return MSIM_OK;
+}
+
+// ---- person-r
+
+int person_enqueue(const msim_person_shard *sh, int64_t capacity_override) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  if (!sh || sh->n < 0 || sh->first_person < 0) return fail(MSIM_ERR_ARG, "bad shard");
+  if (!mrg_seed_ok(sh->seed)) return fail(MSIM_ERR_SEED, "illegal MRG32k3a seed");
+  CohortParams<person_r::Consts> p;
+  memset(&p, 0, sizeof p);
+  p.first_person = sh->first_person;
+  p.n = sh->n;
+  p.outputs = sh->outputs & 7u;
+  p.consts = person_r::make_consts();
+  p.geom = ages_geom(person_r::N_STATE, person_r::N_EVENT, sh->discount_rate);
+  p.capacity = capacity_override > 0 ? capacity_override : rowlog_capacity_guess(sh->n, person_r::MAX_ROWS, 1.25);
+  uint32_t state[6];
+  seed_to_u32(sh->seed, state);
+  g.last_simple_names = false;
+  int grid;
+  size_t smem;
+  if ((rc = cohort_prepare<PersonTraits, false>(p, state, &grid, &smem))) return rc;
+  CK(cudaEventRecord(g.ev0, g.stream));
+  if ((rc = cohort_fire<PersonTraits, false>(p, grid, smem))) return rc;
+  CK(cudaEventRecord(g.ev1, g.stream));
+  g.timing_pending = true;
+  return MSIM_OK;
+}
+
+int person_run(const msim_person_shard *sh) {
+  int rc;
+  if ((rc = person_enqueue(sh, 0))) return rc;
+  int64_t rows = 0;
+  if ((rc = finish_run(&rows))) return rc;
+  if ((sh->outputs & OUT_ROWLOG) && rows > g.last_capacity) {  // rare: rerun with the exact size
+    if ((rc = person_enqueue(sh, rows))) return rc;
+    if ((rc = finish_run(&rows))) return rc;
+  }
+  return MSIM_OK;
+}
+
+// ---- sequential-stream models
+
+template <class Traits>
+int sequential_run(int64_t n, const typename Traits::Consts &consts, int max_draws, unsigned outputs,
+                   const ReportGeom &geom, int max_rows, double mean_rows) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  if (n < 0) return fail(MSIM_ERR_ARG, "n < 0");
+  if (!g.rng.mt_seeded)
+    return fail(MSIM_ERR_STATE, "Mersenne-Twister state not set: call msim_mt_set_seed or msim_mt_set_state first");
+  if (max_draws > CHAIN_MAX_DRAWS) return fail(MSIM_ERR_ARG, "max_draws too large");
+  const int64_t mti0 = g.rng.mt[0];  // next word to hand out, 1..624 (624 = regenerate first)
+  const int64_t n_pos = (int64_t)max_draws * n;
+  const int64_t words_needed = mti0 + n_pos + max_draws + 1;
+  const int64_t n_batches = (words_needed + 623) / 624;  // including batch 0 = current state
+  const int64_t mt_end = n_batches * 624;
+  if ((rc = ensure(g.mt_words, sizeof(uint32_t) * (size_t)mt_end))) return rc;
+  CK(cudaMemcpyAsync(g.mt_words.p, &g.rng.mt[1], sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, g.stream));
+  CK(cudaEventRecord(g.ev0, g.stream));
+  if (n_batches > 1) {
+    mt_generate_kernel<<<1, 256, 0, g.stream>>>((uint32_t *)g.mt_words.p, (int)(n_batches - 1));
+    CK(cudaGetLastError());
+    g.launches++;
+  }
+  CohortParams<typename Traits::Consts> p;
+  memset(&p, 0, sizeof p);
+  g.last_simple_names = true;
+  if (n > 0) {
+    const int64_t n_chunks = (n_pos + CHAIN_CHUNK - 1) / CHAIN_CHUNK;
+    if ((rc = ensure(g.len, (size_t)n_pos))) return rc;
+    if ((rc = ensure(g.starts, sizeof(int64_t) * (size_t)n))) return rc;
+    if ((rc = ensure(g.chain_exit, (size_t)n_chunks * CHAIN_MAX_DRAWS))) return rc;
+    if ((rc = ensure(g.chain_count, sizeof(int) * (size_t)n_chunks * CHAIN_MAX_DRAWS))) return rc;
+    if ((rc = ensure(g.chain_entry, (size_t)n_chunks))) return rc;
+    if ((rc = ensure(g.chain_base, sizeof(int64_t) * (size_t)n_chunks))) return rc;
+    if ((rc = ensure(g.small, 16 * sizeof(double)))) return rc;
+    int lgrid = (int)std::min<int64_t>((n_pos + BLOCK - 1) / BLOCK, (int64_t)g.sm_count * 8);
+    seq_len_kernel<Traits><<<lgrid, BLOCK, 0, g.stream>>>((const uint32_t *)g.mt_words.p, mt_end, mti0, n_pos, consts,
+                                                         (unsigned char *)g.len.p);
+    CK(cudaGetLastError());
+    chain_chunk_kernel<<<(unsigned)n_chunks, 64, 0, g.stream>>>((const unsigned char *)g.len.p, n_pos, max_draws,
+                                                                (unsigned char *)g.chain_exit.p, (int *)g.chain_count.p);
+    CK(cudaGetLastError());
+    chain_scan_kernel<<<1, 256, 0, g.stream>>>((const unsigned char *)g.chain_exit.p, (const int *)g.chain_count.p,
+                                               n_chunks, n, (unsigned char *)g.chain_entry.p, (int64_t *)g.chain_base.p);
+    CK(cudaGetLastError());
+    g.launches += 3;
+  }
+  p.first_person = 0;
+  p.n = n;
+  p.outputs = outputs;
+  p.consts = consts;
+  p.geom = geom;
+  p.capacity = rowlog_capacity_guess(n, max_rows, mean_rows);
+  p.mt_words = (const uint32_t *)g.mt_words.p;
+  p.mt_end = mt_end;
+  p.starts = (const int64_t *)g.starts.p;
+  int grid;
+  size_t smem;
+  uint32_t unused_state[6] = {0, 0, 0, 0, 0, 0};
+  if ((rc = cohort_prepare<Traits, true>(p, unused_state, &grid, &smem))) return rc;  // zeroes `small`
+  if (n > 0) {
+    const int64_t n_chunks = (n_pos + CHAIN_CHUNK - 1) / CHAIN_CHUNK;
+    SmallView sv = small_view();
+    chain_emit_kernel<<<(unsigned)n_chunks, 64, 0, g.stream>>>(
+        (const unsigned char *)g.len.p, n_pos, mti0, (const unsigned char *)g.chain_entry.p,
+        (const int64_t *)g.chain_base.p, n, (int64_t *)g.starts.p, sv.end_word, sv.error);
+    CK(cudaGetLastError());
+    g.launches++;
+  }
+  if ((rc = cohort_fire<Traits, true>(p, grid, smem))) return rc;
+  CK(cudaEventRecord(g.ev1, g.stream));
+  g.timing_pending = true;
+  int64_t rows = 0;
+  if ((rc = finish_run(&rows))) return rc;
+  int64_t end_word = 0;
+  CK(cudaMemcpy(&end_word, small_view().end_word, sizeof end_word, cudaMemcpyDeviceToHost));
+  if ((outputs & OUT_ROWLOG) && rows > g.last_capacity) return fail(MSIM_ERR_CUDA, "row log capacity exceeded");
+  // leave R's generator where the reference would: after the last person's last draw
+  if (n > 0 && end_word > 0) {
+    int64_t batch = (end_word - 1) / 624;
+    int64_t mti = end_word - batch * 624;
+    CK(cudaMemcpy(&g.rng.mt[1], (const uint32_t *)g.mt_words.p + batch * 624, sizeof(uint32_t) * 624,
+                  cudaMemcpyDeviceToHost));
+    g.rng.mt[0] = (uint32_t)mti;
+  }
+  return MSIM_OK;
+}
+
+int seed_from_ints(const int32_t in[6], double seed[6]) {
+  for (int i = 0; i < 6; i++) {
+    if (in[i] < 0) return fail(MSIM_ERR_SEED, "negative seed component");
+    seed[i] = in[i];
+  }
+  if (!mrg_seed_ok(seed)) return fail(MSIM_ERR_SEED, "illegal MRG32k3a seed");
+  return MSIM_OK;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+
+extern "C" {
+
+const char *msim_last_error(void) { return g_err.c_str(); }
+const char *msim_version(void) { return "microsimulation_b200 0.1 (sm_100a)"; }
+
+int msim_init(int device) {
+  if (g.inited && device != g.device) return fail(MSIM_ERR_STATE, "already bound to another device");
+  g.device = device;
+  return ensure_init();
+}
+
+void msim_shutdown(void) {
+  if (!g.inited) return;
+  cudaStreamSynchronize(g.stream);
+  DevBuf *bufs[] = {&g.rowlog, &g.tiles, &g.dense, &g.small, &g.mt_words, &g.len, &g.starts, &g.chain_exit,
+                    &g.chain_count, &g.chain_entry, &g.chain_base, &g.calib_out, &g.calib_par, &g.uniforms};
+  for (DevBuf *b : bufs) {
+    if (b->p) cudaFree(b->p);
+    b->p = nullptr;
+    b->bytes = 0;
+  }
+  cudaFree(g.d_lo);
+  cudaFree(g.d_hi);
+  if (g.pin_cache) cudaFreeHost(g.pin_cache);
+  g.pin_cache = nullptr;
+  g.pin_cache_bytes = 0;
+  cudaEventDestroy(g.ev0);
+  cudaEventDestroy(g.ev1);
+  cudaStreamDestroy(g.stream);
+  g.inited = false;
+  g.have_last = false;
+}
+
+int64_t msim_launch_count(void) { return g.launches; }
+
+void msim_table_free(msim_table *t) {
+  if (!t) return;
+  host_free(t->data);
+  t->data = nullptr;
+  t->nrow = 0;
+}
+void msim_report_free(msim_report *r) {
+  if (!r) return;
+  msim_table_free(&r->pt);
+  msim_table_free(&r->ut);
+  msim_table_free(&r->events);
+  msim_table_free(&r->prev);
+  msim_table_free(&r->costs);
+  msim_table_free(&r->indiv);
+}
+
+// ---- RNG state
+
+void msim_r_create_current_stream(void) {
+  g.rng.default_stream = g.rng.new_stream();
+  g.rng.have_default = true;
+}
+void msim_r_remove_current_stream(void) { g.rng.have_default = false; }
+
+int msim_r_set_user_random_seed(const double seed[6]) {
+  if (!g.rng.have_default) return fail(MSIM_ERR_STATE, "no current stream: call msim_r_create_current_stream");
+  if (!mrg_seed_ok(seed)) return fail(MSIM_ERR_SEED, "illegal MRG32k3a seed (the reference ignores it silently)");
+  uint32_t s[6];
+  seed_to_u32(seed, s);
+  memcpy(g.rng.next_seed, s, sizeof s);  // Rng::SetPackageSeed
+  g.rng.default_stream.set_all(s);       // default_stream->SetSeed
+  return MSIM_OK;
+}
+int msim_r_get_user_random_seed(double seed[6]) {
+  if (!g.rng.have_default) return fail(MSIM_ERR_STATE, "no current stream");
+  for (int i = 0; i < 6; i++) seed[i] = (double)g.rng.default_stream.Cg.s[i];
+  return MSIM_OK;
+}
+int msim_r_next_rng_substream(void) {
+  if (!g.rng.have_default) return fail(MSIM_ERR_STATE, "no current stream");
+  g.rng.default_stream.reset_next_substream();
+  return MSIM_OK;
+}
+int msim_r_rng_advance_substream(double seed[6], const int *n) {
+  HostStream r = g.rng.new_stream();  // `RngStream r;` consumes a package stream (microsimulation.cc:66)
+  if (mrg_seed_ok(seed)) {            // SetSeed keeps the constructed state when the seed is illegal
+    uint32_t s[6];
+    seed_to_u32(seed, s);
+    r.set_all(s);
+  }
+  r.advance_substream(0, *n);
+  for (int i = 0; i < 6; i++) seed[i] = (double)r.Cg.s[i];
+  return MSIM_OK;
+}
+
+int msim_mt_set_state(const uint32_t state[625]) {
+  if (state[0] < 1 || state[0] > 624) return fail(MSIM_ERR_ARG, "MT position must be in 1..624");
+  memcpy(g.rng.mt, state, sizeof g.rng.mt);
+  g.rng.mt_seeded = true;
+  return MSIM_OK;
+}
+int msim_mt_get_state(uint32_t state[625]) {
+  if (!g.rng.mt_seeded) return fail(MSIM_ERR_STATE, "Mersenne-Twister state not set");
+  memcpy(state, g.rng.mt, sizeof g.rng.mt);
+  return MSIM_OK;
+}
+int msim_mt_set_seed(uint32_t seed) {
+  g.rng.mt_set_seed(seed);
+  return MSIM_OK;
+}
+
+// ---- model entry points
+
+int msim_callPersonSimulation(const int32_t inseed[6], int32_t n, msim_table *out) {
+  int rc;
+  if (!out || n < 0) return fail(MSIM_ERR_ARG, "bad arguments");
+  msim_person_shard sh;
+  memset(&sh, 0, sizeof sh);
+  if ((rc = seed_from_ints(inseed, sh.seed))) return rc;
+  // RngStream::SetPackageSeed(seed); rng["NH"] = new Rng(); rng["S"] = new Rng()  (person-r.cc:204-207)
+  seed_to_u32(sh.seed, g.rng.next_seed);
+  (void)g.rng.new_stream();
+  (void)g.rng.new_stream();
+  sh.first_person = 0;
+  sh.n = n;
+  sh.outputs = MSIM_OUT_ROWLOG;
+  if ((rc = person_run(&sh))) return rc;
+  return fetch_rowlog(ROWLOG_COLS_PERSON, out);
+}
+
+int msim_callSimplePerson(int32_t n, msim_table *out) {
+  int rc;
+  if (!out || n < 0) return fail(MSIM_ERR_ARG, "bad arguments");
+  simple_example::Consts c = {0};
+  ReportGeom geom = ages_geom(simple_example::N_STATE, simple_example::N_EVENT, 0.0);
+  if ((rc = sequential_run<SimpleTraits>(n, c, simple_example::MAX_DRAWS, OUT_ROWLOG, geom, simple_example::MAX_ROWS, 1.6)))
+    return rc;
+  return fetch_rowlog(ROWLOG_COLS_SIMPLE, out);
+}
+
+int msim_callSimplePerson2(int32_t n, msim_report *out) {
+  int rc;
+  if (!out || n < 0) return fail(MSIM_ERR_ARG, "bad arguments");
+  simple_example::Consts c = {0};
+  ReportGeom geom = ages_geom(simple_example::N_STATE, simple_example::N_EVENT, 0.0);
+  if ((rc = sequential_run<SimpleTraits>(n, c, simple_example::MAX_DRAWS, OUT_REPORT, geom, simple_example::MAX_ROWS, 1.6)))
+    return rc;
+  return fetch_report(out);
+}
+
+int msim_callIllnessDeath(int32_t n, double cure, double zsd, msim_report *out) {
+  int rc;
+  if (!out || n < 0 || !(zsd >= 0)) return fail(MSIM_ERR_ARG, "bad arguments");
+  illness_death::Consts c = illness_consts(cure, zsd);
+  ReportGeom geom = ages_geom(illness_death::N_STATE, illness_death::N_EVENT, 0.0);
+  int max_draws = (zsd == 0.0) ? 5 : 7;  // rnorm(0, 0) draws nothing
+  if ((rc = sequential_run<IllnessDeathTraits>(n, c, max_draws, OUT_REPORT, geom, illness_death::MAX_ROWS, 1.3))) return rc;
+  return fetch_report(out);
+}
+
+int msim_calibration_sweep(const double seed[6], int64_t first_person, int64_t n, int32_t n_sets, const double *runpar,
+                           msim_calibration *out) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  if (!out || !runpar || n < 0 || n_sets < 1 || n_sets > 65535 || first_person < 0) return fail(MSIM_ERR_ARG, "bad arguments");
+  if (!mrg_seed_ok(seed)) return fail(MSIM_ERR_SEED, "illegal MRG32k3a seed");
+  if ((rc = ensure(g.calib_par, sizeof(double) * 6 * n_sets))) return rc;
+  if ((rc = ensure(g.calib_out, sizeof(double) * 48 * n_sets))) return rc;
+  if ((rc = ensure(g.small, 16 * sizeof(double)))) return rc;
+  CK(cudaMemcpyAsync(g.calib_par.p, runpar, sizeof(double) * 6 * n_sets, cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemsetAsync(g.calib_out.p, 0, sizeof(double) * 48 * n_sets, g.stream));
+  CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
+  CalibParams p;
+  memset(&p, 0, sizeof p);
+  int64_t tiles = (n + BLOCK - 1) / BLOCK;
+  // enough blocks per set to fill the GPU even for few sets, no more than the work
+  int64_t want = std::max<int64_t>(1, ((int64_t)g.sm_count * 8 + n_sets - 1) / n_sets);
+  int grid_x = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, tiles), 2048));
+  uint32_t state[6];
+  seed_to_u32(seed, state);
+  stream_start(state, first_person, grid_x, &p.st);
+  p.n = n;
+  p.n_sets = n_sets;
+  p.runpar = (const double *)g.calib_par.p;
+  p.out = (double *)g.calib_out.p;
+  p.error = small_view().error;
+  CK(cudaEventRecord(g.ev0, g.stream));
+  if (n > 0) {
+    calib_kernel<<<dim3(grid_x, n_sets), BLOCK, 0, g.stream>>>(p);
+    CK(cudaGetLastError());
+    g.launches++;
+  }
+  CK(cudaEventRecord(g.ev1, g.stream));
+  g.timing_pending = true;
+  if ((rc = finish_run(nullptr))) return rc;
+  std::vector<double> h(48 * (size_t)n_sets);
+  CK(cudaMemcpy(h.data(), g.calib_out.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+  for (int s = 0; s < n_sets; s++) {
+    msim_calibration *o = out + s;
+    memset(o, 0, sizeof *o);
+    const double *r = &h[48 * (size_t)s];
+    for (int st = 0; st < 4; st++) {
+      double tot = 0;
+      for (int k = 0; k < 10; k++) {
+        o->occupancy[st * 10 + k] = r[st * 10 + k];
+        tot += r[st * 10 + k];
+      }
+      o->present[st] = tot > 0;  // report[stage] exists once any Count saw that stage (calibperson-r.cc:166-169)
+    }
+    o->n_time_at_risk = (int32_t)r[44];
+    for (int k = 0; k < o->n_time_at_risk; k++) o->time_at_risk[k] = r[40 + k];
+  }
+  return MSIM_OK;
+}
+
+int msim_callCalibrationSimulation(int32_t n, const double runpar[6], msim_calibration *out) {
+  if (!out || !runpar || n < 0) return fail(MSIM_ERR_ARG, "bad arguments");
+  // rng = new Rng(): takes the package seed, which then moves on one stream (calibperson-r.cc:182)
+  HostStream s = g.rng.new_stream();
+  double seed[6];
+  for (int i = 0; i < 6; i++) seed[i] = (double)s.Cg.s[i];
+  return msim_calibration_sweep(seed, 0, n, 1, runpar, out);
+}
+
+// ---- sharded / device-resident forms
+
+int msim_person_enqueue(const msim_person_shard *shard, msim_person_device_result *res) {
+  int rc;
+  if ((rc = person_enqueue(shard, 0))) return rc;
+  if (res) {
+    memset(res, 0, sizeof *res);
+    res->n_rows = -1;  // known after msim_sync()
+    res->capacity = g.last_capacity;
+    res->d_rowlog = (shard->outputs & OUT_ROWLOG) ? (const double *)g.rowlog.p : nullptr;
+    res->d_dense = (shard->outputs & OUT_REPORT) ? (const double *)g.dense.p : nullptr;
+    res->d_counts = (const double *)g.small.p;
+    res->dims.n_state = g.last_geom.n_state;
+    res->dims.n_event = g.last_geom.n_event;
+    res->dims.n_bin = g.last_geom.n_bin;
+    res->dims.n_doubles = g.last_geom.total;
+  }
+  return MSIM_OK;
+}
+
+int msim_sync(void) {
+  if (!g.inited) return fail(MSIM_ERR_STATE, "not initialised");
+  return finish_run(nullptr);
+}
+
+int msim_person_run_device(const msim_person_shard *shard, msim_person_device_result *res) {
+  int rc;
+  if ((rc = person_run(shard))) return rc;
+  if (res) {
+    memset(res, 0, sizeof *res);
+    res->n_rows = g.last_n_rows;
+    res->capacity = g.last_capacity;
+    res->d_rowlog = (shard->outputs & OUT_ROWLOG) ? (const double *)g.rowlog.p : nullptr;
+    res->d_dense = (shard->outputs & OUT_REPORT) ? (const double *)g.dense.p : nullptr;
+    res->d_counts = (const double *)g.small.p;
+    res->dims.n_state = g.last_geom.n_state;
+    res->dims.n_event = g.last_geom.n_event;
+    res->dims.n_bin = g.last_geom.n_bin;
+    res->dims.n_doubles = g.last_geom.total;
+  }
+  return MSIM_OK;
+}
+
+int msim_last_kernel_ms(float *ms) {
+  if (!g.have_last && g.last_ms == 0.f) return fail(MSIM_ERR_STATE, "no run yet");
+  *ms = g.last_ms;
+  return MSIM_OK;
+}
+
+int msim_person_fetch_rowlog(msim_table *out) {
+  if (!g.have_last || !(g.last_outputs & OUT_ROWLOG)) return fail(MSIM_ERR_STATE, "last run produced no row log");
+  if (g.last_n_rows > g.last_capacity) return fail(MSIM_ERR_STATE, "row log overflowed its capacity; use msim_person_run_device");
+  return fetch_rowlog(g.last_simple_names ? ROWLOG_COLS_SIMPLE : ROWLOG_COLS_PERSON, out);
+}
+
+int msim_person_fetch_counts(double counts[9]) {
+  if (!g.have_last) return fail(MSIM_ERR_STATE, "no run yet");
+  CK(cudaMemcpy(counts, g.small.p, sizeof(double) * 9, cudaMemcpyDeviceToHost));
+  return MSIM_OK;
+}
+
+int msim_dense_to_report(const double *host_dense, const msim_dense_dims *dims, double discount_rate, msim_report *out) {
+  if (!host_dense || !dims || !out) return fail(MSIM_ERR_ARG, "bad arguments");
+  ReportGeom G = geom_from_dims(dims, discount_rate);
+  if (G.total != dims->n_doubles) return fail(MSIM_ERR_ARG, "dims.n_doubles does not match the geometry");
+  dense_to_report_impl(host_dense, G, out);
+  return MSIM_OK;
+}
+
+int msim_dense_device_ptr(double **d_ptr, int64_t *n_doubles) {
+  if (!g.have_last || !(g.last_outputs & OUT_REPORT)) return fail(MSIM_ERR_STATE, "last run produced no report");
+  *d_ptr = (double *)g.dense.p;
+  *n_doubles = g.last_geom.total;
+  return MSIM_OK;
+}
+
+int msim_dense_fetch(double *host_dense, int64_t n_doubles) {
+  if (!g.have_last || !(g.last_outputs & OUT_REPORT)) return fail(MSIM_ERR_STATE, "last run produced no report");
+  if (n_doubles != g.last_geom.total) return fail(MSIM_ERR_ARG, "size mismatch");
+  CK(cudaMemcpy(host_dense, g.dense.p, sizeof(double) * n_doubles, cudaMemcpyDeviceToHost));
+  return MSIM_OK;
+}
+
+// ---- parity hooks
+
+int msim_rng_uniforms(const double seed[6], int64_t first_substream, int64_t n_substreams, int32_t draws,
+                      double *uniforms_host) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  if (!uniforms_host || n_substreams < 0 || draws < 1 || first_substream < 0) return fail(MSIM_ERR_ARG, "bad arguments");
+  if (!mrg_seed_ok(seed)) return fail(MSIM_ERR_SEED, "illegal MRG32k3a seed");
+  if (n_substreams == 0) return MSIM_OK;
+  size_t bytes = sizeof(double) * (size_t)n_substreams * draws;
+  if ((rc = ensure(g.uniforms, bytes))) return rc;
+  UniformsParams p;
+  int grid = (int)std::min<int64_t>((n_substreams + BLOCK - 1) / BLOCK, (int64_t)g.sm_count * 8);
+  uint32_t state[6];
+  seed_to_u32(seed, state);
+  // substream j of this hook = j jumps from `seed`; stream_start applies first+1 jumps
+  Mrg32k3a b;
+  memcpy(b.s, state, sizeof b.s);
+  b.jump(mrg_jump_pow(mrg_substream_jump(), (uint64_t)first_substream));
+  memcpy(p.st.base, b.s, sizeof b.s);
+  p.st.lo = g.d_lo;
+  p.st.hi = g.d_hi;
+  p.st.stride = mrg_jump_pow(mrg_substream_jump(), (uint64_t)grid * BLOCK);
+  p.n_substreams = n_substreams;
+  p.draws = draws;
+  p.out = (double *)g.uniforms.p;
+  rng_uniforms_kernel<<<grid, BLOCK, 0, g.stream>>>(p);
+  CK(cudaGetLastError());
+  g.launches++;
+  CK(cudaMemcpyAsync(uniforms_host, g.uniforms.p, bytes, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return MSIM_OK;
+}
+
+int msim_mt_uniforms(int64_t n, double *uniforms_host) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  if (!uniforms_host || n < 0) return fail(MSIM_ERR_ARG, "bad arguments");
+  if (!g.rng.mt_seeded) return fail(MSIM_ERR_STATE, "Mersenne-Twister state not set");
+  if (n == 0) return MSIM_OK;
+  const int64_t mti0 = g.rng.mt[0];
+  const int64_t n_batches = (mti0 + n + 623) / 624;
+  if ((rc = ensure(g.mt_words, sizeof(uint32_t) * (size_t)n_batches * 624))) return rc;
+  if ((rc = ensure(g.uniforms, sizeof(double) * (size_t)n))) return rc;
+  CK(cudaMemcpyAsync(g.mt_words.p, &g.rng.mt[1], sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, g.stream));
+  if (n_batches > 1) {
+    mt_generate_kernel<<<1, 256, 0, g.stream>>>((uint32_t *)g.mt_words.p, (int)(n_batches - 1));
+    CK(cudaGetLastError());
+    g.launches++;
+  }
+  int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)g.sm_count * 8);
+  mt_uniforms_kernel<<<grid, 256, 0, g.stream>>>((const uint32_t *)g.mt_words.p, mti0, n, (double *)g.uniforms.p);
+  CK(cudaGetLastError());
+  g.launches++;
+  CK(cudaMemcpyAsync(uniforms_host, g.uniforms.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return MSIM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,197 @@
+// Device event engine: one simulated process (person) per thread.
+//
+// Mirrors, per thread, the reference's static single-threaded simulator:
+//   ssim::Sim main loop, schedule, clear      src/ssim.cc:92-127, 148-235
+//   Action ordering (time, then priority)     src/ssim.cc:51-63
+//   heap<Action>::insert / pop_first          inst/include/heap.h:75-117
+//   Sim::ignore_event (lazy cancellation)     src/ssim.cc:131-142
+//   Sim::stop_process / stop_simulation       src/ssim.cc:241-253
+// and the OMNeT++-style plugin surface models are written against:
+//   cMessage{kind, priority}, cProcess::scheduleAt / previous / cancel*,
+//   RemoveKind / CancelEvents, now()          inst/include/microsimulation.h:218-447
+//
+// The pending-event set is a fixed-capacity binary heap held in the thread's
+// registers / local memory (CAP entries); it is the SAME algorithm as heap.h —
+// strict `<` on sift-up, right child only if strictly smaller than the left —
+// so ties in (time, priority) resolve exactly as on the CPU, including
+// cancelled entries, which stay in the heap as A_Ignore and are skipped at pop
+// time without advancing the clock.
+//
+// Differences by design: there is one process per simulation (the built models
+// never call cProcess::send), cMessage names (std::string) are not available on
+// the device — kinds only — and a full heap is an error code, not UB.
+#pragma once
+#include <stdint.h>
+
+#include "mrg32k3a.cuh"
+#include "rmath.cuh"
+
+namespace msim {
+
+enum ActionType : int { A_Event = 0, A_Init = 1, A_Stop = 2, A_Ignore = 3 };
+
+// meta word: bits 0-15 kind (int16), bits 16-29 priority + 8192, bits 30-31 type
+MSIM_DEV int pack_meta(int type, int kind, int priority) {
+  return (int)(((uint32_t)kind & 0xffffu) | ((((uint32_t)(priority + 8192)) & 0x3fffu) << 16) | ((uint32_t)type << 30));
+}
+MSIM_DEV int meta_kind(int m) { return (int)(int16_t)((uint32_t)m & 0xffffu); }
+MSIM_DEV int meta_prio(int m) { return (int)(((uint32_t)m >> 16) & 0x3fffu) - 8192; }
+MSIM_DEV int meta_type(int m) { return (int)((uint32_t)m >> 30); }
+
+template <int CAP>
+struct EventHeap {
+  double t[CAP];
+  int meta[CAP];
+  int n;
+
+  MSIM_DEV bool before(double ta, int ma, double tb, int mb) const {
+    return ta < tb || (ta == tb && meta_prio(ma) < meta_prio(mb));  // ssim.cc:60-62
+  }
+
+  // heap.h:75-88
+  MSIM_DEV bool insert(double time, int m) {
+    if (n >= CAP) return false;
+    int k = n++;
+    while (k > 0) {
+      int up = (k - 1) >> 1;
+      double tu = t[up];
+      int mu = meta[up];
+      if (!before(time, m, tu, mu)) break;
+      t[k] = tu;
+      meta[k] = mu;
+      k = up;
+    }
+    t[k] = time;
+    meta[k] = m;
+    return true;
+  }
+
+  // heap.h:90-117 (caller guarantees n > 0)
+  MSIM_DEV void pop_first(double &time, int &m) {
+    time = t[0];
+    m = meta[0];
+    int last = --n;  // index of the element that moves to the root
+    if (last == 0) return;
+    double tx = t[last];
+    int mx = meta[last];
+    last--;  // new last valid index
+    int k = 0;
+    for (;;) {
+      int c = 2 * k + 1;
+      if (c > last) break;
+      double tc = t[c];
+      int mc = meta[c];
+      if (c + 1 <= last) {
+        double tr = t[c + 1];
+        int mr = meta[c + 1];
+        if (before(tr, mr, tc, mc)) {
+          c = c + 1;
+          tc = tr;
+          mc = mr;
+        }
+      }
+      if (!before(tc, mc, tx, mx)) break;
+      t[k] = tc;
+      meta[k] = mc;
+      k = c;
+    }
+    t[k] = tx;
+    meta[k] = mx;
+  }
+};
+
+// CRTP base: `struct Person : cProcess<Person, Src, 4> { void init(); void
+// handleMessage(int kind); }`.  Handler bodies read like the reference's.
+template <class Derived, class Src, int CAP>
+struct cProcess {
+  EventHeap<CAP> actions;
+  double clock_;
+  double startTime, previousEventTime;
+  bool running_, terminated_;
+  int error_;  // MSIM_ERR_HEAP if a schedule did not fit
+  RMath<Src> R;
+
+  MSIM_DEV explicit cProcess(Src *src) : R(src) {
+    actions.n = 0;
+    clock_ = 0.0;
+    startTime = previousEventTime = 0.0;
+    running_ = false;
+    terminated_ = false;
+    error_ = 0;
+  }
+
+  MSIM_DEV double now() const { return clock_; }  // microsimulation.cc:10-12
+  MSIM_DEV double simTime() const { return clock_; }
+  MSIM_DEV double previous() const { return previousEventTime; }
+
+  // cProcess::scheduleAt (microsimulation.h:342-360) + Sim::self_signal_event
+  // (ssim.cc:269-271) + SimImpl::schedule (ssim.cc:92-98): the stored time is
+  // clock + (t - clock), two roundings, as in the reference.
+  MSIM_DEV void scheduleAt(double t, int kind, int priority = 0) {
+    double delay = t - clock_;
+    if (!actions.insert(clock_ + delay, pack_meta(A_Event, kind, priority))) error_ = -4;
+  }
+
+  // Cancel(pred) -> Sim::ignore_event: mark matching A_Event entries A_Ignore
+  template <class Pred>
+  MSIM_DEV void Cancel(Pred pred) {
+    for (int i = 0; i < actions.n; i++) {
+      int m = actions.meta[i];
+      if (meta_type(m) == A_Event && pred(meta_kind(m))) actions.meta[i] = (int)(((uint32_t)m & 0x3fffffffu) | ((uint32_t)A_Ignore << 30));
+    }
+  }
+  MSIM_DEV void RemoveKind(int kind) {
+    Cancel([kind](int k) { return k == kind; });
+  }
+  MSIM_DEV void CancelKind(int kind) { RemoveKind(kind); }
+  MSIM_DEV void cancel_kind(int kind) { RemoveKind(kind); }  // single process: same set
+  MSIM_DEV void CancelEvents() {
+    Cancel([](int) { return true; });
+  }
+  MSIM_DEV void cancel_events() { CancelEvents(); }
+
+  // Sim::stop_process(): A_Stop at the current time; the process is marked
+  // terminated when it is popped and later events are drained (ssim.cc:189-213)
+  MSIM_DEV void stop_process() {
+    if (!actions.insert(clock_, pack_meta(A_Stop, -1, 0))) error_ = -4;
+  }
+  // Sim::stop_simulation(): the loop exits before the next pop (ssim.cc:251)
+  MSIM_DEV void stop_simulation() { running_ = false; }
+
+  MSIM_DEV void stop() {}  // Process::stop hook; models may shadow it
+
+  // create_process + run_simulation + clear for this one process.
+  // create_process pushes A_Init at t = 0 into an empty heap, so the first
+  // pop is always that action: initialize() runs first (microsimulation.h:430).
+  MSIM_DEV void run() {
+    Derived *self = static_cast<Derived *>(this);
+    running_ = true;
+    self->init();
+    previousEventTime = startTime;
+    while (running_ && actions.n > 0) {
+      double t;
+      int m;
+      actions.pop_first(t, m);
+      int type = meta_type(m);
+      if (type == A_Ignore) continue;  // clock untouched (ssim.cc:171-175)
+      clock_ = t;
+      if (terminated_) continue;  // drained (ssim.cc:189-192)
+      if (type == A_Event) {
+        self->handleMessage(meta_kind(m));
+        previousEventTime = clock_;  // microsimulation.h:441
+      } else {                       // A_Stop
+        self->stop();
+        terminated_ = true;
+      }
+    }
+    running_ = false;
+  }
+};
+
+// uniform source: the person's MRG32k3a substream
+struct MrgSource {
+  Mrg32k3a g;
+  MSIM_DEV double unif_rand() { return g.u01(); }
+};
+
+}  // namespace msim

@@ -1,0 +1,307 @@
+// The reference's models, written against the device plugin surface
+// (engine.cuh) so that init()/handleMessage() bodies keep the reference's
+// statement order — the order of random draws is part of the contract.
+//
+//   Person        FHCRC prostate natural history   src/person-r.cc:36-190
+//   CalibPerson   calibration example              src/calibperson-r.cc:35-171
+//   IllnessDeath  illnessDeath::SimplePerson       src/illness-death.cpp:6-71
+//   SimplePerson  row-log / EventReport variants   src/simple-example.cc:11-70,
+//                                                  src/simple-example2.cc:12-60
+//
+// Each model is a template over `Env`, which supplies the uniform source
+// (`Env::Src`) and the output sinks the reference writes to from inside
+// handleMessage: row(...) for the life-history row log, report(...) for
+// EventReport::add, count(...) for per-kind tallies.  Constants that the
+// reference computes with libm from literals (exp(2.3525), pow(hr, 1/shape),
+// b_weibull via gammafn) are evaluated ONCE on the host with the host's libm
+// and passed in, so they are bit-identical to the CPU run.
+#pragma once
+#include "engine.cuh"
+
+namespace msim {
+
+// ------------------------------------------------------------------ person-r
+namespace person_r {
+
+enum gleason_t { nogleason, gleasonLt7, gleason7, gleasonGt7 };
+enum stage_t { Healthy, Localised, DxLocalised, LocallyAdvanced, DxLocallyAdvanced, Metastatic, DxMetastatic, Death };
+enum event_t {
+  toDeath, toPCDeath, toLocalised, toDxLocalised, toDxLocallyAdvanced, toLocallyAdvanced, toMetastatic, toDxMetastatic
+};
+constexpr int N_STATE = 8, N_EVENT = 8, MAX_ROWS = 5, HEAP_CAP = 4;
+
+struct Consts {
+  double onset_inv_shape;  // 1/exp(2.3525)
+  double onset_scale;      // 64.0218
+  // dwell-time Weibulls of toLocalised / toLocallyAdvanced / toMetastatic:
+  // inv_shape[k] = 1/shape_k; scale[k][gleason] = scale_k*pow(progressionHR(gleason)*dxHR(stage_k), 1/shape_k)
+  double inv_shape[3];
+  double scale[3][4];
+  double pDx[3];
+};
+
+// host side: person-r.cc:80-93 (dxHR, progressionHR) and microsimulation.cc:6-8
+inline Consts make_consts() {
+  Consts c;
+  c.onset_inv_shape = 1. / exp(2.3525);
+  c.onset_scale = 64.0218;
+  const double shape[3] = {exp(1.0353), exp(1.4404), exp(1.4404)};
+  const double scale[3] = {19.8617, 16.3863, 1.4242};
+  const double dxHR[3] = {1.1308, 0.5900, 1.3147};  // Localised, LocallyAdvanced, Metastatic
+  const double prog[4] = {1.4027 * 1.3874 /* nogleason falls to the last branch */, 1, 1.3874, 1.4027 * 1.3874};
+  for (int k = 0; k < 3; k++) {
+    c.inv_shape[k] = 1. / shape[k];
+    for (int g = 0; g < 4; g++) {
+      // the reference evaluates this pow at run time (microsimulation.cc:7); keep
+      // the compiler from folding it with different rounding
+      volatile double hr = prog[g] * dxHR[k], e = 1.0 / shape[k];
+      c.scale[k][g] = scale[k] * pow(hr, e);
+    }
+  }
+  c.pDx[0] = 1.1308 / (2.1308);
+  c.pDx[1] = 0.5900 / (1.0 + 0.5900);
+  c.pDx[2] = 1.3147 / (1.0 + 1.3147);
+  return c;
+}
+
+template <class Env>
+struct Person : cProcess<Person<Env>, typename Env::Src, HEAP_CAP> {
+  typedef cProcess<Person<Env>, typename Env::Src, HEAP_CAP> Base;
+  using Base::now;
+  using Base::previousEventTime;
+  using Base::R;
+  using Base::scheduleAt;
+  using Base::stop_simulation;
+
+  int gleason, stage;
+  bool dx;
+  int64_t id;
+  Env &env;
+  const Consts &K;
+
+  MSIM_DEV Person(Env &e, const Consts &k, int64_t i)
+      : Base(&e.src), gleason(nogleason), stage(Healthy), dx(false), id(i), env(e), K(k) {}
+
+  MSIM_DEV void init() {  // person-r.cc:98-103
+    if (R.runif(0.0, 1.0) < 0.2241) scheduleAt(K.onset_scale * pow(-log(R.unif_rand()), K.onset_inv_shape), toLocalised);
+    scheduleAt(R.rexp(80.0), toDeath);
+  }
+
+  // dwell = now() + rweibullHR(shape_k, scale_k, progressionHR(gleason)*dxHR(stage))
+  MSIM_DEV double dwell(int k) { return now() + K.scale[k][gleason] * pow(-log(R.unif_rand()), K.inv_shape[k]); }
+
+  MSIM_DEV void handleMessage(int kind) {  // person-r.cc:108-190
+    env.row((double)id, previousEventTime, now(), stage, kind);  // logged BEFORE the state change (:112-116)
+    env.report(stage, kind, previousEventTime, now());  // EventReport attachment (BASELINE config 4); no-op unless requested
+
+    if (kind == toDeath) {
+      stop_simulation();
+    } else if (kind == toPCDeath) {
+      stop_simulation();
+    } else if (kind == toLocalised) {
+      stage = Localised;
+      gleason = (R.runif(0.0, 1.0) < 0.6812) ? gleasonLt7 : ((R.runif(0.0, 1.0) < 0.5016) ? gleason7 : gleasonGt7);
+      double dwellTime = dwell(0);
+      if (R.runif(0.0, 1.0) < K.pDx[0]) scheduleAt(dwellTime, toDxLocalised);
+      else scheduleAt(dwellTime, toLocallyAdvanced);
+    } else if (kind == toLocallyAdvanced) {
+      stage = LocallyAdvanced;
+      double dwellTime = dwell(1);
+      if (R.runif(0.0, 1.0) < K.pDx[1]) scheduleAt(dwellTime, toDxLocallyAdvanced);
+      else scheduleAt(dwellTime, toMetastatic);
+    } else if (kind == toMetastatic) {
+      stage = Metastatic;
+      double dwellTime = dwell(2);
+      if (R.runif(0.0, 1.0) < K.pDx[2]) scheduleAt(dwellTime, toDxMetastatic);
+      else scheduleAt(dwellTime, toPCDeath);
+    } else if (kind == toDxLocalised || kind == toDxLocallyAdvanced || kind == toDxMetastatic) {
+      dx = true;
+    }
+  }
+};
+
+}  // namespace person_r
+
+// --------------------------------------------------------------- calibperson
+namespace calib {
+
+enum stage_t { DiseaseFree, Precursor, PreClinical, Clinical, Death };
+enum event_t { toPrecursor, toPreClinical, toClinical, toDeath, Count };
+constexpr int HEAP_CAP = 16;  // ten Count events + toPrecursor + toDeath (+ successors)
+
+struct Par {
+  double Lam1, sigm1, p2, lam2, mu3, tau3;
+};
+
+template <class Env>
+struct CalibPerson : cProcess<CalibPerson<Env>, typename Env::Src, HEAP_CAP> {
+  typedef cProcess<CalibPerson<Env>, typename Env::Src, HEAP_CAP> Base;
+  using Base::now;
+  using Base::R;
+  using Base::scheduleAt;
+  using Base::stop_simulation;
+
+  int stage;
+  bool diseasepot;
+  double clinTime;
+  Env &env;
+  const Par &P;
+
+  MSIM_DEV CalibPerson(Env &e, const Par &p) : Base(&e.src), stage(DiseaseFree), diseasepot(false), clinTime(1000), env(e), P(p) {}
+
+  MSIM_DEV void init() {  // calibperson-r.cc:95-110
+    if (R.runif(0, 1) < P.p2) diseasepot = true;
+    else diseasepot = false;
+    clinTime = 1000;
+    stage = DiseaseFree;
+    double lam1 = exp(R.rnorm(P.Lam1, P.sigm1));
+    scheduleAt(R.rexp(lam1), toPrecursor);
+    double x = R.runif(0, 1);
+    scheduleAt((65 - 15 * log(-log(x))), toDeath);  // Gumbel
+    for (int i = 10; i < 110; i = i + 10) scheduleAt(i, Count);
+  }
+
+  MSIM_DEV void handleMessage(int kind) {  // calibperson-r.cc:115-171
+    if (kind == toDeath) {
+      stage = Death;
+      clinTime = fmin(clinTime, now());
+      const double ctime[4] = {20, 40, 60, 80};
+      for (int i = 0; i < 4; i++) {
+        env.time_at_risk(i, fmin(ctime[i], clinTime));
+        if (clinTime < ctime[i]) break;
+      }
+      stop_simulation();
+    } else if (kind == toPrecursor) {
+      stage = Precursor;
+      if (diseasepot) {
+        double dwellTime = now() + R.rexp(P.lam2);
+        scheduleAt(dwellTime, toPreClinical);
+      }
+    } else if (kind == toPreClinical) {
+      stage = PreClinical;
+      double dwellTime = now() + exp(R.rnorm(P.mu3, P.tau3 * P.mu3));
+      scheduleAt(dwellTime, toClinical);
+    } else if (kind == toClinical) {
+      stage = Clinical;
+      clinTime = now();
+    } else if (kind == Count) {
+      int cind = (int)(now() / 10 - 1);
+      if (cind > 9) cind = 9;
+      env.occupancy(stage, cind);
+    }
+  }
+};
+
+}  // namespace calib
+
+// ------------------------------------------------------------- illness-death
+namespace illness_death {
+
+enum state_t { Healthy, Cancer };
+enum event_t { toOtherDeath, toCancer, toCancerDeath };
+constexpr int N_STATE = 2, N_EVENT = 3, HEAP_CAP = 4, MAX_ROWS = 3, MAX_DRAWS = 7;
+
+struct Consts {
+  double cure, zsd;
+  double b_other;         // b_weibull(80, 4)          illness-death.cpp:17-19, :37
+  double b_cancer_mean;   // 80 / gammafn(1 + 1/3)     the rr-independent factor of b_weibull(80, 3, z)
+};
+
+template <class Env>
+struct SimplePerson : cProcess<SimplePerson<Env>, typename Env::Src, HEAP_CAP> {
+  typedef cProcess<SimplePerson<Env>, typename Env::Src, HEAP_CAP> Base;
+  using Base::now;
+  using Base::previousEventTime;
+  using Base::R;
+  using Base::RemoveKind;
+  using Base::scheduleAt;
+  using Base::stop_process;
+
+  int state;
+  double z;
+  Env &env;
+  const Consts &K;
+
+  MSIM_DEV SimplePerson(Env &e, const Consts &k, int64_t /*id*/) : Base(&e.src), state(Healthy), z(1.0), env(e), K(k) {}
+
+  MSIM_DEV void init() {  // illness-death.cpp:35-41
+    state = Healthy;
+    z = exp(R.rnorm(0.0, K.zsd));
+    scheduleAt(R.rweibull(4.0, K.b_other), toOtherDeath);
+    if (R.runif(0.0, 1.0) > K.cure) scheduleAt(R.rweibull(3.0, K.b_cancer_mean * pow(z, -1.0 / 3.0)), toCancer);
+  }
+
+  MSIM_DEV void handleMessage(int kind) {  // illness-death.cpp:46-71
+    env.report(state, kind, previousEventTime, now());
+    switch (kind) {
+      case toOtherDeath:
+      case toCancerDeath:
+        stop_process();
+        break;
+      case toCancer:
+        state = Cancer;
+        RemoveKind(toOtherDeath);
+        if (R.runif(0.0, 1.0) < 0.5) scheduleAt(now() + R.rweibull(1.0, 10.0), toCancerDeath);
+        break;
+      default:
+        break;
+    }
+  }
+};
+
+}  // namespace illness_death
+
+// ------------------------------------------- simple-example / simple-example2
+namespace simple_example {
+
+enum state_t { Healthy, Cancer, Death };
+enum event_t { toOtherDeath, toCancer, toCancerDeath };
+constexpr int N_STATE = 3, N_EVENT = 3, HEAP_CAP = 4, MAX_ROWS = 2, MAX_DRAWS = 4;
+
+struct Consts {
+  int unused;
+};
+
+template <class Env>
+struct SimplePerson : cProcess<SimplePerson<Env>, typename Env::Src, HEAP_CAP> {
+  typedef cProcess<SimplePerson<Env>, typename Env::Src, HEAP_CAP> Base;
+  using Base::now;
+  using Base::previousEventTime;
+  using Base::R;
+  using Base::scheduleAt;
+  using Base::stop_process;
+
+  int state;
+  int64_t id;
+  Env &env;
+
+  MSIM_DEV SimplePerson(Env &e, const Consts &, int64_t i) : Base(&e.src), state(Healthy), id(i), env(e) {}
+
+  MSIM_DEV void init() {  // simple-example.cc:26-32, simple-example2.cc:28-32
+    state = Healthy;
+    double tm = R.rweibull(8.0, 85.0);
+    scheduleAt(tm, toOtherDeath);
+    scheduleAt(R.rweibull(3.0, 90.0), toCancer);
+  }
+
+  MSIM_DEV void handleMessage(int kind) {  // simple-example.cc:41-70, simple-example2.cc:37-60
+    env.row((double)id, previousEventTime, now(), state, kind);  // callSimplePerson
+    env.report(state, kind, previousEventTime, now());           // callSimplePerson2
+    switch (kind) {
+      case toOtherDeath:
+      case toCancerDeath:
+        stop_process();
+        break;
+      case toCancer:
+        state = Cancer;
+        if (R.runif(0.0, 1.0) < 0.5) scheduleAt(now() + R.rweibull(2.0, 10.0), toCancerDeath);
+        break;
+      default:
+        break;
+    }
+  }
+};
+
+}  // namespace simple_example
+
+}  // namespace msim

@@ -1,0 +1,409 @@
+// TEST INFRASTRUCTURE — host emulation of the device engine.
+//
+// Compiles the SAME per-person templates the CUDA kernels instantiate
+// (microsimulation_b200/csrc/{mrg32k3a,rmath,engine,models,report,seqstream}.cuh)
+// with a plain C++ compiler and drives them with the kernels' work
+// decomposition (grid x BLOCK threads, tile loop, stride jump, per-position
+// draw counts + chunked chain resolution, three-wave MT regeneration), one
+// "thread" at a time.  CPU-only tests compare this against the oracle so that
+// heap, RNG, report and stream-offset logic is checked where there is no GPU.
+// It is NOT part of the product: libmsim_b200.so contains none of it.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/msim.h"
+#include "../../microsimulation_b200/csrc/host_state.h"
+#include "../../microsimulation_b200/csrc/models.cuh"
+#include "../../microsimulation_b200/csrc/report.cuh"
+#include "../../microsimulation_b200/csrc/report_host.h"
+#include "../../microsimulation_b200/csrc/seqstream.cuh"
+
+using namespace msim;
+
+namespace {
+
+constexpr int BLOCK = 256;
+constexpr unsigned OUT_ROWLOG = 1u, OUT_REPORT = 2u, OUT_COUNTS = 4u;
+
+struct PlainAcc {
+  double *d;
+  void addf(int idx, double v) { d[idx] += v; }
+  void addi(int idx, int v) { d[idx] += v; }
+};
+
+struct Rows {
+  std::vector<double> end, event, id, start, state;
+};
+
+template <class SrcT>
+struct HostEnv {
+  typedef SrcT Src;
+  Src src;
+  unsigned outputs;
+  Rows *rows;
+  const ReportGeom *geom;
+  PlainAcc acc;
+  double *counts;
+  void row(double id, double start, double end, int state, int kind) {
+    if (outputs & OUT_COUNTS) {
+      counts[kind] += 1;
+      counts[8] += end;
+    }
+    if (outputs & OUT_ROWLOG) {
+      rows->end.push_back(end);
+      rows->event.push_back(kind);
+      rows->id.push_back(id);
+      rows->start.push_back(start);
+      rows->state.push_back(state);
+    }
+  }
+  void report(int state, int kind, double lhs, double rhs) {
+    if (outputs & OUT_REPORT) report_add(*geom, acc, state, kind, lhs, rhs);
+  }
+};
+
+template <class SrcT>
+struct HostNullEnv {
+  typedef SrcT Src;
+  Src src;
+  void row(double, double, double, int, int) {}
+  void report(int, int, double, double) {}
+};
+
+struct Tables {
+  std::vector<MrgJump> lo, hi;
+  Tables() : lo(JUMP_TAB), hi(JUMP_TAB) {
+    const MrgJump &M = mrg_substream_jump();
+    lo[0] = mrg_jump_identity();
+    for (int j = 1; j < JUMP_TAB; j++) lo[j] = mrg_jump_mul(M, lo[j - 1]);
+    MrgJump Mt = mrg_jump_mul(M, lo[JUMP_TAB - 1]);
+    hi[0] = mrg_jump_identity();
+    for (int j = 1; j < JUMP_TAB; j++) hi[j] = mrg_jump_mul(Mt, hi[j - 1]);
+  }
+};
+const Tables &tables() {
+  static Tables T;
+  return T;
+}
+
+void make_start(const double seed[6], int64_t first_person_plus, int grid, StreamStart *st) {
+  uint32_t s[6];
+  seed_to_u32(seed, s);
+  Mrg32k3a b;
+  memcpy(b.s, s, sizeof s);
+  b.jump(mrg_jump_pow(mrg_substream_jump(), (uint64_t)first_person_plus));
+  memcpy(st->base, b.s, sizeof b.s);
+  st->lo = tables().lo.data();
+  st->hi = tables().hi.data();
+  st->stride = mrg_jump_pow(mrg_substream_jump(), (uint64_t)grid * BLOCK);
+}
+
+void rows_to_table(const Rows &r, const char *const *cols, msim_table *t) {
+  int64_t n = (int64_t)r.id.size();
+  t->nrow = n;
+  t->ncol = 5;
+  t->colnames = cols;
+  t->data = (double *)malloc(sizeof(double) * 5 * (n ? n : 1));
+  const std::vector<double> *src[5] = {&r.end, &r.event, &r.id, &r.start, &r.state};
+  for (int j = 0; j < 5; j++)
+    if (n) memcpy(t->data + j * n, src[j]->data(), sizeof(double) * n);
+}
+
+// rows come out in "thread-major" order; the kernel's scan/look-back restores
+// person order, which the emulation does by sorting on (id, emission order)
+void sort_rows_by_person(Rows &r) {
+  size_t n = r.id.size();
+  std::vector<size_t> idx(n);
+  for (size_t i = 0; i < n; i++) idx[i] = i;
+  std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return r.id[a] < r.id[b]; });
+  Rows o;
+  for (size_t i : idx) {
+    o.end.push_back(r.end[i]);
+    o.event.push_back(r.event[i]);
+    o.id.push_back(r.id[i]);
+    o.start.push_back(r.start[i]);
+    o.state.push_back(r.state[i]);
+  }
+  r = o;
+}
+
+// R's MT state -> raw words of the current batch and n_batches-1 regenerations
+std::vector<uint32_t> mt_words_emulated(const uint32_t state[625], int64_t n_batches) {
+  std::vector<uint32_t> w((size_t)n_batches * 624);
+  uint32_t mt[624];
+  memcpy(mt, state + 1, sizeof mt);
+  memcpy(w.data(), mt, sizeof mt);
+  for (int64_t b = 1; b < n_batches; b++) {
+    for (int wave = 0; wave < 3; wave++) {
+      int kk[256];
+      uint32_t v[256];
+      bool act[256];
+      for (int t = 0; t < 256; t++) act[t] = mt_wave_value(mt, wave, t, &kk[t], &v[t]);
+      for (int t = 0; t < 256; t++)
+        if (act[t]) mt[kk[t]] = v[t];
+    }
+    memcpy(w.data() + (size_t)b * 624, mt, sizeof mt);
+  }
+  return w;
+}
+
+template <template <class> class Model, class Consts>
+int sequential(int64_t n, const Consts &consts, int max_draws, unsigned outputs, const ReportGeom &geom,
+               uint32_t state[625], Rows *rows, std::vector<double> *dense) {
+  const int64_t mti0 = state[0];
+  const int64_t n_pos = (int64_t)max_draws * n;
+  const int64_t words_needed = mti0 + n_pos + max_draws + 1;
+  const int64_t n_batches = (words_needed + 623) / 624;
+  const int64_t mt_end = n_batches * 624;
+  std::vector<uint32_t> w = mt_words_emulated(state, n_batches);
+  if (n == 0) return 0;
+  // draws per start position
+  std::vector<unsigned char> len((size_t)n_pos);
+  for (int64_t p = 0; p < n_pos; p++) {
+    typedef HostNullEnv<StreamSource> Env;
+    Env env;
+    env.src.w = w.data();
+    env.src.pos = mti0 + p;
+    env.src.end = mt_end;
+    env.src.overrun = 0;
+    Model<Env> person(env, consts, 0);
+    person.run();
+    int64_t used = env.src.pos - (mti0 + p);
+    len[p] = (env.src.overrun || used > 250 || person.error_) ? 255 : (unsigned char)used;
+  }
+  // chunked chain resolution
+  const int64_t n_chunks = (n_pos + CHAIN_CHUNK - 1) / CHAIN_CHUNK;
+  std::vector<unsigned char> exit_off((size_t)n_chunks * CHAIN_MAX_DRAWS), entry((size_t)n_chunks);
+  std::vector<int> count((size_t)n_chunks * CHAIN_MAX_DRAWS);
+  std::vector<int64_t> base((size_t)n_chunks), starts((size_t)n);
+  std::vector<unsigned char> chunk(CHAIN_CHUNK);
+  for (int64_t c = 0; c < n_chunks; c++) {
+    for (int k = 0; k < CHAIN_CHUNK; k++) chunk[k] = (c * CHAIN_CHUNK + k < n_pos) ? len[c * CHAIN_CHUNK + k] : 255;
+    for (int e = 0; e < max_draws; e++) {
+      int cnt = 0;
+      exit_off[c * CHAIN_MAX_DRAWS + e] = (unsigned char)chain_walk(chunk.data(), e, &cnt);
+      count[c * CHAIN_MAX_DRAWS + e] = cnt;
+    }
+  }
+  int e = 0;
+  int64_t b = 0;
+  for (int64_t c = 0; c < n_chunks; c++) {
+    entry[c] = (unsigned char)e;
+    base[c] = b;
+    chain_scan_step(&exit_off[c * CHAIN_MAX_DRAWS], &count[c * CHAIN_MAX_DRAWS], n, &e, &b);
+  }
+  int64_t end_word = 0;
+  for (int64_t c = 0; c < n_chunks; c++) {
+    if (entry[c] == 255 || base[c] >= n) continue;
+    for (int k = 0; k < CHAIN_CHUNK; k++) chunk[k] = (c * CHAIN_CHUNK + k < n_pos) ? len[c * CHAIN_CHUNK + k] : 255;
+    if (!chain_emit(chunk.data(), entry[c], base[c], n, mti0 + c * CHAIN_CHUNK, starts.data(), &end_word)) return -6;
+  }
+  // the n real persons
+  typedef HostEnv<StreamSource> Env;
+  double counts[9] = {0};
+  Env env;
+  env.outputs = outputs;
+  env.rows = rows;
+  env.geom = &geom;
+  env.acc.d = dense ? dense->data() : 0;
+  env.counts = counts;
+  for (int64_t i = 0; i < n; i++) {
+    env.src.w = w.data();
+    env.src.pos = starts[i];
+    env.src.end = mt_end;
+    env.src.overrun = 0;
+    Model<Env> person(env, consts, i);
+    person.run();
+    if (env.src.overrun) return -6;
+    if (person.error_) return person.error_;
+  }
+  int64_t batch = (end_word - 1) / 624;
+  memcpy(state + 1, w.data() + batch * 624, sizeof(uint32_t) * 624);
+  state[0] = (uint32_t)(end_word - batch * 624);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int emu_rng_uniforms(const double seed[6], int64_t first_substream, int64_t n_substreams, int32_t draws, int grid,
+                     double *out) {
+  StreamStart st;
+  make_start(seed, first_substream, grid, &st);
+  for (int blk = 0; blk < grid; blk++)
+    for (int tid = 0; tid < BLOCK; tid++) {
+      unsigned gth = blk * BLOCK + tid;
+      Mrg32k3a sub = thread_start_state(st, gth);
+      for (int64_t j = gth; j < n_substreams; j += (int64_t)grid * BLOCK) {
+        Mrg32k3a cur = sub;
+        for (int k = 0; k < draws; k++) out[j * draws + k] = cur.u01();
+        sub.jump(st.stride);
+      }
+    }
+  return 0;
+}
+
+int emu_person_run(const msim_person_shard *sh, int grid, msim_table *rowlog, double counts[9], msim_report *report) {
+  if (!mrg_seed_ok(sh->seed)) return MSIM_ERR_SEED;
+  StreamStart st;
+  make_start(sh->seed, sh->first_person + 1, grid, &st);
+  person_r::Consts K = person_r::make_consts();
+  ReportGeom geom = ages_geom(person_r::N_STATE, person_r::N_EVENT, sh->discount_rate);
+  std::vector<double> dense(geom.total, 0.0);
+  Rows rows;
+  typedef HostEnv<MrgSource> Env;
+  Env env;
+  env.outputs = sh->outputs;
+  env.rows = &rows;
+  env.geom = &geom;
+  env.acc.d = dense.data();
+  double cnt[9] = {0};
+  env.counts = cnt;
+  int64_t n_tiles = (sh->n + BLOCK - 1) / BLOCK;
+  for (int blk = 0; blk < grid; blk++)
+    for (int tid = 0; tid < BLOCK; tid++) {
+      Mrg32k3a sub = thread_start_state(st, blk * BLOCK + tid);
+      for (int64_t tile = blk; tile < n_tiles; tile += grid) {
+        int64_t idx = tile * BLOCK + tid;
+        if (idx < sh->n) {
+          env.src.g = sub;
+          person_r::Person<Env> person(env, K, sh->first_person + idx);
+          person.run();
+          if (person.error_) return person.error_;
+        }
+        sub.jump(st.stride);
+      }
+    }
+  if (counts) memcpy(counts, cnt, sizeof cnt);
+  if (rowlog) {
+    sort_rows_by_person(rows);
+    static const char *const cols[5] = {"endTime", "event", "id", "startTime", "state"};
+    rows_to_table(rows, cols, rowlog);
+  }
+  if (report) dense_to_report_impl(dense.data(), geom, report);
+  return 0;
+}
+
+// model: 0 = callSimplePerson (row log), 1 = callSimplePerson2 (report), 2 = callIllnessDeath (report)
+int emu_sequential(int model, int64_t n, double cure, double zsd, uint32_t state[625], msim_table *rowlog,
+                   msim_report *report) {
+  Rows rows;
+  int rc;
+  if (model == 0 || model == 1) {
+    simple_example::Consts c = {0};
+    ReportGeom geom = ages_geom(simple_example::N_STATE, simple_example::N_EVENT, 0.0);
+    std::vector<double> dense(geom.total, 0.0);
+    rc = sequential<simple_example::SimplePerson>(n, c, simple_example::MAX_DRAWS, model == 0 ? OUT_ROWLOG : OUT_REPORT,
+                                                  geom, state, &rows, &dense);
+    if (rc) return rc;
+    static const char *const cols[5] = {"endtime", "event", "id", "startTime", "state"};
+    if (rowlog) rows_to_table(rows, cols, rowlog);
+    if (report) dense_to_report_impl(dense.data(), geom, report);
+    return 0;
+  }
+  illness_death::Consts c = illness_consts(cure, zsd);
+  ReportGeom geom = ages_geom(illness_death::N_STATE, illness_death::N_EVENT, 0.0);
+  std::vector<double> dense(geom.total, 0.0);
+  rc = sequential<illness_death::SimplePerson>(n, c, zsd == 0.0 ? 5 : 7, OUT_REPORT, geom, state, &rows, &dense);
+  if (rc) return rc;
+  if (report) dense_to_report_impl(dense.data(), geom, report);
+  return 0;
+}
+
+struct EmuCalibEnv {
+  typedef MrgSource Src;
+  Src src;
+  double occ[40];
+  double tar[4];
+  int tar_n;
+  void occupancy(int stage, int cind) {
+    if (stage < 4) occ[stage * 10 + cind] += 1;
+  }
+  void time_at_risk(int i, double v) {
+    tar[i] += v;
+    if (i + 1 > tar_n) tar_n = i + 1;
+  }
+};
+
+int emu_calibration(const double seed[6], int64_t first_person, int64_t n, const double runpar[6], int grid,
+                    msim_calibration *out) {
+  StreamStart st;
+  make_start(seed, first_person + 1, grid, &st);
+  calib::Par par = {runpar[0], runpar[1], runpar[2], runpar[3], runpar[4], runpar[5]};
+  EmuCalibEnv env;
+  memset(env.occ, 0, sizeof env.occ);
+  memset(env.tar, 0, sizeof env.tar);
+  env.tar_n = 0;
+  // person order (the sums are order-dependent in the last bits; emulate the reference's order)
+  std::vector<Mrg32k3a> subs((size_t)n);
+  for (int blk = 0; blk < grid; blk++)
+    for (int tid = 0; tid < BLOCK; tid++) {
+      Mrg32k3a sub = thread_start_state(st, blk * BLOCK + tid);
+      for (int64_t idx = (int64_t)blk * BLOCK + tid; idx < n; idx += (int64_t)grid * BLOCK) {
+        subs[idx] = sub;
+        sub.jump(st.stride);
+      }
+    }
+  for (int64_t i = 0; i < n; i++) {
+    env.src.g = subs[i];
+    calib::CalibPerson<EmuCalibEnv> person(env, par);
+    person.run();
+    if (person.error_) return person.error_;
+  }
+  memset(out, 0, sizeof *out);
+  for (int s = 0; s < 4; s++) {
+    double tot = 0;
+    for (int k = 0; k < 10; k++) {
+      out->occupancy[s * 10 + k] = env.occ[s * 10 + k];
+      tot += env.occ[s * 10 + k];
+    }
+    out->present[s] = tot > 0;
+  }
+  out->n_time_at_risk = env.tar_n;
+  for (int k = 0; k < env.tar_n; k++) out->time_at_risk[k] = env.tar[k];
+  return 0;
+}
+
+void emu_mt_set_seed(uint32_t seed, uint32_t state[625]) {
+  HostRngState r;
+  r.mt_set_seed(seed);
+  memcpy(state, r.mt, sizeof r.mt);
+}
+
+// first n uniforms from an MT state (three-wave regeneration), state not advanced
+void emu_mt_uniforms(const uint32_t state[625], int64_t n, double *out) {
+  int64_t mti0 = state[0];
+  int64_t n_batches = (mti0 + n + 623) / 624;
+  std::vector<uint32_t> w = mt_words_emulated(state, n_batches);
+  for (int64_t i = 0; i < n; i++) out[i] = mt_word_to_unif(w[mti0 + i]);
+}
+
+int emu_advance_substream(double seed[6], int n) {
+  HostStream r;
+  uint32_t s[6];
+  seed_to_u32(seed, s);
+  r.set_all(s);
+  r.advance_substream(0, n);
+  for (int i = 0; i < 6; i++) seed[i] = (double)r.Cg.s[i];
+  return 0;
+}
+
+void emu_table_free(msim_table *t) {
+  free(t->data);
+  t->data = 0;
+}
+void emu_report_free(msim_report *r) {
+  emu_table_free(&r->pt);
+  emu_table_free(&r->ut);
+  emu_table_free(&r->events);
+  emu_table_free(&r->prev);
+  emu_table_free(&r->costs);
+  emu_table_free(&r->indiv);
+}
+
+}  // extern "C"
