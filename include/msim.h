@@ -134,9 +134,12 @@ int msim_callCalibrationSimulation(int32_t n, const double runpar[6], msim_calib
 
 /* Dense report geometry (states x events x age bins over the partition
  * {0,1,..,100,1e6} used by every built model). */
+#define MSIM_N_COUNTS 9 /* per-kind event counts [0..7] and sum(endTime) [8] */
+
 typedef struct msim_dense_dims {
   int32_t n_state, n_event, n_bin;
-  int64_t n_doubles; /* length of the dense accumulator vector */
+  int64_t n_doubles; /* length of the accumulator vector: the dense report cells (none if no
+                        report was requested) followed by the MSIM_N_COUNTS count cells */
 } msim_dense_dims;
 
 typedef struct msim_person_shard {
@@ -166,15 +169,21 @@ int msim_sync(void);
 /* Average device time (ms) of the last enqueue/run, measured with CUDA events
  * on the library's stream around the simulation kernel. */
 int msim_last_kernel_ms(float *ms);
+/* CUDA events on the library's stream around a region of enqueued work:
+ * start records, stop records + waits and returns the elapsed device time. */
+int msim_timer_start(void);
+int msim_timer_stop(float *ms);
 /* Copy results of the last run to the host. */
 int msim_person_fetch_rowlog(msim_table *out);
 int msim_person_fetch_counts(double counts[9]);
-/* Dense accumulators (e.g. after an all-reduce done by the caller on the
- * device buffer) -> sparse report tables in the reference's layout. */
+/* Accumulator vector (e.g. after an all-reduce done by the caller on the
+ * device buffer) -> sparse report tables in the reference's layout.  Pure host
+ * code: needs no device. */
 int msim_dense_to_report(const double *host_dense, const msim_dense_dims *dims, double discount_rate,
                          msim_report *out);
-/* Writable device pointer to the dense accumulators of the last run, for an
- * in-place NCCL all-reduce by the host layer. */
+/* Writable device pointer to the accumulator vector of the last run (report
+ * cells + counts), for ONE in-place NCCL all-reduce(sum, f64) by the host layer:
+ * every cell is a sum, integer counts are exact in f64. */
 int msim_dense_device_ptr(double **d_ptr, int64_t *n_doubles);
 int msim_dense_fetch(double *host_dense, int64_t n_doubles);
 

@@ -206,6 +206,16 @@ def last_kernel_ms():
     return ms.value
 
 
+def timer_start():
+    check(load().msim_timer_start())
+
+
+def timer_stop():
+    ms = C.c_float()
+    check(load().msim_timer_stop(C.byref(ms)))
+    return ms.value
+
+
 def person_fetch_rowlog(copy=True):
     t = Table()
     check(load().msim_person_fetch_rowlog(C.byref(t)))

@@ -32,7 +32,7 @@ struct Ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
   MrgJump *d_lo = nullptr, *d_hi = nullptr;
   DevBuf rowlog, tiles, dense, small, mt_words, len, starts, chain_exit, chain_count, chain_entry, chain_base, calib_out,
       calib_par, uniforms;
@@ -42,6 +42,7 @@ struct Ctx {
   ReportGeom last_geom;
   unsigned last_outputs = 0;
   bool last_simple_names = false;
+  int last_cells = 0;  // dense report cells of the last run (0 when no report was requested)
   bool have_last = false;
   float last_ms = 0.f;
   bool timing_pending = false;
@@ -161,9 +162,8 @@ ReportGeom geom_from_dims(const msim_dense_dims *dims, double discount_rate) {
 
 // ---------------------------------------------------------------- cohort launch
 
-// `small` buffer layout (doubles / 8-byte cells): [0..8] counts, [9] n_rows (u64), [10] error (int), [11] end_word (i64)
+// `small` buffer layout (8-byte cells): [9] n_rows (u64), [10] error (int), [11] end_word (i64)
 struct SmallView {
-  double *counts;
   unsigned long long *n_rows;
   int *error;
   int64_t *end_word;
@@ -171,7 +171,6 @@ struct SmallView {
 SmallView small_view() {
   SmallView v;
   double *b = (double *)g.small.p;
-  v.counts = b;
   v.n_rows = (unsigned long long *)(b + 9);
   v.error = (int *)(b + 10);
   v.end_word = (int64_t *)(b + 11);
@@ -204,14 +203,16 @@ int cohort_prepare(CohortParams<typename Traits::Consts> &p, const uint32_t stre
   if ((rc = ensure(g.small, 16 * sizeof(double)))) return rc;
   CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
   SmallView sv = small_view();
-  p.counts = sv.counts;
   p.n_rows = sv.n_rows;
   p.error = sv.error;
-  if (p.outputs & OUT_REPORT) {
-    if ((rc = ensure(g.dense, sizeof(double) * p.geom.total))) return rc;
-    CK(cudaMemsetAsync(g.dense.p, 0, sizeof(double) * p.geom.total, g.stream));
-    p.dense = (double *)g.dense.p;
-  }
+  // one accumulator vector: the dense report cells (if requested) followed by the N_COUNTS count cells,
+  // so that a single all-reduce merges everything a shard produces
+  const int cells = (p.outputs & OUT_REPORT) ? p.geom.total : 0;
+  if ((rc = ensure(g.dense, sizeof(double) * (cells + N_COUNTS)))) return rc;
+  CK(cudaMemsetAsync(g.dense.p, 0, sizeof(double) * (cells + N_COUNTS), g.stream));
+  p.dense = (double *)g.dense.p;
+  p.counts = p.dense + cells;
+  g.last_cells = cells;
   if (p.outputs & OUT_ROWLOG) {
     int64_t tiles = (p.n + BLOCK - 1) / BLOCK;
     if ((rc = ensure(g.tiles, sizeof(unsigned long long) * (size_t)std::max<int64_t>(tiles, 1)))) return rc;
@@ -665,11 +666,11 @@ int msim_person_enqueue(const msim_person_shard *shard, msim_person_device_resul
     res->capacity = g.last_capacity;
     res->d_rowlog = (shard->outputs & OUT_ROWLOG) ? (const double *)g.rowlog.p : nullptr;
     res->d_dense = (shard->outputs & OUT_REPORT) ? (const double *)g.dense.p : nullptr;
-    res->d_counts = (const double *)g.small.p;
+    res->d_counts = (const double *)g.dense.p + g.last_cells;
     res->dims.n_state = g.last_geom.n_state;
     res->dims.n_event = g.last_geom.n_event;
     res->dims.n_bin = g.last_geom.n_bin;
-    res->dims.n_doubles = g.last_geom.total;
+    res->dims.n_doubles = g.last_cells + N_COUNTS;
   }
   return MSIM_OK;
 }
@@ -688,12 +689,32 @@ int msim_person_run_device(const msim_person_shard *shard, msim_person_device_re
     res->capacity = g.last_capacity;
     res->d_rowlog = (shard->outputs & OUT_ROWLOG) ? (const double *)g.rowlog.p : nullptr;
     res->d_dense = (shard->outputs & OUT_REPORT) ? (const double *)g.dense.p : nullptr;
-    res->d_counts = (const double *)g.small.p;
+    res->d_counts = (const double *)g.dense.p + g.last_cells;
     res->dims.n_state = g.last_geom.n_state;
     res->dims.n_event = g.last_geom.n_event;
     res->dims.n_bin = g.last_geom.n_bin;
-    res->dims.n_doubles = g.last_geom.total;
+    res->dims.n_doubles = g.last_cells + N_COUNTS;
   }
+  return MSIM_OK;
+}
+
+// CUDA events on the library's own stream, for callers that time a region of enqueued work
+// (torch.cuda.Event only sees torch's streams).
+int msim_timer_start(void) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  if (!g.tev0) {
+    CK(cudaEventCreate(&g.tev0));
+    CK(cudaEventCreate(&g.tev1));
+  }
+  CK(cudaEventRecord(g.tev0, g.stream));
+  return MSIM_OK;
+}
+int msim_timer_stop(float *ms) {
+  if (!g.tev0) return fail(MSIM_ERR_STATE, "timer not started");
+  CK(cudaEventRecord(g.tev1, g.stream));
+  CK(cudaEventSynchronize(g.tev1));
+  CK(cudaEventElapsedTime(ms, g.tev0, g.tev1));
   return MSIM_OK;
 }
 
@@ -711,28 +732,28 @@ int msim_person_fetch_rowlog(msim_table *out) {
 
 int msim_person_fetch_counts(double counts[9]) {
   if (!g.have_last) return fail(MSIM_ERR_STATE, "no run yet");
-  CK(cudaMemcpy(counts, g.small.p, sizeof(double) * 9, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(counts, (const double *)g.dense.p + g.last_cells, sizeof(double) * N_COUNTS, cudaMemcpyDeviceToHost));
   return MSIM_OK;
 }
 
 int msim_dense_to_report(const double *host_dense, const msim_dense_dims *dims, double discount_rate, msim_report *out) {
   if (!host_dense || !dims || !out) return fail(MSIM_ERR_ARG, "bad arguments");
   ReportGeom G = geom_from_dims(dims, discount_rate);
-  if (G.total != dims->n_doubles) return fail(MSIM_ERR_ARG, "dims.n_doubles does not match the geometry");
+  if (G.total + N_COUNTS != dims->n_doubles) return fail(MSIM_ERR_ARG, "dims.n_doubles does not match the geometry");
   dense_to_report_impl(host_dense, G, out);
   return MSIM_OK;
 }
 
 int msim_dense_device_ptr(double **d_ptr, int64_t *n_doubles) {
-  if (!g.have_last || !(g.last_outputs & OUT_REPORT)) return fail(MSIM_ERR_STATE, "last run produced no report");
+  if (!g.have_last) return fail(MSIM_ERR_STATE, "no run yet");
   *d_ptr = (double *)g.dense.p;
-  *n_doubles = g.last_geom.total;
+  *n_doubles = g.last_cells + N_COUNTS;
   return MSIM_OK;
 }
 
 int msim_dense_fetch(double *host_dense, int64_t n_doubles) {
-  if (!g.have_last || !(g.last_outputs & OUT_REPORT)) return fail(MSIM_ERR_STATE, "last run produced no report");
-  if (n_doubles != g.last_geom.total) return fail(MSIM_ERR_ARG, "size mismatch");
+  if (!g.have_last) return fail(MSIM_ERR_STATE, "no run yet");
+  if (n_doubles != g.last_cells + N_COUNTS) return fail(MSIM_ERR_ARG, "size mismatch");
   CK(cudaMemcpy(host_dense, g.dense.p, sizeof(double) * n_doubles, cudaMemcpyDeviceToHost));
   return MSIM_OK;
 }

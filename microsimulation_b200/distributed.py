@@ -1,0 +1,115 @@
+"""Multi-GPU sharding of the substream-regime models (one process per GPU).
+
+Persons are independent and person i is a pure function of (seed, i), so a
+cohort shards by contiguous person ranges with no data-path exchange; rank r
+jumps straight to its first substream (A^(2^76))^(first+1) on the host.  The
+only collective is ONE all-reduce(sum, f64) over the accumulator vector (dense
+report cells + per-kind counts): every cell is a sum and integer counts are
+exact in f64, so the merged tables equal a single-GPU run's (FP sums to
+rounding).  Row logs stay sharded, in person order within and across ranks.
+
+The reference's own parallel wrappers (R/calibSim.R:16-39, README.org:347-352)
+give chunk k a different RngStream *stream*, which changes the random numbers;
+this keeps the mc.cores = 1 numbering instead (end).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import api
+from ._lib import MSIM_OUT_COUNTS, MSIM_OUT_REPORT, MSIM_OUT_ROWLOG, DenseDims  # noqa: F401
+
+
+def shard_range(n, rank, world_size):
+    """Contiguous [first, first+count) of n persons for `rank`; earlier ranks take the remainder."""
+    base, rem = divmod(int(n), int(world_size))
+    count = base + (1 if rank < rem else 0)
+    first = rank * base + min(rank, rem)
+    return first, count
+
+
+class _CudaBuffer:
+    """Zero-copy view of a device pointer for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def person_dims(with_report):
+    cells = 0
+    d = DenseDims(8, 8, 102, 0)
+    if with_report:
+        sb = 8 * 102
+        cells = 3 * sb + 2 * 8 * 103 + 8 * 8 * 102
+    d.n_doubles = cells + 9
+    return d
+
+
+def _gpu_compute(seed, first, count, outputs, discount_rate):
+    """Runs the shard on this process's GPU; returns a torch CUDA tensor aliasing the library's accumulators."""
+    import torch
+    res = api.person_run_device(seed, first, count, outputs, discount_rate)
+    ptr, n = api.dense_device_ptr()
+    t = torch.as_tensor(_CudaBuffer(ptr, n), device="cuda")
+    return t, res.dims, res.n_rows
+
+
+def person_simulation_sharded(n, seed=(12345,) * 6, outputs=MSIM_OUT_REPORT | MSIM_OUT_COUNTS, discount_rate=0.0,
+                              first_person=0, group=None, compute=None):
+    """callPersonSimulation over all ranks of `group`.
+
+    Returns (report tables or None, counts[9], rows on this rank).  `compute`
+    (tests only) replaces the GPU shard runner with another function of the
+    same signature returning (tensor, dims, n_rows).
+    """
+    import torch.distributed as dist
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    first, count = shard_range(n, rank, world)
+    acc, dims, n_rows = (compute or _gpu_compute)(seed, first_person + first, count, outputs, discount_rate)
+    if world > 1:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)  # the single collective
+    host = acc.detach().cpu().numpy()
+    counts = host[-9:].copy()
+    report = api.dense_to_report(host, dims, discount_rate) if outputs & MSIM_OUT_REPORT else None
+    return report, counts, n_rows
+
+
+def calibration_sweep_sharded(seed, runpars, n, group=None, compute=None):
+    """Config 5: every rank takes a person range of every parameter set; occupancy and TimeAtRisk are sums."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    first, count = shard_range(n, rank, world)
+    runpars = np.ascontiguousarray(runpars, dtype=np.float64).reshape(-1, 6)
+    res = (compute or api.calibration_sweep)(seed, runpars, count, first)
+    # pack: per set 40 occupancy + 4 TimeAtRisk sums; n_time_at_risk merges by max
+    ns = runpars.shape[0]
+    sums = np.zeros((ns, 44))
+    tmax = np.zeros(ns)
+    names = ["DiseaseFree", "Precursor", "PreClinical", "Clinical"]
+    for s, r in enumerate(res):
+        for j, nm in enumerate(names):
+            if nm in r:
+                sums[s, j * 10:(j + 1) * 10] = r[nm]
+        k = len(r["TimeAtRisk"])
+        sums[s, 40:40 + k] = r["TimeAtRisk"]
+        tmax[s] = k
+    dev = "cuda" if (world > 1 and dist.get_backend(group) == "nccl") else "cpu"
+    t_sum = torch.from_numpy(sums).to(dev)
+    t_max = torch.from_numpy(tmax).to(dev)
+    if world > 1:
+        dist.all_reduce(t_sum, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX, group=group)
+    sums, tmax = t_sum.cpu().numpy(), t_max.cpu().numpy()
+    out = []
+    for s in range(ns):
+        d = {"TimeAtRisk": sums[s, 40:40 + int(tmax[s])].copy()}
+        for j, nm in enumerate(names):
+            col = sums[s, j * 10:(j + 1) * 10]
+            if col.sum() > 0:
+                d[nm] = col.copy()
+        out.append(d)
+    return out

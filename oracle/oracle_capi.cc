@@ -110,6 +110,14 @@ int oracle_r_rng_advance_substream(double seed[6], const int *n) {
   ssim::r_rng_advance_substream(seed, &nn);
   return 0;
 }
+// RngStream::AdvanceSubstream(e, c) on a stream seeded with `seed` (RngStream.cpp:454-458)
+int oracle_rng_advance_e(double seed[6], int e, int c) {
+  ssim::RngStream g;
+  if (!g.SetSeed(seed)) return MSIM_ERR_SEED;
+  g.AdvanceSubstream(e, c);
+  g.GetState(seed);
+  return 0;
+}
 int oracle_mt_set_seed(uint32_t seed) {
   rlite::RNGkind(rlite::MERSENNE_TWISTER);
   rlite::set_seed(seed);

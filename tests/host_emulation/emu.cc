@@ -289,6 +289,42 @@ int emu_person_run(const msim_person_shard *sh, int grid, msim_table *rowlog, do
   return 0;
 }
 
+// the accumulator vector a shard contributes to the all-reduce: dense report cells, then the 9 counts
+int emu_person_dense(const msim_person_shard *sh, int grid, double *acc, int64_t n_doubles) {
+  if (!mrg_seed_ok(sh->seed)) return MSIM_ERR_SEED;
+  StreamStart st;
+  make_start(sh->seed, sh->first_person + 1, grid, &st);
+  person_r::Consts K = person_r::make_consts();
+  ReportGeom geom = ages_geom(person_r::N_STATE, person_r::N_EVENT, sh->discount_rate);
+  const int cells = (sh->outputs & OUT_REPORT) ? geom.total : 0;
+  if (n_doubles != cells + 9) return MSIM_ERR_ARG;
+  memset(acc, 0, sizeof(double) * n_doubles);
+  Rows rows;
+  typedef HostEnv<MrgSource> Env;
+  Env env;
+  env.outputs = sh->outputs & ~OUT_ROWLOG;
+  env.rows = &rows;
+  env.geom = &geom;
+  env.acc.d = acc;
+  env.counts = acc + cells;
+  int64_t n_tiles = (sh->n + BLOCK - 1) / BLOCK;
+  for (int blk = 0; blk < grid; blk++)
+    for (int tid = 0; tid < BLOCK; tid++) {
+      Mrg32k3a sub = thread_start_state(st, blk * BLOCK + tid);
+      for (int64_t tile = blk; tile < n_tiles; tile += grid) {
+        int64_t idx = tile * BLOCK + tid;
+        if (idx < sh->n) {
+          env.src.g = sub;
+          person_r::Person<Env> person(env, K, sh->first_person + idx);
+          person.run();
+          if (person.error_) return person.error_;
+        }
+        sub.jump(st.stride);
+      }
+    }
+  return 0;
+}
+
 // model: 0 = callSimplePerson (row log), 1 = callSimplePerson2 (report), 2 = callIllnessDeath (report)
 int emu_sequential(int model, int64_t n, double cure, double zsd, uint32_t state[625], msim_table *rowlog,
                    msim_report *report) {

@@ -1,0 +1,291 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (microsimulation_b200 ->
+libmsim_b200.so), against the CPU oracle on the same seeds, against the committed
+fixtures made from oracle/_ref, and — at BASELINE.json's full sizes — through
+size-independent properties.
+
+Bars (north_star): RNG streams, event kinds, ids, states and every integer table
+bit-exact; FP64 report sums within 1e-9 relative; event TIMES within a few ulp
+(device libm vs glibc for log/pow/exp; DESIGN.md "libm parity")."""
+import numpy as np
+import pytest
+
+from conftest import assert_report_close, assert_rowlog_close
+
+pytestmark = pytest.mark.gpu
+
+TIME_RTOL = 4e-15  # <= ~18 ulp guard; measured max is 2 ulp (4.4e-16)
+
+
+# ------------------------------------------------------------------ RNG (K1)
+
+@pytest.mark.parametrize("seed,first,n,draws", [(12345, 0, 100000, 8), (12345, 99999000, 5000, 4),
+                                                ([1, 2, 3, 4, 5, 6], 17, 70000, 3), (4294944442, 0, 1000, 16)])
+def test_mrg32k3a_substreams_bit_exact(msim, oracle, seed, first, n, draws):
+    assert np.array_equal(msim.rng_uniforms(seed, first, n, draws), oracle.rng_uniforms(seed, first, n, draws))
+
+
+def test_mrg32k3a_golden(msim, golden):
+    assert np.array_equal(msim.rng_uniforms(12345, 0, 64, 8), golden["mrg_uniforms_seed12345_sub0_64x8"])
+    assert np.array_equal(msim.rng_uniforms(12345, 99999990, 8, 4), golden["mrg_uniforms_seed12345_sub99999990_8x4"])
+    assert np.array_equal(np.array(msim.advance_substream(12345, 1000)), golden["advance_substream_12345_1000"])
+
+
+def test_mersenne_twister_bit_exact(msim, oracle, golden):
+    msim.set_seed(12345)
+    oracle.set_seed(12345)
+    u = msim.mt_uniforms(300000)  # 480 regenerations
+    assert np.array_equal(u, oracle.mt_uniforms(300000))
+    assert np.array_equal(u[:2000], golden["mt_uniforms_12345_2000"])
+
+
+def test_bad_seed_is_an_error_code(msim):
+    with pytest.raises(msim.MsimError) as e:
+        msim.rng_uniforms([0, 0, 0, 1, 2, 3], 0, 10, 1)
+    assert e.value.code == -5
+    with pytest.raises(msim.MsimError):
+        msim.callPersonSimulation(10, seed=[4294967087] * 6)
+
+
+# ------------------------------------------------------------------ person-r (config 3)
+
+@pytest.mark.parametrize("n", [0, 1, 20, 255, 256, 257, 1000, 70001])
+def test_person_rowlog_vs_oracle(msim, oracle, n):
+    g, r = msim.callPersonSimulation(n), oracle.callPersonSimulation(n)
+    assert list(g.keys()) == ["endTime", "event", "id", "startTime", "state"]  # std::map key order, person-r.cc:224
+    assert len(g["id"]) == len(r["id"])
+    assert_rowlog_close(g, r, TIME_RTOL)
+
+
+def test_person_rowlog_golden(msim, golden):
+    g = msim.callPersonSimulation(2000)
+    want = {k: golden["person_n2000_" + k] for k in g}
+    assert_rowlog_close(g, want, TIME_RTOL)
+
+
+def test_person_other_seed_and_shard_offset(msim, oracle):
+    import microsimulation_b200.api as api
+    seed = [11, 22, 33, 44, 55, 66]
+    api.person_run_device(seed, 123457, 30000, 1 | 4)
+    g = api.person_fetch_rowlog()
+    r = oracle.person_run(seed, 123457, 30000)
+    assert_rowlog_close(g, r["rowlog"], TIME_RTOL)
+    c = api.person_fetch_counts()
+    assert np.array_equal(c[:8], r["counts"][:8])
+    assert g["id"][0] >= 123457 and g["id"][-1] == 123457 + 30000 - 1
+
+
+@pytest.mark.parametrize("rate", [0.0, 0.03])
+def test_person_event_report_vs_oracle(msim, oracle, rate):
+    n = 150000
+    rep, counts = msim.person_report(12345, 0, n, rate)
+    ref = oracle.person_run(12345, 0, n, rowlog=False, report=True, discount_rate=rate)
+    assert np.array_equal(counts[:8], ref["counts"][:8])
+    assert abs(counts[8] - ref["counts"][8]) <= 1e-12 * ref["counts"][8]
+    assert_report_close(rep, ref["report"], rtol=1e-9)
+    if rate == 0.0:
+        assert np.array_equal(rep["ut"]["utility"], rep["pt"]["pt"])  # utility*(b-a) with utility = 1
+
+
+def test_person_report_golden(msim, golden):
+    rep, counts = msim.person_report(12345, 0, 2000, 0.03)
+    assert np.array_equal(counts[:8], golden["person_n2000_counts"][:8])
+    for tb in ("pt", "ut", "events", "prev"):
+        for k, v in rep[tb].items():
+            w = golden["person_n2000_report_%s_%s" % (tb, k)]
+            if k in ("pt", "utility"):
+                np.testing.assert_allclose(v, w, rtol=1e-9)
+            else:
+                assert np.array_equal(v, w), (tb, k)
+
+
+def test_person_counts_1e6_exact(msim, golden):
+    import microsimulation_b200.api as api
+    api.person_run_device(12345, 0, 10 ** 6, 4)
+    c = api.person_fetch_counts()
+    assert np.array_equal(c[:8], golden["person_n1e6_counts"][:8])  # 991300, 8700, 105038, ...
+    assert abs(c[8] - golden["person_n1e6_counts"][8]) <= 1e-12 * c[8]
+
+
+def test_person_full_size_properties(msim, golden):
+    """BASELINE config 3 (n = 1e7): properties that need no oracle run of that size."""
+    import microsimulation_b200.api as api
+    n = 10 ** 7
+    res = api.person_run_device(12345, 0, n, 1 | 4)
+    counts = api.person_fetch_counts()
+    g = api.person_fetch_rowlog()
+    assert res.n_rows == len(g["id"]) == int(counts[:8].sum())
+    ids = g["id"]
+    assert ids[0] == 0 and ids[-1] == n - 1
+    d = np.diff(ids)
+    assert ((d == 0) | (d == 1)).all()  # person order, nobody missing, rows of a person contiguous
+    assert (g["startTime"] <= g["endTime"]).all()
+    last = np.r_[d == 1, True]  # last row of each person
+    assert np.isin(g["event"][last], (0, 1)).all()  # everybody ends with toDeath / toPCDeath
+    assert not np.isin(g["event"][~last], (0, 1)).any()
+    first = np.r_[True, d == 1]
+    assert (g["startTime"][first] == 0).all() and (g["state"][first] == 0).all()
+    cont = ~first
+    assert np.array_equal(g["startTime"][cont], g["endTime"][np.flatnonzero(cont) - 1])  # intervals chain
+    assert np.array_equal(np.bincount(g["event"].astype(int), minlength=8), counts[:8].astype(int))
+    assert abs(g["endTime"].sum() - counts[8]) <= 1e-10 * counts[8]
+    # prefix property: the first 1e6 persons are the n = 1e6 run
+    head = ids < 10 ** 6
+    assert np.array_equal(np.bincount(g["event"][head].astype(int), minlength=8),
+                          golden["person_n1e6_counts"][:8].astype(int))
+    # shard additivity of counts (the multi-GPU merge is this sum)
+    tot = np.zeros(9)
+    for k in range(4):
+        api.person_run_device(12345, k * n // 4, n // 4, 4)
+        tot += api.person_fetch_counts()
+    assert np.array_equal(tot[:8], counts[:8])
+
+
+def test_person_report_is_deterministic_in_integer_cells(msim):
+    a, _ = msim.person_report(12345, 0, 300000, 0.0)
+    b, _ = msim.person_report(12345, 0, 300000, 0.0)
+    for tb in ("events", "prev"):
+        assert np.array_equal(a[tb]["number"], b[tb]["number"])
+    np.testing.assert_allclose(a["pt"]["pt"], b["pt"]["pt"], rtol=1e-13)
+
+
+# ------------------------------------------------------------------ sequential-stream models (configs 1-2)
+
+@pytest.mark.parametrize("n", [0, 1, 10, 2049, 100000])
+def test_simple_person_vs_oracle(msim, oracle, n):
+    g, r = msim.callSimplePerson(n), oracle.callSimplePerson(n)
+    assert list(g.keys()) == ["endtime", "event", "id", "startTime", "state"]  # simple-example.cc:45 spells "endtime"
+    assert len(g["id"]) == len(r["id"])
+    assert_rowlog_close(g, r, TIME_RTOL, end_col="endtime")
+    assert np.array_equal(msim.mt_uniforms(16), oracle.mt_uniforms(16))  # R's generator left in the same state
+
+
+def test_simple_person_golden(msim, golden):
+    g = msim.callSimplePerson(3000)
+    assert_rowlog_close(g, {k: golden["simple_n3000_" + k] for k in g}, TIME_RTOL, end_col="endtime")
+
+
+@pytest.mark.parametrize("n", [10, 20000, 100000])
+def test_simple_person2_vs_oracle(msim, oracle, n):
+    assert_report_close(msim.callSimplePerson2(n), oracle.callSimplePerson2(n), rtol=1e-9)
+
+
+@pytest.mark.parametrize("n,cure,zsd", [(0, 0.1, 0.0), (10, 0.1, 0.0), (100000, 0.1, 0.0), (100000, 0.2, 0.0),
+                                        (50000, 0.95, 0.0), (50000, 0.1, 0.5)])
+def test_illness_death_vs_oracle(msim, oracle, n, cure, zsd):
+    """BASELINE config 1 (n = 1e5, default rates) and the README's cure = 0.2 run; zsd > 0 adds norm_rand's two draws."""
+    g, r = msim.callIllnessDeath(n, cure, zsd), oracle.callIllnessDeath(n, cure, zsd)
+    assert_report_close(g, r, rtol=1e-9)
+    assert np.array_equal(msim.mt_uniforms(8), oracle.mt_uniforms(8))
+
+
+def test_illness_death_doc_kats(msim, kats):
+    k = kats["illness_prev_1e5_cure02"]  # README.org:114-124
+    num = msim.callIllnessDeath(100000, cure=0.2)["prev"]["number"]
+    assert len(num) == k["rows"] and num.max() == k["max"] and round(num.mean()) == k["mean"]
+    le = msim.callIllnessDeath(10)["pt"]["pt"].sum() / 10  # test/test_microsimulation.R:1610
+    assert abs(le - kats["illness_death_n10_LE"]) < 1e-3
+    ev = msim.callSimplePerson2(100000)["events"]  # README.org:95-107
+    k2 = kats["simple2_events_1e5"]
+    assert len(ev["number"]) == k2["rows"] and ev["number"].max() == k2["max"]
+    assert [int((ev["event"] == e).sum()) for e in range(3)] == k2["by_event"]
+
+
+def test_reports_golden(msim, golden):
+    for name, rep in (("simple2_n20000", msim.callSimplePerson2(20000)),
+                      ("illness_n20000_cure01", msim.callIllnessDeath(20000, 0.1, 0.0)),
+                      ("illness_n20000_cure02_zsd05", msim.callIllnessDeath(20000, 0.2, 0.5))):
+        for tb in ("pt", "ut", "events", "prev"):
+            for k, v in rep[tb].items():
+                w = golden["%s_%s_%s" % (name, tb, k)]
+                if k in ("pt", "utility"):
+                    np.testing.assert_allclose(v, w, rtol=1e-9)
+                else:
+                    assert np.array_equal(v, w), (name, tb, k)
+
+
+def test_sequential_calls_continue_the_stream(msim, oracle):
+    """Two .Calls without re-seeding: the second continues R's stream (Rcpp::RNGScope)."""
+    import ctypes as C
+    from oracle.pyoracle import Table
+    msim.set_seed(777)
+    oracle.set_seed(777)
+    L = msim.load()
+    from microsimulation_b200._lib import Table as MT
+    for n in (333, 1000):
+        a, b = MT(), Table()
+        assert L.msim_callSimplePerson(C.c_int32(n), C.byref(a)) == 0
+        assert oracle.lib.oracle_callSimplePerson(C.c_int32(n), C.byref(b)) == 0
+        assert_rowlog_close(a.to_dict(), b.to_dict(), TIME_RTOL, end_col="endtime")
+        L.msim_table_free(C.byref(a))
+
+
+def test_simple_person_config2_properties(msim):
+    """BASELINE config 2 (n = 1e6): structure checks at full size."""
+    g = msim.callSimplePerson(10 ** 6)
+    ids = g["id"]
+    d = np.diff(ids)
+    assert ids[0] == 0 and ids[-1] == 10 ** 6 - 1 and ((d == 0) | (d == 1)).all()
+    per = np.bincount(ids.astype(int))
+    assert per.min() == 1 and per.max() == 2
+    last = np.r_[d == 1, True]
+    assert np.isin(g["event"][last], (0, 2)).all()  # toOtherDeath / toCancerDeath end a life
+    assert (g["event"][~last] == 1).all()           # a first of two rows is always toCancer
+
+
+# ------------------------------------------------------------------ calibration (config 5)
+
+def test_calibration_vs_oracle(msim, oracle, kats, golden):
+    g = msim.callCalibrationPerson(10, 500)["raw"]
+    r = oracle.callCalibrationPerson(10, 500)
+    assert list(g["DiseaseFree"][:2]) == kats["calibration_seed10_n500_DiseaseFree_first2"]
+    assert set(g) == set(r)
+    for k in r:
+        if k == "TimeAtRisk":
+            np.testing.assert_allclose(g[k], r[k], rtol=1e-12)
+        else:
+            assert np.array_equal(g[k], r[k]), k
+    g = msim.callCalibrationPerson(12345, 20000)["raw"]
+    for k in g:
+        w = golden["calib_seed12345_n20000_" + k]
+        if k == "TimeAtRisk":
+            np.testing.assert_allclose(g[k], w, rtol=1e-12)
+        else:
+            assert np.array_equal(g[k], w), k
+
+
+def test_calibration_sweep_vs_oracle(msim, oracle):
+    rs = np.random.RandomState(7)
+    pars = np.array([4, 0.5, 0.05, 10, 3, 0.5]) * (1 + 0.4 * (rs.rand(6, 6) - 0.5))
+    pars[1, 1] = 0.0  # sigm1 = 0: rnorm draws nothing
+    pars[2, 5] = 0.0  # tau3 = 0
+    pars[3, 2] = 0.0  # p2 = 0: nobody has disease potential -> PreClinical/Clinical never observed
+    g = msim.calibration_sweep(12345, pars, 40000, first_person=1000)
+    r = oracle.calibration_sweep(12345, 1000, 40000, pars)
+    for a, b in zip(g, r):
+        assert set(a) == set(b)
+        for k in b:
+            if k == "TimeAtRisk":
+                np.testing.assert_allclose(a[k], b[k], rtol=1e-12)
+            else:
+                assert np.array_equal(a[k], b[k]), k
+
+
+def test_package_seed_advances_like_the_reference(msim, oracle):
+    """Two calibration calls after ONE set.user.Random.seed: the second `new Rng()` is the next stream."""
+    import ctypes as C
+    msim.set_user_random_seed(99)
+    oracle.set_user_random_seed(99)
+    from microsimulation_b200._lib import Calibration as MC
+    from oracle.pyoracle import Calibration as OC
+    par = (C.c_double * 6)(4, 0.5, 0.05, 10, 3, 0.5)
+    for _ in range(2):
+        a, b = MC(), OC()
+        assert msim.load().msim_callCalibrationSimulation(C.c_int32(3000), par, C.byref(a)) == 0
+        assert oracle.lib.oracle_callCalibrationSimulation(C.c_int32(3000), par, C.byref(b)) == 0
+        assert list(a.occupancy) == list(b.occupancy)
+
+
+def test_kernels_were_launched(msim):
+    before = msim.launch_count()
+    msim.callPersonSimulation(1000)
+    assert msim.launch_count() > before

@@ -1,0 +1,170 @@
+"""CPU-only checks of the product's host logic and of the device engine's
+per-person code compiled for the host (tests/host_emulation): RNG jump tables
+and strides, the event heap, report accumulation, the sequential-stream offset
+resolution.  No kernel runs here; the GPU parity tests are tests/test_gpu_parity.py."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_report_close
+from oracle.pyoracle import Calibration, PersonShard, Report, Table
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import microsimulation_b200 as m
+    L = m.load()
+    hdr = open(os.path.join(ROOT, "include", "msim.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(msim_[a-zA-Z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 30
+    for sym in declared:
+        assert hasattr(L, sym), "libmsim_b200.so does not export " + sym
+    assert sorted(m.SYMBOLS) == declared
+    assert b"sm_100a" in L.msim_version()
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    import microsimulation_b200 as m
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(m.MsimError) as e:
+        m.callPersonSimulation(5)
+    assert e.value.code == -1  # MSIM_ERR_NO_DEVICE
+    with pytest.raises(m.MsimError):
+        m.callIllnessDeath(5)
+
+
+def test_product_never_touches_the_oracle():
+    """No import / include / dlopen of anything under oracle/ (or of the host emulation) in the product."""
+    pkg = os.path.join(ROOT, "microsimulation_b200")
+    bad = re.compile(r"(#include\s*[\"<][^\n]*oracle|import\s+oracle|from\s+oracle|pyoracle|libmsim_oracle|"
+                     r"host_emulation/|libmsim_emu)")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not bad.search(src), f
+
+
+def test_host_rng_state_machine_matches_oracle(oracle):
+    """.C table semantics: package seed, default stream, advance.substream (src/microsimulation.cc:33-75)."""
+    import microsimulation_b200 as m
+    m.set_user_random_seed(12345)
+    oracle.set_user_random_seed(12345)
+    assert m.user_random_seed()[1:] == [int(x) for x in oracle.get_user_random_seed()]
+    for _ in range(3):
+        m.next_user_random_substream()
+        oracle.next_rng_substream()
+    assert m.user_random_seed()[1:] == [int(x) for x in oracle.get_user_random_seed()]
+    for seed, n in ((12345, 1000), ([1, 2, 3, 4, 5, 6], 99999999), (12345, -7), ([407, 9, 8, 7, 6, 5, 4], 3)):
+        assert m.advance_substream(seed, n) == oracle.rng_advance_substream(seed, n)
+    with pytest.raises(m.MsimError) as e:
+        m.set_user_random_seed([0, 0, 0, 1, 1, 1])
+    assert e.value.code == -5
+
+
+def test_mt_set_seed_matches_oracle(oracle, emu):
+    import microsimulation_b200 as m
+    m.set_seed(12345)
+    st = (C.c_uint32 * 625)()
+    emu.emu_mt_set_seed(C.c_uint32(12345), st)
+    assert np.array_equal(m.mt_state(), np.array(st[:], dtype=np.uint32))
+    u = np.empty(1500)
+    emu.emu_mt_uniforms(st, C.c_int64(1500), u.ctypes.data_as(C.POINTER(C.c_double)))
+    oracle.set_seed(12345)
+    assert np.array_equal(u, oracle.mt_uniforms(1500))  # crosses two three-wave regenerations
+    m.set_mt_state(m.mt_state())
+    with pytest.raises(m.MsimError):
+        m.set_mt_state([0] * 625)
+
+
+@pytest.mark.parametrize("first,n,draws,grid", [(0, 3000, 4, 1), (5, 5000, 8, 7), (99999990, 700, 3, 2)])
+def test_emulated_substream_uniforms(oracle, emu, first, n, draws, grid):
+    seed = (C.c_double * 6)(*[12345.0] * 6)
+    out = np.empty(n * draws)
+    emu.emu_rng_uniforms(seed, C.c_int64(first), C.c_int64(n), C.c_int32(draws), C.c_int(grid),
+                         out.ctypes.data_as(C.POINTER(C.c_double)))
+    assert np.array_equal(out.reshape(n, draws), oracle.rng_uniforms(12345, first, n, draws))
+
+
+@pytest.mark.parametrize("first,n,grid", [(0, 20000, 3), (12345, 5000, 40), (0, 1, 1), (7, 255, 2), (0, 257, 1)])
+def test_emulated_person_r(oracle, emu, first, n, grid):
+    """Same templates as the kernel, host libm: rows must be BIT-exact, report sums to 1e-12."""
+    seed = (C.c_double * 6)(*[12345.0] * 6)
+    sh = PersonShard(seed, first, n, 7, 0.03)
+    t, r, cnt = Table(), Report(), (C.c_double * 9)()
+    assert emu.emu_person_run(C.byref(sh), C.c_int(grid), C.byref(t), cnt, C.byref(r)) == 0
+    e, er = t.to_dict(), r.to_dict()
+    ref = oracle.person_run(12345, first, n, rowlog=True, report=True, discount_rate=0.03)
+    for k in e:
+        assert np.array_equal(e[k], ref["rowlog"][k]), k
+    assert np.array_equal(np.array(cnt[:8]), ref["counts"][:8])
+    assert_report_close(er, ref["report"], rtol=1e-12)
+    emu.emu_table_free(C.byref(t))
+    emu.emu_report_free(C.byref(r))
+
+
+@pytest.mark.parametrize("n", [0, 1, 10, 700, 5000, 60000])
+def test_emulated_sequential_stream_models(oracle, emu, n):
+    """Per-position draw counts + chunked chain resolution == the reference's person-after-person consumption."""
+    st = (C.c_uint32 * 625)()
+    emu.emu_mt_set_seed(C.c_uint32(12345), st)
+    t = Table()
+    assert emu.emu_sequential(0, C.c_int64(n), C.c_double(0), C.c_double(0), st, C.byref(t), None) == 0
+    e, ref = t.to_dict(), oracle.callSimplePerson(n)
+    for k in ref:
+        assert np.array_equal(e[k], ref[k]), k
+    # R's generator is left exactly where the reference leaves it
+    u = np.empty(5)
+    emu.emu_mt_uniforms(st, C.c_int64(5), u.ctypes.data_as(C.POINTER(C.c_double)))
+    assert np.array_equal(u, oracle.mt_uniforms(5))
+    emu.emu_mt_set_seed(C.c_uint32(12345), st)
+    r = Report()
+    assert emu.emu_sequential(1, C.c_int64(n), C.c_double(0), C.c_double(0), st, None, C.byref(r)) == 0
+    assert_report_close(r.to_dict(), oracle.callSimplePerson2(n), rtol=1e-13)
+    for cure, zsd in ((0.1, 0.0), (0.2, 0.0), (0.9, 0.0), (0.1, 0.5)):
+        emu.emu_mt_set_seed(C.c_uint32(12345), st)
+        r = Report()
+        assert emu.emu_sequential(2, C.c_int64(n), C.c_double(cure), C.c_double(zsd), st, None, C.byref(r)) == 0
+        assert_report_close(r.to_dict(), oracle.callIllnessDeath(n, cure, zsd), rtol=1e-13)
+
+
+def test_emulated_sequential_from_mid_batch_state(oracle, emu):
+    """The MT position need not be at a regeneration boundary: a second call continues where the first
+    stopped, on both sides (Rcpp::RNGScope writes R's state back, illness-death.cpp:75)."""
+    st = (C.c_uint32 * 625)()
+    emu.emu_mt_set_seed(C.c_uint32(42), st)
+    oracle.set_seed(42)
+    t1, t1_ref = Table(), Table()
+    assert emu.emu_sequential(0, C.c_int64(400), C.c_double(0), C.c_double(0), st, C.byref(t1), None) == 0
+    assert oracle.lib.oracle_callSimplePerson(C.c_int32(400), C.byref(t1_ref)) == 0
+    assert 1 <= st[0] <= 624
+    t2, t2_ref = Table(), Table()
+    assert emu.emu_sequential(0, C.c_int64(300), C.c_double(0), C.c_double(0), st, C.byref(t2), None) == 0
+    assert oracle.lib.oracle_callSimplePerson(C.c_int32(300), C.byref(t2_ref)) == 0
+    a, b = t2.to_dict(), t2_ref.to_dict()
+    for k in b:
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_emulated_calibration(oracle, emu):
+    seed = (C.c_double * 6)(*[10.0] * 6)
+    par = (C.c_double * 6)(4, 0.5, 0.05, 10, 3, 0.5)
+    c = Calibration()
+    assert emu.emu_calibration(seed, C.c_int64(0), C.c_int64(500), par, C.c_int(2), C.byref(c)) == 0
+    got, ref = c.to_dict(), oracle.callCalibrationPerson(10, 500)
+    assert set(got) == set(ref)
+    for k in ref:
+        assert np.array_equal(got[k], ref[k]), k
+    # sigm1 = 0: rnorm draws nothing; tau3 = 0 likewise (calibperson-r.cc:102, 152)
+    par0 = (C.c_double * 6)(4, 0.0, 0.3, 10, 3, 0.0)
+    assert emu.emu_calibration(seed, C.c_int64(100), C.c_int64(2000), par0, C.c_int(3), C.byref(c)) == 0
+    ref = oracle.calibration_sweep(10, 100, 2000, [[4, 0.0, 0.3, 10, 3, 0.0]])[0]
+    got = c.to_dict()
+    assert set(got) == set(ref)
+    for k in ref:
+        assert np.array_equal(got[k], ref[k]), k
