@@ -34,7 +34,7 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
   MrgJump *d_lo = nullptr, *d_hi = nullptr;
-  DevBuf rowlog, tiles, dense, small, mt_words, len, starts, chain_exit, chain_count, chain_entry, chain_base, calib_out,
+  DevBuf rowlog, prov_start, prov_end, prov_meta, tile_count, partial, dense, small, mt_words, len, starts, chain_exit, chain_count, chain_entry, chain_base, calib_out,
       calib_par, uniforms;
   HostRngState rng;
   // last cohort run
@@ -42,6 +42,9 @@ struct Ctx {
   ReportGeom last_geom;
   unsigned last_outputs = 0;
   bool last_simple_names = false;
+  int64_t want_capacity = 0;
+  int64_t last_n = 0, last_first = 0;
+  int last_max_rows = 0;
   int last_cells = 0;  // dense report cells of the last run (0 when no report was requested)
   bool have_last = false;
   float last_ms = 0.f;
@@ -203,7 +206,6 @@ int cohort_prepare(CohortParams<typename Traits::Consts> &p, const uint32_t stre
   if ((rc = ensure(g.small, 16 * sizeof(double)))) return rc;
   CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
   SmallView sv = small_view();
-  p.n_rows = sv.n_rows;
   p.error = sv.error;
   // one accumulator vector: the dense report cells (if requested) followed by the N_COUNTS count cells,
   // so that a single all-reduce merges everything a shard produces
@@ -214,35 +216,69 @@ int cohort_prepare(CohortParams<typename Traits::Consts> &p, const uint32_t stre
   p.counts = p.dense + cells;
   g.last_cells = cells;
   if (p.outputs & OUT_ROWLOG) {
-    int64_t tiles = (p.n + BLOCK - 1) / BLOCK;
-    if ((rc = ensure(g.tiles, sizeof(unsigned long long) * (size_t)std::max<int64_t>(tiles, 1)))) return rc;
-    CK(cudaMemsetAsync(g.tiles.p, 0, sizeof(unsigned long long) * (size_t)std::max<int64_t>(tiles, 1), g.stream));
-    p.tile_status = (unsigned long long *)g.tiles.p;
-    if ((rc = ensure(g.rowlog, sizeof(double) * 5 * (size_t)std::max<int64_t>(p.capacity, 1)))) return rc;
-    p.rowlog = (double *)g.rowlog.p;
+    const int64_t wtiles = std::max<int64_t>((p.n + 31) / 32, 1);
+    const size_t slots = (size_t)wtiles * 32 * Traits::MAX_ROWS;
+    if ((rc = ensure(g.prov_start, sizeof(double) * slots))) return rc;
+    if ((rc = ensure(g.prov_end, sizeof(double) * slots))) return rc;
+    if ((rc = ensure(g.prov_meta, sizeof(int) * slots))) return rc;
+    // the kernel's last block tile may be partial: its idle warps still store a 0 count
+    if ((rc = ensure(g.tile_count, sizeof(int) * (size_t)(wtiles + WARPS)))) return rc;
+    if ((rc = ensure(g.partial, sizeof(unsigned long long) * (size_t)((wtiles + EXPAND_TILES - 1) / EXPAND_TILES + 1)))) return rc;
+    if ((rc = ensure(g.rowlog, sizeof(double) * 5 * (size_t)std::max<int64_t>(g.want_capacity, 1)))) return rc;
+    p.prov_start = (double *)g.prov_start.p;
+    p.prov_end = (double *)g.prov_end.p;
+    p.prov_meta = (int *)g.prov_meta.p;
+    p.tile_count = (int *)g.tile_count.p;
   }
   *grid_out = grid;
   *smem_out = smem;
   return MSIM_OK;
 }
 
+// second pass of the row log: tile counts -> offsets -> final columns
+int rowlog_expand(int64_t n, int64_t first_person, int max_rows, int64_t capacity) {
+  ExpandParams e;
+  memset(&e, 0, sizeof e);
+  e.prov_start = (const double *)g.prov_start.p;
+  e.prov_end = (const double *)g.prov_end.p;
+  e.prov_meta = (const int *)g.prov_meta.p;
+  e.tile_count = (const int *)g.tile_count.p;
+  e.n_warp_tiles = (n + 31) / 32;
+  e.tile_cap = 32 * max_rows;
+  e.partial = (unsigned long long *)g.partial.p;
+  e.n_rows = small_view().n_rows;
+  e.n_chunks = (e.n_warp_tiles + EXPAND_TILES - 1) / EXPAND_TILES;
+  e.first_person = first_person;
+  e.rowlog = (double *)g.rowlog.p;
+  e.capacity = capacity;
+  if (e.n_chunks == 0) return MSIM_OK;
+  rowlog_partial_kernel<<<(unsigned)e.n_chunks, 256, 0, g.stream>>>(e);
+  CK(cudaGetLastError());
+  rowlog_chunk_scan_kernel<<<1, 1024, 0, g.stream>>>(e);
+  CK(cudaGetLastError());
+  rowlog_expand_kernel<<<(unsigned)e.n_chunks, 256, 0, g.stream>>>(e);
+  CK(cudaGetLastError());
+  g.launches += 3;
+  return MSIM_OK;
+}
+
 template <class Traits, bool STREAM>
-int cohort_fire(CohortParams<typename Traits::Consts> &p, int grid, size_t smem) {
+int cohort_fire(CohortParams<typename Traits::Consts> &p, int grid, size_t smem, int64_t capacity) {
   if (p.n > 0) {
-    auto kern = cohort_kernel<Traits, STREAM>;
-    if (p.outputs & OUT_ROWLOG) {
-      // the tile look-back needs every block of the grid resident: a cooperative launch enforces it
-      void *args[] = {(void *)&p};
-      CK(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(BLOCK), args, smem, g.stream));
-    } else {
-      kern<<<grid, BLOCK, smem, g.stream>>>(p);
-      CK(cudaGetLastError());
-    }
+    cohort_kernel<Traits, STREAM><<<grid, BLOCK, smem, g.stream>>>(p);
+    CK(cudaGetLastError());
     g.launches++;
+    if (p.outputs & OUT_ROWLOG) {
+      int rc = rowlog_expand(p.n, p.first_person, Traits::MAX_ROWS, capacity);
+      if (rc) return rc;
+    }
   }
   g.last_geom = p.geom;
   g.last_outputs = p.outputs;
-  g.last_capacity = p.capacity;
+  g.last_capacity = capacity;
+  g.last_n = p.n;
+  g.last_first = p.first_person;
+  g.last_max_rows = Traits::MAX_ROWS;
   g.have_last = true;
   return MSIM_OK;
 }
@@ -294,6 +330,15 @@ int fetch_report(msim_report *out) {
   return MSIM_OK;
 }
 
+// the guessed row capacity was too small: the packed rows are still there, expand again
+int reexpand(int64_t rows) {
+  int rc;
+  if ((rc = ensure(g.rowlog, sizeof(double) * 5 * (size_t)rows))) return rc;
+  if ((rc = rowlog_expand(g.last_n, g.last_first, g.last_max_rows, rows))) return rc;
+  g.last_capacity = rows;
+  return finish_run(nullptr);
+}
+
 // ---- person-r
 
 int person_enqueue(const msim_person_shard *sh, int64_t capacity_override) {
@@ -308,7 +353,8 @@ int person_enqueue(const msim_person_shard *sh, int64_t capacity_override) {
   p.outputs = sh->outputs & 7u;
   p.consts = person_r::make_consts();
   p.geom = ages_geom(person_r::N_STATE, person_r::N_EVENT, sh->discount_rate);
-  p.capacity = capacity_override > 0 ? capacity_override : rowlog_capacity_guess(sh->n, person_r::MAX_ROWS, 1.25);
+  const int64_t capacity = capacity_override > 0 ? capacity_override : rowlog_capacity_guess(sh->n, person_r::MAX_ROWS, 1.25);
+  g.want_capacity = capacity;
   uint32_t state[6];
   seed_to_u32(sh->seed, state);
   g.last_simple_names = false;
@@ -316,7 +362,7 @@ int person_enqueue(const msim_person_shard *sh, int64_t capacity_override) {
   size_t smem;
   if ((rc = cohort_prepare<PersonTraits, false>(p, state, &grid, &smem))) return rc;
   CK(cudaEventRecord(g.ev0, g.stream));
-  if ((rc = cohort_fire<PersonTraits, false>(p, grid, smem))) return rc;
+  if ((rc = cohort_fire<PersonTraits, false>(p, grid, smem, capacity))) return rc;
   CK(cudaEventRecord(g.ev1, g.stream));
   g.timing_pending = true;
   return MSIM_OK;
@@ -327,9 +373,8 @@ int person_run(const msim_person_shard *sh) {
   if ((rc = person_enqueue(sh, 0))) return rc;
   int64_t rows = 0;
   if ((rc = finish_run(&rows))) return rc;
-  if ((sh->outputs & OUT_ROWLOG) && rows > g.last_capacity) {  // rare: rerun with the exact size
-    if ((rc = person_enqueue(sh, rows))) return rc;
-    if ((rc = finish_run(&rows))) return rc;
+  if ((sh->outputs & OUT_ROWLOG) && rows > g.last_capacity) {  // rare: redo the expand pass with the exact size
+    if ((rc = reexpand(rows))) return rc;
   }
   return MSIM_OK;
 }
@@ -387,7 +432,8 @@ int sequential_run(int64_t n, const typename Traits::Consts &consts, int max_dra
   p.outputs = outputs;
   p.consts = consts;
   p.geom = geom;
-  p.capacity = rowlog_capacity_guess(n, max_rows, mean_rows);
+  const int64_t capacity = rowlog_capacity_guess(n, max_rows, mean_rows);
+  g.want_capacity = capacity;
   p.mt_words = (const uint32_t *)g.mt_words.p;
   p.mt_end = mt_end;
   p.starts = (const int64_t *)g.starts.p;
@@ -404,14 +450,14 @@ int sequential_run(int64_t n, const typename Traits::Consts &consts, int max_dra
     CK(cudaGetLastError());
     g.launches++;
   }
-  if ((rc = cohort_fire<Traits, true>(p, grid, smem))) return rc;
+  if ((rc = cohort_fire<Traits, true>(p, grid, smem, capacity))) return rc;
   CK(cudaEventRecord(g.ev1, g.stream));
   g.timing_pending = true;
   int64_t rows = 0;
   if ((rc = finish_run(&rows))) return rc;
   int64_t end_word = 0;
   CK(cudaMemcpy(&end_word, small_view().end_word, sizeof end_word, cudaMemcpyDeviceToHost));
-  if ((outputs & OUT_ROWLOG) && rows > g.last_capacity) return fail(MSIM_ERR_CUDA, "row log capacity exceeded");
+  if ((outputs & OUT_ROWLOG) && rows > g.last_capacity && (rc = reexpand(rows))) return rc;
   // leave R's generator where the reference would: after the last person's last draw
   if (n > 0 && end_word > 0) {
     int64_t batch = (end_word - 1) / 624;
@@ -450,7 +496,7 @@ int msim_init(int device) {
 void msim_shutdown(void) {
   if (!g.inited) return;
   cudaStreamSynchronize(g.stream);
-  DevBuf *bufs[] = {&g.rowlog, &g.tiles, &g.dense, &g.small, &g.mt_words, &g.len, &g.starts, &g.chain_exit,
+  DevBuf *bufs[] = {&g.rowlog, &g.prov_start, &g.prov_end, &g.prov_meta, &g.tile_count, &g.partial, &g.dense, &g.small, &g.mt_words, &g.len, &g.starts, &g.chain_exit,
                     &g.chain_count, &g.chain_entry, &g.chain_base, &g.calib_out, &g.calib_par, &g.uniforms};
   for (DevBuf *b : bufs) {
     if (b->p) cudaFree(b->p);

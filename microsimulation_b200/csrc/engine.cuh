@@ -98,6 +98,93 @@ struct EventHeap {
     t[k] = tx;
     meta[k] = mx;
   }
+
+  // visit the pending entries in array order (Sim::ignore_event's scan)
+  template <class F>
+  MSIM_DEV void for_each_meta(F f) {
+    for (int i = 0; i < n; i++) f(meta[i]);
+  }
+};
+
+// CAP = 4: the same heap, written out as straight-line code over four scalar
+// slots so that it lives entirely in registers (no dynamically indexed local
+// array).  Every built model except the calibration example keeps at most
+// three actions pending.  Comparisons and moves are exactly those heap.h
+// performs for sizes 1..4, so ties resolve identically.
+template <>
+struct EventHeap<4> {
+  double t0, t1, t2, t3;
+  int m0, m1, m2, m3;
+  int n;
+
+  MSIM_DEV static bool before(double ta, int ma, double tb, int mb) {
+    return ta < tb || (ta == tb && meta_prio(ma) < meta_prio(mb));
+  }
+  MSIM_DEV static void swap(double &ta, int &ma, double &tb, int &mb) {
+    double t = ta;
+    ta = tb;
+    tb = t;
+    int m = ma;
+    ma = mb;
+    mb = m;
+  }
+
+  MSIM_DEV bool insert(double time, int m) {
+    if (n == 0) {
+      t0 = time;
+      m0 = m;
+    } else if (n == 1) {  // slot 1, parent 0
+      t1 = time;
+      m1 = m;
+      if (before(t1, m1, t0, m0)) swap(t0, m0, t1, m1);
+    } else if (n == 2) {  // slot 2, parent 0
+      t2 = time;
+      m2 = m;
+      if (before(t2, m2, t0, m0)) swap(t0, m0, t2, m2);
+    } else if (n == 3) {  // slot 3, parent 1, grandparent 0
+      t3 = time;
+      m3 = m;
+      if (before(t3, m3, t1, m1)) {
+        swap(t1, m1, t3, m3);
+        if (before(t1, m1, t0, m0)) swap(t0, m0, t1, m1);
+      }
+    } else {
+      return false;
+    }
+    n++;
+    return true;
+  }
+
+  MSIM_DEV void pop_first(double &time, int &m) {
+    time = t0;
+    m = m0;
+    if (n == 2) {  // last (slot 1) becomes the root, nothing below it
+      t0 = t1;
+      m0 = m1;
+    } else if (n == 3) {  // slot 2 -> root; only child is slot 1
+      t0 = t2;
+      m0 = m2;
+      if (before(t1, m1, t0, m0)) swap(t0, m0, t1, m1);
+    } else if (n == 4) {  // slot 3 -> root; children 1 and 2, both leaves afterwards
+      t0 = t3;
+      m0 = m3;
+      if (before(t2, m2, t1, m1)) {
+        if (before(t2, m2, t0, m0)) swap(t0, m0, t2, m2);
+      } else {
+        if (before(t1, m1, t0, m0)) swap(t0, m0, t1, m1);
+      }
+    }
+    n--;
+  }
+
+  // visit the pending entries in array order (Sim::ignore_event's scan)
+  template <class F>
+  MSIM_DEV void for_each_meta(F f) {
+    if (n > 0) f(m0);
+    if (n > 1) f(m1);
+    if (n > 2) f(m2);
+    if (n > 3) f(m3);
+  }
 };
 
 // CRTP base: `struct Person : cProcess<Person, Src, 4> { void init(); void
@@ -135,10 +222,9 @@ struct cProcess {
   // Cancel(pred) -> Sim::ignore_event: mark matching A_Event entries A_Ignore
   template <class Pred>
   MSIM_DEV void Cancel(Pred pred) {
-    for (int i = 0; i < actions.n; i++) {
-      int m = actions.meta[i];
-      if (meta_type(m) == A_Event && pred(meta_kind(m))) actions.meta[i] = (int)(((uint32_t)m & 0x3fffffffu) | ((uint32_t)A_Ignore << 30));
-    }
+    actions.for_each_meta([&](int &m) {
+      if (meta_type(m) == A_Event && pred(meta_kind(m))) m = (int)(((uint32_t)m & 0x3fffffffu) | ((uint32_t)A_Ignore << 30));
+    });
   }
   MSIM_DEV void RemoveKind(int kind) {
     Cancel([kind](int k) { return k == kind; });

@@ -15,11 +15,10 @@
 //     resolved chunk-wise (chain_*_kernel), and then the n real persons run in
 //     parallel from their resolved offsets;
 //   * the life-history row log must come out in person order with a
-//     data-dependent number of rows per person: each tile does a block scan of
-//     its row counts and obtains its global row offset with a decoupled
-//     look-back over per-tile status words (single pass, no second simulation);
-//     rows are compacted in shared memory and stored with coalesced, linear
-//     writes, column by column;
+//     data-dependent number of rows per person: warps pack their rows into a
+//     provisional area at fixed offsets, and a bandwidth-bound second pass scans
+//     the per-tile counts and expands them into the final columns (no spin
+//     waits, no cross-warp synchronisation inside the simulation kernel);
 //   * report tables and per-kind counts accumulate in shared memory and are
 //     flushed once per block with `red.global.add.f64`.
 #pragma once
@@ -39,15 +38,6 @@ constexpr unsigned OUT_ROWLOG = 1u, OUT_REPORT = 2u, OUT_COUNTS = 4u;
 constexpr int N_COUNTS = 9;  // up to 8 per-kind counts + sum(endTime)
 
 // ---- small device helpers ------------------------------------------------
-
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
 // dense accumulators in shared memory: [0, n_f) doubles, [n_f, total) ints
 struct SharedAcc {
@@ -141,6 +131,15 @@ struct SimpleTraits {
 };
 
 // ---- cohort kernel: run n persons, emit row log / report / counts --------
+//
+// Row log.  Rows must come out in person order with a data-dependent number of
+// rows per person.  The simulation kernel never synchronises across warps for
+// this: each warp owns "warp tiles" of 32 consecutive persons, stages its rows
+// in shared memory, packs them with a warp scan and stores them into a
+// provisional area at a FIXED offset (tile * 32 * MAX_ROWS) together with the
+// tile's row count.  A second, bandwidth-bound pass (rowlog_expand_kernel)
+// scans the tile counts and expands the packed rows (start, end, meta = 20 B)
+// into the final five f64 columns with coalesced stores.
 
 template <class Consts>
 struct CohortParams {
@@ -148,32 +147,29 @@ struct CohortParams {
   StreamStart st;
   // sequential-stream regime
   const uint32_t *mt_words;
-  int64_t mt_end;           // number of valid words
-  const int64_t *starts;    // word index of person i's first draw
+  int64_t mt_end;         // number of valid words
+  const int64_t *starts;  // word index of person i's first draw
   int64_t first_person, n;
   unsigned outputs;  // OUT_*
   Consts consts;
-  // row log: 5 columns (end time, event, id, startTime, state), stride `capacity`
-  double *rowlog;
-  int64_t capacity;
-  unsigned long long *tile_status;  // zeroed before launch
-  unsigned long long *n_rows;       // total rows (may exceed capacity)
+  // provisional packed rows: capacity 32*MAX_ROWS per warp tile
+  double *prov_start, *prov_end;
+  int *prov_meta;
+  int *tile_count;  // rows per warp tile
   ReportGeom geom;
   double *dense;   // dense report accumulators (global, zeroed before launch)
   double *counts;  // N_COUNTS doubles
   int *error;      // first error code seen
 };
 
-constexpr unsigned long long ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, ST_MASK = (1ull << 62) - 1;
-
 template <class SrcT, int MAXR>
 struct CohortEnv {
   typedef SrcT Src;
   Src src;
   unsigned outputs;
-  // per-thread row scratch (at most MAXR rows per person)
-  double r_start[MAXR], r_end[MAXR];
-  int r_meta[MAXR];
+  // this thread's row slots in shared memory: slot k at [k*BLOCK]
+  double *s_start, *s_end;
+  int *s_meta;
   int nrows;
   const ReportGeom *geom;
   SharedAcc acc;
@@ -187,9 +183,9 @@ struct CohortEnv {
     }
     if (outputs & OUT_ROWLOG) {
       if (nrows < MAXR) {
-        r_start[nrows] = start;
-        r_end[nrows] = end;
-        r_meta[nrows] = (state << 8) | kind;
+        s_start[nrows * BLOCK] = start;
+        s_end[nrows * BLOCK] = end;
+        s_meta[nrows * BLOCK] = (state << 8) | kind;
       }
       nrows++;
     }
@@ -208,58 +204,23 @@ struct NullEnv {
   __device__ __forceinline__ void report(int, int, double, double) {}
 };
 
-// Exclusive offset of this tile in the global row log (decoupled look-back).
-// Called by warp 0 only; `total` is the tile's own row count.
-__device__ __forceinline__ unsigned long long tile_lookback(unsigned long long *status, int64_t tile,
-                                                            unsigned long long total) {
-  const int lane = threadIdx.x & 31;
-  if (tile == 0) {
-    if (lane == 0) st_relaxed_u64(&status[0], ST_PREFIX | total);
-    return 0;
-  }
-  if (lane == 0) st_relaxed_u64(&status[tile], ST_AGG | total);
-  unsigned long long excl = 0;
-  int64_t j = tile - 1;  // lane L inspects tile j - L
-  for (;;) {
-    int64_t mine = j - lane;
-    unsigned long long v = ST_PREFIX;  // tiles before 0 act as an empty prefix
-    if (mine >= 0) {
-      do {
-        v = ld_relaxed_u64(&status[mine]);
-      } while ((v >> 62) == 0);
-    }
-    unsigned has_prefix = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-    int first = has_prefix ? (__ffs(has_prefix) - 1) : 32;  // nearest predecessor holding a full prefix
-    unsigned long long contrib = (lane <= first) ? (v & ST_MASK) : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-    excl += contrib;
-    if (has_prefix) break;
-    j -= 32;
-  }
-  if (lane == 0) st_relaxed_u64(&status[tile], ST_PREFIX | (excl + total));
-  return excl;
-}
-
 template <class Traits, bool STREAM>
-__global__ void __launch_bounds__(BLOCK, 2) cohort_kernel(CohortParams<typename Traits::Consts> p) {
+__global__ void __launch_bounds__(BLOCK, 3) cohort_kernel(const __grid_constant__ CohortParams<typename Traits::Consts> p) {
   typedef typename std::conditional<STREAM, StreamSource, MrgSource>::type Src;
   typedef CohortEnv<Src, Traits::MAX_ROWS> Env;
   constexpr int MAXR = Traits::MAX_ROWS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // shared layout: [dense doubles | compact rows (start, end, meta) | dense ints]
+  // shared layout: [dense doubles | row slots start, end | row slots meta | dense ints]
   const int total = (p.outputs & OUT_REPORT) ? p.geom.total : 0;
   const int n_f = (p.outputs & OUT_REPORT) ? p.geom.off_touch : 0;
   double *s_f = reinterpret_cast<double *>(smem_raw);
-  constexpr int CROWS = BLOCK * MAXR;
-  double *c_start = s_f + n_f;
-  double *c_end = c_start + CROWS;
-  int *c_meta = reinterpret_cast<int *>(c_end + CROWS);
-  int *s_i = c_meta + CROWS;
+  constexpr int SLOTS = BLOCK * MAXR;
+  double *slot_start = s_f + n_f;
+  double *slot_end = slot_start + SLOTS;
+  int *slot_meta = reinterpret_cast<int *>(slot_end + SLOTS);
+  int *s_i = slot_meta + SLOTS;
   __shared__ int s_kind[8];
   __shared__ double s_sum[WARPS];
-  __shared__ int s_warp_tot[WARPS];
-  __shared__ unsigned long long s_tile_base;
   __shared__ int s_error;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -272,6 +233,9 @@ __global__ void __launch_bounds__(BLOCK, 2) cohort_kernel(CohortParams<typename 
   env.acc.n_f = n_f;
   env.s_kind = s_kind;
   env.sum_end = 0.0;
+  env.s_start = slot_start + tid;
+  env.s_end = slot_end + tid;
+  env.s_meta = slot_meta + tid;
   if (p.outputs & OUT_REPORT) shared_acc_clear(env.acc, total);
   if (tid < 8) s_kind[tid] = 0;
   if (tid == 0) s_error = 0;
@@ -279,7 +243,8 @@ __global__ void __launch_bounds__(BLOCK, 2) cohort_kernel(CohortParams<typename 
 
   Mrg32k3a sub;
   if constexpr (!STREAM) sub = thread_start_state(p.st, blockIdx.x * BLOCK + tid);
-  const int64_t n_tiles = (p.n + BLOCK - 1) / BLOCK;
+  const int64_t n_tiles = (p.n + BLOCK - 1) / BLOCK;  // block tiles; warp tile = tile*WARPS + warp
+  int err = 0;
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t idx = tile * BLOCK + tid;
@@ -295,64 +260,37 @@ __global__ void __launch_bounds__(BLOCK, 2) cohort_kernel(CohortParams<typename 
       }
       typename Traits::template Model<Env> person(env, p.consts, p.first_person + idx);
       person.run();
-      int err = person.error_;
+      if (person.error_) err = person.error_;
       if (env.nrows > MAXR) err = -4;
       if constexpr (STREAM) {
         if (env.src.overrun) err = -6;
       }
-      if (err) atomicCAS(&s_error, 0, err);
     }
     if constexpr (!STREAM) sub.jump(p.st.stride);
 
     if (p.outputs & OUT_ROWLOG) {
-      // block exclusive scan of the per-person row counts
-      int cnt = env.nrows > MAXR ? MAXR : env.nrows;
+      // pack this warp's rows: exclusive scan of the per-person row counts
+      const int cnt = env.nrows > MAXR ? MAXR : env.nrows;
       int incl = cnt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
       }
-      if (lane == 31) s_warp_tot[warp] = incl;
-      __syncthreads();  // also orders the previous tile's reads of c_* before this tile's writes
-      int woff = 0, tot = 0;
-#pragma unroll
-      for (int w = 0; w < WARPS; w++) {
-        int t = s_warp_tot[w];
-        if (w < warp) woff += t;
-        tot += t;
+      const int tot = __shfl_sync(0xffffffffu, incl, 31);
+      const int off = incl - cnt;
+      const int64_t wt = tile * WARPS + warp;
+      const int64_t base = wt * (32 * MAXR);
+      for (int r = 0; r < cnt; r++) {
+        p.prov_start[base + off + r] = env.s_start[r * BLOCK];
+        p.prov_end[base + off + r] = env.s_end[r * BLOCK];
+        p.prov_meta[base + off + r] = (lane << 16) | env.s_meta[r * BLOCK];
       }
-      const int off = woff + incl - cnt;
-      for (int k = 0; k < cnt; k++) {
-        c_start[off + k] = env.r_start[k];
-        c_end[off + k] = env.r_end[k];
-        c_meta[off + k] = (tid << 16) | env.r_meta[k];
-      }
-      if (warp == 0) {
-        unsigned long long base = tile_lookback(p.tile_status, tile, (unsigned long long)tot);
-        if (lane == 0) {
-          s_tile_base = base;
-          if (tile == n_tiles - 1) *p.n_rows = base + (unsigned long long)tot;
-        }
-      }
-      __syncthreads();
-      const unsigned long long base = s_tile_base;
-      const double id0 = (double)(p.first_person + tile * BLOCK);
-      for (int r = tid; r < tot; r += BLOCK) {
-        unsigned long long g = base + r;
-        if (g < (unsigned long long)p.capacity) {
-          int m = c_meta[r];
-          p.rowlog[0 * p.capacity + g] = c_end[r];
-          p.rowlog[1 * p.capacity + g] = (double)(m & 0xff);
-          p.rowlog[2 * p.capacity + g] = id0 + (double)(m >> 16);
-          p.rowlog[3 * p.capacity + g] = c_start[r];
-          p.rowlog[4 * p.capacity + g] = (double)((m >> 8) & 0xff);
-        }
-      }
-      // the next tile's first __syncthreads() protects c_* against reuse
+      if (lane == 0) p.tile_count[wt] = tot;
     }
   }
 
+  if (err) atomicCAS(&s_error, 0, err);
   __syncthreads();
   if (p.outputs & OUT_REPORT) shared_acc_flush(env.acc, total, p.dense);
   if (p.outputs & OUT_COUNTS) {
@@ -377,6 +315,124 @@ inline size_t cohort_kernel_smem(const ReportGeom &g, unsigned outputs) {
   if (outputs & OUT_REPORT) b += (size_t)g.off_touch * 8 + (size_t)(g.total - g.off_touch) * 4;
   b += (size_t)BLOCK * Traits::MAX_ROWS * (8 + 8 + 4);
   return b;
+}
+
+// ---- row log, second pass: tile counts -> offsets, packed rows -> columns --
+
+constexpr int EXPAND_TILES = 2048;  // warp tiles per block of the expand pass
+
+struct ExpandParams {
+  const double *prov_start, *prov_end;
+  const int *prov_meta;
+  const int *tile_count;
+  int64_t n_warp_tiles;
+  int tile_cap;                  // 32 * MAX_ROWS
+  unsigned long long *partial;   // per-chunk row totals, then (in place) exclusive chunk offsets
+  unsigned long long *n_rows;
+  int64_t n_chunks;
+  int64_t first_person;
+  double *rowlog;   // 5 columns (end time, event, id, startTime, state), column stride `capacity`
+  int64_t capacity;
+};
+
+__global__ void __launch_bounds__(256) rowlog_partial_kernel(ExpandParams p) {
+  __shared__ unsigned long long s_w[8];
+  const int64_t lo = (int64_t)blockIdx.x * EXPAND_TILES;
+  unsigned long long v = 0;
+  for (int k = threadIdx.x; k < EXPAND_TILES; k += 256) {
+    int64_t t = lo + k;
+    if (t < p.n_warp_tiles) v += (unsigned long long)p.tile_count[t];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; w++) t += s_w[w];
+    p.partial[blockIdx.x] = t;
+  }
+}
+
+// one block: exclusive scan of the chunk totals in place; total row count out
+__global__ void __launch_bounds__(1024) rowlog_chunk_scan_kernel(ExpandParams p) {
+  __shared__ unsigned long long s_w[32];
+  __shared__ unsigned long long s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int64_t c0 = 0; c0 < p.n_chunks; c0 += 1024) {
+    int64_t c = c0 + tid;
+    unsigned long long v = (c < p.n_chunks) ? p.partial[c] : 0, incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    unsigned long long woff = 0;
+    for (int w = 0; w < warp; w++) woff += s_w[w];
+    unsigned long long carry = s_carry;
+    if (c < p.n_chunks) p.partial[c] = carry + woff + incl - v;
+    __syncthreads();
+    if (tid == 1023) s_carry = carry + woff + incl;
+    __syncthreads();
+  }
+  if (tid == 0) *p.n_rows = s_carry;
+}
+
+__global__ void __launch_bounds__(256) rowlog_expand_kernel(ExpandParams p) {
+  __shared__ unsigned long long s_off[EXPAND_TILES];  // exclusive row offset of each tile of this chunk
+  __shared__ unsigned long long s_w[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t lo = (int64_t)blockIdx.x * EXPAND_TILES;
+  // block exclusive scan over the chunk's tile counts: thread t owns tiles [8t, 8t+8)
+  constexpr int PER = EXPAND_TILES / 256;
+  int c[PER];
+  unsigned long long v = 0;
+#pragma unroll
+  for (int k = 0; k < PER; k++) {
+    int64_t t = lo + tid * PER + k;
+    c[k] = (t < p.n_warp_tiles) ? p.tile_count[t] : 0;
+    v += (unsigned long long)c[k];
+  }
+  unsigned long long incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  unsigned long long run = p.partial[blockIdx.x] + incl - v;
+  for (int w = 0; w < warp; w++) run += s_w[w];
+#pragma unroll
+  for (int k = 0; k < PER; k++) {
+    s_off[tid * PER + k] = run;
+    run += (unsigned long long)c[k];
+  }
+  __syncthreads();
+  // each warp expands tiles warp, warp+8, ... of the chunk
+  for (int k = warp; k < EXPAND_TILES; k += 8) {
+    const int64_t t = lo + k;
+    if (t >= p.n_warp_tiles) break;
+    const int cnt = p.tile_count[t];
+    const unsigned long long off = s_off[k];
+    const int64_t src = t * p.tile_cap;
+    const double id0 = (double)(p.first_person + t * 32);
+    for (int r = lane; r < cnt; r += 32) {
+      unsigned long long g = off + r;
+      if (g < (unsigned long long)p.capacity) {
+        int m = p.prov_meta[src + r];
+        p.rowlog[0 * p.capacity + g] = p.prov_end[src + r];
+        p.rowlog[1 * p.capacity + g] = (double)(m & 0xff);
+        p.rowlog[2 * p.capacity + g] = id0 + (double)(m >> 16);
+        p.rowlog[3 * p.capacity + g] = p.prov_start[src + r];
+        p.rowlog[4 * p.capacity + g] = (double)((m >> 8) & 0xff);
+      }
+    }
+  }
 }
 
 // ---- sequential-stream regime: draws per start position, chain resolution --

@@ -16,6 +16,17 @@
 
 namespace msim {
 
+// Ahrens & Dieter (1972): q[k-1] = sum_{i=1..k} ln(2)^i / i!
+#ifdef __CUDACC__
+__constant__
+#else
+static
+#endif
+    const double MSIM_EXP_Q[16] = {0.6931471805599453, 0.9333736875190459, 0.9888777961838675, 0.9984589039328340,
+                                   0.9998292811061389, 0.9999833164100727, 0.9999985691438767, 0.9999998906925558,
+                                   0.9999999924734159, 0.9999999995283275, 0.9999999999728814, 0.9999999999985598,
+                                   0.9999999999999289, 0.9999999999999968, 0.9999999999999999, 1.0000000000000000};
+
 // the `R::` namespace as seen from a model: R.runif(a,b), R.rweibull(...), ...
 template <class Src>
 struct RMath {
@@ -37,22 +48,19 @@ struct RMath {
     return scale * pow(-log(unif_rand()), 1. / shape);
   }
 
-  // Ahrens & Dieter (1972): q[k-1] = sum_{i=1..k} ln(2)^i / i!
-  MSIM_DEV_NOINLINE double exp_rand() {
-    const double q[16] = {0.6931471805599453, 0.9333736875190459, 0.9888777961838675, 0.9984589039328340,
-                          0.9998292811061389, 0.9999833164100727, 0.9999985691438767, 0.9999998906925558,
-                          0.9999999924734159, 0.9999999995283275, 0.9999999999728814, 0.9999999999985598,
-                          0.9999999999999289, 0.9999999999999968, 0.9999999999999999, 1.0000000000000000};
+  MSIM_DEV double exp_rand() {
+    const double q0 = 0.6931471805599453;  // MSIM_EXP_Q[0] = ln 2
+    const double *q = MSIM_EXP_Q;
     double a = 0.;
     double u = unif_rand();
     while (u <= 0. || u >= 1.) u = unif_rand();
     for (;;) {
       u += u;
       if (u > 1.) break;
-      a += q[0];
+      a += q0;
     }
     u -= 1.;
-    if (u <= q[0]) return a + u;
+    if (u <= q0) return a + u;
     int i = 0;
     double ustar = unif_rand(), umin = ustar;
     do {
@@ -60,7 +68,7 @@ struct RMath {
       if (umin > ustar) umin = ustar;
       i++;
     } while (u > q[i]);
-    return a + umin * q[0];
+    return a + umin * q0;
   }
 
   MSIM_DEV double rexp(double scale) { return scale * exp_rand(); }
