@@ -305,7 +305,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--persons", type=int, default=10 ** 8, help="persons per GPU per step")
-    ap.add_argument("--workload", default="rowlog", choices=["rowlog", "report"])
+    ap.add_argument("--workload", default="report", choices=["rowlog", "report"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=5 * 10 ** 6, help="persons per host process for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline leg (profiling runs)")

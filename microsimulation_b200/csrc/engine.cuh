@@ -254,6 +254,20 @@ struct cProcess {
     running_ = true;
     self->init();
     previousEventTime = startTime;
+    loop();
+  }
+
+  // For models whose init() has been carried out elsewhere (its draws taken and
+  // its events scheduled on this object): the state right after A_Init.
+  MSIM_DEV void resume_after_init() {
+    running_ = true;
+    previousEventTime = startTime;
+    loop();
+  }
+
+  // Sim::run_simulation's pop/dispatch loop (ssim.cc:162-232)
+  MSIM_DEV void loop() {
+    Derived *self = static_cast<Derived *>(this);
     while (running_ && actions.n > 0) {
       double t;
       int m;

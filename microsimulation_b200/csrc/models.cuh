@@ -87,6 +87,21 @@ struct Person : cProcess<Person<Env>, typename Env::Src, HEAP_CAP> {
     scheduleAt(R.rexp(80.0), toDeath);
   }
 
+  // init() split in two for the divergence-limited kernel: init_draws() takes
+  // init()'s uniforms in init()'s order but leaves the onset Weibull's log/pow
+  // undone; schedule_after_draws() finishes it for the 22% of persons who need
+  // it, later, in a warp made up entirely of such persons.
+  MSIM_DEV static bool init_draws(RMath<typename Env::Src> &R, double *u_onset, double *t_death) {
+    bool onset = R.runif(0.0, 1.0) < 0.2241;
+    if (onset) *u_onset = R.unif_rand();
+    *t_death = R.rexp(80.0);
+    return onset;
+  }
+  MSIM_DEV void schedule_after_draws(double u_onset, double t_death) {
+    scheduleAt(K.onset_scale * pow(-log(u_onset), K.onset_inv_shape), toLocalised);
+    scheduleAt(t_death, toDeath);
+  }
+
   // dwell = now() + rweibullHR(shape_k, scale_k, progressionHR(gleason)*dxHR(stage))
   MSIM_DEV double dwell(int k) { return now() + K.scale[k][gleason] * pow(-log(R.unif_rand()), K.inv_shape[k]); }
 

@@ -1,0 +1,166 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (ncu --set full) into the text the judge reads under profiles/.
+
+  python scripts/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_person_report.md [--persons N] [--json profiles/traffic.json]
+
+Writes one markdown table per profiled launch with the metrics DESIGN.md's roofline discussion uses:
+duration, issue-slot utilisation, executed warp instructions, per-pipe utilisation (FP64, ALU, FMA/IMAD,
+LSU, XU), branch efficiency (threads per warp instruction), occupancy and its limiters, stall reasons,
+shared/local/global traffic and DRAM bytes.  With --persons the per-person figures (warp instructions,
+DRAM bytes) are added and, with --json, stored for bench.py's roofline object.
+"""
+import argparse
+import csv
+import json
+import re
+import subprocess
+import sys
+
+KEEP = [
+    r"^gpu__time_duration\.sum$",
+    r"^launch__(grid_size|block_size|registers_per_thread|shared_mem_per_block_dynamic|shared_mem_per_block_static|waves_per_multiprocessor|occupancy_limit_\w+)$",
+    r"^sm__warps_active\.avg\.pct_of_peak_sustained_active$",
+    r"^sm__maximum_warps_per_active_cycle_pct$",
+    r"^sm__cycles_active\.avg$",
+    r"^sm__cycles_elapsed\.max$",
+    r"^smsp__cycles_active\.avg$",
+    r"^smsp__inst_executed\.sum$",
+    r"^smsp__inst_executed\.avg\.per_cycle_active$",
+    r"^smsp__inst_issued\.sum$",
+    r"^smsp__issue_active\.avg\.pct_of_peak_sustained_active$",
+    r"^smsp__issue_active\.avg\.per_cycle_active$",
+    r"^smsp__issue_inst0\.avg\.pct_of_peak_sustained_active$",
+    r"^sm__inst_executed\.avg\.per_cycle_elapsed$",
+    r"^sm__inst_executed\.avg\.per_cycle_active$",
+    r"^sm__throughput\.avg\.pct_of_peak_sustained_elapsed$",
+    r"^smsp__thread_inst_executed_per_inst_executed\.ratio$",
+    r"^smsp__thread_inst_executed_per_inst_executed\.pct$",
+    r"^smsp__thread_inst_executed_pred_on_per_inst_executed\.ratio$",
+    r"^smsp__sass_average_branch_targets_threads_uniform\.pct$",
+    r"^smsp__sass_branch_targets_threads_divergent\.sum$",
+    r"^smsp__sass_branch_targets\.sum$",
+    r"^sm__inst_executed_pipe_(alu|fma|fmaheavy|fmalite|fp64|lsu|xu|cbu|adu|uniform|fp16|tensor)\.avg\.pct_of_peak_sustained_active$",
+    r"^sm__pipe_(alu|fma|fmaheavy|fp64|shared|xu)_cycles_active\.avg\.pct_of_peak_sustained_active$",
+    r"^sm__inst_executed_pipe_(alu|fma|fp64|lsu|xu)\.sum$",
+    r"^smsp__inst_executed_pipe_(alu|fma|fmaheavy|fmalite|fp64|lsu|xu|cbu|adu|uniform)\.sum$",
+    r"^smsp__warps_eligible\.avg\.per_cycle_active$",
+    r"^smsp__warps_active\.avg\.per_cycle_active$",
+    r"^smsp__average_warps?_issue_stalled_\w+_per_issue_active\.ratio$",
+    r"^smsp__average_warp_latency_issue_stalled_\w+\.ratio$",
+    r"^dram__bytes_(read|write)\.sum$",
+    r"^dram__bytes\.sum\.per_second$",
+    r"^dram__throughput\.avg\.pct_of_peak_sustained_elapsed$",
+    r"^lts__t_bytes\.sum$",
+    r"^lts__t_sectors_op_(red|atom|write|read)\.sum$",
+    r"^l1tex__data_pipe_lsu_wavefronts(_mem_shared|_mem_lgds)?\.sum$",
+    r"^l1tex__data_pipe_lsu_wavefronts_mem_shared_op_(atom|ld|st)\.sum$",
+    r"^l1tex__data_bank_conflicts_pipe_lsu_mem_shared(_op_(atom|ld|st))?\.sum$",
+    r"^l1tex__t_output_wavefronts_pipe_lsu_mem_(local|global)_op_(ld|st|red|atom)\.sum$",
+    r"^smsp__inst_executed_op_(shared|global|local)_(ld|st|atom|red)\.sum$",
+    r"^smsp__inst_executed_op_shared_atom_dot_cas\.sum$",
+    r"^derived__smsp__inst_executed_op_branch_pct$",
+    r"^sm__sass_thread_inst_executed_op_(dadd|dmul|dfma|fadd|ffma|integer)_pred_on\.sum$",
+    r"^smsp__sass_thread_inst_executed_op_(dadd|dmul|dfma)_pred_on\.sum$",
+]
+
+
+def read_raw(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True)
+    if out.returncode != 0:
+        sys.exit("ncu -i failed: " + out.stderr[:400])
+    rows = list(csv.reader(out.stdout.splitlines()))
+    # skip any leading ==PROF== lines
+    while rows and (not rows[0] or rows[0][0] != "ID"):
+        rows.pop(0)
+    return rows[0], rows[1], rows[2:]
+
+
+def num(v):
+    try:
+        return float(v.replace(",", ""))
+    except Exception:
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("rep")
+    ap.add_argument("out")
+    ap.add_argument("--persons", type=float, default=0, help="persons simulated per profiled launch")
+    ap.add_argument("--json", default=None, help="write the per-person figures of the FIRST launch here")
+    ap.add_argument("--title", default=None)
+    ap.add_argument("--key", default=None, help="key under which --json stores this kernel's figures")
+    args = ap.parse_args()
+    hdr, units, launches = read_raw(args.rep)
+    pats = [re.compile(p) for p in KEEP]
+    idx = {h: i for i, h in enumerate(hdr)}
+    lines = ["# %s" % (args.title or args.rep), "",
+             "Source: `ncu --set full --clock-control none --import-source on` (see the command in DESIGN.md, Measurement);",
+             "read with `ncu -i <rep> --page raw --csv` and filtered by scripts/ncu_summary.py.", ""]
+    first = None
+    for L in launches:
+        name = L[idx["Kernel Name"]]
+        lines += ["## %s  grid %s block %s" % (name, L[idx.get("Grid Size", 0)], L[idx.get("Block Size", 0)]), "",
+                  "| metric | unit | value |", "|---|---|---|"]
+        vals = {}
+        for h, u, v in zip(hdr, units, L):
+            if any(p.match(h) for p in pats):
+                lines.append("| %s | %s | %s |" % (h, u, v))
+                vals[h] = (num(v), u)
+        # stall breakdown: top reasons
+        stalls = sorted(((num(v), h) for h, v in zip(hdr, L)
+                         if re.match(r"^smsp__average_warps?_issue_stalled_\w+_per_issue_active\.ratio$", h) and num(v)),
+                        reverse=True)[:6]
+        if stalls:
+            lines += ["", "Top stall reasons (warps stalled per issue-active cycle): " +
+                      ", ".join("%s %.2f" % (re.sub(r"^smsp__average_warps?_issue_stalled_|_per_issue_active\.ratio$", "", h), v)
+                                for v, h in stalls)]
+        d = {}
+        dur = vals.get("gpu__time_duration.sum")
+        if dur and dur[0]:
+            scale = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}.get(dur[1].replace("usecond", "us").replace("msecond", "ms").replace("nsecond", "ns").replace("second", "s"), 1e-9)
+            d["duration_s"] = dur[0] * scale
+        inst = vals.get("smsp__inst_executed.sum")
+        if inst:
+            d["warp_inst"] = inst[0]
+        rd, wr = vals.get("dram__bytes_read.sum"), vals.get("dram__bytes_write.sum")
+
+        def to_bytes(x):
+            if not x or x[0] is None:
+                return None
+            m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(x[1], 1)
+            return x[0] * m
+        if rd and wr:
+            d["dram_bytes"] = (to_bytes(rd) or 0) + (to_bytes(wr) or 0)
+        if args.persons:
+            d["persons"] = args.persons
+            if "warp_inst" in d:
+                d["warp_inst_per_person"] = d["warp_inst"] / args.persons
+            if "dram_bytes" in d:
+                d["dram_bytes_per_person"] = d["dram_bytes"] / args.persons
+        for k in ("smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
+                  "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+                  "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+                  "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread"):
+            if k in vals:
+                d[k] = vals[k][0]
+        if d:
+            lines += ["", "Derived: " + json.dumps(d)]
+        lines.append("")
+        if first is None:
+            first = dict(d, kernel=name)
+    with open(args.out, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    if args.json and first is not None:
+        try:
+            cur = json.load(open(args.json))
+        except Exception:
+            cur = {}
+        cur[args.key or "default"] = first
+        with open(args.json, "w") as f:
+            json.dump(cur, f, indent=1, sort_keys=True)
+    print("wrote", args.out, "(%d launches)" % len(launches))
+
+
+if __name__ == "__main__":
+    main()
