@@ -81,6 +81,18 @@ void msim_shutdown(void);
 /* Number of kernels this library has launched since it was loaded. */
 int64_t msim_launch_count(void);
 
+/* Which GPU schedule the person-r entry points use: 0 (default) = staged
+ * (persons are regrouped between stages so that warps stay full,
+ * csrc/person_staged.cuh), 1 = generic (one person per thread straight
+ * through, the kernel every other model uses).  Same results either way; the
+ * switch exists so tests can check exactly that. */
+int msim_set_person_schedule(int which);
+/* Sizing of the person-r row-log buffers: expected rows per person (default
+ * 1.25; the model logs 1.232) and expected rows beyond a person's first
+ * (default 0.26).  A run that needs more is repeated with the exact sizes, so
+ * the plan only affects speed and memory, never results. */
+int msim_set_rowlog_plan(double rows_per_person, double extra_rows_per_person);
+
 /* ---- RNG state (replaces the .C table, src/init.c:11-30) ------------- */
 
 /* src/microsimulation.cc:33-42 — default RngStream that serves unif_rand()

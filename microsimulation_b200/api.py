@@ -45,6 +45,16 @@ def launch_count():
     return int(load().msim_launch_count())
 
 
+def set_person_schedule(which):
+    """0 / "staged" (default) or 1 / "generic": which GPU schedule runs person-r (same results)."""
+    which = {"staged": 0, "generic": 1}.get(which, which)
+    check(load().msim_set_person_schedule(C.c_int(int(which))))
+
+
+def set_rowlog_plan(rows_per_person=1.25, extra_rows_per_person=0.26):
+    check(load().msim_set_rowlog_plan(rows_per_person, extra_rows_per_person))
+
+
 # ---- RNG utilities (R/rcpp_hello_world.R:104-152)
 
 def set_user_random_seed(seed):

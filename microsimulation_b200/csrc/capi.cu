@@ -15,6 +15,7 @@
 #include "host_state.h"
 #include "report_host.h"
 #include "kernels.cuh"
+#include "person_staged.cuh"
 
 using namespace msim;
 
@@ -35,7 +36,11 @@ struct Ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
   MrgJump *d_lo = nullptr, *d_hi = nullptr;
   DevBuf rowlog, prov_start, prov_end, prov_meta, tile_count, partial, dense, small, mt_words, len, starts, chain_exit, chain_count, chain_entry, chain_base, calib_out,
-      calib_par, uniforms;
+      calib_par, uniforms, first_end, first_tag, row_off, ov_idx, ov_tag, ov_start, ov_end;
+  int person_kernel = 0;  // 0 = staged schedule (person_staged.cuh), 1 = generic cohort kernel
+  bool last_staged = false;
+  double plan_rows = 1.25, plan_extra_rows = 0.26;  // row-log buffer planning (msim_set_rowlog_plan)
+  int64_t last_ov_cap = 0, last_ov_rows = 0;
   HostRngState rng;
   // last cohort run
   int64_t last_n_rows = 0, last_capacity = 0;
@@ -113,14 +118,14 @@ int ensure_init() {
 }
 
 // substream state of person `first_person` of the stream that starts at `state`
-void stream_start(const uint32_t state[6], int64_t first_person, int grid, StreamStart *st) {
+void stream_start(const uint32_t state[6], int64_t first_person, int64_t n_threads, StreamStart *st) {
   Mrg32k3a b;
   memcpy(b.s, state, sizeof b.s);
   b.jump(mrg_jump_pow(mrg_substream_jump(), (uint64_t)first_person + 1));
   memcpy(st->base, b.s, sizeof b.s);
   st->lo = g.d_lo;
   st->hi = g.d_hi;
-  st->stride = mrg_jump_pow(mrg_substream_jump(), (uint64_t)grid * BLOCK);
+  st->stride = mrg_jump_pow(mrg_substream_jump(), (uint64_t)n_threads);
 }
 
 // ---------------------------------------------------------------- host memory
@@ -165,11 +170,12 @@ ReportGeom geom_from_dims(const msim_dense_dims *dims, double discount_rate) {
 
 // ---------------------------------------------------------------- cohort launch
 
-// `small` buffer layout (8-byte cells): [9] n_rows (u64), [10] error (int), [11] end_word (i64)
+// `small` buffer layout (8-byte cells): [9] n_rows (u64), [10] error (int), [11] end_word (i64), [12] overflow rows (u64)
 struct SmallView {
   unsigned long long *n_rows;
   int *error;
   int64_t *end_word;
+  unsigned long long *ov_count;
 };
 SmallView small_view() {
   SmallView v;
@@ -177,6 +183,7 @@ SmallView small_view() {
   v.n_rows = (unsigned long long *)(b + 9);
   v.error = (int *)(b + 10);
   v.end_word = (int64_t *)(b + 11);
+  v.ov_count = (unsigned long long *)(b + 12);
   return v;
 }
 
@@ -202,7 +209,7 @@ int cohort_prepare(CohortParams<typename Traits::Consts> &p, const uint32_t stre
   size_t smem = cohort_kernel_smem<Traits>(p.geom, p.outputs);
   int grid = 1;
   if ((rc = cohort_grid<Traits, STREAM>(smem, p.n, &grid))) return rc;
-  if (!STREAM) stream_start(stream_state, p.first_person, grid, &p.st);
+  if (!STREAM) stream_start(stream_state, p.first_person, (int64_t)grid * BLOCK, &p.st);
   if ((rc = ensure(g.small, 16 * sizeof(double)))) return rc;
   CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
   SmallView sv = small_view();
@@ -279,6 +286,7 @@ int cohort_fire(CohortParams<typename Traits::Consts> &p, int grid, size_t smem,
   g.last_n = p.n;
   g.last_first = p.first_person;
   g.last_max_rows = Traits::MAX_ROWS;
+  g.last_staged = false;
   g.have_last = true;
   return MSIM_OK;
 }
@@ -294,6 +302,7 @@ int finish_run(int64_t *n_rows_out) {
   int err = *(int *)(small + 10);
   unsigned long long nr = *(unsigned long long *)(small + 9);
   g.last_n_rows = (int64_t)nr;
+  g.last_ov_rows = (int64_t) * (unsigned long long *)(small + 12);
   if (n_rows_out) *n_rows_out = (int64_t)nr;
   if (err == MSIM_ERR_HEAP) return fail(MSIM_ERR_HEAP, "a person scheduled more pending events / rows than the device capacity");
   if (err == MSIM_ERR_STREAM) return fail(MSIM_ERR_STREAM, "a person drew more uniforms than the sequential-stream plan allows");
@@ -302,8 +311,8 @@ int finish_run(int64_t *n_rows_out) {
 }
 
 int64_t rowlog_capacity_guess(int64_t n, int max_rows, double mean_rows) {
-  if (n <= 65536) return n * max_rows + 1;
-  int64_t c = (int64_t)((double)n * mean_rows) + 65536;
+  if (n <= 65536 && mean_rows >= 1.0) return n * max_rows + 1;
+  int64_t c = (int64_t)((double)n * mean_rows) + (mean_rows >= 1.0 ? 65536 : 16);
   return std::min<int64_t>(c, n * max_rows + 1);
 }
 
@@ -331,21 +340,148 @@ int fetch_report(msim_report *out) {
 }
 
 // the guessed row capacity was too small: the packed rows are still there, expand again
+int staged_rowpasses(int64_t n, int64_t first_person, int64_t capacity, bool count_first);
+
 int reexpand(int64_t rows) {
   int rc;
   if ((rc = ensure(g.rowlog, sizeof(double) * 5 * (size_t)rows))) return rc;
-  if ((rc = rowlog_expand(g.last_n, g.last_first, g.last_max_rows, rows))) return rc;
+  if (g.last_staged) {
+    if ((rc = staged_rowpasses(g.last_n, g.last_first, rows, false))) return rc;
+  } else if ((rc = rowlog_expand(g.last_n, g.last_first, g.last_max_rows, rows))) {
+    return rc;
+  }
   g.last_capacity = rows;
   return finish_run(nullptr);
 }
 
 // ---- person-r
 
-int person_enqueue(const msim_person_shard *sh, int64_t capacity_override) {
+// the two bandwidth-bound passes that turn first rows + overflow rows into the final columns
+int staged_rowpasses(int64_t n, int64_t first_person, int64_t capacity, bool count_first) {
+  RowPassParams r;
+  memset(&r, 0, sizeof r);
+  SmallView sv = small_view();
+  r.first_end = (const double *)g.first_end.p;
+  r.first_tag = (const unsigned short *)g.first_tag.p;
+  r.ov_idx = (const unsigned *)g.ov_idx.p;
+  r.ov_tag = (const unsigned *)g.ov_tag.p;
+  r.ov_start = (const double *)g.ov_start.p;
+  r.ov_end = (const double *)g.ov_end.p;
+  r.ov_count = sv.ov_count;
+  r.ov_cap = g.last_ov_cap;
+  r.n = n;
+  r.first_person = first_person;
+  r.chunk_rows = (unsigned long long *)g.partial.p;
+  r.n_rows = sv.n_rows;
+  r.n_chunks = (n + ROW_CHUNK - 1) / ROW_CHUNK;
+  r.row_off = (unsigned *)g.row_off.p;
+  r.rowlog = (double *)g.rowlog.p;
+  r.capacity = capacity;
+  if (r.n_chunks == 0) return MSIM_OK;
+  if (count_first) {
+    rowpass_count_kernel<<<(unsigned)r.n_chunks, 256, 0, g.stream>>>(r);
+    CK(cudaGetLastError());
+    rowpass_scan_kernel<<<1, 1024, 0, g.stream>>>(r);
+    CK(cudaGetLastError());
+    g.launches += 2;
+  }
+  rowpass_first_kernel<<<(unsigned)r.n_chunks, 256, 0, g.stream>>>(r);
+  CK(cudaGetLastError());
+  rowpass_scatter_kernel<<<g.sm_count * 8, 256, 0, g.stream>>>(r);
+  CK(cudaGetLastError());
+  g.launches += 2;
+  return MSIM_OK;
+}
+
+int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t ov_cap_override) {
+  int rc;
+  if (sh->n >= (int64_t)4294967296ll) return fail(MSIM_ERR_ARG, "a shard holds at most 2^32 - 1 persons");
+  StagedParams p;
+  memset(&p, 0, sizeof p);
+  p.first_person = sh->first_person;
+  p.n = sh->n;
+  p.outputs = sh->outputs & 7u;
+  p.consts = person_r::make_consts();
+  p.geom = ages_geom(person_r::N_STATE, person_r::N_EVENT, sh->discount_rate);
+  size_t smem = sizeof(WarpQueues) * SWARPS;
+  if (p.outputs & OUT_REPORT) smem += (size_t)p.geom.off_dstart * 8 + (size_t)(p.geom.total - p.geom.off_dstart) * 4;
+  int per_sm = 0;
+  CK(cudaFuncSetAttribute(person_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, person_staged_kernel, SBLOCK, smem));
+  if (per_sm < 1) return fail(MSIM_ERR_CUDA, "staged kernel does not fit on an SM");
+  const int64_t tiles = (sh->n + 31) / 32;
+  int64_t gmax = (int64_t)per_sm * g.sm_count;
+  if (gmax > JUMP_TAB * (int64_t)JUMP_TAB / SBLOCK) gmax = JUMP_TAB * (int64_t)JUMP_TAB / SBLOCK;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(gmax, (tiles + SWARPS - 1) / SWARPS));
+  uint32_t state[6];
+  seed_to_u32(sh->seed, state);
+  stream_start(state, sh->first_person, (int64_t)grid * SBLOCK, &p.st);
+  if ((rc = ensure(g.small, 16 * sizeof(double)))) return rc;
+  CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
+  SmallView sv = small_view();
+  p.error = sv.error;
+  const int cells = (p.outputs & OUT_REPORT) ? p.geom.total : 0;
+  if ((rc = ensure(g.dense, sizeof(double) * (cells + N_COUNTS)))) return rc;
+  CK(cudaMemsetAsync(g.dense.p, 0, sizeof(double) * (cells + N_COUNTS), g.stream));
+  p.dense = (double *)g.dense.p;
+  p.counts = p.dense + cells;
+  g.last_cells = cells;
+  int64_t ov_cap = 0;
+  if (p.outputs & OUT_ROWLOG) {
+    const size_t n1 = (size_t)std::max<int64_t>(sh->n, 1);
+    // rows beyond a person's first: 0.232 per person at the reference's parameters; at most 4
+    ov_cap = ov_cap_override > 0 ? ov_cap_override
+                                 : std::min<int64_t>((int64_t)(g.plan_extra_rows * (double)sh->n) + (g.plan_extra_rows >= 0.2 ? 65536 : 16), sh->n * (person_r::MAX_ROWS - 1) + 1);
+    if ((rc = ensure(g.first_end, sizeof(double) * n1))) return rc;
+    if ((rc = ensure(g.first_tag, sizeof(unsigned short) * n1))) return rc;
+    if ((rc = ensure(g.row_off, sizeof(unsigned) * n1))) return rc;
+    if ((rc = ensure(g.ov_idx, sizeof(unsigned) * (size_t)ov_cap))) return rc;
+    if ((rc = ensure(g.ov_tag, sizeof(unsigned) * (size_t)ov_cap))) return rc;
+    if ((rc = ensure(g.ov_start, sizeof(double) * (size_t)ov_cap))) return rc;
+    if ((rc = ensure(g.ov_end, sizeof(double) * (size_t)ov_cap))) return rc;
+    if ((rc = ensure(g.partial, sizeof(unsigned long long) * (size_t)((sh->n + ROW_CHUNK - 1) / ROW_CHUNK + 1)))) return rc;
+    if ((rc = ensure(g.rowlog, sizeof(double) * 5 * (size_t)std::max<int64_t>(capacity, 1)))) return rc;
+    p.first_end = (double *)g.first_end.p;
+    p.first_tag = (unsigned short *)g.first_tag.p;
+    p.ov_idx = (unsigned *)g.ov_idx.p;
+    p.ov_tag = (unsigned *)g.ov_tag.p;
+    p.ov_start = (double *)g.ov_start.p;
+    p.ov_end = (double *)g.ov_end.p;
+    p.ov_count = sv.ov_count;
+    p.ov_cap = ov_cap;
+  }
+  g.last_ov_cap = ov_cap;
+  CK(cudaEventRecord(g.ev0, g.stream));
+  if (p.n > 0) {
+    person_staged_kernel<<<grid, SBLOCK, smem, g.stream>>>(p);
+    CK(cudaGetLastError());
+    g.launches++;
+    if (p.outputs & OUT_ROWLOG) {
+      if ((rc = staged_rowpasses(p.n, p.first_person, capacity, true))) return rc;
+    }
+  }
+  CK(cudaEventRecord(g.ev1, g.stream));
+  g.timing_pending = true;
+  g.last_geom = p.geom;
+  g.last_outputs = p.outputs;
+  g.last_capacity = capacity;
+  g.last_n = p.n;
+  g.last_first = p.first_person;
+  g.last_max_rows = person_r::MAX_ROWS;
+  g.last_staged = true;
+  g.have_last = true;
+  return MSIM_OK;
+}
+
+int person_enqueue(const msim_person_shard *sh, int64_t capacity_override, int64_t ov_cap_override = 0) {
   int rc;
   if ((rc = ensure_init())) return rc;
   if (!sh || sh->n < 0 || sh->first_person < 0) return fail(MSIM_ERR_ARG, "bad shard");
   if (!mrg_seed_ok(sh->seed)) return fail(MSIM_ERR_SEED, "illegal MRG32k3a seed");
+  const int64_t capacity = capacity_override > 0 ? capacity_override : rowlog_capacity_guess(sh->n, person_r::MAX_ROWS, g.plan_rows);
+  g.want_capacity = capacity;
+  g.last_simple_names = false;
+  if (g.person_kernel == 0) return person_enqueue_staged(sh, capacity, ov_cap_override);
   CohortParams<person_r::Consts> p;
   memset(&p, 0, sizeof p);
   p.first_person = sh->first_person;
@@ -353,11 +489,8 @@ int person_enqueue(const msim_person_shard *sh, int64_t capacity_override) {
   p.outputs = sh->outputs & 7u;
   p.consts = person_r::make_consts();
   p.geom = ages_geom(person_r::N_STATE, person_r::N_EVENT, sh->discount_rate);
-  const int64_t capacity = capacity_override > 0 ? capacity_override : rowlog_capacity_guess(sh->n, person_r::MAX_ROWS, 1.25);
-  g.want_capacity = capacity;
   uint32_t state[6];
   seed_to_u32(sh->seed, state);
-  g.last_simple_names = false;
   int grid;
   size_t smem;
   if ((rc = cohort_prepare<PersonTraits, false>(p, state, &grid, &smem))) return rc;
@@ -373,6 +506,11 @@ int person_run(const msim_person_shard *sh) {
   if ((rc = person_enqueue(sh, 0))) return rc;
   int64_t rows = 0;
   if ((rc = finish_run(&rows))) return rc;
+  if ((sh->outputs & OUT_ROWLOG) && g.last_staged && g.last_ov_rows > g.last_ov_cap) {
+    // rare: more rows beyond the first than planned for — run again with the exact size
+    if ((rc = person_enqueue(sh, rows > g.last_capacity ? rows : 0, g.last_ov_rows))) return rc;
+    if ((rc = finish_run(&rows))) return rc;
+  }
   if ((sh->outputs & OUT_ROWLOG) && rows > g.last_capacity) {  // rare: redo the expand pass with the exact size
     if ((rc = reexpand(rows))) return rc;
   }
@@ -497,7 +635,8 @@ void msim_shutdown(void) {
   if (!g.inited) return;
   cudaStreamSynchronize(g.stream);
   DevBuf *bufs[] = {&g.rowlog, &g.prov_start, &g.prov_end, &g.prov_meta, &g.tile_count, &g.partial, &g.dense, &g.small, &g.mt_words, &g.len, &g.starts, &g.chain_exit,
-                    &g.chain_count, &g.chain_entry, &g.chain_base, &g.calib_out, &g.calib_par, &g.uniforms};
+                    &g.chain_count, &g.chain_entry, &g.chain_base, &g.calib_out, &g.calib_par, &g.uniforms,
+                    &g.first_end, &g.first_tag, &g.row_off, &g.ov_idx, &g.ov_tag, &g.ov_start, &g.ov_end};
   for (DevBuf *b : bufs) {
     if (b->p) cudaFree(b->p);
     b->p = nullptr;
@@ -516,6 +655,19 @@ void msim_shutdown(void) {
 }
 
 int64_t msim_launch_count(void) { return g.launches; }
+
+int msim_set_rowlog_plan(double rows_per_person, double extra_rows_per_person) {
+  if (!(rows_per_person > 0) || !(extra_rows_per_person >= 0)) return fail(MSIM_ERR_ARG, "bad plan");
+  g.plan_rows = rows_per_person;
+  g.plan_extra_rows = extra_rows_per_person;
+  return MSIM_OK;
+}
+
+int msim_set_person_schedule(int which) {
+  if (which != 0 && which != 1) return fail(MSIM_ERR_ARG, "schedule must be 0 (staged) or 1 (generic)");
+  g.person_kernel = which;
+  return MSIM_OK;
+}
 
 void msim_table_free(msim_table *t) {
   if (!t) return;
@@ -657,7 +809,7 @@ int msim_calibration_sweep(const double seed[6], int64_t first_person, int64_t n
   int grid_x = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, tiles), 2048));
   uint32_t state[6];
   seed_to_u32(seed, state);
-  stream_start(state, first_person, grid_x, &p.st);
+  stream_start(state, first_person, (int64_t)grid_x * BLOCK, &p.st);
   p.n = n;
   p.n_sets = n_sets;
   p.runpar = (const double *)g.calib_par.p;

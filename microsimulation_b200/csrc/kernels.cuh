@@ -46,6 +46,7 @@ struct SharedAcc {
   int n_f;
   __device__ __forceinline__ void addf(int idx, double v) { atomicAdd(&f[idx], v); }
   __device__ __forceinline__ void addi(int idx, int v) { atomicAdd(&i[idx - n_f], v); }
+  __device__ __forceinline__ void addc(int idx) { atomicAdd(&i[idx - n_f], 1); }
 };
 
 __device__ __forceinline__ void shared_acc_clear(SharedAcc &a, int total) {
@@ -175,7 +176,9 @@ struct CohortEnv {
   SharedAcc acc;
   int *s_kind;
   double sum_end;
+  ReportCursor cursor;
 
+  __device__ __forceinline__ void begin_person() { cursor.valid = false; }
   __device__ __forceinline__ void row(double, double start, double end, int state, int kind) {
     if (outputs & OUT_COUNTS) {
       atomicAdd(&s_kind[kind], 1);
@@ -191,7 +194,7 @@ struct CohortEnv {
     }
   }
   __device__ __forceinline__ void report(int state, int kind, double lhs, double rhs) {
-    if (outputs & OUT_REPORT) report_add(*geom, acc, state, kind, lhs, rhs);
+    if (outputs & OUT_REPORT) report_add(*geom, acc, cursor, state, kind, lhs, rhs);
   }
 };
 
@@ -200,6 +203,7 @@ template <class SrcT>
 struct NullEnv {
   typedef SrcT Src;
   Src src;
+  __device__ __forceinline__ void begin_person() {}
   __device__ __forceinline__ void row(double, double, double, int, int) {}
   __device__ __forceinline__ void report(int, int, double, double) {}
 };
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(BLOCK, 3) cohort_kernel(const __grid_constant_
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // shared layout: [dense doubles | row slots start, end | row slots meta | dense ints]
   const int total = (p.outputs & OUT_REPORT) ? p.geom.total : 0;
-  const int n_f = (p.outputs & OUT_REPORT) ? p.geom.off_touch : 0;
+  const int n_f = (p.outputs & OUT_REPORT) ? p.geom.off_dstart : 0;
   double *s_f = reinterpret_cast<double *>(smem_raw);
   constexpr int SLOTS = BLOCK * MAXR;
   double *slot_start = s_f + n_f;
@@ -312,7 +316,7 @@ __global__ void __launch_bounds__(BLOCK, 3) cohort_kernel(const __grid_constant_
 template <class Traits>
 inline size_t cohort_kernel_smem(const ReportGeom &g, unsigned outputs) {
   size_t b = 0;
-  if (outputs & OUT_REPORT) b += (size_t)g.off_touch * 8 + (size_t)(g.total - g.off_touch) * 4;
+  if (outputs & OUT_REPORT) b += (size_t)g.off_dstart * 8 + (size_t)(g.total - g.off_dstart) * 4;
   b += (size_t)BLOCK * Traits::MAX_ROWS * (8 + 8 + 4);
   return b;
 }

@@ -80,26 +80,27 @@ struct Person : cProcess<Person<Env>, typename Env::Src, HEAP_CAP> {
   const Consts &K;
 
   MSIM_DEV Person(Env &e, const Consts &k, int64_t i)
-      : Base(&e.src), gleason(nogleason), stage(Healthy), dx(false), id(i), env(e), K(k) {}
+      : Base(&e.src), gleason(nogleason), stage(Healthy), dx(false), id(i), env(e), K(k) {
+    e.begin_person();
+  }
 
   MSIM_DEV void init() {  // person-r.cc:98-103
     if (R.runif(0.0, 1.0) < 0.2241) scheduleAt(K.onset_scale * pow(-log(R.unif_rand()), K.onset_inv_shape), toLocalised);
     scheduleAt(R.rexp(80.0), toDeath);
   }
 
-  // init() split in two for the divergence-limited kernel: init_draws() takes
-  // init()'s uniforms in init()'s order but leaves the onset Weibull's log/pow
-  // undone; schedule_after_draws() finishes it for the 22% of persons who need
-  // it, later, in a warp made up entirely of such persons.
+  // init() in two steps for the staged kernel (person_staged.cuh): init_draws()
+  // takes init()'s uniforms in init()'s order but leaves the onset Weibull's
+  // log/pow undone; onset_time() finishes it later, in a warp made up entirely
+  // of persons who need it.
   MSIM_DEV static bool init_draws(RMath<typename Env::Src> &R, double *u_onset, double *t_death) {
     bool onset = R.runif(0.0, 1.0) < 0.2241;
     if (onset) *u_onset = R.unif_rand();
     *t_death = R.rexp(80.0);
     return onset;
   }
-  MSIM_DEV void schedule_after_draws(double u_onset, double t_death) {
-    scheduleAt(K.onset_scale * pow(-log(u_onset), K.onset_inv_shape), toLocalised);
-    scheduleAt(t_death, toDeath);
+  MSIM_DEV static double onset_time(const Consts &K, double u_onset) {
+    return K.onset_scale * pow(-log(u_onset), K.onset_inv_shape);
   }
 
   // dwell = now() + rweibullHR(shape_k, scale_k, progressionHR(gleason)*dxHR(stage))
@@ -109,28 +110,25 @@ struct Person : cProcess<Person<Env>, typename Env::Src, HEAP_CAP> {
     env.row((double)id, previousEventTime, now(), stage, kind);  // logged BEFORE the state change (:112-116)
     env.report(stage, kind, previousEventTime, now());  // EventReport attachment (BASELINE config 4); no-op unless requested
 
-    if (kind == toDeath) {
+    if (kind == toDeath || kind == toPCDeath) {  // :120-126
       stop_simulation();
-    } else if (kind == toPCDeath) {
-      stop_simulation();
-    } else if (kind == toLocalised) {
-      stage = Localised;
-      gleason = (R.runif(0.0, 1.0) < 0.6812) ? gleasonLt7 : ((R.runif(0.0, 1.0) < 0.5016) ? gleason7 : gleasonGt7);
-      double dwellTime = dwell(0);
-      if (R.runif(0.0, 1.0) < K.pDx[0]) scheduleAt(dwellTime, toDxLocalised);
-      else scheduleAt(dwellTime, toLocallyAdvanced);
-    } else if (kind == toLocallyAdvanced) {
-      stage = LocallyAdvanced;
-      double dwellTime = dwell(1);
-      if (R.runif(0.0, 1.0) < K.pDx[1]) scheduleAt(dwellTime, toDxLocallyAdvanced);
-      else scheduleAt(dwellTime, toMetastatic);
-    } else if (kind == toMetastatic) {
-      stage = Metastatic;
-      double dwellTime = dwell(2);
-      if (R.runif(0.0, 1.0) < K.pDx[2]) scheduleAt(dwellTime, toDxMetastatic);
-      else scheduleAt(dwellTime, toPCDeath);
+    } else if (kind == toLocalised || kind == toLocallyAdvanced || kind == toMetastatic) {
+      // :128-173.  The three progression handlers have the same shape — new
+      // stage, [Gleason draws on toLocalised], one Weibull dwell time, one
+      // uniform choosing between diagnosis and further progression — so lanes
+      // of a warp that handle different ones of them run the same instructions
+      // (the expensive log/pow once) with per-lane constants; the order of the
+      // draws is the reference's.
+      const int k = (kind == toLocalised) ? 0 : (kind == toLocallyAdvanced) ? 1 : 2;
+      stage = (k == 0) ? Localised : (k == 1) ? LocallyAdvanced : Metastatic;
+      if (k == 0)
+        gleason = (R.runif(0.0, 1.0) < 0.6812) ? gleasonLt7 : ((R.runif(0.0, 1.0) < 0.5016) ? gleason7 : gleasonGt7);
+      const double dwellTime = dwell(k);
+      const int dxKind = (k == 0) ? toDxLocalised : (k == 1) ? toDxLocallyAdvanced : toDxMetastatic;
+      const int nextKind = (k == 0) ? toLocallyAdvanced : (k == 1) ? toMetastatic : toPCDeath;
+      scheduleAt(dwellTime, (R.runif(0.0, 1.0) < K.pDx[k]) ? dxKind : nextKind);
     } else if (kind == toDxLocalised || kind == toDxLocallyAdvanced || kind == toDxMetastatic) {
-      dx = true;
+      dx = true;  // :175-188
     }
   }
 };
@@ -237,7 +235,9 @@ struct SimplePerson : cProcess<SimplePerson<Env>, typename Env::Src, HEAP_CAP> {
   Env &env;
   const Consts &K;
 
-  MSIM_DEV SimplePerson(Env &e, const Consts &k, int64_t /*id*/) : Base(&e.src), state(Healthy), z(1.0), env(e), K(k) {}
+  MSIM_DEV SimplePerson(Env &e, const Consts &k, int64_t /*id*/) : Base(&e.src), state(Healthy), z(1.0), env(e), K(k) {
+    e.begin_person();
+  }
 
   MSIM_DEV void init() {  // illness-death.cpp:35-41
     state = Healthy;
@@ -290,7 +290,9 @@ struct SimplePerson : cProcess<SimplePerson<Env>, typename Env::Src, HEAP_CAP> {
   int64_t id;
   Env &env;
 
-  MSIM_DEV SimplePerson(Env &e, const Consts &, int64_t i) : Base(&e.src), state(Healthy), id(i), env(e) {}
+  MSIM_DEV SimplePerson(Env &e, const Consts &, int64_t i) : Base(&e.src), state(Healthy), id(i), env(e) {
+    e.begin_person();
+  }
 
   MSIM_DEV void init() {  // simple-example.cc:26-32, simple-example2.cc:28-32
     state = Healthy;

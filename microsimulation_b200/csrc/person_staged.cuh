@@ -1,0 +1,556 @@
+// Staged execution of the FHCRC natural-history model (src/person-r.cc) —
+// the schedule the person-r entry points use on the GPU.
+//
+// Why.  Run one-person-per-thread straight through, this model leaves ~30% of
+// a warp's lanes active (ncu: 9.6 threads per warp instruction, profiles/r01a):
+// 78% of persons draw three uniforms and die of other causes, while the rest
+// need a Weibull onset time (log + pow) and then, for half of those, a chain of
+// progression / diagnosis events with more log + pow.  Nearly every warp holds
+// a few such persons, so every warp walks the long code with a few lanes on.
+//
+// How.  A person's life is cut at the two points where it may need the
+// expensive arithmetic, and persons that reach a cut are parked, with their
+// RngStream state, in a per-warp queue in shared memory.  A warp runs
+//   stage A   on 32 NEW persons (all lanes): substream jump, init()'s draws;
+//             persons without an onset draw finish here (single toDeath event);
+//   stage B1  whenever >= 32 persons wait for their onset time: log + pow on
+//             all lanes; persons who die before onset finish here;
+//   stage B2  whenever >= 32 persons wait with onset before death: the event
+//             loop (Sim::run_simulation's, engine.cuh) from just after A_Init.
+// No block-level synchronisation is involved: queues are per warp, and pushes
+// and pops are warp ballots.  Every draw a person takes, and the order it takes
+// them in, is the reference's; only WHEN the arithmetic happens moves.  A person's
+// stages run through the same Person<Env> object (models.cuh) the generic kernel
+// uses: scheduleAt(), the 4-slot heap and handleMessage() are shared code, so
+// ties and pop order are the reference's by construction.
+//
+// Row log.  Rows must come out in person order but persons now finish out of
+// order, so the simulation writes, per person, its FIRST row (end time + a
+// 16-bit tag: kind, state, number of further rows) to arrays indexed by person,
+// and appends the further rows (0.23 per person) to an unordered overflow list
+// tagged with (person, row number).  Two bandwidth-bound passes turn that into
+// the final five f64 columns: a scan of the per-person row counts that writes
+// the first rows, and a scatter of the overflow rows.
+#pragma once
+#include "models.cuh"
+#include "report.cuh"
+
+namespace msim {
+namespace person_r {
+
+// a person parked after stage A: init()'s uniforms taken, onset time not yet computed
+struct ParkedOnset {
+  Mrg32k3a g;  // RngStream state after init()'s draws
+  double u_onset, t_death;
+};
+// a person parked after stage B1: both init() events known, toLocalised comes first
+struct ParkedLoop {
+  Mrg32k3a g;
+  double t_onset, t_death;
+};
+
+// Stage A.  Returns true if the person is finished.
+template <class Env>
+MSIM_DEV bool stage_a(Env &env, const Consts &K, int64_t id, ParkedOnset *park) {
+  RMath<typename Env::Src> R(&env.src);
+  double u_onset = 0.0, t_death = 0.0;
+  const bool onset = Person<Env>::init_draws(R, &u_onset, &t_death);
+  if (!onset) {
+    Person<Env> person(env, K, id);
+    person.scheduleAt(t_death, toDeath);  // init(): the only event (person-r.cc:102)
+    person.resume_after_init();
+    return true;
+  }
+  park->g = env.src.g;
+  park->u_onset = u_onset;
+  park->t_death = t_death;
+  return false;
+}
+
+// Stage B1.  Returns true if the person is finished (death pops before onset:
+// strictly earlier, because toLocalised was inserted first — heap.h:75-88).
+template <class Env>
+MSIM_DEV bool stage_b1(Env &env, const Consts &K, int64_t id, const ParkedOnset &in, ParkedLoop *park) {
+  const double t_onset = Person<Env>::onset_time(K, in.u_onset);
+  if (in.t_death < t_onset) {
+    env.src.g = in.g;
+    Person<Env> person(env, K, id);
+    person.scheduleAt(t_onset, toLocalised);
+    person.scheduleAt(in.t_death, toDeath);
+    person.resume_after_init();
+    return true;
+  }
+  park->g = in.g;
+  park->t_onset = t_onset;
+  park->t_death = in.t_death;
+  return false;
+}
+
+// Stage B2: the rest of the life.
+template <class Env>
+MSIM_DEV void stage_b2(Env &env, const Consts &K, int64_t id, const ParkedLoop &in, int *error) {
+  env.src.g = in.g;
+  Person<Env> person(env, K, id);
+  person.scheduleAt(in.t_onset, toLocalised);  // init()'s order (person-r.cc:100-102)
+  person.scheduleAt(in.t_death, toDeath);
+  person.resume_after_init();
+  if (person.error_) *error = person.error_;
+}
+
+}  // namespace person_r
+
+#ifdef __CUDACC__
+
+#ifndef MSIM_SBLOCK
+#define MSIM_SBLOCK 256
+#endif
+#ifndef MSIM_SMINB
+#define MSIM_SMINB 2
+#endif
+constexpr int SBLOCK = MSIM_SBLOCK;  // threads per block of the staged kernel
+constexpr int SWARPS = SBLOCK / 32;
+constexpr int QCAP = 64;        // a queue holds < 32 entries between pushes, < 64 after one
+constexpr int XROWS = 4;        // rows a person may log beyond its first (person_r::MAX_ROWS - 1)
+constexpr int ROW_CHUNK = 8192;  // persons per block of the row-log passes
+
+struct alignas(16) WarpQueues {
+  uint32_t q1_s[6][QCAP];
+  double q1_u[QCAP], q1_t[QCAP];
+  uint32_t q1_idx[QCAP];
+  uint32_t q2_s[6][QCAP];
+  double q2_on[QCAP], q2_t[QCAP];
+  uint32_t q2_idx[QCAP];
+  double x_start[XROWS][32], x_end[XROWS][32];
+  uint32_t x_meta[XROWS][32];
+};
+
+struct StagedParams {
+  StreamStart st;  // stride = M^(gridDim.x*SBLOCK)
+  int64_t first_person, n;
+  unsigned outputs;
+  person_r::Consts consts;
+  ReportGeom geom;
+  double *dense;   // dense report accumulators in global memory (zeroed before launch)
+  double *counts;  // N_COUNTS doubles
+  int *error;
+  // row log, first pass
+  double *first_end;           // [n] end time of each person's first row
+  unsigned short *first_tag;   // [n] kind | state << 4 | (rows - 1) << 8
+  unsigned *ov_idx, *ov_tag;   // overflow rows: person index; row number << 16 | state << 8 | kind
+  double *ov_start, *ov_end;
+  unsigned long long *ov_count;
+  int64_t ov_cap;
+};
+
+// Report accumulators of a block in shared memory ([0, n_f) doubles, then
+// ints), flushed once per block with red.global.add.f64.  (Accumulating
+// straight into global memory was measured at 38 ms per 1e8 persons: a few
+// hundred hot cells serialise in L2.)
+struct StagedAcc {
+  double *f;
+  int *i;
+  int n_f;
+  // one-entry write-combining cache for the `dstart` counter: consecutive +1s
+  // to the same cell (every person's first interval starts in the same cell)
+  // cost nothing until the cell changes
+  int pend_idx;
+  int pend_n;
+  __device__ __forceinline__ void addf(int idx, double v) { atomicAdd(&f[idx], v); }
+  __device__ __forceinline__ void addi(int idx, int v) { atomicAdd(&i[idx - n_f], v); }
+  __device__ __forceinline__ void addc(int idx) {
+    if (idx == pend_idx) {
+      pend_n++;
+    } else {
+      if (pend_n) atomicAdd(&i[pend_idx - n_f], pend_n);
+      pend_idx = idx;
+      pend_n = 1;
+    }
+  }
+  __device__ __forceinline__ void flush() {
+    if (pend_n) atomicAdd(&i[pend_idx - n_f], pend_n);
+    pend_n = 0;
+    pend_idx = -1;
+  }
+};
+
+struct StagedEnv {
+  typedef MrgSource Src;
+  Src src;
+  unsigned outputs;
+  const ReportGeom *geom;
+  StagedAcc acc;
+  ReportCursor cursor;
+  // per-kind tallies: eight 16-bit fields in two words (each kind occurs at most once per person)
+  unsigned long long kinds_lo, kinds_hi;
+  double sum_end;
+  // row log of the person in hand
+  int nrows;
+  double first_end;
+  unsigned first_tag;
+  WarpQueues *wq;
+  int lane;
+
+  __device__ __forceinline__ void begin_person() {
+    cursor.valid = false;
+    nrows = 0;
+  }
+  __device__ __forceinline__ void row(double, double start, double end, int state, int kind) {
+    if (outputs & 4u) {
+      const unsigned long long inc = 1ull << ((kind & 3) * 16);
+      if (kind < 4) kinds_lo += inc;
+      else kinds_hi += inc;
+      sum_end += end;
+    }
+    if (outputs & 1u) {
+      if (nrows == 0) {
+        first_end = end;
+        first_tag = (unsigned)kind | ((unsigned)state << 4);
+      } else if (nrows <= XROWS) {
+        wq->x_start[nrows - 1][lane] = start;
+        wq->x_end[nrows - 1][lane] = end;
+        wq->x_meta[nrows - 1][lane] = ((unsigned)nrows << 16) | ((unsigned)state << 8) | (unsigned)kind;
+      }
+      nrows++;
+    }
+  }
+  __device__ __forceinline__ void report(int state, int kind, double lhs, double rhs) {
+    if (outputs & 2u) report_add(*geom, acc, cursor, state, kind, lhs, rhs);
+  }
+};
+
+// a finished person's first row and row count (rows beyond the first stay staged until the warp appends them)
+__device__ __forceinline__ void staged_finish(const StagedParams &p, StagedEnv &env, uint32_t idx, int *err) {
+  if (p.outputs & 1u) {
+    if (env.nrows > XROWS + 1) *err = -4;
+    const int extra = env.nrows > 0 ? (env.nrows > XROWS + 1 ? XROWS : env.nrows - 1) : 0;
+    p.first_end[idx] = env.first_end;
+    p.first_tag[idx] = (unsigned short)(env.first_tag | ((unsigned)extra << 8) | (env.nrows > 0 ? 0x8000u : 0u));
+  }
+}
+
+// the warp appends its lanes' staged extra rows to the overflow list
+__device__ __forceinline__ void staged_append_extra(const StagedParams &p, StagedEnv &env, bool active, uint32_t idx, int lane) {
+  const int cnt = active ? (env.nrows > XROWS + 1 ? XROWS : (env.nrows > 1 ? env.nrows - 1 : 0)) : 0;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int tot = __shfl_sync(0xffffffffu, incl, 31);
+  if (tot == 0) return;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(p.ov_count, (unsigned long long)tot);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  const unsigned long long at = base + (unsigned)(incl - cnt);
+  for (int r = 0; r < cnt; r++) {
+    if (at + r < (unsigned long long)p.ov_cap) {
+      p.ov_idx[at + r] = idx;
+      p.ov_tag[at + r] = env.wq->x_meta[r][lane];
+      p.ov_start[at + r] = env.wq->x_start[r][lane];
+      p.ov_end[at + r] = env.wq->x_end[r][lane];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const __grid_constant__ StagedParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // shared layout: [per-warp queues | dense doubles | dense ints]
+  WarpQueues *queues = reinterpret_cast<WarpQueues *>(smem_raw);
+  const int total = (p.outputs & 2u) ? p.geom.total : 0;
+  const int n_f = (p.outputs & 2u) ? p.geom.off_dstart : 0;
+  double *s_f = reinterpret_cast<double *>(smem_raw + sizeof(WarpQueues) * SWARPS);
+  int *s_i = reinterpret_cast<int *>(s_f + n_f);
+  __shared__ unsigned s_kind[8];
+  __shared__ double s_sum[SWARPS];
+  __shared__ int s_error;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  WarpQueues &Q = queues[warp];
+  if (tid < 8) s_kind[tid] = 0;
+  if (tid == 0) s_error = 0;
+  for (int k = tid; k < n_f; k += SBLOCK) s_f[k] = 0.0;
+  for (int k = tid; k < total - n_f; k += SBLOCK) s_i[k] = 0;
+  __syncthreads();
+
+  StagedEnv env;
+  env.outputs = p.outputs;
+  env.geom = &p.geom;
+  env.acc.f = s_f;
+  env.acc.i = s_i;
+  env.acc.n_f = n_f;
+  env.acc.pend_idx = -1;
+  env.acc.pend_n = 0;
+  env.kinds_lo = env.kinds_hi = 0;
+  env.sum_end = 0.0;
+  env.nrows = 0;
+  env.first_end = 0.0;
+  env.first_tag = 0;
+  env.wq = &Q;
+  env.lane = lane;
+  env.cursor.valid = false;
+  int err = 0;
+  const person_r::Consts &K = p.consts;
+
+  Mrg32k3a sub = thread_start_state(p.st, blockIdx.x * SBLOCK + tid);
+  const int64_t n_tiles = (p.n + 31) / 32;
+  const int64_t gw = (int64_t)blockIdx.x * SWARPS + warp, GW = (int64_t)gridDim.x * SWARPS;
+  int c1 = 0, c2 = 0;  // queue fills (warp-uniform)
+
+  // ---- stage B2 on the top `m` (<= 32) entries of queue 2
+  auto run_b2 = [&](int m) {
+    c2 -= m;
+    const bool act = lane < m;
+    uint32_t idx = 0;
+    if (act) {
+      const int e = c2 + lane;
+      person_r::ParkedLoop in;
+#pragma unroll
+      for (int k = 0; k < 6; k++) in.g.s[k] = Q.q2_s[k][e];
+      in.t_onset = Q.q2_on[e];
+      in.t_death = Q.q2_t[e];
+      idx = Q.q2_idx[e];
+      person_r::stage_b2(env, K, p.first_person + idx, in, &err);
+      staged_finish(p, env, idx, &err);
+    }
+    __syncwarp();
+    if (p.outputs & 1u) staged_append_extra(p, env, act, idx, lane);
+    __syncwarp();
+  };
+
+  // ---- stage B1 on the top `m` (<= 32) entries of queue 1; survivors go to queue 2
+  auto run_b1 = [&](int m) {
+    c1 -= m;
+    const bool act = lane < m;
+    bool park = false;
+    person_r::ParkedLoop out;
+    uint32_t idx = 0;
+    if (act) {
+      const int e = c1 + lane;
+      person_r::ParkedOnset in;
+#pragma unroll
+      for (int k = 0; k < 6; k++) in.g.s[k] = Q.q1_s[k][e];
+      in.u_onset = Q.q1_u[e];
+      in.t_death = Q.q1_t[e];
+      idx = Q.q1_idx[e];
+      park = !person_r::stage_b1(env, K, p.first_person + idx, in, &out);
+      if (!park) staged_finish(p, env, idx, &err);
+    }
+    __syncwarp();
+    const unsigned mk = __ballot_sync(0xffffffffu, park);
+    if (park) {
+      const int e = c2 + __popc(mk & lt_mask);
+#pragma unroll
+      for (int k = 0; k < 6; k++) Q.q2_s[k][e] = out.g.s[k];
+      Q.q2_on[e] = out.t_onset;
+      Q.q2_t[e] = out.t_death;
+      Q.q2_idx[e] = idx;
+    }
+    c2 += __popc(mk);
+    __syncwarp();
+  };
+
+  // One loop body for all three stages (each stage's code exists once): new
+  // persons while there are tiles, parked persons whenever a full warp of them
+  // waits, and whatever is left once the tiles are used up.
+  for (int64_t tile = gw;;) {
+    const bool fresh = tile < n_tiles;
+    if (fresh) {
+      // ---- stage A on 32 new persons
+      const int64_t i64 = tile * 32 + lane;
+      const uint32_t idx = (uint32_t)i64;
+      bool park = false;
+      person_r::ParkedOnset out;
+      if (i64 < p.n) {
+        env.src.g = sub;
+        park = !person_r::stage_a(env, K, p.first_person + i64, &out);
+        if (!park) staged_finish(p, env, idx, &err);
+      }
+      sub.jump(p.st.stride);
+      const unsigned mk = __ballot_sync(0xffffffffu, park);
+      if (park) {
+        const int e = c1 + __popc(mk & lt_mask);
+#pragma unroll
+        for (int k = 0; k < 6; k++) Q.q1_s[k][e] = out.g.s[k];
+        Q.q1_u[e] = out.u_onset;
+        Q.q1_t[e] = out.t_death;
+        Q.q1_idx[e] = idx;
+      }
+      c1 += __popc(mk);
+      __syncwarp();
+      tile += GW;
+    }
+    const bool last = tile >= n_tiles;
+    if (c1 >= 32 || (last && c1 > 0)) run_b1(c1 > 32 ? 32 : c1);
+    if (c2 >= 32 || (last && c1 == 0 && c2 > 0)) run_b2(c2 > 32 ? 32 : c2);
+    if (last && c1 == 0 && c2 == 0) break;
+  }
+
+  env.acc.flush();
+  if (err) atomicCAS(&s_error, 0, err);
+  if (p.outputs & 4u) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      unsigned v = (unsigned)(((k < 4 ? env.kinds_lo : env.kinds_hi) >> ((k & 3) * 16)) & 0xffffull);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && v) atomicAdd(&s_kind[k], v);
+    }
+    double v = env.sum_end;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_sum[warp] = v;
+  }
+  __syncthreads();
+  for (int k = tid; k < n_f; k += SBLOCK) {
+    const double v = s_f[k];
+    if (v != 0.0) atomicAdd(&p.dense[k], v);
+  }
+  for (int k = tid; k < total - n_f; k += SBLOCK) {
+    const int v = s_i[k];
+    if (v != 0) atomicAdd(&p.dense[n_f + k], (double)v);
+  }
+  if (p.outputs & 4u) {
+    if (tid < 8 && s_kind[tid]) atomicAdd(&p.counts[tid], (double)s_kind[tid]);
+    if (tid == 0) {
+      double t = 0;
+      for (int w = 0; w < SWARPS; w++) t += s_sum[w];
+      atomicAdd(&p.counts[8], t);
+    }
+  }
+  if (tid == 0 && s_error) atomicCAS(p.error, 0, s_error);
+}
+
+// ---- row log passes -----------------------------------------------------------
+
+struct RowPassParams {
+  const double *first_end;
+  const unsigned short *first_tag;
+  const unsigned *ov_idx, *ov_tag;
+  const double *ov_start, *ov_end;
+  const unsigned long long *ov_count;
+  int64_t ov_cap;
+  int64_t n, first_person;
+  unsigned long long *chunk_rows;  // per-chunk totals, then (in place) exclusive offsets
+  unsigned long long *n_rows;
+  int64_t n_chunks;
+  unsigned *row_off;  // [n] a person's first row, relative to its chunk
+  double *rowlog;     // 5 columns (endTime, event, id, startTime, state), column stride `capacity`
+  int64_t capacity;
+};
+
+__device__ __forceinline__ int tag_rows(unsigned short t) { return (t & 0x8000u) ? 1 + ((t >> 8) & 7) : 0; }
+
+// rows per chunk of ROW_CHUNK persons
+__global__ void __launch_bounds__(256) rowpass_count_kernel(RowPassParams p) {
+  __shared__ unsigned s_w[8];
+  const int64_t lo = (int64_t)blockIdx.x * ROW_CHUNK;
+  unsigned v = 0;
+  for (int k = threadIdx.x; k < ROW_CHUNK; k += 256) {
+    int64_t i = lo + k;
+    if (i < p.n) v += tag_rows(p.first_tag[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; w++) t += s_w[w];
+    p.chunk_rows[blockIdx.x] = t;
+  }
+}
+
+// one block: exclusive scan of the chunk totals in place; total row count out
+__global__ void __launch_bounds__(1024) rowpass_scan_kernel(RowPassParams p) {
+  __shared__ unsigned long long s_w[32];
+  __shared__ unsigned long long s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int64_t c0 = 0; c0 < p.n_chunks; c0 += 1024) {
+    int64_t c = c0 + tid;
+    unsigned long long v = (c < p.n_chunks) ? p.chunk_rows[c] : 0, incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    unsigned long long woff = 0;
+    for (int w = 0; w < warp; w++) woff += s_w[w];
+    unsigned long long carry = s_carry;
+    if (c < p.n_chunks) p.chunk_rows[c] = carry + woff + incl - v;
+    __syncthreads();
+    if (tid == 1023) s_carry = carry + woff + incl;
+    __syncthreads();
+  }
+  if (tid == 0) *p.n_rows = s_carry;
+}
+
+// first rows -> final columns; every person's row offset within its chunk
+__global__ void __launch_bounds__(256) rowpass_first_kernel(RowPassParams p) {
+  __shared__ unsigned s_w[8];
+  __shared__ unsigned s_run;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t lo = (int64_t)blockIdx.x * ROW_CHUNK;
+  const unsigned long long base = p.chunk_rows[blockIdx.x];
+  if (tid == 0) s_run = 0;
+  __syncthreads();
+  for (int k0 = 0; k0 < ROW_CHUNK; k0 += 256) {
+    const int64_t i = lo + k0 + tid;
+    unsigned short tag = 0;
+    double end = 0.0;
+    if (i < p.n) {
+      tag = p.first_tag[i];
+      end = p.first_end[i];
+    }
+    const unsigned cnt = tag_rows(tag);
+    unsigned incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    unsigned off = s_run + incl - cnt;
+    for (int w = 0; w < warp; w++) off += s_w[w];
+    if (i < p.n) {
+      p.row_off[i] = off;
+      const unsigned long long g = base + off;
+      if (cnt && g < (unsigned long long)p.capacity) {
+        p.rowlog[0 * p.capacity + g] = end;
+        p.rowlog[1 * p.capacity + g] = (double)(tag & 0xf);
+        p.rowlog[2 * p.capacity + g] = (double)(p.first_person + i);
+        p.rowlog[3 * p.capacity + g] = 0.0;  // a person's first interval starts at startTime = 0 (microsimulation.h:430)
+        p.rowlog[4 * p.capacity + g] = (double)((tag >> 4) & 0xf);
+      }
+    }
+    __syncthreads();
+    if (tid == 255) s_run = off + cnt;
+    __syncthreads();
+  }
+}
+
+// overflow rows -> their place behind their person's first row
+__global__ void __launch_bounds__(256) rowpass_scatter_kernel(RowPassParams p) {
+  unsigned long long m = *p.ov_count;
+  if (m > (unsigned long long)p.ov_cap) m = (unsigned long long)p.ov_cap;
+  for (unsigned long long e = (unsigned long long)blockIdx.x * 256 + threadIdx.x; e < m; e += (unsigned long long)gridDim.x * 256) {
+    const unsigned idx = p.ov_idx[e], tag = p.ov_tag[e];
+    const unsigned long long g = p.chunk_rows[idx / ROW_CHUNK] + p.row_off[idx] + (tag >> 16);
+    if (g < (unsigned long long)p.capacity) {
+      p.rowlog[0 * p.capacity + g] = p.ov_end[e];
+      p.rowlog[1 * p.capacity + g] = (double)(tag & 0xff);
+      p.rowlog[2 * p.capacity + g] = (double)(p.first_person + idx);
+      p.rowlog[3 * p.capacity + g] = p.ov_start[e];
+      p.rowlog[4 * p.capacity + g] = (double)((tag >> 8) & 0xff);
+    }
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace msim

@@ -3,24 +3,36 @@
 // SummaryReport::add (:1070-1107).
 //
 // The reference walks every age bin between the previous event and this one
-// (~70 hash-map updates per person).  Here an interval [lhs, rhs] touches a
-// fixed number of cells:
-//   events[state][event][hi]            += 1                (hi = bin of rhs)
-//   pt / ut partial sums at bins lo, hi += the two partial overlaps
-//   touch[lo], touch[hi]                += 1   (the reference emits a pt/ut row
-//                                               for every bin it visited, even
-//                                               when it added 0.0)
-//   dfull[lo+1] += 1, dfull[hi] -= 1           difference array: bins fully
-//                                               covered; each adds exactly one
-//                                               bin width (and its discounted
-//                                               width) at finalisation
-//   dprev[p0] += 1, dprev[p1+1] -= 1           difference array over the bins
-//                                               whose left edge lies in [lhs, rhs)
-// All cells live in one vector of doubles per report ("dense accumulators");
-// counts are integer-valued doubles (< 2^53), so sums are exact and
-// order-independent, and ONE all-reduce(sum, f64) merges shards.  Finalisation
-// (prefix sums, widths, sparse rows in std::map order) happens once on the
-// host: dense_to_report() in capi.cu.
+// (~70 hash-map updates per person).  Here an interval [lhs, rhs] in state s
+// ending with event e touches a fixed, small number of cells.  With
+// lo = bin(lhs), hi = bin(rhs), plo/phi the left edges of those bins,
+// on_edge = (lhs <= plo)  (the interval starts exactly on a partition point,
+// e.g. every person's first interval starts at age 0):
+//
+//   events[s][e][hi] += 1
+//   dstart[s][f0]    += 1     f0 = first bin the interval covers COMPLETELY
+//                             (lo if on_edge else lo+1), clipped to hi.
+//        The number of intervals covering bin b completely is then
+//        full[b] = sum_{j<=b} dstart[s][j] - sum_{j<=b} sum_e events[s][e][j]
+//        (each interval stops covering whole bins at its own hi), and every
+//        such interval adds exactly one bin width (and its discounted width).
+//   pt/ut[s][lo]     += the partial overlap with bin lo   (only if !on_edge, lo < hi)
+//   pt/ut[s][hi]     += the partial overlap with bin hi
+//   noedge[s][hi]    += 1     only in the RARE case that the interval does not
+//                             contain hi's left edge (phi < lhs, or phi == rhs);
+//        prevalence (cadlag, lhs <= edge < rhs) is then
+//        prev[b] = full[b] + sum_e events[s][e][b] - noedge[s][b].
+//   The reference emits a pt/ut row for every bin an interval visited, even
+//   with value 0.0: bin b has a row iff full[b] > 0, or an interval ended in it
+//   (events > 0), or it received a lo-side partial (always > 0).
+//
+// So a person's first interval costs 2 counter updates + 2 FP sums; exp() is
+// needed once per event (exp(-alpha*rhs); the left edges come from a table and
+// exp(-alpha*lhs) is the previous event's value).  All cells live in ONE
+// vector of doubles ("dense accumulators"); counters are integer-valued
+// doubles (< 2^53), so their sums are exact and order-independent, and ONE
+// all-reduce(sum, f64) merges shards.  Finalisation (prefix sums, widths,
+// sparse rows in std::map order) happens once on the host: report_host.h.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -32,12 +44,15 @@ namespace msim {
 constexpr int REPORT_MAX_BINS = 128;
 
 struct ReportGeom {
-  int n_state, n_event, n_bin;  // n_bin = number of partition points (bins are [part[i], part[i+1]))
+  int n_state, n_event, n_bin;    // n_bin = number of partition points (bins are [part[i], part[i+1]))
   double part_start, part_delta;  // partition = start + i*delta for i < n_bin-1, then part_last
+  double part_inv_delta;          // 1/delta: first guess of a bin index (corrected by comparison)
   double part_last;
-  double discount_rate, alpha;  // alpha = log(1 + discount_rate), computed on the host
-  // offsets (in doubles) into the dense vector
-  int off_pt, off_ut, off_touch, off_dfull, off_dprev, off_events, total;
+  double discount_rate, alpha, inv_alpha;  // alpha = log(1 + discount_rate), inv_alpha = 1/alpha (host libm)
+  // offsets (in doubles) into the dense vector; FP sums first, then counters
+  int off_pt, off_ut, off_dstart, off_noedge, off_events, total;
+  // exp(-alpha*part[i]) for every partition point, evaluated once on the host
+  double edge_decay[REPORT_MAX_BINS];
 };
 
 inline ReportGeom make_report_geom(int n_state, int n_event, int n_bin, double start, double delta, double last,
@@ -48,17 +63,22 @@ inline ReportGeom make_report_geom(int n_state, int n_event, int n_bin, double s
   g.n_bin = n_bin;
   g.part_start = start;
   g.part_delta = delta;
+  g.part_inv_delta = 1.0 / delta;
   g.part_last = last;
   g.discount_rate = discount_rate;
   g.alpha = log(1.0 + discount_rate);
+  g.inv_alpha = discount_rate != 0.0 ? 1.0 / g.alpha : 0.0;
   int sb = n_state * n_bin;
   g.off_pt = 0;
   g.off_ut = g.off_pt + sb;
-  g.off_touch = g.off_ut + sb;
-  g.off_dfull = g.off_touch + sb;
-  g.off_dprev = g.off_dfull + n_state * (n_bin + 1);
-  g.off_events = g.off_dprev + n_state * (n_bin + 1);
+  g.off_dstart = g.off_ut + sb;
+  g.off_noedge = g.off_dstart + sb;
+  g.off_events = g.off_noedge + sb;
   g.total = g.off_events + n_state * n_event * n_bin;
+  for (int i = 0; i < REPORT_MAX_BINS; i++) {
+    double p = (i >= n_bin - 1) ? last : start + i * delta;
+    g.edge_decay[i] = (discount_rate != 0.0) ? exp(-p * g.alpha) : 1.0;
+  }
   return g;
 }
 
@@ -68,64 +88,85 @@ MSIM_HD double report_part(const ReportGeom &g, int i) {
 
 // index of the largest partition point <= x (set<greater>::lower_bound, :937-938)
 MSIM_HD int report_bin(const ReportGeom &g, double x) {
-  int nb = g.n_bin;
-  int i = (int)floor((x - g.part_start) / g.part_delta);
-  if (i < 0) i = 0;
-  if (i > nb - 2) i = nb - 2;
+  const int nb = g.n_bin;
+  double y = (x - g.part_start) * g.part_inv_delta;
+  int i = (y > 0.0) ? ((y < (double)(nb - 2)) ? (int)y : nb - 2) : 0;
   while (i + 1 < nb && report_part(g, i + 1) <= x) i++;
   while (i > 0 && report_part(g, i) > x) i--;
   return i;
 }
 
-// EventReport::discountedUtilities (microsimulation.h:917-928)
+// exp(-alpha*t): the one transcendental an event needs when utilities are discounted
+MSIM_HD double report_decay(const ReportGeom &g, double t) { return exp(-t * g.alpha); }
+
+// EventReport::discountedUtilities (microsimulation.h:917-928) with the two
+// exponentials passed in: utility/alpha*(exp(-a*alpha) - exp(-b*alpha))
+MSIM_HD double report_discounted_e(const ReportGeom &g, double a, double b, double ea, double eb) {
+  if (a == b) return 0.0;
+  return g.inv_alpha * (ea - eb);
+}
 MSIM_HD double report_discounted(const ReportGeom &g, double a, double b, double utility) {
   if (g.discount_rate == 0.0) return utility * (b - a);
   if (a == b) return 0.0;
   return utility / g.alpha * (exp(-a * g.alpha) - exp(-b * g.alpha));
 }
 
-// Acc supplies addf(index, double) and addi(index, int) on the dense vector
-// (shared-memory atomics on the device).
+// What a process remembers between two of its report() calls: the previous
+// interval's right end, its bin and exp(-alpha*rhs) are this interval's left
+// end (previousEventTime), so neither the bin search nor the exponential is
+// repeated.  `valid` is cleared at the start of every person.
+struct ReportCursor {
+  double t, e;
+  int bin;
+  bool valid;
+};
+
+// Acc supplies addf(index, double) for FP sums, addi(index, int) for counters
+// and addc(index) for the `dstart` counter (+1; consecutive calls usually name
+// the same cell, which an accumulator may exploit) on the dense vector.
 template <class Acc>
-MSIM_DEV void report_add(const ReportGeom &g, Acc &acc, int state, int event, double lhs, double rhs) {
+MSIM_DEV void report_add(const ReportGeom &g, Acc &acc, ReportCursor &cur, int state, int event, double lhs, double rhs) {
   const int nb = g.n_bin;
   const bool disc = g.discount_rate != 0.0;  // rate 0: ut == pt, filled in at finalisation
-  int lo = report_bin(g, lhs);
-  int hi = report_bin(g, rhs);
-  acc.addi(g.off_events + (state * g.n_event + event) * nb + hi, 1);
+  int lo;
+  double elhs = 1.0;
+  if (cur.valid && cur.t == lhs) {
+    lo = cur.bin;
+    elhs = cur.e;
+  } else {
+    lo = report_bin(g, lhs);
+    if (disc) elhs = report_decay(g, lhs);
+  }
+  const int hi = report_bin(g, rhs);
+  const double erhs = disc ? report_decay(g, rhs) : 1.0;
+  cur.t = rhs;
+  cur.e = erhs;
+  cur.bin = hi;
+  cur.valid = true;
+
   const int row = state * nb;
-  const int drow = state * (nb + 1);
-  double plo = report_part(g, lo);
+  const double plo = report_part(g, lo);
+  const bool on_edge = lhs <= plo;
+  acc.addi(g.off_events + (state * g.n_event + event) * nb + hi, 1);
+  int f0 = on_edge ? lo : lo + 1;
+  if (f0 > hi) f0 = hi;
+  acc.addc(g.off_dstart + row + f0);
   if (lo == hi) {
-    double a = lhs > plo ? lhs : plo;
-    acc.addi(g.off_touch + row + lo, 1);
-    acc.addf(g.off_pt + row + lo, rhs - a);
-    if (disc) acc.addf(g.off_ut + row + lo, report_discounted(g, a, rhs, 1.0));
-    if (lhs <= plo && plo < rhs) {  // cadlag prevalence at the bin's left edge
-      acc.addi(g.off_dprev + drow + lo, 1);
-      acc.addi(g.off_dprev + drow + lo + 1, -1);
-    }
+    const double a = on_edge ? plo : lhs;
+    acc.addf(g.off_pt + row + hi, rhs - a);
+    if (disc) acc.addf(g.off_ut + row + hi, report_discounted_e(g, a, rhs, on_edge ? g.edge_decay[lo] : elhs, erhs));
+    if (!(on_edge && plo < rhs)) acc.addi(g.off_noedge + row + hi, 1);
     return;
   }
-  double a = lhs > plo ? lhs : plo;
-  double nxt = report_part(g, lo + 1);
-  double phi = report_part(g, hi);
-  acc.addi(g.off_touch + row + lo, 1);
-  acc.addf(g.off_pt + row + lo, nxt - a);
-  if (disc) acc.addf(g.off_ut + row + lo, report_discounted(g, a, nxt, 1.0));
-  acc.addi(g.off_touch + row + hi, 1);
+  if (!on_edge) {
+    const double nxt = report_part(g, lo + 1);
+    acc.addf(g.off_pt + row + lo, nxt - lhs);
+    if (disc) acc.addf(g.off_ut + row + lo, report_discounted_e(g, lhs, nxt, elhs, g.edge_decay[lo + 1]));
+  }
+  const double phi = report_part(g, hi);
   acc.addf(g.off_pt + row + hi, rhs - phi);
-  if (disc) acc.addf(g.off_ut + row + hi, report_discounted(g, phi, rhs, 1.0));
-  if (hi > lo + 1) {
-    acc.addi(g.off_dfull + drow + lo + 1, 1);
-    acc.addi(g.off_dfull + drow + hi, -1);
-  }
-  int p0 = (lhs <= plo) ? lo : lo + 1;
-  int p1 = (phi < rhs) ? hi : hi - 1;
-  if (p0 <= p1) {
-    acc.addi(g.off_dprev + drow + p0, 1);
-    acc.addi(g.off_dprev + drow + p1 + 1, -1);
-  }
+  if (disc) acc.addf(g.off_ut + row + hi, report_discounted_e(g, phi, rhs, g.edge_decay[hi], erhs));
+  if (!(phi < rhs)) acc.addi(g.off_noedge + row + hi, 1);
 }
 
 }  // namespace msim

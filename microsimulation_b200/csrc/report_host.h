@@ -79,20 +79,24 @@ inline void dense_to_report_impl(const double *d, const ReportGeom &G, msim_repo
     }
   if (any_event) {
     for (int s = 0; s < G.n_state; s++) {
-      double full = 0, pv = 0;
+      double starts = 0, ends = 0;  // running sums of dstart and of the intervals ended so far
       for (int b = 0; b < nb; b++) {
-        full += d[G.off_dfull + s * (nb + 1) + b];
-        pv += d[G.off_dprev + s * (nb + 1) + b];
-        double touch = d[G.off_touch + s * nb + b];
-        double age = report_part(G, b);
-        if (touch + full > 0) {
+        double ended = 0;  // intervals in state s that end in bin b
+        for (int e = 0; e < G.n_event; e++) ended += d[G.off_events + (s * G.n_event + e) * nb + b];
+        starts += d[G.off_dstart + s * nb + b];
+        ends += ended;
+        const double full = starts - ends;  // intervals that cover bin b completely
+        const double pv = full + ended - d[G.off_noedge + s * nb + b];
+        const double part = d[G.off_pt + s * nb + b];
+        const double age = report_part(G, b);
+        if (full > 0 || ended > 0 || part != 0) {  // the bins EventReport::add visited
           double width = 0, dwidth = 0;
           if (full > 0) {
             double nxt = report_part(G, b + 1);
             width = nxt - age;
             dwidth = report_discounted(G, age, nxt, 1.0);
           }
-          double ptv = d[G.off_pt + s * nb + b] + full * width;
+          double ptv = part + full * width;
           double utv = (G.discount_rate == 0.0) ? ptv : d[G.off_ut + s * nb + b] + full * dwidth;
           pt.insert(pt.end(), {(double)s, age, ptv});
           ut.insert(ut.end(), {(double)s, age, utv});

@@ -41,7 +41,7 @@ def person_dims(with_report):
     d = DenseDims(8, 8, 102, 0)
     if with_report:
         sb = 8 * 102
-        cells = 3 * sb + 2 * 8 * 103 + 8 * 8 * 102
+        cells = 4 * sb + 8 * 8 * 102  # pt, ut, dstart, noedge + events (csrc/report.cuh)
     d.n_doubles = cells + 9
     return d
 

@@ -5,13 +5,16 @@ import numpy as np
 import microsimulation_b200 as m
 import microsimulation_b200.api as api
 m.init(0)
-for n in (10**7, 10**8):
+for sched in ("staged", "generic"):
+  api.set_person_schedule(sched)
+  for n in (10**7, 10**8):
     for outputs, nm in ((4, "counts"), (1, "rowlog"), (2 | 4, "report+counts"), (1 | 2 | 4, "all")):
         best = 1e9
         for rep_ in range(3):
             res = api.person_run_device(12345, 0, n, outputs, 0.03)
             best = min(best, api.last_kernel_ms())
-        print("person n=%g %-14s %.3f ms  %.3e persons/s rows=%d" % (n, nm, best, n / best * 1e3, res.n_rows), flush=True)
+        print("%s person n=%g %-14s %.3f ms  %.3e persons/s rows=%d" % (sched, n, nm, best, n / best * 1e3, res.n_rows), flush=True)
+api.set_person_schedule("staged")
 t0 = time.time(); g = m.callPersonSimulation(10**7); t1 = time.time()
 t0 = time.time(); g = m.callPersonSimulation(10**7); t1 = time.time()
 print("e2e callPersonSimulation(1e7) warm: %.3f s rows %d" % (t1 - t0, len(g["id"])))

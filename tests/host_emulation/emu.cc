@@ -18,6 +18,7 @@
 #include "../../include/msim.h"
 #include "../../microsimulation_b200/csrc/host_state.h"
 #include "../../microsimulation_b200/csrc/models.cuh"
+#include "../../microsimulation_b200/csrc/person_staged.cuh"
 #include "../../microsimulation_b200/csrc/report.cuh"
 #include "../../microsimulation_b200/csrc/report_host.h"
 #include "../../microsimulation_b200/csrc/seqstream.cuh"
@@ -33,6 +34,7 @@ struct PlainAcc {
   double *d;
   void addf(int idx, double v) { d[idx] += v; }
   void addi(int idx, int v) { d[idx] += v; }
+  void addc(int idx) { d[idx] += 1; }
 };
 
 struct Rows {
@@ -48,6 +50,8 @@ struct HostEnv {
   const ReportGeom *geom;
   PlainAcc acc;
   double *counts;
+  ReportCursor cursor;
+  void begin_person() { cursor.valid = false; }
   void row(double id, double start, double end, int state, int kind) {
     if (outputs & OUT_COUNTS) {
       counts[kind] += 1;
@@ -62,7 +66,7 @@ struct HostEnv {
     }
   }
   void report(int state, int kind, double lhs, double rhs) {
-    if (outputs & OUT_REPORT) report_add(*geom, acc, state, kind, lhs, rhs);
+    if (outputs & OUT_REPORT) report_add(*geom, acc, cursor, state, kind, lhs, rhs);
   }
 };
 
@@ -70,6 +74,7 @@ template <class SrcT>
 struct HostNullEnv {
   typedef SrcT Src;
   Src src;
+  void begin_person() {}
   void row(double, double, double, int, int) {}
   void report(int, int, double, double) {}
 };
@@ -90,7 +95,7 @@ const Tables &tables() {
   return T;
 }
 
-void make_start(const double seed[6], int64_t first_person_plus, int grid, StreamStart *st) {
+void make_start(const double seed[6], int64_t first_person_plus, int grid, StreamStart *st, int block = BLOCK) {
   uint32_t s[6];
   seed_to_u32(seed, s);
   Mrg32k3a b;
@@ -99,7 +104,7 @@ void make_start(const double seed[6], int64_t first_person_plus, int grid, Strea
   memcpy(st->base, b.s, sizeof b.s);
   st->lo = tables().lo.data();
   st->hi = tables().hi.data();
-  st->stride = mrg_jump_pow(mrg_substream_jump(), (uint64_t)grid * BLOCK);
+  st->stride = mrg_jump_pow(mrg_substream_jump(), (uint64_t)grid * block);
 }
 
 void rows_to_table(const Rows &r, const char *const *cols, msim_table *t) {
@@ -279,6 +284,85 @@ int emu_person_run(const msim_person_shard *sh, int grid, msim_table *rowlog, do
         sub.jump(st.stride);
       }
     }
+  if (counts) memcpy(counts, cnt, sizeof cnt);
+  if (rowlog) {
+    sort_rows_by_person(rows);
+    static const char *const cols[5] = {"endTime", "event", "id", "startTime", "state"};
+    rows_to_table(rows, cols, rowlog);
+  }
+  if (report) dense_to_report_impl(dense.data(), geom, report);
+  return 0;
+}
+
+// The staged schedule of person_staged.cuh, one warp at a time, lanes in order:
+// the same stage functions and the same queue discipline (push by lane order,
+// pop the top <= 32 entries) as person_staged_kernel.
+int emu_person_run_staged(const msim_person_shard *sh, int grid, msim_table *rowlog, double counts[9], msim_report *report) {
+  if (!mrg_seed_ok(sh->seed)) return MSIM_ERR_SEED;
+  const int SB = 128, SW = 4;
+  StreamStart st;
+  make_start(sh->seed, sh->first_person + 1, grid, &st, SB);
+  person_r::Consts K = person_r::make_consts();
+  ReportGeom geom = ages_geom(person_r::N_STATE, person_r::N_EVENT, sh->discount_rate);
+  std::vector<double> dense(geom.total, 0.0);
+  Rows rows;
+  typedef HostEnv<MrgSource> Env;
+  Env env;
+  env.outputs = sh->outputs;
+  env.rows = &rows;
+  env.geom = &geom;
+  env.acc.d = dense.data();
+  double cnt[9] = {0};
+  env.counts = cnt;
+  const int64_t n_tiles = (sh->n + 31) / 32, GW = (int64_t)grid * SW;
+  struct E1 {
+    person_r::ParkedOnset p;
+    int64_t idx;
+  };
+  struct E2 {
+    person_r::ParkedLoop p;
+    int64_t idx;
+  };
+  int err = 0;
+  for (int64_t gw = 0; gw < GW; gw++) {
+    Mrg32k3a sub[32];
+    for (int lane = 0; lane < 32; lane++) sub[lane] = thread_start_state(st, (unsigned)(gw * 32 + lane));
+    std::vector<E1> q1;
+    std::vector<E2> q2;
+    for (int64_t tile = gw;;) {
+      if (tile < n_tiles) {
+        for (int lane = 0; lane < 32; lane++) {
+          int64_t i = tile * 32 + lane;
+          if (i < sh->n) {
+            env.src.g = sub[lane];
+            E1 e;
+            e.idx = i;
+            if (!person_r::stage_a(env, K, sh->first_person + i, &e.p)) q1.push_back(e);
+          }
+          sub[lane].jump(st.stride);
+        }
+        tile += GW;
+      }
+      const bool last = tile >= n_tiles;
+      if (q1.size() >= 32 || (last && !q1.empty())) {
+        size_t m = std::min<size_t>(q1.size(), 32), base = q1.size() - m;
+        for (size_t l = 0; l < m; l++) {
+          E2 o;
+          o.idx = q1[base + l].idx;
+          if (!person_r::stage_b1(env, K, sh->first_person + o.idx, q1[base + l].p, &o.p)) q2.push_back(o);
+        }
+        q1.resize(base);
+      }
+      if (q2.size() >= 32 || (last && q1.empty() && !q2.empty())) {
+        size_t m = std::min<size_t>(q2.size(), 32), base = q2.size() - m;
+        for (size_t l = 0; l < m; l++) person_r::stage_b2(env, K, sh->first_person + q2[base + l].idx, q2[base + l].p, &err);
+        q2.resize(base);
+      }
+      if (q1.size() >= 64 || q2.size() >= 64) return -99;  // the kernel's queues hold 64
+      if (last && q1.empty() && q2.empty()) break;
+    }
+  }
+  if (err) return err;
   if (counts) memcpy(counts, cnt, sizeof cnt);
   if (rowlog) {
     sort_rows_by_person(rows);

@@ -16,6 +16,15 @@ pytestmark = pytest.mark.gpu
 TIME_RTOL = 4e-15  # <= ~18 ulp guard; measured max is 2 ulp (4.4e-16)
 
 
+@pytest.fixture(params=["staged", "generic"])
+def pmsim(msim, request):
+    """The product with person-r on either GPU schedule (csrc/person_staged.cuh / the generic cohort kernel)."""
+    import microsimulation_b200.api as api
+    api.set_person_schedule(request.param)
+    yield msim
+    api.set_person_schedule("staged")
+
+
 # ------------------------------------------------------------------ RNG (K1)
 
 @pytest.mark.parametrize("seed,first,n,draws", [(12345, 0, 100000, 8), (12345, 99999000, 5000, 4),
@@ -49,20 +58,20 @@ def test_bad_seed_is_an_error_code(msim):
 # ------------------------------------------------------------------ person-r (config 3)
 
 @pytest.mark.parametrize("n", [0, 1, 20, 255, 256, 257, 1000, 70001])
-def test_person_rowlog_vs_oracle(msim, oracle, n):
-    g, r = msim.callPersonSimulation(n), oracle.callPersonSimulation(n)
+def test_person_rowlog_vs_oracle(pmsim, oracle, n):
+    g, r = pmsim.callPersonSimulation(n), oracle.callPersonSimulation(n)
     assert list(g.keys()) == ["endTime", "event", "id", "startTime", "state"]  # std::map key order, person-r.cc:224
     assert len(g["id"]) == len(r["id"])
     assert_rowlog_close(g, r, TIME_RTOL)
 
 
-def test_person_rowlog_golden(msim, golden):
-    g = msim.callPersonSimulation(2000)
+def test_person_rowlog_golden(pmsim, golden):
+    g = pmsim.callPersonSimulation(2000)
     want = {k: golden["person_n2000_" + k] for k in g}
     assert_rowlog_close(g, want, TIME_RTOL)
 
 
-def test_person_other_seed_and_shard_offset(msim, oracle):
+def test_person_other_seed_and_shard_offset(pmsim, oracle):
     import microsimulation_b200.api as api
     seed = [11, 22, 33, 44, 55, 66]
     api.person_run_device(seed, 123457, 30000, 1 | 4)
@@ -75,9 +84,9 @@ def test_person_other_seed_and_shard_offset(msim, oracle):
 
 
 @pytest.mark.parametrize("rate", [0.0, 0.03])
-def test_person_event_report_vs_oracle(msim, oracle, rate):
+def test_person_event_report_vs_oracle(pmsim, oracle, rate):
     n = 150000
-    rep, counts = msim.person_report(12345, 0, n, rate)
+    rep, counts = pmsim.person_report(12345, 0, n, rate)
     ref = oracle.person_run(12345, 0, n, rowlog=False, report=True, discount_rate=rate)
     assert np.array_equal(counts[:8], ref["counts"][:8])
     assert abs(counts[8] - ref["counts"][8]) <= 1e-12 * ref["counts"][8]
@@ -86,8 +95,8 @@ def test_person_event_report_vs_oracle(msim, oracle, rate):
         assert np.array_equal(rep["ut"]["utility"], rep["pt"]["pt"])  # utility*(b-a) with utility = 1
 
 
-def test_person_report_golden(msim, golden):
-    rep, counts = msim.person_report(12345, 0, 2000, 0.03)
+def test_person_report_golden(pmsim, golden):
+    rep, counts = pmsim.person_report(12345, 0, 2000, 0.03)
     assert np.array_equal(counts[:8], golden["person_n2000_counts"][:8])
     for tb in ("pt", "ut", "events", "prev"):
         for k, v in rep[tb].items():
@@ -98,7 +107,7 @@ def test_person_report_golden(msim, golden):
                 assert np.array_equal(v, w), (tb, k)
 
 
-def test_person_counts_1e6_exact(msim, golden):
+def test_person_counts_1e6_exact(pmsim, golden):
     import microsimulation_b200.api as api
     api.person_run_device(12345, 0, 10 ** 6, 4)
     c = api.person_fetch_counts()
@@ -106,7 +115,7 @@ def test_person_counts_1e6_exact(msim, golden):
     assert abs(c[8] - golden["person_n1e6_counts"][8]) <= 1e-12 * c[8]
 
 
-def test_person_full_size_properties(msim, golden):
+def test_person_full_size_properties(pmsim, golden):
     """BASELINE config 3 (n = 1e7): properties that need no oracle run of that size."""
     import microsimulation_b200.api as api
     n = 10 ** 7
@@ -140,12 +149,53 @@ def test_person_full_size_properties(msim, golden):
     assert np.array_equal(tot[:8], counts[:8])
 
 
-def test_person_report_is_deterministic_in_integer_cells(msim):
-    a, _ = msim.person_report(12345, 0, 300000, 0.0)
-    b, _ = msim.person_report(12345, 0, 300000, 0.0)
+def test_person_report_is_deterministic_in_integer_cells(pmsim):
+    a, _ = pmsim.person_report(12345, 0, 300000, 0.0)
+    b, _ = pmsim.person_report(12345, 0, 300000, 0.0)
     for tb in ("events", "prev"):
         assert np.array_equal(a[tb]["number"], b[tb]["number"])
     np.testing.assert_allclose(a["pt"]["pt"], b["pt"]["pt"], rtol=1e-13)
+
+
+def test_person_schedules_agree_bit_for_bit(msim):
+    """Staged vs generic schedule: same device arithmetic, so rows (times included), counts and every integer
+    table are IDENTICAL; only the order of FP additions into pt/ut differs."""
+    import microsimulation_b200.api as api
+    n, out = 10 ** 6 + 77, {}
+    for sched in ("generic", "staged"):
+        api.set_person_schedule(sched)
+        api.person_run_device(12345, 5, n, 1 | 4)
+        rows, counts = api.person_fetch_rowlog(), api.person_fetch_counts()
+        rep, _ = msim.person_report(12345, 5, n, 0.03)
+        out[sched] = (rows, counts, rep)
+    api.set_person_schedule("staged")
+    (ra, ca, pa), (rb, cb, pb) = out["generic"], out["staged"]
+    for k in ra:
+        assert np.array_equal(ra[k], rb[k]), k
+    assert np.array_equal(ca[:8], cb[:8]) and abs(ca[8] - cb[8]) <= 1e-12 * ca[8]
+    for tb in ("events", "prev"):
+        for k in pa[tb]:
+            assert np.array_equal(pa[tb][k], pb[tb][k]), (tb, k)
+    for tb, k in (("pt", "pt"), ("ut", "utility")):
+        assert np.array_equal(pa[tb]["age"], pb[tb]["age"]) and np.array_equal(pa[tb]["Key"], pb[tb]["Key"])
+        np.testing.assert_allclose(pa[tb][k], pb[tb][k], rtol=1e-11)
+
+
+@pytest.mark.parametrize("sched", ["staged", "generic"])
+def test_person_rowlog_undersized_plan_is_recovered(msim, oracle, sched):
+    """Row-log buffers are sized from a plan (rows per person); a run that needs more is repeated / re-expanded
+    with the exact sizes and returns the same rows."""
+    import microsimulation_b200.api as api
+    api.set_person_schedule(sched)
+    api.set_rowlog_plan(1.01, 0.01)
+    try:
+        g = msim.callPersonSimulation(300000)
+    finally:
+        api.set_rowlog_plan()
+        api.set_person_schedule("staged")
+    r = oracle.callPersonSimulation(300000)
+    assert len(g["id"]) == len(r["id"])
+    assert_rowlog_close(g, r, TIME_RTOL)
 
 
 # ------------------------------------------------------------------ sequential-stream models (configs 1-2)

@@ -108,6 +108,26 @@ def test_emulated_person_r(oracle, emu, first, n, grid):
     emu.emu_report_free(C.byref(r))
 
 
+@pytest.mark.parametrize("first,n,grid", [(0, 20000, 3), (12345, 5000, 40), (0, 1, 1), (7, 255, 2), (0, 257, 1), (3, 0, 1),
+                                          (0, 100000, 7)])
+def test_emulated_person_r_staged_schedule(oracle, emu, first, n, grid):
+    """The staged schedule (stage functions + per-warp queues of person_staged.cuh) gives the reference's
+    rows bit for bit: regrouping persons between stages changes when arithmetic happens, not what is drawn."""
+    seed = (C.c_double * 6)(*[12345.0] * 6)
+    sh = PersonShard(seed, first, n, 7, 0.03)
+    t, r, cnt = Table(), Report(), (C.c_double * 9)()
+    assert emu.emu_person_run_staged(C.byref(sh), C.c_int(grid), C.byref(t), cnt, C.byref(r)) == 0
+    e, er = t.to_dict(), r.to_dict()
+    ref = oracle.person_run(12345, first, n, rowlog=True, report=True, discount_rate=0.03)
+    for k in e:
+        assert np.array_equal(e[k], ref["rowlog"][k]), k
+    assert np.array_equal(np.array(cnt[:8]), ref["counts"][:8])
+    if n:  # FP sums are taken in another order than the reference's person order
+        assert_report_close(er, ref["report"], rtol=1e-10)
+    emu.emu_table_free(C.byref(t))
+    emu.emu_report_free(C.byref(r))
+
+
 @pytest.mark.parametrize("n", [0, 1, 10, 700, 5000, 60000])
 def test_emulated_sequential_stream_models(oracle, emu, n):
     """Per-position draw counts + chunked chain resolution == the reference's person-after-person consumption."""
