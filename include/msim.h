@@ -78,14 +78,20 @@ const char *msim_version(void);
 /* Bind the calling process to a CUDA device (default: device 0 on first use). */
 int msim_init(int device);
 void msim_shutdown(void);
+/* The CUDA stream all work is enqueued on: by default one the library creates;
+ * use_own = 0 makes it `cuda_stream` (a cudaStream_t, e.g. the stream a
+ * caller's NCCL all-reduce runs on, so that the merge needs no host
+ * synchronisation), use_own = 1 returns to the library's own. */
+int msim_set_stream(void *cuda_stream, int use_own);
 /* Number of kernels this library has launched since it was loaded. */
 int64_t msim_launch_count(void);
 
 /* Which GPU schedule the person-r entry points use: 0 (default) = staged
  * (persons are regrouped between stages so that warps stay full,
  * csrc/person_staged.cuh), 1 = generic (one person per thread straight
- * through, the kernel every other model uses).  Same results either way; the
- * switch exists so tests can check exactly that. */
+ * through, the kernel every other model uses), 2 = staged without the per-warp
+ * report tables.  Same results either way; the switch exists so tests can
+ * check exactly that. */
 int msim_set_person_schedule(int which);
 /* Sizing of the person-r row-log buffers: expected rows per person (default
  * 1.25; the model logs 1.232) and expected rows beyond a person's first

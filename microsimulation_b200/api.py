@@ -45,9 +45,14 @@ def launch_count():
     return int(load().msim_launch_count())
 
 
+def set_stream(cuda_stream=None):
+    """Enqueue on `cuda_stream` (an integer cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream); None = own."""
+    check(load().msim_set_stream(C.c_void_p(cuda_stream or 0), C.c_int(1 if cuda_stream is None else 0)))
+
+
 def set_person_schedule(which):
     """0 / "staged" (default) or 1 / "generic": which GPU schedule runs person-r (same results)."""
-    which = {"staged": 0, "generic": 1}.get(which, which)
+    which = {"staged": 0, "generic": 1, "staged-shared": 2}.get(which, which)
     check(load().msim_set_person_schedule(C.c_int(int(which))))
 
 

@@ -32,13 +32,14 @@ struct Ctx {
   bool inited = false;
   int device = 0;
   int sm_count = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
   MrgJump *d_lo = nullptr, *d_hi = nullptr;
   DevBuf rowlog, prov_start, prov_end, prov_meta, tile_count, partial, dense, small, mt_words, len, starts, chain_exit, chain_count, chain_entry, chain_base, calib_out,
       calib_par, uniforms, first_end, first_tag, row_off, ov_idx, ov_tag, ov_start, ov_end;
   int person_kernel = 0;  // 0 = staged schedule (person_staged.cuh), 1 = generic cohort kernel
   bool last_staged = false;
+  int staged_warp_tables = 1;  // 0 switches the per-warp report tables off (experiments)
   double plan_rows = 1.25, plan_extra_rows = 0.26;  // row-log buffer planning (msim_set_rowlog_plan)
   int64_t last_ov_cap = 0, last_ov_rows = 0;
   HostRngState rng;
@@ -98,7 +99,8 @@ int ensure_init() {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, g.device));
   g.sm_count = prop.multiProcessorCount;
-  CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
+  g.stream = g.own_stream;
   CK(cudaEventCreate(&g.ev0));
   CK(cudaEventCreate(&g.ev1));
   // per-thread start tables: lo[j] = M^j, hi[j] = M^(JUMP_TAB*j)
@@ -404,7 +406,16 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
   p.consts = person_r::make_consts();
   p.geom = ages_geom(person_r::N_STATE, person_r::N_EVENT, sh->discount_rate);
   size_t smem = sizeof(WarpQueues) * SWARPS;
-  if (p.outputs & OUT_REPORT) smem += (size_t)p.geom.off_dstart * 8 + (size_t)(p.geom.total - p.geom.off_dstart) * 4;
+  if (p.outputs & OUT_ROWLOG) smem += sizeof(WarpRows) * SWARPS;
+  if (p.outputs & OUT_REPORT) {
+    smem += (size_t)p.geom.off_dstart * 8 + (size_t)(p.geom.total - p.geom.off_dstart) * 4;
+    // per-warp tables for stage A's intervals, unless they would cost a resident block
+    const size_t with = smem + sizeof(WarpHot) * SWARPS;
+    if (g.staged_warp_tables && (with <= 113 * 1024 || smem > 113 * 1024)) {
+      p.warp_tables = 1;
+      smem = with;
+    }
+  }
   int per_sm = 0;
   CK(cudaFuncSetAttribute(person_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, person_staged_kernel, SBLOCK, smem));
@@ -649,12 +660,21 @@ void msim_shutdown(void) {
   g.pin_cache_bytes = 0;
   cudaEventDestroy(g.ev0);
   cudaEventDestroy(g.ev1);
-  cudaStreamDestroy(g.stream);
+  cudaStreamDestroy(g.own_stream);
+  g.stream = g.own_stream = nullptr;
   g.inited = false;
   g.have_last = false;
 }
 
 int64_t msim_launch_count(void) { return g.launches; }
+
+int msim_set_stream(void *cuda_stream, int use_own) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  CK(cudaStreamSynchronize(g.stream));
+  g.stream = use_own ? g.own_stream : (cudaStream_t)cuda_stream;
+  return MSIM_OK;
+}
 
 int msim_set_rowlog_plan(double rows_per_person, double extra_rows_per_person) {
   if (!(rows_per_person > 0) || !(extra_rows_per_person >= 0)) return fail(MSIM_ERR_ARG, "bad plan");
@@ -664,8 +684,9 @@ int msim_set_rowlog_plan(double rows_per_person, double extra_rows_per_person) {
 }
 
 int msim_set_person_schedule(int which) {
-  if (which != 0 && which != 1) return fail(MSIM_ERR_ARG, "schedule must be 0 (staged) or 1 (generic)");
-  g.person_kernel = which;
+  if (which < 0 || which > 2) return fail(MSIM_ERR_ARG, "schedule must be 0 (staged), 1 (generic) or 2 (staged, shared tables only)");
+  g.person_kernel = which == 1 ? 1 : 0;
+  g.staged_warp_tables = which == 2 ? 0 : 1;
   return MSIM_OK;
 }
 

@@ -38,9 +38,10 @@ template <uint32_t C>
 MSIM_HD uint32_t mrg_fold2(uint64_t x) {
   x = (x >> 32) * C + (uint32_t)x;  // < 2^17*C + 2^32 < 2^33
   x = (x >> 32) * C + (uint32_t)x;  // < C + 2^32
-  const uint64_t m = 4294967296ull - C;
-  if (x >= m) x -= m;
-  return (uint32_t)x;
+  // x mod m for x < 2m: x - m = x + C - 2^32, so the reduced value is the low word of
+  // x + C exactly when that sum carries out of 32 bits
+  const uint64_t t = x + C;
+  return (t >> 32) ? (uint32_t)t : (uint32_t)x;
 }
 
 // (a0*s0 + a1*s1 + a2*s2) mod (2^32 - C), all inputs < 2^32.

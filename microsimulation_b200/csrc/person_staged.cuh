@@ -120,8 +120,21 @@ struct alignas(16) WarpQueues {
   uint32_t q2_s[6][QCAP];
   double q2_on[QCAP], q2_t[QCAP];
   uint32_t q2_idx[QCAP];
+};
+// rows a lane logs beyond its person's first, until the warp appends them (row-log runs only)
+struct alignas(16) WarpRows {
   double x_start[XROWS][32], x_end[XROWS][32];
   uint32_t x_meta[XROWS][32];
+};
+// A warp's PRIVATE slice of the report for the commonest interval — a person's
+// first, from the first partition point, in the model's initial state, ended
+// by event `hot_event` — indexed by the age bin it ends in.  Updated with plain
+// loads and stores (no atomics: only this warp touches it, and lanes that hit
+// the same bin are merged first), folded into the block's tables at the end
+// (report runs only).
+struct alignas(16) WarpHot {
+  double pt[REPORT_MAX_BINS], ut[REPORT_MAX_BINS];
+  unsigned ev[REPORT_MAX_BINS];
 };
 
 struct StagedParams {
@@ -140,6 +153,7 @@ struct StagedParams {
   double *ov_start, *ov_end;
   unsigned long long *ov_count;
   int64_t ov_cap;
+  int warp_tables;  // 1: stage A accumulates its intervals in per-warp tables (WarpHot)
 };
 
 // Report accumulators of a block in shared memory ([0, n_f) doubles, then
@@ -187,8 +201,13 @@ struct StagedEnv {
   int nrows;
   double first_end;
   unsigned first_tag;
-  WarpQueues *wq;
+  WarpRows *wq;
   int lane;
+  // stage A with per-warp tables: report() only notes the interval; the warp adds all lanes' together
+  bool defer;
+  bool pend;
+  int pend_state, pend_kind;
+  double pend_lhs, pend_rhs;
 
   __device__ __forceinline__ void begin_person() {
     cursor.valid = false;
@@ -214,9 +233,60 @@ struct StagedEnv {
     }
   }
   __device__ __forceinline__ void report(int state, int kind, double lhs, double rhs) {
-    if (outputs & 2u) report_add(*geom, acc, cursor, state, kind, lhs, rhs);
+    if (!(outputs & 2u)) return;
+    if (defer && !pend) {
+      pend = true;
+      pend_state = state;
+      pend_kind = kind;
+      pend_lhs = lhs;
+      pend_rhs = rhs;
+    } else {
+      report_add(*geom, acc, cursor, state, kind, lhs, rhs);
+    }
   }
 };
+
+// All 32 lanes together add the intervals noted during stage A.  An interval
+// that is not the hot kind goes through report_add as usual.  For the hot kind
+// (lo = first bin, on its edge; report.cuh) the cells are
+//   events[s0][e0][hi] += 1, dstart[s0][0] += 1, pt/ut[s0][hi] += overlap with bin hi,
+// and a lane that is alone in its bin (the usual case) updates the table with a
+// plain load/add/store; lanes that share a bin use atomics among themselves.
+__device__ __forceinline__ void staged_report_warp(const ReportGeom &g, StagedEnv &env, WarpHot &H, int s0, int e0, int lane) {
+  const bool has = env.pend;
+  env.pend = false;
+  const bool hot = has && env.pend_state == s0 && env.pend_kind == e0 && env.pend_lhs == g.part_start;
+  if (has && !hot) {
+    ReportCursor none;
+    none.valid = false;
+    report_add(g, env.acc, none, env.pend_state, env.pend_kind, env.pend_lhs, env.pend_rhs);
+  }
+  __syncwarp();
+  const double rhs = env.pend_rhs;
+  int hi = -1 - lane;  // lanes without a hot interval match nobody
+  double v_pt = 0.0, v_ut = 0.0;
+  if (hot) {
+    hi = report_bin(g, rhs);
+    const double phi = report_part(g, hi);
+    v_pt = rhs - phi;
+    if (g.discount_rate != 0.0) v_ut = report_discounted_e(g, phi, rhs, g.edge_decay[hi], report_decay(g, rhs));
+    env.acc.addc(g.off_dstart + s0 * g.n_bin);
+    if (!(phi < rhs)) env.acc.addi(g.off_noedge + s0 * g.n_bin + hi, 1);
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, hi);
+  if (hot) {
+    if (peers == (1u << lane)) {  // the only lane ending in this bin: plain read-modify-write
+      H.pt[hi] += v_pt;
+      H.ut[hi] += v_ut;
+      H.ev[hi] += 1u;
+    } else {  // a few lanes share the bin: they (and nobody else) meet on its cells
+      atomicAdd(&H.pt[hi], v_pt);
+      atomicAdd(&H.ut[hi], v_ut);
+      if (lane == __ffs(peers) - 1) atomicAdd(&H.ev[hi], (unsigned)__popc(peers));
+    }
+  }
+  __syncwarp();
+}
 
 // a finished person's first row and row count (rows beyond the first stay staged until the warp appends them)
 __device__ __forceinline__ void staged_finish(const StagedParams &p, StagedEnv &env, uint32_t idx, int *err) {
@@ -255,11 +325,17 @@ __device__ __forceinline__ void staged_append_extra(const StagedParams &p, Stage
 
 __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const __grid_constant__ StagedParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // shared layout: [per-warp queues | dense doubles | dense ints]
+  // shared layout: [per-warp queues | per-warp row staging (row log) | per-warp hot tables (report) |
+  //                 dense doubles | dense ints]
   WarpQueues *queues = reinterpret_cast<WarpQueues *>(smem_raw);
+  unsigned char *sp = smem_raw + sizeof(WarpQueues) * SWARPS;
+  WarpRows *rows_stage = reinterpret_cast<WarpRows *>(sp);
+  if (p.outputs & 1u) sp += sizeof(WarpRows) * SWARPS;
+  WarpHot *hots = reinterpret_cast<WarpHot *>(sp);
+  if (p.warp_tables) sp += sizeof(WarpHot) * SWARPS;
   const int total = (p.outputs & 2u) ? p.geom.total : 0;
   const int n_f = (p.outputs & 2u) ? p.geom.off_dstart : 0;
-  double *s_f = reinterpret_cast<double *>(smem_raw + sizeof(WarpQueues) * SWARPS);
+  double *s_f = reinterpret_cast<double *>(sp);
   int *s_i = reinterpret_cast<int *>(s_f + n_f);
   __shared__ unsigned s_kind[8];
   __shared__ double s_sum[SWARPS];
@@ -271,6 +347,13 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
   if (tid == 0) s_error = 0;
   for (int k = tid; k < n_f; k += SBLOCK) s_f[k] = 0.0;
   for (int k = tid; k < total - n_f; k += SBLOCK) s_i[k] = 0;
+  WarpHot &H = hots[warp];
+  if (p.warp_tables)
+    for (int k = lane; k < REPORT_MAX_BINS; k += 32) {
+      H.pt[k] = 0.0;
+      H.ut[k] = 0.0;
+      H.ev[k] = 0u;
+    }
   __syncthreads();
 
   StagedEnv env;
@@ -286,7 +369,11 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
   env.nrows = 0;
   env.first_end = 0.0;
   env.first_tag = 0;
-  env.wq = &Q;
+  env.wq = &rows_stage[warp];
+  env.defer = false;
+  env.pend = false;
+  env.pend_state = env.pend_kind = 0;
+  env.pend_lhs = env.pend_rhs = 0.0;
   env.lane = lane;
   env.cursor.valid = false;
   int err = 0;
@@ -361,11 +448,14 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
       const uint32_t idx = (uint32_t)i64;
       bool park = false;
       person_r::ParkedOnset out;
+      env.defer = p.warp_tables != 0;
       if (i64 < p.n) {
         env.src.g = sub;
         park = !person_r::stage_a(env, K, p.first_person + i64, &out);
         if (!park) staged_finish(p, env, idx, &err);
       }
+      env.defer = false;
+      if (p.warp_tables) staged_report_warp(p.geom, env, H, person_r::Healthy, person_r::toDeath, lane);
       sub.jump(p.st.stride);
       const unsigned mk = __ballot_sync(0xffffffffu, park);
       if (park) {
@@ -387,6 +477,18 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
   }
 
   env.acc.flush();
+  if (p.warp_tables) {  // fold this warp's private slice into the block's tables
+    __syncwarp();
+    const ReportGeom &g = p.geom;
+    const int s0 = person_r::Healthy, e0 = person_r::toDeath;
+    for (int k = lane; k < g.n_bin; k += 32) {
+      if (H.ev[k]) {
+        atomicAdd(&s_f[g.off_pt + s0 * g.n_bin + k], H.pt[k]);
+        if (g.discount_rate != 0.0) atomicAdd(&s_f[g.off_ut + s0 * g.n_bin + k], H.ut[k]);
+        atomicAdd(&s_i[g.off_events + (s0 * g.n_event + e0) * g.n_bin + k - n_f], (int)H.ev[k]);
+      }
+    }
+  }
   if (err) atomicCAS(&s_error, 0, err);
   if (p.outputs & 4u) {
 #pragma unroll

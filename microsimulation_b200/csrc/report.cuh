@@ -48,6 +48,7 @@ struct ReportGeom {
   double part_start, part_delta;  // partition = start + i*delta for i < n_bin-1, then part_last
   double part_inv_delta;          // 1/delta: first guess of a bin index (corrected by comparison)
   double part_last;
+  int unit;  // 1: partition {0, 1, 2, ..., n_bin-2, part_last}: a bin index is just the integer part
   double discount_rate, alpha, inv_alpha;  // alpha = log(1 + discount_rate), inv_alpha = 1/alpha (host libm)
   // offsets (in doubles) into the dense vector; FP sums first, then counters
   int off_pt, off_ut, off_dstart, off_noedge, off_events, total;
@@ -65,6 +66,7 @@ inline ReportGeom make_report_geom(int n_state, int n_event, int n_bin, double s
   g.part_delta = delta;
   g.part_inv_delta = 1.0 / delta;
   g.part_last = last;
+  g.unit = (start == 0.0 && delta == 1.0 && last >= (double)(n_bin - 1)) ? 1 : 0;
   g.discount_rate = discount_rate;
   g.alpha = log(1.0 + discount_rate);
   g.inv_alpha = discount_rate != 0.0 ? 1.0 / g.alpha : 0.0;
@@ -89,6 +91,10 @@ MSIM_HD double report_part(const ReportGeom &g, int i) {
 // index of the largest partition point <= x (set<greater>::lower_bound, :937-938)
 MSIM_HD int report_bin(const ReportGeom &g, double x) {
   const int nb = g.n_bin;
+  if (g.unit) {  // every built model's partition {0, 1, ..., 100, 1e6}: exact without a search
+    if (x >= g.part_last) return nb - 1;
+    return (x > 0.0) ? ((x < (double)(nb - 2)) ? (int)x : nb - 2) : 0;
+  }
   double y = (x - g.part_start) * g.part_inv_delta;
   int i = (y > 0.0) ? ((y < (double)(nb - 2)) ? (int)y : nb - 2) : 0;
   while (i + 1 < nb && report_part(g, i + 1) <= x) i++;

@@ -90,6 +90,7 @@ def main():
     ap.add_argument("--json", default=None, help="write the per-person figures of the FIRST launch here")
     ap.add_argument("--title", default=None)
     ap.add_argument("--key", default=None, help="key under which --json stores this kernel's figures")
+    ap.add_argument("--pick", default=None, help="substring of the kernel name whose first launch --json stores (default: first launch)")
     args = ap.parse_args()
     hdr, units, launches = read_raw(args.rep)
     pats = [re.compile(p) for p in KEEP]
@@ -147,7 +148,7 @@ def main():
         if d:
             lines += ["", "Derived: " + json.dumps(d)]
         lines.append("")
-        if first is None:
+        if first is None and (args.pick is None or args.pick in name):
             first = dict(d, kernel=name)
     with open(args.out, "w") as f:
         f.write("\n".join(lines) + "\n")

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 TIME_RTOL = 4e-15  # <= ~18 ulp guard; measured max is 2 ulp (4.4e-16)
 
 
-@pytest.fixture(params=["staged", "generic"])
+@pytest.fixture(params=["staged", "generic", "staged-shared"])
 def pmsim(msim, request):
     """The product with person-r on either GPU schedule (csrc/person_staged.cuh / the generic cohort kernel)."""
     import microsimulation_b200.api as api
@@ -162,14 +162,19 @@ def test_person_schedules_agree_bit_for_bit(msim):
     table are IDENTICAL; only the order of FP additions into pt/ut differs."""
     import microsimulation_b200.api as api
     n, out = 10 ** 6 + 77, {}
-    for sched in ("generic", "staged"):
+    for sched in ("generic", "staged", "staged-shared"):
         api.set_person_schedule(sched)
         api.person_run_device(12345, 5, n, 1 | 4)
         rows, counts = api.person_fetch_rowlog(), api.person_fetch_counts()
         rep, _ = msim.person_report(12345, 5, n, 0.03)
         out[sched] = (rows, counts, rep)
     api.set_person_schedule("staged")
-    (ra, ca, pa), (rb, cb, pb) = out["generic"], out["staged"]
+    for other in ("staged", "staged-shared"):
+        _schedules_equal(out["generic"], out[other])
+
+
+def _schedules_equal(x, y):
+    (ra, ca, pa), (rb, cb, pb) = x, y
     for k in ra:
         assert np.array_equal(ra[k], rb[k]), k
     assert np.array_equal(ca[:8], cb[:8]) and abs(ca[8] - cb[8]) <= 1e-12 * ca[8]
