@@ -144,6 +144,18 @@ int msim_callIllnessDeath(int32_t n, double cure, double zsd, msim_report *out);
  * Uses the package seed last set with msim_r_set_user_random_seed. */
 int msim_callCalibrationSimulation(int32_t n, const double runpar[6], msim_calibration *out);
 
+/* callSim(n, param, indivp) of the reference's documented SummaryReport
+ * example, the continuous-time Sick-Sicker model (README.org:148-301; an
+ * inline Rcpp function there, not a registered symbol).  param = r_HS1, r_HD,
+ * r_S1H, r_S1S2, r_S1D, r_S2D, c_H, c_S1, c_S2, c_Trt, u_H, u_S1, u_S2, u_Trt,
+ * discountRate, partitionBy, Trt.  substreams = 0: draws from R's
+ * Mersenne-Twister state, person after person (the README's runs);
+ * substreams = 1: person i draws from substream first_person+i+1 of a stream
+ * made from the package seed.  out: pt, ut, events, prev, costs and indiv
+ * (n rows, or one row of totals when indivp = 0), SummaryReport::asList. */
+int msim_callSim_SickSicker(int32_t n, const double param[17], int indivp, int substreams, int64_t first_person,
+                            msim_report *out);
+
 /* ---- sharded / device-resident forms (multi-GPU, benchmarks) --------- */
 
 #define MSIM_OUT_ROWLOG 1u   /* life-history rows */

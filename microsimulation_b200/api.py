@@ -179,6 +179,31 @@ def callCalibrationPerson(seed=12345, n=500, runpar=(4, 0.5, 0.05, 10, 3, 0.5), 
     return {"StateOccupancy": mat, "TimeAtRisk": d["TimeAtRisk"], "raw": d}
 
 
+SICK_SICKER_KEYS = ["r_HS1", "r_HD", "r_S1H", "r_S1S2", "r_S1D", "r_S2D", "c_H", "c_S1", "c_S2", "c_Trt", "u_H", "u_S1",
+                    "u_S2", "u_Trt", "discountRate", "partitionBy", "Trt"]
+
+
+def sick_sicker_param(Trt=False):
+    """The README's parameter list (README.org:148-187); rates are the logm(Pmat) entries."""
+    return dict(r_HS1=0.28424764950662157, r_HD=0.0034485118628178875, r_S1H=0.9474921650220719,
+                r_S1S2=0.17396002318490003, r_S1D=0.017327099626200958, r_S2D=0.05012541823544285,
+                c_H=2000.0, c_S1=4000.0, c_S2=15000.0, c_Trt=12000.0, u_H=1.0, u_S1=0.75, u_S2=0.5, u_Trt=0.95,
+                discountRate=0.03, partitionBy=1.0, Trt=int(Trt))
+
+
+def callSim(n, param, indivp=True, substreams=False, first_person=0, seed=12345):
+    """README.org:289-301 callSim(n, param, indivp): the Sick-Sicker model with a SummaryReport.  As in the README's
+    runs, set.seed(seed) precedes the call (substreams=False); substreams=True uses one RngStream substream per
+    person of a stream made from the package seed (set_user_random_seed)."""
+    if substreams:
+        _ensure_stream()
+    else:
+        set_seed(seed)
+    par = (C.c_double * 17)(*[float(param[k]) for k in SICK_SICKER_KEYS])
+    return _report(load().msim_callSim_SickSicker, C.c_int32(n), par, C.c_int(int(indivp)), C.c_int(int(substreams)),
+                   C.c_int64(first_person))
+
+
 def calibration_sweep(seed, runpars, n, first_person=0):
     """n_sets parameter vectors x persons [first_person, first_person+n), one seed (common random numbers)."""
     runpars = np.ascontiguousarray(runpars, dtype=np.float64).reshape(-1, 6)

@@ -203,9 +203,12 @@ template <class SrcT>
 struct NullEnv {
   typedef SrcT Src;
   Src src;
+  int code = 0;  // last set_uc() code (models with carried-over report state, sick_sicker)
   __device__ __forceinline__ void begin_person() {}
   __device__ __forceinline__ void row(double, double, double, int, int) {}
   __device__ __forceinline__ void report(int, int, double, double) {}
+  __device__ __forceinline__ void summary(int, int, double, double) {}
+  __device__ __forceinline__ void set_uc(int k, double, double) { code = k; }
 };
 
 template <class Traits, bool STREAM>
@@ -446,7 +449,7 @@ __global__ void __launch_bounds__(256) rowlog_expand_kernel(ExpandParams p) {
 template <class Traits>
 __global__ void __launch_bounds__(BLOCK) seq_len_kernel(const uint32_t *words, int64_t mt_end, int64_t first_word,
                                                         int64_t n_pos, typename Traits::Consts consts,
-                                                        unsigned char *len) {
+                                                        unsigned char *len, unsigned char *aux) {
   typedef NullEnv<StreamSource> Env;
   for (int64_t p = (int64_t)blockIdx.x * BLOCK + threadIdx.x; p < n_pos; p += (int64_t)gridDim.x * BLOCK) {
     Env env;
@@ -458,14 +461,15 @@ __global__ void __launch_bounds__(BLOCK) seq_len_kernel(const uint32_t *words, i
     person.run();
     int64_t used = env.src.pos - (first_word + p);
     len[p] = (env.src.overrun || used > 250 || person.error_) ? 255 : (unsigned char)used;
+    if (aux) aux[p] = (unsigned char)env.code;
   }
 }
 
 // For chunk c and entry offset e: walk p += len[p] from c*CHUNK+e to the chunk
 // end; record where the chain enters the next chunk and how many persons
 // started inside this one.
-__global__ void __launch_bounds__(64) chain_chunk_kernel(const unsigned char *len, int64_t n_pos, int max_draws,
-                                                         unsigned char *exit_off, int *count) {
+__global__ void __launch_bounds__(256) chain_chunk_kernel(const unsigned char *len, int64_t n_pos, int max_draws,
+                                                          int stride, unsigned char *exit_off, int *count) {
   __shared__ unsigned char s_len[CHAIN_CHUNK];
   const int64_t c = blockIdx.x;
   const int64_t lo = c * CHAIN_CHUNK;
@@ -475,8 +479,8 @@ __global__ void __launch_bounds__(64) chain_chunk_kernel(const unsigned char *le
   if (e < max_draws) {
     int cnt = 0;
     int ex = chain_walk(s_len, e, &cnt);
-    exit_off[c * CHAIN_MAX_DRAWS + e] = (unsigned char)ex;
-    count[c * CHAIN_MAX_DRAWS + e] = cnt;
+    exit_off[c * stride + e] = (unsigned char)ex;
+    count[c * stride + e] = cnt;
   }
 }
 
@@ -486,7 +490,7 @@ __global__ void __launch_bounds__(64) chain_chunk_kernel(const unsigned char *le
 // entry = 255 marks "chain broken / not reached".
 constexpr int SCAN_BATCH = 512;
 __global__ void __launch_bounds__(256) chain_scan_kernel(const unsigned char *exit_off, const int *count,
-                                                         int64_t n_chunks, int64_t n, unsigned char *entry,
+                                                         int64_t n_chunks, int64_t n, int stride, unsigned char *entry,
                                                          int64_t *base) {
   __shared__ unsigned char s_exit[SCAN_BATCH * CHAIN_MAX_DRAWS];
   __shared__ int s_count[SCAN_BATCH * CHAIN_MAX_DRAWS];
@@ -494,6 +498,24 @@ __global__ void __launch_bounds__(256) chain_scan_kernel(const unsigned char *ex
   __shared__ int64_t s_base[SCAN_BATCH];
   __shared__ int s_e;
   __shared__ int64_t s_b;
+  if (stride > CHAIN_MAX_DRAWS) {
+    // wide tables (models with many draws per person): thread 0 follows the chain through global memory
+    if (threadIdx.x == 0) {
+      int e = 0;
+      int64_t b = 0;
+      for (int64_t c = 0; c < n_chunks; c++) {
+        entry[c] = (unsigned char)e;
+        base[c] = b;
+        if (e == 255 || b >= n) {
+          e = 255;
+        } else {
+          b += count[c * stride + e];
+          e = exit_off[c * stride + e];
+        }
+      }
+    }
+    return;
+  }
   if (threadIdx.x == 0) {
     s_e = 0;
     s_b = 0;

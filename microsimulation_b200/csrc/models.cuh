@@ -321,4 +321,110 @@ struct SimplePerson : cProcess<SimplePerson<Env>, typename Env::Src, HEAP_CAP> {
 
 }  // namespace simple_example
 
+// ------------------------------------------------- Sick-Sicker (README.org:148-301)
+// The reference's documented SummaryReport example: a continuous-time
+// Healthy / Sick / Sicker / Dead model with utilities and costs that change at
+// each transition, 31 years of follow-up, exponential transition times.
+namespace sick_sicker {
+
+enum state_t { Healthy, Sick, Sicker, Dead };
+enum event_t { toS1, toS2, toH, toD, toEOF };
+// every transition cancels the pending events lazily (they stay in the heap until their time comes) and
+// schedules up to three new ones, so the heap holds a few entries per transition made so far
+constexpr int N_STATE = 4, N_EVENT = 5, HEAP_CAP = 160;
+
+struct Par {
+  double r_HS1, r_HD, r_S1H, r_S1S2, r_S1D, r_S2D;
+  double c_H, c_S1, c_S2, c_Trt, u_H, u_S1, u_S2, u_Trt;
+  int Trt;
+};
+
+template <class Env>
+struct SickSicker : cProcess<SickSicker<Env>, typename Env::Src, HEAP_CAP> {
+  typedef cProcess<SickSicker<Env>, typename Env::Src, HEAP_CAP> Base;
+  using Base::Cancel;
+  using Base::now;
+  using Base::previousEventTime;
+  using Base::R;
+  using Base::scheduleAt;
+  using Base::stop_simulation;
+
+  int state;
+  Env &env;
+  const Par &P;
+
+  MSIM_DEV SickSicker(Env &e, const Par &p, int64_t /*id*/) : Base(&e.src), state(Healthy), env(e), P(p) { e.begin_person(); }
+
+  MSIM_DEV double rexpRate(double rate) { return R.rexp(1.0 / rate); }  // README.org:200
+
+  MSIM_DEV void init() {  // README.org:226-232
+    state = Healthy;
+    scheduleAt(rexpRate(P.r_HS1), toS1);
+    scheduleAt(rexpRate(P.r_HD), toD);
+    scheduleAt(31.0, toEOF);  // end of follow-up
+  }
+
+  // RemoveKind(toH); RemoveKind(toS1); RemoveKind(toS2); RemoveKind(toD)  (README.org:236-241) in one scan
+  MSIM_DEV void cancelEvents() {
+    Cancel([](int k) { return k == toH || k == toS1 || k == toS2 || k == toD; });
+  }
+
+  MSIM_DEV void handleMessage(int kind) {  // README.org:245-285
+    env.summary(state, kind, previousEventTime, now());
+    switch (kind) {
+      case toH:
+        state = Healthy;
+        env.set_uc(1, P.u_H, P.c_H);
+        cancelEvents();
+        scheduleAt(now() + rexpRate(P.r_HS1), toS1);
+        scheduleAt(now() + rexpRate(P.r_HD), toD);
+        break;
+      case toS1:
+        state = Sick;
+        env.set_uc(2, P.Trt ? P.u_Trt : P.u_S1, P.c_S1 + (P.Trt ? P.c_Trt : 0.0));
+        cancelEvents();
+        scheduleAt(now() + rexpRate(P.r_S1H), toH);
+        scheduleAt(now() + rexpRate(P.r_S1S2), toS2);
+        scheduleAt(now() + rexpRate(P.r_S1D), toD);
+        break;
+      case toS2:
+        state = Sicker;
+        env.set_uc(3, P.u_S2, P.c_S2 + (P.Trt ? P.c_Trt : 0.0));
+        cancelEvents();
+        scheduleAt(now() + rexpRate(P.r_S2D), toD);
+        break;
+      case toD:
+      case toEOF:
+        stop_simulation();
+        break;
+      default:
+        break;
+    }
+  }
+};
+
+// The report's utility and cost are NOT reset between persons in the
+// reference (README.org:292-299: one Report, one process object, n runs), so a
+// person's first interval is valued with whatever the previous person's last
+// transition set.  code 0 = nothing set yet (the constructor's utility 1, cost
+// 0), 1/2/3 = the values toH / toS1 / toS2 set.
+MSIM_HD void uc_of_code(const Par &P, int code, double *u, double *c) {
+  if (code == 1) {
+    *u = P.u_H;
+    *c = P.c_H;
+  } else if (code == 2) {
+    *u = P.Trt ? P.u_Trt : P.u_S1;
+    *c = P.c_S1 + (P.Trt ? P.c_Trt : 0.0);
+  } else if (code == 3) {
+    *u = P.u_S2;
+    *c = P.c_S2 + (P.Trt ? P.c_Trt : 0.0);
+  } else {
+    *u = 1.0;
+    *c = 0.0;
+  }
+}
+
+}  // namespace sick_sicker
+
+
 }  // namespace msim

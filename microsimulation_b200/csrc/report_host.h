@@ -10,6 +10,7 @@
 #include "../../include/msim.h"
 #include "models.cuh"
 #include "report.cuh"
+#include "summary.cuh"
 
 namespace msim {
 
@@ -116,6 +117,66 @@ inline void dense_to_report_impl(const double *d, const ReportGeom &G, msim_repo
   table_from_rows(prev, 3, PREV_COLS, &out->prev);
   table_from_rows(none, 3, COST_COLS, &out->costs);
   table_from_rows(none, 2, INDIV_COLS, &out->indiv);
+}
+
+// SummaryReport::asList (microsimulation.h:1125-1145): pt, ut, events, prev, costs (sparse, key-sorted) and the
+// per-individual discounted utilities and costs
+inline void dense_to_summary_impl(const double *d, const SummaryGeom &G, const double *indiv, int64_t n_indiv,
+                                  msim_report *out) {
+  std::vector<double> pt, ut, ev, prev, cost, ind;
+  const int nb = G.n_bin;
+  bool any_event = false;
+  for (int i = 0; i < G.n_state * G.n_event * nb; i++)
+    if (d[G.off_events + i] != 0) {
+      any_event = true;
+      break;
+    }
+  if (any_event) {
+    for (int s = 0; s < G.n_state; s++) {
+      double starts = 0, ends = 0, wu = 0, wc = 0;
+      for (int b = 0; b < nb; b++) {
+        double ended = 0;
+        for (int e = 0; e < G.n_event; e++) ended += d[G.off_events + (s * G.n_event + e) * nb + b];
+        starts += d[G.off_dstart + s * nb + b];
+        ends += ended;
+        wu += d[G.off_wu0 + s * nb + b] - d[G.off_wu1 + s * nb + b];
+        wc += d[G.off_wc0 + s * nb + b] - d[G.off_wc1 + s * nb + b];
+        const double full = starts - ends;
+        const double pv = full + ended - d[G.off_noedge + s * nb + b];
+        const double part = d[G.off_pt + s * nb + b];
+        const double age = G.part[b];
+        const bool visited = full > 0 || ended > 0 || part != 0;
+        const double pcn = d[G.off_pcn + s * nb + b];
+        double utv = d[G.off_ut + s * nb + b], cv = d[G.off_cost + s * nb + b];
+        if (visited) {
+          double width = 0;
+          if (full > 0 && b + 1 < nb) {
+            const double nxt = G.part[b + 1];
+            width = nxt - age;
+            // weights of the intervals covering the bin completely, times the bin's discounted width
+            utv += wu * (G.u_rate == 0.0 ? width : G.u_inv_alpha * (G.u_decay[b] - G.u_decay[b + 1]));
+            cv += wc * (G.c_rate == 0.0 ? width : G.c_inv_alpha * (G.c_decay[b] - G.c_decay[b + 1]));
+          }
+          pt.insert(pt.end(), {(double)s, age, part + full * width});
+          ut.insert(ut.end(), {(double)s, age, utv});
+        }
+        if (visited || pcn > 0) cost.insert(cost.end(), {(double)s, age, cv});
+        if (pv > 0) prev.insert(prev.end(), {(double)s, age, pv});
+      }
+      for (int e = 0; e < G.n_event; e++)
+        for (int b = 0; b < nb; b++) {
+          double c = d[G.off_events + (s * G.n_event + e) * nb + b];
+          if (c > 0) ev.insert(ev.end(), {(double)s, (double)e, G.part[b], c});
+        }
+    }
+    for (int64_t i = 0; i < n_indiv; i++) ind.insert(ind.end(), {indiv[2 * i], indiv[2 * i + 1]});
+  }
+  table_from_rows(pt, 3, PT_COLS, &out->pt);
+  table_from_rows(ut, 3, UT_COLS, &out->ut);
+  table_from_rows(ev, 4, EV_COLS, &out->events);
+  table_from_rows(prev, 3, PREV_COLS, &out->prev);
+  table_from_rows(cost, 3, COST_COLS, &out->costs);
+  table_from_rows(ind, 2, INDIV_COLS, &out->indiv);
 }
 
 inline ReportGeom ages_geom(int n_state, int n_event, double discount_rate) {

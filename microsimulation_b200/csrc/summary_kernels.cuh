@@ -1,0 +1,195 @@
+// Kernels for models that report through SummaryReport (summary.cuh); the one
+// such model the reference documents is Sick-Sicker (README.org:148-301).
+//
+// Two regimes, as for the other models: R's single Mersenne-Twister stream
+// (the README's runs: set.seed(12345), draws consumed person after person — the
+// stream-offset resolution of kernels.cuh applies, with up to 250 draws per
+// person), or one RngStream substream per person.
+//
+// The report's utility and cost carry over from one person to the next in the
+// reference (models.cuh, sick_sicker::uc_of_code).  A first pass therefore
+// finds each person's LAST set_uc() code (sick_code_kernel, or the draw-count
+// pass in the stream regime), carry_scan_kernel turns that into the code each
+// person starts with, and only then does sick_kernel run the persons.
+#pragma once
+#include "kernels.cuh"
+#include "summary.cuh"
+
+namespace msim {
+
+struct SickTraits {
+  typedef sick_sicker::Par Consts;
+  template <class Env> using Model = sick_sicker::SickSicker<Env>;
+  static constexpr int MAX_ROWS = 1;
+};
+
+struct SickParams {
+  StreamStart st;             // substream regime
+  const uint32_t *mt_words;   // stream regime
+  int64_t mt_end;
+  const int64_t *starts;
+  int64_t first_person, n;
+  sick_sicker::Par par;
+  const SummaryGeom *geom;       // in global memory
+  const unsigned char *code_in;  // [n] the set_uc() code in force when person i starts
+  unsigned char *code_out;       // [n] (first pass) person i's last set_uc() code, 0 = none
+  double *dense;                 // geom->total accumulators
+  double *indiv;                 // [2n] (utilities, costs) per person if indivp, else [2]
+  int indivp;
+  int *error;
+};
+
+// first pass, substream regime: each person's last set_uc() code
+__global__ void __launch_bounds__(BLOCK) sick_code_kernel(SickParams p) {
+  typedef NullEnv<MrgSource> Env;
+  Mrg32k3a sub = thread_start_state(p.st, blockIdx.x * BLOCK + threadIdx.x);
+  const int64_t stride = (int64_t)gridDim.x * BLOCK;
+  for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < p.n; i += stride) {
+    Env env;
+    env.src.g = sub;
+    sick_sicker::SickSicker<Env> person(env, p.par, 0);
+    person.run();
+    p.code_out[i] = (unsigned char)env.code;
+    if (person.error_) atomicCAS(p.error, 0, person.error_);
+    sub.jump(p.st.stride);
+  }
+}
+
+// stream regime: person i's last code is the one found for its start position
+__global__ void gather_code_kernel(const unsigned char *aux, const int64_t *starts, int64_t first_word, int64_t n,
+                                   unsigned char *code_out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    code_out[i] = aux[starts[i] - first_word];
+}
+
+// code_in[i] = last non-zero code_out[j], j < i (code0 if none): an exclusive scan under "last writer wins".
+// One block; the n bytes are read once.
+__global__ void __launch_bounds__(1024) carry_scan_kernel(const unsigned char *code_out, int64_t n, int code0,
+                                                          unsigned char *code_in) {
+  __shared__ int s_w[32];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = code0;
+  __syncthreads();
+  for (int64_t i0 = 0; i0 < n; i0 += 1024) {
+    const int64_t i = i0 + tid;
+    const int v = (i < n) ? code_out[i] : 0;
+    int incl = v;  // inclusive scan: last non-zero among lanes <= this one
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o && incl == 0) incl = t;
+    }
+    int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 0;
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    int before = s_carry;  // last non-zero before this warp
+    for (int w = 0; w < warp; w++)
+      if (s_w[w]) before = s_w[w];
+    if (i < n) code_in[i] = (unsigned char)(excl ? excl : before);
+    __syncthreads();
+    if (tid == 1023) s_carry = incl ? incl : before;
+    __syncthreads();
+  }
+}
+
+template <class SrcT>
+struct SummaryEnv {
+  typedef SrcT Src;
+  Src src;
+  const SummaryGeom *geom;  // shared-memory copy
+  SharedAcc acc;
+  double u, c;      // the report's current utility and cost
+  double tot_u, tot_c;  // this person's discounted totals
+  __device__ __forceinline__ void begin_person() {}
+  __device__ __forceinline__ void row(double, double, double, int, int) {}
+  __device__ __forceinline__ void report(int, int, double, double) {}
+  __device__ __forceinline__ void set_uc(int, double uu, double cc) {
+    u = uu;
+    c = cc;
+  }
+  __device__ __forceinline__ void summary(int state, int kind, double lhs, double rhs) {
+    double du, dc;
+    summary_add(*geom, acc, state, kind, lhs, rhs, u, c, &du, &dc);
+    tot_u += du;
+    tot_c += dc;
+  }
+};
+
+template <bool STREAM>
+__global__ void __launch_bounds__(BLOCK) sick_kernel(SickParams p) {
+  typedef typename std::conditional<STREAM, StreamSource, MrgSource>::type Src;
+  typedef SummaryEnv<Src> Env;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SummaryGeom *sg = reinterpret_cast<SummaryGeom *>(smem_raw);
+  {
+    const int *src = reinterpret_cast<const int *>(p.geom);
+    int *dst = reinterpret_cast<int *>(sg);
+    for (int k = threadIdx.x; k < (int)(sizeof(SummaryGeom) / 4); k += BLOCK) dst[k] = src[k];
+  }
+  __syncthreads();
+  const int total = sg->total, n_f = sg->n_float;
+  double *s_f = reinterpret_cast<double *>(smem_raw + ((sizeof(SummaryGeom) + 15) & ~(size_t)15));
+  int *s_i = reinterpret_cast<int *>(s_f + n_f);
+  Env env;
+  env.geom = sg;
+  env.acc.f = s_f;
+  env.acc.i = s_i;
+  env.acc.n_f = n_f;
+  shared_acc_clear(env.acc, total);
+  __syncthreads();
+
+  Mrg32k3a sub;
+  if constexpr (!STREAM) sub = thread_start_state(p.st, blockIdx.x * BLOCK + threadIdx.x);
+  const int64_t stride = (int64_t)gridDim.x * BLOCK;
+  int err = 0;
+  double all_u = 0.0, all_c = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < p.n; i += stride) {
+    if constexpr (STREAM) {
+      env.src.w = p.mt_words;
+      env.src.pos = p.starts[i];
+      env.src.end = p.mt_end;
+      env.src.overrun = 0;
+    } else {
+      env.src.g = sub;
+    }
+    sick_sicker::uc_of_code(p.par, p.code_in[i], &env.u, &env.c);
+    env.tot_u = env.tot_c = 0.0;
+    sick_sicker::SickSicker<Env> person(env, p.par, p.first_person + i);
+    person.run();
+    if (person.error_) err = person.error_;
+    if constexpr (STREAM) {
+      if (env.src.overrun) err = -6;
+    } else {
+      sub.jump(p.st.stride);
+    }
+    if (p.indivp) {
+      p.indiv[2 * i] = env.tot_u;
+      p.indiv[2 * i + 1] = env.tot_c;
+    } else {
+      all_u += env.tot_u;
+      all_c += env.tot_c;
+    }
+  }
+  if (!p.indivp) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      all_u += __shfl_xor_sync(0xffffffffu, all_u, o);
+      all_c += __shfl_xor_sync(0xffffffffu, all_c, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&p.indiv[0], all_u);
+      atomicAdd(&p.indiv[1], all_c);
+    }
+  }
+  if (err) atomicCAS(p.error, 0, err);
+  __syncthreads();
+  shared_acc_flush(env.acc, total, p.dense);
+}
+
+inline size_t sick_kernel_smem(const SummaryGeom &g) {
+  return ((sizeof(SummaryGeom) + 15) & ~(size_t)15) + (size_t)g.n_float * 8 + (size_t)(g.total - g.n_float) * 4;
+}
+
+}  // namespace msim

@@ -22,6 +22,7 @@
 #include "../../microsimulation_b200/csrc/report.cuh"
 #include "../../microsimulation_b200/csrc/report_host.h"
 #include "../../microsimulation_b200/csrc/seqstream.cuh"
+#include "../../microsimulation_b200/csrc/summary.cuh"
 
 using namespace msim;
 
@@ -74,7 +75,10 @@ template <class SrcT>
 struct HostNullEnv {
   typedef SrcT Src;
   Src src;
+  int code = 0;
   void begin_person() {}
+  void summary(int, int, double, double) {}
+  void set_uc(int k, double, double) { code = k; }
   void row(double, double, double, int, int) {}
   void report(int, int, double, double) {}
 };
@@ -233,6 +237,29 @@ int sequential(int64_t n, const Consts &consts, int max_draws, unsigned outputs,
 }
 
 }  // namespace
+
+template <class SrcT>
+struct HostSummaryEnv {
+  typedef SrcT Src;
+  Src src;
+  const SummaryGeom *geom;
+  PlainAcc acc;
+  double u, c, tot_u, tot_c;
+  void begin_person() {}
+  void row(double, double, double, int, int) {}
+  void report(int, int, double, double) {}
+  void set_uc(int, double uu, double cc) {
+    u = uu;
+    c = cc;
+  }
+  void summary(int state, int kind, double lhs, double rhs) {
+    double du, dc;
+    summary_add(*geom, acc, state, kind, lhs, rhs, u, c, &du, &dc);
+    tot_u += du;
+    tot_c += dc;
+  }
+};
+
 
 extern "C" {
 
@@ -486,6 +513,116 @@ int emu_calibration(const double seed[6], int64_t first_person, int64_t n, const
   }
   out->n_time_at_risk = env.tar_n;
   for (int k = 0; k < env.tar_n; k++) out->time_at_risk[k] = env.tar[k];
+  return 0;
+}
+
+// callSim (Sick-Sicker, SummaryReport) with the device's decomposition: a first pass for every person's last
+// set_uc() code, the carry scan, then the persons.  substreams = 0 reads R's Mersenne-Twister stream from `state`
+// (advanced on return); substreams = 1 uses substream first_person+i+1 of the stream whose seed is `seed`.
+int emu_sick_sicker(int64_t n, const double par17[17], int indivp, int substreams, int64_t first_person, const double seed[6],
+                    uint32_t state[625], msim_report *out) {
+  sick_sicker::Par P;
+  P.r_HS1 = par17[0]; P.r_HD = par17[1]; P.r_S1H = par17[2]; P.r_S1S2 = par17[3]; P.r_S1D = par17[4]; P.r_S2D = par17[5];
+  P.c_H = par17[6]; P.c_S1 = par17[7]; P.c_S2 = par17[8]; P.c_Trt = par17[9];
+  P.u_H = par17[10]; P.u_S1 = par17[11]; P.u_S2 = par17[12]; P.u_Trt = par17[13];
+  P.Trt = par17[16] != 0.0;
+  SummaryGeom G;
+  if (!make_summary_geom(&G, sick_sicker::N_STATE, sick_sicker::N_EVENT, 0.0, 31.0, par17[15], 1.0e100, par17[14], par17[14]))
+    return MSIM_ERR_ARG;
+  std::vector<double> dense(G.total, 0.0), indiv(2 * (size_t)std::max<int64_t>(indivp ? n : 1, 1), 0.0);
+  std::vector<unsigned char> code_out((size_t)std::max<int64_t>(n, 1)), code_in((size_t)std::max<int64_t>(n, 1));
+  std::vector<Mrg32k3a> subs;
+  std::vector<int64_t> starts;
+  std::vector<uint32_t> w;
+  int64_t mti0 = 0, mt_end = 0, end_word = 0;
+  if (substreams) {
+    StreamStart st;
+    make_start(seed, first_person + 1, 1, &st);
+    subs.resize((size_t)n);
+    Mrg32k3a b;
+    memcpy(b.s, st.base, sizeof b.s);
+    for (int64_t i = 0; i < n; i++) {
+      subs[i] = b;
+      b.jump(mrg_substream_jump());
+    }
+    for (int64_t i = 0; i < n; i++) {
+      HostNullEnv<MrgSource> env;
+      env.src.g = subs[i];
+      sick_sicker::SickSicker<HostNullEnv<MrgSource> > person(env, P, 0);
+      person.run();
+      if (person.error_) return person.error_;
+      code_out[i] = (unsigned char)env.code;
+    }
+  } else {
+    mti0 = state[0];
+    const int64_t n_batches = (mti0 + 250 * n + 251 + 623) / 624;
+    mt_end = n_batches * 624;
+    w = mt_words_emulated(state, n_batches);
+    starts.resize((size_t)n);
+    int64_t pos = mti0;
+    for (int64_t i = 0; i < n; i++) {  // (the chain resolution itself is exercised by the other stream models)
+      HostNullEnv<StreamSource> env;
+      env.src.w = w.data();
+      env.src.pos = pos;
+      env.src.end = mt_end;
+      env.src.overrun = 0;
+      sick_sicker::SickSicker<HostNullEnv<StreamSource> > person(env, P, 0);
+      person.run();
+      if (env.src.overrun) return -6;
+      if (person.error_) return person.error_;
+      starts[i] = pos;
+      code_out[i] = (unsigned char)env.code;
+      pos = env.src.pos;
+    }
+    end_word = pos;
+  }
+  int carry = 0;
+  for (int64_t i = 0; i < n; i++) {
+    code_in[i] = (unsigned char)carry;
+    if (code_out[i]) carry = code_out[i];
+  }
+  for (int64_t i = 0; i < n; i++) {
+    double tu, tc;
+    if (substreams) {
+      HostSummaryEnv<MrgSource> env;
+      env.geom = &G;
+      env.acc.d = dense.data();
+      env.src.g = subs[i];
+      sick_sicker::uc_of_code(P, code_in[i], &env.u, &env.c);
+      env.tot_u = env.tot_c = 0;
+      sick_sicker::SickSicker<HostSummaryEnv<MrgSource> > person(env, P, first_person + i);
+      person.run();
+      tu = env.tot_u;
+      tc = env.tot_c;
+    } else {
+      HostSummaryEnv<StreamSource> env;
+      env.geom = &G;
+      env.acc.d = dense.data();
+      env.src.w = w.data();
+      env.src.pos = starts[i];
+      env.src.end = mt_end;
+      env.src.overrun = 0;
+      sick_sicker::uc_of_code(P, code_in[i], &env.u, &env.c);
+      env.tot_u = env.tot_c = 0;
+      sick_sicker::SickSicker<HostSummaryEnv<StreamSource> > person(env, P, first_person + i);
+      person.run();
+      tu = env.tot_u;
+      tc = env.tot_c;
+    }
+    if (indivp) {
+      indiv[2 * i] = tu;
+      indiv[2 * i + 1] = tc;
+    } else {
+      indiv[0] += tu;
+      indiv[1] += tc;
+    }
+  }
+  dense_to_summary_impl(dense.data(), G, indiv.data(), indivp ? n : 1, out);
+  if (!substreams && n > 0) {
+    int64_t batch = (end_word - 1) / 624;
+    memcpy(state + 1, w.data() + batch * 624, sizeof(uint32_t) * 624);
+    state[0] = (uint32_t)(end_word - batch * 624);
+  }
   return 0;
 }
 

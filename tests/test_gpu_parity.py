@@ -325,6 +325,66 @@ def test_calibration_sweep_vs_oracle(msim, oracle):
                 assert np.array_equal(a[k], b[k]), k
 
 
+# ------------------------------------------------------------------ SummaryReport: Sick-Sicker (README.org:148-301)
+
+def _summary_equal(g, r, rtol=1e-9):
+    for tb, val in (("pt", "pt"), ("ut", "utility"), ("costs", "cost")):
+        assert np.array_equal(g[tb]["Key"], r[tb]["Key"]) and np.array_equal(g[tb]["age"], r[tb]["age"]), tb
+        np.testing.assert_allclose(g[tb][val], r[tb][val], rtol=rtol, atol=1e-9, err_msg=tb)
+    for tb in ("events", "prev"):
+        for k in r[tb]:
+            assert np.array_equal(g[tb][k], r[tb][k]), (tb, k)
+    assert g["indiv"]["utilities"].shape == r["indiv"]["utilities"].shape
+    np.testing.assert_allclose(g["indiv"]["utilities"], r["indiv"]["utilities"], rtol=1e-12)
+    np.testing.assert_allclose(g["indiv"]["costs"], r["indiv"]["costs"], rtol=1e-12)
+
+
+def test_sick_sicker_readme_table(msim, kats):
+    """README.org:333-337: mean discounted costs and QALYs, n = 1000, set.seed(12345), both arms."""
+    import microsimulation_b200.api as api
+    k = kats["sick_sicker_n1000"]
+    for arm, trt in (("no_treatment", False), ("treatment", True)):
+        r = api.callSim(1000, api.sick_sicker_param(trt))
+        assert round(r["indiv"]["costs"].mean(), 1) == k[arm][0]
+        assert round(r["indiv"]["utilities"].mean(), 3) == k[arm][1]
+
+
+@pytest.mark.parametrize("n,trt,indivp,by", [(0, 0, 1, 1.0), (5, 0, 1, 1.0), (1000, 1, 1, 1.0), (20000, 0, 1, 1.0),
+                                             (20000, 1, 0, 1.0), (5000, 0, 1, 0.5), (5000, 1, 1, 2.5)])
+def test_sick_sicker_stream_regime_vs_oracle(msim, oracle, n, trt, indivp, by):
+    import microsimulation_b200.api as api
+    par = api.sick_sicker_param(bool(trt))
+    par["partitionBy"] = by
+    g = api.callSim(n, par, indivp=bool(indivp))
+    r = oracle.sick_sicker(n, par, indivp=bool(indivp))
+    _summary_equal(g, r)
+    if n:  # R's generator is left where the reference leaves it: the next model continues the stream
+        assert np.array_equal(api.mt_uniforms(4), _oracle_after_sick(oracle, n, par, indivp))
+
+
+def _oracle_after_sick(oracle, n, par, indivp):
+    import ctypes as C
+    from oracle.pyoracle import SICK_SICKER_KEYS, Report
+    oracle.set_seed(12345)
+    p17 = (C.c_double * 17)(*[float(par[k]) for k in SICK_SICKER_KEYS])
+    r = Report()
+    assert oracle.lib.oracle_sick_sicker(C.c_int64(n), p17, C.c_int(int(indivp)), C.c_int(0), C.c_int64(0), C.byref(r), None,
+                                         C.c_int64(0), C.byref(C.c_int64(0))) == 0
+    oracle.lib.oracle_report_free(C.byref(r))
+    return oracle.mt_uniforms(4)
+
+
+@pytest.mark.parametrize("n,first", [(30000, 0), (10000, 123456)])
+def test_sick_sicker_substream_regime_vs_oracle(msim, oracle, n, first):
+    import microsimulation_b200.api as api
+    par = api.sick_sicker_param(True)
+    api.set_user_random_seed(12345)
+    oracle.set_user_random_seed(12345)
+    g = api.callSim(n, par, substreams=True, first_person=first)
+    r = oracle.sick_sicker(n, par, substreams=True, first_person=first)
+    _summary_equal(g, r)
+
+
 def test_package_seed_advances_like_the_reference(msim, oracle):
     """Two calibration calls after ONE set.user.Random.seed: the second `new Rng()` is the next stream."""
     import ctypes as C

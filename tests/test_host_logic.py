@@ -188,3 +188,35 @@ def test_emulated_calibration(oracle, emu):
     assert set(got) == set(ref)
     for k in ref:
         assert np.array_equal(got[k], ref[k]), k
+
+
+@pytest.mark.parametrize("n,trt,indivp,substreams,by", [(5, 0, 1, 0, 1.0), (1000, 0, 1, 0, 1.0), (1000, 1, 1, 0, 1.0),
+                                                        (700, 1, 0, 0, 1.0), (800, 0, 1, 1, 1.0), (0, 0, 1, 0, 1.0),
+                                                        (600, 0, 1, 0, 0.5), (600, 1, 1, 0, 2.5)])
+def test_emulated_sick_sicker_summary_report(oracle, emu, n, trt, indivp, substreams, by):
+    """SummaryReport in O(1) cells per interval (weighted difference arrays, carried-over utility/cost) equals the
+    reference's bin-by-bin walk: Sick-Sicker (README.org:148-301), both RNG regimes, several partitions."""
+    from oracle.pyoracle import SICK_SICKER_KEYS, sick_sicker_param
+    par = sick_sicker_param(bool(trt))
+    par["partitionBy"] = by
+    p17 = (C.c_double * 17)(*[float(par[k]) for k in SICK_SICKER_KEYS])
+    seed = (C.c_double * 6)(*[12345.0] * 6)
+    st = (C.c_uint32 * 625)()
+    emu.emu_mt_set_seed(C.c_uint32(12345), st)
+    r = Report()
+    assert emu.emu_sick_sicker(C.c_int64(n), p17, C.c_int(indivp), C.c_int(substreams), C.c_int64(3 if substreams else 0),
+                               seed, st, C.byref(r)) == 0
+    e = r.to_dict()
+    if substreams:
+        oracle.set_user_random_seed(12345)
+    ref = oracle.sick_sicker(n, par, indivp=bool(indivp), substreams=bool(substreams), first_person=3 if substreams else 0)
+    for tb, val in (("pt", "pt"), ("ut", "utility"), ("costs", "cost")):
+        assert np.array_equal(e[tb]["Key"], ref[tb]["Key"]) and np.array_equal(e[tb]["age"], ref[tb]["age"]), tb
+        np.testing.assert_allclose(e[tb][val], ref[tb][val], rtol=1e-11, atol=1e-9, err_msg=tb)
+    for tb in ("events", "prev"):
+        for k in ref[tb]:
+            assert np.array_equal(e[tb][k], ref[tb][k]), (tb, k)
+    assert e["indiv"]["utilities"].shape == ref["indiv"]["utilities"].shape
+    np.testing.assert_allclose(e["indiv"]["utilities"], ref["indiv"]["utilities"], rtol=1e-12)
+    np.testing.assert_allclose(e["indiv"]["costs"], ref["indiv"]["costs"], rtol=1e-12)
+    emu.emu_report_free(C.byref(r))
