@@ -156,6 +156,39 @@ int msim_callCalibrationSimulation(int32_t n, const double runpar[6], msim_calib
 int msim_callSim_SickSicker(int32_t n, const double param[17], int indivp, int substreams, int64_t first_person,
                             msim_report *out);
 
+/* ---- generalised survival models (src/gsm.cpp, src/splines.cpp) ------- */
+
+/* The fields of the Rcpp::List that gsm::gsm(Rcpp::List) reads (gsm.cpp:60-92). */
+typedef struct msim_gsm_term {
+  int32_t n_gamma;             /* length of gamma = rows of the natural-spline basis */
+  int32_t n_knots;             /* interior knots */
+  int32_t intercept, cure;
+  int32_t q_rows, q_cols;      /* q_const as given (either orientation, splines.cpp:197-198), row-major */
+  const double *gamma, *knots, *q_const;
+  double Boundary_knots[2];
+  const double *x;             /* [n_index] covariate value per covariate pattern */
+} msim_gsm_term;
+
+typedef struct msim_gsm {
+  int32_t link;                /* 0 = "PH" (the only link the reference implements) */
+  int32_t log_time;
+  int32_t n_index;             /* covariate patterns: length of etap, etap0 and every term's x */
+  int32_t n_terms;
+  double tmin, tmax, inflate, t0;
+  const double *etap, *etap0;
+  const msim_gsm_term *terms;
+} msim_gsm;
+
+/* out[i] = gsm::randU(u[i], tentry[i], index[i], scale)   (gsm.cpp:38-47): the
+ * time t with S(t | t > tentry) = u, by Brent's method on the spline scale, one
+ * inversion per GPU thread.  tentry and index may be NULL (all 0). */
+int msim_gsm_randU(const msim_gsm *model, int64_t n, const double *u, const double *tentry, const int32_t *index,
+                   double scale, double *out);
+/* out[i] = gsm::randU0(u[i], index[i], scale)             (gsm.cpp:48-58) */
+int msim_gsm_randU0(const msim_gsm *model, int64_t n, const double *u, const int32_t *index, double scale, double *out);
+/* out[i] = gsm::eta(y[i]) for covariate pattern index[i]   (gsm.cpp:15-21); parity hook */
+int msim_gsm_eta(const msim_gsm *model, int64_t n, const double *y, const int32_t *index, double *out);
+
 /* ---- sharded / device-resident forms (multi-GPU, benchmarks) --------- */
 
 #define MSIM_OUT_ROWLOG 1u   /* life-history rows */

@@ -26,6 +26,7 @@
 
 #include <type_traits>
 
+#include "gsm.cuh"
 #include "models.cuh"
 #include "report.cuh"
 #include "seqstream.cuh"
@@ -654,6 +655,20 @@ __global__ void __launch_bounds__(BLOCK) calib_kernel(CalibParams p) {
     unsigned long long *cell = reinterpret_cast<unsigned long long *>(&out[44]);
     atomicMax(cell, (unsigned long long)__double_as_longlong((double)s_tar_n));
     if (s_error) atomicCAS(p.error, 0, s_error);
+  }
+}
+
+// ---- generalised survival model: one inversion per thread ----------------
+// mode 0: randU(u, tentry, index), 1: randU0(u, index), 2: eta(y = u, index)
+__global__ void __launch_bounds__(128) gsm_kernel(const GsmModel *M, int mode, int64_t n, const double *u, const double *tentry,
+                                                  const int *index, double scale, double *out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int idx = index ? index[i] : 0;
+    double r;
+    if (mode == 0) r = gsm_randU(*M, u[i], tentry ? tentry[i] : 0.0, idx, scale);
+    else if (mode == 1) r = gsm_randU0(*M, u[i], idx, scale);
+    else r = gsm_eta(*M, idx, u[i], false);
+    out[i] = r;
   }
 }
 

@@ -11,6 +11,7 @@
 
 #include "cprocess_lite.h"
 #include "models.h"
+#include "gsm_lite.h"
 
 using namespace orc;
 
@@ -259,6 +260,69 @@ int oracle_priority_demo(double order[4]) {
   run_priority_demo(&o);
   for (size_t i = 0; i < o.size() && i < 4; i++) order[i] = o[i];
   return (int)o.size();
+}
+
+// ---- generalised survival model (gsm_lite)
+static orc::gsm make_gsm(const msim_gsm *m) {  // gsm::gsm(Rcpp::List), gsm.cpp:60-92
+  orc::gsm g;
+  g.tmin = m->tmin / m->inflate;
+  g.tmax = m->tmax * m->inflate;
+  g.etap.assign(m->etap, m->etap + m->n_index);
+  g.etap0.assign(m->etap0, m->etap0 + m->n_index);
+  for (int i = 0; i < m->n_terms; i++) {
+    const msim_gsm_term &t = m->terms[i];
+    orc::gsm_term term;
+    term.gamma.assign(t.gamma, t.gamma + t.n_gamma);
+    orc::vec knots(t.knots, t.knots + t.n_knots), B(t.Boundary_knots, t.Boundary_knots + 2);
+    std::vector<orc::vec> q(t.q_rows, orc::vec(t.q_cols));
+    for (int r = 0; r < t.q_rows; r++)
+      for (int c = 0; c < t.q_cols; c++) q[r][c] = t.q_const[r * t.q_cols + c];
+    term.ns1 = orc::ns(B, knots, q, t.intercept, t.cure);
+    term.x.assign(t.x, t.x + m->n_index);
+    g.terms.push_back(term);
+  }
+  g.log_time = m->log_time != 0;
+  g.target = g.target0 = 0.0;
+  g.index = 0;
+  g.t0 = m->t0;
+  return g;
+}
+int oracle_gsm_randU(const msim_gsm *m, int64_t n, const double *u, const double *tentry, const int32_t *index, double scale,
+                     double *out) {
+  orc::gsm g = make_gsm(m);
+  for (int64_t i = 0; i < n; i++) out[i] = g.randU(u[i], tentry ? tentry[i] : 0.0, index ? index[i] : 0, scale);
+  return 0;
+}
+int oracle_gsm_randU0(const msim_gsm *m, int64_t n, const double *u, const int32_t *index, double scale, double *out) {
+  orc::gsm g = make_gsm(m);
+  for (int64_t i = 0; i < n; i++) out[i] = g.randU0(u[i], index ? index[i] : 0, scale);
+  return 0;
+}
+int oracle_gsm_eta(const msim_gsm *m, int64_t n, const double *y, const int32_t *index, double *out) {
+  orc::gsm g = make_gsm(m);
+  for (int64_t i = 0; i < n; i++) {
+    g.index = index ? index[i] : 0;
+    out[i] = g.eta(y[i]);
+  }
+  return 0;
+}
+// ns::eval(x, der) of term `term`: n_gamma values per x (scipy cross-check of the spline code)
+int oracle_ns_eval(const msim_gsm *m, int term, int64_t n, const double *x, int der, double *out) {
+  orc::gsm g = make_gsm(m);
+  for (int64_t i = 0; i < n; i++) {
+    orc::vec v = g.terms[term].ns1.eval(x[i], der);
+    for (size_t k = 0; k < v.size(); k++) out[i * v.size() + k] = v[k];
+  }
+  return 0;
+}
+// bs::eval(x, der) of term `term`: df values per x
+int oracle_bs_eval(const msim_gsm *m, int term, int64_t n, const double *x, int der, double *out) {
+  orc::gsm g = make_gsm(m);
+  for (int64_t i = 0; i < n; i++) {
+    orc::vec v = g.terms[term].ns1.bs::eval(x[i], der);
+    for (size_t k = 0; k < v.size(); k++) out[i * v.size() + k] = v[k];
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -242,6 +242,38 @@ class Oracle:
             d["trace"] = tr[:tlen.value].reshape(-1, 5)
         return d
 
+    # ---- generalised survival model (gsm_lite); `model` is a ctypes msim_gsm (include/msim.h), passed by reference
+    def _gsm(self, fn, model, u, extra, index, scale):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        out = np.empty_like(u)
+        idx = None if index is None else np.ascontiguousarray(index, dtype=np.int32)
+        args = [C.byref(model), C.c_int64(u.size), u.ctypes.data_as(C.POINTER(C.c_double))] + extra
+        args.append(idx.ctypes.data_as(C.POINTER(C.c_int32)) if idx is not None else None)
+        if scale is not None:
+            args.append(C.c_double(scale))
+        args.append(out.ctypes.data_as(C.POINTER(C.c_double)))
+        assert fn(*args) == 0
+        return out
+
+    def gsm_randU(self, model, u, tentry=None, index=None, scale=10.0):
+        te = None if tentry is None else np.ascontiguousarray(tentry, dtype=np.float64)
+        return self._gsm(self.lib.oracle_gsm_randU, model, u, [None if te is None else te.ctypes.data_as(C.POINTER(C.c_double))],
+                         index, scale)
+
+    def gsm_randU0(self, model, u, index=None, scale=10.0):
+        return self._gsm(self.lib.oracle_gsm_randU0, model, u, [], index, scale)
+
+    def gsm_eta(self, model, y, index=None):
+        return self._gsm(self.lib.oracle_gsm_eta, model, y, [], index, None)
+
+    def spline_eval(self, model, term, x, der=0, natural=True, width=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.zeros((x.size, width))
+        fn = self.lib.oracle_ns_eval if natural else self.lib.oracle_bs_eval
+        assert fn(C.byref(model), C.c_int(term), C.c_int64(x.size), x.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(der),
+                  out.ctypes.data_as(C.POINTER(C.c_double))) == 0
+        return out
+
     def tick_tock(self):
         buf = np.zeros(4096)
         n = self.lib.oracle_tick_tock(buf.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(buf.size))

@@ -21,6 +21,7 @@
 #include "../../microsimulation_b200/csrc/person_staged.cuh"
 #include "../../microsimulation_b200/csrc/report.cuh"
 #include "../../microsimulation_b200/csrc/report_host.h"
+#include "../../microsimulation_b200/csrc/gsm.cuh"
 #include "../../microsimulation_b200/csrc/seqstream.cuh"
 #include "../../microsimulation_b200/csrc/summary.cuh"
 
@@ -622,6 +623,52 @@ int emu_sick_sicker(int64_t n, const double par17[17], int indivp, int substream
     int64_t batch = (end_word - 1) / 624;
     memcpy(state + 1, w.data() + batch * 624, sizeof(uint32_t) * 624);
     state[0] = (uint32_t)(end_word - batch * 624);
+  }
+  return 0;
+}
+
+// the device's gsm functions (gsm.cuh) on the host: mode 0 randU, 1 randU0, 2 eta
+int emu_gsm(const msim_gsm *m, int mode, int64_t n, const double *u, const double *tentry, const int32_t *index, double scale,
+            double *out) {
+  static GsmModel M;
+  memset(&M, 0, sizeof M);
+  M.n_terms = m->n_terms;
+  M.log_time = m->log_time != 0;
+  M.n_index = m->n_index;
+  M.tmin = m->tmin / m->inflate;
+  M.tmax = m->tmax * m->inflate;
+  M.t0 = m->t0;
+  M.etap = m->etap;
+  M.etap0 = m->etap0;
+  for (int i = 0; i < m->n_terms; i++) {
+    const msim_gsm_term &t = m->terms[i];
+    GsmTerm &T = M.terms[i];
+    T.n_interior = t.n_knots;
+    T.intercept = t.intercept != 0;
+    T.cure = t.cure;
+    T.b0 = t.Boundary_knots[0];
+    T.b1 = t.Boundary_knots[1];
+    T.df = T.intercept + 3 + T.n_interior;
+    T.nknots = T.n_interior + 8;
+    T.ncoef = T.nknots - 4;
+    for (int k = 0; k < 4; k++) {
+      T.knots[k] = T.b0;
+      T.knots[T.nknots - k - 1] = T.b1;
+    }
+    for (int k = 0; k < T.n_interior; k++) T.knots[k + 4] = t.knots[k];
+    const bool tr = t.q_cols < t.q_rows;
+    const int rows = tr ? t.q_cols : t.q_rows, cols = tr ? t.q_rows : t.q_cols;
+    T.n_ns = rows;
+    for (int r = 0; r < rows; r++)
+      for (int c = 0; c < cols; c++) T.q[r][c] = tr ? t.q_const[c * t.q_cols + r] : t.q_const[r * t.q_cols + c];
+    for (int r = 0; r < rows; r++) T.gamma[r] = t.gamma[r];
+    gsm_term_finish(T);
+    M.x[i] = t.x;
+  }
+  for (int64_t i = 0; i < n; i++) {
+    int idx = index ? index[i] : 0;
+    out[i] = mode == 0 ? gsm_randU(M, u[i], tentry ? tentry[i] : 0.0, idx, scale)
+             : mode == 1 ? gsm_randU0(M, u[i], idx, scale) : gsm_eta(M, idx, u[i], false);
   }
   return 0;
 }
