@@ -89,9 +89,8 @@ int64_t msim_launch_count(void);
 /* Which GPU schedule the person-r entry points use: 0 (default) = staged
  * (persons are regrouped between stages so that warps stay full,
  * csrc/person_staged.cuh), 1 = generic (one person per thread straight
- * through, the kernel every other model uses), 2 = staged without the per-warp
- * report tables.  Same results either way; the switch exists so tests can
- * check exactly that. */
+ * through, the kernel every other model uses).  Same results either way; the
+ * switch exists so tests can check exactly that. */
 int msim_set_person_schedule(int which);
 /* Sizing of the person-r row-log buffers: expected rows per person (default
  * 1.25; the model logs 1.232) and expected rows beyond a person's first
@@ -155,6 +154,11 @@ int msim_callCalibrationSimulation(int32_t n, const double runpar[6], msim_calib
  * (n rows, or one row of totals when indivp = 0), SummaryReport::asList. */
 int msim_callSim_SickSicker(int32_t n, const double param[17], int indivp, int substreams, int64_t first_person,
                             msim_report *out);
+
+/* discountedInterval(y, start, end, rate) (mode 0; b = end) and discountedPoint(y, time, rate) (mode 1; b unused)
+ * of inst/include/microsimulation.h:811-836, element-wise on the GPU: the device functions models use for
+ * their own discounted totals; parity hook. */
+int msim_discounted(int mode, int64_t n, const double *y, const double *a, const double *b, double rate, double *out);
 
 /* ---- generalised survival models (src/gsm.cpp, src/splines.cpp) ------- */
 

@@ -52,7 +52,7 @@ def set_stream(cuda_stream=None):
 
 def set_person_schedule(which):
     """0 / "staged" (default) or 1 / "generic": which GPU schedule runs person-r (same results)."""
-    which = {"staged": 0, "generic": 1, "staged-shared": 2}.get(which, which)
+    which = {"staged": 0, "generic": 1}.get(which, which)
     check(load().msim_set_person_schedule(C.c_int(int(which))))
 
 
@@ -115,6 +115,26 @@ def rng_uniforms(seed, first_substream, n_substreams, draws):
 def mt_uniforms(n):
     out = np.empty(n)
     check(load().msim_mt_uniforms(C.c_int64(n), out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+def discountedInterval(y, start, end, discountRate):
+    """R/rcpp_hello_world.R:392-400 / microsimulation.h:821-824, element-wise on the GPU."""
+    y, a, b = (np.ascontiguousarray(np.broadcast_to(v, np.broadcast(y, start, end).shape), dtype=np.float64).ravel()
+               for v in (y, start, end))
+    out = np.empty_like(y)
+    dp = C.POINTER(C.c_double)
+    check(load().msim_discounted(0, y.size, y.ctypes.data_as(dp), a.ctypes.data_as(dp), b.ctypes.data_as(dp), float(discountRate),
+                                 out.ctypes.data_as(dp)))
+    return out
+
+
+def discountedPoint(y, time, discountRate):
+    y, a = (np.ascontiguousarray(np.broadcast_to(v, np.broadcast(y, time).shape), dtype=np.float64).ravel() for v in (y, time))
+    out = np.empty_like(y)
+    dp = C.POINTER(C.c_double)
+    check(load().msim_discounted(1, y.size, y.ctypes.data_as(dp), a.ctypes.data_as(dp), None, float(discountRate),
+                                 out.ctypes.data_as(dp)))
     return out
 
 

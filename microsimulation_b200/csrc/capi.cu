@@ -38,10 +38,9 @@ struct Ctx {
   MrgJump *d_lo = nullptr, *d_hi = nullptr;
   DevBuf rowlog, prov_start, prov_end, prov_meta, tile_count, partial, dense, small, mt_words, len, starts, chain_exit, chain_count, chain_entry, chain_base, calib_out,
       calib_par, uniforms, first_end, first_tag, row_off, ov_idx, ov_tag, ov_start, ov_end, aux, code_in, code_out, sgeom,
-      indiv, gsm_model, gsm_data, gsm_in, gsm_out;
+      indiv, gsm_model, gsm_data, gsm_in, gsm_out, slices;
   int person_kernel = 0;  // 0 = staged schedule (person_staged.cuh), 1 = generic cohort kernel
   bool last_staged = false;
-  int staged_warp_tables = 1;  // 0 switches the per-warp report tables off (experiments)
   double plan_rows = 1.25, plan_extra_rows = 0.26;  // row-log buffer planning (msim_set_rowlog_plan)
   int64_t last_ov_cap = 0, last_ov_rows = 0;
   HostRngState rng;
@@ -410,13 +409,7 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
   size_t smem = sizeof(WarpQueues) * SWARPS;
   if (p.outputs & OUT_ROWLOG) smem += sizeof(WarpRows) * SWARPS;
   if (p.outputs & OUT_REPORT) {
-    smem += (size_t)p.geom.off_dstart * 8 + (size_t)(p.geom.total - p.geom.off_dstart) * 4;
-    // per-warp tables for stage A's intervals, unless they would cost a resident block
-    const size_t with = smem + sizeof(WarpHot) * SWARPS;
-    if (g.staged_warp_tables && (with <= 113 * 1024 || smem > 113 * 1024)) {
-      p.warp_tables = 1;
-      smem = with;
-    }
+    smem += (size_t)(p.geom.total - p.geom.off_dstart) * 4;  // the counters; FP sums go to per-block global slices
   }
   int per_sm = 0;
   CK(cudaFuncSetAttribute(person_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -464,11 +457,27 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
     p.ov_cap = ov_cap;
   }
   g.last_ov_cap = ov_cap;
+#ifdef MSIM_EXP_GLOBAL_COUNTERS
+  const int slice = p.geom.total;
+#else
+  const int slice = p.geom.off_dstart;  // the FP sums (pt, ut)
+#endif
+  if (p.outputs & OUT_REPORT) {
+    const size_t bytes = sizeof(double) * (size_t)grid * slice;
+    if ((rc = ensure(g.slices, bytes))) return rc;
+    CK(cudaMemsetAsync(g.slices.p, 0, bytes, g.stream));
+    p.slices = (double *)g.slices.p;
+  }
   CK(cudaEventRecord(g.ev0, g.stream));
   if (p.n > 0) {
     person_staged_kernel<<<grid, SBLOCK, smem, g.stream>>>(p);
     CK(cudaGetLastError());
     g.launches++;
+    if (p.outputs & OUT_REPORT) {
+      fold_slices_kernel<<<(slice + 255) / 256, 256, 0, g.stream>>>(p.slices, grid, slice, p.dense);
+      CK(cudaGetLastError());
+      g.launches++;
+    }
     if (p.outputs & OUT_ROWLOG) {
       if ((rc = staged_rowpasses(p.n, p.first_person, capacity, true))) return rc;
     }
@@ -905,7 +914,7 @@ void msim_shutdown(void) {
   DevBuf *bufs[] = {&g.rowlog, &g.prov_start, &g.prov_end, &g.prov_meta, &g.tile_count, &g.partial, &g.dense, &g.small, &g.mt_words, &g.len, &g.starts, &g.chain_exit,
                     &g.chain_count, &g.chain_entry, &g.chain_base, &g.calib_out, &g.calib_par, &g.uniforms,
                     &g.first_end, &g.first_tag, &g.row_off, &g.ov_idx, &g.ov_tag, &g.ov_start, &g.ov_end,
-                    &g.aux, &g.code_in, &g.code_out, &g.sgeom, &g.indiv, &g.gsm_model, &g.gsm_data, &g.gsm_in, &g.gsm_out};
+                    &g.aux, &g.code_in, &g.code_out, &g.sgeom, &g.indiv, &g.gsm_model, &g.gsm_data, &g.gsm_in, &g.gsm_out, &g.slices};
   for (DevBuf *b : bufs) {
     if (b->p) cudaFree(b->p);
     b->p = nullptr;
@@ -942,9 +951,8 @@ int msim_set_rowlog_plan(double rows_per_person, double extra_rows_per_person) {
 }
 
 int msim_set_person_schedule(int which) {
-  if (which < 0 || which > 2) return fail(MSIM_ERR_ARG, "schedule must be 0 (staged), 1 (generic) or 2 (staged, shared tables only)");
-  g.person_kernel = which == 1 ? 1 : 0;
-  g.staged_warp_tables = which == 2 ? 0 : 1;
+  if (which != 0 && which != 1) return fail(MSIM_ERR_ARG, "schedule must be 0 (staged) or 1 (generic)");
+  g.person_kernel = which;
   return MSIM_OK;
 }
 
@@ -1135,6 +1143,27 @@ int msim_callCalibrationSimulation(int32_t n, const double runpar[6], msim_calib
 int msim_callSim_SickSicker(int32_t n, const double param[17], int indivp, int substreams, int64_t first_person,
                             msim_report *out) {
   return sick_sicker_run(n, param, indivp, substreams, first_person, out);
+}
+
+int msim_discounted(int mode, int64_t n, const double *y, const double *a, const double *b, double rate, double *out) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  if (n < 0 || (mode != 0 && mode != 1) || (n > 0 && (!y || !a || !out || (mode == 0 && !b)))) return fail(MSIM_ERR_ARG, "bad arguments");
+  if (n == 0) return MSIM_OK;
+  const size_t nn = (size_t)n;
+  if ((rc = ensure(g.gsm_in, sizeof(double) * 3 * nn))) return rc;
+  if ((rc = ensure(g.gsm_out, sizeof(double) * nn))) return rc;
+  double *d = (double *)g.gsm_in.p;
+  CK(cudaMemcpyAsync(d, y, sizeof(double) * nn, cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemcpyAsync(d + nn, a, sizeof(double) * nn, cudaMemcpyHostToDevice, g.stream));
+  if (mode == 0) CK(cudaMemcpyAsync(d + 2 * nn, b, sizeof(double) * nn, cudaMemcpyHostToDevice, g.stream));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)g.sm_count * 8));
+  discount_kernel<<<grid, 256, 0, g.stream>>>(mode, n, d, d + nn, d + 2 * nn, rate, (double *)g.gsm_out.p);
+  CK(cudaGetLastError());
+  g.launches++;
+  CK(cudaMemcpyAsync(out, g.gsm_out.p, sizeof(double) * nn, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return MSIM_OK;
 }
 
 int msim_gsm_randU(const msim_gsm *model, int64_t n, const double *u, const double *tentry, const int32_t *index,

@@ -126,17 +126,6 @@ struct alignas(16) WarpRows {
   double x_start[XROWS][32], x_end[XROWS][32];
   uint32_t x_meta[XROWS][32];
 };
-// A warp's PRIVATE slice of the report for the commonest interval — a person's
-// first, from the first partition point, in the model's initial state, ended
-// by event `hot_event` — indexed by the age bin it ends in.  Updated with plain
-// loads and stores (no atomics: only this warp touches it, and lanes that hit
-// the same bin are merged first), folded into the block's tables at the end
-// (report runs only).
-struct alignas(16) WarpHot {
-  double pt[REPORT_MAX_BINS], ut[REPORT_MAX_BINS];
-  unsigned ev[REPORT_MAX_BINS];
-};
-
 struct StagedParams {
   StreamStart st;  // stride = M^(gridDim.x*SBLOCK)
   int64_t first_person, n;
@@ -144,6 +133,7 @@ struct StagedParams {
   person_r::Consts consts;
   ReportGeom geom;
   double *dense;   // dense report accumulators in global memory (zeroed before launch)
+  double *slices;  // gridDim.x slices of geom.off_dstart doubles (pt, ut), zeroed before launch
   double *counts;  // N_COUNTS doubles
   int *error;
   // row log, first pass
@@ -153,13 +143,17 @@ struct StagedParams {
   double *ov_start, *ov_end;
   unsigned long long *ov_count;
   int64_t ov_cap;
-  int warp_tables;  // 1: stage A accumulates its intervals in per-warp tables (WarpHot)
 };
 
-// Report accumulators of a block in shared memory ([0, n_f) doubles, then
-// ints), flushed once per block with red.global.add.f64.  (Accumulating
-// straight into global memory was measured at 38 ms per 1e8 persons: a few
-// hundred hot cells serialise in L2.)
+// Report accumulators of a block.  Counters: a shared-memory table, native
+// 32-bit atomics, flushed once per block with red.global.add.f64.  FP sums
+// (pt, ut) outside the per-warp hot tables: red.global.add.f64 into a slice of
+// global memory that only THIS block writes (fire and forget, no return value
+// to wait for; shared memory has no native f64 add on sm_100a — atomicAdd there
+// is a compare-and-swap loop that cost 2.7 ms per 1e8 persons).  A fold kernel
+// sums the slices afterwards.  (All blocks accumulating into ONE global vector
+// was measured at 38 ms per 1e8 persons: a few hundred hot cells serialise in
+// L2.)
 struct StagedAcc {
   double *f;
   int *i;
@@ -169,19 +163,23 @@ struct StagedAcc {
   // cost nothing until the cell changes
   int pend_idx;
   int pend_n;
-  __device__ __forceinline__ void addf(int idx, double v) { atomicAdd(&f[idx], v); }
+  __device__ __forceinline__ void addf(int idx, double v) { atomicAdd(&f[idx], v); }  // f: this block's global slice
+#ifdef MSIM_EXP_GLOBAL_COUNTERS  // experiment: counters, too, as f64 REDs into the block's global slice
+  __device__ __forceinline__ void addi(int idx, int v) { atomicAdd(&f[idx], (double)v); }
+#else
   __device__ __forceinline__ void addi(int idx, int v) { atomicAdd(&i[idx - n_f], v); }
+#endif
   __device__ __forceinline__ void addc(int idx) {
     if (idx == pend_idx) {
       pend_n++;
     } else {
-      if (pend_n) atomicAdd(&i[pend_idx - n_f], pend_n);
+      if (pend_n) addi(pend_idx, pend_n);
       pend_idx = idx;
       pend_n = 1;
     }
   }
   __device__ __forceinline__ void flush() {
-    if (pend_n) atomicAdd(&i[pend_idx - n_f], pend_n);
+    if (pend_n) addi(pend_idx, pend_n);
     pend_n = 0;
     pend_idx = -1;
   }
@@ -203,12 +201,6 @@ struct StagedEnv {
   unsigned first_tag;
   WarpRows *wq;
   int lane;
-  // stage A with per-warp tables: report() only notes the interval; the warp adds all lanes' together
-  bool defer;
-  bool pend;
-  int pend_state, pend_kind;
-  double pend_lhs, pend_rhs;
-
   __device__ __forceinline__ void begin_person() {
     cursor.valid = false;
     nrows = 0;
@@ -233,60 +225,9 @@ struct StagedEnv {
     }
   }
   __device__ __forceinline__ void report(int state, int kind, double lhs, double rhs) {
-    if (!(outputs & 2u)) return;
-    if (defer && !pend) {
-      pend = true;
-      pend_state = state;
-      pend_kind = kind;
-      pend_lhs = lhs;
-      pend_rhs = rhs;
-    } else {
-      report_add(*geom, acc, cursor, state, kind, lhs, rhs);
-    }
+    if (outputs & 2u) report_add(*geom, acc, cursor, state, kind, lhs, rhs);
   }
 };
-
-// All 32 lanes together add the intervals noted during stage A.  An interval
-// that is not the hot kind goes through report_add as usual.  For the hot kind
-// (lo = first bin, on its edge; report.cuh) the cells are
-//   events[s0][e0][hi] += 1, dstart[s0][0] += 1, pt/ut[s0][hi] += overlap with bin hi,
-// and a lane that is alone in its bin (the usual case) updates the table with a
-// plain load/add/store; lanes that share a bin use atomics among themselves.
-__device__ __forceinline__ void staged_report_warp(const ReportGeom &g, StagedEnv &env, WarpHot &H, int s0, int e0, int lane) {
-  const bool has = env.pend;
-  env.pend = false;
-  const bool hot = has && env.pend_state == s0 && env.pend_kind == e0 && env.pend_lhs == g.part_start;
-  if (has && !hot) {
-    ReportCursor none;
-    none.valid = false;
-    report_add(g, env.acc, none, env.pend_state, env.pend_kind, env.pend_lhs, env.pend_rhs);
-  }
-  __syncwarp();
-  const double rhs = env.pend_rhs;
-  int hi = -1 - lane;  // lanes without a hot interval match nobody
-  double v_pt = 0.0, v_ut = 0.0;
-  if (hot) {
-    hi = report_bin(g, rhs);
-    const double phi = report_part(g, hi);
-    v_pt = rhs - phi;
-    if (g.discount_rate != 0.0) v_ut = report_discounted_e(g, phi, rhs, g.edge_decay[hi], report_decay(g, rhs));
-    env.acc.addc(g.off_dstart + s0 * g.n_bin);
-    if (!(phi < rhs)) env.acc.addi(g.off_noedge + s0 * g.n_bin + hi, 1);
-  }
-  const unsigned peers = __match_any_sync(0xffffffffu, hi);
-  if (hot) {
-    if (peers == (1u << lane)) {  // the only lane ending in this bin: plain read-modify-write
-      H.pt[hi] += v_pt;
-      H.ut[hi] += v_ut;
-      H.ev[hi] += 1u;
-    } else {  // a few lanes share the bin: they (and nobody else) meet on its cells
-      atomicAdd(&H.pt[hi], v_pt);
-      atomicAdd(&H.ut[hi], v_ut);
-      if (lane == __ffs(peers) - 1) atomicAdd(&H.ev[hi], (unsigned)__popc(peers));
-    }
-  }
-  __syncwarp();
-}
 
 // a finished person's first row and row count (rows beyond the first stay staged until the warp appends them)
 __device__ __forceinline__ void staged_finish(const StagedParams &p, StagedEnv &env, uint32_t idx, int *err) {
@@ -325,18 +266,19 @@ __device__ __forceinline__ void staged_append_extra(const StagedParams &p, Stage
 
 __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const __grid_constant__ StagedParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // shared layout: [per-warp queues | per-warp row staging (row log) | per-warp hot tables (report) |
-  //                 dense doubles | dense ints]
+  // shared layout: [per-warp queues | per-warp row staging (row log) | report counters]
   WarpQueues *queues = reinterpret_cast<WarpQueues *>(smem_raw);
   unsigned char *sp = smem_raw + sizeof(WarpQueues) * SWARPS;
   WarpRows *rows_stage = reinterpret_cast<WarpRows *>(sp);
   if (p.outputs & 1u) sp += sizeof(WarpRows) * SWARPS;
-  WarpHot *hots = reinterpret_cast<WarpHot *>(sp);
-  if (p.warp_tables) sp += sizeof(WarpHot) * SWARPS;
   const int total = (p.outputs & 2u) ? p.geom.total : 0;
   const int n_f = (p.outputs & 2u) ? p.geom.off_dstart : 0;
-  double *s_f = reinterpret_cast<double *>(sp);
-  int *s_i = reinterpret_cast<int *>(s_f + n_f);
+  int *s_i = reinterpret_cast<int *>(sp);
+#ifdef MSIM_EXP_GLOBAL_COUNTERS
+  double *g_f = p.slices + (size_t)blockIdx.x * p.geom.total;
+#else
+  double *g_f = p.slices + (size_t)blockIdx.x * n_f;  // this block's slice of the FP sums
+#endif
   __shared__ unsigned s_kind[8];
   __shared__ double s_sum[SWARPS];
   __shared__ int s_error;
@@ -345,21 +287,13 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
   WarpQueues &Q = queues[warp];
   if (tid < 8) s_kind[tid] = 0;
   if (tid == 0) s_error = 0;
-  for (int k = tid; k < n_f; k += SBLOCK) s_f[k] = 0.0;
   for (int k = tid; k < total - n_f; k += SBLOCK) s_i[k] = 0;
-  WarpHot &H = hots[warp];
-  if (p.warp_tables)
-    for (int k = lane; k < REPORT_MAX_BINS; k += 32) {
-      H.pt[k] = 0.0;
-      H.ut[k] = 0.0;
-      H.ev[k] = 0u;
-    }
   __syncthreads();
 
   StagedEnv env;
   env.outputs = p.outputs;
   env.geom = &p.geom;
-  env.acc.f = s_f;
+  env.acc.f = g_f;
   env.acc.i = s_i;
   env.acc.n_f = n_f;
   env.acc.pend_idx = -1;
@@ -370,10 +304,6 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
   env.first_end = 0.0;
   env.first_tag = 0;
   env.wq = &rows_stage[warp];
-  env.defer = false;
-  env.pend = false;
-  env.pend_state = env.pend_kind = 0;
-  env.pend_lhs = env.pend_rhs = 0.0;
   env.lane = lane;
   env.cursor.valid = false;
   int err = 0;
@@ -448,14 +378,11 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
       const uint32_t idx = (uint32_t)i64;
       bool park = false;
       person_r::ParkedOnset out;
-      env.defer = p.warp_tables != 0;
       if (i64 < p.n) {
         env.src.g = sub;
         park = !person_r::stage_a(env, K, p.first_person + i64, &out);
         if (!park) staged_finish(p, env, idx, &err);
       }
-      env.defer = false;
-      if (p.warp_tables) staged_report_warp(p.geom, env, H, person_r::Healthy, person_r::toDeath, lane);
       sub.jump(p.st.stride);
       const unsigned mk = __ballot_sync(0xffffffffu, park);
       if (park) {
@@ -477,18 +404,6 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
   }
 
   env.acc.flush();
-  if (p.warp_tables) {  // fold this warp's private slice into the block's tables
-    __syncwarp();
-    const ReportGeom &g = p.geom;
-    const int s0 = person_r::Healthy, e0 = person_r::toDeath;
-    for (int k = lane; k < g.n_bin; k += 32) {
-      if (H.ev[k]) {
-        atomicAdd(&s_f[g.off_pt + s0 * g.n_bin + k], H.pt[k]);
-        if (g.discount_rate != 0.0) atomicAdd(&s_f[g.off_ut + s0 * g.n_bin + k], H.ut[k]);
-        atomicAdd(&s_i[g.off_events + (s0 * g.n_event + e0) * g.n_bin + k - n_f], (int)H.ev[k]);
-      }
-    }
-  }
   if (err) atomicCAS(&s_error, 0, err);
   if (p.outputs & 4u) {
 #pragma unroll
@@ -504,10 +419,6 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
     if (lane == 0) s_sum[warp] = v;
   }
   __syncthreads();
-  for (int k = tid; k < n_f; k += SBLOCK) {
-    const double v = s_f[k];
-    if (v != 0.0) atomicAdd(&p.dense[k], v);
-  }
   for (int k = tid; k < total - n_f; k += SBLOCK) {
     const int v = s_i[k];
     if (v != 0) atomicAdd(&p.dense[n_f + k], (double)v);
@@ -521,6 +432,15 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
     }
   }
   if (tid == 0 && s_error) atomicCAS(p.error, 0, s_error);
+}
+
+// dense[k] += sum over blocks of slices[b][k], k < n_f: one thread per cell, a fixed order of addition
+__global__ void __launch_bounds__(256) fold_slices_kernel(const double *slices, int n_slices, int n_f, double *dense) {
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= n_f) return;
+  double t = 0.0;
+  for (int b = 0; b < n_slices; b++) t += slices[(size_t)b * n_f + k];
+  dense[k] += t;
 }
 
 // ---- row log passes -----------------------------------------------------------

@@ -127,13 +127,20 @@ struct ReportCursor {
   bool valid;
 };
 
-// Acc supplies addf(index, double) for FP sums, addi(index, int) for counters
-// and addc(index) for the `dstart` counter (+1; consecutive calls usually name
-// the same cell, which an accumulator may exploit) on the dense vector.
-template <class Acc>
-MSIM_DEV void report_add(const ReportGeom &g, Acc &acc, ReportCursor &cur, int state, int event, double lhs, double rhs) {
+// The cells one interval touches (see the header comment): what report_add
+// adds, separated from HOW it is added so that a warp can add its lanes'
+// intervals together (person_staged.cuh).
+struct ReportCells {
+  int i_events, i_dstart;  // counters to increment
+  bool noedge;             // also increment noedge[s][hi]
+  int row_hi, row_lo;      // state*n_bin + bin of the partial overlaps; row_lo < 0: none
+  double pt_hi, ut_hi, pt_lo, ut_lo;
+};
+
+MSIM_HD ReportCells report_cells(const ReportGeom &g, ReportCursor &cur, int state, int event, double lhs, double rhs) {
   const int nb = g.n_bin;
   const bool disc = g.discount_rate != 0.0;  // rate 0: ut == pt, filled in at finalisation
+  ReportCells c;
   int lo;
   double elhs = 1.0;
   if (cur.valid && cur.t == lhs) {
@@ -153,26 +160,50 @@ MSIM_DEV void report_add(const ReportGeom &g, Acc &acc, ReportCursor &cur, int s
   const int row = state * nb;
   const double plo = report_part(g, lo);
   const bool on_edge = lhs <= plo;
-  acc.addi(g.off_events + (state * g.n_event + event) * nb + hi, 1);
+  c.i_events = g.off_events + (state * g.n_event + event) * nb + hi;
   int f0 = on_edge ? lo : lo + 1;
   if (f0 > hi) f0 = hi;
-  acc.addc(g.off_dstart + row + f0);
+  c.i_dstart = g.off_dstart + row + f0;
+  c.row_hi = row + hi;
+  c.row_lo = -1;
+  c.pt_lo = c.ut_lo = 0.0;
+  c.ut_hi = 0.0;
   if (lo == hi) {
     const double a = on_edge ? plo : lhs;
-    acc.addf(g.off_pt + row + hi, rhs - a);
-    if (disc) acc.addf(g.off_ut + row + hi, report_discounted_e(g, a, rhs, on_edge ? g.edge_decay[lo] : elhs, erhs));
-    if (!(on_edge && plo < rhs)) acc.addi(g.off_noedge + row + hi, 1);
-    return;
+    c.pt_hi = rhs - a;
+    if (disc) c.ut_hi = report_discounted_e(g, a, rhs, on_edge ? g.edge_decay[lo] : elhs, erhs);
+    c.noedge = !(on_edge && plo < rhs);
+    return c;
   }
   if (!on_edge) {
     const double nxt = report_part(g, lo + 1);
-    acc.addf(g.off_pt + row + lo, nxt - lhs);
-    if (disc) acc.addf(g.off_ut + row + lo, report_discounted_e(g, lhs, nxt, elhs, g.edge_decay[lo + 1]));
+    c.row_lo = row + lo;
+    c.pt_lo = nxt - lhs;
+    if (disc) c.ut_lo = report_discounted_e(g, lhs, nxt, elhs, g.edge_decay[lo + 1]);
   }
   const double phi = report_part(g, hi);
-  acc.addf(g.off_pt + row + hi, rhs - phi);
-  if (disc) acc.addf(g.off_ut + row + hi, report_discounted_e(g, phi, rhs, g.edge_decay[hi], erhs));
-  if (!(phi < rhs)) acc.addi(g.off_noedge + row + hi, 1);
+  c.pt_hi = rhs - phi;
+  if (disc) c.ut_hi = report_discounted_e(g, phi, rhs, g.edge_decay[hi], erhs);
+  c.noedge = !(phi < rhs);
+  return c;
+}
+
+// Acc supplies addf(index, double) for FP sums, addi(index, int) for counters
+// and addc(index) for the `dstart` counter (+1; consecutive calls usually name
+// the same cell, which an accumulator may exploit) on the dense vector.
+template <class Acc>
+MSIM_DEV void report_add(const ReportGeom &g, Acc &acc, ReportCursor &cur, int state, int event, double lhs, double rhs) {
+  const ReportCells c = report_cells(g, cur, state, event, lhs, rhs);
+  const bool disc = g.discount_rate != 0.0;
+  acc.addi(c.i_events, 1);
+  acc.addc(c.i_dstart);
+  if (c.row_lo >= 0) {
+    acc.addf(g.off_pt + c.row_lo, c.pt_lo);
+    if (disc) acc.addf(g.off_ut + c.row_lo, c.ut_lo);
+  }
+  acc.addf(g.off_pt + c.row_hi, c.pt_hi);
+  if (disc) acc.addf(g.off_ut + c.row_hi, c.ut_hi);
+  if (c.noedge) acc.addi(g.off_noedge + c.row_hi, 1);
 }
 
 }  // namespace msim

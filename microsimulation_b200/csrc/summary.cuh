@@ -161,4 +161,22 @@ MSIM_DEV double summary_point_cost(const SummaryGeom &g, Acc &acc, int state, do
   return v;
 }
 
+// The free functions models use for their own running totals (microsimulation.h:811-836; e.g. the
+// illness-death doc example, inst/doc/examples.org:300-336): integral of y*(1+rate)^(-u) over [start, end],
+// and y/(1+rate)^time.  Written with pow, as the reference writes them.
+MSIM_HD double discountedInterval(double y, double start, double end, double discountRate) {
+  if (discountRate == 0.0) return y * (end - start);
+  return y * (pow(1.0 + discountRate, -start) - pow(1.0 + discountRate, -end)) / log(1.0 + discountRate);
+}
+MSIM_HD double discountedInterval(double start, double end, double discountRate) {
+  if (discountRate == 0.0) return end - start;
+  return (pow(1.0 + discountRate, -start) - pow(1.0 + discountRate, -end)) / log(1.0 + discountRate);
+}
+MSIM_HD double discountedPoint(double y, double time, double discountRate) {
+  return discountRate <= 0.0 ? y : y * pow(1.0 + discountRate, -time);
+}
+MSIM_HD double discountedPoint(double time, double discountRate) {
+  return discountRate <= 0.0 ? 1.0 : pow(1.0 + discountRate, -time);
+}
+
 }  // namespace msim

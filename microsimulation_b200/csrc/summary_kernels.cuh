@@ -192,4 +192,11 @@ inline size_t sick_kernel_smem(const SummaryGeom &g) {
   return ((sizeof(SummaryGeom) + 15) & ~(size_t)15) + (size_t)g.n_float * 8 + (size_t)(g.total - g.n_float) * 4;
 }
 
+// parity hook for the discounting free functions: out[i] = discountedInterval(y[i], a[i], b[i], rate) (mode 0) or
+// discountedPoint(y[i], a[i], rate) (mode 1)
+__global__ void discount_kernel(int mode, int64_t n, const double *y, const double *a, const double *b, double rate, double *out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = mode == 0 ? discountedInterval(y[i], a[i], b[i], rate) : discountedPoint(y[i], a[i], rate);
+}
+
 }  // namespace msim

@@ -11,7 +11,7 @@ api.set_person_schedule(int(os.environ.get("MSIM_SCHED", "0")))
 for outputs, nm in ((4, "counts"), (2 | 4, "report+counts"), (1, "rowlog")):
     best = 1e9
     for _ in range(4):
-        api.person_run_device(12345, 0, n, outputs, 0.03)
+        api.person_run_device(12345, 0, n, outputs, float(os.environ.get("MSIM_RATE", "0.03")))
         best = min(best, api.last_kernel_ms())
     print("%%-28s %%-14s %%.3f ms  %%.3e persons/s" %% (os.path.basename(os.environ.get("MSIM_B200_LIB", "default")) + " s" + os.environ.get("MSIM_SCHED", "0"), nm, best, n / best * 1e3), flush=True)
 ''' % ROOT
