@@ -43,22 +43,24 @@ struct ParkedOnset {
   Mrg32k3a g;  // RngStream state after init()'s draws
   double u_onset, t_death;
 };
-// a person parked after stage B1: both init() events known, toLocalised comes first
-struct ParkedLoop {
+// a person whose init() events are known: toLocalised at t_onset (if has_onset) and toDeath at t_death
+struct Life {
   Mrg32k3a g;
   double t_onset, t_death;
+  bool has_onset;
 };
 
-// Stage A.  Returns true if the person is finished.
+// Stage A: init()'s draws.  Returns true if the person can run now (no onset draw: a single toDeath event).
 template <class Env>
-MSIM_DEV bool stage_a(Env &env, const Consts &K, int64_t id, ParkedOnset *park) {
+MSIM_DEV bool stage_a(Env &env, ParkedOnset *park, Life *life) {
   RMath<typename Env::Src> R(&env.src);
   double u_onset = 0.0, t_death = 0.0;
   const bool onset = Person<Env>::init_draws(R, &u_onset, &t_death);
   if (!onset) {
-    Person<Env> person(env, K, id);
-    person.scheduleAt(t_death, toDeath);  // init(): the only event (person-r.cc:102)
-    person.resume_after_init();
+    life->g = env.src.g;
+    life->t_onset = 0.0;
+    life->t_death = t_death;
+    life->has_onset = false;
     return true;
   }
   park->g = env.src.g;
@@ -67,32 +69,27 @@ MSIM_DEV bool stage_a(Env &env, const Consts &K, int64_t id, ParkedOnset *park) 
   return false;
 }
 
-// Stage B1.  Returns true if the person is finished (death pops before onset:
-// strictly earlier, because toLocalised was inserted first — heap.h:75-88).
+// Stage B1: the onset time.  Returns true if the person can run now: death pops before onset (strictly
+// earlier, because toLocalised was inserted first — heap.h:75-88), so nothing but toDeath will be handled.
 template <class Env>
-MSIM_DEV bool stage_b1(Env &env, const Consts &K, int64_t id, const ParkedOnset &in, ParkedLoop *park) {
-  const double t_onset = Person<Env>::onset_time(K, in.u_onset);
-  if (in.t_death < t_onset) {
-    env.src.g = in.g;
-    Person<Env> person(env, K, id);
-    person.scheduleAt(t_onset, toLocalised);
-    person.scheduleAt(in.t_death, toDeath);
-    person.resume_after_init();
-    return true;
-  }
-  park->g = in.g;
-  park->t_onset = t_onset;
-  park->t_death = in.t_death;
-  return false;
+MSIM_DEV bool stage_b1(const Consts &K, const ParkedOnset &in, Life *life) {
+  life->g = in.g;
+  life->t_onset = Person<Env>::onset_time(K, in.u_onset);
+  life->t_death = in.t_death;
+  life->has_onset = true;
+  return in.t_death < life->t_onset;
 }
 
-// Stage B2: the rest of the life.
+// The one place a person's events run: init()'s scheduleAt calls in init()'s order (person-r.cc:100-102), then
+// Sim::run_simulation's loop from just after A_Init.
 template <class Env>
-MSIM_DEV void stage_b2(Env &env, const Consts &K, int64_t id, const ParkedLoop &in, int *error) {
-  env.src.g = in.g;
+MSIM_DEV void run_life(Env &env, const Consts &K, int64_t id, const Life &life, int *error) {
+  env.src.g = life.g;
   Person<Env> person(env, K, id);
-  person.scheduleAt(in.t_onset, toLocalised);  // init()'s order (person-r.cc:100-102)
-  person.scheduleAt(in.t_death, toDeath);
+  // (one code path for every person: writing the one-event case apart lets the compiler fold it — 5% faster
+  // without reports — but a second copy of the handler and report code costs more than that with them)
+  if (life.has_onset) person.scheduleAt(life.t_onset, toLocalised);
+  person.scheduleAt(life.t_death, toDeath);
   person.resume_after_init();
   if (person.error_) *error = person.error_;
 }
@@ -281,18 +278,23 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
 #endif
   __shared__ unsigned s_kind[8];
   __shared__ double s_sum[SWARPS];
+  // the report geometry in shared memory: its tables are indexed per lane (a constant-bank load with a
+  // different index in every lane is serialised)
+  __shared__ ReportGeom s_geom;
   __shared__ int s_error;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   WarpQueues &Q = queues[warp];
   if (tid < 8) s_kind[tid] = 0;
   if (tid == 0) s_error = 0;
+  for (int k = tid; k < (int)(sizeof(ReportGeom) / 4); k += SBLOCK)
+    reinterpret_cast<int *>(&s_geom)[k] = reinterpret_cast<const int *>(&p.geom)[k];
   for (int k = tid; k < total - n_f; k += SBLOCK) s_i[k] = 0;
   __syncthreads();
 
   StagedEnv env;
   env.outputs = p.outputs;
-  env.geom = &p.geom;
+  env.geom = &s_geom;
   env.acc.f = g_f;
   env.acc.i = s_i;
   env.acc.n_f = n_f;
@@ -314,93 +316,86 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
   const int64_t gw = (int64_t)blockIdx.x * SWARPS + warp, GW = (int64_t)gridDim.x * SWARPS;
   int c1 = 0, c2 = 0;  // queue fills (warp-uniform)
 
-  // ---- stage B2 on the top `m` (<= 32) entries of queue 2
-  auto run_b2 = [&](int m) {
-    c2 -= m;
-    const bool act = lane < m;
+  // Each pass of the loop runs ONE stage on up to 32 persons and then, in one place for all stages, the events
+  // of the persons that became ready in it: new persons while there are tiles (stage A), parked persons
+  // whenever a full warp of them waits (B1: onset times; B2: lives with onset before death), and whatever is
+  // left once the tiles are used up.
+  for (int64_t tile = gw;;) {
+    const bool last = tile >= n_tiles;
+    bool ready = false, park1 = false, park2 = false;
+    person_r::Life life;
+    person_r::ParkedOnset po;
     uint32_t idx = 0;
-    if (act) {
-      const int e = c2 + lane;
-      person_r::ParkedLoop in;
+    if (c2 >= 32 || (last && c1 == 0 && c2 > 0)) {
+      // ---- stage B2: the top <= 32 entries of queue 2
+      const int m = c2 > 32 ? 32 : c2;
+      c2 -= m;
+      if (lane < m) {
+        const int e = c2 + lane;
 #pragma unroll
-      for (int k = 0; k < 6; k++) in.g.s[k] = Q.q2_s[k][e];
-      in.t_onset = Q.q2_on[e];
-      in.t_death = Q.q2_t[e];
-      idx = Q.q2_idx[e];
-      person_r::stage_b2(env, K, p.first_person + idx, in, &err);
+        for (int k = 0; k < 6; k++) life.g.s[k] = Q.q2_s[k][e];
+        life.t_onset = Q.q2_on[e];
+        life.t_death = Q.q2_t[e];
+        life.has_onset = true;
+        idx = Q.q2_idx[e];
+        ready = true;
+      }
+    } else if (c1 >= 32 || (last && c1 > 0)) {
+      // ---- stage B1: the top <= 32 entries of queue 1; those with onset before death go to queue 2
+      const int m = c1 > 32 ? 32 : c1;
+      c1 -= m;
+      if (lane < m) {
+        const int e = c1 + lane;
+#pragma unroll
+        for (int k = 0; k < 6; k++) po.g.s[k] = Q.q1_s[k][e];
+        po.u_onset = Q.q1_u[e];
+        po.t_death = Q.q1_t[e];
+        idx = Q.q1_idx[e];
+        ready = person_r::stage_b1<StagedEnv>(K, po, &life);
+        park2 = !ready;
+      }
+    } else if (!last) {
+      // ---- stage A: 32 new persons
+      const int64_t i64 = tile * 32 + lane;
+      idx = (uint32_t)i64;
+      if (i64 < p.n) {
+        env.src.g = sub;
+        ready = person_r::stage_a(env, &po, &life);
+        park1 = !ready;
+      }
+      sub.jump(p.st.stride);
+      tile += GW;
+    } else {
+      break;
+    }
+    // ---- parked persons join their queue (push by lane order)
+    const unsigned m1 = __ballot_sync(0xffffffffu, park1), m2 = __ballot_sync(0xffffffffu, park2);
+    if (park1) {
+      const int e = c1 + __popc(m1 & lt_mask);
+#pragma unroll
+      for (int k = 0; k < 6; k++) Q.q1_s[k][e] = po.g.s[k];
+      Q.q1_u[e] = po.u_onset;
+      Q.q1_t[e] = po.t_death;
+      Q.q1_idx[e] = idx;
+    }
+    if (park2) {
+      const int e = c2 + __popc(m2 & lt_mask);
+#pragma unroll
+      for (int k = 0; k < 6; k++) Q.q2_s[k][e] = life.g.s[k];
+      Q.q2_on[e] = life.t_onset;
+      Q.q2_t[e] = life.t_death;
+      Q.q2_idx[e] = idx;
+    }
+    c1 += __popc(m1);
+    c2 += __popc(m2);
+    // ---- the persons that are ready run their events
+    if (ready) {
+      person_r::run_life(env, K, p.first_person + idx, life, &err);
       staged_finish(p, env, idx, &err);
     }
     __syncwarp();
-    if (p.outputs & 1u) staged_append_extra(p, env, act, idx, lane);
+    if (p.outputs & 1u) staged_append_extra(p, env, ready, idx, lane);
     __syncwarp();
-  };
-
-  // ---- stage B1 on the top `m` (<= 32) entries of queue 1; survivors go to queue 2
-  auto run_b1 = [&](int m) {
-    c1 -= m;
-    const bool act = lane < m;
-    bool park = false;
-    person_r::ParkedLoop out;
-    uint32_t idx = 0;
-    if (act) {
-      const int e = c1 + lane;
-      person_r::ParkedOnset in;
-#pragma unroll
-      for (int k = 0; k < 6; k++) in.g.s[k] = Q.q1_s[k][e];
-      in.u_onset = Q.q1_u[e];
-      in.t_death = Q.q1_t[e];
-      idx = Q.q1_idx[e];
-      park = !person_r::stage_b1(env, K, p.first_person + idx, in, &out);
-      if (!park) staged_finish(p, env, idx, &err);
-    }
-    __syncwarp();
-    const unsigned mk = __ballot_sync(0xffffffffu, park);
-    if (park) {
-      const int e = c2 + __popc(mk & lt_mask);
-#pragma unroll
-      for (int k = 0; k < 6; k++) Q.q2_s[k][e] = out.g.s[k];
-      Q.q2_on[e] = out.t_onset;
-      Q.q2_t[e] = out.t_death;
-      Q.q2_idx[e] = idx;
-    }
-    c2 += __popc(mk);
-    __syncwarp();
-  };
-
-  // One loop body for all three stages (each stage's code exists once): new
-  // persons while there are tiles, parked persons whenever a full warp of them
-  // waits, and whatever is left once the tiles are used up.
-  for (int64_t tile = gw;;) {
-    const bool fresh = tile < n_tiles;
-    if (fresh) {
-      // ---- stage A on 32 new persons
-      const int64_t i64 = tile * 32 + lane;
-      const uint32_t idx = (uint32_t)i64;
-      bool park = false;
-      person_r::ParkedOnset out;
-      if (i64 < p.n) {
-        env.src.g = sub;
-        park = !person_r::stage_a(env, K, p.first_person + i64, &out);
-        if (!park) staged_finish(p, env, idx, &err);
-      }
-      sub.jump(p.st.stride);
-      const unsigned mk = __ballot_sync(0xffffffffu, park);
-      if (park) {
-        const int e = c1 + __popc(mk & lt_mask);
-#pragma unroll
-        for (int k = 0; k < 6; k++) Q.q1_s[k][e] = out.g.s[k];
-        Q.q1_u[e] = out.u_onset;
-        Q.q1_t[e] = out.t_death;
-        Q.q1_idx[e] = idx;
-      }
-      c1 += __popc(mk);
-      __syncwarp();
-      tile += GW;
-    }
-    const bool last = tile >= n_tiles;
-    if (c1 >= 32 || (last && c1 > 0)) run_b1(c1 > 32 ? 32 : c1);
-    if (c2 >= 32 || (last && c1 == 0 && c2 > 0)) run_b2(c2 > 32 ? 32 : c2);
-    if (last && c1 == 0 && c2 == 0) break;
   }
 
   env.acc.flush();

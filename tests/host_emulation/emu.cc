@@ -348,7 +348,7 @@ int emu_person_run_staged(const msim_person_shard *sh, int grid, msim_table *row
     int64_t idx;
   };
   struct E2 {
-    person_r::ParkedLoop p;
+    person_r::Life p;
     int64_t idx;
   };
   int err = 0;
@@ -358,36 +358,42 @@ int emu_person_run_staged(const msim_person_shard *sh, int grid, msim_table *row
     std::vector<E1> q1;
     std::vector<E2> q2;
     for (int64_t tile = gw;;) {
-      if (tile < n_tiles) {
+      const bool last = tile >= n_tiles;
+      std::vector<E2> ready;
+      if (q2.size() >= 32 || (last && q1.empty() && !q2.empty())) {
+        size_t m = std::min<size_t>(q2.size(), 32), base = q2.size() - m;
+        for (size_t l = 0; l < m; l++) ready.push_back(q2[base + l]);
+        q2.resize(base);
+      } else if (q1.size() >= 32 || (last && !q1.empty())) {
+        size_t m = std::min<size_t>(q1.size(), 32), base = q1.size() - m;
+        std::vector<E2> parked;
+        for (size_t l = 0; l < m; l++) {
+          E2 o;
+          o.idx = q1[base + l].idx;
+          if (person_r::stage_b1<Env>(K, q1[base + l].p, &o.p)) ready.push_back(o);
+          else parked.push_back(o);
+        }
+        q1.resize(base);
+        q2.insert(q2.end(), parked.begin(), parked.end());
+      } else if (!last) {
         for (int lane = 0; lane < 32; lane++) {
           int64_t i = tile * 32 + lane;
           if (i < sh->n) {
             env.src.g = sub[lane];
             E1 e;
-            e.idx = i;
-            if (!person_r::stage_a(env, K, sh->first_person + i, &e.p)) q1.push_back(e);
+            E2 r;
+            e.idx = r.idx = i;
+            if (person_r::stage_a(env, &e.p, &r.p)) ready.push_back(r);
+            else q1.push_back(e);
           }
           sub[lane].jump(st.stride);
         }
         tile += GW;
-      }
-      const bool last = tile >= n_tiles;
-      if (q1.size() >= 32 || (last && !q1.empty())) {
-        size_t m = std::min<size_t>(q1.size(), 32), base = q1.size() - m;
-        for (size_t l = 0; l < m; l++) {
-          E2 o;
-          o.idx = q1[base + l].idx;
-          if (!person_r::stage_b1(env, K, sh->first_person + o.idx, q1[base + l].p, &o.p)) q2.push_back(o);
-        }
-        q1.resize(base);
-      }
-      if (q2.size() >= 32 || (last && q1.empty() && !q2.empty())) {
-        size_t m = std::min<size_t>(q2.size(), 32), base = q2.size() - m;
-        for (size_t l = 0; l < m; l++) person_r::stage_b2(env, K, sh->first_person + q2[base + l].idx, q2[base + l].p, &err);
-        q2.resize(base);
+      } else {
+        break;
       }
       if (q1.size() >= 64 || q2.size() >= 64) return -99;  // the kernel's queues hold 64
-      if (last && q1.empty() && q2.empty()) break;
+      for (size_t l = 0; l < ready.size(); l++) person_r::run_life(env, K, sh->first_person + ready[l].idx, ready[l].p, &err);
     }
   }
   if (err) return err;
