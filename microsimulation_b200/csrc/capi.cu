@@ -37,7 +37,7 @@ struct Ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
   MrgJump *d_lo = nullptr, *d_hi = nullptr;
   DevBuf rowlog, prov_start, prov_end, prov_meta, tile_count, partial, dense, small, mt_words, len, starts, chain_exit, chain_count, chain_entry, chain_base, calib_out,
-      calib_par, uniforms, first_end, first_tag, row_off, ov_idx, ov_tag, ov_start, ov_end, aux, code_in, code_out, sgeom,
+      calib_par, uniforms, first_end, first_tag, ov_fill, ov_tag, ov_start, ov_end, aux, code_in, code_out, sgeom,
       indiv, gsm_model, gsm_data, gsm_in, gsm_out, slices;
   int person_kernel = 0;  // 0 = staged schedule (person_staged.cuh), 1 = generic cohort kernel
   bool last_staged = false;
@@ -359,25 +359,24 @@ int reexpand(int64_t rows) {
 
 // ---- person-r
 
-// the two bandwidth-bound passes that turn first rows + overflow rows into the final columns
+// the bandwidth-bound passes that turn first rows + further rows into the final columns
 int staged_rowpasses(int64_t n, int64_t first_person, int64_t capacity, bool count_first) {
   RowPassParams r;
   memset(&r, 0, sizeof r);
   SmallView sv = small_view();
   r.first_end = (const double *)g.first_end.p;
   r.first_tag = (const unsigned short *)g.first_tag.p;
-  r.ov_idx = (const unsigned *)g.ov_idx.p;
   r.ov_tag = (const unsigned *)g.ov_tag.p;
   r.ov_start = (const double *)g.ov_start.p;
   r.ov_end = (const double *)g.ov_end.p;
-  r.ov_count = sv.ov_count;
-  r.ov_cap = g.last_ov_cap;
+  r.ov_fill = (const unsigned *)g.ov_fill.p;
+  r.max_fill = sv.ov_count;
+  r.ov_cap = (int)g.last_ov_cap;
   r.n = n;
   r.first_person = first_person;
   r.chunk_rows = (unsigned long long *)g.partial.p;
   r.n_rows = sv.n_rows;
   r.n_chunks = (n + ROW_CHUNK - 1) / ROW_CHUNK;
-  r.row_off = (unsigned *)g.row_off.p;
   r.rowlog = (double *)g.rowlog.p;
   r.capacity = capacity;
   if (r.n_chunks == 0) return MSIM_OK;
@@ -388,11 +387,9 @@ int staged_rowpasses(int64_t n, int64_t first_person, int64_t capacity, bool cou
     CK(cudaGetLastError());
     g.launches += 2;
   }
-  rowpass_first_kernel<<<(unsigned)r.n_chunks, 256, 0, g.stream>>>(r);
+  rowpass_final_kernel<<<(unsigned)r.n_chunks, 256, 0, g.stream>>>(r);
   CK(cudaGetLastError());
-  rowpass_scatter_kernel<<<g.sm_count * 8, 256, 0, g.stream>>>(r);
-  CK(cudaGetLastError());
-  g.launches += 2;
+  g.launches++;
   return MSIM_OK;
 }
 
@@ -435,33 +432,32 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
   int64_t ov_cap = 0;
   if (p.outputs & OUT_ROWLOG) {
     const size_t n1 = (size_t)std::max<int64_t>(sh->n, 1);
-    // rows beyond a person's first: 0.232 per person at the reference's parameters; at most 4
+    // rows beyond a person's first: 0.232 per person at the reference's parameters, at most 4; each chunk of
+    // ROW_CHUNK persons owns a region planned with a wide margin (a chunk that needs more repeats the run)
+    const int64_t n_chunks = (sh->n + ROW_CHUNK - 1) / ROW_CHUNK;
     ov_cap = ov_cap_override > 0 ? ov_cap_override
-                                 : std::min<int64_t>((int64_t)(g.plan_extra_rows * (double)sh->n) + (g.plan_extra_rows >= 0.2 ? 65536 : 16), sh->n * (person_r::MAX_ROWS - 1) + 1);
+                                 : std::min<int64_t>((int64_t)(g.plan_extra_rows * 1.6 * ROW_CHUNK) + (g.plan_extra_rows >= 0.2 ? 96 : 1),
+                                                     (int64_t)ROW_CHUNK * (person_r::MAX_ROWS - 1));
+    const size_t ov_n = (size_t)std::max<int64_t>(n_chunks, 1) * (size_t)ov_cap;
     if ((rc = ensure(g.first_end, sizeof(double) * n1))) return rc;
     if ((rc = ensure(g.first_tag, sizeof(unsigned short) * n1))) return rc;
-    if ((rc = ensure(g.row_off, sizeof(unsigned) * n1))) return rc;
-    if ((rc = ensure(g.ov_idx, sizeof(unsigned) * (size_t)ov_cap))) return rc;
-    if ((rc = ensure(g.ov_tag, sizeof(unsigned) * (size_t)ov_cap))) return rc;
-    if ((rc = ensure(g.ov_start, sizeof(double) * (size_t)ov_cap))) return rc;
-    if ((rc = ensure(g.ov_end, sizeof(double) * (size_t)ov_cap))) return rc;
+    if ((rc = ensure(g.ov_fill, sizeof(unsigned) * (size_t)std::max<int64_t>(n_chunks, 1)))) return rc;
+    if ((rc = ensure(g.ov_tag, sizeof(unsigned) * ov_n))) return rc;
+    if ((rc = ensure(g.ov_start, sizeof(double) * ov_n))) return rc;
+    if ((rc = ensure(g.ov_end, sizeof(double) * ov_n))) return rc;
+    CK(cudaMemsetAsync(g.ov_fill.p, 0, sizeof(unsigned) * (size_t)std::max<int64_t>(n_chunks, 1), g.stream));
     if ((rc = ensure(g.partial, sizeof(unsigned long long) * (size_t)((sh->n + ROW_CHUNK - 1) / ROW_CHUNK + 1)))) return rc;
     if ((rc = ensure(g.rowlog, sizeof(double) * 5 * (size_t)std::max<int64_t>(capacity, 1)))) return rc;
     p.first_end = (double *)g.first_end.p;
     p.first_tag = (unsigned short *)g.first_tag.p;
-    p.ov_idx = (unsigned *)g.ov_idx.p;
     p.ov_tag = (unsigned *)g.ov_tag.p;
     p.ov_start = (double *)g.ov_start.p;
     p.ov_end = (double *)g.ov_end.p;
-    p.ov_count = sv.ov_count;
-    p.ov_cap = ov_cap;
+    p.ov_fill = (unsigned *)g.ov_fill.p;
+    p.ov_cap = (int)ov_cap;
   }
   g.last_ov_cap = ov_cap;
-#ifdef MSIM_EXP_GLOBAL_COUNTERS
-  const int slice = p.geom.total;
-#else
   const int slice = p.geom.off_dstart;  // the FP sums (pt, ut)
-#endif
   if (p.outputs & OUT_REPORT) {
     const size_t bytes = sizeof(double) * (size_t)grid * slice;
     if ((rc = ensure(g.slices, bytes))) return rc;
@@ -913,7 +909,7 @@ void msim_shutdown(void) {
   cudaStreamSynchronize(g.stream);
   DevBuf *bufs[] = {&g.rowlog, &g.prov_start, &g.prov_end, &g.prov_meta, &g.tile_count, &g.partial, &g.dense, &g.small, &g.mt_words, &g.len, &g.starts, &g.chain_exit,
                     &g.chain_count, &g.chain_entry, &g.chain_base, &g.calib_out, &g.calib_par, &g.uniforms,
-                    &g.first_end, &g.first_tag, &g.row_off, &g.ov_idx, &g.ov_tag, &g.ov_start, &g.ov_end,
+                    &g.first_end, &g.first_tag, &g.ov_fill, &g.ov_tag, &g.ov_start, &g.ov_end,
                     &g.aux, &g.code_in, &g.code_out, &g.sgeom, &g.indiv, &g.gsm_model, &g.gsm_data, &g.gsm_in, &g.gsm_out, &g.slices};
   for (DevBuf *b : bufs) {
     if (b->p) cudaFree(b->p);

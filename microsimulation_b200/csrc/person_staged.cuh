@@ -27,10 +27,11 @@
 // Row log.  Rows must come out in person order but persons now finish out of
 // order, so the simulation writes, per person, its FIRST row (end time + a
 // 16-bit tag: kind, state, number of further rows) to arrays indexed by person,
-// and appends the further rows (0.23 per person) to an unordered overflow list
-// tagged with (person, row number).  Two bandwidth-bound passes turn that into
-// the final five f64 columns: a scan of the per-person row counts that writes
-// the first rows, and a scatter of the overflow rows.
+// and appends the further rows (0.23 per person) to a small overflow region
+// owned by the person's chunk of ROW_CHUNK consecutive persons, tagged with
+// (person, row number).  A bandwidth-bound pass per chunk then merges both in
+// shared memory and streams the final five f64 columns out fully coalesced
+// (reads 10 B per person + 20 B per further row, writes 40 B per row).
 #pragma once
 #include "models.cuh"
 #include "report.cuh"
@@ -108,7 +109,8 @@ constexpr int SBLOCK = MSIM_SBLOCK;  // threads per block of the staged kernel
 constexpr int SWARPS = SBLOCK / 32;
 constexpr int QCAP = 64;        // a queue holds < 32 entries between pushes, < 64 after one
 constexpr int XROWS = 4;        // rows a person may log beyond its first (person_r::MAX_ROWS - 1)
-constexpr int ROW_CHUNK = 8192;  // persons per block of the row-log passes
+constexpr int ROW_CHUNK = 1024;  // persons per block of the row-log passes
+constexpr int ROW_WINDOW = 2048;  // rows a block of the final pass stages at a time (a chunk holds 1262 on average)
 
 struct alignas(16) WarpQueues {
   uint32_t q1_s[6][QCAP];
@@ -136,20 +138,23 @@ struct StagedParams {
   // row log, first pass
   double *first_end;           // [n] end time of each person's first row
   unsigned short *first_tag;   // [n] kind | state << 4 | (rows - 1) << 8
-  unsigned *ov_idx, *ov_tag;   // overflow rows: person index; row number << 16 | state << 8 | kind
+  // further rows: chunk c owns entries [c*ov_cap, (c+1)*ov_cap); tag = person-in-chunk << 16 | row << 12 | state << 8 | kind
+  unsigned *ov_tag;
   double *ov_start, *ov_end;
-  unsigned long long *ov_count;
-  int64_t ov_cap;
+  unsigned *ov_fill;           // [chunks] entries appended to each chunk's region (may exceed ov_cap: then the run is repeated)
+  int ov_cap;
 };
 
 // Report accumulators of a block.  Counters: a shared-memory table, native
 // 32-bit atomics, flushed once per block with red.global.add.f64.  FP sums
-// (pt, ut) outside the per-warp hot tables: red.global.add.f64 into a slice of
-// global memory that only THIS block writes (fire and forget, no return value
-// to wait for; shared memory has no native f64 add on sm_100a — atomicAdd there
-// is a compare-and-swap loop that cost 2.7 ms per 1e8 persons).  A fold kernel
-// sums the slices afterwards.  (All blocks accumulating into ONE global vector
-// was measured at 38 ms per 1e8 persons: a few hundred hot cells serialise in
+// (pt, ut): red.global.add.f64 into a slice of global memory that only THIS
+// block writes — fire and forget, no return value to wait for.  Shared memory
+// has no native f64 add on sm_100a (atomicAdd there is a compare-and-swap
+// loop: 2.7 ms per 1e8 persons for the 19% of intervals that are not a
+// person's first; per-warp private tables with plain load/add/store for the
+// first intervals were also slower than the REDs).  A fold kernel sums the
+// slices afterwards, in a fixed order.  (All blocks accumulating into ONE
+// global vector: 38 ms per 1e8 persons, a few hundred hot cells serialise in
 // L2.)
 struct StagedAcc {
   double *f;
@@ -161,11 +166,8 @@ struct StagedAcc {
   int pend_idx;
   int pend_n;
   __device__ __forceinline__ void addf(int idx, double v) { atomicAdd(&f[idx], v); }  // f: this block's global slice
-#ifdef MSIM_EXP_GLOBAL_COUNTERS  // experiment: counters, too, as f64 REDs into the block's global slice
-  __device__ __forceinline__ void addi(int idx, int v) { atomicAdd(&f[idx], (double)v); }
-#else
+  // (counters as REDs into the global slice as well were measured 2% slower than these shared-memory atomics)
   __device__ __forceinline__ void addi(int idx, int v) { atomicAdd(&i[idx - n_f], v); }
-#endif
   __device__ __forceinline__ void addc(int idx) {
     if (idx == pend_idx) {
       pend_n++;
@@ -216,7 +218,7 @@ struct StagedEnv {
       } else if (nrows <= XROWS) {
         wq->x_start[nrows - 1][lane] = start;
         wq->x_end[nrows - 1][lane] = end;
-        wq->x_meta[nrows - 1][lane] = ((unsigned)nrows << 16) | ((unsigned)state << 8) | (unsigned)kind;
+        wq->x_meta[nrows - 1][lane] = ((unsigned)nrows << 12) | ((unsigned)state << 8) | (unsigned)kind;
       }
       nrows++;
     }
@@ -236,27 +238,18 @@ __device__ __forceinline__ void staged_finish(const StagedParams &p, StagedEnv &
   }
 }
 
-// the warp appends its lanes' staged extra rows to the overflow list
+// a lane appends its person's further rows to the region of the person's chunk
 __device__ __forceinline__ void staged_append_extra(const StagedParams &p, StagedEnv &env, bool active, uint32_t idx, int lane) {
   const int cnt = active ? (env.nrows > XROWS + 1 ? XROWS : (env.nrows > 1 ? env.nrows - 1 : 0)) : 0;
-  int incl = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  const int tot = __shfl_sync(0xffffffffu, incl, 31);
-  if (tot == 0) return;
-  unsigned long long base = 0;
-  if (lane == 0) base = atomicAdd(p.ov_count, (unsigned long long)tot);
-  base = __shfl_sync(0xffffffffu, base, 0);
-  const unsigned long long at = base + (unsigned)(incl - cnt);
+  if (cnt == 0) return;
+  const unsigned chunk = idx / ROW_CHUNK, local = idx % ROW_CHUNK;
+  const unsigned at = atomicAdd(&p.ov_fill[chunk], (unsigned)cnt);
   for (int r = 0; r < cnt; r++) {
-    if (at + r < (unsigned long long)p.ov_cap) {
-      p.ov_idx[at + r] = idx;
-      p.ov_tag[at + r] = env.wq->x_meta[r][lane];
-      p.ov_start[at + r] = env.wq->x_start[r][lane];
-      p.ov_end[at + r] = env.wq->x_end[r][lane];
+    if (at + r < (unsigned)p.ov_cap) {
+      const size_t e = (size_t)chunk * p.ov_cap + at + r;
+      p.ov_tag[e] = (local << 16) | env.wq->x_meta[r][lane];
+      p.ov_start[e] = env.wq->x_start[r][lane];
+      p.ov_end[e] = env.wq->x_end[r][lane];
     }
   }
 }
@@ -271,11 +264,7 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
   const int total = (p.outputs & 2u) ? p.geom.total : 0;
   const int n_f = (p.outputs & 2u) ? p.geom.off_dstart : 0;
   int *s_i = reinterpret_cast<int *>(sp);
-#ifdef MSIM_EXP_GLOBAL_COUNTERS
-  double *g_f = p.slices + (size_t)blockIdx.x * p.geom.total;
-#else
   double *g_f = p.slices + (size_t)blockIdx.x * n_f;  // this block's slice of the FP sums
-#endif
   __shared__ unsigned s_kind[8];
   __shared__ double s_sum[SWARPS];
   // the report geometry in shared memory: its tables are indexed per lane (a constant-bank load with a
@@ -443,22 +432,22 @@ __global__ void __launch_bounds__(256) fold_slices_kernel(const double *slices, 
 struct RowPassParams {
   const double *first_end;
   const unsigned short *first_tag;
-  const unsigned *ov_idx, *ov_tag;
+  const unsigned *ov_tag;
   const double *ov_start, *ov_end;
-  const unsigned long long *ov_count;
-  int64_t ov_cap;
+  const unsigned *ov_fill;
+  int ov_cap;
   int64_t n, first_person;
   unsigned long long *chunk_rows;  // per-chunk totals, then (in place) exclusive offsets
   unsigned long long *n_rows;
+  unsigned long long *max_fill;    // largest ov_fill seen (tells the host whether ov_cap was enough)
   int64_t n_chunks;
-  unsigned *row_off;  // [n] a person's first row, relative to its chunk
-  double *rowlog;     // 5 columns (endTime, event, id, startTime, state), column stride `capacity`
+  double *rowlog;  // 5 columns (endTime, event, id, startTime, state), column stride `capacity`
   int64_t capacity;
 };
 
 __device__ __forceinline__ int tag_rows(unsigned short t) { return (t & 0x8000u) ? 1 + ((t >> 8) & 7) : 0; }
 
-// rows per chunk of ROW_CHUNK persons
+// rows per chunk of ROW_CHUNK persons; largest overflow fill
 __global__ void __launch_bounds__(256) rowpass_count_kernel(RowPassParams p) {
   __shared__ unsigned s_w[8];
   const int64_t lo = (int64_t)blockIdx.x * ROW_CHUNK;
@@ -475,6 +464,7 @@ __global__ void __launch_bounds__(256) rowpass_count_kernel(RowPassParams p) {
     unsigned long long t = 0;
     for (int w = 0; w < 8; w++) t += s_w[w];
     p.chunk_rows[blockIdx.x] = t;
+    atomicMax(p.max_fill, (unsigned long long)p.ov_fill[blockIdx.x]);
   }
 }
 
@@ -506,65 +496,83 @@ __global__ void __launch_bounds__(1024) rowpass_scan_kernel(RowPassParams p) {
   if (tid == 0) *p.n_rows = s_carry;
 }
 
-// first rows -> final columns; every person's row offset within its chunk
-__global__ void __launch_bounds__(256) rowpass_first_kernel(RowPassParams p) {
+// One block per chunk: every person's row offset by a block scan of the row counts, first rows and further
+// rows placed in shared memory in final order, then streamed out (all global accesses coalesced).
+__global__ void __launch_bounds__(256) rowpass_final_kernel(RowPassParams p) {
+  __shared__ unsigned short s_tag[ROW_CHUNK];
+  __shared__ unsigned short s_off[ROW_CHUNK];
+  __shared__ double s_end[ROW_WINDOW], s_start[ROW_WINDOW];
+  __shared__ unsigned s_meta[ROW_WINDOW];
   __shared__ unsigned s_w[8];
-  __shared__ unsigned s_run;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t lo = (int64_t)blockIdx.x * ROW_CHUNK;
-  const unsigned long long base = p.chunk_rows[blockIdx.x];
-  if (tid == 0) s_run = 0;
-  __syncthreads();
-  for (int k0 = 0; k0 < ROW_CHUNK; k0 += 256) {
-    const int64_t i = lo + k0 + tid;
-    unsigned short tag = 0;
-    double end = 0.0;
-    if (i < p.n) {
-      tag = p.first_tag[i];
-      end = p.first_end[i];
-    }
-    const unsigned cnt = tag_rows(tag);
-    unsigned incl = cnt;
+  const int64_t c = blockIdx.x, lo = c * ROW_CHUNK;
+  constexpr int PER = ROW_CHUNK / 256;
+  // ---- row offsets: thread t owns persons [PER*t, PER*t + PER)
+  unsigned cnt[PER], v = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
+  for (int k = 0; k < PER; k++) {
+    const int64_t i = lo + tid * PER + k;
+    const unsigned short tag = (i < p.n) ? p.first_tag[i] : (unsigned short)0;
+    s_tag[tid * PER + k] = tag;
+    cnt[k] = tag_rows(tag);
+    v += cnt[k];
+  }
+  unsigned incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  unsigned run = incl - v, total = 0;
+  for (int w = 0; w < 8; w++) {
+    if (w < warp) run += s_w[w];
+    total += s_w[w];
+  }
+#pragma unroll
+  for (int k = 0; k < PER; k++) {
+    s_off[tid * PER + k] = (unsigned short)run;
+    run += cnt[k];
+  }
+  __syncthreads();
+  const unsigned long long base = p.chunk_rows[c];
+  unsigned m = p.ov_fill[c];
+  if (m > (unsigned)p.ov_cap) m = (unsigned)p.ov_cap;
+  const size_t ov0 = (size_t)c * p.ov_cap;
+  for (unsigned w0 = 0; w0 < total; w0 += ROW_WINDOW) {
+    for (int i = tid; i < ROW_CHUNK; i += 256) {
+      const unsigned short tag = s_tag[i];
+      const unsigned o = (unsigned)s_off[i] - w0;
+      if ((tag & 0x8000u) && o < (unsigned)ROW_WINDOW) {  // (unsigned wrap-around rejects rows before the window)
+        s_end[o] = p.first_end[lo + i];
+        s_start[o] = 0.0;  // a person's first interval starts at startTime = 0 (microsimulation.h:430)
+        s_meta[o] = ((unsigned)i << 16) | (((unsigned)tag >> 4) & 0xfu) << 8 | ((unsigned)tag & 0xfu);
+      }
     }
-    if (lane == 31) s_w[warp] = incl;
-    __syncthreads();
-    unsigned off = s_run + incl - cnt;
-    for (int w = 0; w < warp; w++) off += s_w[w];
-    if (i < p.n) {
-      p.row_off[i] = off;
-      const unsigned long long g = base + off;
-      if (cnt && g < (unsigned long long)p.capacity) {
-        p.rowlog[0 * p.capacity + g] = end;
-        p.rowlog[1 * p.capacity + g] = (double)(tag & 0xf);
-        p.rowlog[2 * p.capacity + g] = (double)(p.first_person + i);
-        p.rowlog[3 * p.capacity + g] = 0.0;  // a person's first interval starts at startTime = 0 (microsimulation.h:430)
-        p.rowlog[4 * p.capacity + g] = (double)((tag >> 4) & 0xf);
+    for (unsigned e = tid; e < m; e += 256) {
+      const unsigned tag = p.ov_tag[ov0 + e];
+      const unsigned o = (unsigned)s_off[tag >> 16] + ((tag >> 12) & 0xfu) - w0;
+      if (o < (unsigned)ROW_WINDOW) {
+        s_end[o] = p.ov_end[ov0 + e];
+        s_start[o] = p.ov_start[ov0 + e];
+        s_meta[o] = (tag & 0xffff0000u) | (tag & 0xfffu);
       }
     }
     __syncthreads();
-    if (tid == 255) s_run = off + cnt;
-    __syncthreads();
-  }
-}
-
-// overflow rows -> their place behind their person's first row
-__global__ void __launch_bounds__(256) rowpass_scatter_kernel(RowPassParams p) {
-  unsigned long long m = *p.ov_count;
-  if (m > (unsigned long long)p.ov_cap) m = (unsigned long long)p.ov_cap;
-  for (unsigned long long e = (unsigned long long)blockIdx.x * 256 + threadIdx.x; e < m; e += (unsigned long long)gridDim.x * 256) {
-    const unsigned idx = p.ov_idx[e], tag = p.ov_tag[e];
-    const unsigned long long g = p.chunk_rows[idx / ROW_CHUNK] + p.row_off[idx] + (tag >> 16);
-    if (g < (unsigned long long)p.capacity) {
-      p.rowlog[0 * p.capacity + g] = p.ov_end[e];
-      p.rowlog[1 * p.capacity + g] = (double)(tag & 0xff);
-      p.rowlog[2 * p.capacity + g] = (double)(p.first_person + idx);
-      p.rowlog[3 * p.capacity + g] = p.ov_start[e];
-      p.rowlog[4 * p.capacity + g] = (double)((tag >> 8) & 0xff);
+    const unsigned nw = (total - w0 < (unsigned)ROW_WINDOW) ? total - w0 : (unsigned)ROW_WINDOW;
+    for (unsigned r = tid; r < nw; r += 256) {
+      const unsigned long long g = base + w0 + r;
+      if (g < (unsigned long long)p.capacity) {
+        const unsigned mt = s_meta[r];
+        p.rowlog[0 * p.capacity + g] = s_end[r];
+        p.rowlog[1 * p.capacity + g] = (double)(mt & 0xffu);
+        p.rowlog[2 * p.capacity + g] = (double)(p.first_person + lo + (mt >> 16));
+        p.rowlog[3 * p.capacity + g] = s_start[r];
+        p.rowlog[4 * p.capacity + g] = (double)((mt >> 8) & 0xfu);
+      }
     }
+    __syncthreads();
   }
 }
 
