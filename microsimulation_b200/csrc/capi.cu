@@ -409,8 +409,14 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
     smem += (size_t)(p.geom.total - p.geom.off_dstart) * 4;  // the counters; FP sums go to per-block global slices
   }
   int per_sm = 0;
-  CK(cudaFuncSetAttribute(person_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, person_staged_kernel, SBLOCK, smem));
+  typedef void (*StagedKernel)(const StagedParams);
+  // kernels specialised for the output combinations without a report; the general one with (person_staged.cuh)
+  static const StagedKernel kernels[8] = {person_staged_kernel<0>, person_staged_kernel<1>, person_staged_kernel<OUT_RUNTIME>,
+                                          person_staged_kernel<OUT_RUNTIME>, person_staged_kernel<4>, person_staged_kernel<5>,
+                                          person_staged_kernel<OUT_RUNTIME>, person_staged_kernel<OUT_RUNTIME>};
+  const StagedKernel kernel = kernels[p.outputs & 7u];
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SBLOCK, smem));
   if (per_sm < 1) return fail(MSIM_ERR_CUDA, "staged kernel does not fit on an SM");
   const int64_t tiles = (sh->n + 31) / 32;
   int64_t gmax = (int64_t)per_sm * g.sm_count;
@@ -466,7 +472,7 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
   }
   CK(cudaEventRecord(g.ev0, g.stream));
   if (p.n > 0) {
-    person_staged_kernel<<<grid, SBLOCK, smem, g.stream>>>(p);
+    kernel<<<grid, SBLOCK, smem, g.stream>>>(p);
     CK(cudaGetLastError());
     g.launches++;
     if (p.outputs & OUT_REPORT) {

@@ -156,6 +156,13 @@ struct StagedParams {
 // slices afterwards, in a fixed order.  (All blocks accumulating into ONE
 // global vector: 38 ms per 1e8 persons, a few hundred hot cells serialise in
 // L2.)
+// red.shared.add.s32: one instruction, no return value.  (Written in PTX because the compiler turns some
+// atomicAdd calls on shared memory into a loop that groups the lanes by address first — up to 32 passes when the
+// addresses differ, as they do here — which made the report kernel 50% slower.)
+__device__ __forceinline__ void red_shared_add(int *ptr, int v) {
+  asm volatile("red.shared.add.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(ptr)), "r"(v) : "memory");
+}
+
 struct StagedAcc {
   double *f;
   int *i;
@@ -167,7 +174,7 @@ struct StagedAcc {
   int pend_n;
   __device__ __forceinline__ void addf(int idx, double v) { atomicAdd(&f[idx], v); }  // f: this block's global slice
   // (counters as REDs into the global slice as well were measured 2% slower than these shared-memory atomics)
-  __device__ __forceinline__ void addi(int idx, int v) { atomicAdd(&i[idx - n_f], v); }
+  __device__ __forceinline__ void addi(int idx, int v) { red_shared_add(&i[idx - n_f], v); }
   __device__ __forceinline__ void addc(int idx) {
     if (idx == pend_idx) {
       pend_n++;
@@ -184,11 +191,19 @@ struct StagedAcc {
   }
 };
 
-struct StagedEnv {
+// OUT = the MSIM_OUT_* combination when it is known at compile time (each such combination is its own kernel),
+// or OUT_RUNTIME: read from the parameters.  Which is faster is a matter of what the compiler makes of it
+// (measured on 1e8 persons): without a report the specialised kernels win (counts 3.97 vs 4.30 ms, row log 5.92
+// vs 6.15 ms); with one the general kernel does (6.2 vs 9.6 ms — the specialised one runs the substream jump and
+// the draws in fragments of a few lanes).
+constexpr unsigned OUT_RUNTIME = 0xffu;
+template <unsigned OUT>
+struct StagedEnvT {
   typedef MrgSource Src;
   Src src;
-  unsigned outputs;
-  const ReportGeom *geom;
+  unsigned outputs_rt;
+  __device__ __forceinline__ unsigned out() const { return OUT == OUT_RUNTIME ? outputs_rt : OUT; }
+  const ReportGeom *geom;  // in shared memory
   StagedAcc acc;
   ReportCursor cursor;
   // per-kind tallies: eight 16-bit fields in two words (each kind occurs at most once per person)
@@ -205,13 +220,13 @@ struct StagedEnv {
     nrows = 0;
   }
   __device__ __forceinline__ void row(double, double start, double end, int state, int kind) {
-    if (outputs & 4u) {
+    if (out() & 4u) {
       const unsigned long long inc = 1ull << ((kind & 3) * 16);
       if (kind < 4) kinds_lo += inc;
       else kinds_hi += inc;
       sum_end += end;
     }
-    if (outputs & 1u) {
+    if (out() & 1u) {
       if (nrows == 0) {
         first_end = end;
         first_tag = (unsigned)kind | ((unsigned)state << 4);
@@ -224,13 +239,14 @@ struct StagedEnv {
     }
   }
   __device__ __forceinline__ void report(int state, int kind, double lhs, double rhs) {
-    if (outputs & 2u) report_add(*geom, acc, cursor, state, kind, lhs, rhs);
+    if (out() & 2u) report_add(*geom, acc, cursor, state, kind, lhs, rhs);
   }
 };
 
 // a finished person's first row and row count (rows beyond the first stay staged until the warp appends them)
+template <class StagedEnv>
 __device__ __forceinline__ void staged_finish(const StagedParams &p, StagedEnv &env, uint32_t idx, int *err) {
-  if (p.outputs & 1u) {
+  if (env.out() & 1u) {
     if (env.nrows > XROWS + 1) *err = -4;
     const int extra = env.nrows > 0 ? (env.nrows > XROWS + 1 ? XROWS : env.nrows - 1) : 0;
     p.first_end[idx] = env.first_end;
@@ -239,6 +255,7 @@ __device__ __forceinline__ void staged_finish(const StagedParams &p, StagedEnv &
 }
 
 // a lane appends its person's further rows to the region of the person's chunk
+template <class StagedEnv>
 __device__ __forceinline__ void staged_append_extra(const StagedParams &p, StagedEnv &env, bool active, uint32_t idx, int lane) {
   const int cnt = active ? (env.nrows > XROWS + 1 ? XROWS : (env.nrows > 1 ? env.nrows - 1 : 0)) : 0;
   if (cnt == 0) return;
@@ -254,15 +271,18 @@ __device__ __forceinline__ void staged_append_extra(const StagedParams &p, Stage
   }
 }
 
+template <unsigned OUT>
 __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const __grid_constant__ StagedParams p) {
+  typedef StagedEnvT<OUT> StagedEnv;
+  const unsigned outs = (OUT == OUT_RUNTIME) ? p.outputs : OUT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // shared layout: [per-warp queues | per-warp row staging (row log) | report counters]
   WarpQueues *queues = reinterpret_cast<WarpQueues *>(smem_raw);
   unsigned char *sp = smem_raw + sizeof(WarpQueues) * SWARPS;
   WarpRows *rows_stage = reinterpret_cast<WarpRows *>(sp);
-  if (p.outputs & 1u) sp += sizeof(WarpRows) * SWARPS;
-  const int total = (p.outputs & 2u) ? p.geom.total : 0;
-  const int n_f = (p.outputs & 2u) ? p.geom.off_dstart : 0;
+  if (outs & 1u) sp += sizeof(WarpRows) * SWARPS;
+  const int total = (outs & 2u) ? p.geom.total : 0;
+  const int n_f = (outs & 2u) ? p.geom.off_dstart : 0;
   int *s_i = reinterpret_cast<int *>(sp);
   double *g_f = p.slices + (size_t)blockIdx.x * n_f;  // this block's slice of the FP sums
   __shared__ unsigned s_kind[8];
@@ -282,13 +302,14 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
   __syncthreads();
 
   StagedEnv env;
-  env.outputs = p.outputs;
+  env.outputs_rt = p.outputs;
   env.geom = &s_geom;
   env.acc.f = g_f;
   env.acc.i = s_i;
   env.acc.n_f = n_f;
   env.acc.pend_idx = -1;
   env.acc.pend_n = 0;
+  env.cursor.valid = false;
   env.kinds_lo = env.kinds_hi = 0;
   env.sum_end = 0.0;
   env.nrows = 0;
@@ -296,7 +317,6 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
   env.first_tag = 0;
   env.wq = &rows_stage[warp];
   env.lane = lane;
-  env.cursor.valid = false;
   int err = 0;
   const person_r::Consts &K = p.consts;
 
@@ -343,6 +363,7 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
         ready = person_r::stage_b1<StagedEnv>(K, po, &life);
         park2 = !ready;
       }
+      __syncwarp();
     } else if (!last) {
       // ---- stage A: 32 new persons
       const int64_t i64 = tile * 32 + lane;
@@ -352,6 +373,7 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
         ready = person_r::stage_a(env, &po, &life);
         park1 = !ready;
       }
+      __syncwarp();  // the draws diverge (exp_rand's loops): reconverge before the 18 modular multiplications of the jump
       sub.jump(p.st.stride);
       tile += GW;
     } else {
@@ -383,13 +405,13 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
       staged_finish(p, env, idx, &err);
     }
     __syncwarp();
-    if (p.outputs & 1u) staged_append_extra(p, env, ready, idx, lane);
+    if (outs & 1u) staged_append_extra(p, env, ready, idx, lane);
     __syncwarp();
   }
 
   env.acc.flush();
   if (err) atomicCAS(&s_error, 0, err);
-  if (p.outputs & 4u) {
+  if (outs & 4u) {
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       unsigned v = (unsigned)(((k < 4 ? env.kinds_lo : env.kinds_hi) >> ((k & 3) * 16)) & 0xffffull);
@@ -407,7 +429,7 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
     const int v = s_i[k];
     if (v != 0) atomicAdd(&p.dense[n_f + k], (double)v);
   }
-  if (p.outputs & 4u) {
+  if (outs & 4u) {
     if (tid < 8 && s_kind[tid]) atomicAdd(&p.counts[tid], (double)s_kind[tid]);
     if (tid == 0) {
       double t = 0;
