@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(BLOCK, 3) cohort_kernel(const __grid_constant_
         if (env.src.overrun) err = -6;
       }
     }
+    __syncwarp();  // persons end after different numbers of events: re-form the warp before the jump and the next tile
     if constexpr (!STREAM) sub.jump(p.st.stride);
 
     if (p.outputs & OUT_ROWLOG) {
@@ -452,7 +453,10 @@ __global__ void __launch_bounds__(BLOCK) seq_len_kernel(const uint32_t *words, i
                                                         int64_t n_pos, typename Traits::Consts consts,
                                                         unsigned char *len, unsigned char *aux) {
   typedef NullEnv<StreamSource> Env;
-  for (int64_t p = (int64_t)blockIdx.x * BLOCK + threadIdx.x; p < n_pos; p += (int64_t)gridDim.x * BLOCK) {
+  for (int64_t p0 = (int64_t)blockIdx.x * BLOCK + (threadIdx.x & ~31); p0 < n_pos; p0 += (int64_t)gridDim.x * BLOCK) {
+    const int64_t p = p0 + (threadIdx.x & 31);
+    __syncwarp();  // every pass starts with the warp together
+    if (p >= n_pos) continue;
     Env env;
     env.src.w = words;
     env.src.pos = first_word + p;
@@ -626,11 +630,20 @@ __global__ void __launch_bounds__(BLOCK) calib_kernel(CalibParams p) {
 
   Mrg32k3a sub = thread_start_state(p.st, blockIdx.x * BLOCK + tid);
   const int64_t stride = (int64_t)gridDim.x * BLOCK;
-  for (int64_t idx = (int64_t)blockIdx.x * BLOCK + tid; idx < p.n; idx += stride) {
-    env.src.g = sub;
-    calib::CalibPerson<CalibEnv> person(env, par);
-    person.run();
-    if (person.error_) atomicCAS(&s_error, 0, person.error_);
+  // the trip count is the warp's (lane 0 has the smallest index), and every pass starts with the warp together:
+  // without the __syncwarp, lanes whose person ends early run on into the substream jump and the next person on
+  // their own and the warp never re-forms (6 of 32 lanes active, measured)
+  const int64_t warp_first = (int64_t)blockIdx.x * BLOCK + (tid & ~31);
+  for (int64_t base = warp_first; base < p.n; base += stride) {
+    const int64_t idx = base + lane;
+    __syncwarp();
+    if (idx < p.n) {
+      env.src.g = sub;
+      calib::CalibPerson<CalibEnv> person(env, par);
+      person.run();
+      if (person.error_) atomicCAS(&s_error, 0, person.error_);
+    }
+    __syncwarp();
     sub.jump(p.st.stride);
   }
 

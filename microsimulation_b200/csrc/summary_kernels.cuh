@@ -44,13 +44,18 @@ __global__ void __launch_bounds__(BLOCK) sick_code_kernel(SickParams p) {
   typedef NullEnv<MrgSource> Env;
   Mrg32k3a sub = thread_start_state(p.st, blockIdx.x * BLOCK + threadIdx.x);
   const int64_t stride = (int64_t)gridDim.x * BLOCK;
-  for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < p.n; i += stride) {
-    Env env;
-    env.src.g = sub;
-    sick_sicker::SickSicker<Env> person(env, p.par, 0);
-    person.run();
-    p.code_out[i] = (unsigned char)env.code;
-    if (person.error_) atomicCAS(p.error, 0, person.error_);
+  for (int64_t i0 = (int64_t)blockIdx.x * BLOCK + (threadIdx.x & ~31); i0 < p.n; i0 += stride) {
+    const int64_t i = i0 + (threadIdx.x & 31);
+    __syncwarp();  // every pass starts with the warp together (kernels.cuh, calib_kernel)
+    if (i < p.n) {
+      Env env;
+      env.src.g = sub;
+      sick_sicker::SickSicker<Env> person(env, p.par, 0);
+      person.run();
+      p.code_out[i] = (unsigned char)env.code;
+      if (person.error_) atomicCAS(p.error, 0, person.error_);
+    }
+    __syncwarp();
     sub.jump(p.st.stride);
   }
 }
@@ -145,7 +150,13 @@ __global__ void __launch_bounds__(BLOCK) sick_kernel(SickParams p) {
   const int64_t stride = (int64_t)gridDim.x * BLOCK;
   int err = 0;
   double all_u = 0.0, all_c = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < p.n; i += stride) {
+  for (int64_t i0 = (int64_t)blockIdx.x * BLOCK + (threadIdx.x & ~31); i0 < p.n; i0 += stride) {
+    const int64_t i = i0 + (threadIdx.x & 31);
+    __syncwarp();  // every pass starts with the warp together (kernels.cuh, calib_kernel)
+    if (i >= p.n) {
+      if constexpr (!STREAM) sub.jump(p.st.stride);
+      continue;
+    }
     if constexpr (STREAM) {
       env.src.w = p.mt_words;
       env.src.pos = p.starts[i];
