@@ -324,6 +324,69 @@ def test_calibration_sweep_vs_oracle(msim, oracle):
                 assert np.array_equal(a[k], b[k]), k
 
 
+def test_calibration_config5_full_size_properties(msim):
+    """BASELINE config 5 (256 parameter sets x 1e6 persons): properties that need no oracle run of that size."""
+    import microsimulation_b200.api as api
+    rs = np.random.RandomState(2024)
+    base = np.array([4, 0.5, 0.05, 10, 3, 0.5])
+    pars = base * (1 + 0.2 * (2 * rs.rand(256, 6) - 1))  # each component within +-20% (SURVEY 8(d).5)
+    n = 10 ** 6
+    full = api.calibration_sweep(12345, pars, n)
+    names = ["DiseaseFree", "Precursor", "PreClinical", "Clinical"]
+    for r in full:
+        occ = sum(r.get(nm, np.zeros(10)) for nm in names)
+        assert (np.diff(occ) <= 0).all() and occ[0] <= n  # persons alive at 10, 20, ..., 100: only ever fewer
+        assert len(r["TimeAtRisk"]) == 4 and (r["TimeAtRisk"] > 0).all() and (r["TimeAtRisk"] <= 80.0 * n).all()
+    # the death time does not depend on the parameters (Gumbel from the person's 4th+ uniform): every set with
+    # sigm1 != 0 sees the same persons alive at each decade (common random numbers, R/calibSim.R:12-14)
+    alive = [sum(r.get(nm, np.zeros(10)) for nm in names) for r in full]
+    assert all(np.array_equal(a, alive[0]) for a in alive)
+    # shard additivity (the multi-GPU merge is this sum) and independence of the other sets in the launch
+    a = api.calibration_sweep(12345, pars[:3], n // 2, first_person=0)
+    b = api.calibration_sweep(12345, pars[:3], n - n // 2, first_person=n // 2)
+    for k in range(3):
+        for nm in names:
+            if nm in full[k]:
+                assert np.array_equal(a[k].get(nm, 0) + b[k].get(nm, 0), full[k][nm]), (k, nm)
+        np.testing.assert_allclose(a[k]["TimeAtRisk"] + b[k]["TimeAtRisk"], full[k]["TimeAtRisk"], rtol=1e-12)
+
+
+def test_person_config4_full_size_properties(msim, golden):
+    """BASELINE config 4 as built (n = 1e8, EventReport with 3% discounting + counts): exact properties."""
+    import microsimulation_b200.api as api
+    n, rate = 10 ** 8, 0.03
+    rep, counts = msim.person_report(12345, 0, n, rate)
+    ev = rep["events"]
+    by_kind = np.bincount(ev["event"].astype(int), weights=ev["number"], minlength=8)
+    assert np.array_equal(by_kind, counts[:8])                 # the report's events table and the per-kind tally agree
+    assert by_kind[0] + by_kind[1] == n                        # everybody ends with toDeath or toPCDeath
+    prev = rep["prev"]
+    at0 = prev["number"][(prev["Key"] == 0) & (prev["age"] == 0)]
+    assert at0.size == 1 and at0[0] == n                       # everybody is Healthy at age 0
+    pt, ut = rep["pt"], rep["ut"]
+    assert np.array_equal(pt["Key"], ut["Key"]) and np.array_equal(pt["age"], ut["age"])
+    assert (ut["utility"] <= pt["pt"] * (1 + 1e-12)).all() and (ut["utility"] > 0).all()  # discounting only shrinks
+    healthy = (pt["Key"] == 0) & (pt["age"] < 100)
+    assert (np.diff(pt["pt"][healthy]) < 0).all()              # Healthy person-time per year of age only falls
+    # four shards of 2.5e7 persons: every integer cell adds up exactly (what the all-reduce relies on)
+    tot_counts, dense, dims = np.zeros(9), None, None
+    for k in range(4):
+        res = api.person_run_device(12345, k * (n // 4), n // 4, api.MSIM_OUT_REPORT | api.MSIM_OUT_COUNTS, rate)
+        d = api.dense_fetch(res.dims.n_doubles)
+        dense, dims = (d if dense is None else dense + d), res.dims
+        tot_counts += api.person_fetch_counts()
+    merged = api.dense_to_report(dense, dims, rate)
+    assert np.array_equal(tot_counts[:8], counts[:8])
+    for tb in ("events", "prev"):
+        for k in rep[tb]:
+            assert np.array_equal(merged[tb][k], rep[tb][k]), (tb, k)
+    np.testing.assert_allclose(merged["pt"]["pt"], rep["pt"]["pt"], rtol=1e-11)
+    np.testing.assert_allclose(merged["ut"]["utility"], rep["ut"]["utility"], rtol=1e-11)
+    # prefix property: the first 1e6 persons are the n = 1e6 run pinned against the reference's own engine
+    api.person_run_device(12345, 0, 10 ** 6, api.MSIM_OUT_COUNTS)
+    assert np.array_equal(api.person_fetch_counts()[:8], golden["person_n1e6_counts"][:8])
+
+
 # ------------------------------------------------------------------ SummaryReport: Sick-Sicker (README.org:148-301)
 
 def _summary_equal(g, r, rtol=1e-9):
