@@ -1,0 +1,286 @@
+// Host side of the generic cohort kernel (kernels.cuh): launch, the row-log expand pass, result fetches, and the
+// sequential-stream pipeline (Mersenne-Twister stream -> draws per position -> chain resolution -> persons).
+#pragma once
+#include "host_runtime.h"
+
+namespace msim_host {
+using namespace msim;
+
+// ---------------------------------------------------------------- cohort launch
+
+// `small` buffer layout (8-byte cells): [9] n_rows (u64), [10] error (int), [11] end_word (i64), [12] overflow rows (u64)
+struct SmallView {
+  unsigned long long *n_rows;
+  int *error;
+  int64_t *end_word;
+  unsigned long long *ov_count;
+};
+SmallView small_view() {
+  SmallView v;
+  double *b = (double *)g.small.p;
+  v.n_rows = (unsigned long long *)(b + 9);
+  v.error = (int *)(b + 10);
+  v.end_word = (int64_t *)(b + 11);
+  v.ov_count = (unsigned long long *)(b + 12);
+  return v;
+}
+
+template <class Traits, bool STREAM>
+int cohort_grid(size_t smem, int64_t n, int *grid) {
+  auto kern = cohort_kernel<Traits, STREAM>;
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem));
+  if (per_sm < 1) return fail(MSIM_ERR_CUDA, "cohort kernel does not fit on an SM");
+  int64_t tiles = (n + BLOCK - 1) / BLOCK;
+  int64_t gmax = (int64_t)per_sm * g.sm_count;
+  if (gmax > JUMP_TAB * (int64_t)JUMP_TAB / BLOCK) gmax = JUMP_TAB * (int64_t)JUMP_TAB / BLOCK;
+  *grid = (int)std::max<int64_t>(1, std::min<int64_t>(gmax, tiles));
+  return MSIM_OK;
+}
+
+// Allocates and zeroes the accumulators a run needs and fills the pointers in p.
+template <class Traits, bool STREAM>
+int cohort_prepare(CohortParams<typename Traits::Consts> &p, const uint32_t stream_state[6], int *grid_out,
+                   size_t *smem_out) {
+  int rc;
+  size_t smem = cohort_kernel_smem<Traits>(p.geom, p.outputs);
+  int grid = 1;
+  if ((rc = cohort_grid<Traits, STREAM>(smem, p.n, &grid))) return rc;
+  if (!STREAM) stream_start(stream_state, p.first_person, (int64_t)grid * BLOCK, &p.st);
+  if ((rc = ensure(g.small, 16 * sizeof(double)))) return rc;
+  CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
+  SmallView sv = small_view();
+  p.error = sv.error;
+  // one accumulator vector: the dense report cells (if requested) followed by the N_COUNTS count cells,
+  // so that a single all-reduce merges everything a shard produces
+  const int cells = (p.outputs & OUT_REPORT) ? p.geom.total : 0;
+  if ((rc = ensure(g.dense, sizeof(double) * (cells + N_COUNTS)))) return rc;
+  CK(cudaMemsetAsync(g.dense.p, 0, sizeof(double) * (cells + N_COUNTS), g.stream));
+  p.dense = (double *)g.dense.p;
+  p.counts = p.dense + cells;
+  g.last_cells = cells;
+  if (p.outputs & OUT_ROWLOG) {
+    const int64_t wtiles = std::max<int64_t>((p.n + 31) / 32, 1);
+    const size_t slots = (size_t)wtiles * 32 * Traits::MAX_ROWS;
+    if ((rc = ensure(g.prov_start, sizeof(double) * slots))) return rc;
+    if ((rc = ensure(g.prov_end, sizeof(double) * slots))) return rc;
+    if ((rc = ensure(g.prov_meta, sizeof(int) * slots))) return rc;
+    // the kernel's last block tile may be partial: its idle warps still store a 0 count
+    if ((rc = ensure(g.tile_count, sizeof(int) * (size_t)(wtiles + WARPS)))) return rc;
+    if ((rc = ensure(g.partial, sizeof(unsigned long long) * (size_t)((wtiles + EXPAND_TILES - 1) / EXPAND_TILES + 1)))) return rc;
+    if ((rc = ensure(g.rowlog, sizeof(double) * 5 * (size_t)std::max<int64_t>(g.want_capacity, 1)))) return rc;
+    p.prov_start = (double *)g.prov_start.p;
+    p.prov_end = (double *)g.prov_end.p;
+    p.prov_meta = (int *)g.prov_meta.p;
+    p.tile_count = (int *)g.tile_count.p;
+  }
+  *grid_out = grid;
+  *smem_out = smem;
+  return MSIM_OK;
+}
+
+// second pass of the row log: tile counts -> offsets -> final columns
+int rowlog_expand(int64_t n, int64_t first_person, int max_rows, int64_t capacity) {
+  ExpandParams e;
+  memset(&e, 0, sizeof e);
+  e.prov_start = (const double *)g.prov_start.p;
+  e.prov_end = (const double *)g.prov_end.p;
+  e.prov_meta = (const int *)g.prov_meta.p;
+  e.tile_count = (const int *)g.tile_count.p;
+  e.n_warp_tiles = (n + 31) / 32;
+  e.tile_cap = 32 * max_rows;
+  e.partial = (unsigned long long *)g.partial.p;
+  e.n_rows = small_view().n_rows;
+  e.n_chunks = (e.n_warp_tiles + EXPAND_TILES - 1) / EXPAND_TILES;
+  e.first_person = first_person;
+  e.rowlog = (double *)g.rowlog.p;
+  e.capacity = capacity;
+  if (e.n_chunks == 0) return MSIM_OK;
+  rowlog_partial_kernel<<<(unsigned)e.n_chunks, 256, 0, g.stream>>>(e);
+  CK(cudaGetLastError());
+  rowlog_chunk_scan_kernel<<<1, 1024, 0, g.stream>>>(e);
+  CK(cudaGetLastError());
+  rowlog_expand_kernel<<<(unsigned)e.n_chunks, 256, 0, g.stream>>>(e);
+  CK(cudaGetLastError());
+  g.launches += 3;
+  return MSIM_OK;
+}
+
+template <class Traits, bool STREAM>
+int cohort_fire(CohortParams<typename Traits::Consts> &p, int grid, size_t smem, int64_t capacity) {
+  if (p.n > 0) {
+    cohort_kernel<Traits, STREAM><<<grid, BLOCK, smem, g.stream>>>(p);
+    CK(cudaGetLastError());
+    g.launches++;
+    if (p.outputs & OUT_ROWLOG) {
+      int rc = rowlog_expand(p.n, p.first_person, Traits::MAX_ROWS, capacity);
+      if (rc) return rc;
+    }
+  }
+  g.last_geom = p.geom;
+  g.last_outputs = p.outputs;
+  g.last_capacity = capacity;
+  g.last_n = p.n;
+  g.last_first = p.first_person;
+  g.last_max_rows = Traits::MAX_ROWS;
+  g.last_staged = false;
+  g.have_last = true;
+  return MSIM_OK;
+}
+
+int finish_run(int64_t *n_rows_out) {
+  CK(cudaStreamSynchronize(g.stream));
+  if (g.timing_pending) {
+    CK(cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1));
+    g.timing_pending = false;
+  }
+  double small[16];
+  CK(cudaMemcpy(small, g.small.p, sizeof small, cudaMemcpyDeviceToHost));
+  int err = *(int *)(small + 10);
+  unsigned long long nr = *(unsigned long long *)(small + 9);
+  g.last_n_rows = (int64_t)nr;
+  g.last_ov_rows = (int64_t) * (unsigned long long *)(small + 12);
+  if (n_rows_out) *n_rows_out = (int64_t)nr;
+  if (err == MSIM_ERR_HEAP) return fail(MSIM_ERR_HEAP, "a person scheduled more pending events / rows than the device capacity");
+  if (err == MSIM_ERR_STREAM) return fail(MSIM_ERR_STREAM, "a person drew more uniforms than the sequential-stream plan allows");
+  if (err) return fail(err, "device-side error");
+  return MSIM_OK;
+}
+
+int64_t rowlog_capacity_guess(int64_t n, int max_rows, double mean_rows) {
+  if (n <= 65536 && mean_rows >= 1.0) return n * max_rows + 1;
+  int64_t c = (int64_t)((double)n * mean_rows) + (mean_rows >= 1.0 ? 65536 : 16);
+  return std::min<int64_t>(c, n * max_rows + 1);
+}
+
+int fetch_rowlog(const char *const *cols, msim_table *out) {
+  int64_t n = g.last_n_rows, cap = g.last_capacity;
+  out->nrow = n;
+  out->ncol = 5;
+  out->colnames = cols;
+  out->data = nullptr;
+  int rc;
+  if ((rc = pinned_alloc(sizeof(double) * 5 * (size_t)std::max<int64_t>(n, 1), &out->data))) return rc;
+  if (n > 0) {
+    CK(cudaMemcpy2DAsync(out->data, sizeof(double) * n, g.rowlog.p, sizeof(double) * cap, sizeof(double) * n, 5,
+                         cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+  }
+  return MSIM_OK;
+}
+
+int fetch_report(msim_report *out) {
+  std::vector<double> d(g.last_geom.total);
+  CK(cudaMemcpy(d.data(), g.dense.p, sizeof(double) * d.size(), cudaMemcpyDeviceToHost));
+  dense_to_report_impl(d.data(), g.last_geom, out);
+  return MSIM_OK;
+}
+
+// the guessed row capacity was too small: the packed rows are still there, expand again
+int staged_rowpasses(int64_t n, int64_t first_person, int64_t capacity, bool count_first);  // host_person.h
+
+int reexpand(int64_t rows) {
+  int rc;
+  if ((rc = ensure(g.rowlog, sizeof(double) * 5 * (size_t)rows))) return rc;
+  if (g.last_staged) {
+    if ((rc = staged_rowpasses(g.last_n, g.last_first, rows, false))) return rc;
+  } else if ((rc = rowlog_expand(g.last_n, g.last_first, g.last_max_rows, rows))) {
+    return rc;
+  }
+  g.last_capacity = rows;
+  return finish_run(nullptr);
+}
+
+
+// ---- sequential-stream models
+
+template <class Traits>
+int sequential_run(int64_t n, const typename Traits::Consts &consts, int max_draws, unsigned outputs,
+                   const ReportGeom &geom, int max_rows, double mean_rows) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  if (n < 0) return fail(MSIM_ERR_ARG, "n < 0");
+  if (!g.rng.mt_seeded)
+    return fail(MSIM_ERR_STATE, "Mersenne-Twister state not set: call msim_mt_set_seed or msim_mt_set_state first");
+  if (max_draws > CHAIN_MAX_DRAWS) return fail(MSIM_ERR_ARG, "max_draws too large");
+  const int64_t mti0 = g.rng.mt[0];  // next word to hand out, 1..624 (624 = regenerate first)
+  const int64_t n_pos = (int64_t)max_draws * n;
+  const int64_t words_needed = mti0 + n_pos + max_draws + 1;
+  const int64_t n_batches = (words_needed + 623) / 624;  // including batch 0 = current state
+  const int64_t mt_end = n_batches * 624;
+  if ((rc = ensure(g.mt_words, sizeof(uint32_t) * (size_t)mt_end))) return rc;
+  CK(cudaMemcpyAsync(g.mt_words.p, &g.rng.mt[1], sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, g.stream));
+  CK(cudaEventRecord(g.ev0, g.stream));
+  if (n_batches > 1) {
+    mt_generate_kernel<<<1, 256, 0, g.stream>>>((uint32_t *)g.mt_words.p, (int)(n_batches - 1));
+    CK(cudaGetLastError());
+    g.launches++;
+  }
+  CohortParams<typename Traits::Consts> p;
+  memset(&p, 0, sizeof p);
+  g.last_simple_names = true;
+  if (n > 0) {
+    const int64_t n_chunks = (n_pos + CHAIN_CHUNK - 1) / CHAIN_CHUNK;
+    if ((rc = ensure(g.len, (size_t)n_pos))) return rc;
+    if ((rc = ensure(g.starts, sizeof(int64_t) * (size_t)n))) return rc;
+    if ((rc = ensure(g.chain_exit, (size_t)n_chunks * CHAIN_MAX_DRAWS))) return rc;
+    if ((rc = ensure(g.chain_count, sizeof(int) * (size_t)n_chunks * CHAIN_MAX_DRAWS))) return rc;
+    if ((rc = ensure(g.chain_entry, (size_t)n_chunks))) return rc;
+    if ((rc = ensure(g.chain_base, sizeof(int64_t) * (size_t)n_chunks))) return rc;
+    if ((rc = ensure(g.small, 16 * sizeof(double)))) return rc;
+    int lgrid = (int)std::min<int64_t>((n_pos + BLOCK - 1) / BLOCK, (int64_t)g.sm_count * 8);
+    seq_len_kernel<Traits><<<lgrid, BLOCK, 0, g.stream>>>((const uint32_t *)g.mt_words.p, mt_end, mti0, n_pos, consts,
+                                                         (unsigned char *)g.len.p, nullptr);
+    CK(cudaGetLastError());
+    chain_chunk_kernel<<<(unsigned)n_chunks, 64, 0, g.stream>>>((const unsigned char *)g.len.p, n_pos, max_draws, CHAIN_MAX_DRAWS,
+                                                                (unsigned char *)g.chain_exit.p, (int *)g.chain_count.p);
+    CK(cudaGetLastError());
+    chain_scan_kernel<<<1, 256, 0, g.stream>>>((const unsigned char *)g.chain_exit.p, (const int *)g.chain_count.p,
+                                               n_chunks, n, CHAIN_MAX_DRAWS, (unsigned char *)g.chain_entry.p, (int64_t *)g.chain_base.p);
+    CK(cudaGetLastError());
+    g.launches += 3;
+  }
+  p.first_person = 0;
+  p.n = n;
+  p.outputs = outputs;
+  p.consts = consts;
+  p.geom = geom;
+  const int64_t capacity = rowlog_capacity_guess(n, max_rows, mean_rows);
+  g.want_capacity = capacity;
+  p.mt_words = (const uint32_t *)g.mt_words.p;
+  p.mt_end = mt_end;
+  p.starts = (const int64_t *)g.starts.p;
+  int grid;
+  size_t smem;
+  uint32_t unused_state[6] = {0, 0, 0, 0, 0, 0};
+  if ((rc = cohort_prepare<Traits, true>(p, unused_state, &grid, &smem))) return rc;  // zeroes `small`
+  if (n > 0) {
+    const int64_t n_chunks = (n_pos + CHAIN_CHUNK - 1) / CHAIN_CHUNK;
+    SmallView sv = small_view();
+    chain_emit_kernel<<<(unsigned)n_chunks, 64, 0, g.stream>>>(
+        (const unsigned char *)g.len.p, n_pos, mti0, (const unsigned char *)g.chain_entry.p,
+        (const int64_t *)g.chain_base.p, n, (int64_t *)g.starts.p, sv.end_word, sv.error);
+    CK(cudaGetLastError());
+    g.launches++;
+  }
+  if ((rc = cohort_fire<Traits, true>(p, grid, smem, capacity))) return rc;
+  CK(cudaEventRecord(g.ev1, g.stream));
+  g.timing_pending = true;
+  int64_t rows = 0;
+  if ((rc = finish_run(&rows))) return rc;
+  int64_t end_word = 0;
+  CK(cudaMemcpy(&end_word, small_view().end_word, sizeof end_word, cudaMemcpyDeviceToHost));
+  if ((outputs & OUT_ROWLOG) && rows > g.last_capacity && (rc = reexpand(rows))) return rc;
+  // leave R's generator where the reference would: after the last person's last draw
+  if (n > 0 && end_word > 0) {
+    int64_t batch = (end_word - 1) / 624;
+    int64_t mti = end_word - batch * 624;
+    CK(cudaMemcpy(&g.rng.mt[1], (const uint32_t *)g.mt_words.p + batch * 624, sizeof(uint32_t) * 624,
+                  cudaMemcpyDeviceToHost));
+    g.rng.mt[0] = (uint32_t)mti;
+  }
+  return MSIM_OK;
+}
+
+}  // namespace msim_host

@@ -1,0 +1,193 @@
+// Host side of the person-r entry points: the staged kernel (person_staged.cuh) with its row-log passes and
+// report slices, or the generic cohort kernel (msim_set_person_schedule).
+#pragma once
+#include "host_cohort.h"
+
+namespace msim_host {
+using namespace msim;
+
+// ---- person-r
+
+// the bandwidth-bound passes that turn first rows + further rows into the final columns
+int staged_rowpasses(int64_t n, int64_t first_person, int64_t capacity, bool count_first) {
+  RowPassParams r;
+  memset(&r, 0, sizeof r);
+  SmallView sv = small_view();
+  r.first_end = (const double *)g.first_end.p;
+  r.first_tag = (const unsigned short *)g.first_tag.p;
+  r.ov_tag = (const unsigned *)g.ov_tag.p;
+  r.ov_start = (const double *)g.ov_start.p;
+  r.ov_end = (const double *)g.ov_end.p;
+  r.ov_fill = (const unsigned *)g.ov_fill.p;
+  r.max_fill = sv.ov_count;
+  r.ov_cap = (int)g.last_ov_cap;
+  r.n = n;
+  r.first_person = first_person;
+  r.chunk_rows = (unsigned long long *)g.partial.p;
+  r.n_rows = sv.n_rows;
+  r.n_chunks = (n + ROW_CHUNK - 1) / ROW_CHUNK;
+  r.rowlog = (double *)g.rowlog.p;
+  r.capacity = capacity;
+  if (r.n_chunks == 0) return MSIM_OK;
+  if (count_first) {
+    rowpass_count_kernel<<<(unsigned)r.n_chunks, 256, 0, g.stream>>>(r);
+    CK(cudaGetLastError());
+    rowpass_scan_kernel<<<1, 1024, 0, g.stream>>>(r);
+    CK(cudaGetLastError());
+    g.launches += 2;
+  }
+  rowpass_final_kernel<<<(unsigned)r.n_chunks, 256, 0, g.stream>>>(r);
+  CK(cudaGetLastError());
+  g.launches++;
+  return MSIM_OK;
+}
+
+int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t ov_cap_override) {
+  int rc;
+  if (sh->n >= (int64_t)4294967296ll) return fail(MSIM_ERR_ARG, "a shard holds at most 2^32 - 1 persons");
+  StagedParams p;
+  memset(&p, 0, sizeof p);
+  p.first_person = sh->first_person;
+  p.n = sh->n;
+  p.outputs = sh->outputs & 7u;
+  p.consts = person_r::make_consts();
+  p.geom = ages_geom(person_r::N_STATE, person_r::N_EVENT, sh->discount_rate);
+  size_t smem = sizeof(WarpQueues) * SWARPS;
+  if (p.outputs & OUT_ROWLOG) smem += sizeof(WarpRows) * SWARPS;
+  if (p.outputs & OUT_REPORT) {
+    smem += (size_t)(p.geom.total - p.geom.off_dstart) * 4;  // the counters; FP sums go to per-block global slices
+  }
+  int per_sm = 0;
+  typedef void (*StagedKernel)(const StagedParams);
+  // kernels specialised for the output combinations without a report; the general one with (person_staged.cuh)
+  static const StagedKernel kernels[8] = {person_staged_kernel<0>, person_staged_kernel<1>, person_staged_kernel<OUT_RUNTIME>,
+                                          person_staged_kernel<OUT_RUNTIME>, person_staged_kernel<4>, person_staged_kernel<5>,
+                                          person_staged_kernel<OUT_RUNTIME>, person_staged_kernel<OUT_RUNTIME>};
+  const StagedKernel kernel = kernels[p.outputs & 7u];
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SBLOCK, smem));
+  if (per_sm < 1) return fail(MSIM_ERR_CUDA, "staged kernel does not fit on an SM");
+  const int64_t tiles = (sh->n + 31) / 32;
+  int64_t gmax = (int64_t)per_sm * g.sm_count;
+  if (gmax > JUMP_TAB * (int64_t)JUMP_TAB / SBLOCK) gmax = JUMP_TAB * (int64_t)JUMP_TAB / SBLOCK;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(gmax, (tiles + SWARPS - 1) / SWARPS));
+  uint32_t state[6];
+  seed_to_u32(sh->seed, state);
+  stream_start(state, sh->first_person, (int64_t)grid * SBLOCK, &p.st);
+  if ((rc = ensure(g.small, 16 * sizeof(double)))) return rc;
+  CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
+  SmallView sv = small_view();
+  p.error = sv.error;
+  const int cells = (p.outputs & OUT_REPORT) ? p.geom.total : 0;
+  if ((rc = ensure(g.dense, sizeof(double) * (cells + N_COUNTS)))) return rc;
+  CK(cudaMemsetAsync(g.dense.p, 0, sizeof(double) * (cells + N_COUNTS), g.stream));
+  p.dense = (double *)g.dense.p;
+  p.counts = p.dense + cells;
+  g.last_cells = cells;
+  int64_t ov_cap = 0;
+  if (p.outputs & OUT_ROWLOG) {
+    const size_t n1 = (size_t)std::max<int64_t>(sh->n, 1);
+    // rows beyond a person's first: 0.232 per person at the reference's parameters, at most 4; each chunk of
+    // ROW_CHUNK persons owns a region planned with a wide margin (a chunk that needs more repeats the run)
+    const int64_t n_chunks = (sh->n + ROW_CHUNK - 1) / ROW_CHUNK;
+    ov_cap = ov_cap_override > 0 ? ov_cap_override
+                                 : std::min<int64_t>((int64_t)(g.plan_extra_rows * 1.6 * ROW_CHUNK) + (g.plan_extra_rows >= 0.2 ? 96 : 1),
+                                                     (int64_t)ROW_CHUNK * (person_r::MAX_ROWS - 1));
+    const size_t ov_n = (size_t)std::max<int64_t>(n_chunks, 1) * (size_t)ov_cap;
+    if ((rc = ensure(g.first_end, sizeof(double) * n1))) return rc;
+    if ((rc = ensure(g.first_tag, sizeof(unsigned short) * n1))) return rc;
+    if ((rc = ensure(g.ov_fill, sizeof(unsigned) * (size_t)std::max<int64_t>(n_chunks, 1)))) return rc;
+    if ((rc = ensure(g.ov_tag, sizeof(unsigned) * ov_n))) return rc;
+    if ((rc = ensure(g.ov_start, sizeof(double) * ov_n))) return rc;
+    if ((rc = ensure(g.ov_end, sizeof(double) * ov_n))) return rc;
+    CK(cudaMemsetAsync(g.ov_fill.p, 0, sizeof(unsigned) * (size_t)std::max<int64_t>(n_chunks, 1), g.stream));
+    if ((rc = ensure(g.partial, sizeof(unsigned long long) * (size_t)((sh->n + ROW_CHUNK - 1) / ROW_CHUNK + 1)))) return rc;
+    if ((rc = ensure(g.rowlog, sizeof(double) * 5 * (size_t)std::max<int64_t>(capacity, 1)))) return rc;
+    p.first_end = (double *)g.first_end.p;
+    p.first_tag = (unsigned short *)g.first_tag.p;
+    p.ov_tag = (unsigned *)g.ov_tag.p;
+    p.ov_start = (double *)g.ov_start.p;
+    p.ov_end = (double *)g.ov_end.p;
+    p.ov_fill = (unsigned *)g.ov_fill.p;
+    p.ov_cap = (int)ov_cap;
+  }
+  g.last_ov_cap = ov_cap;
+  const int slice = p.geom.off_dstart;  // the FP sums (pt, ut)
+  if (p.outputs & OUT_REPORT) {
+    const size_t bytes = sizeof(double) * (size_t)grid * slice;
+    if ((rc = ensure(g.slices, bytes))) return rc;
+    CK(cudaMemsetAsync(g.slices.p, 0, bytes, g.stream));
+    p.slices = (double *)g.slices.p;
+  }
+  CK(cudaEventRecord(g.ev0, g.stream));
+  if (p.n > 0) {
+    kernel<<<grid, SBLOCK, smem, g.stream>>>(p);
+    CK(cudaGetLastError());
+    g.launches++;
+    if (p.outputs & OUT_REPORT) {
+      fold_slices_kernel<<<(slice + 255) / 256, 256, 0, g.stream>>>(p.slices, grid, slice, p.dense);
+      CK(cudaGetLastError());
+      g.launches++;
+    }
+    if (p.outputs & OUT_ROWLOG) {
+      if ((rc = staged_rowpasses(p.n, p.first_person, capacity, true))) return rc;
+    }
+  }
+  CK(cudaEventRecord(g.ev1, g.stream));
+  g.timing_pending = true;
+  g.last_geom = p.geom;
+  g.last_outputs = p.outputs;
+  g.last_capacity = capacity;
+  g.last_n = p.n;
+  g.last_first = p.first_person;
+  g.last_max_rows = person_r::MAX_ROWS;
+  g.last_staged = true;
+  g.have_last = true;
+  return MSIM_OK;
+}
+
+int person_enqueue(const msim_person_shard *sh, int64_t capacity_override, int64_t ov_cap_override = 0) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  if (!sh || sh->n < 0 || sh->first_person < 0) return fail(MSIM_ERR_ARG, "bad shard");
+  if (!mrg_seed_ok(sh->seed)) return fail(MSIM_ERR_SEED, "illegal MRG32k3a seed");
+  const int64_t capacity = capacity_override > 0 ? capacity_override : rowlog_capacity_guess(sh->n, person_r::MAX_ROWS, g.plan_rows);
+  g.want_capacity = capacity;
+  g.last_simple_names = false;
+  if (g.person_kernel == 0) return person_enqueue_staged(sh, capacity, ov_cap_override);
+  CohortParams<person_r::Consts> p;
+  memset(&p, 0, sizeof p);
+  p.first_person = sh->first_person;
+  p.n = sh->n;
+  p.outputs = sh->outputs & 7u;
+  p.consts = person_r::make_consts();
+  p.geom = ages_geom(person_r::N_STATE, person_r::N_EVENT, sh->discount_rate);
+  uint32_t state[6];
+  seed_to_u32(sh->seed, state);
+  int grid;
+  size_t smem;
+  if ((rc = cohort_prepare<PersonTraits, false>(p, state, &grid, &smem))) return rc;
+  CK(cudaEventRecord(g.ev0, g.stream));
+  if ((rc = cohort_fire<PersonTraits, false>(p, grid, smem, capacity))) return rc;
+  CK(cudaEventRecord(g.ev1, g.stream));
+  g.timing_pending = true;
+  return MSIM_OK;
+}
+
+int person_run(const msim_person_shard *sh) {
+  int rc;
+  if ((rc = person_enqueue(sh, 0))) return rc;
+  int64_t rows = 0;
+  if ((rc = finish_run(&rows))) return rc;
+  if ((sh->outputs & OUT_ROWLOG) && g.last_staged && g.last_ov_rows > g.last_ov_cap) {
+    // rare: more rows beyond the first than planned for — run again with the exact size
+    if ((rc = person_enqueue(sh, rows > g.last_capacity ? rows : 0, g.last_ov_rows))) return rc;
+    if ((rc = finish_run(&rows))) return rc;
+  }
+  if ((sh->outputs & OUT_ROWLOG) && rows > g.last_capacity) {  // rare: redo the expand pass with the exact size
+    if ((rc = reexpand(rows))) return rc;
+  }
+  return MSIM_OK;
+}
+
+}  // namespace msim_host

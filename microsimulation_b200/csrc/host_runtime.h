@@ -1,0 +1,175 @@
+// Host-side runtime of the C ABI: the per-process context (device, stream, buffers that grow on demand),
+// error reporting, page-locked host memory.  Everything in host_*.h lives in namespace msim_host; capi.cu holds
+// the extern "C" entry points.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/msim.h"
+#include "host_state.h"
+#include "report_host.h"
+#include "kernels.cuh"
+#include "person_staged.cuh"
+#include "summary_kernels.cuh"
+
+namespace msim_host {
+using namespace msim;
+
+// ---------------------------------------------------------------- context
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+};
+
+struct Ctx {
+  bool inited = false;
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
+  MrgJump *d_lo = nullptr, *d_hi = nullptr;
+  DevBuf rowlog, prov_start, prov_end, prov_meta, tile_count, partial, dense, small, mt_words, len, starts, chain_exit, chain_count, chain_entry, chain_base, calib_out,
+      calib_par, uniforms, first_end, first_tag, ov_fill, ov_tag, ov_start, ov_end, aux, code_in, code_out, sgeom,
+      indiv, gsm_model, gsm_data, gsm_in, gsm_out, slices;
+  int person_kernel = 0;  // 0 = staged schedule (person_staged.cuh), 1 = generic cohort kernel
+  bool last_staged = false;
+  double plan_rows = 1.25, plan_extra_rows = 0.26;  // row-log buffer planning (msim_set_rowlog_plan)
+  int64_t last_ov_cap = 0, last_ov_rows = 0;
+  HostRngState rng;
+  // last cohort run
+  int64_t last_n_rows = 0, last_capacity = 0;
+  ReportGeom last_geom;
+  unsigned last_outputs = 0;
+  bool last_simple_names = false;
+  int64_t want_capacity = 0;
+  int64_t last_n = 0, last_first = 0;
+  int last_max_rows = 0;
+  int last_cells = 0;  // dense report cells of the last run (0 when no report was requested)
+  bool have_last = false;
+  float last_ms = 0.f;
+  bool timing_pending = false;
+  int64_t launches = 0;
+  // pinned host cache (one buffer) so steady-state row-log fetches do not re-pin
+  void *pin_cache = nullptr;
+  size_t pin_cache_bytes = 0;
+  std::unordered_map<void *, size_t> pinned;  // live pinned allocations -> bytes
+};
+
+static Ctx g;  // one context per process (this header is included by capi.cu only)
+static thread_local std::string g_err;
+
+inline int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(MSIM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));             \
+  } while (0)
+
+inline int ensure(DevBuf &b, size_t bytes) {
+  if (b.bytes >= bytes && b.p) return MSIM_OK;
+  if (b.p) CK(cudaFree(b.p));
+  b.p = nullptr;
+  b.bytes = 0;
+  size_t want = bytes < 256 ? 256 : bytes;
+  CK(cudaMalloc(&b.p, want));
+  b.bytes = want;
+  return MSIM_OK;
+}
+
+inline int ensure_init() {
+  if (g.inited) return MSIM_OK;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(MSIM_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0"));
+  if (g.device >= ndev) return fail(MSIM_ERR_ARG, "device index out of range");
+  CK(cudaSetDevice(g.device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, g.device));
+  g.sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
+  g.stream = g.own_stream;
+  CK(cudaEventCreate(&g.ev0));
+  CK(cudaEventCreate(&g.ev1));
+  // per-thread start tables: lo[j] = M^j, hi[j] = M^(JUMP_TAB*j)
+  std::vector<MrgJump> lo(JUMP_TAB), hi(JUMP_TAB);
+  const MrgJump &M = mrg_substream_jump();
+  lo[0] = mrg_jump_identity();
+  for (int j = 1; j < JUMP_TAB; j++) lo[j] = mrg_jump_mul(M, lo[j - 1]);
+  MrgJump Mt = mrg_jump_mul(M, lo[JUMP_TAB - 1]);  // M^JUMP_TAB
+  hi[0] = mrg_jump_identity();
+  for (int j = 1; j < JUMP_TAB; j++) hi[j] = mrg_jump_mul(Mt, hi[j - 1]);
+  CK(cudaMalloc(&g.d_lo, sizeof(MrgJump) * JUMP_TAB));
+  CK(cudaMalloc(&g.d_hi, sizeof(MrgJump) * JUMP_TAB));
+  CK(cudaMemcpy(g.d_lo, lo.data(), sizeof(MrgJump) * JUMP_TAB, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(g.d_hi, hi.data(), sizeof(MrgJump) * JUMP_TAB, cudaMemcpyHostToDevice));
+  g.inited = true;
+  return MSIM_OK;
+}
+
+// substream state of person `first_person` of the stream that starts at `state`
+void stream_start(const uint32_t state[6], int64_t first_person, int64_t n_threads, StreamStart *st) {
+  Mrg32k3a b;
+  memcpy(b.s, state, sizeof b.s);
+  b.jump(mrg_jump_pow(mrg_substream_jump(), (uint64_t)first_person + 1));
+  memcpy(st->base, b.s, sizeof b.s);
+  st->lo = g.d_lo;
+  st->hi = g.d_hi;
+  st->stride = mrg_jump_pow(mrg_substream_jump(), (uint64_t)n_threads);
+}
+
+// ---------------------------------------------------------------- host memory
+
+int pinned_alloc(size_t bytes, double **out) {
+  if (bytes == 0) bytes = 8;
+  if (g.pin_cache && g.pin_cache_bytes >= bytes) {
+    *out = (double *)g.pin_cache;
+    g.pinned[g.pin_cache] = g.pin_cache_bytes;
+    g.pin_cache = nullptr;
+    g.pin_cache_bytes = 0;
+    return MSIM_OK;
+  }
+  void *p = nullptr;
+  CK(cudaMallocHost(&p, bytes));
+  g.pinned[p] = bytes;
+  *out = (double *)p;
+  return MSIM_OK;
+}
+
+void host_free(double *p) {
+  if (!p) return;
+  auto it = g.pinned.find(p);
+  if (it == g.pinned.end()) {
+    free(p);
+    return;
+  }
+  size_t bytes = it->second;
+  g.pinned.erase(it);
+  if (bytes > g.pin_cache_bytes) {  // keep the largest buffer for the next call
+    if (g.pin_cache) cudaFreeHost(g.pin_cache);
+    g.pin_cache = p;
+    g.pin_cache_bytes = bytes;
+  } else {
+    cudaFreeHost(p);
+  }
+}
+
+ReportGeom geom_from_dims(const msim_dense_dims *dims, double discount_rate) {
+  return ages_geom(dims->n_state, dims->n_event, discount_rate);
+}
+
+}  // namespace msim_host

@@ -1,0 +1,169 @@
+// Host side of the SummaryReport model (Sick-Sicker, summary_kernels.cuh).
+#pragma once
+#include "host_cohort.h"
+
+namespace msim_host {
+using namespace msim;
+
+// ---- Sick-Sicker (SummaryReport)
+
+// One attempt in the stream regime with `n_pos` start positions planned for; *short_plan is set when the chain
+// of persons ran off the planned positions before person n-1 (the caller retries with the maximum).
+int sick_stream_attempt(int64_t n, const SickParams &base, int64_t n_pos, int max_draws, bool *short_plan, int64_t *end_word_out,
+                        int64_t *mt_end_out) {
+  int rc;
+  *short_plan = false;
+  const int64_t mti0 = g.rng.mt[0];
+  const int64_t words_needed = mti0 + n_pos + max_draws + 1;
+  const int64_t n_batches = (words_needed + 623) / 624;
+  const int64_t mt_end = n_batches * 624;
+  *mt_end_out = mt_end;
+  if ((rc = ensure(g.mt_words, sizeof(uint32_t) * (size_t)mt_end))) return rc;
+  CK(cudaMemcpyAsync(g.mt_words.p, &g.rng.mt[1], sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, g.stream));
+  if (n_batches > 1) {
+    mt_generate_kernel<<<1, 256, 0, g.stream>>>((uint32_t *)g.mt_words.p, (int)(n_batches - 1));
+    CK(cudaGetLastError());
+    g.launches++;
+  }
+  const int stride = 256;
+  const int64_t n_chunks = (n_pos + CHAIN_CHUNK - 1) / CHAIN_CHUNK;
+  if ((rc = ensure(g.len, (size_t)n_pos))) return rc;
+  if ((rc = ensure(g.aux, (size_t)n_pos))) return rc;
+  if ((rc = ensure(g.starts, sizeof(int64_t) * (size_t)n))) return rc;
+  if ((rc = ensure(g.chain_exit, (size_t)n_chunks * stride))) return rc;
+  if ((rc = ensure(g.chain_count, sizeof(int) * (size_t)n_chunks * stride))) return rc;
+  if ((rc = ensure(g.chain_entry, (size_t)n_chunks))) return rc;
+  if ((rc = ensure(g.chain_base, sizeof(int64_t) * (size_t)n_chunks))) return rc;
+  CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
+  SmallView sv = small_view();
+  int lgrid = (int)std::min<int64_t>((n_pos + BLOCK - 1) / BLOCK, (int64_t)g.sm_count * 8);
+  seq_len_kernel<SickTraits><<<lgrid, BLOCK, 0, g.stream>>>((const uint32_t *)g.mt_words.p, mt_end, mti0, n_pos, base.par,
+                                                            (unsigned char *)g.len.p, (unsigned char *)g.aux.p);
+  CK(cudaGetLastError());
+  chain_chunk_kernel<<<(unsigned)n_chunks, 256, 0, g.stream>>>((const unsigned char *)g.len.p, n_pos, max_draws, stride,
+                                                               (unsigned char *)g.chain_exit.p, (int *)g.chain_count.p);
+  CK(cudaGetLastError());
+  chain_scan_kernel<<<1, 256, 0, g.stream>>>((const unsigned char *)g.chain_exit.p, (const int *)g.chain_count.p, n_chunks, n,
+                                             stride, (unsigned char *)g.chain_entry.p, (int64_t *)g.chain_base.p);
+  CK(cudaGetLastError());
+  chain_emit_kernel<<<(unsigned)n_chunks, 64, 0, g.stream>>>((const unsigned char *)g.len.p, n_pos, mti0,
+                                                             (const unsigned char *)g.chain_entry.p, (const int64_t *)g.chain_base.p,
+                                                             n, (int64_t *)g.starts.p, sv.end_word, sv.error);
+  CK(cudaGetLastError());
+  g.launches += 4;
+  CK(cudaStreamSynchronize(g.stream));
+  double small[16];
+  CK(cudaMemcpy(small, g.small.p, sizeof small, cudaMemcpyDeviceToHost));
+  const int64_t end_word = *(int64_t *)(small + 11);
+  const int err = *(int *)(small + 10);
+  if (end_word == 0 || err == MSIM_ERR_STREAM) {  // person n-1 was never reached
+    *short_plan = true;
+    return MSIM_OK;
+  }
+  if (err) return fail(err, "device-side error while resolving stream offsets");
+  *end_word_out = end_word;
+  return MSIM_OK;
+}
+
+int sick_sicker_run(int64_t n, const double par17[17], int indivp, int substreams, int64_t first_person, msim_report *out) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  if (!out || !par17 || n < 0 || first_person < 0) return fail(MSIM_ERR_ARG, "bad arguments");
+  SickParams p;
+  memset(&p, 0, sizeof p);
+  sick_sicker::Par &P = p.par;
+  P.r_HS1 = par17[0]; P.r_HD = par17[1]; P.r_S1H = par17[2]; P.r_S1S2 = par17[3]; P.r_S1D = par17[4]; P.r_S2D = par17[5];
+  P.c_H = par17[6]; P.c_S1 = par17[7]; P.c_S2 = par17[8]; P.c_Trt = par17[9];
+  P.u_H = par17[10]; P.u_S1 = par17[11]; P.u_S2 = par17[12]; P.u_Trt = par17[13];
+  const double rate = par17[14], by = par17[15];
+  P.Trt = par17[16] != 0.0;
+  if (!(rate >= 0)) return fail(MSIM_ERR_ARG, "discountRate must be >= 0");
+  SummaryGeom G;
+  // report.setPartition(0.0, 31.0, partitionBy); report.setDiscountRate(discountRate)   (README.org:294-295)
+  if (!make_summary_geom(&G, sick_sicker::N_STATE, sick_sicker::N_EVENT, 0.0, 31.0, by, 1.0e100, rate, rate))
+    return fail(MSIM_ERR_ARG, "partitionBy gives more age bins than the report holds");
+  if ((rc = ensure(g.sgeom, sizeof G))) return rc;
+  CK(cudaMemcpyAsync(g.sgeom.p, &G, sizeof G, cudaMemcpyHostToDevice, g.stream));
+  CK(cudaStreamSynchronize(g.stream));  // G is a stack object
+  const int64_t n_indiv = indivp ? n : 1;
+  if ((rc = ensure(g.dense, sizeof(double) * G.total))) return rc;
+  if ((rc = ensure(g.indiv, sizeof(double) * 2 * (size_t)std::max<int64_t>(n_indiv, 1)))) return rc;
+  if ((rc = ensure(g.code_in, (size_t)std::max<int64_t>(n, 1)))) return rc;
+  if ((rc = ensure(g.code_out, (size_t)std::max<int64_t>(n, 1)))) return rc;
+  if ((rc = ensure(g.small, 16 * sizeof(double)))) return rc;
+  CK(cudaMemsetAsync(g.dense.p, 0, sizeof(double) * G.total, g.stream));
+  CK(cudaMemsetAsync(g.indiv.p, 0, sizeof(double) * 2 * (size_t)std::max<int64_t>(n_indiv, 1), g.stream));
+  CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
+  p.first_person = first_person;
+  p.n = n;
+  p.geom = (const SummaryGeom *)g.sgeom.p;
+  p.code_in = (const unsigned char *)g.code_in.p;
+  p.code_out = (unsigned char *)g.code_out.p;
+  p.dense = (double *)g.dense.p;
+  p.indiv = (double *)g.indiv.p;
+  p.indivp = indivp ? 1 : 0;
+  p.error = small_view().error;
+  const size_t smem = sick_kernel_smem(G);
+  const int64_t tiles = (n + BLOCK - 1) / BLOCK;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)g.sm_count * 4, tiles));
+  int64_t end_word = 0;
+  CK(cudaEventRecord(g.ev0, g.stream));
+  if (n > 0 && !substreams) {
+    if (!g.rng.mt_seeded)
+      return fail(MSIM_ERR_STATE, "Mersenne-Twister state not set: call msim_mt_set_seed or msim_mt_set_state first");
+    const int max_draws = 250;
+    bool short_plan = false;
+    int64_t mt_end = 0;
+    // 36.4 draws per person at the README's rates; plan for 48 and fall back to the per-person maximum
+    int64_t n_pos = std::min<int64_t>(48 * n + 8192, (int64_t)max_draws * n);
+    if ((rc = sick_stream_attempt(n, p, n_pos, max_draws, &short_plan, &end_word, &mt_end))) return rc;
+    if (short_plan && n_pos < (int64_t)max_draws * n) {
+      n_pos = (int64_t)max_draws * n;
+      if ((rc = sick_stream_attempt(n, p, n_pos, max_draws, &short_plan, &end_word, &mt_end))) return rc;
+    }
+    if (short_plan) return fail(MSIM_ERR_STREAM, "a person drew more uniforms than the sequential-stream plan allows (250)");
+    CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
+    p.mt_words = (const uint32_t *)g.mt_words.p;
+    p.mt_end = mt_end;
+    p.starts = (const int64_t *)g.starts.p;
+    gather_code_kernel<<<g.sm_count * 4, 256, 0, g.stream>>>((const unsigned char *)g.aux.p, p.starts, (int64_t)g.rng.mt[0], n,
+                                                             p.code_out);
+    CK(cudaGetLastError());
+    carry_scan_kernel<<<1, 1024, 0, g.stream>>>(p.code_out, n, 0, (unsigned char *)g.code_in.p);
+    CK(cudaGetLastError());
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(sick_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sick_kernel<true><<<grid, BLOCK, smem, g.stream>>>(p);
+    CK(cudaGetLastError());
+    g.launches += 3;
+  } else if (n > 0) {
+    // rng = new Rng(): takes the package seed, which then moves on one stream; person i draws from substream
+    // first_person + i + 1 (the regime the oracle's `substreams` flag selects)
+    HostStream hs = g.rng.new_stream();
+    stream_start(hs.Cg.s, first_person, (int64_t)grid * BLOCK, &p.st);
+    sick_code_kernel<<<grid, BLOCK, 0, g.stream>>>(p);
+    CK(cudaGetLastError());
+    carry_scan_kernel<<<1, 1024, 0, g.stream>>>(p.code_out, n, 0, (unsigned char *)g.code_in.p);
+    CK(cudaGetLastError());
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(sick_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sick_kernel<false><<<grid, BLOCK, smem, g.stream>>>(p);
+    CK(cudaGetLastError());
+    g.launches += 3;
+  }
+  CK(cudaEventRecord(g.ev1, g.stream));
+  g.timing_pending = true;
+  g.have_last = false;
+  if ((rc = finish_run(nullptr))) return rc;
+  std::vector<double> d(G.total), ind(2 * (size_t)std::max<int64_t>(n_indiv, 1));
+  CK(cudaMemcpy(d.data(), g.dense.p, sizeof(double) * d.size(), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ind.data(), g.indiv.p, sizeof(double) * ind.size(), cudaMemcpyDeviceToHost));
+  dense_to_summary_impl(d.data(), G, ind.data(), n_indiv, out);
+  if (n > 0 && !substreams && end_word > 0) {  // leave R's generator after the last person's last draw
+    int64_t batch = (end_word - 1) / 624;
+    int64_t mti = end_word - batch * 624;
+    CK(cudaMemcpy(&g.rng.mt[1], (const uint32_t *)g.mt_words.p + batch * 624, sizeof(uint32_t) * 624, cudaMemcpyDeviceToHost));
+    g.rng.mt[0] = (uint32_t)mti;
+  }
+  return MSIM_OK;
+}
+
+}  // namespace msim_host
