@@ -160,6 +160,25 @@ int msim_callSim_SickSicker(int32_t n, const double param[17], int indivp, int s
  * their own discounted totals; parity hook. */
 int msim_discounted(int mode, int64_t n, const double *y, const double *a, const double *b, double rate, double *out);
 
+/* ---- survival-time utilities and lookup tables --------------------------
+ * The building blocks of the external FHCRC screening model, element-wise on the GPU.
+ *
+ * Rpexp(h, t, n_t) (inst/include/microsimulation.h:527-617), piecewise constant hazards h[i] from t[i]:
+ *   mode 0  rand(u = a[i], from = b[i])  (b may be NULL: 0); an all-zero hazard tail is MSIM_ERR_ARG (Rcpp::stop)
+ *   mode 1  H(a[i])   2  h(a[i])   3  p(a[i]) (lower tail)   4  d(a[i])                                        */
+int msim_rpexp(int mode, int32_t n_t, const double *h, const double *t, int64_t n, const double *a, const double *b, double *out);
+/* Rpexp_gamma(theta, mu, t, n_t) (microsimulation.h:626-704), gamma frailty Z[i]:
+ *   mode 0  rand(u = a[i], Z[i], from[i])  (from may be NULL)   1  H(a[i], Z[i])   2  h(a[i], Z[i])   3  p(a[i], Z[i]) */
+int msim_rpexp_gamma(int mode, int32_t n_t, double theta, const double *mu, const double *t, int64_t n, const double *a,
+                     const double *Z, const double *from, double *out);
+/* NumericInterpolate over points (x, y) (inst/include/rcpp_table.h:52-111):
+ *   mode 0  approx(xfind)   1  operator()(xfind) (step)   2  invert(yfind)   3  invert_decreasing(yfind)          */
+int msim_interpolate(int mode, int32_t n_pts, const double *x, const double *y, int64_t n, const double *xfind, double *out);
+/* Table<key..., Outcome> built from the rows of a data frame (rcpp_table.h:136-324): rows is n_rows x (n_axes + 1)
+ * row-major, keys first, outcome last; keys is n x n_axes.  On every axis the largest key <= the argument is taken
+ * (the smallest if there is none); combinations the data frame does not hold give 0.                              */
+int msim_table_lookup(int32_t n_axes, int64_t n_rows, const double *rows, int64_t n, const double *keys, double *out);
+
 /* ---- generalised survival models (src/gsm.cpp, src/splines.cpp) ------- */
 
 /* The fields of the Rcpp::List that gsm::gsm(Rcpp::List) reads (gsm.cpp:60-92). */

@@ -16,6 +16,7 @@
 #include "report_host.h"
 #include "host_cohort.h"
 #include "host_gsm.h"
+#include "host_lookups.h"
 #include "host_person.h"
 #include "host_runtime.h"
 #include "host_summary.h"
@@ -306,6 +307,94 @@ int msim_discounted(int mode, int64_t n, const double *y, const double *a, const
   CK(cudaMemcpyAsync(out, g.gsm_out.p, sizeof(double) * nn, cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
   return MSIM_OK;
+}
+
+int msim_rpexp(int mode, int32_t n_t, const double *h, const double *t, int64_t n, const double *a, const double *b, double *out) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  if (n_t < 1 || !h || !t || n < 0 || mode < 0 || mode > 4 || (n > 0 && (!a || !out))) return fail(MSIM_ERR_ARG, "bad arguments");
+  std::vector<double> Hi(n_t);
+  rpexp_cumulate(n_t, h, t, Hi.data());
+  std::vector<const double *> ptr;
+  if ((rc = upload_vectors({Hi, std::vector<double>(h, h + n_t), std::vector<double>(t, t + n_t)}, &ptr))) return rc;
+  LookupParams p;
+  memset(&p, 0, sizeof p);
+  p.family = 0;
+  p.mode = mode;
+  p.pexp = Rpexp{n_t, ptr[0], ptr[1], ptr[2]};
+  return lookup_run(p, n, n, a, mode == 0 ? b : nullptr, nullptr, out);
+}
+
+int msim_rpexp_gamma(int mode, int32_t n_t, double theta, const double *mu, const double *t, int64_t n, const double *a,
+                     const double *Z, const double *from, double *out) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  if (n_t < 1 || !mu || !t || !(theta > 0) || n < 0 || mode < 0 || mode > 3 || (n > 0 && (!a || !Z || !out)))
+    return fail(MSIM_ERR_ARG, "bad arguments");
+  std::vector<double> H0(n_t);
+  rpexp_gamma_cumulate(n_t, theta, mu, t, H0.data());
+  std::vector<const double *> ptr;
+  if ((rc = upload_vectors({H0, std::vector<double>(mu, mu + n_t), std::vector<double>(t, t + n_t)}, &ptr))) return rc;
+  LookupParams p;
+  memset(&p, 0, sizeof p);
+  p.family = 1;
+  p.mode = mode;
+  p.pgam = RpexpGamma{n_t, theta, ptr[0], ptr[1], ptr[2]};
+  return lookup_run(p, n, n, a, Z, mode == 0 ? from : nullptr, out);
+}
+
+int msim_interpolate(int mode, int32_t n_pts, const double *x, const double *y, int64_t n, const double *xfind, double *out) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  if (n_pts < 2 || !x || !y || n < 0 || mode < 0 || mode > 3 || (n > 0 && (!xfind || !out))) return fail(MSIM_ERR_ARG, "bad arguments");
+  std::vector<double> slope(n_pts - 1);
+  for (int i = 0; i < n_pts - 1; i++) slope[i] = (y[i + 1] - y[i]) / (x[i + 1] - x[i]);  // NumericInterpolate::prepare
+  std::vector<const double *> ptr;
+  if ((rc = upload_vectors({std::vector<double>(x, x + n_pts), std::vector<double>(y, y + n_pts), slope}, &ptr))) return rc;
+  LookupParams p;
+  memset(&p, 0, sizeof p);
+  p.family = 2;
+  p.mode = mode;
+  p.interp = Interp{n_pts, ptr[0], ptr[1], ptr[2]};
+  return lookup_run(p, n, n, xfind, nullptr, nullptr, out);
+}
+
+int msim_table_lookup(int32_t n_axes, int64_t n_rows, const double *rows, int64_t n, const double *keys, double *out) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  if (n_axes < 1 || n_axes > TABLE_MAX_AXES || n_rows < 1 || !rows || n < 0 || (n > 0 && (!keys || !out)))
+    return fail(MSIM_ERR_ARG, "bad arguments");
+  // axes = sorted distinct key values per column; outcomes on the dense grid, 0 where no row names the combination
+  std::vector<std::vector<double> > vecs(n_axes);
+  for (int a = 0; a < n_axes; a++) {
+    for (int64_t r = 0; r < n_rows; r++) vecs[a].push_back(rows[r * (n_axes + 1) + a]);
+    std::sort(vecs[a].begin(), vecs[a].end());
+    vecs[a].erase(std::unique(vecs[a].begin(), vecs[a].end()), vecs[a].end());
+  }
+  size_t cells = 1;
+  for (int a = 0; a < n_axes; a++) cells *= vecs[a].size();
+  if (cells > ((size_t)1 << 26)) return fail(MSIM_ERR_ARG, "table grid too large");
+  std::vector<double> values(cells, 0.0);
+  for (int64_t r = 0; r < n_rows; r++) {  // later rows overwrite earlier ones, as map::operator[] = does
+    size_t flat = 0;
+    for (int a = 0; a < n_axes; a++)
+      flat = flat * vecs[a].size() +
+             (size_t)(std::lower_bound(vecs[a].begin(), vecs[a].end(), rows[r * (n_axes + 1) + a]) - vecs[a].begin());
+    values[flat] = rows[r * (n_axes + 1) + n_axes];
+  }
+  vecs.push_back(values);
+  std::vector<const double *> ptr;
+  if ((rc = upload_vectors(vecs, &ptr))) return rc;
+  LookupParams p;
+  memset(&p, 0, sizeof p);
+  p.family = 3;
+  p.table.n_axes = n_axes;
+  for (int a = 0; a < n_axes; a++) {
+    p.table.n[a] = (int)vecs[a].size();
+    p.table.axis[a] = ptr[a];
+  }
+  p.table.values = ptr[n_axes];
+  return lookup_run(p, n, n * n_axes, keys, nullptr, nullptr, out);
 }
 
 int msim_gsm_randU(const msim_gsm *model, int64_t n, const double *u, const double *tentry, const int32_t *index,

@@ -8,23 +8,6 @@ using namespace msim;
 
 // ---------------------------------------------------------------- cohort launch
 
-// `small` buffer layout (8-byte cells): [9] n_rows (u64), [10] error (int), [11] end_word (i64), [12] overflow rows (u64)
-struct SmallView {
-  unsigned long long *n_rows;
-  int *error;
-  int64_t *end_word;
-  unsigned long long *ov_count;
-};
-SmallView small_view() {
-  SmallView v;
-  double *b = (double *)g.small.p;
-  v.n_rows = (unsigned long long *)(b + 9);
-  v.error = (int *)(b + 10);
-  v.end_word = (int64_t *)(b + 11);
-  v.ov_count = (unsigned long long *)(b + 12);
-  return v;
-}
-
 template <class Traits, bool STREAM>
 int cohort_grid(size_t smem, int64_t n, int *grid) {
   auto kern = cohort_kernel<Traits, STREAM>;

@@ -27,6 +27,7 @@
 #include <type_traits>
 
 #include "gsm.cuh"
+#include "lookups.cuh"
 #include "models.cuh"
 #include "report.cuh"
 #include "seqstream.cuh"
@@ -668,6 +669,45 @@ __global__ void __launch_bounds__(BLOCK) calib_kernel(CalibParams p) {
     unsigned long long *cell = reinterpret_cast<unsigned long long *>(&out[44]);
     atomicMax(cell, (unsigned long long)__double_as_longlong((double)s_tar_n));
     if (s_error) atomicCAS(p.error, 0, s_error);
+  }
+}
+
+// ---- survival-time utilities and lookup tables: one evaluation per thread --
+struct LookupParams {
+  int family, mode;  // family 0 Rpexp, 1 Rpexp_gamma, 2 NumericInterpolate, 3 Table; modes as in include/msim.h
+  Rpexp pexp;
+  RpexpGamma pgam;
+  Interp interp;
+  DenseTable table;
+  int64_t n;
+  const double *a, *b, *c;  // inputs (b, c may be null: 0); for tables a = keys [n][n_axes]
+  double *out;
+  int *error;
+};
+__global__ void __launch_bounds__(256) lookup_kernel(LookupParams p) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x) {
+    double r = 0.0;
+    if (p.family == 0) {
+      const double x = p.a[i];
+      if (p.mode == 0) {
+        int failed = 0;
+        r = rpexp_rand(p.pexp, x, p.b ? p.b[i] : 0.0, &failed);
+        if (failed) atomicCAS(p.error, 0, -3);
+      } else {
+        r = p.mode == 1 ? rpexp_H(p.pexp, x) : p.mode == 2 ? rpexp_h(p.pexp, x) : p.mode == 3 ? rpexp_p(p.pexp, x, true) : rpexp_d(p.pexp, x);
+      }
+    } else if (p.family == 1) {
+      const double x = p.a[i], Z = p.b[i];
+      r = p.mode == 0 ? rpexp_gamma_rand(p.pgam, x, Z, p.c ? p.c[i] : 0.0)
+          : p.mode == 1 ? rpexp_gamma_H(p.pgam, x, Z) : p.mode == 2 ? rpexp_gamma_h(p.pgam, x, Z) : rpexp_gamma_p(p.pgam, x, Z, true);
+    } else if (p.family == 2) {
+      const double x = p.a[i];
+      r = p.mode == 0 ? interp_approx(p.interp, x) : p.mode == 1 ? interp_step(p.interp, x)
+          : p.mode == 2 ? interp_invert(p.interp, x) : interp_invert_decreasing(p.interp, x);
+    } else {
+      r = table_lookup(p.table, p.a + i * p.table.n_axes);
+    }
+    p.out[i] = r;
   }
 }
 

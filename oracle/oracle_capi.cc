@@ -12,6 +12,7 @@
 #include "cprocess_lite.h"
 #include "models.h"
 #include "gsm_lite.h"
+#include "lookups_lite.h"
 
 using namespace orc;
 
@@ -322,6 +323,42 @@ int oracle_bs_eval(const msim_gsm *m, int term, int64_t n, const double *x, int 
     orc::vec v = g.terms[term].ns1.bs::eval(x[i], der);
     for (size_t k = 0; k < v.size(); k++) out[i * v.size() + k] = v[k];
   }
+  return 0;
+}
+
+// ---- survival-time utilities and lookup tables (lookups_lite.h); modes as in include/msim.h
+int oracle_rpexp(int mode, int n_t, const double *h, const double *t, int64_t n, const double *a, const double *b, double *out) {
+  orc::Rpexp r(h, t, n_t);
+  for (int64_t i = 0; i < n; i++) {
+    try {
+      out[i] = mode == 0 ? r.rand(a[i], b ? b[i] : 0.0) : mode == 1 ? r.H(a[i]) : mode == 2 ? r.h(a[i]) : mode == 3 ? r.p(a[i]) : r.d(a[i]);
+    } catch (std::exception &) {
+      return -3;  // Rcpp::stop in the reference
+    }
+  }
+  return 0;
+}
+int oracle_rpexp_gamma(int mode, int n_t, double theta, const double *mu, const double *t, int64_t n, const double *a, const double *Z,
+                       const double *from, double *out) {
+  orc::Rpexp_gamma r(theta, mu, t, (size_t)n_t);
+  for (int64_t i = 0; i < n; i++)
+    out[i] = mode == 0 ? r.rand(a[i], Z[i], from ? from[i] : 0.0) : mode == 1 ? r.H(a[i], Z[i]) : mode == 2 ? r.h(a[i], Z[i]) : r.p(a[i], Z[i]);
+  return 0;
+}
+int oracle_interpolate(int mode, int n_pts, const double *x, const double *y, int64_t n, const double *xfind, double *out) {
+  orc::NumericInterpolate f(x, y, n_pts);
+  for (int64_t i = 0; i < n; i++)
+    out[i] = mode == 0 ? f.approx(xfind[i]) : mode == 1 ? f(xfind[i]) : mode == 2 ? f.invert(xfind[i]) : f.invert_decreasing(xfind[i]);
+  return 0;
+}
+// the table as the rows of a data frame: n_rows x (n_axes keys + outcome), row-major
+int oracle_table_lookup(int n_axes, int64_t n_rows, const double *rows, int64_t n, const double *keys, double *out) {
+  orc::Table T(n_axes);
+  for (int64_t r = 0; r < n_rows; r++) {
+    std::vector<double> key(rows + r * (n_axes + 1), rows + r * (n_axes + 1) + n_axes);
+    T.insert(key, rows[r * (n_axes + 1) + n_axes]);
+  }
+  for (int64_t i = 0; i < n; i++) out[i] = T(std::vector<double>(keys + i * n_axes, keys + (i + 1) * n_axes));
   return 0;
 }
 

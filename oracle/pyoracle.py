@@ -274,6 +274,47 @@ class Oracle:
                   out.ctypes.data_as(C.POINTER(C.c_double))) == 0
         return out
 
+    # ---- survival-time utilities and lookup tables (lookups_lite.h); modes as in include/msim.h
+    def rpexp(self, mode, h, t, a, b=None):
+        h, t, a = (np.ascontiguousarray(v, dtype=np.float64) for v in (h, t, a))
+        b = None if b is None else np.ascontiguousarray(np.broadcast_to(b, a.shape), dtype=np.float64)
+        out = np.empty_like(a)
+        dp = C.POINTER(C.c_double)
+        rc = self.lib.oracle_rpexp(C.c_int(mode), C.c_int(h.size), h.ctypes.data_as(dp), t.ctypes.data_as(dp), C.c_int64(a.size),
+                                   a.ctypes.data_as(dp), None if b is None else b.ctypes.data_as(dp), out.ctypes.data_as(dp))
+        if rc:
+            raise RuntimeError("Rpexp.rand() failed due to zero hazards")
+        return out
+
+    def rpexp_gamma(self, mode, theta, mu, t, a, Z, start=None):
+        mu, t, a = (np.ascontiguousarray(v, dtype=np.float64) for v in (mu, t, a))
+        Z = np.ascontiguousarray(np.broadcast_to(Z, a.shape), dtype=np.float64)
+        start = None if start is None else np.ascontiguousarray(np.broadcast_to(start, a.shape), dtype=np.float64)
+        out = np.empty_like(a)
+        dp = C.POINTER(C.c_double)
+        assert self.lib.oracle_rpexp_gamma(C.c_int(mode), C.c_int(mu.size), C.c_double(theta), mu.ctypes.data_as(dp),
+                                           t.ctypes.data_as(dp), C.c_int64(a.size), a.ctypes.data_as(dp), Z.ctypes.data_as(dp),
+                                           None if start is None else start.ctypes.data_as(dp), out.ctypes.data_as(dp)) == 0
+        return out
+
+    def interpolate(self, mode, x, y, v):
+        x, y, v = (np.ascontiguousarray(w, dtype=np.float64) for w in (x, y, v))
+        out = np.empty_like(v)
+        dp = C.POINTER(C.c_double)
+        assert self.lib.oracle_interpolate(C.c_int(mode), C.c_int(x.size), x.ctypes.data_as(dp), y.ctypes.data_as(dp),
+                                           C.c_int64(v.size), v.ctypes.data_as(dp), out.ctypes.data_as(dp)) == 0
+        return out
+
+    def table_lookup(self, rows, keys):
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        k = rows.shape[1] - 1
+        keys = np.ascontiguousarray(keys, dtype=np.float64).reshape(-1, k)
+        out = np.empty(keys.shape[0])
+        dp = C.POINTER(C.c_double)
+        assert self.lib.oracle_table_lookup(C.c_int(k), C.c_int64(rows.shape[0]), rows.ctypes.data_as(dp), C.c_int64(keys.shape[0]),
+                                            keys.ctypes.data_as(dp), out.ctypes.data_as(dp)) == 0
+        return out
+
     def tick_tock(self):
         buf = np.zeros(4096)
         n = self.lib.oracle_tick_tock(buf.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(buf.size))

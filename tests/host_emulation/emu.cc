@@ -22,6 +22,7 @@
 #include "../../microsimulation_b200/csrc/report.cuh"
 #include "../../microsimulation_b200/csrc/report_host.h"
 #include "../../microsimulation_b200/csrc/gsm.cuh"
+#include "../../microsimulation_b200/csrc/lookups.cuh"
 #include "../../microsimulation_b200/csrc/seqstream.cuh"
 #include "../../microsimulation_b200/csrc/summary.cuh"
 
@@ -676,6 +677,39 @@ int emu_gsm(const msim_gsm *m, int mode, int64_t n, const double *u, const doubl
     out[i] = mode == 0 ? gsm_randU(M, u[i], tentry ? tentry[i] : 0.0, idx, scale)
              : mode == 1 ? gsm_randU0(M, u[i], idx, scale) : gsm_eta(M, idx, u[i], false);
   }
+  return 0;
+}
+
+// the device's lookup functions (lookups.cuh) on the host; families and modes as in include/msim.h
+int emu_rpexp(int mode, int n_t, const double *h, const double *t, int64_t n, const double *a, const double *b, double *out) {
+  std::vector<double> Hi(n_t);
+  rpexp_cumulate(n_t, h, t, Hi.data());
+  Rpexp T = {n_t, Hi.data(), h, t};
+  for (int64_t i = 0; i < n; i++) {
+    int failed = 0;
+    out[i] = mode == 0 ? rpexp_rand(T, a[i], b ? b[i] : 0.0, &failed)
+             : mode == 1 ? rpexp_H(T, a[i]) : mode == 2 ? rpexp_h(T, a[i]) : mode == 3 ? rpexp_p(T, a[i], true) : rpexp_d(T, a[i]);
+    if (failed) return -3;
+  }
+  return 0;
+}
+int emu_rpexp_gamma(int mode, int n_t, double theta, const double *mu, const double *t, int64_t n, const double *a, const double *Z,
+                    const double *from, double *out) {
+  std::vector<double> H0(n_t);
+  rpexp_gamma_cumulate(n_t, theta, mu, t, H0.data());
+  RpexpGamma T = {n_t, theta, H0.data(), mu, t};
+  for (int64_t i = 0; i < n; i++)
+    out[i] = mode == 0 ? rpexp_gamma_rand(T, a[i], Z[i], from ? from[i] : 0.0)
+             : mode == 1 ? rpexp_gamma_H(T, a[i], Z[i]) : mode == 2 ? rpexp_gamma_h(T, a[i], Z[i]) : rpexp_gamma_p(T, a[i], Z[i], true);
+  return 0;
+}
+int emu_interpolate(int mode, int n_pts, const double *x, const double *y, int64_t n, const double *xfind, double *out) {
+  std::vector<double> slope(n_pts - 1);
+  for (int i = 0; i < n_pts - 1; i++) slope[i] = (y[i + 1] - y[i]) / (x[i + 1] - x[i]);
+  Interp T = {n_pts, x, y, slope.data()};
+  for (int64_t i = 0; i < n; i++)
+    out[i] = mode == 0 ? interp_approx(T, xfind[i]) : mode == 1 ? interp_step(T, xfind[i])
+             : mode == 2 ? interp_invert(T, xfind[i]) : interp_invert_decreasing(T, xfind[i]);
   return 0;
 }
 
