@@ -88,24 +88,32 @@ __global__ void __launch_bounds__(BLOCK) rng_uniforms_kernel(UniformsParams p) {
 
 // ---- Mersenne-Twister stream generation ----------------------------------
 // One block.  words[0..624) holds the current state; writes n_batches further
-// regenerations behind it (three barrier-separated waves each, seqstream.cuh).
+// regenerations behind it.  Seen as ONE sequence x[0], x[1], ... (x[624 b + k] =
+// word k of regeneration b) MT19937 is the recurrence
+//     x[n] = x[n-227] ^ twist(x[n-624], x[n-623]),
+// so 227 consecutive elements are independent of one another: each pass of
+// the loop produces 227 of them, reading only elements of earlier passes from
+// a 1024-word circular buffer in shared memory (writes of a pass land at least
+// 170 words away from anything it reads), with ONE barrier per pass.  The
+// stream is serial by nature — 227-wide is all the parallelism it has without
+// polynomial jump-ahead — which makes this kernel the bulk of the
+// sequential-stream models' time.
 __global__ void __launch_bounds__(256) mt_generate_kernel(uint32_t *words, int n_batches) {
-  __shared__ uint32_t mt[624];
+  __shared__ uint32_t x[1024];
   const int t = threadIdx.x;
-  for (int k = t; k < 624; k += 256) mt[k] = words[k];
+  for (int k = t; k < 624; k += 256) x[k] = words[k];
   __syncthreads();
-  for (int b = 1; b <= n_batches; b++) {
-#pragma unroll
-    for (int wave = 0; wave < 3; wave++) {
-      int kk = 0;
-      uint32_t v = 0;
-      bool act = mt_wave_value(mt, wave, t, &kk, &v);
-      __syncthreads();
-      if (act) mt[kk] = v;
-      __syncthreads();
+  const int64_t total = (int64_t)(n_batches + 1) * 624;
+  for (int64_t n = 624; n < total; n += 227) {
+    const int64_t i = n + t;
+    if (t < 227 && i < total) {
+      const uint32_t a = x[(i - 624) & 1023], b = x[(i - 623) & 1023], c = x[(i - 227) & 1023];
+      const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+      const uint32_t v = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      x[i & 1023] = v;
+      words[i] = v;
     }
-    uint32_t *dst = words + (size_t)b * 624;
-    for (int k = t; k < 624; k += 256) dst[k] = mt[k];
+    __syncthreads();
   }
 }
 
