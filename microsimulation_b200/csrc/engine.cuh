@@ -23,6 +23,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "mrg32k3a.cuh"
 #include "rmath.cuh"
 
@@ -38,10 +40,39 @@ MSIM_DEV int meta_kind(int m) { return (int)(int16_t)((uint32_t)m & 0xffffu); }
 MSIM_DEV int meta_prio(int m) { return (int)(((uint32_t)m >> 16) & 0x3fffu) - 8192; }
 MSIM_DEV int meta_type(int m) { return (int)((uint32_t)m >> 30); }
 
+// Storage of the generic heap: CAP > 4 keeps the entries in the thread's own
+// arrays (local memory); CAP < 0 means -CAP entries in memory the caller binds
+// (shared memory: slot k of this thread at base[k * stride]), which the
+// calibration model uses — its 12 pending actions in local memory were that
+// kernel's top stall.
 template <int CAP>
-struct EventHeap {
-  double t[CAP];
-  int meta[CAP];
+struct HeapStore {
+  double t_[CAP];
+  int m_[CAP];
+  static constexpr int capacity = CAP;
+  MSIM_DEV double &T(int k) { return t_[k]; }
+  MSIM_DEV int &M(int k) { return m_[k]; }
+};
+template <int CAP>
+struct HeapStoreBound {
+  double *t_;
+  int *m_;
+  int stride_;
+  static constexpr int capacity = CAP;
+  MSIM_DEV void bind(double *t, int *m, int stride) {
+    t_ = t;
+    m_ = m;
+    stride_ = stride;
+  }
+  MSIM_DEV double &T(int k) { return t_[k * stride_]; }
+  MSIM_DEV int &M(int k) { return m_[k * stride_]; }
+};
+
+template <int CAP>
+struct EventHeap : std::conditional<(CAP > 0), HeapStore<(CAP > 0 ? CAP : 1)>, HeapStoreBound<(CAP > 0 ? 1 : -CAP)> >::type {
+  typedef typename std::conditional<(CAP > 0), HeapStore<(CAP > 0 ? CAP : 1)>, HeapStoreBound<(CAP > 0 ? 1 : -CAP)> >::type Store;
+  using Store::M;
+  using Store::T;
   int n;
 
   MSIM_DEV bool before(double ta, int ma, double tb, int mb) const {
@@ -50,40 +81,40 @@ struct EventHeap {
 
   // heap.h:75-88
   MSIM_DEV bool insert(double time, int m) {
-    if (n >= CAP) return false;
+    if (n >= Store::capacity) return false;
     int k = n++;
     while (k > 0) {
       int up = (k - 1) >> 1;
-      double tu = t[up];
-      int mu = meta[up];
+      double tu = T(up);
+      int mu = M(up);
       if (!before(time, m, tu, mu)) break;
-      t[k] = tu;
-      meta[k] = mu;
+      T(k) = tu;
+      M(k) = mu;
       k = up;
     }
-    t[k] = time;
-    meta[k] = m;
+    T(k) = time;
+    M(k) = m;
     return true;
   }
 
   // heap.h:90-117 (caller guarantees n > 0)
   MSIM_DEV void pop_first(double &time, int &m) {
-    time = t[0];
-    m = meta[0];
+    time = T(0);
+    m = M(0);
     int last = --n;  // index of the element that moves to the root
     if (last == 0) return;
-    double tx = t[last];
-    int mx = meta[last];
+    double tx = T(last);
+    int mx = M(last);
     last--;  // new last valid index
     int k = 0;
     for (;;) {
       int c = 2 * k + 1;
       if (c > last) break;
-      double tc = t[c];
-      int mc = meta[c];
+      double tc = T(c);
+      int mc = M(c);
       if (c + 1 <= last) {
-        double tr = t[c + 1];
-        int mr = meta[c + 1];
+        double tr = T(c + 1);
+        int mr = M(c + 1);
         if (before(tr, mr, tc, mc)) {
           c = c + 1;
           tc = tr;
@@ -91,18 +122,18 @@ struct EventHeap {
         }
       }
       if (!before(tc, mc, tx, mx)) break;
-      t[k] = tc;
-      meta[k] = mc;
+      T(k) = tc;
+      M(k) = mc;
       k = c;
     }
-    t[k] = tx;
-    meta[k] = mx;
+    T(k) = tx;
+    M(k) = mx;
   }
 
   // visit the pending entries in array order (Sim::ignore_event's scan)
   template <class F>
   MSIM_DEV void for_each_meta(F f) {
-    for (int i = 0; i < n; i++) f(meta[i]);
+    for (int i = 0; i < n; i++) f(M(i));
   }
 };
 

@@ -593,6 +593,9 @@ struct CalibEnv {
   typedef MrgSource Src;
   Src src;
   int *s_occ;     // [4][10]
+  double *heap_t;  // this thread's event-heap slots in shared memory: slot k at heap_t[k * heap_stride]
+  int *heap_m;
+  int heap_stride;
   double tar[4];  // per-thread TimeAtRisk partial sums
   int tar_n;      // 1 + largest TimeAtRisk index this thread touched
   __device__ __forceinline__ void occupancy(int stage, int cind) {
@@ -611,6 +614,8 @@ struct CalibEnv {
 // (common random numbers, R/calibSim.R:12-14 with one seed for all sets).
 __global__ void __launch_bounds__(BLOCK) calib_kernel(CalibParams p) {
   __shared__ int s_occ[40];
+  __shared__ double s_heap_t[calib::HEAP_SLOTS * BLOCK];  // 28 KB + 14 KB: every thread's heap slots
+  __shared__ int s_heap_m[calib::HEAP_SLOTS * BLOCK];
   __shared__ double s_tar[WARPS][4];
   __shared__ int s_tar_n;
   __shared__ int s_error;
@@ -634,6 +639,9 @@ __global__ void __launch_bounds__(BLOCK) calib_kernel(CalibParams p) {
 
   CalibEnv env;
   env.s_occ = s_occ;
+  env.heap_t = s_heap_t + tid;
+  env.heap_m = s_heap_m + tid;
+  env.heap_stride = BLOCK;
   env.tar[0] = env.tar[1] = env.tar[2] = env.tar[3] = 0.0;
   env.tar_n = 0;
 

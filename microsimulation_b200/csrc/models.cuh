@@ -140,7 +140,8 @@ namespace calib {
 
 enum stage_t { DiseaseFree, Precursor, PreClinical, Clinical, Death };
 enum event_t { toPrecursor, toPreClinical, toClinical, toDeath, Count };
-constexpr int HEAP_CAP = 16;  // ten Count events + toPrecursor + toDeath (+ successors)
+constexpr int HEAP_SLOTS = 14;  // at most 12 pending: ten Count events + toPrecursor (or its successor) + toDeath
+constexpr int HEAP_CAP = -HEAP_SLOTS;  // negative: the slots live in memory the environment provides (engine.cuh)
 
 struct Par {
   double Lam1, sigm1, p2, lam2, mu3, tau3;
@@ -160,7 +161,9 @@ struct CalibPerson : cProcess<CalibPerson<Env>, typename Env::Src, HEAP_CAP> {
   Env &env;
   const Par &P;
 
-  MSIM_DEV CalibPerson(Env &e, const Par &p) : Base(&e.src), stage(DiseaseFree), diseasepot(false), clinTime(1000), env(e), P(p) {}
+  MSIM_DEV CalibPerson(Env &e, const Par &p) : Base(&e.src), stage(DiseaseFree), diseasepot(false), clinTime(1000), env(e), P(p) {
+    this->actions.bind(e.heap_t, e.heap_m, e.heap_stride);
+  }
 
   MSIM_DEV void init() {  // calibperson-r.cc:95-110
     if (R.runif(0, 1) < P.p2) diseasepot = true;

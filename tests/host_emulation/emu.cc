@@ -473,6 +473,11 @@ int emu_sequential(int model, int64_t n, double cure, double zsd, uint32_t state
 struct EmuCalibEnv {
   typedef MrgSource Src;
   Src src;
+  double heap_store_t[calib::HEAP_SLOTS];
+  int heap_store_m[calib::HEAP_SLOTS];
+  double *heap_t = heap_store_t;
+  int *heap_m = heap_store_m;
+  int heap_stride = 1;
   double occ[40];
   double tar[4];
   int tar_n;
