@@ -394,7 +394,7 @@ int emu_person_run_staged(const msim_person_shard *sh, int grid, msim_table *row
         break;
       }
       if (q1.size() >= 64 || q2.size() >= 64) return -99;  // the kernel's queues hold 64
-      for (size_t l = 0; l < ready.size(); l++) person_r::run_life(env, K, sh->first_person + ready[l].idx, ready[l].p, &err);
+      for (size_t l = 0; l < ready.size(); l++) person_r::run_life<false>(env, K, sh->first_person + ready[l].idx, ready[l].p, &err);
     }
   }
   if (err) return err;
