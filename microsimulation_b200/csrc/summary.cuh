@@ -161,6 +161,21 @@ MSIM_DEV double summary_point_cost(const SummaryGeom &g, Acc &acc, int state, do
   return v;
 }
 
+// CostReport::add(state, time, cost) (microsimulation.h:1265-1278): a point cost discounted as cost/(1+rate)^time
+// (pow, not the exp form SummaryReport uses) into the bin of `time`.  Returns what the reference adds to the
+// individual's running total `current` (discounted from startReportAge on).  Uses the cost cells of a SummaryGeom.
+template <class Acc>
+MSIM_DEV double cost_report_add(const SummaryGeom &g, Acc &acc, int state, double time, double cost, double rate,
+                                double startReportAge) {
+  const double c = (rate == 0.0) ? cost : cost / pow(1 + rate, time);
+  const int b = summary_bin(g, time);
+  acc.addf(g.off_cost + state * g.n_bin + b, c);
+  acc.addi(g.off_pcn + state * g.n_bin + b, 1);
+  if (startReportAge == 0.0) return c;
+  if (time >= startReportAge) return (rate == 0.0) ? cost : cost / pow(1 + rate, time - startReportAge);
+  return 0.0;
+}
+
 // The free functions models use for their own running totals (microsimulation.h:811-836; e.g. the
 // illness-death doc example, inst/doc/examples.org:300-336): integral of y*(1+rate)^(-u) over [start, end],
 // and y/(1+rate)^time.  Written with pow, as the reference writes them.

@@ -13,6 +13,7 @@
 #include "models.h"
 #include "gsm_lite.h"
 #include "lookups_lite.h"
+#include "reports_lite.h"
 
 using namespace orc;
 
@@ -324,6 +325,22 @@ int oracle_bs_eval(const msim_gsm *m, int term, int64_t n, const double *x, int 
     for (size_t k = 0; k < v.size(); k++) out[i * v.size() + k] = v[k];
   }
   return 0;
+}
+
+// CostReport (reports_lite.h): n point costs; rows (state, age, cost) in key order; returns the row count
+int oracle_cost_report(double rate, double start_age, double p_start, double p_finish, double p_delta, int64_t n, const int *state,
+                       const double *time, const double *cost, double *out_rows, int64_t cap, double *current) {
+  ssim::CostReport<short> rep(rate, start_age);
+  rep.setPartition(p_start, p_finish, p_delta);
+  for (int64_t i = 0; i < n; i++) rep.add((short)state[i], time[i], cost[i]);
+  *current = rep.current;
+  int64_t k = 0;
+  for (auto it = rep._table.begin(); it != rep._table.end() && k < cap; ++it, ++k) {
+    out_rows[3 * k] = it->first.first;
+    out_rows[3 * k + 1] = it->first.second;
+    out_rows[3 * k + 2] = it->second;
+  }
+  return (int)k;
 }
 
 // ---- survival-time utilities and lookup tables (lookups_lite.h); modes as in include/msim.h

@@ -718,6 +718,30 @@ int emu_interpolate(int mode, int n_pts, const double *x, const double *y, int64
   return 0;
 }
 
+// CostReport: n point costs (state, time, cost) into a report over setPartition(start, finish, delta); out_rows gets
+// (state, age, cost) per non-empty cell in key order, *current the individual's running total
+int emu_cost_report(double rate, double start_age, double p_start, double p_finish, double p_delta, int64_t n, const int *state,
+                    const double *time, const double *cost, double *out_rows, int64_t cap, double *current) {
+  SummaryGeom G;
+  if (!make_summary_geom(&G, 8, 1, p_start, p_finish, p_delta, 1.0e100, 0.0, rate)) return -1;
+  std::vector<double> dense(G.total, 0.0);
+  PlainAcc acc;
+  acc.d = dense.data();
+  double cur = 0.0;
+  for (int64_t i = 0; i < n; i++) cur += cost_report_add(G, acc, state[i], time[i], cost[i], rate, start_age);
+  *current = cur;
+  int64_t k = 0;
+  for (int s = 0; s < G.n_state; s++)
+    for (int b = 0; b < G.n_bin; b++)
+      if (dense[G.off_pcn + s * G.n_bin + b] > 0 && k < cap) {
+        out_rows[3 * k] = s;
+        out_rows[3 * k + 1] = G.part[b];
+        out_rows[3 * k + 2] = dense[G.off_cost + s * G.n_bin + b];
+        k++;
+      }
+  return (int)k;
+}
+
 void emu_mt_set_seed(uint32_t seed, uint32_t state[625]) {
   HostRngState r;
   r.mt_set_seed(seed);

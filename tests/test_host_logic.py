@@ -220,3 +220,26 @@ def test_emulated_sick_sicker_summary_report(oracle, emu, n, trt, indivp, substr
     np.testing.assert_allclose(e["indiv"]["utilities"], ref["indiv"]["utilities"], rtol=1e-12)
     np.testing.assert_allclose(e["indiv"]["costs"], ref["indiv"]["costs"], rtol=1e-12)
     emu.emu_report_free(C.byref(r))
+
+
+@pytest.mark.parametrize("rate,start_age", [(0.0, 0.0), (0.03, 0.0), (0.05, 50.0)])
+def test_emulated_cost_report(oracle, emu, rate, start_age):
+    """CostReport::add (microsimulation.h:1265-1278) on the SummaryReport cost cells vs the restated class."""
+    rs = np.random.RandomState(9)
+    n = 3000
+    state = rs.randint(0, 4, n).astype(np.int32)
+    time_ = np.r_[rs.uniform(0, 110, n - 3), [0.0, 50.0, 100.0]]
+    cost = rs.uniform(10, 5000, n)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    outs = []
+    for lib, fn in ((emu, "emu_cost_report"), (oracle.lib, "oracle_cost_report")):
+        rows, cur = np.zeros(3 * 2000), C.c_double()
+        k = getattr(lib, fn)(C.c_double(rate), C.c_double(start_age), C.c_double(0.0), C.c_double(100.0), C.c_double(1.0),
+                             C.c_int64(n), state.ctypes.data_as(ip), time_.ctypes.data_as(dp), cost.ctypes.data_as(dp),
+                             rows.ctypes.data_as(dp), C.c_int64(2000), C.byref(cur))
+        assert k > 0
+        outs.append((rows[:3 * k].reshape(k, 3), cur.value))
+    (a, ca), (b, cb) = outs
+    assert a.shape == b.shape and np.array_equal(a[:, :2], b[:, :2])
+    np.testing.assert_allclose(a[:, 2], b[:, 2], rtol=1e-13)
+    assert abs(ca - cb) <= 1e-12 * abs(cb)
