@@ -374,13 +374,14 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
       // ---- stage A: 32 new persons
       const int64_t i64 = tile * 32 + lane;
       idx = (uint32_t)i64;
+      // the jump to the lane's NEXT person first, while the warp is together (placed after the draws, whose loops
+      // diverge, its 18 modular multiplications ran in fragments of 6-8 lanes)
+      env.src.g = sub;
+      sub.jump(p.st.stride);
       if (i64 < p.n) {
-        env.src.g = sub;
         ready = person_r::stage_a(env, &po, &life);
         park1 = !ready;
       }
-      __syncwarp();  // the draws diverge (exp_rand's loops): reconverge before the 18 modular multiplications of the jump
-      sub.jump(p.st.stride);
       tile += GW;
     } else {
       break;
