@@ -10,13 +10,15 @@
 //
 // How.  A person's life is cut at the two points where it may need the
 // expensive arithmetic, and persons that reach a cut are parked, with their
-// RngStream state, in a per-warp queue in shared memory.  A warp runs
-//   stage A   on 32 NEW persons (all lanes): substream jump, init()'s draws;
-//             persons without an onset draw finish here (single toDeath event);
-//   stage B1  whenever >= 32 persons wait for their onset time: log + pow on
-//             all lanes; persons who die before onset finish here;
-//   stage B2  whenever >= 32 persons wait with onset before death: the event
-//             loop (Sim::run_simulation's, engine.cuh) from just after A_Init.
+// RngStream state, in a per-warp queue in shared memory.  Each pass of a
+// warp's loop runs ONE stage on up to 32 persons —
+//   stage A   32 NEW persons (all lanes): substream jump, init()'s draws;
+//             persons without an onset draw are ready (a single toDeath event);
+//   stage B1  when >= 32 persons wait for their onset time: log + pow on all
+//             lanes; persons who die before onset are ready;
+//   stage B2  when >= 32 persons wait with onset before death: ready;
+// — and then, in ONE place for all stages (run_life), the ready persons run
+// the event loop (Sim::run_simulation's, engine.cuh) from just after A_Init.
 // No block-level synchronisation is involved: queues are per warp, and pushes
 // and pops are warp ballots.  Every draw a person takes, and the order it takes
 // them in, is the reference's; only WHEN the arithmetic happens moves.  A person's
@@ -162,9 +164,9 @@ struct StagedParams {
 // slices afterwards, in a fixed order.  (All blocks accumulating into ONE
 // global vector: 38 ms per 1e8 persons, a few hundred hot cells serialise in
 // L2.)
-// red.shared.add.s32: one instruction, no return value.  (Written in PTX because the compiler turns some
-// atomicAdd calls on shared memory into a loop that groups the lanes by address first — up to 32 passes when the
-// addresses differ, as they do here — which made the report kernel 50% slower.)
+// red.shared.add.s32: one instruction, no return value.  (Written in PTX: the compiler turns some atomicAdd calls
+// on shared memory into a loop that groups the lanes by address first — up to 32 passes when the addresses differ,
+// as they do here.)
 __device__ __forceinline__ void red_shared_add(int *ptr, int v) {
   asm volatile("red.shared.add.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(ptr)), "r"(v) : "memory");
 }
