@@ -71,6 +71,8 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
   int64_t gmax = (int64_t)per_sm * g.sm_count;
   if (gmax > JUMP_TAB * (int64_t)JUMP_TAB / SBLOCK) gmax = JUMP_TAB * (int64_t)JUMP_TAB / SBLOCK;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(gmax, (tiles + SWARPS - 1) / SWARPS));
+  // a lane tallies event kinds in 16-bit fields (person_staged.cuh): at most 65535 persons per lane
+  if (sh->n / ((int64_t)grid * SBLOCK) >= 65000) return fail(MSIM_ERR_ARG, "shard too large for this device: split it");
   uint32_t state[6];
   seed_to_u32(sh->seed, state);
   stream_start(state, sh->first_person, (int64_t)grid * SBLOCK, &p.st);
