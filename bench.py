@@ -110,7 +110,7 @@ def run_reference_arm(args):
                        "seed": "12345x6"},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(w):
@@ -340,12 +340,35 @@ def run_ours(args):
         line["other_workload"] = {"workload": workload_name(other_name), "value": other["value"], "unit": UNIT,
                                   "ms_per_step": other["ms_per_step"], "e2e": other["e2e"], "gpu_launches": other["launches"],
                                   "rows_per_step_rank0": other["rows"], "roofline": roofline_of(other_name, other, P)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """stdout carries ONE line, the JSON: whatever libraries print there (NCCL's version banner, ...) goes to
+    stderr instead.  The JSON is written to the saved descriptor by emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        sys.stdout.buffer.write(data)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
