@@ -113,6 +113,11 @@ int msim_r_next_rng_substream(void);
 /* src/microsimulation.cc:65-75: seed <- seed advanced by *n substreams
  * (side effect kept: it constructs an RngStream, advancing the package seed). */
 int msim_r_rng_advance_substream(double seed[6], const int *n);
+/* src/microsimulation.cc:77-85 — the hook R resolves BY NAME (`user_unif_rand`)
+ * under RNGkind("user"): one U01 draw of the default stream, on the host (it
+ * serves R-level runif() between simulations; the models never call it).
+ * NULL if no stream exists, as in the reference. */
+double *msim_user_unif_rand(void);
 
 /* R's own generator, which the wrappers select with
  * RNGkind("Mersenne-Twister"); set.seed(12345) before the .Call

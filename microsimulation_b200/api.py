@@ -81,6 +81,19 @@ def next_user_random_substream():
     check(load().msim_r_next_rng_substream())
 
 
+def user_unif_rand(n=1):
+    """n draws of the hook R calls under RNGkind("user") (src/microsimulation.cc:77-85): runif(n) there."""
+    _ensure_stream()
+    L = load()
+    out = np.empty(int(n))
+    for i in range(int(n)):
+        p = L.msim_user_unif_rand()
+        if not p:
+            raise RuntimeError(L.msim_last_error().decode())
+        out[i] = p[0]
+    return out
+
+
 def advance_substream(seed, n):
     s = (C.c_double * 6)(*_seed6(seed))
     nn = C.c_int(int(n))

@@ -154,6 +154,16 @@ int msim_r_rng_advance_substream(double seed[6], const int *n) {
   return MSIM_OK;
 }
 
+double *msim_user_unif_rand(void) {
+  static double rn;
+  if (!g.rng.have_default) {
+    fail(MSIM_ERR_STATE, "user_unif_rand(): no stream created yet");
+    return nullptr;
+  }
+  rn = g.rng.default_stream.Cg.u01();
+  return &rn;
+}
+
 int msim_mt_set_state(const uint32_t state[625]) {
   if (state[0] < 1 || state[0] > 624) return fail(MSIM_ERR_ARG, "MT position must be in 1..624");
   memcpy(g.rng.mt, state, sizeof g.rng.mt);

@@ -67,6 +67,24 @@ def test_host_rng_state_machine_matches_oracle(oracle):
     assert e.value.code == -5
 
 
+def test_user_unif_rand_hook_matches_oracle(oracle):
+    """`user_unif_rand` (src/microsimulation.cc:77-85): R-level runif() under RNGkind("user") draws from the default
+    stream; next.user.Random.substream() moves it to the next substream."""
+    import microsimulation_b200 as m
+    m.set_user_random_seed(12345)
+    want = oracle.rng_uniforms(12345, 0, 3, 7)
+    assert np.array_equal(m.user_unif_rand(7), want[0])
+    assert abs(want[0][0] - 0.1270111) < 1e-7  # the RngStream paper's first value for seed 12345 x 6
+    m.next_user_random_substream()
+    assert np.array_equal(m.user_unif_rand(5), want[1][:5])
+    m.next_user_random_substream()
+    assert np.array_equal(m.user_unif_rand(7), want[2])
+    seed_after = m.user_random_seed()[1:]   # the state moved with the draws (r_get_user_random_seed returns Cg)
+    m.set_user_random_seed(seed_after)
+    oracle_after = oracle.rng_uniforms(seed_after, 0, 1, 2)[0]
+    assert np.array_equal(m.user_unif_rand(2), oracle_after)
+
+
 def test_mt_set_seed_matches_oracle(oracle, emu):
     import microsimulation_b200 as m
     m.set_seed(12345)
