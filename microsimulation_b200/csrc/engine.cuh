@@ -281,10 +281,7 @@ struct cProcess {
   // create_process pushes A_Init at t = 0 into an empty heap, so the first
   // pop is always that action: initialize() runs first (microsimulation.h:430).
   MSIM_DEV void run() {
-    Derived *self = static_cast<Derived *>(this);
-    running_ = true;
-    self->init();
-    previousEventTime = startTime;
+    begin();
     loop();
   }
 
@@ -298,24 +295,41 @@ struct cProcess {
 
   // Sim::run_simulation's pop/dispatch loop (ssim.cc:162-232)
   MSIM_DEV void loop() {
+    if (alive())
+      while (step()) {
+      }
+    running_ = false;
+  }
+
+  // The same loop in pieces, for schedulers that interleave persons: begin() is everything up
+  // to the loop's first test after A_Init, alive() that test, step() one pass (one pop; an event is dispatched unless
+  // the action is ignored or the process has terminated) followed by the test for the next pass.
+  MSIM_DEV void begin() {
     Derived *self = static_cast<Derived *>(this);
-    while (running_ && actions.n > 0) {
-      double t;
-      int m;
-      actions.pop_first(t, m);
-      int type = meta_type(m);
-      if (type == A_Ignore) continue;  // clock untouched (ssim.cc:171-175)
+    running_ = true;
+    self->init();
+    previousEventTime = startTime;
+  }
+  MSIM_DEV bool alive() const { return running_ && actions.n > 0; }
+  MSIM_DEV bool step() {  // requires alive()
+    Derived *self = static_cast<Derived *>(this);
+    double t;
+    int m;
+    actions.pop_first(t, m);
+    int type = meta_type(m);
+    if (type != A_Ignore) {  // an ignored action leaves the clock untouched (ssim.cc:171-175)
       clock_ = t;
-      if (terminated_) continue;  // drained (ssim.cc:189-192)
-      if (type == A_Event) {
-        self->handleMessage(meta_kind(m));
-        previousEventTime = clock_;  // microsimulation.h:441
-      } else {                       // A_Stop
-        self->stop();
-        terminated_ = true;
+      if (!terminated_) {  // else drained (ssim.cc:189-192)
+        if (type == A_Event) {
+          self->handleMessage(meta_kind(m));
+          previousEventTime = clock_;  // microsimulation.h:441
+        } else {                       // A_Stop
+          self->stop();
+          terminated_ = true;
+        }
       }
     }
-    running_ = false;
+    return alive();
   }
 };
 
