@@ -89,8 +89,11 @@ int64_t msim_launch_count(void);
 /* Which GPU schedule the person-r entry points use: 0 (default) = staged
  * (persons are regrouped between stages so that warps stay full,
  * csrc/person_staged.cuh), 1 = generic (one person per thread straight
- * through, the kernel every other model uses).  Same results either way; the
- * switch exists so tests can check exactly that. */
+ * through, the kernel every other model uses).  The calibration model keeps its
+ * pending actions in an ordered array under 0 (a run in which two pending
+ * actions compared equal is repeated with the heap) and in heap.h's binary heap
+ * under 1.  Same results either way; the switch exists so tests can check
+ * exactly that.  2 = 0 with the repeat taken unconditionally (tests). */
 int msim_set_person_schedule(int which);
 /* Sizing of the person-r row-log buffers: expected rows per person (default
  * 1.25; the model logs 1.232) and expected rows beyond a person's first

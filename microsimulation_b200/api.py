@@ -51,8 +51,10 @@ def set_stream(cuda_stream=None):
 
 
 def set_person_schedule(which):
-    """0 / "staged" (default) or 1 / "generic": which GPU schedule runs person-r (same results)."""
-    which = {"staged": 0, "generic": 1}.get(which, which)
+    """0 / "staged" (default) or 1 / "generic": which GPU schedule runs person-r, and whether the calibration model
+    keeps its pending actions in an ordered array (0) or the binary heap (1).  Same results either way.  2 / "repeat"
+    is 0 with the repeat paths forced (tests)."""
+    which = {"staged": 0, "generic": 1, "repeat": 2}.get(which, which)
     check(load().msim_set_person_schedule(C.c_int(int(which))))
 
 

@@ -74,7 +74,9 @@ struct EventHeap : std::conditional<(CAP > 0), HeapStore<(CAP > 0 ? CAP : 1)>, H
   using Store::M;
   using Store::T;
   int n;
+  static constexpr bool tie = false;  // ties resolve as in heap.h: nothing to report
 
+  MSIM_DEV void reset() { n = 0; }
   MSIM_DEV bool before(double ta, int ma, double tb, int mb) const {
     return ta < tb || (ta == tb && meta_prio(ma) < meta_prio(mb));  // ssim.cc:60-62
   }
@@ -147,6 +149,9 @@ struct EventHeap<4> {
   double t0, t1, t2, t3;
   int m0, m1, m2, m3;
   int n;
+  static constexpr bool tie = false;
+
+  MSIM_DEV void reset() { n = 0; }
 
   MSIM_DEV static bool before(double ta, int ma, double tb, int mb) {
     return ta < tb || (ta == tb && meta_prio(ma) < meta_prio(mb));
@@ -218,11 +223,73 @@ struct EventHeap<4> {
   }
 };
 
+// The pending-event set as an ORDERED array, for models that keep many actions pending (the calibration model: 12).
+// Popping the minimum is then a load (the binary heap's sift-down over 12 entries was 44% of that kernel's
+// instructions).  It pops in exactly the heap's order as long as no two pending actions compare equal — neither
+// before the other in (time, priority): then the minimum is unique at every pop, whatever the data structure.  Where
+// two do compare equal, heap.h's order depends on the heap's shape, which this queue does not model: it sets `tie`
+// instead, and the caller repeats the run with EventHeap (host side: msim_calibration_sweep).  Event times are
+// continuous draws, so this essentially never happens; exactness does not rest on that.
+// Entries live in caller-bound memory, ascending in [head, tail); insertion scans from the late end.
+template <int CAP>
+struct OrderedEvents : HeapStoreBound<CAP> {
+  typedef HeapStoreBound<CAP> Store;
+  using Store::M;
+  using Store::T;
+  int n, head, tail;
+  bool tie;
+
+  MSIM_DEV void reset() {
+    n = head = tail = 0;
+    tie = false;
+  }
+  MSIM_DEV static bool before(double ta, int ma, double tb, int mb) {
+    return ta < tb || (ta == tb && meta_prio(ma) < meta_prio(mb));  // ssim.cc:60-62
+  }
+  MSIM_DEV bool insert(double time, int m) {
+    if (tail == CAP) {
+      if (head == 0) return false;
+      for (int i = 0; i < n; i++) {  // make room at the late end
+        T(i) = T(head + i);
+        M(i) = M(head + i);
+      }
+      head = 0;
+      tail = n;
+    }
+    int k = tail++;
+    n++;
+    while (k > head) {
+      const double tu = T(k - 1);
+      const int mu = M(k - 1);
+      if (!before(time, m, tu, mu)) {
+        if (!before(tu, mu, time, m)) tie = true;
+        break;
+      }
+      T(k) = tu;
+      M(k) = mu;
+      k--;
+    }
+    T(k) = time;
+    M(k) = m;
+    return true;
+  }
+  MSIM_DEV void pop_first(double &time, int &m) {  // caller guarantees n > 0
+    time = T(head);
+    m = M(head);
+    head++;
+    n--;
+  }
+  template <class F>
+  MSIM_DEV void for_each_meta(F f) {
+    for (int i = head; i < tail; i++) f(M(i));
+  }
+};
+
 // CRTP base: `struct Person : cProcess<Person, Src, 4> { void init(); void
 // handleMessage(int kind); }`.  Handler bodies read like the reference's.
-template <class Derived, class Src, int CAP>
+template <class Derived, class Src, int CAP, class Actions = EventHeap<CAP> >
 struct cProcess {
-  EventHeap<CAP> actions;
+  Actions actions;
   double clock_;
   double startTime, previousEventTime;
   bool running_, terminated_;
@@ -230,7 +297,7 @@ struct cProcess {
   RMath<Src> R;
 
   MSIM_DEV explicit cProcess(Src *src) : R(src) {
-    actions.n = 0;
+    actions.reset();
     clock_ = 0.0;
     startTime = previousEventTime = 0.0;
     running_ = false;

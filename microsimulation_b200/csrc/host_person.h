@@ -156,7 +156,7 @@ int person_enqueue(const msim_person_shard *sh, int64_t capacity_override, int64
   const int64_t capacity = capacity_override > 0 ? capacity_override : rowlog_capacity_guess(sh->n, person_r::MAX_ROWS, g.plan_rows);
   g.want_capacity = capacity;
   g.last_simple_names = false;
-  if (g.person_kernel == 0) return person_enqueue_staged(sh, capacity, ov_cap_override);
+  if (g.person_kernel != 1) return person_enqueue_staged(sh, capacity, ov_cap_override);
   CohortParams<person_r::Consts> p;
   memset(&p, 0, sizeof p);
   p.first_person = sh->first_person;

@@ -37,7 +37,7 @@ struct Ctx {
   cudaStream_t stream = nullptr, own_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
   MrgJump *d_lo = nullptr, *d_hi = nullptr;
-  DevBuf rowlog, prov_start, prov_end, prov_meta, tile_count, partial, dense, small, mt_words, len, starts, chain_exit, chain_count, chain_entry, chain_base, calib_out,
+  DevBuf rowlog, prov_start, prov_end, prov_meta, tile_count, partial, dense, small, mt_words, len, starts, chain_exit, chain_count, chain_entry, chain_base, calib_out, calib_partial,
       calib_par, uniforms, first_end, first_tag, ov_fill, ov_tag, ov_start, ov_end, aux, code_in, code_out, sgeom,
       indiv, gsm_model, gsm_data, gsm_in, gsm_out, slices;
   int person_kernel = 0;  // 0 = staged schedule (person_staged.cuh), 1 = generic cohort kernel

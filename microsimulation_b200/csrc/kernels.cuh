@@ -587,6 +587,8 @@ struct CalibParams {
   const double *runpar;  // [n_sets][6]
   double *out;           // [n_sets][48]: occupancy[4][10], TimeAtRisk[4], n_time_at_risk, pad
   int *error;
+  int *tie;              // set if two pending actions of a person compared equal (ORDERED only)
+  double *partial;       // [n_sets][gridDim.x][4]: every block's TimeAtRisk sums, added up in block order afterwards
 };
 
 struct CalibEnv {
@@ -612,6 +614,8 @@ struct CalibEnv {
 
 // grid = (blocks_x, n_sets): every parameter set sees the same substreams
 // (common random numbers, R/calibSim.R:12-14 with one seed for all sets).
+// ORDERED: the pending actions as an ordered array (engine.cuh, OrderedEvents); results are valid unless *p.tie is set
+template <bool ORDERED>
 __global__ void __launch_bounds__(BLOCK) calib_kernel(CalibParams p) {
   __shared__ int s_occ[40];
   __shared__ double s_heap_t[calib::HEAP_SLOTS * BLOCK];  // 28 KB + 14 KB: every thread's heap slots
@@ -651,14 +655,16 @@ __global__ void __launch_bounds__(BLOCK) calib_kernel(CalibParams p) {
   // without the __syncwarp, lanes whose person ends early run on into the substream jump and the next person on
   // their own and the warp never re-forms (6 of 32 lanes active, measured)
   const int64_t warp_first = (int64_t)blockIdx.x * BLOCK + (tid & ~31);
+  bool tie = false;
   for (int64_t base = warp_first; base < p.n; base += stride) {
     const int64_t idx = base + lane;
     __syncwarp();
     if (idx < p.n) {
       env.src.g = sub;
-      calib::CalibPerson<CalibEnv> person(env, par);
+      calib::CalibPerson<CalibEnv, ORDERED> person(env, par);
       person.run();
       if (person.error_) atomicCAS(&s_error, 0, person.error_);
+      if (person.actions.tie) tie = true;
     }
     __syncwarp();
     sub.jump(p.st.stride);
@@ -678,13 +684,24 @@ __global__ void __launch_bounds__(BLOCK) calib_kernel(CalibParams p) {
   if (tid < 4) {
     double t = 0;
     for (int w = 0; w < WARPS; w++) t += s_tar[w][tid];
-    if (t != 0.0) atomicAdd(&out[40 + tid], t);
+    p.partial[((size_t)set * gridDim.x + blockIdx.x) * 4 + tid] = t;  // no atomics: the sum must not depend on timing
   }
   if (tid == 0) {
     // max over blocks of a non-negative integer-valued double (bit order = value order)
     unsigned long long *cell = reinterpret_cast<unsigned long long *>(&out[44]);
     atomicMax(cell, (unsigned long long)__double_as_longlong((double)s_tar_n));
     if (s_error) atomicCAS(p.error, 0, s_error);
+  }
+  if (ORDERED && tie) *p.tie = 1;
+}
+
+// TimeAtRisk of every set: the blocks' sums in block order (one block per set, threads 0..3)
+__global__ void calib_fold_kernel(const double *partial, int blocks, double *out) {
+  if (threadIdx.x < 4) {
+    const double *q = partial + (size_t)blockIdx.x * blocks * 4 + threadIdx.x;
+    double t = 0.0;
+    for (int b = 0; b < blocks; b++) t += q[4 * b];
+    out[48 * (size_t)blockIdx.x + 40 + threadIdx.x] = t;
   }
 }
 

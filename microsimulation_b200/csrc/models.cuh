@@ -147,9 +147,12 @@ struct Par {
   double Lam1, sigm1, p2, lam2, mu3, tau3;
 };
 
-template <class Env>
-struct CalibPerson : cProcess<CalibPerson<Env>, typename Env::Src, HEAP_CAP> {
-  typedef cProcess<CalibPerson<Env>, typename Env::Src, HEAP_CAP> Base;
+// ORDERED: pending actions in an ordered array (engine.cuh, OrderedEvents) instead of the binary heap
+template <class Env, bool ORDERED = false>
+struct CalibPerson : cProcess<CalibPerson<Env, ORDERED>, typename Env::Src, HEAP_CAP,
+                              typename std::conditional<ORDERED, OrderedEvents<HEAP_SLOTS>, EventHeap<HEAP_CAP> >::type> {
+  typedef cProcess<CalibPerson<Env, ORDERED>, typename Env::Src, HEAP_CAP,
+                   typename std::conditional<ORDERED, OrderedEvents<HEAP_SLOTS>, EventHeap<HEAP_CAP> >::type> Base;
   using Base::now;
   using Base::R;
   using Base::scheduleAt;

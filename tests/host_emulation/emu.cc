@@ -263,6 +263,69 @@ struct HostSummaryEnv {
 };
 
 
+struct EmuCalibEnv {
+  typedef MrgSource Src;
+  Src src;
+  double heap_store_t[calib::HEAP_SLOTS];
+  int heap_store_m[calib::HEAP_SLOTS];
+  double *heap_t = heap_store_t;
+  int *heap_m = heap_store_m;
+  int heap_stride = 1;
+  double occ[40];
+  double tar[4];
+  int tar_n;
+  void occupancy(int stage, int cind) {
+    if (stage < 4) occ[stage * 10 + cind] += 1;
+  }
+  void time_at_risk(int i, double v) {
+    tar[i] += v;
+    if (i + 1 > tar_n) tar_n = i + 1;
+  }
+};
+
+// the pending-event set as the binary heap (ordered = 0) or as the ordered array (ordered = 1; *tie_out says whether
+// any person saw two pending actions compare equal, in which case the device repeats the run with the heap)
+template <bool ORDERED>
+static int emu_calibration_t(const double seed[6], int64_t first_person, int64_t n, const double runpar[6], int grid,
+                             msim_calibration *out, int *tie_out) {
+  StreamStart st;
+  make_start(seed, first_person + 1, grid, &st);
+  calib::Par par = {runpar[0], runpar[1], runpar[2], runpar[3], runpar[4], runpar[5]};
+  EmuCalibEnv env;
+  memset(env.occ, 0, sizeof env.occ);
+  memset(env.tar, 0, sizeof env.tar);
+  env.tar_n = 0;
+  // person order (the sums are order-dependent in the last bits; emulate the reference's order)
+  std::vector<Mrg32k3a> subs((size_t)n);
+  for (int blk = 0; blk < grid; blk++)
+    for (int tid = 0; tid < BLOCK; tid++) {
+      Mrg32k3a sub = thread_start_state(st, blk * BLOCK + tid);
+      for (int64_t idx = (int64_t)blk * BLOCK + tid; idx < n; idx += (int64_t)grid * BLOCK) {
+        subs[idx] = sub;
+        sub.jump(st.stride);
+      }
+    }
+  for (int64_t i = 0; i < n; i++) {
+    env.src.g = subs[i];
+    calib::CalibPerson<EmuCalibEnv, ORDERED> person(env, par);
+    person.run();
+    if (person.error_) return person.error_;
+    if (person.actions.tie) *tie_out = 1;
+  }
+  memset(out, 0, sizeof *out);
+  for (int s = 0; s < 4; s++) {
+    double tot = 0;
+    for (int k = 0; k < 10; k++) {
+      out->occupancy[s * 10 + k] = env.occ[s * 10 + k];
+      tot += env.occ[s * 10 + k];
+    }
+    out->present[s] = tot > 0;
+  }
+  out->n_time_at_risk = env.tar_n;
+  for (int k = 0; k < env.tar_n; k++) out->time_at_risk[k] = env.tar[k];
+  return 0;
+}
+
 extern "C" {
 
 int emu_rng_uniforms(const double seed[6], int64_t first_substream, int64_t n_substreams, int32_t draws, int grid,
@@ -470,63 +533,69 @@ int emu_sequential(int model, int64_t n, double cure, double zsd, uint32_t state
   return 0;
 }
 
-struct EmuCalibEnv {
-  typedef MrgSource Src;
-  Src src;
-  double heap_store_t[calib::HEAP_SLOTS];
-  int heap_store_m[calib::HEAP_SLOTS];
-  double *heap_t = heap_store_t;
-  int *heap_m = heap_store_m;
-  int heap_stride = 1;
-  double occ[40];
-  double tar[4];
-  int tar_n;
-  void occupancy(int stage, int cind) {
-    if (stage < 4) occ[stage * 10 + cind] += 1;
-  }
-  void time_at_risk(int i, double v) {
-    tar[i] += v;
-    if (i + 1 > tar_n) tar_n = i + 1;
-  }
-};
-
 int emu_calibration(const double seed[6], int64_t first_person, int64_t n, const double runpar[6], int grid,
                     msim_calibration *out) {
-  StreamStart st;
-  make_start(seed, first_person + 1, grid, &st);
-  calib::Par par = {runpar[0], runpar[1], runpar[2], runpar[3], runpar[4], runpar[5]};
-  EmuCalibEnv env;
-  memset(env.occ, 0, sizeof env.occ);
-  memset(env.tar, 0, sizeof env.tar);
-  env.tar_n = 0;
-  // person order (the sums are order-dependent in the last bits; emulate the reference's order)
-  std::vector<Mrg32k3a> subs((size_t)n);
-  for (int blk = 0; blk < grid; blk++)
-    for (int tid = 0; tid < BLOCK; tid++) {
-      Mrg32k3a sub = thread_start_state(st, blk * BLOCK + tid);
-      for (int64_t idx = (int64_t)blk * BLOCK + tid; idx < n; idx += (int64_t)grid * BLOCK) {
-        subs[idx] = sub;
-        sub.jump(st.stride);
-      }
+  int tie = 0;
+  return emu_calibration_t<false>(seed, first_person, n, runpar, grid, out, &tie);
+}
+int emu_calibration_ordered(const double seed[6], int64_t first_person, int64_t n, const double runpar[6], int grid,
+                            msim_calibration *out, int *tie_out) {
+  *tie_out = 0;
+  return emu_calibration_t<true>(seed, first_person, n, runpar, grid, out, tie_out);
+}
+
+// OrderedEvents against EventHeap on a random schedule/pop sequence (engine.cuh).  Times are drawn from `n_times`
+// distinct values and priorities from `n_prios`, so small values force pairs that compare equal.  Returns -1 if the
+// queue failed to flag such a pair (checked by brute force over the pending set at every insert), the number of pops
+// that differed from the heap's otherwise; *tie_out = the queue's flag at the end.
+int emu_ordered_vs_heap(uint32_t seed, int ops, int n_times, int n_prios, int *tie_out) {
+  constexpr int CAP = 14;
+  double ht[CAP], qt[CAP];
+  int hm[CAP], qm[CAP];
+  EventHeap<-CAP> heap;
+  OrderedEvents<CAP> queue;
+  heap.bind(ht, hm, 1);
+  queue.bind(qt, qm, 1);
+  heap.reset();
+  queue.reset();
+  std::vector<std::pair<double, int> > pending;
+  bool equal_pair = false;
+  int differ = 0;
+  uint32_t x = seed ? seed : 1u;
+  auto next = [&x]() {
+    x ^= x << 13;
+    x ^= x >> 17;
+    x ^= x << 5;
+    return x;
+  };
+  for (int i = 0; i < ops; i++) {
+    const bool push = heap.n == 0 || (heap.n < CAP && next() % 5 < 3);
+    if (push) {
+      const double t = (double)(next() % (uint32_t)n_times) * 0.25;
+      const int prio = (int)(next() % (uint32_t)n_prios) - 1;
+      const int m = pack_meta(A_Event, (int)(next() % 7), prio);
+      for (size_t k = 0; k < pending.size(); k++)
+        if (pending[k].first == t && meta_prio(pending[k].second) == prio) equal_pair = true;
+      pending.push_back(std::make_pair(t, m));
+      if (!heap.insert(t, m) || !queue.insert(t, m)) return -2;
+    } else {
+      double t1, t2;
+      int m1, m2;
+      heap.pop_first(t1, m1);
+      queue.pop_first(t2, m2);
+      if (t1 != t2 || m1 != m2) differ++;
+      for (size_t k = 0; k < pending.size(); k++)
+        if (pending[k].first == t1 && pending[k].second == m1) {
+          pending.erase(pending.begin() + (long)k);
+          break;
+        }
     }
-  for (int64_t i = 0; i < n; i++) {
-    env.src.g = subs[i];
-    calib::CalibPerson<EmuCalibEnv> person(env, par);
-    person.run();
-    if (person.error_) return person.error_;
+    if (heap.n != queue.n) return -3;
+    if (equal_pair && !queue.tie) return -1;
   }
-  memset(out, 0, sizeof *out);
-  for (int s = 0; s < 4; s++) {
-    double tot = 0;
-    for (int k = 0; k < 10; k++) {
-      out->occupancy[s * 10 + k] = env.occ[s * 10 + k];
-      tot += env.occ[s * 10 + k];
-    }
-    out->present[s] = tot > 0;
-  }
-  out->n_time_at_risk = env.tar_n;
-  for (int k = 0; k < env.tar_n; k++) out->time_at_risk[k] = env.tar[k];
-  return 0;
+  *tie_out = queue.tie ? 1 : 0;
+  if (!equal_pair && queue.tie) return -4;  // a false alarm costs a repeat, but there should be none
+  return differ;
 }
 
 // callSim (Sick-Sicker, SummaryReport) with the device's decomposition: a first pass for every person's last

@@ -324,6 +324,28 @@ def test_calibration_sweep_vs_oracle(msim, oracle):
                 assert np.array_equal(a[k], b[k]), k
 
 
+def test_calibration_event_queues_agree_bit_for_bit(msim):
+    """Ordered array (default), binary heap, and the repeat path (ordered, then the heap again): identical tables,
+    TimeAtRisk included (each thread adds the same persons in the same order)."""
+    rs = np.random.RandomState(11)
+    pars = np.array([4, 0.5, 0.05, 10, 3, 0.5]) * (1 + 0.4 * (rs.rand(16, 6) - 0.5))
+    runs = {}
+    try:
+        for sched in ("staged", "generic", "repeat"):
+            msim.set_person_schedule(sched)
+            runs[sched] = msim.calibration_sweep(12345, pars, 100000, first_person=77)
+            runs[sched + "_launches"] = msim.launch_count()
+    finally:
+        msim.set_person_schedule("staged")
+    assert runs["repeat_launches"] - runs["generic_launches"] == 4   # the ordered attempt and the heap repeat (+ folds)
+    assert runs["generic_launches"] - runs["staged_launches"] == 2
+    for other in ("generic", "repeat"):
+        for a, b in zip(runs["staged"], runs[other]):
+            assert set(a) == set(b)
+            for k in a:
+                assert np.array_equal(a[k], b[k]), (other, k)
+
+
 def test_calibration_config5_full_size_properties(msim):
     """BASELINE config 5 (256 parameter sets x 1e6 persons): properties that need no oracle run of that size."""
     import microsimulation_b200.api as api

@@ -208,6 +208,44 @@ def test_emulated_calibration(oracle, emu):
         assert np.array_equal(got[k], ref[k]), k
 
 
+def test_ordered_event_queue_pops_in_heap_order_or_says_so(emu):
+    """engine.cuh OrderedEvents: the heap's pop order whenever no two pending actions compare equal; where two do, the
+    `tie` flag (the device then repeats the run with the binary heap)."""
+    tie = C.c_int(0)
+    clean = 0
+    for seed in range(1, 41):
+        # many distinct times: equal pairs are rare; every pop must agree with the heap unless one was flagged
+        d = emu.emu_ordered_vs_heap(C.c_uint32(seed), 4000, 1 << 20, 3, C.byref(tie))
+        assert d >= 0, d
+        if not tie.value:
+            assert d == 0
+            clean += 1
+    assert clean >= 30
+    flagged = 0
+    for seed in range(1, 21):
+        # 6 times x 2 priorities: equal pairs all over; the queue must flag them (return -1 = one went unnoticed)
+        d = emu.emu_ordered_vs_heap(C.c_uint32(seed), 500, 6, 2, C.byref(tie))
+        assert d >= 0, d
+        flagged += tie.value
+    assert flagged == 20
+
+
+def test_emulated_calibration_ordered_queue(oracle, emu):
+    """The calibration model over the ordered queue: same tables as over the heap, no equal pair in thousands of lives."""
+    seed = (C.c_double * 6)(*[10.0] * 6)
+    tie = C.c_int(0)
+    for par, first, n in (((4, 0.5, 0.05, 10, 3, 0.5), 0, 3000), ((3, 0.8, 0.6, 4, 1, 0.9), 12345, 3000)):
+        a, b = Calibration(), Calibration()
+        p = (C.c_double * 6)(*par)
+        assert emu.emu_calibration(seed, C.c_int64(first), C.c_int64(n), p, C.c_int(2), C.byref(a)) == 0
+        assert emu.emu_calibration_ordered(seed, C.c_int64(first), C.c_int64(n), p, C.c_int(2), C.byref(b), C.byref(tie)) == 0
+        assert tie.value == 0
+        a, b = a.to_dict(), b.to_dict()
+        assert set(a) == set(b)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+
+
 @pytest.mark.parametrize("n,trt,indivp,substreams,by", [(5, 0, 1, 0, 1.0), (1000, 0, 1, 0, 1.0), (1000, 1, 1, 0, 1.0),
                                                         (700, 1, 0, 0, 1.0), (800, 0, 1, 1, 1.0), (0, 0, 1, 0, 1.0),
                                                         (600, 0, 1, 0, 0.5), (600, 1, 1, 0, 2.5)])
