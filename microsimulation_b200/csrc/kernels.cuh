@@ -603,12 +603,28 @@ struct CalibEnv {
   __device__ __forceinline__ void occupancy(int stage, int cind) {
     if (stage < 4) atomicAdd(&s_occ[stage * 10 + cind], 1);
   }
-  __device__ __forceinline__ void time_at_risk(int i, double v) {
-    if (i == 0) tar[0] += v;
-    else if (i == 1) tar[1] += v;
-    else if (i == 2) tar[2] += v;
-    else tar[3] += v;
-    if (i + 1 > tar_n) tar_n = i + 1;
+  double died_clin;  // clinTime of the person that died in the event loop just run, < 0 if nobody did
+  __device__ __forceinline__ void at_death(double clinTime) { died_clin = clinTime; }
+  // after the event loop, all lanes together
+  __device__ __forceinline__ void settle() {
+    if (died_clin >= 0.0) {
+      const double c = died_clin;
+      tar[0] += fmin(20.0, c);
+      int reached = 1;
+      if (!(c < 20.0)) {
+        tar[1] += fmin(40.0, c);
+        reached = 2;
+        if (!(c < 40.0)) {
+          tar[2] += fmin(60.0, c);
+          reached = 3;
+          if (!(c < 60.0)) {
+            tar[3] += fmin(80.0, c);
+            reached = 4;
+          }
+        }
+      }
+      if (reached > tar_n) tar_n = reached;
+    }
   }
 };
 
@@ -661,10 +677,12 @@ __global__ void __launch_bounds__(BLOCK) calib_kernel(CalibParams p) {
     __syncwarp();
     if (idx < p.n) {
       env.src.g = sub;
+      env.died_clin = -1.0;
       calib::CalibPerson<CalibEnv, ORDERED> person(env, par);
       person.run();
       if (person.error_) atomicCAS(&s_error, 0, person.error_);
       if (person.actions.tie) tie = true;
+      env.settle();  // = calib::time_at_risk_terms(), written out
     }
     __syncwarp();
     sub.jump(p.st.stride);

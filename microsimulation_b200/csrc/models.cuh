@@ -147,6 +147,18 @@ struct Par {
   double Lam1, sigm1, p2, lam2, mu3, tau3;
 };
 
+// The TimeAtRisk bookkeeping of the toDeath handler (calibperson-r.cc:124-135): f(i, min(ctime[i], clinTime)) for
+// i = 0.. until clinTime < ctime[i].  A person dies once, so an environment may run this after the event loop, where
+// the warp is together again (in the handler only the few lanes that die in the same pass are active).
+template <class F>
+MSIM_HD void time_at_risk_terms(double clinTime, F f) {
+  const double ctime[4] = {20, 40, 60, 80};
+  for (int i = 0; i < 4; i++) {
+    f(i, fmin(ctime[i], clinTime));
+    if (clinTime < ctime[i]) break;
+  }
+}
+
 // ORDERED: pending actions in an ordered array (engine.cuh, OrderedEvents) instead of the binary heap
 template <class Env, bool ORDERED = false>
 struct CalibPerson : cProcess<CalibPerson<Env, ORDERED>, typename Env::Src, HEAP_CAP,
@@ -184,11 +196,7 @@ struct CalibPerson : cProcess<CalibPerson<Env, ORDERED>, typename Env::Src, HEAP
     if (kind == toDeath) {
       stage = Death;
       clinTime = fmin(clinTime, now());
-      const double ctime[4] = {20, 40, 60, 80};
-      for (int i = 0; i < 4; i++) {
-        env.time_at_risk(i, fmin(ctime[i], clinTime));
-        if (clinTime < ctime[i]) break;
-      }
+      env.at_death(clinTime);  // TimeAtRisk: time_at_risk_terms(), run by the environment
       stop_simulation();
     } else if (kind == toPrecursor) {
       stage = Precursor;

@@ -277,9 +277,11 @@ struct EmuCalibEnv {
   void occupancy(int stage, int cind) {
     if (stage < 4) occ[stage * 10 + cind] += 1;
   }
-  void time_at_risk(int i, double v) {
-    tar[i] += v;
-    if (i + 1 > tar_n) tar_n = i + 1;
+  void at_death(double clinTime) {
+    calib::time_at_risk_terms(clinTime, [this](int i, double v) {
+      tar[i] += v;
+      if (i + 1 > tar_n) tar_n = i + 1;
+    });
   }
 };
 
