@@ -9,7 +9,7 @@ using namespace msim;
 // ---------------------------------------------------------------- cohort launch
 
 template <class Traits, bool STREAM>
-int cohort_grid(size_t smem, int64_t n, int *grid) {
+inline int cohort_grid(size_t smem, int64_t n, int *grid) {
   auto kern = cohort_kernel<Traits, STREAM>;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
@@ -24,7 +24,7 @@ int cohort_grid(size_t smem, int64_t n, int *grid) {
 
 // Allocates and zeroes the accumulators a run needs and fills the pointers in p.
 template <class Traits, bool STREAM>
-int cohort_prepare(CohortParams<typename Traits::Consts> &p, const uint32_t stream_state[6], int *grid_out,
+inline int cohort_prepare(CohortParams<typename Traits::Consts> &p, const uint32_t stream_state[6], int *grid_out,
                    size_t *smem_out) {
   int rc;
   size_t smem = cohort_kernel_smem<Traits>(p.geom, p.outputs);
@@ -64,7 +64,7 @@ int cohort_prepare(CohortParams<typename Traits::Consts> &p, const uint32_t stre
 }
 
 // second pass of the row log: tile counts -> offsets -> final columns
-int rowlog_expand(int64_t n, int64_t first_person, int max_rows, int64_t capacity) {
+inline int rowlog_expand(int64_t n, int64_t first_person, int max_rows, int64_t capacity) {
   ExpandParams e;
   memset(&e, 0, sizeof e);
   e.prov_start = (const double *)g.prov_start.p;
@@ -91,7 +91,7 @@ int rowlog_expand(int64_t n, int64_t first_person, int max_rows, int64_t capacit
 }
 
 template <class Traits, bool STREAM>
-int cohort_fire(CohortParams<typename Traits::Consts> &p, int grid, size_t smem, int64_t capacity) {
+inline int cohort_fire(CohortParams<typename Traits::Consts> &p, int grid, size_t smem, int64_t capacity) {
   if (p.n > 0) {
     cohort_kernel<Traits, STREAM><<<grid, BLOCK, smem, g.stream>>>(p);
     CK(cudaGetLastError());
@@ -112,7 +112,7 @@ int cohort_fire(CohortParams<typename Traits::Consts> &p, int grid, size_t smem,
   return MSIM_OK;
 }
 
-int finish_run(int64_t *n_rows_out) {
+inline int finish_run(int64_t *n_rows_out) {
   CK(cudaStreamSynchronize(g.stream));
   if (g.timing_pending) {
     CK(cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1));
@@ -131,13 +131,13 @@ int finish_run(int64_t *n_rows_out) {
   return MSIM_OK;
 }
 
-int64_t rowlog_capacity_guess(int64_t n, int max_rows, double mean_rows) {
+inline int64_t rowlog_capacity_guess(int64_t n, int max_rows, double mean_rows) {
   if (n <= 65536 && mean_rows >= 1.0) return n * max_rows + 1;
   int64_t c = (int64_t)((double)n * mean_rows) + (mean_rows >= 1.0 ? 65536 : 16);
   return std::min<int64_t>(c, n * max_rows + 1);
 }
 
-int fetch_rowlog(const char *const *cols, msim_table *out) {
+inline int fetch_rowlog(const char *const *cols, msim_table *out) {
   int64_t n = g.last_n_rows, cap = g.last_capacity;
   out->nrow = n;
   out->ncol = 5;
@@ -153,7 +153,7 @@ int fetch_rowlog(const char *const *cols, msim_table *out) {
   return MSIM_OK;
 }
 
-int fetch_report(msim_report *out) {
+inline int fetch_report(msim_report *out) {
   std::vector<double> d(g.last_geom.total);
   CK(cudaMemcpy(d.data(), g.dense.p, sizeof(double) * d.size(), cudaMemcpyDeviceToHost));
   dense_to_report_impl(d.data(), g.last_geom, out);
@@ -163,7 +163,7 @@ int fetch_report(msim_report *out) {
 // the guessed row capacity was too small: the packed rows are still there, expand again
 int staged_rowpasses(int64_t n, int64_t first_person, int64_t capacity, bool count_first);  // host_person.h
 
-int reexpand(int64_t rows) {
+inline int reexpand(int64_t rows) {
   int rc;
   if ((rc = ensure(g.rowlog, sizeof(double) * 5 * (size_t)rows))) return rc;
   if (g.last_staged) {
@@ -179,7 +179,7 @@ int reexpand(int64_t rows) {
 // ---- sequential-stream models
 
 template <class Traits>
-int sequential_run(int64_t n, const typename Traits::Consts &consts, int max_draws, unsigned outputs,
+inline int sequential_run(int64_t n, const typename Traits::Consts &consts, int max_draws, unsigned outputs,
                    const ReportGeom &geom, int max_rows, double mean_rows) {
   int rc;
   if ((rc = ensure_init())) return rc;
@@ -265,5 +265,66 @@ int sequential_run(int64_t n, const typename Traits::Consts &consts, int max_dra
   }
   return MSIM_OK;
 }
+
+// Stream regime for models that may draw many uniforms per person (up to 250; chunk tables with a stride of 256
+// instead of sequential_run's 8).  One attempt with `n_pos` start positions planned for; *short_plan is set when the chain
+// of persons ran off the planned positions before person n-1 (the caller retries with the maximum).
+template <class Traits>
+inline int stream_offsets_attempt(int64_t n, const typename Traits::Consts &consts, int64_t n_pos, int max_draws, bool want_aux,
+                           bool *short_plan, int64_t *end_word_out, int64_t *mt_end_out) {
+  int rc;
+  *short_plan = false;
+  const int64_t mti0 = g.rng.mt[0];
+  const int64_t words_needed = mti0 + n_pos + max_draws + 1;
+  const int64_t n_batches = (words_needed + 623) / 624;
+  const int64_t mt_end = n_batches * 624;
+  *mt_end_out = mt_end;
+  if ((rc = ensure(g.mt_words, sizeof(uint32_t) * (size_t)mt_end))) return rc;
+  CK(cudaMemcpyAsync(g.mt_words.p, &g.rng.mt[1], sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, g.stream));
+  if (n_batches > 1) {
+    mt_generate_kernel<<<1, 256, 0, g.stream>>>((uint32_t *)g.mt_words.p, (int)(n_batches - 1));
+    CK(cudaGetLastError());
+    g.launches++;
+  }
+  const int stride = 256;
+  const int64_t n_chunks = (n_pos + CHAIN_CHUNK - 1) / CHAIN_CHUNK;
+  if ((rc = ensure(g.len, (size_t)n_pos))) return rc;
+  if (want_aux && (rc = ensure(g.aux, (size_t)n_pos))) return rc;
+  if ((rc = ensure(g.starts, sizeof(int64_t) * (size_t)n))) return rc;
+  if ((rc = ensure(g.chain_exit, (size_t)n_chunks * stride))) return rc;
+  if ((rc = ensure(g.chain_count, sizeof(int) * (size_t)n_chunks * stride))) return rc;
+  if ((rc = ensure(g.chain_entry, (size_t)n_chunks))) return rc;
+  if ((rc = ensure(g.chain_base, sizeof(int64_t) * (size_t)n_chunks))) return rc;
+  CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
+  SmallView sv = small_view();
+  int lgrid = (int)std::min<int64_t>((n_pos + BLOCK - 1) / BLOCK, (int64_t)g.sm_count * 8);
+  seq_len_kernel<Traits><<<lgrid, BLOCK, 0, g.stream>>>((const uint32_t *)g.mt_words.p, mt_end, mti0, n_pos, consts,
+                                                        (unsigned char *)g.len.p, want_aux ? (unsigned char *)g.aux.p : nullptr);
+  CK(cudaGetLastError());
+  chain_chunk_kernel<<<(unsigned)n_chunks, 256, 0, g.stream>>>((const unsigned char *)g.len.p, n_pos, max_draws, stride,
+                                                               (unsigned char *)g.chain_exit.p, (int *)g.chain_count.p);
+  CK(cudaGetLastError());
+  chain_scan_kernel<<<1, 256, 0, g.stream>>>((const unsigned char *)g.chain_exit.p, (const int *)g.chain_count.p, n_chunks, n,
+                                             stride, (unsigned char *)g.chain_entry.p, (int64_t *)g.chain_base.p);
+  CK(cudaGetLastError());
+  chain_emit_kernel<<<(unsigned)n_chunks, 64, 0, g.stream>>>((const unsigned char *)g.len.p, n_pos, mti0,
+                                                             (const unsigned char *)g.chain_entry.p, (const int64_t *)g.chain_base.p,
+                                                             n, (int64_t *)g.starts.p, sv.end_word, sv.error);
+  CK(cudaGetLastError());
+  g.launches += 4;
+  CK(cudaStreamSynchronize(g.stream));
+  double small[16];
+  CK(cudaMemcpy(small, g.small.p, sizeof small, cudaMemcpyDeviceToHost));
+  const int64_t end_word = *(int64_t *)(small + 11);
+  const int err = *(int *)(small + 10);
+  if (end_word == 0 || err == MSIM_ERR_STREAM) {  // person n-1 was never reached
+    *short_plan = true;
+    return MSIM_OK;
+  }
+  if (err) return fail(err, "device-side error while resolving stream offsets");
+  *end_word_out = end_word;
+  return MSIM_OK;
+}
+
 
 }  // namespace msim_host

@@ -122,7 +122,7 @@ inline int ensure_init() {
 }
 
 // substream state of person `first_person` of the stream that starts at `state`
-void stream_start(const uint32_t state[6], int64_t first_person, int64_t n_threads, StreamStart *st) {
+inline void stream_start(const uint32_t state[6], int64_t first_person, int64_t n_threads, StreamStart *st) {
   Mrg32k3a b;
   memcpy(b.s, state, sizeof b.s);
   b.jump(mrg_jump_pow(mrg_substream_jump(), (uint64_t)first_person + 1));
@@ -134,7 +134,7 @@ void stream_start(const uint32_t state[6], int64_t first_person, int64_t n_threa
 
 // ---------------------------------------------------------------- host memory
 
-int pinned_alloc(size_t bytes, double **out) {
+inline int pinned_alloc(size_t bytes, double **out) {
   if (bytes == 0) bytes = 8;
   if (g.pin_cache && g.pin_cache_bytes >= bytes) {
     *out = (double *)g.pin_cache;
@@ -150,7 +150,7 @@ int pinned_alloc(size_t bytes, double **out) {
   return MSIM_OK;
 }
 
-void host_free(double *p) {
+inline void host_free(double *p) {
   if (!p) return;
   auto it = g.pinned.find(p);
   if (it == g.pinned.end()) {
@@ -168,7 +168,7 @@ void host_free(double *p) {
   }
 }
 
-ReportGeom geom_from_dims(const msim_dense_dims *dims, double discount_rate) {
+inline ReportGeom geom_from_dims(const msim_dense_dims *dims, double discount_rate) {
   return ages_geom(dims->n_state, dims->n_event, discount_rate);
 }
 
@@ -179,7 +179,7 @@ struct SmallView {
   int64_t *end_word;
   unsigned long long *ov_count;
 };
-SmallView small_view() {
+inline SmallView small_view() {
   SmallView v;
   double *b = (double *)g.small.p;
   v.n_rows = (unsigned long long *)(b + 9);

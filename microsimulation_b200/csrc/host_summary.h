@@ -7,64 +7,6 @@ using namespace msim;
 
 // ---- Sick-Sicker (SummaryReport)
 
-// One attempt in the stream regime with `n_pos` start positions planned for; *short_plan is set when the chain
-// of persons ran off the planned positions before person n-1 (the caller retries with the maximum).
-int sick_stream_attempt(int64_t n, const SickParams &base, int64_t n_pos, int max_draws, bool *short_plan, int64_t *end_word_out,
-                        int64_t *mt_end_out) {
-  int rc;
-  *short_plan = false;
-  const int64_t mti0 = g.rng.mt[0];
-  const int64_t words_needed = mti0 + n_pos + max_draws + 1;
-  const int64_t n_batches = (words_needed + 623) / 624;
-  const int64_t mt_end = n_batches * 624;
-  *mt_end_out = mt_end;
-  if ((rc = ensure(g.mt_words, sizeof(uint32_t) * (size_t)mt_end))) return rc;
-  CK(cudaMemcpyAsync(g.mt_words.p, &g.rng.mt[1], sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, g.stream));
-  if (n_batches > 1) {
-    mt_generate_kernel<<<1, 256, 0, g.stream>>>((uint32_t *)g.mt_words.p, (int)(n_batches - 1));
-    CK(cudaGetLastError());
-    g.launches++;
-  }
-  const int stride = 256;
-  const int64_t n_chunks = (n_pos + CHAIN_CHUNK - 1) / CHAIN_CHUNK;
-  if ((rc = ensure(g.len, (size_t)n_pos))) return rc;
-  if ((rc = ensure(g.aux, (size_t)n_pos))) return rc;
-  if ((rc = ensure(g.starts, sizeof(int64_t) * (size_t)n))) return rc;
-  if ((rc = ensure(g.chain_exit, (size_t)n_chunks * stride))) return rc;
-  if ((rc = ensure(g.chain_count, sizeof(int) * (size_t)n_chunks * stride))) return rc;
-  if ((rc = ensure(g.chain_entry, (size_t)n_chunks))) return rc;
-  if ((rc = ensure(g.chain_base, sizeof(int64_t) * (size_t)n_chunks))) return rc;
-  CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
-  SmallView sv = small_view();
-  int lgrid = (int)std::min<int64_t>((n_pos + BLOCK - 1) / BLOCK, (int64_t)g.sm_count * 8);
-  seq_len_kernel<SickTraits><<<lgrid, BLOCK, 0, g.stream>>>((const uint32_t *)g.mt_words.p, mt_end, mti0, n_pos, base.par,
-                                                            (unsigned char *)g.len.p, (unsigned char *)g.aux.p);
-  CK(cudaGetLastError());
-  chain_chunk_kernel<<<(unsigned)n_chunks, 256, 0, g.stream>>>((const unsigned char *)g.len.p, n_pos, max_draws, stride,
-                                                               (unsigned char *)g.chain_exit.p, (int *)g.chain_count.p);
-  CK(cudaGetLastError());
-  chain_scan_kernel<<<1, 256, 0, g.stream>>>((const unsigned char *)g.chain_exit.p, (const int *)g.chain_count.p, n_chunks, n,
-                                             stride, (unsigned char *)g.chain_entry.p, (int64_t *)g.chain_base.p);
-  CK(cudaGetLastError());
-  chain_emit_kernel<<<(unsigned)n_chunks, 64, 0, g.stream>>>((const unsigned char *)g.len.p, n_pos, mti0,
-                                                             (const unsigned char *)g.chain_entry.p, (const int64_t *)g.chain_base.p,
-                                                             n, (int64_t *)g.starts.p, sv.end_word, sv.error);
-  CK(cudaGetLastError());
-  g.launches += 4;
-  CK(cudaStreamSynchronize(g.stream));
-  double small[16];
-  CK(cudaMemcpy(small, g.small.p, sizeof small, cudaMemcpyDeviceToHost));
-  const int64_t end_word = *(int64_t *)(small + 11);
-  const int err = *(int *)(small + 10);
-  if (end_word == 0 || err == MSIM_ERR_STREAM) {  // person n-1 was never reached
-    *short_plan = true;
-    return MSIM_OK;
-  }
-  if (err) return fail(err, "device-side error while resolving stream offsets");
-  *end_word_out = end_word;
-  return MSIM_OK;
-}
-
 int sick_sicker_run(int64_t n, const double par17[17], int indivp, int substreams, int64_t first_person, msim_report *out) {
   int rc;
   if ((rc = ensure_init())) return rc;
@@ -116,10 +58,10 @@ int sick_sicker_run(int64_t n, const double par17[17], int indivp, int substream
     int64_t mt_end = 0;
     // 36.4 draws per person at the README's rates; plan for 48 and fall back to the per-person maximum
     int64_t n_pos = std::min<int64_t>(48 * n + 8192, (int64_t)max_draws * n);
-    if ((rc = sick_stream_attempt(n, p, n_pos, max_draws, &short_plan, &end_word, &mt_end))) return rc;
+    if ((rc = stream_offsets_attempt<SickTraits>(n, p.par, n_pos, max_draws, true, &short_plan, &end_word, &mt_end))) return rc;
     if (short_plan && n_pos < (int64_t)max_draws * n) {
       n_pos = (int64_t)max_draws * n;
-      if ((rc = sick_stream_attempt(n, p, n_pos, max_draws, &short_plan, &end_word, &mt_end))) return rc;
+      if ((rc = stream_offsets_attempt<SickTraits>(n, p.par, n_pos, max_draws, true, &short_plan, &end_word, &mt_end))) return rc;
     }
     if (short_plan) return fail(MSIM_ERR_STREAM, "a person drew more uniforms than the sequential-stream plan allows (250)");
     CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));

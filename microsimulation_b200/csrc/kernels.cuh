@@ -219,6 +219,7 @@ struct NullEnv {
   __device__ __forceinline__ void report(int, int, double, double) {}
   __device__ __forceinline__ void summary(int, int, double, double) {}
   __device__ __forceinline__ void set_uc(int k, double, double) { code = k; }
+  __device__ __forceinline__ void value(int, double) {}  // plugin.cuh
 };
 
 template <class Traits, bool STREAM>
