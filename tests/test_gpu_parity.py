@@ -344,6 +344,10 @@ def test_calibration_event_queues_agree_bit_for_bit(msim):
             assert set(a) == set(b)
             for k in a:
                 assert np.array_equal(a[k], b[k]), (other, k)
+    again = msim.calibration_sweep(12345, pars, 100000, first_person=77)
+    for a, b in zip(runs["staged"], again):
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k   # run to run: bit-identical, TimeAtRisk included
 
 
 def test_calibration_config5_full_size_properties(msim):
