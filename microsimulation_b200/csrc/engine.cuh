@@ -74,7 +74,8 @@ struct EventHeap : std::conditional<(CAP > 0), HeapStore<(CAP > 0 ? CAP : 1)>, H
   using Store::M;
   using Store::T;
   int n;
-  static constexpr bool tie = false;  // ties resolve as in heap.h: nothing to report
+  static constexpr bool tie = false;       // ties resolve as in heap.h: nothing to report
+  static constexpr bool compacts = false;  // cancelled entries stay (A_Ignore), as in ssim.cc:131-142
 
   MSIM_DEV void reset() { n = 0; }
   MSIM_DEV bool before(double ta, int ma, double tb, int mb) const {
@@ -150,6 +151,7 @@ struct EventHeap<4> {
   int m0, m1, m2, m3;
   int n;
   static constexpr bool tie = false;
+  static constexpr bool compacts = false;
 
   MSIM_DEV void reset() { n = 0; }
 
@@ -230,14 +232,38 @@ struct EventHeap<4> {
 // two do compare equal, heap.h's order depends on the heap's shape, which this queue does not model: it sets `tie`
 // instead, and the caller repeats the run with EventHeap (host side: msim_calibration_sweep).  Event times are
 // continuous draws, so this essentially never happens; exactness does not rest on that.
-// Entries live in caller-bound memory, ascending in [head, tail); insertion scans from the late end.
-template <int CAP>
-struct OrderedEvents : HeapStoreBound<CAP> {
-  typedef HeapStoreBound<CAP> Store;
+// Entries are ascending in [head, tail) of caller-bound memory (the default) or of the thread's own small array
+// (StoreT = HeapStore<CAP>); insertion scans from the late end.
+// Cancelled actions are REMOVED instead of lingering as A_Ignore: popping an ignored action has no effect in the
+// reference (no clock update, no dispatch: ssim.cc:171-175), so the live actions' pop order — all that is
+// observable — is the same, and a model that cancels at every transition (Sick-Sicker) keeps a handful of entries
+// instead of hundreds.
+template <int CAP, class StoreT = HeapStoreBound<CAP> >
+struct OrderedEvents : StoreT {
+  typedef StoreT Store;
   using Store::M;
   using Store::T;
   int n, head, tail;
   bool tie;
+  static constexpr bool compacts = true;
+
+  // drop the entries whose meta word satisfies pred
+  template <class Pred>
+  MSIM_DEV void remove_if(Pred pred) {
+    int w = head;
+    for (int i = head; i < tail; i++) {
+      const int m = M(i);
+      if (!pred(m)) {
+        if (w != i) {
+          T(w) = T(i);
+          M(w) = m;
+        }
+        w++;
+      }
+    }
+    tail = w;
+    n = tail - head;
+  }
 
   MSIM_DEV void reset() {
     n = head = tail = 0;
@@ -320,9 +346,13 @@ struct cProcess {
   // Cancel(pred) -> Sim::ignore_event: mark matching A_Event entries A_Ignore
   template <class Pred>
   MSIM_DEV void Cancel(Pred pred) {
-    actions.for_each_meta([&](int &m) {
-      if (meta_type(m) == A_Event && pred(meta_kind(m))) m = (int)(((uint32_t)m & 0x3fffffffu) | ((uint32_t)A_Ignore << 30));
-    });
+    if constexpr (Actions::compacts) {
+      actions.remove_if([&](int m) { return meta_type(m) == A_Event && pred(meta_kind(m)); });
+    } else {
+      actions.for_each_meta([&](int &m) {
+        if (meta_type(m) == A_Event && pred(meta_kind(m))) m = (int)(((uint32_t)m & 0x3fffffffu) | ((uint32_t)A_Ignore << 30));
+      });
+    }
   }
   MSIM_DEV void RemoveKind(int kind) {
     Cancel([kind](int k) { return k == kind; });

@@ -7,6 +7,53 @@ using namespace msim;
 
 // ---- Sick-Sicker (SummaryReport)
 
+// One pass over the n persons: first-pass codes, carry scan, the persons (both regimes)
+template <bool ORDERED>
+int sick_launch(SickParams &p, int64_t n, bool substreams, const HostStream &hs, int64_t first_person, int grid, size_t smem,
+                int64_t *end_word) {
+  int rc;
+  typedef SickTraitsT<ORDERED> Traits;
+  if (!substreams) {
+    const int max_draws = 250;
+    bool short_plan = false;
+    int64_t mt_end = 0;
+    // 36.4 draws per person at the README's rates; plan for 48 and fall back to the per-person maximum
+    int64_t n_pos = std::min<int64_t>(48 * n + 8192, (int64_t)max_draws * n);
+    if ((rc = stream_offsets_attempt<Traits>(n, p.par, n_pos, max_draws, true, &short_plan, end_word, &mt_end))) return rc;
+    if (short_plan && n_pos < (int64_t)max_draws * n) {
+      n_pos = (int64_t)max_draws * n;
+      if ((rc = stream_offsets_attempt<Traits>(n, p.par, n_pos, max_draws, true, &short_plan, end_word, &mt_end))) return rc;
+    }
+    if (short_plan) return fail(MSIM_ERR_STREAM, "a person drew more uniforms than the sequential-stream plan allows (250)");
+    CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
+    p.mt_words = (const uint32_t *)g.mt_words.p;
+    p.mt_end = mt_end;
+    p.starts = (const int64_t *)g.starts.p;
+    gather_code_kernel<<<g.sm_count * 4, 256, 0, g.stream>>>((const unsigned char *)g.aux.p, p.starts, (int64_t)g.rng.mt[0], n,
+                                                             p.code_out);
+    CK(cudaGetLastError());
+    carry_scan_kernel<<<1, 1024, 0, g.stream>>>(p.code_out, n, 0, (unsigned char *)g.code_in.p);
+    CK(cudaGetLastError());
+    auto kern = sick_kernel<true, ORDERED>;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, BLOCK, smem, g.stream>>>(p);
+    CK(cudaGetLastError());
+    g.launches += 3;
+  } else {
+    stream_start(hs.Cg.s, first_person, (int64_t)grid * BLOCK, &p.st);
+    sick_code_kernel<ORDERED><<<grid, BLOCK, 0, g.stream>>>(p);
+    CK(cudaGetLastError());
+    carry_scan_kernel<<<1, 1024, 0, g.stream>>>(p.code_out, n, 0, (unsigned char *)g.code_in.p);
+    CK(cudaGetLastError());
+    auto kern = sick_kernel<false, ORDERED>;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, BLOCK, smem, g.stream>>>(p);
+    CK(cudaGetLastError());
+    g.launches += 3;
+  }
+  return MSIM_OK;
+}
+
 int sick_sicker_run(int64_t n, const double par17[17], int indivp, int substreams, int64_t first_person, msim_report *out) {
   int rc;
   if ((rc = ensure_init())) return rc;
@@ -49,52 +96,35 @@ int sick_sicker_run(int64_t n, const double par17[17], int indivp, int substream
   const int64_t tiles = (n + BLOCK - 1) / BLOCK;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)g.sm_count * 4, tiles));
   int64_t end_word = 0;
-  CK(cudaEventRecord(g.ev0, g.stream));
-  if (n > 0 && !substreams) {
-    if (!g.rng.mt_seeded)
-      return fail(MSIM_ERR_STATE, "Mersenne-Twister state not set: call msim_mt_set_seed or msim_mt_set_state first");
-    const int max_draws = 250;
-    bool short_plan = false;
-    int64_t mt_end = 0;
-    // 36.4 draws per person at the README's rates; plan for 48 and fall back to the per-person maximum
-    int64_t n_pos = std::min<int64_t>(48 * n + 8192, (int64_t)max_draws * n);
-    if ((rc = stream_offsets_attempt<SickTraits>(n, p.par, n_pos, max_draws, true, &short_plan, &end_word, &mt_end))) return rc;
-    if (short_plan && n_pos < (int64_t)max_draws * n) {
-      n_pos = (int64_t)max_draws * n;
-      if ((rc = stream_offsets_attempt<SickTraits>(n, p.par, n_pos, max_draws, true, &short_plan, &end_word, &mt_end))) return rc;
-    }
-    if (short_plan) return fail(MSIM_ERR_STREAM, "a person drew more uniforms than the sequential-stream plan allows (250)");
+  p.tie = (int *)((double *)g.small.p + 13);
+  if (n > 0 && !substreams && !g.rng.mt_seeded)
+    return fail(MSIM_ERR_STATE, "Mersenne-Twister state not set: call msim_mt_set_seed or msim_mt_set_state first");
+  // rng = new Rng(): takes the package seed, which then moves on one stream; person i draws from substream
+  // first_person + i + 1 (the regime the oracle's `substreams` flag selects)
+  HostStream hs;
+  if (n > 0 && substreams) hs = g.rng.new_stream();
+  // Schedule 0 keeps the live actions in a small ordered array (engine.cuh, OrderedEvents; cancelled actions are
+  // removed), which pops in the heap's order unless two pending actions compare equal; a run that saw such a pair is
+  // repeated with heap.h's binary heap and lingering cancelled entries (schedule 1).  Schedule 2 (tests) takes the
+  // repeat path unconditionally.
+  for (int attempt = g.person_kernel == 1 ? 1 : 0; attempt < 2; attempt++) {
+    CK(cudaMemsetAsync(g.dense.p, 0, sizeof(double) * G.total, g.stream));
+    CK(cudaMemsetAsync(g.indiv.p, 0, sizeof(double) * 2 * (size_t)std::max<int64_t>(n_indiv, 1), g.stream));
     CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
-    p.mt_words = (const uint32_t *)g.mt_words.p;
-    p.mt_end = mt_end;
-    p.starts = (const int64_t *)g.starts.p;
-    gather_code_kernel<<<g.sm_count * 4, 256, 0, g.stream>>>((const unsigned char *)g.aux.p, p.starts, (int64_t)g.rng.mt[0], n,
-                                                             p.code_out);
-    CK(cudaGetLastError());
-    carry_scan_kernel<<<1, 1024, 0, g.stream>>>(p.code_out, n, 0, (unsigned char *)g.code_in.p);
-    CK(cudaGetLastError());
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(sick_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sick_kernel<true><<<grid, BLOCK, smem, g.stream>>>(p);
-    CK(cudaGetLastError());
-    g.launches += 3;
-  } else if (n > 0) {
-    // rng = new Rng(): takes the package seed, which then moves on one stream; person i draws from substream
-    // first_person + i + 1 (the regime the oracle's `substreams` flag selects)
-    HostStream hs = g.rng.new_stream();
-    stream_start(hs.Cg.s, first_person, (int64_t)grid * BLOCK, &p.st);
-    sick_code_kernel<<<grid, BLOCK, 0, g.stream>>>(p);
-    CK(cudaGetLastError());
-    carry_scan_kernel<<<1, 1024, 0, g.stream>>>(p.code_out, n, 0, (unsigned char *)g.code_in.p);
-    CK(cudaGetLastError());
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(sick_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sick_kernel<false><<<grid, BLOCK, smem, g.stream>>>(p);
-    CK(cudaGetLastError());
-    g.launches += 3;
+    CK(cudaEventRecord(g.ev0, g.stream));
+    if (n > 0) {
+      rc = attempt == 0 ? sick_launch<true>(p, n, substreams != 0, hs, first_person, grid, smem, &end_word)
+                        : sick_launch<false>(p, n, substreams != 0, hs, first_person, grid, smem, &end_word);
+      if (rc) return rc;
+    }
+    CK(cudaEventRecord(g.ev1, g.stream));
+    g.timing_pending = true;
+    g.have_last = false;
+    if ((rc = finish_run(nullptr))) return rc;
+    int tie = 0;
+    CK(cudaMemcpy(&tie, p.tie, sizeof tie, cudaMemcpyDeviceToHost));
+    if (attempt == 0 && !tie && g.person_kernel != 2) break;
   }
-  CK(cudaEventRecord(g.ev1, g.stream));
-  g.timing_pending = true;
-  g.have_last = false;
-  if ((rc = finish_run(nullptr))) return rc;
   std::vector<double> d(G.total), ind(2 * (size_t)std::max<int64_t>(n_indiv, 1));
   CK(cudaMemcpy(d.data(), g.dense.p, sizeof(double) * d.size(), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(ind.data(), g.indiv.p, sizeof(double) * ind.size(), cudaMemcpyDeviceToHost));

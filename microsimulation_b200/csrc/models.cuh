@@ -353,9 +353,14 @@ struct Par {
   int Trt;
 };
 
-template <class Env>
-struct SickSicker : cProcess<SickSicker<Env>, typename Env::Src, HEAP_CAP> {
-  typedef cProcess<SickSicker<Env>, typename Env::Src, HEAP_CAP> Base;
+// ORDERED: pending actions in a small ordered array with cancelled actions removed (engine.cuh, OrderedEvents): at
+// most toEOF and three competing transitions are live at any time
+constexpr int LIVE_CAP = 8;
+template <class Env, bool ORDERED = false>
+struct SickSicker : cProcess<SickSicker<Env, ORDERED>, typename Env::Src, HEAP_CAP,
+                             typename std::conditional<ORDERED, OrderedEvents<LIVE_CAP, HeapStore<LIVE_CAP> >, EventHeap<HEAP_CAP> >::type> {
+  typedef cProcess<SickSicker<Env, ORDERED>, typename Env::Src, HEAP_CAP,
+                   typename std::conditional<ORDERED, OrderedEvents<LIVE_CAP, HeapStore<LIVE_CAP> >, EventHeap<HEAP_CAP> >::type> Base;
   using Base::Cancel;
   using Base::now;
   using Base::previousEventTime;

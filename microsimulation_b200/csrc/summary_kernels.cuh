@@ -17,11 +17,13 @@
 
 namespace msim {
 
-struct SickTraits {
+template <bool ORDERED>
+struct SickTraitsT {
   typedef sick_sicker::Par Consts;
-  template <class Env> using Model = sick_sicker::SickSicker<Env>;
+  template <class Env> using Model = sick_sicker::SickSicker<Env, ORDERED>;
   static constexpr int MAX_ROWS = 1;
 };
+typedef SickTraitsT<false> SickTraits;
 
 struct SickParams {
   StreamStart st;             // substream regime
@@ -37,9 +39,11 @@ struct SickParams {
   double *indiv;                 // [2n] (utilities, costs) per person if indivp, else [2]
   int indivp;
   int *error;
+  int *tie;  // set if two pending actions of a person compared equal (ORDERED only)
 };
 
 // first pass, substream regime: each person's last set_uc() code
+template <bool ORDERED>
 __global__ void __launch_bounds__(BLOCK) sick_code_kernel(SickParams p) {
   typedef NullEnv<MrgSource> Env;
   Mrg32k3a sub = thread_start_state(p.st, blockIdx.x * BLOCK + threadIdx.x);
@@ -50,10 +54,11 @@ __global__ void __launch_bounds__(BLOCK) sick_code_kernel(SickParams p) {
     if (i < p.n) {
       Env env;
       env.src.g = sub;
-      sick_sicker::SickSicker<Env> person(env, p.par, 0);
+      sick_sicker::SickSicker<Env, ORDERED> person(env, p.par, 0);
       person.run();
       p.code_out[i] = (unsigned char)env.code;
       if (person.error_) atomicCAS(p.error, 0, person.error_);
+      if (ORDERED && person.actions.tie) *p.tie = 1;
     }
     __syncwarp();
     sub.jump(p.st.stride);
@@ -122,7 +127,7 @@ struct SummaryEnv {
   }
 };
 
-template <bool STREAM>
+template <bool STREAM, bool ORDERED>
 __global__ void __launch_bounds__(BLOCK) sick_kernel(SickParams p) {
   typedef typename std::conditional<STREAM, StreamSource, MrgSource>::type Src;
   typedef SummaryEnv<Src> Env;
@@ -167,9 +172,10 @@ __global__ void __launch_bounds__(BLOCK) sick_kernel(SickParams p) {
     }
     sick_sicker::uc_of_code(p.par, p.code_in[i], &env.u, &env.c);
     env.tot_u = env.tot_c = 0.0;
-    sick_sicker::SickSicker<Env> person(env, p.par, p.first_person + i);
+    sick_sicker::SickSicker<Env, ORDERED> person(env, p.par, p.first_person + i);
     person.run();
     if (person.error_) err = person.error_;
+    if (ORDERED && person.actions.tie) *p.tie = 1;
     if constexpr (STREAM) {
       if (env.src.overrun) err = -6;
     } else {

@@ -473,6 +473,36 @@ def test_sick_sicker_substream_regime_vs_oracle(msim, oracle, n, first):
     _summary_equal(g, r)
 
 
+@pytest.mark.parametrize("substreams", [False, True])
+def test_sick_sicker_event_queues_agree(msim, oracle, substreams):
+    """Default (small ordered array, cancelled actions removed), heap.h's binary heap with lingering cancelled entries,
+    and the repeat path (default, then the heap kernels again): the same report, and the same generator state after."""
+    import microsimulation_b200.api as api
+    par = api.sick_sicker_param(True)
+    runs, after = {}, {}
+    try:
+        for sched in ("staged", "generic", "repeat"):
+            msim.set_person_schedule(sched)
+            if substreams:
+                api.set_user_random_seed(12345)
+            before = msim.launch_count()
+            runs[sched] = api.callSim(8000, par, substreams=substreams, first_person=17 if substreams else 0)
+            runs[sched + "_launches"] = msim.launch_count() - before
+            after[sched] = api.user_random_seed() if substreams else api.mt_state().copy()
+    finally:
+        msim.set_person_schedule("staged")
+    assert runs["repeat_launches"] == runs["staged_launches"] + runs["generic_launches"]
+    for other in ("generic", "repeat"):
+        _summary_equal(runs["staged"], runs[other], rtol=1e-12)
+        assert np.array_equal(after["staged"], after[other])
+        # per-person totals do not depend on any accumulation order: bit for bit
+        assert np.array_equal(runs["staged"]["indiv"]["utilities"], runs[other]["indiv"]["utilities"])
+        assert np.array_equal(runs["staged"]["indiv"]["costs"], runs[other]["indiv"]["costs"])
+    if substreams:
+        oracle.set_user_random_seed(12345)
+    _summary_equal(runs["staged"], oracle.sick_sicker(8000, par, substreams=substreams, first_person=17 if substreams else 0))
+
+
 def test_discounting_free_functions(msim, oracle):
     """discountedInterval / discountedPoint (microsimulation.h:811-836) as device functions: pow() differs from glibc's
     in the last bits only."""
