@@ -546,21 +546,23 @@ int emu_calibration_ordered(const double seed[6], int64_t first_person, int64_t 
   return emu_calibration_t<true>(seed, first_person, n, runpar, grid, out, tie_out);
 }
 
-// OrderedEvents against EventHeap on a random schedule/pop sequence (engine.cuh).  Times are drawn from `n_times`
-// distinct values and priorities from `n_prios`, so small values force pairs that compare equal.  Returns -1 if the
-// queue failed to flag such a pair (checked by brute force over the pending set at every insert), the number of pops
-// that differed from the heap's otherwise; *tie_out = the queue's flag at the end.
-int emu_ordered_vs_heap(uint32_t seed, int ops, int n_times, int n_prios, int *tie_out) {
+// OrderedEvents against EventHeap on a random schedule/pop(/cancel) sequence (engine.cuh).  Times are drawn from
+// `n_times` distinct values and priorities from `n_prios`, so small values force pairs that compare equal.  With
+// cancel_every > 0 every so many operations cancel one event kind: the heap marks those entries A_Ignore and pops them
+// later without effect (ssim.cc:131-142, 171-175), the queue removes them; what must agree is the sequence of LIVE
+// pops.  Returns -1 if the queue failed to flag a pair comparing equal (checked by brute force over the pending set
+// at every insert), otherwise the number of live pops that differed from the heap's; *tie_out = the queue's flag.
+int emu_ordered_vs_heap(uint32_t seed, int ops, int n_times, int n_prios, int cancel_every, int *tie_out) {
   constexpr int CAP = 14;
-  double ht[CAP], qt[CAP];
-  int hm[CAP], qm[CAP];
-  EventHeap<-CAP> heap;
+  double ht[4 * CAP], qt[CAP];
+  int hm[4 * CAP], qm[CAP];
+  EventHeap<-4 * CAP> heap;  // lingering cancelled entries need room
   OrderedEvents<CAP> queue;
   heap.bind(ht, hm, 1);
   queue.bind(qt, qm, 1);
   heap.reset();
   queue.reset();
-  std::vector<std::pair<double, int> > pending;
+  std::vector<std::pair<double, int> > pending;  // live entries
   bool equal_pair = false;
   int differ = 0;
   uint32_t x = seed ? seed : 1u;
@@ -571,7 +573,17 @@ int emu_ordered_vs_heap(uint32_t seed, int ops, int n_times, int n_prios, int *t
     return x;
   };
   for (int i = 0; i < ops; i++) {
-    const bool push = heap.n == 0 || (heap.n < CAP && next() % 5 < 3);
+    if (cancel_every > 0 && i % cancel_every == cancel_every - 1) {
+      const int kind = (int)(next() % 7);
+      heap.for_each_meta([kind](int &m) {
+        if (meta_type(m) == A_Event && meta_kind(m) == kind) m = (int)(((uint32_t)m & 0x3fffffffu) | ((uint32_t)A_Ignore << 30));
+      });
+      queue.remove_if([kind](int m) { return meta_type(m) == A_Event && meta_kind(m) == kind; });
+      for (size_t k = pending.size(); k-- > 0;)
+        if (meta_kind(pending[k].second) == kind) pending.erase(pending.begin() + (long)k);
+      continue;
+    }
+    const bool push = queue.n == 0 || (queue.n < CAP && heap.n < 4 * CAP && next() % 5 < 3);
     if (push) {
       const double t = (double)(next() % (uint32_t)n_times) * 0.25;
       const int prio = (int)(next() % (uint32_t)n_prios) - 1;
@@ -581,18 +593,23 @@ int emu_ordered_vs_heap(uint32_t seed, int ops, int n_times, int n_prios, int *t
       pending.push_back(std::make_pair(t, m));
       if (!heap.insert(t, m) || !queue.insert(t, m)) return -2;
     } else {
-      double t1, t2;
-      int m1, m2;
-      heap.pop_first(t1, m1);
+      double t1 = 0, t2;
+      int m1 = 0, m2;
+      bool live = false;
+      while (heap.n > 0 && !live) {  // the reference's loop: ignored actions are popped and skipped
+        heap.pop_first(t1, m1);
+        live = meta_type(m1) != A_Ignore;
+      }
+      if (!live) return -5;  // the queue says there is a live action, the heap has none
       queue.pop_first(t2, m2);
       if (t1 != t2 || m1 != m2) differ++;
       for (size_t k = 0; k < pending.size(); k++)
-        if (pending[k].first == t1 && pending[k].second == m1) {
+        if (pending[k].first == t2 && pending[k].second == m2) {
           pending.erase(pending.begin() + (long)k);
           break;
         }
     }
-    if (heap.n != queue.n) return -3;
+    if ((size_t)queue.n != pending.size()) return -3;
     if (equal_pair && !queue.tie) return -1;
   }
   *tie_out = queue.tie ? 1 : 0;

@@ -215,7 +215,7 @@ def test_ordered_event_queue_pops_in_heap_order_or_says_so(emu):
     clean = 0
     for seed in range(1, 41):
         # many distinct times: equal pairs are rare; every pop must agree with the heap unless one was flagged
-        d = emu.emu_ordered_vs_heap(C.c_uint32(seed), 4000, 1 << 20, 3, C.byref(tie))
+        d = emu.emu_ordered_vs_heap(C.c_uint32(seed), 4000, 1 << 20, 3, 0, C.byref(tie))
         assert d >= 0, d
         if not tie.value:
             assert d == 0
@@ -224,10 +224,20 @@ def test_ordered_event_queue_pops_in_heap_order_or_says_so(emu):
     flagged = 0
     for seed in range(1, 21):
         # 6 times x 2 priorities: equal pairs all over; the queue must flag them (return -1 = one went unnoticed)
-        d = emu.emu_ordered_vs_heap(C.c_uint32(seed), 500, 6, 2, C.byref(tie))
+        d = emu.emu_ordered_vs_heap(C.c_uint32(seed), 500, 6, 2, 0, C.byref(tie))
         assert d >= 0, d
         flagged += tie.value
     assert flagged == 20
+    # with cancellations: the heap keeps cancelled entries and skips them at pop time, the queue removes them; the
+    # sequence of live pops is the same
+    clean = 0
+    for seed in range(1, 41):
+        d = emu.emu_ordered_vs_heap(C.c_uint32(seed), 4000, 1 << 20, 3, 5, C.byref(tie))
+        assert d >= 0, d
+        if not tie.value:
+            assert d == 0
+            clean += 1
+    assert clean >= 30
 
 
 def test_emulated_calibration_ordered_queue(oracle, emu):
