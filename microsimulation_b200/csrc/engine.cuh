@@ -15,7 +15,9 @@
 // strict `<` on sift-up, right child only if strictly smaller than the left —
 // so ties in (time, priority) resolve exactly as on the CPU, including
 // cancelled entries, which stay in the heap as A_Ignore and are skipped at pop
-// time without advancing the clock.
+// time without advancing the clock.  Models with many pending actions may use OrderedEvents instead (below): an
+// ordered array that pops in the heap's order whenever that order does not depend on the heap's shape, and says so
+// when it might (the run is then repeated with the heap).
 //
 // Differences by design: there is one process per simulation (the built models
 // never call cProcess::send), cMessage names (std::string) are not available on
