@@ -116,6 +116,10 @@ int msim_r_next_rng_substream(void);
 /* src/microsimulation.cc:65-75: seed <- seed advanced by *n substreams
  * (side effect kept: it constructs an RngStream, advancing the package seed). */
 int msim_r_rng_advance_substream(double seed[6], const int *n);
+/* seed <- the start of the NEXT stream (A^(2^127) applied, RngStream.cpp:337-355): what base R's
+ * parallel::nextRNGStream() does to the six seed words, which the reference's R code uses to give every mclapply
+ * chunk its own stream (R/calibSim.R:21-24) and inside the RNGStream R class (R/rcpp_hello_world.R:793, 807). */
+int msim_next_rng_stream(double seed[6]);
 /* src/microsimulation.cc:77-85 — the hook R resolves BY NAME (`user_unif_rand`)
  * under RNGkind("user"): one U01 draw of the default stream, on the host (it
  * serves R-level runif() between simulations; the models never call it).

@@ -74,7 +74,7 @@ SYMBOLS = [
     "msim_table_free", "msim_report_free", "msim_last_error", "msim_version", "msim_init", "msim_shutdown",
     "msim_launch_count", "msim_set_stream", "msim_set_person_schedule", "msim_set_rowlog_plan", "msim_r_create_current_stream", "msim_r_remove_current_stream",
     "msim_r_set_user_random_seed", "msim_r_get_user_random_seed", "msim_r_next_rng_substream",
-    "msim_r_rng_advance_substream", "msim_user_unif_rand", "msim_mt_set_state", "msim_mt_get_state", "msim_mt_set_seed",
+    "msim_r_rng_advance_substream", "msim_next_rng_stream", "msim_user_unif_rand", "msim_mt_set_state", "msim_mt_get_state", "msim_mt_set_seed",
     "msim_callPersonSimulation", "msim_callSimplePerson", "msim_callSimplePerson2", "msim_callIllnessDeath",
     "msim_callCalibrationSimulation", "msim_callSim_SickSicker", "msim_discounted", "msim_rpexp", "msim_rpexp_gamma", "msim_interpolate", "msim_table_lookup", "msim_gsm_randU", "msim_gsm_randU0", "msim_gsm_eta", "msim_person_run_device", "msim_person_enqueue", "msim_sync",
     "msim_last_kernel_ms", "msim_timer_start", "msim_timer_stop", "msim_person_fetch_rowlog", "msim_person_fetch_counts", "msim_dense_to_report",

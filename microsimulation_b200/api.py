@@ -197,21 +197,42 @@ def callIllnessDeath(n=10, cure=0.1, zsd=0.0):
     return _report(load().msim_callIllnessDeath, C.c_int32(n), C.c_double(cure), C.c_double(zsd))
 
 
+def next_rng_stream(seed):
+    """parallel::nextRNGStream on the six seed words (R/calibSim.R:21)."""
+    s = (C.c_double * 6)(*_seed6(seed))
+    check(load().msim_next_rng_stream(s))
+    return [int(x) for x in s]
+
+
+def calibration_chunks(n, mc_cores):
+    """Sizes of split(1:n, rep(1:mc.cores, length.out = n)) (R/calibSim.R:17-18)."""
+    return [len(range(i, n, mc_cores)) for i in range(mc_cores)]
+
+
 def callCalibrationPerson(seed=12345, n=500, runpar=(4, 0.5, 0.05, 10, 3, 0.5), mc_cores=1):
-    """R/calibSim.R:10-40 with mc.cores = 1 (more cores change the random numbers in the reference too)."""
-    if mc_cores != 1:
-        raise ValueError("mc_cores > 1 uses different streams per chunk in the reference; shard with calibration_sweep")
+    """R/calibSim.R:10-40.  As in the reference, mc.cores chunks each run on a stream of their own (the first on the
+    seed's, chunk i on the stream after chunk i-1's), so the result depends on mc_cores; to use several GPUs WITHOUT
+    changing the random numbers, shard with distributed.calibration_sweep_sharded instead."""
     set_user_random_seed(seed)
+    current = user_random_seed()[1:]
     par = (C.c_double * 6)(*[float(x) for x in runpar])
-    c = Calibration()
-    check(load().msim_callCalibrationSimulation(C.c_int32(n), par, C.byref(c)))
-    d = c.to_dict()
     states = ["DiseaseFree", "Precursor", "PreClinical", "Clinical"]
-    mat = np.zeros((10, 4))
-    for j, nm in enumerate(states):
-        if nm in d:
-            mat[:, j] = d[nm]
-    return {"StateOccupancy": mat, "TimeAtRisk": d["TimeAtRisk"], "raw": d}
+    mat, tar, raw = np.zeros((10, 4)), None, []
+    for i, n_chunk in enumerate(calibration_chunks(int(n), int(mc_cores))):
+        if i > 0:
+            current = next_rng_stream(current)
+        set_user_random_seed(current)
+        c = Calibration()
+        check(load().msim_callCalibrationSimulation(C.c_int32(n_chunk), par, C.byref(c)))
+        d = c.to_dict()
+        raw.append(d)
+        for j, nm in enumerate(states):
+            if nm in d:
+                mat[:, j] += d[nm]
+        # Reduce(... u$TimeAtRisk + z$TimeAtRisk): R recycles a shorter vector; chunks of any size reach all four
+        t = d["TimeAtRisk"]
+        tar = t.copy() if tar is None else (tar + t if len(tar) == len(t) else np.resize(tar, max(len(tar), len(t))) + np.resize(t, max(len(tar), len(t))))
+    return {"StateOccupancy": mat, "TimeAtRisk": tar, "raw": raw[0] if mc_cores == 1 else raw}
 
 
 SICK_SICKER_KEYS = ["r_HS1", "r_HD", "r_S1H", "r_S1S2", "r_S1D", "r_S2D", "c_H", "c_S1", "c_S2", "c_Trt", "u_H", "u_S1",

@@ -154,6 +154,15 @@ int msim_r_rng_advance_substream(double seed[6], const int *n) {
   return MSIM_OK;
 }
 
+int msim_next_rng_stream(double seed[6]) {
+  if (!seed || !mrg_seed_ok(seed)) return fail(MSIM_ERR_SEED, "illegal MRG32k3a seed");
+  Mrg32k3a t;
+  seed_to_u32(seed, t.s);
+  t.jump(mrg_stream_jump());
+  for (int i = 0; i < 6; i++) seed[i] = (double)t.s[i];
+  return MSIM_OK;
+}
+
 double *msim_user_unif_rand(void) {
   static double rn;
   if (!g.rng.have_default) {

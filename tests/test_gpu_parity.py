@@ -533,6 +533,28 @@ def test_package_seed_advances_like_the_reference(msim, oracle):
         assert list(a.occupancy) == list(b.occupancy)
 
 
+def test_calibration_person_mc_cores_like_mclapply(msim, oracle):
+    """R/calibSim.R:16-39 with mc.cores = 3: chunk i runs its persons on the stream after chunk i-1's; the sum depends on
+    mc.cores exactly as in the reference."""
+    n, runpar = 4000, [4, 0.5, 0.05, 10, 3, 0.5]
+    got = msim.callCalibrationPerson(777, n, runpar, mc_cores=3)
+    states = ["DiseaseFree", "Precursor", "PreClinical", "Clinical"]
+    mat, tar = np.zeros((10, 4)), np.zeros(4)
+    seed = [777] * 6
+    for i, n_chunk in enumerate(msim.calibration_chunks(n, 3)):
+        if i:
+            seed = msim.next_rng_stream(seed)   # checked against the reference's RngStream.cpp in test_host_logic.py
+        d = oracle.callCalibrationPerson(seed, n_chunk, runpar)
+        for j, nm in enumerate(states):
+            if nm in d:
+                mat[:, j] += d[nm]
+        tar[:len(d["TimeAtRisk"])] += d["TimeAtRisk"]
+    assert np.array_equal(got["StateOccupancy"], mat)
+    np.testing.assert_allclose(got["TimeAtRisk"], tar, rtol=1e-12)
+    one = msim.callCalibrationPerson(777, n, runpar, mc_cores=1)
+    assert not np.array_equal(one["StateOccupancy"], mat)   # as in the reference, mc.cores changes the random numbers
+
+
 def test_kernels_were_launched(msim):
     before = msim.launch_count()
     msim.callPersonSimulation(1000)

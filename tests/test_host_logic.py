@@ -85,6 +85,21 @@ def test_user_unif_rand_hook_matches_oracle(oracle):
     assert np.array_equal(m.user_unif_rand(2), oracle_after)
 
 
+def test_next_rng_stream_matches_the_reference_jump(oracle, oracle_ref):
+    """parallel::nextRNGStream (used by R/calibSim.R:21 and the RNGStream R class) is A^(2^127): 2^51 substreams of
+    2^76 steps, which RngStream::AdvanceSubstream(51, 0) of the reference's own RngStream.cpp computes."""
+    import microsimulation_b200 as m
+    for seed in ([12345] * 6, [1, 2, 3, 4, 5, 6], [4294967086, 4294967086, 4294967086, 4294944442, 4294944442, 4294944442]):
+        want = (C.c_double * 6)(*[float(x) for x in seed])
+        assert oracle_ref.lib.oracle_rng_advance_e(want, 51, 0) == 0
+        port = (C.c_double * 6)(*[float(x) for x in seed])
+        assert oracle.lib.oracle_rng_advance_e(port, 51, 0) == 0
+        assert m.next_rng_stream(seed) == [int(x) for x in want] == [int(x) for x in port]
+    with pytest.raises(m.MsimError):
+        m.next_rng_stream([0, 0, 0, 1, 1, 1])
+    assert m.calibration_chunks(10, 3) == [4, 3, 3] and m.calibration_chunks(2, 4) == [1, 1, 0, 0]
+
+
 def test_mt_set_seed_matches_oracle(oracle, emu):
     import microsimulation_b200 as m
     m.set_seed(12345)
