@@ -124,6 +124,7 @@ void msim_r_create_current_stream(void) {
 void msim_r_remove_current_stream(void) { g.rng.have_default = false; }
 
 int msim_r_set_user_random_seed(const double seed[6]) {
+  if (!seed) return fail(MSIM_ERR_ARG, "null seed");
   if (!g.rng.have_default) return fail(MSIM_ERR_STATE, "no current stream: call msim_r_create_current_stream");
   if (!mrg_seed_ok(seed)) return fail(MSIM_ERR_SEED, "illegal MRG32k3a seed (the reference ignores it silently)");
   uint32_t s[6];
@@ -133,6 +134,7 @@ int msim_r_set_user_random_seed(const double seed[6]) {
   return MSIM_OK;
 }
 int msim_r_get_user_random_seed(double seed[6]) {
+  if (!seed) return fail(MSIM_ERR_ARG, "null seed");
   if (!g.rng.have_default) return fail(MSIM_ERR_STATE, "no current stream");
   for (int i = 0; i < 6; i++) seed[i] = (double)g.rng.default_stream.Cg.s[i];
   return MSIM_OK;
@@ -143,6 +145,7 @@ int msim_r_next_rng_substream(void) {
   return MSIM_OK;
 }
 int msim_r_rng_advance_substream(double seed[6], const int *n) {
+  if (!seed || !n) return fail(MSIM_ERR_ARG, "null argument");
   HostStream r = g.rng.new_stream();  // `RngStream r;` consumes a package stream (microsimulation.cc:66)
   if (mrg_seed_ok(seed)) {            // SetSeed keeps the constructed state when the seed is illegal
     uint32_t s[6];
@@ -174,12 +177,14 @@ double *msim_user_unif_rand(void) {
 }
 
 int msim_mt_set_state(const uint32_t state[625]) {
+  if (!state) return fail(MSIM_ERR_ARG, "null state");
   if (state[0] < 1 || state[0] > 624) return fail(MSIM_ERR_ARG, "MT position must be in 1..624");
   memcpy(g.rng.mt, state, sizeof g.rng.mt);
   g.rng.mt_seeded = true;
   return MSIM_OK;
 }
 int msim_mt_get_state(uint32_t state[625]) {
+  if (!state) return fail(MSIM_ERR_ARG, "null state");
   if (!g.rng.mt_seeded) return fail(MSIM_ERR_STATE, "Mersenne-Twister state not set");
   memcpy(state, g.rng.mt, sizeof g.rng.mt);
   return MSIM_OK;

@@ -555,6 +555,19 @@ def test_calibration_person_mc_cores_like_mclapply(msim, oracle):
     assert not np.array_equal(one["StateOccupancy"], mat)   # as in the reference, mc.cores changes the random numbers
 
 
+def test_null_arguments_with_a_device(msim):
+    """The same with the device initialised: argument checks that sit behind the device check are reached."""
+    import os
+    import fuzz_null_args
+    os.environ["MSIM_FUZZ_INIT"] = "1"
+    try:
+        res = fuzz_null_args.run_all()
+    finally:
+        del os.environ["MSIM_FUZZ_INIT"]
+    crashed = {k: v for k, v in res.items() if v[0] != 0}
+    assert not crashed, crashed
+
+
 def test_kernels_were_launched(msim):
     before = msim.launch_count()
     msim.callPersonSimulation(1000)

@@ -38,6 +38,15 @@ def test_no_cpu_fallback_without_a_device():
         m.callIllnessDeath(5)
 
 
+def test_null_arguments_are_error_codes_not_crashes():
+    """Every entry point of include/msim.h with null pointers: an error code (or a no-op for the free functions)."""
+    import fuzz_null_args
+    res = fuzz_null_args.run_all()
+    assert len(res) >= 30
+    crashed = {k: v for k, v in res.items() if v[0] != 0}
+    assert not crashed, crashed
+
+
 def test_product_never_touches_the_oracle():
     """No import / include / dlopen of anything under oracle/ (or of the host emulation) in the product."""
     pkg = os.path.join(ROOT, "microsimulation_b200")
