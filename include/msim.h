@@ -95,6 +95,11 @@ int64_t msim_launch_count(void);
  * under 1.  Same results either way; the switch exists so tests can check
  * exactly that.  2 = 0 with the repeat taken unconditionally (tests). */
 int msim_set_person_schedule(int which);
+/* R's Mersenne-Twister stream is generated in parallel segments started by jump-ahead when the table of jump
+ * polynomials (mt_jump.bin, next to the library; written at build time) is present and the stream is long; 0
+ * switches that off (one block generates the whole stream).  Same words either way; the switch exists so tests can
+ * check exactly that.  Returns 1 if switched on without a table. */
+int msim_set_mt_parallel(int on);
 /* Sizing of the person-r row-log buffers: expected rows per person (default
  * 1.25; the model logs 1.232) and expected rows beyond a person's first
  * (default 0.26).  A run that needs more is repeated with the exact sizes, so

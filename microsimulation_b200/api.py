@@ -58,6 +58,11 @@ def set_person_schedule(which):
     check(load().msim_set_person_schedule(C.c_int(int(which))))
 
 
+def set_mt_parallel(on=True):
+    """Parallel (jump-ahead) generation of R's Mersenne-Twister stream on / off; returns False if no table is loaded."""
+    return load().msim_set_mt_parallel(C.c_int(int(bool(on)))) == 0
+
+
 def set_rowlog_plan(rows_per_person=1.25, extra_rows_per_person=0.26):
     check(load().msim_set_rowlog_plan(rows_per_person, extra_rows_per_person))
 

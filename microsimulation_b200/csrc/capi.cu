@@ -58,6 +58,9 @@ void msim_shutdown(void) {
                     &g.chain_count, &g.chain_entry, &g.chain_base, &g.calib_out, &g.calib_partial, &g.calib_par, &g.uniforms,
                     &g.first_end, &g.first_tag, &g.ov_fill, &g.ov_tag, &g.ov_start, &g.ov_end,
                     &g.aux, &g.code_in, &g.code_out, &g.sgeom, &g.indiv, &g.gsm_model, &g.gsm_data, &g.gsm_in, &g.gsm_out, &g.slices};
+  if (g.d_mt_table) cudaFree(g.d_mt_table);
+  g.d_mt_table = nullptr;
+  g.mt_table_polys = 0;
   for (DevBuf *b : bufs) {
     if (b->p) cudaFree(b->p);
     b->p = nullptr;
@@ -91,6 +94,11 @@ int msim_set_rowlog_plan(double rows_per_person, double extra_rows_per_person) {
   g.plan_rows = rows_per_person;
   g.plan_extra_rows = extra_rows_per_person;
   return MSIM_OK;
+}
+
+int msim_set_mt_parallel(int on) {
+  g.mt_parallel = on != 0;
+  return (on && g.inited && !g.d_mt_table) ? 1 : MSIM_OK;  // 1: asked for, but mt_jump.bin was not found
 }
 
 int msim_set_person_schedule(int which) {
@@ -595,9 +603,7 @@ int msim_mt_uniforms(int64_t n, double *uniforms_host) {
   if ((rc = ensure(g.uniforms, sizeof(double) * (size_t)n))) return rc;
   CK(cudaMemcpyAsync(g.mt_words.p, &g.rng.mt[1], sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, g.stream));
   if (n_batches > 1) {
-    mt_generate_kernel<<<1, 256, 0, g.stream>>>((uint32_t *)g.mt_words.p, (int)(n_batches - 1));
-    CK(cudaGetLastError());
-    g.launches++;
+    if ((rc = mt_generate((uint32_t *)g.mt_words.p, n_batches * 624))) return rc;
   }
   int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)g.sm_count * 8);
   mt_uniforms_kernel<<<grid, 256, 0, g.stream>>>((const uint32_t *)g.mt_words.p, mti0, n, (double *)g.uniforms.p);

@@ -196,9 +196,7 @@ inline int sequential_run(int64_t n, const typename Traits::Consts &consts, int 
   CK(cudaMemcpyAsync(g.mt_words.p, &g.rng.mt[1], sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, g.stream));
   CK(cudaEventRecord(g.ev0, g.stream));
   if (n_batches > 1) {
-    mt_generate_kernel<<<1, 256, 0, g.stream>>>((uint32_t *)g.mt_words.p, (int)(n_batches - 1));
-    CK(cudaGetLastError());
-    g.launches++;
+    if ((rc = mt_generate((uint32_t *)g.mt_words.p, mt_end))) return rc;
   }
   CohortParams<typename Traits::Consts> p;
   memset(&p, 0, sizeof p);
@@ -282,9 +280,7 @@ inline int stream_offsets_attempt(int64_t n, const typename Traits::Consts &cons
   if ((rc = ensure(g.mt_words, sizeof(uint32_t) * (size_t)mt_end))) return rc;
   CK(cudaMemcpyAsync(g.mt_words.p, &g.rng.mt[1], sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, g.stream));
   if (n_batches > 1) {
-    mt_generate_kernel<<<1, 256, 0, g.stream>>>((uint32_t *)g.mt_words.p, (int)(n_batches - 1));
-    CK(cudaGetLastError());
-    g.launches++;
+    if ((rc = mt_generate((uint32_t *)g.mt_words.p, mt_end))) return rc;
   }
   const int stride = 256;
   const int64_t n_chunks = (n_pos + CHAIN_CHUNK - 1) / CHAIN_CHUNK;

@@ -3,6 +3,7 @@
 // the extern "C" entry points.
 #pragma once
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -37,6 +38,9 @@ struct Ctx {
   cudaStream_t stream = nullptr, own_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
   MrgJump *d_lo = nullptr, *d_hi = nullptr;
+  uint32_t *d_mt_table = nullptr;  // jump-ahead polynomials of MT19937 (mt_jump.bin), null if the file is absent
+  int mt_table_polys = 0;
+  bool mt_parallel = true;         // msim_set_mt_parallel: tests switch the jump-ahead path off to compare
   DevBuf rowlog, prov_start, prov_end, prov_meta, tile_count, partial, dense, small, mt_words, len, starts, chain_exit, chain_count, chain_entry, chain_base, calib_out, calib_partial,
       calib_par, uniforms, first_end, first_tag, ov_fill, ov_tag, ov_start, ov_end, aux, code_in, code_out, sgeom,
       indiv, gsm_model, gsm_data, gsm_in, gsm_out, slices;
@@ -90,6 +94,64 @@ inline int ensure(DevBuf &b, size_t bytes) {
   return MSIM_OK;
 }
 
+// mt_jump.bin (written by microsimulation_b200/mt_jump.py at build time) sits next to the shared library
+inline void load_mt_jump_table() {
+  Dl_info info;
+  if (!dladdr((const void *)&load_mt_jump_table, &info) || !info.dli_fname) return;
+  std::string path(info.dli_fname);
+  const size_t slash = path.rfind('/');
+  path = (slash == std::string::npos ? std::string(".") : path.substr(0, slash)) + "/mt_jump.bin";
+  if (const char *env = getenv("MSIM_MT_JUMP_TABLE")) path = env;
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) return;
+  char magic[4];
+  uint32_t hdr[3];
+  std::vector<uint32_t> tab;
+  bool ok = fread(magic, 1, 4, f) == 4 && memcmp(magic, "MTJ1", 4) == 0 && fread(hdr, 4, 3, f) == 3 &&
+            hdr[0] == (uint32_t)MT_SEGMENT && hdr[2] == (uint32_t)MT_POLY_WORDS && hdr[1] >= 1 && hdr[1] < 65536;
+  if (ok) {
+    tab.resize((size_t)hdr[1] * MT_POLY_WORDS);
+    ok = fread(tab.data(), 4, tab.size(), f) == tab.size();
+  }
+  fclose(f);
+  if (!ok) return;
+  if (cudaMalloc(&g.d_mt_table, tab.size() * 4) != cudaSuccess) {
+    g.d_mt_table = nullptr;
+    return;
+  }
+  if (cudaMemcpy(g.d_mt_table, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(g.d_mt_table);
+    g.d_mt_table = nullptr;
+    return;
+  }
+  g.mt_table_polys = (int)hdr[1];
+}
+
+// The stream behind the state in words[0..624): words [624, total).  Long streams run as parallel segments started by
+// jump-ahead (kernels.cuh); short ones, or all of them without the table, as one block.
+inline int mt_generate(uint32_t *words, int64_t total) {
+  if (total <= 624) return MSIM_OK;
+  int64_t segments = 1;
+  if (g.d_mt_table && g.mt_parallel && total >= 3 * MT_SEGMENT)
+    segments = std::min<int64_t>((total + MT_SEGMENT - 1) / MT_SEGMENT, (int64_t)g.mt_table_polys + 1);
+  if (segments == 1) {
+    mt_segment_kernel<<<1, 256, 0, g.stream>>>(words, total, 0);
+    CK(cudaGetLastError());
+    g.launches++;
+    return MSIM_OK;
+  }
+  // the words a jump reads, then the start states of segments 1.., then all segments side by side
+  CK(cudaMemset2DAsync(words + MT_SEGMENT, sizeof(uint32_t) * MT_SEGMENT, 0, sizeof(uint32_t) * 624, (size_t)(segments - 1), g.stream));
+  mt_segment_kernel<<<1, 256, 0, g.stream>>>(words, MT_JUMP_INPUT, 0);
+  CK(cudaGetLastError());
+  mt_jump_kernel<<<dim3((unsigned)(segments - 1), MT_JUMP_SPLIT), 640, 0, g.stream>>>(words, g.d_mt_table);
+  CK(cudaGetLastError());
+  mt_segment_kernel<<<(unsigned)segments, 256, 0, g.stream>>>(words, total, MT_JUMP_INPUT - 624);
+  CK(cudaGetLastError());
+  g.launches += 3;
+  return MSIM_OK;
+}
+
 inline int ensure_init() {
   if (g.inited) return MSIM_OK;
   int ndev = 0;
@@ -117,6 +179,7 @@ inline int ensure_init() {
   CK(cudaMalloc(&g.d_hi, sizeof(MrgJump) * JUMP_TAB));
   CK(cudaMemcpy(g.d_lo, lo.data(), sizeof(MrgJump) * JUMP_TAB, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(g.d_hi, hi.data(), sizeof(MrgJump) * JUMP_TAB, cudaMemcpyHostToDevice));
+  load_mt_jump_table();  // optional: without it the stream is generated by one block
   g.inited = true;
   return MSIM_OK;
 }

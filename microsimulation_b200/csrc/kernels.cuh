@@ -87,26 +87,39 @@ __global__ void __launch_bounds__(BLOCK) rng_uniforms_kernel(UniformsParams p) {
 }
 
 // ---- Mersenne-Twister stream generation ----------------------------------
-// One block.  words[0..624) holds the current state; writes n_batches further
-// regenerations behind it.  Seen as ONE sequence x[0], x[1], ... (x[624 b + k] =
-// word k of regeneration b) MT19937 is the recurrence
+// words[0..624) holds the current state; the kernels below write the words that follow it.  Seen as ONE sequence
+// x[0], x[1], ... MT19937 is the recurrence
 //     x[n] = x[n-227] ^ twist(x[n-624], x[n-623]),
-// so 227 consecutive elements are independent of one another: each pass of
-// the loop produces 227 of them, reading only elements of earlier passes from
-// a 1024-word circular buffer in shared memory (writes of a pass land at least
-// 170 words away from anything it reads), with ONE barrier per pass.  The
-// stream is serial by nature — 227-wide is all the parallelism it has without
-// polynomial jump-ahead — which makes this kernel the bulk of the
-// sequential-stream models' time.
-__global__ void __launch_bounds__(256) mt_generate_kernel(uint32_t *words, int n_batches) {
+// so 227 consecutive elements are independent of one another: each pass of mt_segment_kernel's loop produces 227 of
+// them, reading only elements of earlier passes from a 1024-word circular buffer in shared memory (writes of a pass
+// land at least 170 words away from anything it reads), with ONE barrier per pass.  That is all the parallelism the
+// recurrence has by itself, and run as one block it used to be the bulk of the sequential-stream models' time.
+//
+// Long streams are therefore cut into segments of MT_SEGMENT words that run side by side.  The state a segment
+// starts from — the 624 words x[pS .. pS+623] — comes from JUMP-AHEAD: from index 1 on the word sequence obeys a
+// GF(2)-linear recurrence with a characteristic polynomial phi of degree 19937, so
+//     x[pS + k] = XOR over the set bits i of g_p of x[1 + k + i],    g_p(t) = t^(pS-1) mod phi(t),
+// a binary convolution of a precomputed polynomial (mt_jump.py writes the table at build time) with the first 20560
+// words of the stream (mt_jump_kernel).  Every word is still exactly R's.
+constexpr int64_t MT_SEGMENT = 65536;          // words per segment; must match mt_jump.py
+constexpr int MT_POLY_WORDS = 624;             // 19937 coefficient bits
+constexpr int MT_JUMP_INPUT = 1 + 19937 + 623;  // words [0, MT_JUMP_INPUT) must exist before a jump
+constexpr int MT_JUMP_SPLIT = 8;               // blocks per jump, each taking a slice of the polynomial
+
+// Block b generates segment p = b: [base + 624, end) from the state words[base .. base+623], where base = p *
+// MT_SEGMENT (block 0: seg0_base, the last 624 words generated so far) and end = (p + 1) * MT_SEGMENT (last block:
+// total).
+__global__ void __launch_bounds__(256) mt_segment_kernel(uint32_t *words, int64_t total, int64_t seg0_base) {
   __shared__ uint32_t x[1024];
   const int t = threadIdx.x;
-  for (int k = t; k < 624; k += 256) x[k] = words[k];
+  const int64_t p = blockIdx.x;
+  const int64_t base = p ? p * MT_SEGMENT : seg0_base;
+  const int64_t end = (p == gridDim.x - 1) ? total : (p + 1) * MT_SEGMENT;
+  for (int k = t; k < 624; k += 256) x[(base + k) & 1023] = words[base + k];
   __syncthreads();
-  const int64_t total = (int64_t)(n_batches + 1) * 624;
-  for (int64_t n = 624; n < total; n += 227) {
+  for (int64_t n = base + 624; n < end; n += 227) {
     const int64_t i = n + t;
-    if (t < 227 && i < total) {
+    if (t < 227 && i < end) {
       const uint32_t a = x[(i - 624) & 1023], b = x[(i - 623) & 1023], c = x[(i - 227) & 1023];
       const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
       const uint32_t v = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
@@ -114,6 +127,34 @@ __global__ void __launch_bounds__(256) mt_generate_kernel(uint32_t *words, int n
       words[i] = v;
     }
     __syncthreads();
+  }
+}
+
+// grid (segments - 1, MT_JUMP_SPLIT), 640 threads.  Block (p - 1, q) XORs into words[p S + k], k < 624 (zeroed
+// beforehand), the terms of polynomial words [q W, (q + 1) W), W = 624 / MT_JUMP_SPLIT: its window of the stream,
+// x[1 + 32 q W .. + 32 W + 623], sits in shared memory, and every thread walks the same set bits (no divergence,
+// consecutive shared-memory addresses across the block).
+__global__ void __launch_bounds__(640) mt_jump_kernel(uint32_t *words, const uint32_t *table) {
+  constexpr int W = MT_POLY_WORDS / MT_JUMP_SPLIT;  // 78 polynomial words = 2496 coefficients per block
+  __shared__ uint32_t win[32 * W + 624];
+  __shared__ uint32_t g[W];
+  const int t = threadIdx.x, q = blockIdx.y;
+  const int64_t p = blockIdx.x + 1;
+  const int first = 1 + 32 * q * W;  // stream index of win[0]
+  for (int k = t; k < 32 * W + 624; k += 640) win[k] = (first + k < MT_JUMP_INPUT) ? words[first + k] : 0u;
+  if (t < W) g[t] = table[(p - 1) * MT_POLY_WORDS + q * W + t];
+  __syncthreads();
+  if (t < 624) {
+    uint32_t acc = 0;
+    for (int w = 0; w < W; w++) {
+      uint32_t bits = g[w];  // the same for every thread
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        acc ^= win[32 * w + b + t];
+      }
+    }
+    if (acc) atomicXor(&words[p * MT_SEGMENT + t], acc);
   }
 }
 

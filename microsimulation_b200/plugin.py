@@ -48,6 +48,10 @@ def build(source, out=None, defines=(), quiet=True):
 
 class Plugin:
     def __init__(self, library, name, consts_type=None):
+        # the plugin's own runtime looks for the Mersenne-Twister jump table next to ITS library; point it at ours
+        table = os.path.join(ROOT, "microsimulation_b200", "mt_jump.bin")
+        if os.path.exists(table):
+            os.environ.setdefault("MSIM_MT_JUMP_TABLE", table)
         self.lib = C.CDLL(library)
         self.name = name
         self._run = getattr(self.lib, name + "_run")
