@@ -144,7 +144,7 @@ inline int mt_generate(uint32_t *words, int64_t total) {
   CK(cudaMemset2DAsync(words + MT_SEGMENT, sizeof(uint32_t) * MT_SEGMENT, 0, sizeof(uint32_t) * 624, (size_t)(segments - 1), g.stream));
   mt_segment_kernel<<<1, 256, 0, g.stream>>>(words, MT_JUMP_INPUT, 0);
   CK(cudaGetLastError());
-  mt_jump_kernel<<<dim3((unsigned)(segments - 1), MT_JUMP_SPLIT), 640, 0, g.stream>>>(words, g.d_mt_table);
+  mt_jump_kernel<<<dim3((unsigned)(segments - 1), MT_JUMP_SPLIT), 160, 0, g.stream>>>(words, g.d_mt_table);
   CK(cudaGetLastError());
   mt_segment_kernel<<<(unsigned)segments, 256, 0, g.stream>>>(words, total, MT_JUMP_INPUT - 624);
   CK(cudaGetLastError());

@@ -130,31 +130,40 @@ __global__ void __launch_bounds__(256) mt_segment_kernel(uint32_t *words, int64_
   }
 }
 
-// grid (segments - 1, MT_JUMP_SPLIT), 640 threads.  Block (p - 1, q) XORs into words[p S + k], k < 624 (zeroed
+// grid (segments - 1, MT_JUMP_SPLIT), 160 threads.  Block (p - 1, q) XORs into words[p S + k], k < 624 (zeroed
 // beforehand), the terms of polynomial words [q W, (q + 1) W), W = 624 / MT_JUMP_SPLIT: its window of the stream,
-// x[1 + 32 q W .. + 32 W + 623], sits in shared memory, and every thread walks the same set bits (no divergence,
-// consecutive shared-memory addresses across the block).
-__global__ void __launch_bounds__(640) mt_jump_kernel(uint32_t *words, const uint32_t *table) {
+// x[1 + 32 q W .. + 32 W + 623], sits in shared memory.  Every thread walks the same set bits (no divergence) for FOUR
+// outputs (k = t, t + 156, t + 312, t + 468), so the bit bookkeeping is shared and the four loads are independent.
+__global__ void __launch_bounds__(160) mt_jump_kernel(uint32_t *words, const uint32_t *table) {
   constexpr int W = MT_POLY_WORDS / MT_JUMP_SPLIT;  // 78 polynomial words = 2496 coefficients per block
+  constexpr int Q = 156;                            // 624 / 4
   __shared__ uint32_t win[32 * W + 624];
   __shared__ uint32_t g[W];
   const int t = threadIdx.x, q = blockIdx.y;
   const int64_t p = blockIdx.x + 1;
   const int first = 1 + 32 * q * W;  // stream index of win[0]
-  for (int k = t; k < 32 * W + 624; k += 640) win[k] = (first + k < MT_JUMP_INPUT) ? words[first + k] : 0u;
+  for (int k = t; k < 32 * W + 624; k += 160) win[k] = (first + k < MT_JUMP_INPUT) ? words[first + k] : 0u;
   if (t < W) g[t] = table[(p - 1) * MT_POLY_WORDS + q * W + t];
   __syncthreads();
-  if (t < 624) {
-    uint32_t acc = 0;
+  if (t < Q) {
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     for (int w = 0; w < W; w++) {
       uint32_t bits = g[w];  // the same for every thread
+      const uint32_t *row = win + 32 * w + t;
       while (bits) {
         const int b = __ffs(bits) - 1;
         bits &= bits - 1;
-        acc ^= win[32 * w + b + t];
+        a0 ^= row[b];
+        a1 ^= row[b + Q];
+        a2 ^= row[b + 2 * Q];
+        a3 ^= row[b + 3 * Q];
       }
     }
-    if (acc) atomicXor(&words[p * MT_SEGMENT + t], acc);
+    uint32_t *out = words + p * MT_SEGMENT + t;
+    if (a0) atomicXor(out, a0);
+    if (a1) atomicXor(out + Q, a1);
+    if (a2) atomicXor(out + 2 * Q, a2);
+    if (a3) atomicXor(out + 3 * Q, a3);
   }
 }
 
@@ -379,7 +388,7 @@ inline size_t cohort_kernel_smem(const ReportGeom &g, unsigned outputs) {
 
 // ---- row log, second pass: tile counts -> offsets, packed rows -> columns --
 
-constexpr int EXPAND_TILES = 2048;  // warp tiles per block of the expand pass
+constexpr int EXPAND_TILES = 256;  // warp tiles (8192 persons) per block of the expand pass: 122 blocks for 1e6 persons
 
 struct ExpandParams {
   const double *prov_start, *prov_end;
