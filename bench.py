@@ -61,7 +61,7 @@ def _cpu_worker(args):
     else:  # builds the row log, as callPersonSimulation does
         r = o.person_run(SEED, first, n, rowlog=True)
     dt = time.perf_counter() - t0
-    return dt, int(r["counts"][:8].sum())
+    return dt, [int(x) for x in r["counts"][:8]]
 
 
 def cpu_reference(sample_per_core, workload, cores=None, repeats=1):
@@ -83,7 +83,8 @@ def cpu_reference(sample_per_core, workload, cores=None, repeats=1):
             v = cores * sample_per_core / wall
             best = v if best is None else max(best, v)
     kind = "reference" if flavour == "ref" else "port"
-    return {"value": best, "unit": UNIT, "cores": cores, "kind": kind,
+    counts = [sum(r[1][k] for r in res) for k in range(8)]  # per event kind, persons [0, cores * sample_per_core)
+    return {"value": best, "unit": UNIT, "cores": cores, "kind": kind, "persons": cores * sample_per_core, "event_counts": counts,
             "sample": "%d persons per process x %d processes (contiguous person ranges, each jumping to its first substream), %s, seed 12345x6"
                       % (sample_per_core, cores, "EventReport (3 percent discounting) + counts" if workload == "report" else "row log built in memory")}
 
@@ -324,6 +325,11 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu_baseline:
         cpu = cpu_reference(args.cpu_sample or (10 ** 6 if report_mode else 5 * 10 ** 6), args.workload)
+        # the persons the CPU reference just simulated, on the GPU: the per-kind event counts must be identical
+        import microsimulation_b200.api as api
+        api.person_run_device(SEED, 0, cpu["persons"], api.MSIM_OUT_COUNTS)
+        gpu_counts = [int(x) for x in api.person_fetch_counts()[:8]]
+        cpu["event_counts_equal_gpu"] = gpu_counts == cpu["event_counts"]
     line = {"metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
