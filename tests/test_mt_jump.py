@@ -51,7 +51,8 @@ def test_table_file_matches_the_generator(phi):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("position,n", [(624, 1_000_000), (1, 250_000), (300, 3_000_000)])
+@pytest.mark.parametrize("position,n", [(624, 1_000_000), (1, 250_000), (300, 3_000_000),
+                                        (624, 20_000_000)])  # the last: beyond the table (255 segments), serial tail
 def test_parallel_stream_equals_the_serial_one(msim, oracle, position, n):
     """The words behind a state, generated as jump-started segments, are R's: against the oracle's MT19937 and against
     the one-block generator."""
