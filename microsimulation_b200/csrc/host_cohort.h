@@ -300,9 +300,30 @@ inline int stream_offsets_attempt(int64_t n, const typename Traits::Consts &cons
   chain_chunk_kernel<<<(unsigned)n_chunks, 256, 0, g.stream>>>((const unsigned char *)g.len.p, n_pos, max_draws, stride,
                                                                (unsigned char *)g.chain_exit.p, (int *)g.chain_count.p);
   CK(cudaGetLastError());
-  chain_scan_kernel<<<1, 256, 0, g.stream>>>((const unsigned char *)g.chain_exit.p, (const int *)g.chain_count.p, n_chunks, n,
-                                             stride, (unsigned char *)g.chain_entry.p, (int64_t *)g.chain_base.p);
-  CK(cudaGetLastError());
+  if (n_chunks > 4 * CHAIN_GROUP) {
+    // groups of chunks composed in parallel, the scan over the groups, then the chunks of every group
+    const int64_t n_groups = (n_chunks + CHAIN_GROUP - 1) / CHAIN_GROUP;
+    if ((rc = ensure(g.chain_gexit, (size_t)n_groups * stride))) return rc;
+    if ((rc = ensure(g.chain_gcount, sizeof(int) * (size_t)n_groups * stride))) return rc;
+    if ((rc = ensure(g.chain_gentry, (size_t)n_groups))) return rc;
+    if ((rc = ensure(g.chain_gbase, sizeof(int64_t) * (size_t)n_groups))) return rc;
+    chain_group_kernel<<<(unsigned)n_groups, 256, 0, g.stream>>>((const unsigned char *)g.chain_exit.p, (const int *)g.chain_count.p,
+                                                                 n_chunks, stride, (unsigned char *)g.chain_gexit.p, (int *)g.chain_gcount.p);
+    CK(cudaGetLastError());
+    chain_scan_kernel<<<1, 256, 0, g.stream>>>((const unsigned char *)g.chain_gexit.p, (const int *)g.chain_gcount.p, n_groups, n,
+                                               stride, (unsigned char *)g.chain_gentry.p, (int64_t *)g.chain_gbase.p);
+    CK(cudaGetLastError());
+    chain_expand_kernel<<<(unsigned)((n_groups + 63) / 64), 64, 0, g.stream>>>(
+        (const unsigned char *)g.chain_exit.p, (const int *)g.chain_count.p, n_chunks, n_groups, n, stride,
+        (const unsigned char *)g.chain_gentry.p, (const int64_t *)g.chain_gbase.p, (unsigned char *)g.chain_entry.p,
+        (int64_t *)g.chain_base.p);
+    CK(cudaGetLastError());
+    g.launches += 2;
+  } else {
+    chain_scan_kernel<<<1, 256, 0, g.stream>>>((const unsigned char *)g.chain_exit.p, (const int *)g.chain_count.p, n_chunks, n,
+                                               stride, (unsigned char *)g.chain_entry.p, (int64_t *)g.chain_base.p);
+    CK(cudaGetLastError());
+  }
   chain_emit_kernel<<<(unsigned)n_chunks, 64, 0, g.stream>>>((const unsigned char *)g.len.p, n_pos, mti0,
                                                              (const unsigned char *)g.chain_entry.p, (const int64_t *)g.chain_base.p,
                                                              n, (int64_t *)g.starts.p, sv.end_word, sv.error);

@@ -41,7 +41,7 @@ struct Ctx {
   uint32_t *d_mt_table = nullptr;  // jump-ahead polynomials of MT19937 (mt_jump.bin), null if the file is absent
   int mt_table_polys = 0;
   bool mt_parallel = true;         // msim_set_mt_parallel: tests switch the jump-ahead path off to compare
-  DevBuf rowlog, prov_start, prov_end, prov_meta, tile_count, partial, dense, small, mt_words, len, starts, chain_exit, chain_count, chain_entry, chain_base, calib_out, calib_partial,
+  DevBuf rowlog, prov_start, prov_end, prov_meta, tile_count, partial, dense, small, mt_words, len, starts, chain_exit, chain_count, chain_entry, chain_base, chain_gexit, chain_gcount, chain_gentry, chain_gbase, calib_out, calib_partial,
       calib_par, uniforms, first_end, first_tag, ov_fill, ov_tag, ov_start, ov_end, aux, code_in, code_out, sgeom,
       indiv, gsm_model, gsm_data, gsm_in, gsm_out, slices;
   int person_kernel = 0;  // 0 = staged schedule (person_staged.cuh), 1 = generic cohort kernel

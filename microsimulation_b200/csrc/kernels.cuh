@@ -549,66 +549,146 @@ __global__ void __launch_bounds__(256) chain_chunk_kernel(const unsigned char *l
   }
 }
 
-// Serial pass over chunks: entry offset and first person index of every chunk.
-// The dependency chain is inherently sequential but tiny; the block stages
-// SCAN_BATCH chunks' tables in shared memory and thread 0 walks them there.
-// entry = 255 marks "chain broken / not reached".
+// Pass over chunks: entry offset and first person index of every chunk (entry = 255 marks "chain broken / not
+// reached").  The dependency chain is sequential — chunk c+1 is entered where chunk c is left — but every link is a
+// table lookup, so the one block does it in two levels: tables are staged in shared memory; groups of SCAN_GROUP
+// chunks are composed for EVERY entry offset in parallel; one thread walks the groups; the groups are expanded in
+// parallel with the exact per-chunk rule (chain_scan_step).  Narrow tables (models with <= 8 draws per person) take
+// 512 chunks per batch; wide tables (stride 256) 32 chunks per batch and are walked chunk by chunk in shared memory.
 constexpr int SCAN_BATCH = 512;
+constexpr int SCAN_GROUP = 8;
+constexpr int SCAN_WIDE_BATCH = 32;
 __global__ void __launch_bounds__(256) chain_scan_kernel(const unsigned char *exit_off, const int *count,
                                                          int64_t n_chunks, int64_t n, int stride, unsigned char *entry,
                                                          int64_t *base) {
-  __shared__ unsigned char s_exit[SCAN_BATCH * CHAIN_MAX_DRAWS];
-  __shared__ int s_count[SCAN_BATCH * CHAIN_MAX_DRAWS];
+  // narrow: 512 x 8 exits (4 KB) + counts (16 KB); wide: 32 x 256 exits (8 KB) + counts (32 KB, the larger)
+  __shared__ unsigned char s_exit[SCAN_WIDE_BATCH * 256];
+  __shared__ int s_count[SCAN_WIDE_BATCH * 256];
   __shared__ unsigned char s_entry[SCAN_BATCH];
   __shared__ int64_t s_base[SCAN_BATCH];
+  __shared__ unsigned char g_exit[(SCAN_BATCH / SCAN_GROUP) * CHAIN_MAX_DRAWS];
+  __shared__ int g_count[(SCAN_BATCH / SCAN_GROUP) * CHAIN_MAX_DRAWS];
+  __shared__ unsigned char g_entry[SCAN_BATCH / SCAN_GROUP];
+  __shared__ int64_t g_base[SCAN_BATCH / SCAN_GROUP];
   __shared__ int s_e;
   __shared__ int64_t s_b;
-  if (stride > CHAIN_MAX_DRAWS) {
-    // wide tables (models with many draws per person): thread 0 follows the chain through global memory
-    if (threadIdx.x == 0) {
-      int e = 0;
-      int64_t b = 0;
-      for (int64_t c = 0; c < n_chunks; c++) {
-        entry[c] = (unsigned char)e;
-        base[c] = b;
-        if (e == 255 || b >= n) {
-          e = 255;
-        } else {
-          b += count[c * stride + e];
-          e = exit_off[c * stride + e];
-        }
-      }
-    }
-    return;
-  }
+  static_assert(SCAN_BATCH * CHAIN_MAX_DRAWS <= SCAN_WIDE_BATCH * 256, "shared tables are sized by the wide layout");
   if (threadIdx.x == 0) {
     s_e = 0;
     s_b = 0;
   }
+  if (stride > CHAIN_MAX_DRAWS) {
+    // wide tables: stage 32 chunks at a time, thread 0 follows the chain in shared memory
+    for (int64_t c0 = 0; c0 < n_chunks; c0 += SCAN_WIDE_BATCH) {
+      const int m = (int)((n_chunks - c0 < SCAN_WIDE_BATCH) ? (n_chunks - c0) : SCAN_WIDE_BATCH);
+      __syncthreads();
+      for (int k = threadIdx.x; k < m * stride; k += blockDim.x) {
+        s_exit[k] = exit_off[c0 * stride + k];
+        s_count[k] = count[c0 * stride + k];
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int e = s_e;
+        int64_t b = s_b;
+        for (int c = 0; c < m; c++) {
+          s_entry[c] = (unsigned char)e;
+          s_base[c] = b;
+          chain_scan_step(&s_exit[c * stride], &s_count[c * stride], n, &e, &b);
+        }
+        s_e = e;
+        s_b = b;
+      }
+      __syncthreads();
+      for (int k = threadIdx.x; k < m; k += blockDim.x) {
+        entry[c0 + k] = s_entry[k];
+        base[c0 + k] = s_base[k];
+      }
+    }
+    return;
+  }
   for (int64_t c0 = 0; c0 < n_chunks; c0 += SCAN_BATCH) {
-    int m = (int)((n_chunks - c0 < SCAN_BATCH) ? (n_chunks - c0) : SCAN_BATCH);
+    const int m = (int)((n_chunks - c0 < SCAN_BATCH) ? (n_chunks - c0) : SCAN_BATCH);
+    const int n_groups = (m + SCAN_GROUP - 1) / SCAN_GROUP;
+    __syncthreads();
     for (int k = threadIdx.x; k < m * CHAIN_MAX_DRAWS; k += blockDim.x) {
       s_exit[k] = exit_off[c0 * CHAIN_MAX_DRAWS + k];
       s_count[k] = count[c0 * CHAIN_MAX_DRAWS + k];
     }
     __syncthreads();
+    // every group, from every entry offset: where the chain leaves it and how many persons start inside
+    for (int k = threadIdx.x; k < n_groups * CHAIN_MAX_DRAWS; k += blockDim.x) {
+      const int grp = k / CHAIN_MAX_DRAWS;
+      int e = k % CHAIN_MAX_DRAWS, cnt = 0;
+      const int c_end = min(m, (grp + 1) * SCAN_GROUP);
+      for (int c = grp * SCAN_GROUP; c < c_end && e != 255; c++) {
+        cnt += s_count[c * CHAIN_MAX_DRAWS + e];
+        e = s_exit[c * CHAIN_MAX_DRAWS + e];
+        if (e != 255 && e >= CHAIN_MAX_DRAWS) e = 255;  // cannot happen for a model within its draw bound
+      }
+      g_exit[k] = (unsigned char)e;
+      g_count[k] = cnt;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
       int e = s_e;
       int64_t b = s_b;
-      for (int c = 0; c < m; c++) {
+      for (int grp = 0; grp < n_groups; grp++) {
+        g_entry[grp] = (unsigned char)e;
+        g_base[grp] = b;
+        // past person n, or broken: everything behind is 255 (the exact rule is applied chunk by chunk below)
+        chain_scan_step(&g_exit[grp * CHAIN_MAX_DRAWS], &g_count[grp * CHAIN_MAX_DRAWS], n, &e, &b);
+      }
+      s_e = e;
+      s_b = b;
+    }
+    __syncthreads();
+    for (int grp = threadIdx.x; grp < n_groups; grp += blockDim.x) {
+      int e = g_entry[grp];
+      int64_t b = g_base[grp];
+      const int c_end = min(m, (grp + 1) * SCAN_GROUP);
+      for (int c = grp * SCAN_GROUP; c < c_end; c++) {
         s_entry[c] = (unsigned char)e;
         s_base[c] = b;
         chain_scan_step(&s_exit[c * CHAIN_MAX_DRAWS], &s_count[c * CHAIN_MAX_DRAWS], n, &e, &b);
       }
-      s_e = e;
-      s_b = b;
     }
     __syncthreads();
     for (int k = threadIdx.x; k < m; k += blockDim.x) {
       entry[c0 + k] = s_entry[k];
       base[c0 + k] = s_base[k];
     }
-    __syncthreads();
+  }
+}
+
+// Wide tables, many chunks: one more level across blocks.  chain_group_kernel composes CHAIN_GROUP consecutive chunks
+// for every entry offset (one block per group, one thread per offset), chain_scan_kernel then runs over the GROUPS, and
+// chain_expand_kernel walks each group's chunks from the group's resolved entry with the exact per-chunk rule.
+constexpr int CHAIN_GROUP = 32;
+__global__ void __launch_bounds__(256) chain_group_kernel(const unsigned char *exit_off, const int *count, int64_t n_chunks,
+                                                          int stride, unsigned char *g_exit, int *g_count) {
+  const int64_t grp = blockIdx.x;
+  int e = threadIdx.x, cnt = 0;
+  if (e >= stride) return;
+  const int64_t c_end = min(n_chunks, (grp + 1) * CHAIN_GROUP);
+  for (int64_t c = grp * CHAIN_GROUP; c < c_end && e != 255; c++) {
+    cnt += count[c * stride + e];
+    e = exit_off[c * stride + e];
+  }
+  g_exit[grp * stride + threadIdx.x] = (unsigned char)e;
+  g_count[grp * stride + threadIdx.x] = cnt;
+}
+__global__ void __launch_bounds__(64) chain_expand_kernel(const unsigned char *exit_off, const int *count, int64_t n_chunks,
+                                                          int64_t n_groups, int64_t n, int stride, const unsigned char *g_entry,
+                                                          const int64_t *g_base, unsigned char *entry, int64_t *base) {
+  const int64_t grp = (int64_t)blockIdx.x * 64 + threadIdx.x;
+  if (grp >= n_groups) return;
+  int e = g_entry[grp];
+  int64_t b = g_base[grp];
+  const int64_t c_end = min(n_chunks, (grp + 1) * CHAIN_GROUP);
+  for (int64_t c = grp * CHAIN_GROUP; c < c_end; c++) {
+    entry[c] = (unsigned char)e;
+    base[c] = b;
+    chain_scan_step(exit_off + c * stride, count + c * stride, n, &e, &b);
   }
 }
 
