@@ -1,6 +1,6 @@
 """Quick GPU parity + timing probe (development aid; the real checks are tests/ -m gpu)."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import microsimulation_b200 as m
 from oracle.pyoracle import Oracle

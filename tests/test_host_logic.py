@@ -52,11 +52,13 @@ def test_product_never_touches_the_oracle():
     pkg = os.path.join(ROOT, "microsimulation_b200")
     bad = re.compile(r"(#include\s*[\"<][^\n]*oracle|import\s+oracle|from\s+oracle|pyoracle|libmsim_oracle|"
                      r"host_emulation/|libmsim_emu)")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
-                src = open(os.path.join(dirpath, f)).read()
-                assert not bad.search(src), f
+    for top in (pkg, os.path.join(ROOT, "scripts"), os.path.join(ROOT, "glue"), os.path.join(ROOT, "examples"),
+                os.path.join(ROOT, "include")):
+        for dirpath, _, files in os.walk(top):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cpp", ".sh")):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert not bad.search(src), os.path.join(dirpath, f)
 
 
 def test_host_rng_state_machine_matches_oracle(oracle):
