@@ -293,6 +293,11 @@ def roofline_of(workload, meas, P):
                               "ncu_issue_active_pct": tr.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                               "ncu_threads_per_warp_inst": tr.get("smsp__thread_inst_executed_per_inst_executed.ratio"),
                               "source": "profiles/traffic.json (ncu --set full of the same kernel)"}
+                lanes = tr.get("smsp__thread_inst_executed_per_inst_executed.ratio")
+                if lanes:
+                    # against the work of warps with zero divergence (thread instructions / 32)
+                    r["issue"]["lane_efficiency"] = lanes / 32.0
+                    r["issue"]["frac_divergence_free"] = r["issue"]["frac"] * lanes / 32.0
         except Exception as e:  # a missing profile must not break the bench
             r["issue_error"] = str(e)
     return r
