@@ -131,22 +131,29 @@ inline void load_mt_jump_table() {
 // jump-ahead (kernels.cuh); short ones, or all of them without the table, as one block.
 inline int mt_generate(uint32_t *words, int64_t total) {
   if (total <= 624) return MSIM_OK;
-  int64_t segments = 1;
-  if (g.d_mt_table && g.mt_parallel && total >= 3 * MT_SEGMENT)
-    segments = std::min<int64_t>((total + MT_SEGMENT - 1) / MT_SEGMENT, (int64_t)g.mt_table_polys + 1);
-  if (segments == 1) {
-    mt_segment_kernel<<<1, 256, 0, g.stream>>>(words, total, 0);
+  int64_t segments = 1, mult = 1;
+  if (g.d_mt_table && g.mt_parallel && total >= 3 * MT_SEGMENT) {
+    // a jump costs about as much as generating 1/19 of a table segment: with P segments of mult table segments each,
+    // time ~ P + 19 * mult, so mult ~ sqrt(table segments / 19); longer segments also reach further with one table
+    const double tab = (double)total / (double)MT_SEGMENT;
+    mult = std::max<int64_t>(1, (int64_t)(sqrt(tab / 19.0) + 0.5));
+    while ((total + mult * MT_SEGMENT - 1) / (mult * MT_SEGMENT) - 1 > g.mt_table_polys / mult && mult < 64) mult++;
+    segments = std::min<int64_t>((total + mult * MT_SEGMENT - 1) / (mult * MT_SEGMENT), (int64_t)(g.mt_table_polys / mult) + 1);
+  }
+  if (segments <= 1) {
+    mt_segment_kernel<<<1, 256, 0, g.stream>>>(words, total, 0, total);
     CK(cudaGetLastError());
     g.launches++;
     return MSIM_OK;
   }
+  const int64_t seg = mult * MT_SEGMENT;
   // the words a jump reads, then the start states of segments 1.., then all segments side by side
-  CK(cudaMemset2DAsync(words + MT_SEGMENT, sizeof(uint32_t) * MT_SEGMENT, 0, sizeof(uint32_t) * 624, (size_t)(segments - 1), g.stream));
-  mt_segment_kernel<<<1, 256, 0, g.stream>>>(words, MT_JUMP_INPUT, 0);
+  CK(cudaMemset2DAsync(words + seg, sizeof(uint32_t) * seg, 0, sizeof(uint32_t) * 624, (size_t)(segments - 1), g.stream));
+  mt_segment_kernel<<<1, 256, 0, g.stream>>>(words, MT_JUMP_INPUT, 0, MT_JUMP_INPUT);
   CK(cudaGetLastError());
-  mt_jump_kernel<<<dim3((unsigned)(segments - 1), MT_JUMP_SPLIT), 160, 0, g.stream>>>(words, g.d_mt_table);
+  mt_jump_kernel<<<dim3((unsigned)(segments - 1), MT_JUMP_SPLIT), 160, 0, g.stream>>>(words, g.d_mt_table, (int)mult);
   CK(cudaGetLastError());
-  mt_segment_kernel<<<(unsigned)segments, 256, 0, g.stream>>>(words, total, MT_JUMP_INPUT - 624);
+  mt_segment_kernel<<<(unsigned)segments, 256, 0, g.stream>>>(words, total, MT_JUMP_INPUT - 624, seg);
   CK(cudaGetLastError());
   g.launches += 3;
   return MSIM_OK;

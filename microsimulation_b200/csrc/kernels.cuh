@@ -106,15 +106,15 @@ constexpr int MT_POLY_WORDS = 624;             // 19937 coefficient bits
 constexpr int MT_JUMP_INPUT = 1 + 19937 + 623;  // words [0, MT_JUMP_INPUT) must exist before a jump
 constexpr int MT_JUMP_SPLIT = 8;               // blocks per jump, each taking a slice of the polynomial
 
-// Block b generates segment p = b: [base + 624, end) from the state words[base .. base+623], where base = p *
-// MT_SEGMENT (block 0: seg0_base, the last 624 words generated so far) and end = (p + 1) * MT_SEGMENT (last block:
-// total).
-__global__ void __launch_bounds__(256) mt_segment_kernel(uint32_t *words, int64_t total, int64_t seg0_base) {
+// Block b generates segment p = b: [base + 624, end) from the state words[base .. base+623], where base = p * seg
+// (block 0: seg0_base, the last 624 words generated so far) and end = (p + 1) * seg (last block: total).  seg is a
+// multiple of MT_SEGMENT: the host picks it so that jumping and generating take about equally long.
+__global__ void __launch_bounds__(256) mt_segment_kernel(uint32_t *words, int64_t total, int64_t seg0_base, int64_t seg) {
   __shared__ uint32_t x[1024];
   const int t = threadIdx.x;
   const int64_t p = blockIdx.x;
-  const int64_t base = p ? p * MT_SEGMENT : seg0_base;
-  const int64_t end = (p == gridDim.x - 1) ? total : (p + 1) * MT_SEGMENT;
+  const int64_t base = p ? p * seg : seg0_base;
+  const int64_t end = (p == gridDim.x - 1) ? total : (p + 1) * seg;
   for (int k = t; k < 624; k += 256) x[(base + k) & 1023] = words[base + k];
   __syncthreads();
   for (int64_t n = base + 624; n < end; n += 227) {
@@ -130,11 +130,12 @@ __global__ void __launch_bounds__(256) mt_segment_kernel(uint32_t *words, int64_
   }
 }
 
-// grid (segments - 1, MT_JUMP_SPLIT), 160 threads.  Block (p - 1, q) XORs into words[p S + k], k < 624 (zeroed
+// grid (segments - 1, MT_JUMP_SPLIT), 160 threads; segments are `mult` table segments long (polynomial p * mult - 1
+// of the table).  Block (p - 1, q) XORs into words[p S + k], k < 624 (zeroed
 // beforehand), the terms of polynomial words [q W, (q + 1) W), W = 624 / MT_JUMP_SPLIT: its window of the stream,
 // x[1 + 32 q W .. + 32 W + 623], sits in shared memory.  Every thread walks the same set bits (no divergence) for FOUR
 // outputs (k = t, t + 156, t + 312, t + 468), so the bit bookkeeping is shared and the four loads are independent.
-__global__ void __launch_bounds__(160) mt_jump_kernel(uint32_t *words, const uint32_t *table) {
+__global__ void __launch_bounds__(160) mt_jump_kernel(uint32_t *words, const uint32_t *table, int mult) {
   constexpr int W = MT_POLY_WORDS / MT_JUMP_SPLIT;  // 78 polynomial words = 2496 coefficients per block
   constexpr int Q = 156;                            // 624 / 4
   __shared__ uint32_t win[32 * W + 624];
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(160) mt_jump_kernel(uint32_t *words, const uin
   const int64_t p = blockIdx.x + 1;
   const int first = 1 + 32 * q * W;  // stream index of win[0]
   for (int k = t; k < 32 * W + 624; k += 160) win[k] = (first + k < MT_JUMP_INPUT) ? words[first + k] : 0u;
-  if (t < W) g[t] = table[(p - 1) * MT_POLY_WORDS + q * W + t];
+  if (t < W) g[t] = table[(p * mult - 1) * MT_POLY_WORDS + q * W + t];
   __syncthreads();
   if (t < Q) {
     uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(160) mt_jump_kernel(uint32_t *words, const uin
         a3 ^= row[b + 3 * Q];
       }
     }
-    uint32_t *out = words + p * MT_SEGMENT + t;
+    uint32_t *out = words + p * mult * MT_SEGMENT + t;
     if (a0) atomicXor(out, a0);
     if (a1) atomicXor(out + Q, a1);
     if (a2) atomicXor(out + 2 * Q, a2);
