@@ -106,6 +106,17 @@ def test_next_rng_stream_matches_the_reference_jump(oracle, oracle_ref):
         port = (C.c_double * 6)(*[float(x) for x in seed])
         assert oracle.lib.oracle_rng_advance_e(port, 51, 0) == 0
         assert m.next_rng_stream(seed) == [int(x) for x in want] == [int(x) for x in port]
+    # the reference's own known answers (src/rngstream-example.cpp:9-13): first uniform of stream 1, of stream 2, and
+    # of stream 1's second substream, through the hook R-level runif() uses
+    s2 = m.next_rng_stream([12345] * 6)
+    assert s2 == [3692455944, 1366884236, 2968912127, 335948734, 4161675175, 475798818]
+    m.set_user_random_seed(12345)
+    assert round(float(m.user_unif_rand(1)[0]), 6) == 0.127011
+    m.set_user_random_seed(s2)
+    assert round(float(m.user_unif_rand(1)[0]), 6) == 0.759582
+    m.set_user_random_seed(12345)
+    m.next_user_random_substream()
+    assert round(float(m.user_unif_rand(1)[0]), 6) == 0.079399
     with pytest.raises(m.MsimError):
         m.next_rng_stream([0, 0, 0, 1, 1, 1])
     assert m.calibration_chunks(10, 3) == [4, 3, 3] and m.calibration_chunks(2, 4) == [1, 1, 0, 0]
