@@ -112,6 +112,17 @@ def test_documented_model_substream_regime_shards(doc_plugin):
 
 
 @pytest.mark.gpu
+def test_speed_test_model_of_the_reference():
+    """callSpeedTest's VerySimple process (src/person-r.cc:234-255): two events each, nothing else."""
+    import struct
+    from microsimulation_b200 import plugin
+    p = plugin.Plugin(plugin.build(os.path.join(PLUGINS, "very_simple.cu")), "very_simple")
+    values, _ = p.run(10**6, struct.pack("i", 0), seed=[12345] * 6)
+    assert values["events"].shape == (10**6,) and np.all(values["events"] == 2.0)
+    # (no timing claim: with two constant event times and an empty handler the compiler folds the whole life away)
+
+
+@pytest.mark.gpu
 def test_heap_capacity_overflow_is_an_error_code():
     from microsimulation_b200 import MsimError, plugin
     lib = plugin.build(os.path.join(PLUGINS, "illness_death_doc.cu"), out=os.path.join(ROOT, "build", "libillness_death_doc_cap3.so"),
