@@ -555,6 +555,29 @@ def test_calibration_person_mc_cores_like_mclapply(msim, oracle):
     assert not np.array_equal(one["StateOccupancy"], mat)   # as in the reference, mc.cores changes the random numbers
 
 
+def test_gpu_against_the_reference_linked_oracle(msim, oracle_ref):
+    """The same comparisons with the oracle build that links the reference's OWN ssim.cc / RngStream.cpp / heap.h
+    (oracle/_ref, prebuilt where /root/reference exists): event loop, heap order and generator are the reference's."""
+    import microsimulation_b200.api as api
+    assert oracle_ref.flavour == "reference"
+    assert_rowlog_close(msim.callPersonSimulation(30000), oracle_ref.callPersonSimulation(30000))
+    rep, counts = msim.person_report(12345, 500, 40000, 0.03)
+    ref = oracle_ref.person_run(12345, 500, 40000, rowlog=False, report=True, discount_rate=0.03)
+    assert np.array_equal(counts[:8], ref["counts"][:8])
+    assert_report_close(rep, ref["report"])
+    assert_report_close(msim.callIllnessDeath(50000, 0.1, 0.0), oracle_ref.callIllnessDeath(50000, 0.1, 0.0))
+    assert_rowlog_close(msim.callSimplePerson(50000), oracle_ref.callSimplePerson(50000), end_col="endtime")
+    g, r = msim.callCalibrationPerson(10, 20000)["raw"], oracle_ref.callCalibrationPerson(10, 20000)
+    assert set(g) == set(r)
+    for k in r:
+        if k == "TimeAtRisk":
+            np.testing.assert_allclose(g[k], r[k], rtol=1e-12)
+        else:
+            assert np.array_equal(g[k], r[k]), k
+    par = api.sick_sicker_param(True)
+    _summary_equal(api.callSim(3000, par), oracle_ref.sick_sicker(3000, par))
+
+
 def test_null_arguments_with_a_device(msim):
     """The same with the device initialised: argument checks that sit behind the device check are reached."""
     import os
