@@ -57,7 +57,7 @@ void msim_shutdown(void) {
   DevBuf *bufs[] = {&g.rowlog, &g.prov_start, &g.prov_end, &g.prov_meta, &g.tile_count, &g.partial, &g.dense, &g.small, &g.mt_words, &g.len, &g.starts, &g.chain_exit,
                     &g.chain_count, &g.chain_entry, &g.chain_base, &g.chain_gexit, &g.chain_gcount, &g.chain_gentry, &g.chain_gbase, &g.calib_out, &g.calib_partial, &g.calib_par, &g.uniforms,
                     &g.first_end, &g.first_tag, &g.ov_fill, &g.ov_tag, &g.ov_start, &g.ov_end,
-                    &g.aux, &g.code_in, &g.code_out, &g.sgeom, &g.indiv, &g.gsm_model, &g.gsm_data, &g.gsm_in, &g.gsm_out, &g.slices};
+                    &g.aux, &g.code_in, &g.code_out, &g.sgeom, &g.indiv, &g.gsm_model, &g.gsm_data, &g.gsm_in, &g.gsm_out, &g.slices, &g.carry_tiles};
   if (g.d_mt_table) cudaFree(g.d_mt_table);
   g.d_mt_table = nullptr;
   g.mt_table_polys = 0;

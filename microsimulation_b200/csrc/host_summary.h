@@ -32,8 +32,16 @@ int sick_launch(SickParams &p, int64_t n, bool substreams, const HostStream &hs,
     gather_code_kernel<<<g.sm_count * 4, 256, 0, g.stream>>>((const unsigned char *)g.aux.p, p.starts, (int64_t)g.rng.mt[0], n,
                                                              p.code_out);
     CK(cudaGetLastError());
-    carry_scan_kernel<<<1, 1024, 0, g.stream>>>(p.code_out, n, 0, (unsigned char *)g.code_in.p);
-    CK(cudaGetLastError());
+    {
+      const unsigned tiles = (unsigned)((n + CARRY_TILE - 1) / CARRY_TILE);
+      if ((rc = ensure(g.carry_tiles, tiles))) return rc;
+      carry_tile_kernel<<<tiles, 256, 0, g.stream>>>(p.code_out, n, (unsigned char *)g.carry_tiles.p);
+      CK(cudaGetLastError());
+      carry_apply_kernel<<<tiles, 256, 0, g.stream>>>(p.code_out, n, 0, (const unsigned char *)g.carry_tiles.p,
+                                                      (unsigned char *)g.code_in.p);
+      CK(cudaGetLastError());
+      g.launches++;
+    }
     auto kern = sick_kernel<true, ORDERED>;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, BLOCK, smem, g.stream>>>(p);
@@ -43,8 +51,16 @@ int sick_launch(SickParams &p, int64_t n, bool substreams, const HostStream &hs,
     stream_start(hs.Cg.s, first_person, (int64_t)grid * BLOCK, &p.st);
     sick_code_kernel<ORDERED><<<grid, BLOCK, 0, g.stream>>>(p);
     CK(cudaGetLastError());
-    carry_scan_kernel<<<1, 1024, 0, g.stream>>>(p.code_out, n, 0, (unsigned char *)g.code_in.p);
-    CK(cudaGetLastError());
+    {
+      const unsigned tiles = (unsigned)((n + CARRY_TILE - 1) / CARRY_TILE);
+      if ((rc = ensure(g.carry_tiles, tiles))) return rc;
+      carry_tile_kernel<<<tiles, 256, 0, g.stream>>>(p.code_out, n, (unsigned char *)g.carry_tiles.p);
+      CK(cudaGetLastError());
+      carry_apply_kernel<<<tiles, 256, 0, g.stream>>>(p.code_out, n, 0, (const unsigned char *)g.carry_tiles.p,
+                                                      (unsigned char *)g.code_in.p);
+      CK(cudaGetLastError());
+      g.launches++;
+    }
     auto kern = sick_kernel<false, ORDERED>;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, BLOCK, smem, g.stream>>>(p);

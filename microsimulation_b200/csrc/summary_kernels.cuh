@@ -9,7 +9,7 @@
 // The report's utility and cost carry over from one person to the next in the
 // reference (models.cuh, sick_sicker::uc_of_code).  A first pass therefore
 // finds each person's LAST set_uc() code (sick_code_kernel, or the draw-count
-// pass in the stream regime), carry_scan_kernel turns that into the code each
+// pass in the stream regime), carry_tile_kernel / carry_apply_kernel turn that into the code each
 // person starts with, and only then does sick_kernel run the persons.
 #pragma once
 #include "kernels.cuh"
@@ -72,35 +72,73 @@ __global__ void gather_code_kernel(const unsigned char *aux, const int64_t *star
     code_out[i] = aux[starts[i] - first_word];
 }
 
-// code_in[i] = last non-zero code_out[j], j < i (code0 if none): an exclusive scan under "last writer wins".
-// One block; the n bytes are read once.
-__global__ void __launch_bounds__(1024) carry_scan_kernel(const unsigned char *code_out, int64_t n, int code0,
-                                                          unsigned char *code_in) {
-  __shared__ int s_w[32];
-  __shared__ int s_carry;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_carry = code0;
-  __syncthreads();
-  for (int64_t i0 = 0; i0 < n; i0 += 1024) {
-    const int64_t i = i0 + tid;
-    const int v = (i < n) ? code_out[i] : 0;
-    int incl = v;  // inclusive scan: last non-zero among lanes <= this one
+// code_in[i] = last non-zero code_out[j], j < i (code0 if none): an exclusive scan under "last writer wins", in two
+// launches over tiles of CARRY_TILE persons: every tile's last non-zero code (carry_tile_kernel), then per tile the
+// carry from the tiles before it and the scan inside it (carry_apply_kernel).
+constexpr int CARRY_TILE = 4096;
+constexpr int CARRY_PER = CARRY_TILE / 256;  // consecutive persons per thread
+
+// last non-zero among this thread's CARRY_PER consecutive codes, then among the block's threads up to and including t
+__device__ __forceinline__ int carry_block_inclusive(int mine, int *s_w) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = mine;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o && incl == 0) incl = t;
-    }
-    int excl = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane == 0) excl = 0;
-    if (lane == 31) s_w[warp] = incl;
-    __syncthreads();
-    int before = s_carry;  // last non-zero before this warp
-    for (int w = 0; w < warp; w++)
-      if (s_w[w]) before = s_w[w];
-    if (i < n) code_in[i] = (unsigned char)(excl ? excl : before);
-    __syncthreads();
-    if (tid == 1023) s_carry = incl ? incl : before;
-    __syncthreads();
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o && incl == 0) incl = t;
+  }
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  if (incl == 0)
+    for (int w = warp - 1; w >= 0 && incl == 0; w--) incl = s_w[w];
+  return incl;
+}
+
+__global__ void __launch_bounds__(256) carry_tile_kernel(const unsigned char *code_out, int64_t n, unsigned char *tile_last) {
+  __shared__ int s_w[8];
+  const int64_t lo = (int64_t)blockIdx.x * CARRY_TILE + (int64_t)threadIdx.x * CARRY_PER;
+  int mine = 0;
+#pragma unroll
+  for (int k = 0; k < CARRY_PER; k++) {
+    const int v = (lo + k < n) ? code_out[lo + k] : 0;
+    if (v) mine = v;
+  }
+  const int incl = carry_block_inclusive(mine, s_w);
+  if (threadIdx.x == 255) tile_last[blockIdx.x] = (unsigned char)incl;
+}
+
+__global__ void __launch_bounds__(256) carry_apply_kernel(const unsigned char *code_out, int64_t n, int code0,
+                                                          const unsigned char *tile_last, unsigned char *code_in) {
+  __shared__ int s_w[8];
+  __shared__ int s_before;
+  if (threadIdx.x == 0) {
+    int before = code0;  // last non-zero code of the tiles before this one
+    for (int64_t j = (int64_t)blockIdx.x - 1; j >= 0; j--)
+      if (tile_last[j]) {
+        before = tile_last[j];
+        break;
+      }
+    s_before = before;
+  }
+  const int64_t lo = (int64_t)blockIdx.x * CARRY_TILE + (int64_t)threadIdx.x * CARRY_PER;
+  int v[CARRY_PER], mine = 0;
+#pragma unroll
+  for (int k = 0; k < CARRY_PER; k++) {
+    v[k] = (lo + k < n) ? code_out[lo + k] : 0;
+    if (v[k]) mine = v[k];
+  }
+  const int incl = carry_block_inclusive(mine, s_w);  // (contains the barrier that publishes s_before)
+  // exclusive over threads: the inclusive value of the thread before this one
+  int carry = __shfl_up_sync(0xffffffffu, incl, 1);
+  if ((threadIdx.x & 31) == 0) {
+    carry = 0;
+    for (int w = (threadIdx.x >> 5) - 1; w >= 0 && carry == 0; w--) carry = s_w[w];
+  }
+  if (carry == 0) carry = s_before;
+#pragma unroll
+  for (int k = 0; k < CARRY_PER; k++) {
+    if (lo + k < n) code_in[lo + k] = (unsigned char)carry;
+    if (v[k]) carry = v[k];
   }
 }
 
