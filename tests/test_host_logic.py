@@ -38,6 +38,20 @@ def test_no_cpu_fallback_without_a_device():
         m.callIllnessDeath(5)
 
 
+@pytest.mark.parametrize("header", ["msim.h", "msim_plugin.h"])
+def test_public_headers_are_plain_c(header):
+    """The drop-in boundary is a C ABI: both headers compile as C99 (pedantic) and as C++11, with nothing but <stdint.h>."""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    for cc, std, lang in (("gcc", "-std=c99", "c"), ("g++", "-std=c++11", "c++")):
+        r = subprocess.run([cc, std, "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + inc, "-fsyntax-only", "-x", lang, "-"],
+                           input='#include "%s"\nint main(void) { return 0; }\n' % header, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    src = open(os.path.join(inc, header)).read()
+    includes = re.findall(r"#include\s*[<\"]([^>\"]+)", src)
+    assert set(includes) <= {"stdint.h", "stddef.h", "msim.h"}, includes   # no torch, CUDA, R or C++ headers
+
+
 def test_null_arguments_are_error_codes_not_crashes():
     """Every entry point of include/msim.h with null pointers: an error code (or a no-op for the free functions)."""
     import fuzz_null_args
