@@ -89,11 +89,11 @@ int64_t msim_launch_count(void);
 /* Which GPU schedule the person-r entry points use: 0 (default) = staged
  * (persons are regrouped between stages so that warps stay full,
  * csrc/person_staged.cuh), 1 = generic (one person per thread straight
- * through, the kernel every other model uses).  The calibration model keeps its
- * pending actions in an ordered array under 0 (a run in which two pending
- * actions compared equal is repeated with the heap) and in heap.h's binary heap
- * under 1.  Same results either way; the switch exists so tests can check
- * exactly that.  2 = 0 with the repeat taken unconditionally (tests). */
+ * through, the kernel every other model uses).  The calibration and Sick-Sicker
+ * models keep their pending actions in an ordered array under 0 (a run in which
+ * two pending actions compared equal is repeated with the heap) and in heap.h's
+ * binary heap under 1.  Same results either way; the switch exists so tests can
+ * check exactly that.  2 = 0 with the repeat taken unconditionally (tests). */
 int msim_set_person_schedule(int which);
 /* R's Mersenne-Twister stream is generated in parallel segments started by jump-ahead when the table of jump
  * polynomials (mt_jump.bin, next to the library; written at build time) is present and the stream is long; 0
