@@ -896,15 +896,31 @@ __global__ void __launch_bounds__(256) lookup_kernel(LookupParams p) {
 
 // ---- generalised survival model: one inversion per thread ----------------
 // mode 0: randU(u, tentry, index), 1: randU0(u, index), 2: eta(y = u, index)
-__global__ void __launch_bounds__(128) gsm_kernel(const GsmModel *M, int mode, int64_t n, const double *u, const double *tentry,
+__global__ void __launch_bounds__(128) gsm_kernel(const GsmModel *M_global, int mode, int64_t n, const double *u, const double *tentry,
                                                   const int *index, double scale, double *out) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int idx = index ? index[i] : 0;
-    double r;
-    if (mode == 0) r = gsm_randU(*M, u[i], tentry ? tentry[i] : 0.0, idx, scale);
-    else if (mode == 1) r = gsm_randU0(*M, u[i], idx, scale);
-    else r = gsm_eta(*M, idx, u[i], false);
-    out[i] = r;
+  // the model (knots, projection matrices, coefficients: ~10 KB) is read at every spline evaluation: keep it on chip
+  __shared__ GsmModel M;
+  {
+    const int *src = reinterpret_cast<const int *>(M_global);
+    int *dst = reinterpret_cast<int *>(&M);
+    for (int k = threadIdx.x; k < (int)(sizeof(GsmModel) / sizeof(int)); k += blockDim.x) dst[k] = src[k];
+  }
+  __syncthreads();
+  // Brent's iteration count differs from inversion to inversion: re-form the warp at the head of every pass (trip
+  // count = the warp's), or lanes that finish early run on into their next inversion on their own and the warp never
+  // comes together again (5.6 threads per warp instruction, measured)
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {
+    const int64_t i = i0 + (threadIdx.x & 31);
+    __syncwarp();
+    if (i < n) {
+      const int idx = index ? index[i] : 0;
+      double r;
+      if (mode == 0) r = gsm_randU(M, u[i], tentry ? tentry[i] : 0.0, idx, scale);
+      else if (mode == 1) r = gsm_randU0(M, u[i], idx, scale);
+      else r = gsm_eta(M, idx, u[i], false);
+      out[i] = r;
+    }
   }
 }
 
