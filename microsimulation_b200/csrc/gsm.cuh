@@ -183,48 +183,102 @@ struct GsmTarget {
   }
 };
 
-// R_zeroin2_functor_ptr (c_optim.h:9-105): Brent's root finder exactly as R's zeroin.c
-template <class F>
-MSIM_HD double zeroin2(double ax, double bx, const F &f, double Tol, int Maxit) {
-  double a = ax, b = bx, fa = f(a), fb = f(b);
-  double c = a, fc = fa;
-  int maxit = Maxit + 1;
-  const double tol = Tol;
-  if (fa == 0.0) return a;
-  if (fb == 0.0) return b;
-  while (maxit--) {
-    double prev_step = b - a, tol_act, p, q, new_step;
-    if (fabs(fc) < fabs(fb)) {
-      a = b; b = c; c = a;
-      fa = fb; fb = fc; fc = fa;
+// R_zeroin2_functor_ptr (c_optim.h:9-105): Brent's root finder exactly as R's zeroin.c, written as a state machine
+// that ASKS for function values (x = where f is wanted next) instead of calling f: the arithmetic and its order are
+// zeroin.c's, but a scheduler may interleave the evaluations of many searches (kernels.cuh, gsm_kernel: every lane
+// evaluates the spline once per pass, whatever stage its search is in).  zeroin2() below is the plain loop over it.
+struct Brent {
+  double a, b, c, fa, fb, fc, tol;
+  double x;     // evaluate f here and feed the value
+  double root;  // valid once done
+  int maxit, phase;
+  bool done;
+};
+MSIM_HD void brent_begin(Brent &s, double ax, double bx, double Tol, int Maxit) {
+  s.a = ax;
+  s.b = bx;
+  s.tol = Tol;
+  s.maxit = Maxit + 1;
+  s.phase = 0;
+  s.x = ax;
+  s.done = false;
+  s.root = bx;
+}
+MSIM_HD void brent_feed(Brent &s, double value) {
+  if (s.phase == 0) {  // fa = f(a)
+    s.fa = value;
+    s.phase = 1;
+    s.x = s.b;
+    return;
+  }
+  if (s.phase == 1) {  // fb = f(b); c = a
+    s.fb = value;
+    s.c = s.a;
+    s.fc = s.fa;
+    s.phase = 2;
+    if (s.fa == 0.0) {
+      s.root = s.a;
+      s.done = true;
+      return;
     }
-    tol_act = 2 * DBL_EPSILON * fabs(b) + tol / 2;
-    new_step = (c - b) / 2;
-    if (fabs(new_step) <= tol_act || fb == 0.0) return b;
-    if (fabs(prev_step) >= tol_act && fabs(fa) > fabs(fb)) {
-      double t1, cb, t2;
-      cb = c - b;
-      if (a == c) {
-        t1 = fb / fa;
-        p = cb * t1;
-        q = 1.0 - t1;
-      } else {
-        q = fa / fc; t1 = fb / fc; t2 = fb / fa;
-        p = t2 * (cb * q * (q - t1) - (b - a) * (t1 - 1.0));
-        q = (q - 1.0) * (t1 - 1.0) * (t2 - 1.0);
-      }
-      if (p > 0.0) q = -q;
-      else p = -p;
-      if (p < (0.75 * cb * q - fabs(tol_act * q) / 2) && p < fabs(prev_step * q / 2)) new_step = p / q;
+    if (s.fb == 0.0) {
+      s.root = s.b;
+      s.done = true;
+      return;
     }
-    if (fabs(new_step) < tol_act) new_step = (new_step > 0.0) ? tol_act : -tol_act;
-    a = b; fa = fb;
-    b += new_step; fb = f(b);
-    if ((fb > 0 && fc > 0) || (fb < 0 && fc < 0)) {
-      c = a; fc = fa;
+  } else {  // the end of the loop body: fb = f(b) after the step
+    s.fb = value;
+    if ((s.fb > 0 && s.fc > 0) || (s.fb < 0 && s.fc < 0)) {
+      s.c = s.a;
+      s.fc = s.fa;
     }
   }
-  return b;  // not converged within Maxit: the last approximation, as the reference returns
+  // while (maxit--)
+  if (s.maxit == 0) {
+    s.root = s.b;  // not converged within Maxit: the last approximation, as the reference returns
+    s.done = true;
+    return;
+  }
+  s.maxit--;
+  double prev_step = s.b - s.a, tol_act, p, q, new_step;
+  if (fabs(s.fc) < fabs(s.fb)) {
+    s.a = s.b; s.b = s.c; s.c = s.a;
+    s.fa = s.fb; s.fb = s.fc; s.fc = s.fa;
+  }
+  tol_act = 2 * DBL_EPSILON * fabs(s.b) + s.tol / 2;
+  new_step = (s.c - s.b) / 2;
+  if (fabs(new_step) <= tol_act || s.fb == 0.0) {
+    s.root = s.b;
+    s.done = true;
+    return;
+  }
+  if (fabs(prev_step) >= tol_act && fabs(s.fa) > fabs(s.fb)) {
+    double t1, cb, t2;
+    cb = s.c - s.b;
+    if (s.a == s.c) {
+      t1 = s.fb / s.fa;
+      p = cb * t1;
+      q = 1.0 - t1;
+    } else {
+      q = s.fa / s.fc; t1 = s.fb / s.fc; t2 = s.fb / s.fa;
+      p = t2 * (cb * q * (q - t1) - (s.b - s.a) * (t1 - 1.0));
+      q = (q - 1.0) * (t1 - 1.0) * (t2 - 1.0);
+    }
+    if (p > 0.0) q = -q;
+    else p = -p;
+    if (p < (0.75 * cb * q - fabs(tol_act * q) / 2) && p < fabs(prev_step * q / 2)) new_step = p / q;
+  }
+  if (fabs(new_step) < tol_act) new_step = (new_step > 0.0) ? tol_act : -tol_act;
+  s.a = s.b; s.fa = s.fb;
+  s.b += new_step;
+  s.x = s.b;  // fb = f(b) comes with the next feed
+}
+template <class F>
+MSIM_HD double zeroin2(double ax, double bx, const F &f, double Tol, int Maxit) {
+  Brent s;
+  brent_begin(s, ax, bx, Tol, Maxit);
+  while (!s.done) brent_feed(s, f(s.x));
+  return s.root;
 }
 
 // gsm::randU (gsm.cpp:38-47)

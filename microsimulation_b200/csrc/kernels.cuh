@@ -906,20 +906,74 @@ __global__ void __launch_bounds__(128) gsm_kernel(const GsmModel *M_global, int 
     for (int k = threadIdx.x; k < (int)(sizeof(GsmModel) / sizeof(int)); k += blockDim.x) dst[k] = src[k];
   }
   __syncthreads();
-  // Brent's iteration count differs from inversion to inversion: re-form the warp at the head of every pass (trip
-  // count = the warp's), or lanes that finish early run on into their next inversion on their own and the warp never
-  // comes together again (5.6 threads per warp instruction, measured)
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {
-    const int64_t i = i0 + (threadIdx.x & 31);
+  if (mode == 2) {  // eta only: one evaluation each
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+      out[i] = gsm_eta(M, index ? index[i] : 0, u[i], false);
+    return;
+  }
+  // randU / randU0.  A search takes 2 + (4 to 40) evaluations of the spline, so with one search per lane per pass a
+  // warp waits for its slowest search (5.6 threads per warp instruction, profiles/r01c_secondary_kernels.md).  Here
+  // every lane carries the state of ITS search (gsm.cuh, Brent: the state machine asks for a function value) and
+  // every pass of the loop is ONE spline evaluation on every lane, whatever stage the lane's search is in — the
+  // target's own evaluations (tentry, randU0's t0) included; a lane whose search has ended starts its next one.
+  int64_t next = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, cur = 0;
+  Brent s;
+  double target = 0.0, target0 = 0.0, y = 0.0, uu = 0.0, e_first = 0.0, ymin = 0.0, ymax = 0.0;
+  int idx = 0, stage = 0;  // 0: idle, 1: eta(ymin) for randU's target, 2/3: eta(y0, true/false) for randU0's, 4: searching
+  bool base0 = false;
+  for (;;) {
     __syncwarp();
-    if (i < n) {
-      const int idx = index ? index[i] : 0;
-      double r;
-      if (mode == 0) r = gsm_randU(M, u[i], tentry ? tentry[i] : 0.0, idx, scale);
-      else if (mode == 1) r = gsm_randU0(M, u[i], idx, scale);
-      else r = gsm_eta(M, idx, u[i], false);
-      out[i] = r;
+    if (stage == 0 && next < n) {
+      cur = next;
+      next += stride;
+      idx = index ? index[cur] : 0;
+      uu = u[cur];
+      const double te = (mode == 0 && tentry) ? tentry[cur] : 0.0;
+      ymin = te == 0.0 ? (M.log_time ? log(M.tmin / scale) : M.tmin / scale) : (M.log_time ? log(te) : te);
+      ymax = M.log_time ? log(M.tmax * scale) : M.tmax * scale;
+      target0 = 0.0;
+      if (mode == 0 && te != 0.0) {  // gsm::randU with an entry time (gsm.cpp:40-43)
+        stage = 1;
+        y = ymin;
+        base0 = false;
+      } else if (mode == 1) {  // gsm::randU0 (gsm.cpp:52-55)
+        stage = 2;
+        y = M.log_time ? log(M.t0) : M.t0;
+        base0 = true;
+      } else {
+        target = gsm_link(uu);
+        brent_begin(s, ymin, ymax, 1.0e-8, 100);
+        stage = 4;
+      }
+    }
+    if (__ballot_sync(0xffffffffu, stage != 0) == 0) break;
+    if (stage != 0) {
+      if (stage == 4) {  // the search's function (gsm.cpp:29-31): which baseline depends on where it is evaluated
+        y = s.x;
+        base0 = !((M.log_time ? exp(y) : y) < M.t0);
+      }
+      const double e = gsm_eta(M, idx, y, base0);
+      if (stage == 4) {
+        brent_feed(s, e - (base0 ? target0 : target));
+        if (s.done) {
+          out[cur] = M.log_time ? exp(s.root) : s.root;
+          stage = 0;
+        }
+      } else if (stage == 1) {
+        target = gsm_link(uu * gsm_linkinv(e));
+        brent_begin(s, ymin, ymax, 1.0e-8, 100);
+        stage = 4;
+      } else if (stage == 2) {
+        e_first = e;  // eta(y0, true)
+        base0 = false;
+        stage = 3;
+      } else {  // stage 3: eta(y0, false)
+        target = gsm_link(uu);
+        target0 = gsm_link(uu * gsm_linkinv(e_first) / gsm_linkinv(e));
+        brent_begin(s, ymin, ymax, 1.0e-8, 100);
+        stage = 4;
+      }
     }
   }
 }
