@@ -36,6 +36,7 @@ extern "C" {
 #define MSIM_ERR_SEED (-5)        /* illegal MRG32k3a seed (RngStream.cpp:234-268) */
 #define MSIM_ERR_STREAM (-6)      /* sequential-stream model drew more uniforms per person than planned for */
 #define MSIM_ERR_STATE (-7)       /* call order error (e.g. no current stream) */
+#define MSIM_ERR_MODEL (-8)       /* a model reported a (state, event) pair outside the set it declared reachable */
 
 /* ---- tables --------------------------------------------------------- */
 

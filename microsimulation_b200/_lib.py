@@ -9,7 +9,7 @@ from . import build as _build
 MSIM_OUT_ROWLOG, MSIM_OUT_REPORT, MSIM_OUT_COUNTS = 1, 2, 4
 
 ERRORS = {-1: "MSIM_ERR_NO_DEVICE", -2: "MSIM_ERR_CUDA", -3: "MSIM_ERR_ARG", -4: "MSIM_ERR_HEAP", -5: "MSIM_ERR_SEED",
-          -6: "MSIM_ERR_STREAM", -7: "MSIM_ERR_STATE"}
+          -6: "MSIM_ERR_STREAM", -7: "MSIM_ERR_STATE", -8: "MSIM_ERR_MODEL"}
 
 
 class MsimError(RuntimeError):

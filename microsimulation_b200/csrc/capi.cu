@@ -57,7 +57,7 @@ void msim_shutdown(void) {
   DevBuf *bufs[] = {&g.rowlog, &g.prov_start, &g.prov_end, &g.prov_meta, &g.tile_count, &g.partial, &g.dense, &g.small, &g.mt_words, &g.len, &g.starts, &g.chain_exit,
                     &g.chain_count, &g.chain_entry, &g.chain_base, &g.chain_gexit, &g.chain_gcount, &g.chain_gentry, &g.chain_gbase, &g.calib_out, &g.calib_partial, &g.calib_par, &g.uniforms,
                     &g.first_end, &g.first_tag, &g.ov_fill, &g.ov_tag, &g.ov_start, &g.ov_end,
-                    &g.aux, &g.code_in, &g.code_out, &g.sgeom, &g.indiv, &g.gsm_model, &g.gsm_data, &g.gsm_in, &g.gsm_out, &g.slices, &g.carry_tiles};
+                    &g.aux, &g.code_in, &g.code_out, &g.sgeom, &g.indiv, &g.gsm_model, &g.gsm_data, &g.gsm_in, &g.gsm_out, &g.slices, &g.fold_sync, &g.carry_tiles};
   if (g.d_mt_table) cudaFree(g.d_mt_table);
   g.d_mt_table = nullptr;
   g.mt_table_polys = 0;
@@ -90,7 +90,8 @@ int msim_set_stream(void *cuda_stream, int use_own) {
 }
 
 int msim_set_rowlog_plan(double rows_per_person, double extra_rows_per_person) {
-  if (!(rows_per_person > 0) || !(extra_rows_per_person >= 0)) return fail(MSIM_ERR_ARG, "bad plan");
+  if (!(rows_per_person > 0) || !(extra_rows_per_person >= 0) || rows_per_person > 1e6 || extra_rows_per_person > 1e6)
+    return fail(MSIM_ERR_ARG, "bad plan");
   g.plan_rows = rows_per_person;
   g.plan_extra_rows = extra_rows_per_person;
   return MSIM_OK;
@@ -206,7 +207,7 @@ int msim_mt_set_seed(uint32_t seed) {
 
 int msim_callPersonSimulation(const int32_t inseed[6], int32_t n, msim_table *out) {
   int rc;
-  if (!out || n < 0) return fail(MSIM_ERR_ARG, "bad arguments");
+  if (!out || !inseed || n < 0) return fail(MSIM_ERR_ARG, "bad arguments");
   msim_person_shard sh;
   memset(&sh, 0, sizeof sh);
   if ((rc = seed_from_ints(inseed, sh.seed))) return rc;
@@ -255,7 +256,7 @@ int msim_calibration_sweep(const double seed[6], int64_t first_person, int64_t n
                            msim_calibration *out) {
   int rc;
   if ((rc = ensure_init())) return rc;
-  if (!out || !runpar || n < 0 || n_sets < 1 || n_sets > 65535 || first_person < 0) return fail(MSIM_ERR_ARG, "bad arguments");
+  if (!seed || !out || !runpar || n < 0 || n_sets < 1 || n_sets > 65535 || first_person < 0) return fail(MSIM_ERR_ARG, "bad arguments");
   if (!mrg_seed_ok(seed)) return fail(MSIM_ERR_SEED, "illegal MRG32k3a seed");
   if ((rc = ensure(g.calib_par, sizeof(double) * 6 * n_sets))) return rc;
   if ((rc = ensure(g.calib_out, sizeof(double) * 48 * n_sets))) return rc;
@@ -476,7 +477,9 @@ int msim_person_enqueue(const msim_person_shard *shard, msim_person_device_resul
 
 int msim_sync(void) {
   if (!g.inited) return fail(MSIM_ERR_STATE, "not initialised");
-  return finish_run(nullptr);
+  int rc;
+  if ((rc = finish_run(nullptr))) return rc;
+  return rowlog_overflow_check();
 }
 
 int msim_person_run_device(const msim_person_shard *shard, msim_person_device_result *res) {
@@ -510,6 +513,7 @@ int msim_timer_start(void) {
   return MSIM_OK;
 }
 int msim_timer_stop(float *ms) {
+  if (!ms) return fail(MSIM_ERR_ARG, "null argument");
   if (!g.tev0) return fail(MSIM_ERR_STATE, "timer not started");
   CK(cudaEventRecord(g.tev1, g.stream));
   CK(cudaEventSynchronize(g.tev1));
@@ -518,6 +522,7 @@ int msim_timer_stop(float *ms) {
 }
 
 int msim_last_kernel_ms(float *ms) {
+  if (!ms) return fail(MSIM_ERR_ARG, "null argument");
   if (!g.have_last && g.last_ms == 0.f) return fail(MSIM_ERR_STATE, "no run yet");
   *ms = g.last_ms;
   return MSIM_OK;
@@ -526,10 +531,13 @@ int msim_last_kernel_ms(float *ms) {
 int msim_person_fetch_rowlog(msim_table *out) {
   if (!g.have_last || !(g.last_outputs & OUT_ROWLOG)) return fail(MSIM_ERR_STATE, "last run produced no row log");
   if (g.last_n_rows > g.last_capacity) return fail(MSIM_ERR_STATE, "row log overflowed its capacity; use msim_person_run_device");
+  int rc;
+  if ((rc = rowlog_overflow_check())) return rc;
   return fetch_rowlog(g.last_simple_names ? ROWLOG_COLS_SIMPLE : ROWLOG_COLS_PERSON, out);
 }
 
 int msim_person_fetch_counts(double counts[9]) {
+  if (!counts) return fail(MSIM_ERR_ARG, "null argument");
   if (!g.have_last) return fail(MSIM_ERR_STATE, "no run yet");
   CK(cudaMemcpy(counts, (const double *)g.dense.p + g.last_cells, sizeof(double) * N_COUNTS, cudaMemcpyDeviceToHost));
   return MSIM_OK;
@@ -544,6 +552,7 @@ int msim_dense_to_report(const double *host_dense, const msim_dense_dims *dims, 
 }
 
 int msim_dense_device_ptr(double **d_ptr, int64_t *n_doubles) {
+  if (!d_ptr || !n_doubles) return fail(MSIM_ERR_ARG, "null argument");
   if (!g.have_last) return fail(MSIM_ERR_STATE, "no run yet");
   *d_ptr = (double *)g.dense.p;
   *n_doubles = g.last_cells + N_COUNTS;
@@ -551,6 +560,7 @@ int msim_dense_device_ptr(double **d_ptr, int64_t *n_doubles) {
 }
 
 int msim_dense_fetch(double *host_dense, int64_t n_doubles) {
+  if (!host_dense) return fail(MSIM_ERR_ARG, "null argument");
   if (!g.have_last) return fail(MSIM_ERR_STATE, "no run yet");
   if (n_doubles != g.last_cells + N_COUNTS) return fail(MSIM_ERR_ARG, "size mismatch");
   CK(cudaMemcpy(host_dense, g.dense.p, sizeof(double) * n_doubles, cudaMemcpyDeviceToHost));
@@ -563,7 +573,7 @@ int msim_rng_uniforms(const double seed[6], int64_t first_substream, int64_t n_s
                       double *uniforms_host) {
   int rc;
   if ((rc = ensure_init())) return rc;
-  if (!uniforms_host || n_substreams < 0 || draws < 1 || first_substream < 0) return fail(MSIM_ERR_ARG, "bad arguments");
+  if (!seed || !uniforms_host || n_substreams < 0 || draws < 1 || first_substream < 0) return fail(MSIM_ERR_ARG, "bad arguments");
   if (!mrg_seed_ok(seed)) return fail(MSIM_ERR_SEED, "illegal MRG32k3a seed");
   if (n_substreams == 0) return MSIM_OK;
   size_t bytes = sizeof(double) * (size_t)n_substreams * draws;

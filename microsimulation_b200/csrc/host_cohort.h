@@ -127,7 +127,18 @@ inline int finish_run(int64_t *n_rows_out) {
   if (n_rows_out) *n_rows_out = (int64_t)nr;
   if (err == MSIM_ERR_HEAP) return fail(MSIM_ERR_HEAP, "a person scheduled more pending events / rows than the device capacity");
   if (err == MSIM_ERR_STREAM) return fail(MSIM_ERR_STREAM, "a person drew more uniforms than the sequential-stream plan allows");
+  if (err == MSIM_ERR_MODEL) return fail(MSIM_ERR_MODEL, "a model reported a (state, event) pair outside the set it declared reachable");
   if (err) return fail(err, "device-side error");
+  return MSIM_OK;
+}
+
+// The staged person-r schedule keeps rows beyond a person's first in a region per chunk of persons; a chunk that
+// logged more than the region holds has dropped rows.  msim_person_run_device repeats such a run with the exact
+// size; the asynchronous entries (msim_person_enqueue + msim_sync / msim_person_fetch_rowlog) report it instead.
+inline int rowlog_overflow_check() {
+  if (g.have_last && g.last_staged && (g.last_outputs & OUT_ROWLOG) && g.last_ov_rows > g.last_ov_cap)
+    return fail(MSIM_ERR_HEAP, "row log: a chunk of persons logged more rows beyond their first than planned for "
+                               "(msim_set_rowlog_plan); use msim_person_run_device, which repeats such a run with the exact size");
   return MSIM_OK;
 }
 

@@ -52,27 +52,35 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
   p.outputs = sh->outputs & 7u;
   p.consts = person_r::make_consts();
   p.geom = ages_geom(person_r::N_STATE, person_r::N_EVENT, sh->discount_rate);
+  if (!make_report_compact(p.geom, &person_r::REACHABLE_PAIRS[0][0], person_r::N_REACHABLE_PAIRS, &p.compact))
+    return fail(MSIM_ERR_ARG, "report geometry too large for the block tables");
   size_t smem = sizeof(WarpQueues) * SWARPS;
   if (p.outputs & OUT_ROWLOG) smem += sizeof(WarpRows) * SWARPS;
-  if (p.outputs & OUT_REPORT) {
-    smem += (size_t)(p.geom.total - p.geom.off_dstart) * 4;  // the counters; FP sums go to per-block global slices
-  }
-  int per_sm = 0;
+  if (p.outputs & OUT_REPORT) smem += staged_counter_bytes(p.geom, p.compact);  // the counters; FP sums go to per-block global slices
   typedef void (*StagedKernel)(const StagedParams);
   // kernels specialised for the output combinations without a report; the general one with (person_staged.cuh)
   static const StagedKernel kernels[8] = {person_staged_kernel<0>, person_staged_kernel<1>, person_staged_kernel<OUT_RUNTIME>,
                                           person_staged_kernel<OUT_RUNTIME>, person_staged_kernel<4>, person_staged_kernel<5>,
                                           person_staged_kernel<OUT_RUNTIME>, person_staged_kernel<OUT_RUNTIME>};
   const StagedKernel kernel = kernels[p.outputs & 7u];
-  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SBLOCK, smem));
-  if (per_sm < 1) return fail(MSIM_ERR_CUDA, "staged kernel does not fit on an SM");
+  // blocks per SM for this (kernel, shared memory) pair: asked once, the answer does not change
+  static size_t occ_smem[8] = {0};
+  static int occ_per_sm[8] = {0};
+  int per_sm = occ_per_sm[p.outputs & 7u];
+  if (per_sm == 0 || occ_smem[p.outputs & 7u] != smem) {
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SBLOCK, smem));
+    if (per_sm < 1) return fail(MSIM_ERR_CUDA, "staged kernel does not fit on an SM");
+    occ_per_sm[p.outputs & 7u] = per_sm;
+    occ_smem[p.outputs & 7u] = smem;
+  }
   const int64_t tiles = (sh->n + 31) / 32;
   int64_t gmax = (int64_t)per_sm * g.sm_count;
   if (gmax > JUMP_TAB * (int64_t)JUMP_TAB / SBLOCK) gmax = JUMP_TAB * (int64_t)JUMP_TAB / SBLOCK;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(gmax, (tiles + SWARPS - 1) / SWARPS));
   // a lane tallies event kinds in 16-bit fields (person_staged.cuh): at most 65535 persons per lane
-  if (sh->n / ((int64_t)grid * SBLOCK) >= 65000) return fail(MSIM_ERR_ARG, "shard too large for this device: split it");
+  // (persons are handed to lanes by queue position, not evenly: keep a factor of two in hand)
+  if (sh->n / ((int64_t)grid * SBLOCK) >= 32000) return fail(MSIM_ERR_ARG, "shard too large for this device: split it");
   uint32_t state[6];
   seed_to_u32(sh->seed, state);
   stream_start(state, sh->first_person, (int64_t)grid * SBLOCK, &p.st);
@@ -93,7 +101,7 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
     // ROW_CHUNK persons owns a region planned with a wide margin (a chunk that needs more repeats the run)
     const int64_t n_chunks = (sh->n + ROW_CHUNK - 1) / ROW_CHUNK;
     ov_cap = ov_cap_override > 0 ? ov_cap_override
-                                 : std::min<int64_t>((int64_t)(g.plan_extra_rows * 1.6 * ROW_CHUNK) + (g.plan_extra_rows >= 0.2 ? 96 : 1),
+                                 : std::min<int64_t>(std::max<int64_t>((int64_t)(g.plan_extra_rows * 1.6 * ROW_CHUNK) + 96, ROW_OV_MIN),
                                                      (int64_t)ROW_CHUNK * (person_r::MAX_ROWS - 1));
     const size_t ov_n = (size_t)std::max<int64_t>(n_chunks, 1) * (size_t)ov_cap;
     if ((rc = ensure(g.first_end, sizeof(double) * n1))) return rc;
@@ -114,23 +122,23 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
     p.ov_cap = (int)ov_cap;
   }
   g.last_ov_cap = ov_cap;
-  const int slice = p.geom.off_dstart;  // the FP sums (pt, ut)
   if (p.outputs & OUT_REPORT) {
-    const size_t bytes = sizeof(double) * (size_t)grid * slice;
+    // per-block slices of the FP sums (pt, ut): zeroed by their blocks, added up by the launch itself
+    const size_t bytes = sizeof(double) * (size_t)grid * staged_slice_doubles(p.geom, p.compact);
     if ((rc = ensure(g.slices, bytes))) return rc;
-    CK(cudaMemsetAsync(g.slices.p, 0, bytes, g.stream));
     p.slices = (double *)g.slices.p;
+    const size_t sync_bytes = sizeof(unsigned) * (size_t)((grid + FOLD_GROUP - 1) / FOLD_GROUP + 1);
+    if (g.fold_sync.bytes < sync_bytes || !g.fold_sync.p) {  // arrival counters: zero once, every launch leaves them zero
+      if ((rc = ensure(g.fold_sync, sync_bytes))) return rc;
+      CK(cudaMemsetAsync(g.fold_sync.p, 0, g.fold_sync.bytes, g.stream));
+    }
+    p.fold_sync = (unsigned *)g.fold_sync.p;
   }
   CK(cudaEventRecord(g.ev0, g.stream));
   if (p.n > 0) {
     kernel<<<grid, SBLOCK, smem, g.stream>>>(p);
     CK(cudaGetLastError());
     g.launches++;
-    if (p.outputs & OUT_REPORT) {
-      fold_slices_kernel<<<(slice + 255) / 256, 256, 0, g.stream>>>(p.slices, grid, slice, p.dense);
-      CK(cudaGetLastError());
-      g.launches++;
-    }
     if (p.outputs & OUT_ROWLOG) {
       if ((rc = staged_rowpasses(p.n, p.first_person, capacity, true))) return rc;
     }

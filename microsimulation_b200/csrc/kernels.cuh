@@ -239,7 +239,7 @@ struct CohortEnv {
   double sum_end;
   ReportCursor cursor;
 
-  __device__ __forceinline__ void begin_person() { cursor.valid = false; }
+  __device__ __forceinline__ void begin_person() { report_cursor_start(*geom, cursor); }
   __device__ __forceinline__ void row(double, double start, double end, int state, int kind) {
     if (outputs & OUT_COUNTS) {
       atomicAdd(&s_kind[kind], 1);

@@ -30,6 +30,16 @@ enum event_t {
 };
 constexpr int N_STATE = 8, N_EVENT = 8, MAX_ROWS = 5, HEAP_CAP = 4;
 
+// (stage, event) pairs handleMessage can see (person-r.cc:108-190): `stage` only ever holds the four undiagnosed
+// stages (diagnosis sets a flag), and from each of them a person dies of other causes, is diagnosed, or progresses.
+constexpr int REACHABLE_PAIRS[][2] = {{Healthy, toDeath},           {Healthy, toLocalised},
+                                      {Localised, toDeath},         {Localised, toDxLocalised},
+                                      {Localised, toLocallyAdvanced}, {LocallyAdvanced, toDeath},
+                                      {LocallyAdvanced, toDxLocallyAdvanced}, {LocallyAdvanced, toMetastatic},
+                                      {Metastatic, toDeath},        {Metastatic, toDxMetastatic},
+                                      {Metastatic, toPCDeath}};
+constexpr int N_REACHABLE_PAIRS = sizeof(REACHABLE_PAIRS) / sizeof(REACHABLE_PAIRS[0]);
+
 struct Consts {
   double onset_inv_shape;  // 1/exp(2.3525)
   double onset_scale;      // 64.0218

@@ -33,26 +33,46 @@ constexpr uint32_t MRG_C1 = 209u;
 constexpr uint32_t MRG_C2 = 22853u;
 constexpr double MRG_NORM = 2.328306549295727688e-10;  // 1/(m1+1), RngStream.cpp:41
 
-// x mod (2^32 - C) for x < 2^49 (C <= 22853): two folds, one conditional subtract.
+// Reduction mod m = 2^32 - C by folding 2^32 = C (mod m).  Written so that the compiler emits the short
+// sequences (profiles/r02_*): a canonical residue costs one 32-bit multiply-add, two compares and a predicated add
+// once the value is below (C+1)*2^32.
+//
+// (hi*2^32 + lo) mod m, canonical, for hi*C < 2^32.
+//   r = hi*C + lo (mod 2^32).  If the sum carried, the value is 2^32 + r = r + C (mod m) with r < hi*C, so r + C < m.
+//   Otherwise r < 2^32 < 2m: subtract m once if r >= m, i.e. add C and drop the carry.
 template <uint32_t C>
-MSIM_HD uint32_t mrg_fold2(uint64_t x) {
-  x = (x >> 32) * C + (uint32_t)x;  // < 2^17*C + 2^32 < 2^33
-  x = (x >> 32) * C + (uint32_t)x;  // < C + 2^32
-  // x mod m for x < 2m: x - m = x + C - 2^32, so the reduced value is the low word of
-  // x + C exactly when that sum carries out of 32 bits
-  const uint64_t t = x + C;
-  return (t >> 32) ? (uint32_t)t : (uint32_t)x;
+MSIM_HD uint32_t mrg_fold_small(uint32_t hi, uint32_t lo) {
+  uint32_t r = hi * C + lo;
+  if ((r < lo) | (r >= (0u - C))) r += C;
+  return r;
 }
 
-// (a0*s0 + a1*s1 + a2*s2) mod (2^32 - C), all inputs < 2^32.
+// one fold of a 64-bit value: (x >> 32)*C + (x & 0xffffffff) < (C+1)*2^32, congruent to x
+template <uint32_t C>
+MSIM_HD uint64_t mrg_fold64(uint64_t x) {
+  return (x >> 32) * C + (uint32_t)x;
+}
+
+// x mod m, canonical, for any 64-bit x: after one fold the high word is <= C and C*C < 2^32
+template <uint32_t C>
+MSIM_HD uint32_t mrg_reduce(uint64_t x) {
+  const uint64_t y = mrg_fold64<C>(x);
+  return mrg_fold_small<C>((uint32_t)(y >> 32), (uint32_t)y);
+}
+template <uint32_t C>
+MSIM_HD uint32_t mrg_fold2(uint64_t x) {  // (older name)
+  return mrg_reduce<C>(x);
+}
+
+// (a0*s0 + a1*s1 + a2*s2) mod m for canonical inputs (all < m).  A product of two residues is at most
+// (2^32 - C - 1)^2 = 2^64 - 2(C+1)*2^32 + (C+1)^2 and a folded value is below (C+1)*2^32, so
+// fold(acc) + a*s < 2^64 - (C+1)*2^32 + (C+1)^2 < 2^64: the running sum never overflows.
 template <uint32_t C>
 MSIM_HD uint32_t mrg_dot3(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t s0, uint32_t s1, uint32_t s2) {
-  uint64_t p0 = (uint64_t)a0 * s0, p1 = (uint64_t)a1 * s1, p2 = (uint64_t)a2 * s2;
-  // fold each product once: < 2^32*C + 2^32 < 2^47; the sum of three < 2^49
-  uint64_t acc = (p0 >> 32) * C + (uint32_t)p0;
-  acc += (p1 >> 32) * C + (uint32_t)p1;
-  acc += (p2 >> 32) * C + (uint32_t)p2;
-  return mrg_fold2<C>(acc);
+  uint64_t acc = (uint64_t)a0 * s0;
+  acc = mrg_fold64<C>(acc) + (uint64_t)a1 * s1;
+  acc = mrg_fold64<C>(acc) + (uint64_t)a2 * s2;
+  return mrg_reduce<C>(acc);
 }
 
 // 3x3 transition matrix pair (component 1 mod m1, component 2 mod m2), row-major.
@@ -67,19 +87,20 @@ struct Mrg32k3a {
   // RngStream::U01 (RngStream.cpp:276-299), anti = false, incPrec = false
   MSIM_HD double u01() {
     // p1 = (1403580*s11 - 810728*s10) mod m1, with -x = (m1 - x)
-    uint64_t t1 = 1403580ull * s[1] + 810728ull * (uint64_t)(MRG_M1 - s[0]);  // < 2^54
-    uint32_t p1 = mrg_fold2<MRG_C1>(t1);
+    uint64_t t1 = 1403580ull * s[1] + 810728ull * (uint64_t)(MRG_M1 - s[0]);  // < 2^54: high word * C1 < 2^30
+    uint32_t p1 = mrg_fold_small<MRG_C1>((uint32_t)(t1 >> 32), (uint32_t)t1);
     s[0] = s[1];
     s[1] = s[2];
     s[2] = p1;
     // p2 = (527612*s22 - 1370589*s20) mod m2
     uint64_t t2 = 527612ull * s[5] + 1370589ull * (uint64_t)(MRG_M2 - s[3]);  // < 2^54
-    uint32_t p2 = mrg_fold2<MRG_C2>(t2);
+    uint32_t p2 = mrg_reduce<MRG_C2>(t2);
     s[3] = s[4];
     s[4] = s[5];
     s[5] = p2;
     // (p1 - p2) or (p1 - p2 + m1): an integer in [1, m1], exact in double
-    uint32_t d = (p1 > p2) ? (p1 - p2) : (p1 - p2 + MRG_M1);
+    uint32_t d = p1 - p2;
+    if (p1 <= p2) d += MRG_M1;
     return (double)d * MRG_NORM;
   }
 

@@ -39,6 +39,8 @@
 #include "report.cuh"
 
 namespace msim {
+constexpr int MSIM_ERR_MODEL_DEV = -8;  // include/msim.h MSIM_ERR_MODEL
+
 namespace person_r {
 
 // a person parked after stage A: init()'s uniforms taken, onset time not yet computed
@@ -118,6 +120,7 @@ constexpr int SWARPS = SBLOCK / 32;
 constexpr int QCAP = 64;        // a queue holds < 32 entries between pushes, < 64 after one
 constexpr int XROWS = 4;        // rows a person may log beyond its first (person_r::MAX_ROWS - 1)
 constexpr int ROW_CHUNK = 1024;  // persons per block of the row-log passes
+constexpr int ROW_OV_MIN = 64;    // smallest region for a chunk's further rows, whatever the plan says
 constexpr int ROW_WINDOW = 2048;  // rows a block of the final pass stages at a time (a chunk holds 1262 on average)
 
 struct alignas(16) WarpQueues {
@@ -133,14 +136,18 @@ struct alignas(16) WarpRows {
   double x_start[XROWS][32], x_end[XROWS][32];
   uint32_t x_meta[XROWS][32];
 };
+constexpr int FOLD_GROUP = 16;  // blocks whose report slices are added by the last of them to finish
+
 struct StagedParams {
   StreamStart st;  // stride = M^(gridDim.x*SBLOCK)
   int64_t first_person, n;
   unsigned outputs;
   person_r::Consts consts;
   ReportGeom geom;
+  ReportCompact compact;  // the rows of the report this model can reach (block tables are laid out by these)
   double *dense;   // dense report accumulators in global memory (zeroed before launch)
-  double *slices;  // gridDim.x slices of geom.off_dstart doubles (pt, ut), zeroed before launch
+  double *slices;  // gridDim.x slices of 2 * compact.n_states * n_bin doubles (pt, ut); every block zeroes its own
+  unsigned *fold_sync;  // [groups + 1] arrival counters of the fold, zero before the first launch, left zero by every launch
   double *counts;  // N_COUNTS doubles
   int *error;
   // row log, first pass
@@ -153,17 +160,17 @@ struct StagedParams {
   int ov_cap;
 };
 
-// Report accumulators of a block.  Counters: a shared-memory table, native
-// 32-bit atomics, flushed once per block with red.global.add.f64.  FP sums
+// Report accumulators of a block.  Counters: tables in shared memory laid out by the model's reachable states and
+// (state, event) pairs (ReportCompact), native 32-bit atomics, flushed once per block.  FP sums
 // (pt, ut): red.global.add.f64 into a slice of global memory that only THIS
 // block writes — fire and forget, no return value to wait for.  Shared memory
 // has no native f64 add on sm_100a (atomicAdd there is a compare-and-swap
 // loop: 2.7 ms per 1e8 persons for the 19% of intervals that are not a
 // person's first; per-warp private tables with plain load/add/store for the
-// first intervals were also slower than the REDs).  A fold kernel sums the
-// slices afterwards, in a fixed order.  (All blocks accumulating into ONE
-// global vector: 38 ms per 1e8 persons, a few hundred hot cells serialise in
-// L2.)
+// first intervals were also slower than the REDs).  The slices are added in a fixed order inside the same launch:
+// the last block of every group of FOLD_GROUP to finish adds the group's slices, the last group to finish adds the
+// groups (no second kernel; the order of addition does not depend on which block does it).  (All blocks
+// accumulating into ONE global vector: 38 ms per 1e8 persons, a few hundred hot cells serialise in L2.)
 // red.shared.add.s32: one instruction, no return value.  (Written in PTX: the compiler turns some atomicAdd calls
 // on shared memory into a loop that groups the lanes by address first — up to 32 passes when the addresses differ,
 // as they do here.)
@@ -172,30 +179,48 @@ __device__ __forceinline__ void red_shared_add(int *ptr, int v) {
 }
 
 struct StagedAcc {
-  double *f;
-  int *i;
-  int n_f;
+  double *f;                 // this block's global slice: pt[slot][bin], then ut[slot][bin]
+  int *i;                    // shared: dstart[slot][bin], noedge[slot][bin], events[pair][bin]
+  const ReportCompact *cm;   // in shared memory
+  int nb, n_event, off_ut, off_noedge, off_events;
+  int *err;
   // one-entry write-combining cache for the `dstart` counter: consecutive +1s
   // to the same cell (every person's first interval starts in the same cell)
   // cost nothing until the cell changes
   int pend_idx;
   int pend_n;
-  __device__ __forceinline__ void addf(int idx, double v) { atomicAdd(&f[idx], v); }  // f: this block's global slice
-  // (counters as REDs into the global slice as well were measured 2% slower than these shared-memory atomics)
-  __device__ __forceinline__ void addi(int idx, int v) { red_shared_add(&i[idx - n_f], v); }
   __device__ __forceinline__ void addc(int idx) {
     if (idx == pend_idx) {
       pend_n++;
     } else {
-      if (pend_n) addi(pend_idx, pend_n);
+      if (pend_n) red_shared_add(&i[pend_idx], pend_n);
       pend_idx = idx;
       pend_n = 1;
     }
   }
   __device__ __forceinline__ void flush() {
-    if (pend_n) addi(pend_idx, pend_n);
+    if (pend_n) red_shared_add(&i[pend_idx], pend_n);
     pend_n = 0;
     pend_idx = -1;
+  }
+  // what report_add (report.cuh) adds, on this block's tables
+  __device__ __forceinline__ void add(const ReportCells &c, bool disc) {
+    const int ss = cm->state_slot[c.state], ps = cm->pair_slot[c.state * n_event + c.event];
+    if (ss < 0 || ps < 0) {
+      *err = MSIM_ERR_MODEL_DEV;
+      return;
+    }
+    const int row = ss * nb;
+    red_shared_add(&i[off_events + ps * nb + c.bin_hi], 1);
+    addc(row + c.bin_f0);
+    if (c.row_lo >= 0) {
+      const int lo = row + (c.row_lo - c.state * nb);
+      atomicAdd(&f[lo], c.pt_lo);
+      if (disc) atomicAdd(&f[off_ut + lo], c.ut_lo);
+    }
+    atomicAdd(&f[row + c.bin_hi], c.pt_hi);
+    if (disc) atomicAdd(&f[off_ut + row + c.bin_hi], c.ut_hi);
+    if (c.noedge) red_shared_add(&i[off_noedge + row + c.bin_hi], 1);
   }
 };
 
@@ -214,7 +239,8 @@ struct StagedEnvT {
   const ReportGeom *geom;  // in shared memory
   StagedAcc acc;
   ReportCursor cursor;
-  // per-kind tallies: eight 16-bit fields in two words (each kind occurs at most once per person)
+  // per-kind tallies: eight 16-bit fields in two words (each kind occurs at most once per person).  Only kept when
+  // there is no report: with one, the per-kind counts are the column sums of the block's event table.
   unsigned long long kinds_lo, kinds_hi;
   double sum_end;
   // row log of the person in hand
@@ -224,14 +250,16 @@ struct StagedEnvT {
   WarpRows *wq;
   int lane;
   __device__ __forceinline__ void begin_person() {
-    cursor.valid = false;
+    report_cursor_start(*geom, cursor);
     nrows = 0;
   }
   __device__ __forceinline__ void row(double, double start, double end, int state, int kind) {
     if (out() & 4u) {
-      const unsigned long long inc = 1ull << ((kind & 3) * 16);
-      if (kind < 4) kinds_lo += inc;
-      else kinds_hi += inc;
+      if (!(out() & 2u)) {
+        const unsigned long long inc = 1ull << ((kind & 3) * 16);
+        if (kind < 4) kinds_lo += inc;
+        else kinds_hi += inc;
+      }
       sum_end += end;
     }
     if (out() & 1u) {
@@ -247,7 +275,7 @@ struct StagedEnvT {
     }
   }
   __device__ __forceinline__ void report(int state, int kind, double lhs, double rhs) {
-    if (out() & 2u) report_add(*geom, acc, cursor, state, kind, lhs, rhs);
+    if (out() & 2u) acc.add(report_cells(*geom, cursor, state, kind, lhs, rhs), geom->discount_rate != 0.0);
   }
 };
 
@@ -279,6 +307,12 @@ __device__ __forceinline__ void staged_append_extra(const StagedParams &p, Stage
   }
 }
 
+// shared-memory bytes of the block tables for a report laid out by `cm`
+inline size_t staged_counter_bytes(const ReportGeom &g, const ReportCompact &cm) {
+  return sizeof(int) * (size_t)(2 * cm.n_states + cm.n_pairs) * g.n_bin;
+}
+inline int staged_slice_doubles(const ReportGeom &g, const ReportCompact &cm) { return 2 * cm.n_states * g.n_bin; }
+
 template <unsigned OUT>
 __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const __grid_constant__ StagedParams p) {
   typedef StagedEnvT<OUT> StagedEnv;
@@ -289,8 +323,12 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
   unsigned char *sp = smem_raw + sizeof(WarpQueues) * SWARPS;
   WarpRows *rows_stage = reinterpret_cast<WarpRows *>(sp);
   if (outs & 1u) sp += sizeof(WarpRows) * SWARPS;
-  const int total = (outs & 2u) ? p.geom.total : 0;
-  const int n_f = (outs & 2u) ? p.geom.off_dstart : 0;
+  const bool rep = (outs & 2u) != 0;
+  const int nb = p.geom.n_bin;
+  const int n_sb = rep ? p.compact.n_states * nb : 0;          // cells of one [slot][bin] table
+  const int n_i = rep ? 2 * n_sb + p.compact.n_pairs * nb : 0;  // counters: dstart, noedge, events
+  const int n_f = 2 * n_sb;                                     // FP sums: pt, ut
+  const int n_sb_d = n_sb > 0 ? n_sb : 1, nb_d = nb > 0 ? nb : 1;  // divisors (the tables are empty without a report)
   int *s_i = reinterpret_cast<int *>(sp);
   double *g_f = p.slices + (size_t)blockIdx.x * n_f;  // this block's slice of the FP sums
   __shared__ unsigned s_kind[8];
@@ -298,7 +336,9 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
   // the report geometry in shared memory: its tables are indexed per lane (a constant-bank load with a
   // different index in every lane is serialised)
   __shared__ ReportGeom s_geom;
+  __shared__ ReportCompact s_cm;
   __shared__ int s_error;
+  __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   WarpQueues &Q = queues[warp];
@@ -306,15 +346,25 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
   if (tid == 0) s_error = 0;
   for (int k = tid; k < (int)(sizeof(ReportGeom) / 4); k += SBLOCK)
     reinterpret_cast<int *>(&s_geom)[k] = reinterpret_cast<const int *>(&p.geom)[k];
-  for (int k = tid; k < total - n_f; k += SBLOCK) s_i[k] = 0;
+  for (int k = tid; k < (int)(sizeof(ReportCompact) / 4); k += SBLOCK)
+    reinterpret_cast<int *>(&s_cm)[k] = reinterpret_cast<const int *>(&p.compact)[k];
+  for (int k = tid; k < n_i; k += SBLOCK) s_i[k] = 0;
+  for (int k = tid; k < n_f; k += SBLOCK) g_f[k] = 0.0;
   __syncthreads();
 
   StagedEnv env;
+  int err = 0;
   env.outputs_rt = p.outputs;
   env.geom = &s_geom;
   env.acc.f = g_f;
   env.acc.i = s_i;
-  env.acc.n_f = n_f;
+  env.acc.cm = &s_cm;
+  env.acc.nb = nb;
+  env.acc.n_event = p.geom.n_event;
+  env.acc.off_ut = n_sb;
+  env.acc.off_noedge = n_sb;
+  env.acc.off_events = 2 * n_sb;
+  env.acc.err = &err;
   env.acc.pend_idx = -1;
   env.acc.pend_n = 0;
   env.cursor.valid = false;
@@ -325,7 +375,6 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
   env.first_tag = 0;
   env.wq = &rows_stage[warp];
   env.lane = lane;
-  int err = 0;
   const person_r::Consts &K = p.consts;
 
   Mrg32k3a sub = thread_start_state(p.st, blockIdx.x * SBLOCK + tid);
@@ -421,12 +470,14 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
   env.acc.flush();
   if (err) atomicCAS(&s_error, 0, err);
   if (outs & 4u) {
+    if (!rep) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-      unsigned v = (unsigned)(((k < 4 ? env.kinds_lo : env.kinds_hi) >> ((k & 3) * 16)) & 0xffffull);
+      for (int k = 0; k < 8; k++) {
+        unsigned v = (unsigned)(((k < 4 ? env.kinds_lo : env.kinds_hi) >> ((k & 3) * 16)) & 0xffffull);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && v) atomicAdd(&s_kind[k], v);
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(&s_kind[k], v);
+      }
     }
     double v = env.sum_end;
 #pragma unroll
@@ -434,11 +485,25 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
     if (lane == 0) s_sum[warp] = v;
   }
   __syncthreads();
-  for (int k = tid; k < total - n_f; k += SBLOCK) {
+  // the block's counters -> the dense vector (cell by cell through the compact layout); with a report the per-kind
+  // event counts are the column sums of the event table
+  for (int k = tid; k < n_i; k += SBLOCK) {
     const int v = s_i[k];
-    if (v != 0) atomicAdd(&p.dense[n_f + k], (double)v);
+    if (v == 0) continue;
+    int cell;
+    if (k < 2 * n_sb) {
+      const int t = k / n_sb_d, r = k - t * n_sb, slot = r / nb_d, b = r - slot * nb;
+      cell = (t == 0 ? p.geom.off_dstart : p.geom.off_noedge) + (int)s_cm.slot_state[slot] * nb + b;
+    } else {
+      const int r = k - 2 * n_sb, ps = r / nb_d, b = r - ps * nb;
+      const int ev = s_cm.pair_event[ps];
+      cell = p.geom.off_events + ((int)s_cm.pair_state[ps] * p.geom.n_event + ev) * nb + b;
+      if (outs & 4u) atomicAdd(&s_kind[ev & 7], (unsigned)v);
+    }
+    atomicAdd(&p.dense[cell], (double)v);
   }
   if (outs & 4u) {
+    __syncthreads();
     if (tid < 8 && s_kind[tid]) atomicAdd(&p.counts[tid], (double)s_kind[tid]);
     if (tid == 0) {
       double t = 0;
@@ -447,15 +512,41 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
     }
   }
   if (tid == 0 && s_error) atomicCAS(p.error, 0, s_error);
-}
+  if (!rep) return;
 
-// dense[k] += sum over blocks of slices[b][k], k < n_f: one thread per cell, a fixed order of addition
-__global__ void __launch_bounds__(256) fold_slices_kernel(const double *slices, int n_slices, int n_f, double *dense) {
-  const int k = blockIdx.x * 256 + threadIdx.x;
-  if (k >= n_f) return;
-  double t = 0.0;
-  for (int b = 0; b < n_slices; b++) t += slices[(size_t)b * n_f + k];
-  dense[k] += t;
+  // ---- the FP sums: slices -> dense, inside this launch.  The last block of a group to arrive adds the group's
+  // slices (into the group's first slice), the last group to arrive adds the groups, both in index order, so the
+  // result does not depend on who does the adding.
+  const int n_groups = (gridDim.x + FOLD_GROUP - 1) / FOLD_GROUP;
+  const int group = blockIdx.x / FOLD_GROUP, g0 = group * FOLD_GROUP;
+  const int g_size = min(FOLD_GROUP, (int)gridDim.x - g0);
+  __threadfence();  // this thread's REDs are performed before the arrival below is visible
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&p.fold_sync[group], 1u) == (unsigned)(g_size - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int k = tid; k < n_f; k += SBLOCK) {
+    double t = 0.0;
+    for (int b = 0; b < g_size; b++) t += __ldcg(&p.slices[(size_t)(g0 + b) * n_f + k]);
+    __stcg(&p.slices[(size_t)g0 * n_f + k], t);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    p.fold_sync[group] = 0;  // left as found, for the next launch
+    s_last = (atomicAdd(&p.fold_sync[n_groups], 1u) == (unsigned)(n_groups - 1));
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int k = tid; k < n_f; k += SBLOCK) {
+    double t = 0.0;
+    for (int gi = 0; gi < n_groups; gi++) t += __ldcg(&p.slices[(size_t)gi * FOLD_GROUP * n_f + k]);
+    const int tb = k / n_sb_d, r = k - tb * n_sb, slot = r / nb_d, b = r - slot * nb;
+    p.dense[(tb == 0 ? p.geom.off_pt : p.geom.off_ut) + (int)s_cm.slot_state[slot] * nb + b] = t;
+  }
+  if (tid == 0) p.fold_sync[n_groups] = 0;
 }
 
 // ---- row log passes -----------------------------------------------------------

@@ -66,7 +66,7 @@ struct PluginEnv {
   ReportCursor cursor;
   double *my_values;  // this person's N_VALUES cells
   int code = 0;
-  __device__ __forceinline__ void begin_person() { cursor.valid = false; }
+  __device__ __forceinline__ void begin_person() { report_cursor_start(*geom, cursor); }
   // EventReport::add(state, event, lhs, rhs)
   __device__ __forceinline__ void report(int state, int kind, double lhs, double rhs) {
     if (outputs & OUT_REPORT) report_add(*geom, acc, cursor, state, kind, lhs, rhs);

@@ -49,6 +49,7 @@ struct ReportGeom {
   double part_inv_delta;          // 1/delta: first guess of a bin index (corrected by comparison)
   double part_last;
   int unit;  // 1: partition {0, 1, 2, ..., n_bin-2, part_last}: a bin index is just the integer part
+  int bin0;  // the bin of time 0, where every person's first interval starts (cProcess::startTime)
   double discount_rate, alpha, inv_alpha;  // alpha = log(1 + discount_rate), inv_alpha = 1/alpha (host libm)
   // offsets (in doubles) into the dense vector; FP sums first, then counters
   int off_pt, off_ut, off_dstart, off_noedge, off_events, total;
@@ -81,6 +82,8 @@ inline ReportGeom make_report_geom(int n_state, int n_event, int n_bin, double s
     double p = (i >= n_bin - 1) ? last : start + i * delta;
     g.edge_decay[i] = (discount_rate != 0.0) ? exp(-p * g.alpha) : 1.0;
   }
+  g.bin0 = 0;
+  while (g.bin0 + 1 < n_bin && ((g.bin0 + 1 >= n_bin - 1) ? last : start + (g.bin0 + 1) * delta) <= 0.0) g.bin0++;
   return g;
 }
 
@@ -117,6 +120,44 @@ MSIM_HD double report_discounted(const ReportGeom &g, double a, double b, double
   return utility / g.alpha * (exp(-a * g.alpha) - exp(-b * g.alpha));
 }
 
+// Which cells of the dense report a model can reach: a kernel that keeps its block-level tables in shared memory
+// only needs rows for the states a person can be in and for the (state, event) pairs that can occur (person-r:
+// 4 of 8 states, 11 of 64 pairs — 8 KB of counters instead of 33 KB).  Built on the host from the model's list;
+// a pair outside the list raises an error on the device instead of being lost.
+constexpr int REPORT_MAX_STATES = 16, REPORT_MAX_PAIRS = 256, REPORT_MAX_USED_PAIRS = 32;
+struct ReportCompact {
+  signed char state_slot[REPORT_MAX_STATES];  // state -> row of the compact tables, -1 = not reachable
+  signed char pair_slot[REPORT_MAX_PAIRS];    // state * n_event + event -> row of the compact event table
+  unsigned char slot_state[REPORT_MAX_STATES];
+  unsigned char pair_state[REPORT_MAX_USED_PAIRS], pair_event[REPORT_MAX_USED_PAIRS];
+  int n_states, n_pairs;
+};
+
+// pairs = {state, event, state, event, ...}; returns false if the geometry is too large for the tables
+inline bool make_report_compact(const ReportGeom &g, const int *pairs, int n_pairs, ReportCompact *out) {
+  ReportCompact c;
+  for (int i = 0; i < REPORT_MAX_STATES; i++) c.state_slot[i] = -1, c.slot_state[i] = 0;
+  for (int i = 0; i < REPORT_MAX_PAIRS; i++) c.pair_slot[i] = -1;
+  for (int i = 0; i < REPORT_MAX_USED_PAIRS; i++) c.pair_state[i] = c.pair_event[i] = 0;
+  c.n_states = c.n_pairs = 0;
+  if (g.n_state > REPORT_MAX_STATES || g.n_state * g.n_event > REPORT_MAX_PAIRS || n_pairs > REPORT_MAX_USED_PAIRS) return false;
+  for (int k = 0; k < n_pairs; k++) {
+    const int st = pairs[2 * k], ev = pairs[2 * k + 1];
+    if (st < 0 || st >= g.n_state || ev < 0 || ev >= g.n_event) return false;
+    if (c.state_slot[st] < 0) {
+      c.slot_state[c.n_states] = (unsigned char)st;
+      c.state_slot[st] = (signed char)c.n_states++;
+    }
+    if (c.pair_slot[st * g.n_event + ev] < 0) {
+      c.pair_state[c.n_pairs] = (unsigned char)st;
+      c.pair_event[c.n_pairs] = (unsigned char)ev;
+      c.pair_slot[st * g.n_event + ev] = (signed char)c.n_pairs++;
+    }
+  }
+  *out = c;
+  return true;
+}
+
 // What a process remembers between two of its report() calls: the previous
 // interval's right end, its bin and exp(-alpha*rhs) are this interval's left
 // end (previousEventTime), so neither the bin search nor the exponential is
@@ -127,10 +168,21 @@ struct ReportCursor {
   bool valid;
 };
 
+// A person's first interval starts at startTime = 0 (microsimulation.h:430): its bin is known and
+// exp(-alpha * 0) = 1 exactly, so the cursor can start out valid and the first event needs no second bin search
+// and no second exponential.
+MSIM_HD void report_cursor_start(const ReportGeom &g, ReportCursor &cur) {
+  cur.t = 0.0;
+  cur.e = 1.0;
+  cur.bin = g.bin0;
+  cur.valid = true;
+}
+
 // The cells one interval touches (see the header comment): what report_add
 // adds, separated from HOW it is added so that a warp can add its lanes'
 // intervals together (person_staged.cuh).
 struct ReportCells {
+  int state, event, bin_hi, bin_f0;  // the same cells by coordinates, for accumulators with their own layout
   int i_events, i_dstart;  // counters to increment
   bool noedge;             // also increment noedge[s][hi]
   int row_hi, row_lo;      // state*n_bin + bin of the partial overlaps; row_lo < 0: none
@@ -163,6 +215,10 @@ MSIM_HD ReportCells report_cells(const ReportGeom &g, ReportCursor &cur, int sta
   c.i_events = g.off_events + (state * g.n_event + event) * nb + hi;
   int f0 = on_edge ? lo : lo + 1;
   if (f0 > hi) f0 = hi;
+  c.state = state;
+  c.event = event;
+  c.bin_hi = hi;
+  c.bin_f0 = f0;
   c.i_dstart = g.off_dstart + row + f0;
   c.row_hi = row + hi;
   c.row_lo = -1;

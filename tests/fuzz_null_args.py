@@ -22,6 +22,14 @@ calls = {
  "msim_person_fetch_counts": "(None,)", "msim_dense_to_report": "(None, None, C.c_double(0), None)",
  "msim_dense_device_ptr": "(None, None)", "msim_dense_fetch": "(None, C.c_int64(5))",
  "msim_rng_uniforms": "(None, C.c_int64(0), C.c_int64(1), C.c_int32(1), None)", "msim_mt_uniforms": "(C.c_int64(5), None)",
+ # one null at a time: the other arguments are valid, so an earlier check cannot hide a missing one
+ "msim_calibration_sweep#seed": "(None, C.c_int64(0), C.c_int64(5), C.c_int32(1), buf, buf)",
+ "msim_rng_uniforms#seed": "(None, C.c_int64(0), C.c_int64(1), C.c_int32(1), buf)",
+ "msim_callPersonSimulation#seed": "(None, C.c_int32(5), buf)",
+ "msim_callPersonSimulation#out": "(ibuf, C.c_int32(5), None)",
+ "msim_last_kernel_ms": "(None,)", "msim_timer_stop": "(None,)", "msim_dense_device_ptr#n": "(buf, None)",
+ "msim_dense_device_ptr#p": "(None, buf)", "msim_dense_fetch#n": "(None, C.c_int64(9))",
+ "msim_r_rng_advance_substream#n": "(buf, None)", "msim_r_rng_advance_substream#seed": "(None, ibuf)",
  "msim_table_free": "(None,)", "msim_report_free": "(None,)", "msim_set_stream": "(None, 0)",
 }
 if __name__ == "__main__" and len(sys.argv) > 1:
@@ -30,7 +38,8 @@ if __name__ == "__main__" and len(sys.argv) > 1:
     L.msim_r_create_current_stream()
     if os.environ.get("MSIM_FUZZ_INIT"):
         m.init(0)
-    f = getattr(L, sys.argv[1]); f.argtypes = None
+    f = getattr(L, sys.argv[1].split("#")[0]); f.argtypes = None
+    buf, ibuf = (C.c_double * 512)(), (C.c_int32 * 16)(*([12345] * 16))
     rc = eval("f" + calls[sys.argv[1]])
     print("rc", rc)
     sys.exit(0)

@@ -54,7 +54,7 @@ struct HostEnv {
   PlainAcc acc;
   double *counts;
   ReportCursor cursor;
-  void begin_person() { cursor.valid = false; }
+  void begin_person() { report_cursor_start(*geom, cursor); }
   void row(double id, double start, double end, int state, int kind) {
     if (outputs & OUT_COUNTS) {
       counts[kind] += 1;
@@ -326,6 +326,36 @@ static int emu_calibration_t(const double seed[6], int64_t first_person, int64_t
   out->n_time_at_risk = env.tar_n;
   for (int k = 0; k < env.tar_n; k++) out->time_at_risk[k] = env.tar[k];
   return 0;
+}
+
+// The modular arithmetic of mrg32k3a.cuh against 128-bit integer arithmetic: random inputs and the extremes
+// (residues m - 1, the largest products, values that make the folded sum carry).  Returns the number of mismatches.
+template <uint32_t C>
+static int64_t mrg_selftest_component(uint64_t seed, int64_t n) {
+  const uint32_t m = 0u - C;
+  int64_t bad = 0;
+  uint64_t x = seed * 6364136223846793005ull + 1442695040888963407ull;
+  auto next = [&]() {
+    x ^= x << 13;
+    x ^= x >> 7;
+    x ^= x << 17;
+    return x;
+  };
+  const uint32_t edge[10] = {0u, 1u, 2u, C - 1, C, C + 1, m - 2, m - 1, m / 2, 0x80000000u};
+  for (int64_t i = 0; i < n; i++) {
+    uint32_t v[6];
+    for (int k = 0; k < 6; k++) {
+      const uint64_t r = next();
+      v[k] = ((r >> 60) < 6) ? edge[(r >> 32) % 10] : (uint32_t)(r % m);  // about a third of the operands are extremes
+    }
+    const unsigned __int128 want = ((unsigned __int128)v[0] * v[3] + (unsigned __int128)v[1] * v[4] + (unsigned __int128)v[2] * v[5]) % m;
+    if (mrg_dot3<C>(v[0], v[1], v[2], v[3], v[4], v[5]) != (uint32_t)want) bad++;
+    const uint64_t y = next() | ((i & 7) == 0 ? 0xffffffff00000000ull : 0ull);  // any 64-bit value, many with a full high word
+    if (mrg_reduce<C>(y) != (uint32_t)(y % m)) bad++;
+    const uint32_t hi = (uint32_t)(next() % (0xffffffffu / C)), lo = (i & 3) ? (uint32_t)next() : 0xffffffffu - (uint32_t)(next() % (2 * C));
+    if (mrg_fold_small<C>(hi, lo) != (uint32_t)((((uint64_t)hi << 32) | lo) % m)) bad++;
+  }
+  return bad;
 }
 
 extern "C" {
@@ -865,6 +895,11 @@ void emu_report_free(msim_report *r) {
   emu_table_free(&r->prev);
   emu_table_free(&r->costs);
   emu_table_free(&r->indiv);
+}
+
+
+int64_t emu_mrg_selftest(uint64_t seed, int64_t n) {
+  return mrg_selftest_component<MRG_C1>(seed, n) + mrg_selftest_component<MRG_C2>(seed + 1, n);
 }
 
 }  // extern "C"

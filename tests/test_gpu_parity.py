@@ -578,6 +578,33 @@ def test_gpu_against_the_reference_linked_oracle(msim, oracle_ref):
     _summary_equal(api.callSim(3000, par), oracle_ref.sick_sicker(3000, par))
 
 
+def test_person_1e7_rows_and_report_against_the_reference_on_all_cores(msim):
+    """BASELINE configs[2] at its full size, and the bench's report workload at a size where a 1-ulp libm difference
+    could move an event across an age-bin edge: 1e7 persons on the GPU against the reference-linked oracle run on
+    every host core (oracle/parallel.py) — every row (ids, states, events exactly, times to a few ulp) and every
+    cell of the EventReport (events / prev exactly, pt / ut to 1e-9)."""
+    import os
+    import microsimulation_b200.api as api
+    from oracle import parallel
+    n = 10 ** 7
+    api.person_run_device(12345, 0, n, 1 | 4)
+    rows = api.person_fetch_rowlog()
+    counts = api.person_fetch_counts()
+    assert np.all(np.diff(rows["id"]) >= 0)
+    ref = parallel.person_run_parallel(12345, 0, n, cores=os.cpu_count(), rows_to_check=rows, report=True,
+                                       discount_rate=0.03, time_rtol=TIME_RTOL)
+    assert ref["rows_ok"], ref["rows_msg"]
+    assert ref["n_rows"] == len(rows["id"])
+    assert np.array_equal(counts[:8], ref["counts"][:8])
+    assert ref["max_time_rel_err"] <= TIME_RTOL
+    del rows
+    rep, counts2 = msim.person_report(12345, 0, n, 0.03)
+    assert np.array_equal(counts2[:8], ref["counts"][:8])
+    ok, worst, msg = parallel.report_equal(rep, ref["report"], rtol=1e-9)
+    assert ok, msg
+    assert_report_close(rep, ref["report"], rtol=1e-9)
+
+
 def test_null_arguments_with_a_device(msim):
     """The same with the device initialised: argument checks that sit behind the device check are reached."""
     import os

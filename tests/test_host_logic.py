@@ -136,6 +136,13 @@ def test_next_rng_stream_matches_the_reference_jump(oracle, oracle_ref):
     assert m.calibration_chunks(10, 3) == [4, 3, 3] and m.calibration_chunks(2, 4) == [1, 1, 0, 0]
 
 
+def test_mrg_modular_arithmetic_against_128_bit_integers(emu):
+    """mrg_fold_small / mrg_reduce / mrg_dot3 (csrc/mrg32k3a.cuh, the code the device runs) on random operands and
+    on the extremes: residues m - 1, full high words, sums that carry out of 32 bits."""
+    emu.emu_mrg_selftest.restype = C.c_int64
+    assert emu.emu_mrg_selftest(C.c_uint64(12345), C.c_int64(3000000)) == 0
+
+
 def test_mt_set_seed_matches_oracle(oracle, emu):
     import microsimulation_b200 as m
     m.set_seed(12345)
