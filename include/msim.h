@@ -297,6 +297,18 @@ int msim_dense_fetch(double *host_dense, int64_t n_doubles);
 int msim_calibration_sweep(const double seed[6], int64_t first_person, int64_t n, int32_t n_sets,
                            const double *runpar, msim_calibration *out);
 
+/* The sweep in pieces, for sharding over GPUs (BASELINE configs[4]): parameter sets [set_lo, set_hi) of the n_sets
+ * given, on persons [first_person, first_person + n), results left on the device as ONE vector of 48 doubles per
+ * set — occupancy[4][10], TimeAtRisk[4], and for k < 4 the number of thread blocks that added to TimeAtRisk[k] —
+ * in which every cell is a sum: shards of the person range and shards of the sets both merge with a single
+ * all-reduce(sum, f64) on *d_vector (rows of sets outside [set_lo, set_hi) are zero).  msim_calibration_fetch
+ * copies the (merged) vector to the host, msim_calibration_unpack (pure host code) turns it into the reference's
+ * per-set lists.  R/calibSim.R:10-40 does the same with mclapply chunks and Reduce("+"). */
+int msim_calibration_sweep_device(const double seed[6], int64_t first_person, int64_t n, int32_t n_sets, const double *runpar,
+                                  int32_t set_lo, int32_t set_hi, double **d_vector, int64_t *n_doubles);
+int msim_calibration_fetch(double *host_vector, int64_t n_doubles);
+int msim_calibration_unpack(const double *host_vector, int32_t n_sets, msim_calibration *out);
+
 /* K1 parity hook: uniforms[j*draws + k] = k-th uniform of substream
  * first_substream+j of the stream whose state is `seed` (substream 0 = seed). */
 int msim_rng_uniforms(const double seed[6], int64_t first_substream, int64_t n_substreams, int32_t draws,

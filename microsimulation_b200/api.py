@@ -276,6 +276,35 @@ def calibration_sweep(seed, runpars, n, first_person=0):
     return [arr[i].to_dict() for i in range(ns)]
 
 
+def calibration_sweep_device(seed, runpars, n, first_person=0, set_lo=0, set_hi=None):
+    """Sets [set_lo, set_hi) of `runpars` on persons [first_person, first_person + n), results left on the device as
+    one vector of 48 doubles per set in which every cell is a sum.  Returns (device pointer, number of doubles)."""
+    runpars = np.ascontiguousarray(runpars, dtype=np.float64).reshape(-1, 6)
+    ns = runpars.shape[0]
+    s = (C.c_double * 6)(*_seed6(seed))
+    p = C.POINTER(C.c_double)()
+    nd = C.c_int64()
+    check(load().msim_calibration_sweep_device(s, C.c_int64(first_person), C.c_int64(n), C.c_int32(ns),
+                                               runpars.ctypes.data_as(C.POINTER(C.c_double)), C.c_int32(set_lo),
+                                               C.c_int32(ns if set_hi is None else set_hi), C.byref(p), C.byref(nd)))
+    return C.cast(p, C.c_void_p).value, nd.value
+
+
+def calibration_fetch(n_doubles):
+    out = np.empty(n_doubles)
+    check(load().msim_calibration_fetch(out.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(n_doubles)))
+    return out
+
+
+def calibration_unpack(vector, as_dicts=True):
+    """The (merged) vector of a sweep -> the reference's per-set lists (pure host code)."""
+    vector = np.ascontiguousarray(vector, dtype=np.float64)
+    ns = vector.size // 48
+    arr = (Calibration * ns)()
+    check(load().msim_calibration_unpack(vector.ctypes.data_as(C.POINTER(C.c_double)), C.c_int32(ns), arr))
+    return [arr[i].to_dict() for i in range(ns)] if as_dicts else arr
+
+
 # ---- sharded / device-resident person-r runs (multi-GPU, benchmarks)
 
 def person_shard(seed, first_person, n, outputs, discount_rate=0.0):

@@ -252,12 +252,16 @@ int msim_callIllnessDeath(int32_t n, double cure, double zsd, msim_report *out) 
   return fetch_report(out);
 }
 
-int msim_calibration_sweep(const double seed[6], int64_t first_person, int64_t n, int32_t n_sets, const double *runpar,
-                           msim_calibration *out) {
+// sets [set_lo, set_hi) of the n_sets parameter vectors on persons [first_person, first_person + n): the device
+// vector [n_sets][48] (rows of the other sets zero), complete on return
+static int calibration_run(const double seed[6], int64_t first_person, int64_t n, int32_t n_sets, const double *runpar,
+                           int32_t set_lo, int32_t set_hi) {
   int rc;
   if ((rc = ensure_init())) return rc;
-  if (!seed || !out || !runpar || n < 0 || n_sets < 1 || n_sets > 65535 || first_person < 0) return fail(MSIM_ERR_ARG, "bad arguments");
+  if (!seed || !runpar || n < 0 || n_sets < 1 || n_sets > 65535 || first_person < 0 || set_lo < 0 || set_hi > n_sets || set_lo > set_hi)
+    return fail(MSIM_ERR_ARG, "bad arguments");
   if (!mrg_seed_ok(seed)) return fail(MSIM_ERR_SEED, "illegal MRG32k3a seed");
+  const int n_here = set_hi - set_lo;
   if ((rc = ensure(g.calib_par, sizeof(double) * 6 * n_sets))) return rc;
   if ((rc = ensure(g.calib_out, sizeof(double) * 48 * n_sets))) return rc;
   if ((rc = ensure(g.small, 16 * sizeof(double)))) return rc;
@@ -266,19 +270,21 @@ int msim_calibration_sweep(const double seed[6], int64_t first_person, int64_t n
   memset(&p, 0, sizeof p);
   int64_t tiles = (n + BLOCK - 1) / BLOCK;
   // enough blocks per set to fill the GPU even for few sets, no more than the work
-  int64_t want = std::max<int64_t>(1, ((int64_t)g.sm_count * 8 + n_sets - 1) / n_sets);
+  int64_t want = std::max<int64_t>(1, ((int64_t)g.sm_count * 8 + std::max(n_here, 1) - 1) / std::max(n_here, 1));
   int grid_x = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, tiles), 2048));
   uint32_t state[6];
   seed_to_u32(seed, state);
   stream_start(state, first_person, (int64_t)grid_x * BLOCK, &p.st);
   p.n = n;
   p.n_sets = n_sets;
+  p.set0 = set_lo;
   p.runpar = (const double *)g.calib_par.p;
   p.out = (double *)g.calib_out.p;
   p.error = small_view().error;
   p.tie = (int *)((double *)g.small.p + 13);
-  if ((rc = ensure(g.calib_partial, sizeof(double) * 4 * (size_t)grid_x * n_sets))) return rc;
+  if ((rc = ensure(g.calib_partial, sizeof(double) * 4 * (size_t)grid_x * std::max(n_here, 1)))) return rc;
   p.partial = (double *)g.calib_partial.p;
+  g.last_calib_sets = n_sets;
   // Schedule 0 keeps the pending actions in an ordered array (engine.cuh, OrderedEvents), which pops in the heap's
   // order unless two pending actions compare equal; a run that saw such a pair is repeated with the binary heap
   // (schedule 1).  Schedule 2 (tests) takes the repeat path unconditionally.
@@ -286,11 +292,11 @@ int msim_calibration_sweep(const double seed[6], int64_t first_person, int64_t n
     CK(cudaMemsetAsync(g.calib_out.p, 0, sizeof(double) * 48 * n_sets, g.stream));
     CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
     CK(cudaEventRecord(g.ev0, g.stream));
-    if (n > 0) {
-      if (attempt == 0) calib_kernel<true><<<dim3(grid_x, n_sets), BLOCK, 0, g.stream>>>(p);
-      else calib_kernel<false><<<dim3(grid_x, n_sets), BLOCK, 0, g.stream>>>(p);
+    if (n > 0 && n_here > 0) {
+      if (attempt == 0) calib_kernel<true><<<dim3(grid_x, n_here), BLOCK, 0, g.stream>>>(p);
+      else calib_kernel<false><<<dim3(grid_x, n_here), BLOCK, 0, g.stream>>>(p);
       CK(cudaGetLastError());
-      calib_fold_kernel<<<n_sets, 32, 0, g.stream>>>(p.partial, grid_x, p.out);
+      calib_fold_kernel<<<n_here, 32, 0, g.stream>>>(p.partial, grid_x, set_lo, p.out);
       CK(cudaGetLastError());
       g.launches += 2;
     }
@@ -301,12 +307,15 @@ int msim_calibration_sweep(const double seed[6], int64_t first_person, int64_t n
     CK(cudaMemcpy(&tie, p.tie, sizeof tie, cudaMemcpyDeviceToHost));
     if (attempt == 0 && !tie && g.person_kernel != 2) break;
   }
-  std::vector<double> h(48 * (size_t)n_sets);
-  CK(cudaMemcpy(h.data(), g.calib_out.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+  return MSIM_OK;
+}
+
+int msim_calibration_unpack(const double *host_vector, int32_t n_sets, msim_calibration *out) {
+  if (!host_vector || !out || n_sets < 1) return fail(MSIM_ERR_ARG, "bad arguments");
   for (int s = 0; s < n_sets; s++) {
     msim_calibration *o = out + s;
     memset(o, 0, sizeof *o);
-    const double *r = &h[48 * (size_t)s];
+    const double *r = host_vector + 48 * (size_t)s;
     for (int st = 0; st < 4; st++) {
       double tot = 0;
       for (int k = 0; k < 10; k++) {
@@ -315,10 +324,40 @@ int msim_calibration_sweep(const double seed[6], int64_t first_person, int64_t n
       }
       o->present[st] = tot > 0;  // report[stage] exists once any Count saw that stage (calibperson-r.cc:166-169)
     }
-    o->n_time_at_risk = (int32_t)r[44];
-    for (int k = 0; k < o->n_time_at_risk; k++) o->time_at_risk[k] = r[40 + k];
+    int nt = 0;
+    while (nt < 4 && r[44 + nt] > 0) nt++;  // indices are reached in order (the loop at calibperson-r.cc:124-135 breaks)
+    o->n_time_at_risk = nt;
+    for (int k = 0; k < nt; k++) o->time_at_risk[k] = r[40 + k];
   }
   return MSIM_OK;
+}
+
+int msim_calibration_sweep_device(const double seed[6], int64_t first_person, int64_t n, int32_t n_sets, const double *runpar,
+                                  int32_t set_lo, int32_t set_hi, double **d_vector, int64_t *n_doubles) {
+  int rc;
+  if (!d_vector || !n_doubles) return fail(MSIM_ERR_ARG, "null argument");
+  if ((rc = calibration_run(seed, first_person, n, n_sets, runpar, set_lo, set_hi))) return rc;
+  *d_vector = (double *)g.calib_out.p;
+  *n_doubles = 48 * (int64_t)n_sets;
+  return MSIM_OK;
+}
+
+int msim_calibration_fetch(double *host_vector, int64_t n_doubles) {
+  if (!host_vector) return fail(MSIM_ERR_ARG, "null argument");
+  if (g.last_calib_sets < 1 || n_doubles != 48 * (int64_t)g.last_calib_sets) return fail(MSIM_ERR_STATE, "no calibration run of that size");
+  CK(cudaMemcpyAsync(host_vector, g.calib_out.p, sizeof(double) * n_doubles, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return MSIM_OK;
+}
+
+int msim_calibration_sweep(const double seed[6], int64_t first_person, int64_t n, int32_t n_sets, const double *runpar,
+                           msim_calibration *out) {
+  int rc;
+  if (!out) return fail(MSIM_ERR_ARG, "bad arguments");
+  if ((rc = calibration_run(seed, first_person, n, n_sets, runpar, 0, n_sets))) return rc;
+  std::vector<double> h(48 * (size_t)n_sets);
+  CK(cudaMemcpy(h.data(), g.calib_out.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+  return msim_calibration_unpack(h.data(), n_sets, out);
 }
 
 int msim_callCalibrationSimulation(int32_t n, const double runpar[6], msim_calibration *out) {

@@ -69,6 +69,8 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
   int per_sm = occ_per_sm[p.outputs & 7u];
   if (per_sm == 0 || occ_smem[p.outputs & 7u] != smem) {
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // as much of the SM's memory as shared memory as there is: the kernel reads no global data worth caching
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SBLOCK, smem));
     if (per_sm < 1) return fail(MSIM_ERR_CUDA, "staged kernel does not fit on an SM");
     occ_per_sm[p.outputs & 7u] = per_sm;

@@ -57,6 +57,7 @@ struct Ctx {
   int64_t want_capacity = 0;
   int64_t last_n = 0, last_first = 0;
   int last_max_rows = 0;
+  int last_calib_sets = 0;  // parameter sets of the last calibration run (rows of calib_out)
   int last_cells = 0;  // dense report cells of the last run (0 when no report was requested)
   bool have_last = false;
   float last_ms = 0.f;

@@ -717,7 +717,8 @@ struct CalibParams {
   int64_t n;
   int n_sets;
   const double *runpar;  // [n_sets][6]
-  double *out;           // [n_sets][48]: occupancy[4][10], TimeAtRisk[4], n_time_at_risk, pad
+  double *out;           // [n_sets][48]: occupancy[4][10], TimeAtRisk[4], then for k < 4 how many blocks added to TimeAtRisk[k]
+  int set0;              // blockIdx.y = 0 is parameter set set0 (a launch may cover a range of the sets)
   int *error;
   int *tie;              // set if two pending actions of a person compared equal (ORDERED only)
   double *partial;       // [n_sets][gridDim.x][4]: every block's TimeAtRisk sums, added up in block order afterwards
@@ -772,7 +773,7 @@ __global__ void __launch_bounds__(BLOCK) calib_kernel(CalibParams p) {
   __shared__ int s_tar_n;
   __shared__ int s_error;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int set = blockIdx.y;
+  const int set = p.set0 + blockIdx.y;
   if (tid < 40) s_occ[tid] = 0;
   if (tid == 0) {
     s_tar_n = 0;
@@ -834,24 +835,22 @@ __global__ void __launch_bounds__(BLOCK) calib_kernel(CalibParams p) {
   if (tid < 4) {
     double t = 0;
     for (int w = 0; w < WARPS; w++) t += s_tar[w][tid];
-    p.partial[((size_t)set * gridDim.x + blockIdx.x) * 4 + tid] = t;  // no atomics: the sum must not depend on timing
+    p.partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4 + tid] = t;  // no atomics: the sum must not depend on timing
+    // TimeAtRisk has as many entries as the largest index any person reached (calibperson-r.cc:124-135); kept as
+    // counts per index so that shards merge by addition like everything else in the vector
+    if (tid < s_tar_n) atomicAdd(&out[44 + tid], 1.0);
   }
-  if (tid == 0) {
-    // max over blocks of a non-negative integer-valued double (bit order = value order)
-    unsigned long long *cell = reinterpret_cast<unsigned long long *>(&out[44]);
-    atomicMax(cell, (unsigned long long)__double_as_longlong((double)s_tar_n));
-    if (s_error) atomicCAS(p.error, 0, s_error);
-  }
+  if (tid == 0 && s_error) atomicCAS(p.error, 0, s_error);
   if (ORDERED && tie) *p.tie = 1;
 }
 
 // TimeAtRisk of every set: the blocks' sums in block order (one block per set, threads 0..3)
-__global__ void calib_fold_kernel(const double *partial, int blocks, double *out) {
+__global__ void calib_fold_kernel(const double *partial, int blocks, int set0, double *out) {
   if (threadIdx.x < 4) {
     const double *q = partial + (size_t)blockIdx.x * blocks * 4 + threadIdx.x;
     double t = 0.0;
     for (int b = 0; b < blocks; b++) t += q[4 * b];
-    out[48 * (size_t)blockIdx.x + 40 + threadIdx.x] = t;
+    out[48 * (size_t)(set0 + blockIdx.x) + 40 + threadIdx.x] = t;
   }
 }
 

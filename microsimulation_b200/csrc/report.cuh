@@ -37,6 +37,7 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "fastmath.cuh"
 #include "mrg32k3a.cuh"
 
 namespace msim {
@@ -80,7 +81,7 @@ inline ReportGeom make_report_geom(int n_state, int n_event, int n_bin, double s
   g.total = g.off_events + n_state * n_event * n_bin;
   for (int i = 0; i < REPORT_MAX_BINS; i++) {
     double p = (i >= n_bin - 1) ? last : start + i * delta;
-    g.edge_decay[i] = (discount_rate != 0.0) ? exp(-p * g.alpha) : 1.0;
+    g.edge_decay[i] = (discount_rate != 0.0) ? fm_exp(-p * g.alpha) : 1.0;  // the function the events use (report_decay)
   }
   g.bin0 = 0;
   while (g.bin0 + 1 < n_bin && ((g.bin0 + 1 >= n_bin - 1) ? last : start + (g.bin0 + 1) * delta) <= 0.0) g.bin0++;
@@ -106,7 +107,7 @@ MSIM_HD int report_bin(const ReportGeom &g, double x) {
 }
 
 // exp(-alpha*t): the one transcendental an event needs when utilities are discounted
-MSIM_HD double report_decay(const ReportGeom &g, double t) { return exp(-t * g.alpha); }
+MSIM_HD double report_decay(const ReportGeom &g, double t) { return fm_exp(-t * g.alpha); }
 
 // EventReport::discountedUtilities (microsimulation.h:917-928) with the two
 // exponentials passed in: utility/alpha*(exp(-a*alpha) - exp(-b*alpha))

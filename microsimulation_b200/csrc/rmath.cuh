@@ -12,6 +12,7 @@
 #pragma once
 #include <math.h>
 
+#include "fastmath.cuh"
 #include "mrg32k3a.cuh"
 
 namespace msim {
@@ -45,7 +46,7 @@ struct RMath {
   }
 
   MSIM_DEV double rweibull(double shape, double scale) {
-    return scale * pow(-log(unif_rand()), 1. / shape);
+    return scale * fm_pow(-fm_log(unif_rand()), 1. / shape);  // exp / log / pow: fastmath.cuh
   }
 
   MSIM_DEV double exp_rand() {

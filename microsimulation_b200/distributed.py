@@ -76,40 +76,48 @@ def person_simulation_sharded(n, seed=(12345,) * 6, outputs=MSIM_OUT_REPORT | MS
     return report, counts, n_rows
 
 
-def calibration_sweep_sharded(seed, runpars, n, group=None, compute=None):
-    """Config 5: every rank takes a person range of every parameter set; occupancy and TimeAtRisk are sums."""
+def calibration_grid(world_size, n_sets):
+    """How `world_size` ranks split a sweep: (groups of sets, groups of persons).  Sets are split first (every GPU
+    keeps whole sets and a full grid of blocks per set), persons only by what is left over — the 2-D split of
+    SURVEY.md 8(e)."""
+    gs = 1
+    for d in range(1, world_size + 1):
+        if world_size % d == 0 and d <= max(1, n_sets):
+            gs = d
+    return gs, world_size // gs
+
+
+def calibration_shard(rank, world_size, n_sets, n):
+    """This rank's (set_lo, set_hi, first_person, persons)."""
+    gs, gp = calibration_grid(world_size, n_sets)
+    set_lo, n_here = shard_range(n_sets, rank % gs, gs)
+    first, count = shard_range(n, rank // gs, gp)
+    return set_lo, set_lo + n_here, first, count
+
+
+def _gpu_calibration(seed, runpars, set_lo, set_hi, first, count):
+    """Runs the shard on this process's GPU; returns a torch CUDA tensor aliasing the library's result vector."""
     import torch
+    ptr, nd = api.calibration_sweep_device(seed, runpars, count, first, set_lo, set_hi)
+    return torch.as_tensor(_CudaBuffer(ptr, nd), device="cuda")
+
+
+def calibration_sweep_sharded(seed, runpars, n, group=None, compute=None, unpack=True):
+    """BASELINE configs[4] (R/calibSim.R:10-40): n_sets parameter vectors x n persons over all ranks of `group`,
+    every set on the same substreams (common random numbers) and — unlike mclapply chunks, which take a new stream
+    each — with the same random numbers as a single-GPU run.  Ranks split the sets first and the persons second;
+    every cell of the result vector (48 doubles per set) is a sum, so ONE all-reduce on the device merges both
+    kinds of shard.  `compute` (tests only) replaces the GPU shard runner: f(seed, runpars, set_lo, set_hi,
+    first_person, persons) -> tensor of 48 * n_sets doubles."""
     import torch.distributed as dist
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    first, count = shard_range(n, rank, world)
     runpars = np.ascontiguousarray(runpars, dtype=np.float64).reshape(-1, 6)
-    res = (compute or api.calibration_sweep)(seed, runpars, count, first)
-    # pack: per set 40 occupancy + 4 TimeAtRisk sums; n_time_at_risk merges by max
-    ns = runpars.shape[0]
-    sums = np.zeros((ns, 44))
-    tmax = np.zeros(ns)
-    names = ["DiseaseFree", "Precursor", "PreClinical", "Clinical"]
-    for s, r in enumerate(res):
-        for j, nm in enumerate(names):
-            if nm in r:
-                sums[s, j * 10:(j + 1) * 10] = r[nm]
-        k = len(r["TimeAtRisk"])
-        sums[s, 40:40 + k] = r["TimeAtRisk"]
-        tmax[s] = k
-    dev = "cuda" if (world > 1 and dist.get_backend(group) == "nccl") else "cpu"
-    t_sum = torch.from_numpy(sums).to(dev)
-    t_max = torch.from_numpy(tmax).to(dev)
+    set_lo, set_hi, first, count = calibration_shard(rank, world, runpars.shape[0], n)
+    vec = (compute or _gpu_calibration)(seed, runpars, set_lo, set_hi, first, count)
     if world > 1:
-        dist.all_reduce(t_sum, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(t_max, op=dist.ReduceOp.MAX, group=group)
-    sums, tmax = t_sum.cpu().numpy(), t_max.cpu().numpy()
-    out = []
-    for s in range(ns):
-        d = {"TimeAtRisk": sums[s, 40:40 + int(tmax[s])].copy()}
-        for j, nm in enumerate(names):
-            col = sums[s, j * 10:(j + 1) * 10]
-            if col.sum() > 0:
-                d[nm] = col.copy()
-        out.append(d)
-    return out
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)  # the single collective
+    if not unpack:
+        return vec
+    host = vec.detach().cpu().numpy()
+    return api.calibration_unpack(host)

@@ -17,6 +17,7 @@
 
 #include "../../include/msim.h"
 #include "../../microsimulation_b200/csrc/host_state.h"
+#include "../../microsimulation_b200/csrc/fastmath.cuh"
 #include "../../microsimulation_b200/csrc/models.cuh"
 #include "../../microsimulation_b200/csrc/person_staged.cuh"
 #include "../../microsimulation_b200/csrc/report.cuh"
@@ -900,6 +901,12 @@ void emu_report_free(msim_report *r) {
 
 int64_t emu_mrg_selftest(uint64_t seed, int64_t n) {
   return mrg_selftest_component<MRG_C1>(seed, n) + mrg_selftest_component<MRG_C2>(seed + 1, n);
+}
+
+
+// csrc/fastmath.cuh on the host (the device runs the same source): mode 0 exp(x), 1 log(x), 2 pow(x, c)
+void emu_fastmath(int mode, int64_t n, const double *x, double c, double *out) {
+  for (int64_t i = 0; i < n; i++) out[i] = mode == 0 ? fm_exp(x[i]) : (mode == 1 ? fm_log(x[i]) : fm_pow(x[i], c));
 }
 
 }  // extern "C"

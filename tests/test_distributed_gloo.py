@@ -28,6 +28,20 @@ def test_shard_range_partitions():
             assert nxt == n
 
 
+def test_calibration_shards_cover_sets_and_persons_once():
+    """The 2-D split of the sweep: every (set, person) belongs to exactly one rank; sets are split before persons."""
+    from microsimulation_b200.distributed import calibration_grid, calibration_shard
+    assert calibration_grid(8, 256) == (8, 1) and calibration_grid(8, 4) == (4, 2) and calibration_grid(8, 1) == (1, 8)
+    assert calibration_grid(4, 3) == (2, 2) and calibration_grid(1, 256) == (1, 1) and calibration_grid(6, 5) == (3, 2)
+    for world, n_sets, n in ((8, 256, 10 ** 6), (8, 4, 1001), (4, 3, 77), (2, 1, 501), (6, 5, 13), (3, 2, 0)):
+        seen = np.zeros((n_sets, n), dtype=np.int32)
+        for r in range(world):
+            lo, hi, first, count = calibration_shard(r, world, n_sets, n)
+            assert 0 <= lo <= hi <= n_sets and first >= 0 and first + count <= n
+            seen[lo:hi, first:first + count] += 1
+        assert np.all(seen == 1)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -57,18 +71,24 @@ def _worker(rank, world, port, n, q):
 
     rep, counts, _ = D.person_simulation_sharded(n, 12345, outputs=6, discount_rate=0.03, compute=compute)
 
-    def calib(seed, runpars, count, first):
+    def calib(seed, runpars, set_lo, set_hi, first, count):
+        """one vector of 48 doubles per set, every cell a sum (include/msim.h, msim_calibration_sweep_device)"""
         from oracle.pyoracle import Calibration
         from microsimulation_b200.api import _seed6
-        out = []
-        for par in runpars:
+        vec = np.zeros(48 * len(runpars))
+        for s_ in range(set_lo, set_hi):
             c = Calibration()
             assert emu.emu_calibration((C.c_double * 6)(*_seed6(seed)), C.c_int64(first), C.c_int64(count),
-                                       (C.c_double * 6)(*par), C.c_int(2), C.byref(c)) == 0
-            out.append(c.to_dict())
-        return out
+                                       (C.c_double * 6)(*runpars[s_]), C.c_int(2), C.byref(c)) == 0
+            vec[48 * s_:48 * s_ + 40] = c.occupancy[:]
+            vec[48 * s_ + 40:48 * s_ + 40 + c.n_time_at_risk] = c.time_at_risk[:c.n_time_at_risk]
+            vec[48 * s_ + 44:48 * s_ + 44 + c.n_time_at_risk] = 1.0
+        return torch.from_numpy(vec)
 
-    cal = D.calibration_sweep_sharded(10, [[4, 0.5, 0.05, 10, 3, 0.5], [4, 0.0, 0.3, 8, 3, 0.2]], 501, compute=calib)
+    pars = [[4, 0.5, 0.05, 10, 3, 0.5], [4, 0.0, 0.3, 8, 3, 0.2], [3.5, 0.4, 0.1, 9, 3, 0.4]]
+    cal = D.calibration_sweep_sharded(10, pars, 501, compute=calib)        # 3 sets over 2 ranks: split by sets
+    cal1 = D.calibration_sweep_sharded(10, pars[:1], 501, compute=calib)   # 1 set over 2 ranks: split by persons
+    cal = cal + cal1
     if rank == 0:
         q.put((rep, counts, cal))
     dist.destroy_process_group()
@@ -91,7 +111,9 @@ def test_two_rank_merge_equals_single_run(oracle, emu):
     assert np.array_equal(counts[:8], ref["counts"][:8])
     assert abs(counts[8] - ref["counts"][8]) <= 1e-12 * ref["counts"][8]
     assert_report_close(rep, ref["report"], rtol=1e-12)
-    refc = oracle.calibration_sweep(10, 0, 501, [[4, 0.5, 0.05, 10, 3, 0.5], [4, 0.0, 0.3, 8, 3, 0.2]])
+    pars = [[4, 0.5, 0.05, 10, 3, 0.5], [4, 0.0, 0.3, 8, 3, 0.2], [3.5, 0.4, 0.1, 9, 3, 0.4]]
+    refc = oracle.calibration_sweep(10, 0, 501, pars + pars[:1])
+    assert len(cal) == 4
     for got, want in zip(cal, refc):
         assert set(got) == set(want)
         for k in want:
