@@ -5,6 +5,7 @@
 
 #include <stdint.h>
 
+#include <map>
 #include <vector>
 
 #include "../include/msim.h"
@@ -36,8 +37,11 @@ struct SickSickerParam {  // README.org:148-187
   int Trt;
 };
 
-template <class Map3>
-void flatten3(const Map3 &m, std::vector<double> &rows, int64_t &n) {  // (state, age) -> value
+// wrap_map on an unordered_map: copied into a std::map first, so rows come out key-sorted (microsimulation.h:1843-1860)
+template <class UMap3>
+void flatten3(const UMap3 &um, std::vector<double> &rows, int64_t &n) {  // (state, age) -> value
+  typedef std::map<typename UMap3::key_type, typename UMap3::mapped_type> Map3;
+  const Map3 m(um.begin(), um.end());
   rows.clear();
   for (typename Map3::const_iterator it = m.begin(); it != m.end(); ++it) {
     rows.push_back((double)it->first.first);
@@ -46,8 +50,10 @@ void flatten3(const Map3 &m, std::vector<double> &rows, int64_t &n) {  // (state
   }
   n = (int64_t)m.size();
 }
-template <class Map4>
-void flatten4(const Map4 &m, std::vector<double> &rows, int64_t &n) {  // (state, event, age) -> number
+template <class UMap4>
+void flatten4(const UMap4 &um, std::vector<double> &rows, int64_t &n) {  // (state, event, age) -> number
+  typedef std::map<typename UMap4::key_type, typename UMap4::mapped_type> Map4;
+  const Map4 m(um.begin(), um.end());
   rows.clear();
   for (typename Map4::const_iterator it = m.begin(); it != m.end(); ++it) {
     rows.push_back((double)std::get<0>(it->first));

@@ -5,10 +5,12 @@
 //   EventReport    inst/include/microsimulation.h:860-1005
 //   SummaryReport  inst/include/microsimulation.h:1010-1190
 //   CostReport     inst/include/microsimulation.h:1195-1296
-// The reference keeps std::unordered_map tables and sorts them into std::map
-// order when wrapping for R (microsimulation.h:1797-1860); the per-key
-// accumulation order is the call order either way, so std::map is used
-// directly here and "wrapping" is flattening to columns.
+// As in the reference the tables are std::unordered_map keyed by pair / tuple with
+// the reference's hash (boost-style hash_combine over the members,
+// microsimulation.h:41-98) — the containers are where the reference's CPU time
+// goes for report models, so the timed baseline uses the same ones — and they are
+// sorted into std::map order when "wrapped" (flattened to columns here), as
+// wrap_map does (microsimulation.h:1843-1860).
 #ifndef MSIM_ORACLE_REPORTS_LITE_H
 #define MSIM_ORACLE_REPORTS_LITE_H
 
@@ -17,11 +19,35 @@
 #include <map>
 #include <set>
 #include <tuple>
+#include <unordered_map>
 #include <vector>
 
 #include "cprocess_lite.h"
 
 namespace ssim {
+
+// microsimulation.h:50-98: seed ^= hash(v) + 0x9e3779b9 + (seed << 6) + (seed >> 2), member after member from seed 0
+template <class T>
+inline void hash_combine(std::size_t &seed, T const &v) {
+  seed ^= std::hash<T>()(v) + 0x9e3779b9 + (seed << 6) + (seed >> 2);
+}
+struct KeyHash {
+  template <class A, class B>
+  std::size_t operator()(std::pair<A, B> const &p) const {
+    std::size_t seed = 0;
+    hash_combine(seed, p.first);
+    hash_combine(seed, p.second);
+    return seed;
+  }
+  template <class A, class B, class C>
+  std::size_t operator()(std::tuple<A, B, C> const &t) const {
+    std::size_t seed = 0;
+    hash_combine(seed, std::get<0>(t));
+    hash_combine(seed, std::get<1>(t));
+    hash_combine(seed, std::get<2>(t));
+    return seed;
+  }
+};
 
 template <class State, class Event, class Time = double, class Utility = double>
 class EventReport {
@@ -95,10 +121,10 @@ class EventReport {
   Utility discountRate, current;
   bool outputUtilities;
   Partition _partition;
-  std::map<Pair, int> _prev;
-  std::map<Pair, Utility> _ut;
-  std::map<Pair, Time> _pt;
-  std::map<Triple, int> _events;
+  std::unordered_map<Pair, int, KeyHash> _prev;
+  std::unordered_map<Pair, Utility, KeyHash> _ut;
+  std::unordered_map<Pair, Time, KeyHash> _pt;
+  std::unordered_map<Triple, int, KeyHash> _events;
   Time startReportAge;
 };
 
@@ -209,11 +235,11 @@ class SummaryReport {
   int n;
   bool indivp;
   Partition _partition;
-  std::map<Pair, int> _prev;
-  std::map<Pair, Utility> _ut;
-  std::map<Pair, Time> _pt;
-  std::map<Triple, int> _events;
-  std::map<Pair, Cost> _costs;
+  std::unordered_map<Pair, int, KeyHash> _prev;
+  std::unordered_map<Pair, Utility, KeyHash> _ut;
+  std::unordered_map<Pair, Time, KeyHash> _pt;
+  std::unordered_map<Triple, int, KeyHash> _events;
+  std::unordered_map<Pair, Cost, KeyHash> _costs;
   std::vector<Utility> _indivUtilities;
   std::vector<Cost> _indivCosts;
   Utility utilityDiscountRate, utilityAlpha, utility;
@@ -251,7 +277,7 @@ class CostReport {
   }
   Cost discountRate, current;
   Partition _partition;
-  std::map<Pair, Cost> _table;
+  std::unordered_map<Pair, Cost, KeyHash> _table;
   Time startReportAge;
 };
 
