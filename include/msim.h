@@ -173,6 +173,21 @@ int msim_callCalibrationSimulation(int32_t n, const double runpar[6], msim_calib
 int msim_callSim_SickSicker(int32_t n, const double param[17], int indivp, int substreams, int64_t first_person,
                             msim_report *out);
 
+/* simulations(n, discountRate, odShape, partitionBy) of the reference's dev-script example with costs
+ * (test/test_microsimulation.R:1006-1093, and :782-865 for the id-indexed calls): a SummaryReport over
+ * setPartition(0, 100, partitionBy) with SummaryReport::add for every interval and SummaryReport::addPointCost
+ * (microsimulation.h:1105-1112) at cancer onset (15000) and at every two-yearly management visit (1000).  Person i
+ * draws from substream first_person+i+1 of a stream made from the package seed.  out as for msim_callSim_SickSicker. */
+int msim_callSim_CancerManagement(int32_t n, double odShape, double discountRate, double partitionBy, int indivp,
+                                  int64_t first_person, msim_report *out);
+
+/* CostReport<State>(discountRate, size, startReportAge) + setPartition(start, finish, delta) + add(state, time, cost)
+ * for n point costs (inst/include/microsimulation.h:1198-1296), all booked to one individual (no individualReset
+ * between them): out = wrap() — Key, age, cost for every cell a cost was booked to — and *current = the individual's
+ * running discounted total (discounted from startReportAge on when that is not 0, microsimulation.h:1273-1277). */
+int msim_cost_report(double discountRate, double startReportAge, double start, double finish, double delta, int32_t n_state,
+                     int64_t n, const int32_t *state, const double *time, const double *cost, msim_table *out, double *current);
+
 /* discountedInterval(y, start, end, rate) (mode 0; b = end) and discountedPoint(y, time, rate) (mode 1; b unused)
  * of inst/include/microsimulation.h:811-836, element-wise on the GPU: the device functions models use for
  * their own discounted totals; parity hook. */

@@ -76,7 +76,7 @@ SYMBOLS = [
     "msim_r_set_user_random_seed", "msim_r_get_user_random_seed", "msim_r_next_rng_substream",
     "msim_r_rng_advance_substream", "msim_next_rng_stream", "msim_user_unif_rand", "msim_mt_set_state", "msim_mt_get_state", "msim_mt_set_seed",
     "msim_callPersonSimulation", "msim_callSimplePerson", "msim_callSimplePerson2", "msim_callIllnessDeath",
-    "msim_callCalibrationSimulation", "msim_callSim_SickSicker", "msim_discounted", "msim_rpexp", "msim_rpexp_gamma", "msim_interpolate", "msim_table_lookup", "msim_gsm_randU", "msim_gsm_randU0", "msim_gsm_eta", "msim_person_run_device", "msim_person_enqueue", "msim_sync",
+    "msim_callCalibrationSimulation", "msim_callSim_SickSicker", "msim_callSim_CancerManagement", "msim_cost_report", "msim_discounted", "msim_rpexp", "msim_rpexp_gamma", "msim_interpolate", "msim_table_lookup", "msim_gsm_randU", "msim_gsm_randU0", "msim_gsm_eta", "msim_person_run_device", "msim_person_enqueue", "msim_sync",
     "msim_last_kernel_ms", "msim_timer_start", "msim_timer_stop", "msim_person_fetch_rowlog", "msim_person_fetch_counts", "msim_dense_to_report",
     "msim_dense_device_ptr", "msim_dense_fetch", "msim_calibration_sweep", "msim_calibration_sweep_device", "msim_calibration_fetch", "msim_calibration_unpack",
     "msim_rng_uniforms", "msim_mt_uniforms",
@@ -113,6 +113,9 @@ def load():
     L.msim_rpexp_gamma.argtypes = [C.c_int, C.c_int32, C.c_double, dp, dp, C.c_int64, dp, dp, dp, dp]
     L.msim_interpolate.argtypes = [C.c_int, C.c_int32, dp, dp, C.c_int64, dp, dp]
     L.msim_table_lookup.argtypes = [C.c_int32, C.c_int64, dp, C.c_int64, dp, dp]
+    L.msim_callSim_CancerManagement.argtypes = [C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int64, C.POINTER(Report)]
+    L.msim_cost_report.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int64,
+                                   C.POINTER(C.c_int32), dp, dp, C.POINTER(Table), dp]
     L.msim_set_stream.argtypes = [C.c_void_p, C.c_int]
     L.msim_set_rowlog_plan.argtypes = [C.c_double, C.c_double]
     L.msim_dense_to_report.argtypes = [C.POINTER(C.c_double), C.POINTER(DenseDims), C.c_double, C.POINTER(Report)]

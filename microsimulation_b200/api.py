@@ -265,6 +265,31 @@ def callSim(n, param, indivp=True, substreams=False, first_person=0, seed=12345)
                    C.c_int64(first_person))
 
 
+def cancer_management(n, odShape=8.0, discountRate=0.03, partitionBy=50.0, indivp=True, first_person=0):
+    """simulations(n, discountRate, odShape, partitionBy) of test/test_microsimulation.R:1006-1093: SummaryReport with
+    point costs (addPointCost); one substream per person of a stream made from the package seed."""
+    _ensure_stream()
+    return _report(load().msim_callSim_CancerManagement, C.c_int32(n), C.c_double(odShape), C.c_double(discountRate),
+                   C.c_double(partitionBy), C.c_int(int(indivp)), C.c_int64(first_person))
+
+
+def cost_report(state, time, cost, discountRate=0.0, startReportAge=0.0, partition=(0.0, 100.0, 1.0), n_state=8):
+    """CostReport(discountRate, startReportAge); setPartition(*partition); add(state[i], time[i], cost[i]) for all i
+    (microsimulation.h:1198-1296).  Returns (wrap() as a dict of columns, the individual's running total)."""
+    state = np.ascontiguousarray(state, dtype=np.int32)
+    time = np.ascontiguousarray(time, dtype=np.float64)
+    cost = np.ascontiguousarray(cost, dtype=np.float64)
+    t = Table()
+    cur = C.c_double()
+    dp = C.POINTER(C.c_double)
+    check(load().msim_cost_report(float(discountRate), float(startReportAge), float(partition[0]), float(partition[1]),
+                                  float(partition[2]), int(n_state), state.size, state.ctypes.data_as(C.POINTER(C.c_int32)),
+                                  time.ctypes.data_as(dp), cost.ctypes.data_as(dp), C.byref(t), C.byref(cur)))
+    d = t.to_dict()
+    load().msim_table_free(C.byref(t))
+    return d, cur.value
+
+
 def calibration_sweep(seed, runpars, n, first_person=0):
     """n_sets parameter vectors x persons [first_person, first_person+n), one seed (common random numbers)."""
     runpars = np.ascontiguousarray(runpars, dtype=np.float64).reshape(-1, 6)

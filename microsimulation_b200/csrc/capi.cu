@@ -374,6 +374,16 @@ int msim_callSim_SickSicker(int32_t n, const double param[17], int indivp, int s
   return sick_sicker_run(n, param, indivp, substreams, first_person, out);
 }
 
+int msim_callSim_CancerManagement(int32_t n, double odShape, double discountRate, double partitionBy, int indivp,
+                                  int64_t first_person, msim_report *out) {
+  return cancer_management_run(n, odShape, discountRate, partitionBy, indivp, first_person, out);
+}
+
+int msim_cost_report(double discountRate, double startReportAge, double start, double finish, double delta, int32_t n_state,
+                     int64_t n, const int32_t *state, const double *time, const double *cost, msim_table *out, double *current) {
+  return cost_report_run(discountRate, startReportAge, start, finish, delta, n_state, n, state, time, cost, out, current);
+}
+
 int msim_discounted(int mode, int64_t n, const double *y, const double *a, const double *b, double rate, double *out) {
   int rc;
   if ((rc = ensure_init())) return rc;

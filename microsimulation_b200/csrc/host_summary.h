@@ -154,4 +154,103 @@ int sick_sicker_run(int64_t n, const double par17[17], int indivp, int substream
   return MSIM_OK;
 }
 
+// ---- cancer management (SummaryReport + addPointCost)
+
+int cancer_management_run(int64_t n, double odShape, double rate, double by, int indivp, int64_t first_person, msim_report *out) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  if (!out || n < 0 || first_person < 0 || !(odShape > 0)) return fail(MSIM_ERR_ARG, "bad arguments");
+  if (!(rate >= 0)) return fail(MSIM_ERR_ARG, "discountRate must be >= 0");
+  SummaryGeom G;
+  // report.setPartition(0.0, 100.0, partitionBy); report.setDiscountRate(discountRate)   (test_microsimulation.R:1029-1030)
+  if (!make_summary_geom(&G, cancer_mgmt::N_STATE, cancer_mgmt::N_EVENT, 0.0, 100.0, by, 1.0e100, rate, rate))
+    return fail(MSIM_ERR_ARG, "partitionBy gives more age bins than the report holds");
+  if ((rc = ensure(g.sgeom, sizeof G))) return rc;
+  CK(cudaMemcpyAsync(g.sgeom.p, &G, sizeof G, cudaMemcpyHostToDevice, g.stream));
+  CK(cudaStreamSynchronize(g.stream));  // G is a stack object
+  const int64_t n_indiv = indivp ? n : 1;
+  if ((rc = ensure(g.dense, sizeof(double) * G.total))) return rc;
+  if ((rc = ensure(g.indiv, sizeof(double) * 2 * (size_t)std::max<int64_t>(n_indiv, 1)))) return rc;
+  if ((rc = ensure(g.small, 16 * sizeof(double)))) return rc;
+  CK(cudaMemsetAsync(g.dense.p, 0, sizeof(double) * G.total, g.stream));
+  CK(cudaMemsetAsync(g.indiv.p, 0, sizeof(double) * 2 * (size_t)std::max<int64_t>(n_indiv, 1), g.stream));
+  CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
+  MgmtParams p;
+  memset(&p, 0, sizeof p);
+  p.first_person = first_person;
+  p.n = n;
+  p.par.odShape = odShape;
+  p.geom = (const SummaryGeom *)g.sgeom.p;
+  p.dense = (double *)g.dense.p;
+  p.indiv = (double *)g.indiv.p;
+  p.indivp = indivp ? 1 : 0;
+  p.error = small_view().error;
+  const size_t smem = sick_kernel_smem(G);
+  const int64_t tiles = (n + BLOCK - 1) / BLOCK;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)g.sm_count * 4, tiles));
+  CK(cudaEventRecord(g.ev0, g.stream));
+  if (n > 0) {
+    // rng = new Rng(): takes the package seed, which then moves on one stream; person i draws from substream first_person + i + 1
+    HostStream hs = g.rng.new_stream();
+    stream_start(hs.Cg.s, first_person, (int64_t)grid * BLOCK, &p.st);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(mgmt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mgmt_kernel<<<grid, BLOCK, smem, g.stream>>>(p);
+    CK(cudaGetLastError());
+    g.launches++;
+  }
+  CK(cudaEventRecord(g.ev1, g.stream));
+  g.timing_pending = true;
+  g.have_last = false;
+  if ((rc = finish_run(nullptr))) return rc;
+  std::vector<double> d(G.total), ind(2 * (size_t)std::max<int64_t>(n_indiv, 1));
+  CK(cudaMemcpy(d.data(), g.dense.p, sizeof(double) * d.size(), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ind.data(), g.indiv.p, sizeof(double) * ind.size(), cudaMemcpyDeviceToHost));
+  dense_to_summary_impl(d.data(), G, ind.data(), n_indiv, out);
+  return MSIM_OK;
+}
+
+// ---- CostReport: a batch of point costs
+
+int cost_report_run(double rate, double start_age, double p_start, double p_finish, double p_delta, int32_t n_state, int64_t n,
+                    const int32_t *state, const double *time, const double *cost, msim_table *out, double *current) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  if (!out || !current || n < 0 || n_state < 1 || n_state > 64 || (n > 0 && (!state || !time || !cost)) || !(rate >= 0))
+    return fail(MSIM_ERR_ARG, "bad arguments");
+  SummaryGeom G;
+  if (!make_summary_geom(&G, n_state, 1, p_start, p_finish, p_delta, 1.0e100, 0.0, rate))
+    return fail(MSIM_ERR_ARG, "the partition has more age bins than the report holds");
+  const size_t nn = (size_t)std::max<int64_t>(n, 1);
+  if ((rc = ensure(g.sgeom, sizeof G))) return rc;
+  if ((rc = ensure(g.dense, sizeof(double) * (G.total + 1)))) return rc;
+  if ((rc = ensure(g.gsm_in, sizeof(double) * 2 * nn))) return rc;
+  if ((rc = ensure(g.aux, sizeof(int) * nn))) return rc;
+  if ((rc = ensure(g.small, 16 * sizeof(double)))) return rc;
+  CK(cudaMemcpyAsync(g.sgeom.p, &G, sizeof G, cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemsetAsync(g.dense.p, 0, sizeof(double) * (G.total + 1), g.stream));
+  CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
+  double *d_time = (double *)g.gsm_in.p, *d_cost = d_time + nn;
+  if (n > 0) {
+    CK(cudaMemcpyAsync(d_time, time, sizeof(double) * n, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(d_cost, cost, sizeof(double) * n, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.aux.p, state, sizeof(int) * n, cudaMemcpyHostToDevice, g.stream));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)g.sm_count * 8));
+    cost_report_kernel<<<grid, 256, 0, g.stream>>>((const SummaryGeom *)g.sgeom.p, n, (const int *)g.aux.p, d_time, d_cost, rate,
+                                                   start_age, (double *)g.dense.p, (double *)g.dense.p + G.total, small_view().error);
+    CK(cudaGetLastError());
+    g.launches++;
+  }
+  g.have_last = false;
+  if ((rc = finish_run(nullptr))) return rc;
+  std::vector<double> d(G.total + 1);
+  CK(cudaMemcpy(d.data(), g.dense.p, sizeof(double) * d.size(), cudaMemcpyDeviceToHost));
+  *current = d[G.total];
+  std::vector<double> rows;  // CostReport::wrap(): (Key, age, cost) for every cell a cost was booked to, key-sorted
+  for (int s = 0; s < G.n_state; s++)
+    for (int b = 0; b < G.n_bin; b++)
+      if (d[G.off_pcn + s * G.n_bin + b] > 0) rows.insert(rows.end(), {(double)s, G.part[b], d[G.off_cost + s * G.n_bin + b]});
+  table_from_rows(rows, 3, COST_COLS, out);
+  return MSIM_OK;
+}
+
 }  // namespace msim_host

@@ -457,4 +457,66 @@ MSIM_HD void uc_of_code(const Par &P, int code, double *u, double *c) {
 }  // namespace sick_sicker
 
 
+// ------------- SummaryReport + addPointCost (test/test_microsimulation.R:782-865, 1006-1093)
+// The reference's dev-script example with costs: other-cause death and cancer onset as Weibulls, a one-off cost when
+// cancer starts and a management cost every two years after (SummaryReport::addPointCost, microsimulation.h:1105-1112).
+namespace cancer_mgmt {
+
+enum state_t { Healthy, Cancer, Death };
+enum event_t { toOtherDeath, toCancer, toCancerDeath, toCancerManagement };
+constexpr int N_STATE = 3, N_EVENT = 4, HEAP_CAP = 4;  // pending: toOtherDeath, toCancerManagement, toCancerDeath
+
+struct Par {
+  double odShape;
+};
+
+template <class Env>
+struct SimplePerson : cProcess<SimplePerson<Env>, typename Env::Src, HEAP_CAP> {
+  typedef cProcess<SimplePerson<Env>, typename Env::Src, HEAP_CAP> Base;
+  using Base::now;
+  using Base::previous;
+  using Base::R;
+  using Base::scheduleAt;
+  using Base::stop_simulation;
+
+  int state;
+  double utility;
+  Env &env;
+  const Par &P;
+
+  MSIM_DEV SimplePerson(Env &e, const Par &p, int64_t /*id*/) : Base(&e.src), state(Healthy), utility(1.0), env(e), P(p) { e.begin_person(); }
+
+  MSIM_DEV void init() {  // test_microsimulation.R:1038-1044
+    state = Healthy;
+    utility = 1.0;
+    scheduleAt(R.rweibull(P.odShape, 85.0), toOtherDeath);
+    scheduleAt(R.rweibull(3.0, 90.0), toCancer);
+  }
+
+  MSIM_DEV void handleMessage(int kind) {  // test_microsimulation.R:1048-1071
+    env.summary(state, kind, previous(), now());
+    switch (kind) {
+      case toOtherDeath:
+      case toCancerDeath:
+        stop_simulation();
+        break;
+      case toCancer:
+        state = Cancer;
+        utility = 0.8;
+        env.point_cost(state, now(), 15000.0);
+        scheduleAt(now() + 2.0, toCancerManagement);
+        if (R.runif(0.0, 1.0) < 0.5) scheduleAt(now() + R.rweibull(2.0, 10.0), toCancerDeath);
+        break;
+      case toCancerManagement:
+        env.point_cost(state, now(), 1000.0);
+        scheduleAt(now() + 2.0, toCancerManagement);
+        break;
+      default:
+        break;
+    }
+  }
+};
+
+}  // namespace cancer_mgmt
+
 }  // namespace msim

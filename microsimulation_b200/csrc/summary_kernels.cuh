@@ -163,6 +163,8 @@ struct SummaryEnv {
     tot_u += du;
     tot_c += dc;
   }
+  // SummaryReport::addPointCost(state, cost, id) at the current time
+  __device__ __forceinline__ void point_cost(int state, double now, double cost) { tot_c += summary_point_cost(*geom, acc, state, now, cost); }
 };
 
 template <bool STREAM, bool ORDERED>
@@ -241,6 +243,103 @@ __global__ void __launch_bounds__(BLOCK) sick_kernel(SickParams p) {
   if (err) atomicCAS(p.error, 0, err);
   __syncthreads();
   shared_acc_flush(env.acc, total, p.dense);
+}
+
+// The cancer-management example (models.cuh, cancer_mgmt): SummaryReport::add for every interval and addPointCost at
+// onset and at every management visit; one substream per person.
+struct MgmtParams {
+  StreamStart st;
+  int64_t first_person, n;
+  cancer_mgmt::Par par;
+  const SummaryGeom *geom;  // in global memory
+  double *dense;            // geom->total accumulators
+  double *indiv;            // [2n] (utilities, costs) per person if indivp, else [2]
+  int indivp;
+  int *error;
+};
+
+__global__ void __launch_bounds__(BLOCK) mgmt_kernel(MgmtParams p) {
+  typedef SummaryEnv<MrgSource> Env;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SummaryGeom *sg = reinterpret_cast<SummaryGeom *>(smem_raw);
+  {
+    const int *src = reinterpret_cast<const int *>(p.geom);
+    int *dst = reinterpret_cast<int *>(sg);
+    for (int k = threadIdx.x; k < (int)(sizeof(SummaryGeom) / 4); k += BLOCK) dst[k] = src[k];
+  }
+  __syncthreads();
+  const int total = sg->total, n_f = sg->n_float;
+  double *s_f = reinterpret_cast<double *>(smem_raw + ((sizeof(SummaryGeom) + 15) & ~(size_t)15));
+  int *s_i = reinterpret_cast<int *>(s_f + n_f);
+  Env env;
+  env.geom = sg;
+  env.acc.f = s_f;
+  env.acc.i = s_i;
+  env.acc.n_f = n_f;
+  shared_acc_clear(env.acc, total);
+  __syncthreads();
+  Mrg32k3a sub = thread_start_state(p.st, blockIdx.x * BLOCK + threadIdx.x);
+  const int64_t stride = (int64_t)gridDim.x * BLOCK;
+  int err = 0;
+  double all_u = 0.0, all_c = 0.0;
+  for (int64_t i0 = (int64_t)blockIdx.x * BLOCK + (threadIdx.x & ~31); i0 < p.n; i0 += stride) {
+    const int64_t i = i0 + (threadIdx.x & 31);
+    __syncwarp();  // every pass starts with the warp together
+    if (i < p.n) {
+      env.src.g = sub;
+      env.u = 1.0;  // the report's utility and cost are never set by this model: the constructor's (microsimulation.h:1030-1031)
+      env.c = 0.0;
+      env.tot_u = env.tot_c = 0.0;
+      cancer_mgmt::SimplePerson<Env> person(env, p.par, p.first_person + i);
+      person.run();
+      if (person.error_) err = person.error_;
+      if (p.indivp) {
+        p.indiv[2 * i] = env.tot_u;
+        p.indiv[2 * i + 1] = env.tot_c;
+      } else {
+        all_u += env.tot_u;
+        all_c += env.tot_c;
+      }
+    }
+    __syncwarp();
+    sub.jump(p.st.stride);
+  }
+  if (!p.indivp) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      all_u += __shfl_xor_sync(0xffffffffu, all_u, o);
+      all_c += __shfl_xor_sync(0xffffffffu, all_c, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&p.indiv[0], all_u);
+      atomicAdd(&p.indiv[1], all_c);
+    }
+  }
+  if (err) atomicCAS(p.error, 0, err);
+  __syncthreads();
+  shared_acc_flush(env.acc, total, p.dense);
+}
+
+// CostReport::add (microsimulation.h:1265-1278) for a batch of point costs, all booked to one individual: the cost
+// cells of a SummaryGeom in global memory and the individual's running total `current`
+__global__ void cost_report_kernel(const SummaryGeom *geom, int64_t n, const int *state, const double *time, const double *cost,
+                                   double rate, double start_age, double *dense, double *current, int *error) {
+  struct GlobalAcc {
+    double *d;
+    __device__ __forceinline__ void addf(int i, double v) { atomicAdd(&d[i], v); }
+    __device__ __forceinline__ void addi(int i, int v) { atomicAdd(&d[i], (double)v); }
+  } acc = {dense};
+  double cur = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (state[i] < 0 || state[i] >= geom->n_state) {
+      atomicCAS(error, 0, -3);
+      continue;
+    }
+    cur += cost_report_add(*geom, acc, state[i], time[i], cost[i], rate, start_age);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cur += __shfl_xor_sync(0xffffffffu, cur, o);
+  if ((threadIdx.x & 31) == 0 && cur != 0.0) atomicAdd(current, cur);
 }
 
 inline size_t sick_kernel_smem(const SummaryGeom &g) {

@@ -569,6 +569,82 @@ void run_sick_sicker(int64_t n, const SickSickerParam *param, bool indivp, bool 
   flatten_summary(report, out);
 }
 
+// ------------------------- SummaryReport + addPointCost (test/test_microsimulation.R:782-865, 1006-1093)
+// The dev script's "simple example" with cancer management: other-cause death and cancer onset as Weibulls, a
+// one-off cost when cancer starts and a management cost every two years after (SummaryReport::addPointCost,
+// microsimulation.h:1105-1112), intervals and point costs booked to the individual `id`.  Onset is the Weibull of the
+// script's second version (:1043); the first version's gsm onset (:818) needs a fitted model the script does not keep.
+namespace cancermgmt {
+
+enum state_t { Healthy, Cancer, Death };
+enum event_t { toOtherDeath, toCancer, toCancerDeath, toCancerManagement };
+typedef SummaryReport<short, short> Report;
+
+class SimplePerson : public cProcess {
+ public:
+  int id;
+  state_t state;
+  double utility, odShape;
+  Report *report;
+  SimplePerson(double odShape, Report *report) : id(-1), odShape(odShape), report(report) {}
+  void init() {
+    id++;
+    state = Healthy;
+    utility = 1.0;
+    scheduleAt(R::rweibull(odShape, 85.0), toOtherDeath);
+    scheduleAt(R::rweibull(3.0, 90.0), toCancer);
+  }
+  void handleMessage(const cMessage *msg) {
+    g_events_handled++;
+    report->add(state, msg->kind, this->previous(), now(), id);
+    switch (msg->kind) {
+      case toOtherDeath:
+      case toCancerDeath:
+        Sim::stop_simulation();
+        break;
+      case toCancer:
+        state = Cancer;
+        utility = 0.8;
+        report->addPointCost(state, 15000.0, id);
+        scheduleAt(now() + 2.0, toCancerManagement);
+        if (R::runif(0.0, 1.0) < 0.5) scheduleAt(now() + R::rweibull(2.0, 10.0), toCancerDeath);
+        break;
+      case toCancerManagement:
+        report->addPointCost(state, 1000.0, id);
+        scheduleAt(now() + 2.0, toCancerManagement);
+        break;
+      default:
+        break;
+    }
+  }
+};
+
+}  // namespace cancermgmt
+
+// simulations(n, discountRate, odShape, partitionBy) of the dev script, person i on substream first_person+i+1 of a
+// stream made from the package seed
+void run_cancer_management(int64_t n, double odShape, double discountRate, double partitionBy, bool indivp, int64_t first_person,
+                           ReportTables *out) {
+  using namespace cancermgmt;
+  Report report((int)n, indivp);
+  report.setPartition(0.0, 100.0, partitionBy);
+  report.setDiscountRate(discountRate);
+  SimplePerson person(odShape, &report);
+  rlite::RNGkind(rlite::USER_UNIF);
+  rlite::set_user_unif_rand(user_unif_rand);
+  Rng *rng = new Rng();
+  rng->set();
+  if (first_person > 0) rng->AdvanceSubstream(0, (int32_t)first_person);
+  for (int64_t i = 0; i < n; i++) {
+    rng->nextSubstream();
+    Sim::create_process(&person);
+    Sim::run_simulation();
+    Sim::clear();
+  }
+  delete rng;
+  flatten_summary(report, out);
+}
+
 // ----------------------------------------------- doc examples (examples.org)
 namespace docs {
 

@@ -97,6 +97,8 @@ void run_calibration(int64_t first_person, int64_t n, const double par[6], msim_
 void run_illness_death(int64_t n, double cure, double zsd, ReportTables *out);
 void run_simple_person(int64_t n, RowLog *log);
 void run_simple_person2(int64_t n, ReportTables *out);
+void run_cancer_management(int64_t n, double odShape, double discountRate, double partitionBy, bool indivp, int64_t first_person,
+                           ReportTables *out);
 void run_sick_sicker(int64_t n, const SickSickerParam *param, bool indivp, bool substreams, int64_t first_person,
                      ReportTables *out, std::vector<double> *trace);
 double run_tick_tock(std::vector<double> *times);

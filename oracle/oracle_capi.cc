@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <vector>
 
 #include "cprocess_lite.h"
@@ -243,6 +244,14 @@ int oracle_sick_sicker(int64_t n, const double par[17], int indivp, int substrea
   return 0;
 }
 
+int oracle_cancer_management(int64_t n, double odShape, double discountRate, double partitionBy, int indivp, int64_t first_person,
+                             msim_report *out) {
+  ReportTables rt;
+  run_cancer_management(n, odShape, discountRate, partitionBy, indivp != 0, first_person, &rt);
+  fill_report(rt, out);
+  return 0;
+}
+
 // doc examples: return event times; tick_tock's finish time is the last one
 int64_t oracle_tick_tock(double *times, int64_t cap) {
   std::vector<double> t;
@@ -335,7 +344,8 @@ int oracle_cost_report(double rate, double start_age, double p_start, double p_f
   for (int64_t i = 0; i < n; i++) rep.add((short)state[i], time[i], cost[i]);
   *current = rep.current;
   int64_t k = 0;
-  for (auto it = rep._table.begin(); it != rep._table.end() && k < cap; ++it, ++k) {
+  const std::map<std::pair<short, double>, double> sorted(rep._table.begin(), rep._table.end());  // wrap_map order
+  for (auto it = sorted.begin(); it != sorted.end() && k < cap; ++it, ++k) {
     out_rows[3 * k] = it->first.first;
     out_rows[3 * k + 1] = it->first.second;
     out_rows[3 * k + 2] = it->second;

@@ -242,6 +242,17 @@ class Oracle:
             d["trace"] = tr[:tlen.value].reshape(-1, 5)
         return d
 
+    def cancer_management(self, n, odShape=8.0, discountRate=0.03, partitionBy=50.0, indivp=True, first_person=0):
+        """simulations() of test/test_microsimulation.R:782-865 / 1006-1093 (SummaryReport + addPointCost), person i
+        on substream first_person + i + 1 of a stream made from the package seed."""
+        r = Report()
+        rc = self.lib.oracle_cancer_management(C.c_int64(n), C.c_double(odShape), C.c_double(discountRate), C.c_double(partitionBy),
+                                               C.c_int(int(indivp)), C.c_int64(first_person), C.byref(r))
+        assert rc == 0
+        d = r.to_dict()
+        self.lib.oracle_report_free(C.byref(r))
+        return d
+
     # ---- generalised survival model (gsm_lite); `model` is a ctypes msim_gsm (include/msim.h), passed by reference
     def _gsm(self, fn, model, u, extra, index, scale):
         u = np.ascontiguousarray(u, dtype=np.float64)

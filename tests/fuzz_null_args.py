@@ -10,6 +10,10 @@ calls = {
  "msim_callPersonSimulation": "(None, C.c_int32(5), None)", "msim_callSimplePerson": "(C.c_int32(5), None)",
  "msim_callSimplePerson2": "(C.c_int32(5), None)", "msim_callIllnessDeath": "(C.c_int32(5), C.c_double(.1), C.c_double(0), None)",
  "msim_callCalibrationSimulation": "(C.c_int32(5), None, None)", "msim_callSim_SickSicker": "(C.c_int32(5), None, 1, 0, C.c_int64(0), None)",
+ "msim_callSim_CancerManagement": "(C.c_int32(5), C.c_double(8), C.c_double(0.03), C.c_double(50), 1, C.c_int64(0), None)",
+ "msim_cost_report": "(C.c_double(0.03), C.c_double(0), C.c_double(0), C.c_double(100), C.c_double(1), C.c_int32(8), C.c_int64(5), None, None, None, None, None)",
+ "msim_calibration_sweep_device": "(None, C.c_int64(0), C.c_int64(5), C.c_int32(1), None, C.c_int32(0), C.c_int32(1), None, None)",
+ "msim_calibration_fetch": "(None, C.c_int64(48))", "msim_calibration_unpack": "(None, C.c_int32(1), None)",
  "msim_calibration_sweep": "(None, C.c_int64(0), C.c_int64(5), C.c_int32(1), None, None)",
  "msim_discounted": "(0, C.c_int64(5), None, None, None, C.c_double(0.03), None)",
  "msim_rpexp": "(0, C.c_int32(3), None, None, C.c_int64(5), None, None, None)",

@@ -473,6 +473,53 @@ def test_sick_sicker_substream_regime_vs_oracle(msim, oracle, n, first):
     _summary_equal(g, r)
 
 
+@pytest.mark.parametrize("n,first,by,rate,indivp", [(0, 0, 50.0, 0.03, 1), (7, 0, 50.0, 0.03, 1), (20000, 0, 20.0, 0.03, 1),
+                                                   (20000, 5000, 1.0, 0.0, 1), (30000, 0, 50.0, 0.05, 0)])
+def test_summary_report_point_costs_vs_oracle(msim, oracle, n, first, by, rate, indivp):
+    """SummaryReport::addPointCost (microsimulation.h:1105-1112) on the GPU: the reference's dev-script example with a
+    one-off cost at cancer onset and a management cost every two years (test/test_microsimulation.R:1006-1093),
+    against the oracle — cost rows (including cells that only ever received a point cost), per-individual totals."""
+    import microsimulation_b200.api as api
+    api.set_user_random_seed(12345)
+    oracle.set_user_random_seed(12345)
+    g = api.cancer_management(n, 8.0, rate, by, indivp=bool(indivp), first_person=first)
+    r = oracle.cancer_management(n, 8.0, rate, by, indivp=bool(indivp), first_person=first)
+    _summary_equal(g, r)
+    if n >= 20000:
+        assert g["costs"]["cost"].sum() > 0 and len(g["costs"]["cost"]) >= len(g["pt"]["pt"])
+        # the Cancer state's costs are point costs only (the report's interval cost is never set: 0)
+        np.testing.assert_allclose(g["indiv"]["costs"].sum(), g["costs"]["cost"].sum(), rtol=1e-12)
+
+
+@pytest.mark.parametrize("rate,start_age,part", [(0.0, 0.0, (0.0, 100.0, 1.0)), (0.03, 0.0, (0.0, 100.0, 5.0)),
+                                                  (0.03, 50.0, (0.0, 100.0, 10.0)), (0.05, 30.0, (20.0, 90.0, 2.5))])
+def test_cost_report_add_vs_oracle(msim, oracle, rate, start_age, part):
+    """CostReport::add / addPointCost (microsimulation.h:1265-1278) as a batch on the GPU against the oracle's
+    CostReport: the wrap() table and the individual's running total (discounted from startReportAge on)."""
+    import ctypes as C
+    import microsimulation_b200.api as api
+    rng = np.random.RandomState(7)
+    n = 50000
+    state = rng.randint(0, 5, n).astype(np.int32)
+    time = np.round(rng.uniform(0, 110, n), 3)
+    time[:100] = np.arange(100)           # exactly on partition points
+    cost = np.round(rng.uniform(0, 2e4, n), 2)
+    cost[100:120] = 0.0
+    got, cur = api.cost_report(state, time, cost, rate, start_age, part, n_state=8)
+    rows = np.zeros(3 * 4096)
+    ref_cur = C.c_double()
+    dp = C.POINTER(C.c_double)
+    k = oracle.lib.oracle_cost_report(C.c_double(rate), C.c_double(start_age), C.c_double(part[0]), C.c_double(part[1]), C.c_double(part[2]),
+                                      C.c_int64(n), state.ctypes.data_as(C.POINTER(C.c_int)), time.ctypes.data_as(dp),
+                                      cost.ctypes.data_as(dp), rows.ctypes.data_as(dp), C.c_int64(4096), C.byref(ref_cur))
+    ref = rows[:3 * k].reshape(k, 3)
+    assert np.array_equal(got["Key"], ref[:, 0]) and np.array_equal(got["age"], ref[:, 1])
+    np.testing.assert_allclose(got["cost"], ref[:, 2], rtol=1e-11)
+    np.testing.assert_allclose(cur, ref_cur.value, rtol=1e-11)
+    with pytest.raises(msim.MsimError):
+        api.cost_report(np.array([9], dtype=np.int32), [1.0], [1.0], n_state=8)
+
+
 @pytest.mark.parametrize("substreams", [False, True])
 def test_sick_sicker_event_queues_agree(msim, oracle, substreams):
     """Default (small ordered array, cancelled actions removed), heap.h's binary heap with lingering cancelled entries,
