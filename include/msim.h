@@ -328,6 +328,12 @@ int msim_calibration_unpack(const double *host_vector, int32_t n_sets, msim_cali
  * first_substream+j of the stream whose state is `seed` (substream 0 = seed). */
 int msim_rng_uniforms(const double seed[6], int64_t first_substream, int64_t n_substreams, int32_t draws,
                       double *uniforms_host);
+/* Measurement hook: one launch of building block `op` of the person-r path (0 empty loop, 1 substream jump, 2 U01,
+ * 3 Weibull arithmetic (log + pow), 4 exp_rand, 5 event queue insert + pop, 6 EventReport::add, 7 exp) on n_threads
+ * threads (a multiple of 256), `reps` repetitions per thread, every warp full and converged.  Run under ncu to read
+ * the block's instruction count (scripts/inst_floor.py -> profiles/traffic.json "instruction_floor"); *ms is the
+ * kernel's device time. */
+int msim_microbench(int op, int64_t n_threads, int reps, float *ms);
 /* MT19937 parity hook: the first n uniforms R's unif_rand() would return from
  * the current MT state (state is NOT advanced). */
 int msim_mt_uniforms(int64_t n, double *uniforms_host);

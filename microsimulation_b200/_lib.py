@@ -79,7 +79,7 @@ SYMBOLS = [
     "msim_callCalibrationSimulation", "msim_callSim_SickSicker", "msim_callSim_CancerManagement", "msim_cost_report", "msim_discounted", "msim_rpexp", "msim_rpexp_gamma", "msim_interpolate", "msim_table_lookup", "msim_gsm_randU", "msim_gsm_randU0", "msim_gsm_eta", "msim_person_run_device", "msim_person_enqueue", "msim_sync",
     "msim_last_kernel_ms", "msim_timer_start", "msim_timer_stop", "msim_person_fetch_rowlog", "msim_person_fetch_counts", "msim_dense_to_report",
     "msim_dense_device_ptr", "msim_dense_fetch", "msim_calibration_sweep", "msim_calibration_sweep_device", "msim_calibration_fetch", "msim_calibration_unpack",
-    "msim_rng_uniforms", "msim_mt_uniforms",
+    "msim_rng_uniforms", "msim_mt_uniforms", "msim_microbench",
 ]
 
 _lib = None

@@ -20,6 +20,7 @@
 #include "host_person.h"
 #include "host_runtime.h"
 #include "host_summary.h"
+#include "microbench.cuh"
 
 using namespace msim;
 
@@ -647,6 +648,36 @@ int msim_rng_uniforms(const double seed[6], int64_t first_substream, int64_t n_s
   g.launches++;
   CK(cudaMemcpyAsync(uniforms_host, g.uniforms.p, bytes, cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
+  return MSIM_OK;
+}
+
+// Instruction-weight microbenchmarks (csrc/microbench.cuh): one launch of building block `op` on n_threads threads,
+// `reps` repetitions each; meant to be run under ncu (scripts/inst_floor.py).  Returns the kernel's device time.
+int msim_microbench(int op, int64_t n_threads, int reps, float *ms) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  if (op < 0 || op >= MB_N_OPS || n_threads < 256 || n_threads > (int64_t)JUMP_TAB * JUMP_TAB || reps < 1 || !ms)
+    return fail(MSIM_ERR_ARG, "bad arguments");
+  const int grid = (int)(n_threads / 256);
+  if ((rc = ensure(g.uniforms, sizeof(double) * (size_t)grid * 256))) return rc;
+  MicroParams p;
+  memset(&p, 0, sizeof p);
+  uint32_t state[6] = {12345, 12345, 12345, 12345, 12345, 12345};
+  stream_start(state, 0, (int64_t)grid * 256, &p.st);
+  p.geom = ages_geom(person_r::N_STATE, person_r::N_EVENT, 0.03);
+  p.reps = reps;
+  p.sink = (double *)g.uniforms.p;
+  typedef void (*K)(const MicroParams);
+  static const K kernels[MB_N_OPS] = {microbench_kernel<MB_EMPTY>, microbench_kernel<MB_JUMP>,     microbench_kernel<MB_U01>,
+                                      microbench_kernel<MB_WEIBULL>, microbench_kernel<MB_EXP_RAND>, microbench_kernel<MB_HEAP>,
+                                      microbench_kernel<MB_REPORT>, microbench_kernel<MB_EXP>};
+  CK(cudaEventRecord(g.ev0, g.stream));
+  kernels[op]<<<grid, 256, 0, g.stream>>>(p);
+  CK(cudaGetLastError());
+  g.launches++;
+  CK(cudaEventRecord(g.ev1, g.stream));
+  CK(cudaEventSynchronize(g.ev1));
+  CK(cudaEventElapsedTime(ms, g.ev0, g.ev1));
   return MSIM_OK;
 }
 

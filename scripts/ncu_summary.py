@@ -90,6 +90,7 @@ def main():
     ap.add_argument("--json", default=None, help="write the per-person figures of the FIRST launch here")
     ap.add_argument("--title", default=None)
     ap.add_argument("--key", default=None, help="key under which --json stores this kernel's figures")
+    ap.add_argument("--build-hash", default=None, help="hash of the sources the profiled library was built from (microsimulation_b200.build.source_hash), stored with --json")
     ap.add_argument("--pick", default=None, help="substring of the kernel name whose first launch --json stores (default: first launch)")
     args = ap.parse_args()
     hdr, units, launches = read_raw(args.rep)
@@ -158,6 +159,8 @@ def main():
         except Exception:
             cur = {}
         cur[args.key or "default"] = first
+        if args.build_hash:
+            cur["build_hash"] = args.build_hash
         with open(args.json, "w") as f:
             json.dump(cur, f, indent=1, sort_keys=True)
     print("wrote", args.out, "(%d launches)" % len(launches))
