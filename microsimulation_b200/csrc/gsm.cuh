@@ -1,12 +1,18 @@
 // Generalised survival model: survival-time inversion as a device function
-// (north_star (e)).  Follows the reference's
+// (north_star (e)).  What the reference computes with
 //   gsm::eta / operator() / randU / randU0      src/gsm.cpp:15-58
-//   ns::eval, bs::eval, SplineBasis::set_cursor /
-//   basis_funcs / slow_evaluate                  src/splines.cpp:24-118, 145-167, 204-219
+//   ns::eval (natural cubic spline basis, linear beyond the boundary knots)   src/splines.cpp:194-219
 //   R_zeroin2_functor_ptr (Brent)                inst/include/c_optim.h:9-105
-// with Armadillo vectors replaced by fixed-capacity arrays.  S(t) = u is
-// solved for a natural-cubic-spline log cumulative hazard eta(log t) (link PH:
-// log(-log S)), one inversion per thread.
+// S(t) = u is solved for a natural-cubic-spline log cumulative hazard eta(log t) (link PH: log(-log S)), one
+// inversion per thread.
+//
+// The spline is NOT evaluated the reference's way (B-spline basis by the de Boor recurrence at every call, then the
+// projection matrix, then the coefficients: ~n_ns x df multiply-adds per evaluation).  A term's contribution
+// f(y) = ns::eval(y) . gamma is a piecewise cubic with a line on either side of the boundary knots, so the host
+// expands it ONCE per model into polynomial coefficients per knot interval (Cox-de Boor carried out on polynomials,
+// projection matrix and gamma folded in: gsm_term_build below), and an evaluation on the device is a short search
+// over the breakpoints and three multiply-adds.  Parity for this row is unpinned in the reference (no expected value
+// in the tree); the oracle restates the reference's evaluation and the two agree to rounding (tests/test_gsm.py).
 //
 // The model is a flat struct (no pointers except the per-covariate-pattern
 // vectors) so that it can be passed by value to a kernel; msim_gsm (msim.h) is
@@ -16,24 +22,22 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "fastmath.cuh"
 #include "mrg32k3a.cuh"
 
 namespace msim {
 
 constexpr int GSM_MAX_TERMS = 4;
-constexpr int GSM_MAX_INTERIOR = 12;                  // interior knots per term
-constexpr int GSM_MAX_COEF = GSM_MAX_INTERIOR + 4;    // B-spline coefficients (order 4)
-constexpr int GSM_MAX_KNOTS = GSM_MAX_INTERIOR + 8;   // full knot vector
-constexpr int GSM_MAX_NS = GSM_MAX_COEF;              // rows of the natural-spline projection
+constexpr int GSM_MAX_INTERIOR = 12;                 // interior knots per term
+constexpr int GSM_MAX_PIECES = GSM_MAX_INTERIOR + 3;  // a line, up to n_interior + 1 cubics, a line
+constexpr int GSM_MAX_NS = GSM_MAX_INTERIOR + 4;      // rows of the natural-spline projection the host accepts
 
 struct GsmTerm {
-  int n_interior, intercept, cure, n_ns, df;  // df = intercept + 3 + n_interior = length of bs::eval
-  int nknots, ncoef;
-  double knots[GSM_MAX_KNOTS];
-  double b0, b1;                          // Boundary_knots
-  double q[GSM_MAX_NS][GSM_MAX_COEF];     // q_matrix, n_ns x df
-  double gamma[GSM_MAX_NS];
-  double tl0[GSM_MAX_NS], tl1[GSM_MAX_NS], tr0[GSM_MAX_NS], tr1[GSM_MAX_NS];
+  int n_pieces;                 // piece 0: y < b0; pieces 1 .. n_pieces-2: [brk[p], brk[p+1]); piece n_pieces-1: y > b1
+  double b0, b1;                // Boundary_knots
+  double brk[GSM_MAX_PIECES];   // left end of piece p (p >= 1), ascending; brk[n_pieces-1] = b1
+  double org[GSM_MAX_PIECES];   // origin of piece p's polynomial (b0 for piece 0, b1 for the last, else brk[p])
+  double c[GSM_MAX_PIECES][4];  // f(y) = c0 + h (c1 + h (c2 + h c3)), h = y - org[p]
 };
 
 struct GsmModel {
@@ -44,125 +48,123 @@ struct GsmModel {
   const double *x[GSM_MAX_TERMS];      // [n_index] each
 };
 
-// ---- SplineBasis (order 4) ------------------------------------------------
+// ns::eval(y, 0) . gamma of one term (splines.cpp:204-219 and gsm.cpp:19), from the expanded form
+MSIM_HD double ns_dot_gamma(const GsmTerm &T, double y) {
+  int p;
+  if (y < T.b0) {
+    p = 0;
+  } else if (y > T.b1) {
+    p = T.n_pieces - 1;
+  } else {
+    p = 1;
+    while (p + 2 < T.n_pieces && y >= T.brk[p + 1]) p++;
+  }
+  const double h = y - T.org[p];
+  return MSIM_FMA(h, MSIM_FMA(h, MSIM_FMA(h, T.c[p][3], T.c[p][2]), T.c[p][1]), T.c[p][0]);
+}
 
-struct SplineCursor {
-  int curs, boundary;
+// ---- model set-up (host) ----------------------------------------------------
+
+// What ns::ns + bs::bs hold for a term (splines.cpp:145-203): boundary and interior knots, whether the first
+// B-spline is kept (intercept), the projection matrix q (n_ns x df, df = intercept + 3 + n_interior) and gamma.
+struct GsmTermSpec {
+  int n_interior, intercept, n_ns;
+  double b0, b1;
+  const double *interior;  // ascending, strictly inside (b0, b1)
+  const double *q;         // row-major n_ns x df
+  const double *gamma;     // n_ns
 };
 
-// splines.cpp:24-41
-MSIM_HD SplineCursor spline_set_cursor(const GsmTerm &T, double x) {
-  SplineCursor c;
-  c.curs = -1;
-  c.boundary = 0;
-  for (int i = 0; i < T.nknots; i++) {
-    if (T.knots[i] >= x) c.curs = i;
-    if (T.knots[i] > x) break;
+// Expands a term into per-interval polynomials.  On the knot interval [t_j, t_j+1) the four cubic B-splines that are
+// non-zero there are built by the Cox-de Boor recurrence
+//   N_{i,k}(x) = (x - t_i)/(t_{i+k-1} - t_i) N_{i,k-1}(x) + (t_{i+k} - x)/(t_{i+k} - t_{i+1}) N_{i+1,k-1}(x)
+// with the N's held as polynomials in h = x - t_j (terms with a zero denominator vanish), then weighted by
+// w_i = sum_r gamma_r q[r][i - 1 + intercept] (bs::eval drops the first B-spline unless intercept) and summed.
+// The lines beyond the boundary knots continue value and slope there (ns::eval, splines.cpp:205-217).
+inline bool gsm_term_build(GsmTerm &T, const GsmTermSpec &S) {
+  const int ni = S.n_interior, m = ni + 8, ncoef = m - 4, df = S.intercept + 3 + ni;
+  if (ni < 0 || ni > GSM_MAX_INTERIOR || S.n_ns < 1 || S.n_ns > GSM_MAX_NS || !(S.b0 < S.b1)) return false;
+  double t[GSM_MAX_INTERIOR + 8], w[GSM_MAX_INTERIOR + 4];
+  for (int k = 0; k < 4; k++) t[k] = S.b0, t[m - 1 - k] = S.b1;
+  for (int k = 0; k < ni; k++) {
+    t[4 + k] = S.interior[k];
+    if (!(t[4 + k] > t[3 + k]) || !(t[4 + k] < S.b1)) return false;  // ascending, strictly inside
   }
-  if (c.curs > T.nknots - 4) {
-    int lastLegit = T.nknots - 4;
-    if (x == T.knots[lastLegit]) {
-      c.boundary = 1;
-      c.curs = lastLegit;
-    }
+  for (int i = 0; i < ncoef; i++) {
+    const int col = i - 1 + S.intercept;
+    w[i] = 0.0;
+    if (col >= 0 && col < df)
+      for (int r = 0; r < S.n_ns; r++) w[i] += S.gamma[r] * S.q[r * df + col];
   }
-  return c;
-}
-
-// splines.cpp:74-97: the four cubic B-splines that are non-zero at x
-MSIM_HD void spline_basis_funcs(const GsmTerm &T, int curs, double x, double b[4]) {
-  double rdel[3], ldel[3];
-  for (int i = 0; i < 3; i++) {  // diff_table, :42-50
-    rdel[i] = T.knots[curs + i] - x;
-    ldel[i] = x - T.knots[curs - (i + 1)];
-  }
-  b[0] = 1.0;
-  for (int j = 1; j <= 3; j++) {
-    double saved = 0.0;
-    for (int r = 0; r < j; r++) {
-      double den = rdel[r] + ldel[j - 1 - r];
-      if (den != 0.0) {
-        double term = b[r] / den;
-        b[r] = saved + rdel[r] * term;
-        saved = ldel[j - 1 - r] * term;
-      } else {
-        if (r != 0 || rdel[r] != 0.0) b[r] = saved;
-        saved = 0.0;
+  T.b0 = S.b0;
+  T.b1 = S.b1;
+  int np = 1;  // piece 0 is the left line, filled in below
+  for (int j = 3; j < m - 4; j++) {
+    if (!(t[j] < t[j + 1])) continue;
+    // N[k][a]: polynomial (coefficients of h^0..h^3) of N_{j-k+1+a, k} for a = 0..k-1, on this interval
+    double N[5][4][4] = {};
+    N[1][0][0] = 1.0;
+    for (int k = 2; k <= 4; k++)
+      for (int a = 0; a < k; a++) {
+        const int i = j - k + 1 + a;
+        double out[4] = {0, 0, 0, 0};
+        if (a >= 1) {  // first term: (x - t_i)/(t_{i+k-1} - t_i) * N_{i,k-1}; N_{i,k-1} is entry a-1 of order k-1
+          const double den = t[i + k - 1] - t[i];
+          if (den != 0.0) {
+            const double *P = N[k - 1][a - 1];
+            const double s0 = (t[j] - t[i]) / den, s1 = 1.0 / den;  // (x - t_i)/den = s0 + s1 h
+            for (int d = 0; d < 4; d++) {
+              out[d] += s0 * P[d];
+              if (d + 1 < 4) out[d + 1] += s1 * P[d];
+            }
+          }
+        }
+        if (a <= k - 2) {  // second term: (t_{i+k} - x)/(t_{i+k} - t_{i+1}) * N_{i+1,k-1}; entry a of order k-1
+          const double den = t[i + k] - t[i + 1];
+          if (den != 0.0) {
+            const double *P = N[k - 1][a];
+            const double s0 = (t[i + k] - t[j]) / den, s1 = -1.0 / den;
+            for (int d = 0; d < 4; d++) {
+              out[d] += s0 * P[d];
+              if (d + 1 < 4) out[d + 1] += s1 * P[d];
+            }
+          }
+        }
+        for (int d = 0; d < 4; d++) N[k][a][d] = out[d];
       }
+    if (np >= GSM_MAX_PIECES - 1) return false;
+    T.brk[np] = T.org[np] = t[j];
+    for (int d = 0; d < 4; d++) {
+      double v = 0.0;
+      for (int a = 0; a < 4; a++) v += w[j - 3 + a] * N[4][a][d];
+      T.c[np][d] = v;
     }
-    b[j] = saved;
+    np++;
   }
-}
-
-// splines.cpp:51-73: value of the nder-th derivative of sum_i a[i] B_i at x (a is scratch, overwritten)
-MSIM_HD double spline_slow_evaluate(const GsmTerm &T, const SplineCursor &c, double x, int nder, double a[4]) {
-  int ti = c.curs, lpt, apt, rpt, inner, outer = 3;
-  if (c.boundary && nder == 3) return 0.0;
-  while (nder--) {
-    for (inner = outer, apt = 0, lpt = ti - outer; inner--; apt++, lpt++)
-      a[apt] = (double)outer * (a[apt + 1] - a[apt]) / (T.knots[lpt + outer] - T.knots[lpt]);
-    outer--;
+  // the lines: value and slope at the boundary knots
+  const int last = np - 1;
+  const double hl = S.b1 - T.org[last];
+  const double *cl = T.c[last];
+  T.brk[0] = T.org[0] = S.b0;
+  T.c[0][0] = T.c[1][0];
+  T.c[0][1] = T.c[1][1];
+  T.c[0][2] = T.c[0][3] = 0.0;
+  T.brk[np] = T.org[np] = S.b1;
+  T.c[np][0] = cl[0] + hl * (cl[1] + hl * (cl[2] + hl * cl[3]));
+  T.c[np][1] = cl[1] + hl * (2.0 * cl[2] + hl * 3.0 * cl[3]);
+  T.c[np][2] = T.c[np][3] = 0.0;
+  T.n_pieces = np + 1;
+  for (int p = T.n_pieces; p < GSM_MAX_PIECES; p++) {
+    T.brk[p] = T.org[p] = S.b1;
+    for (int d = 0; d < 4; d++) T.c[p][d] = 0.0;
   }
-  double rdel[3], ldel[3];
-  for (int i = 0; i < outer; i++) {
-    rdel[i] = T.knots[c.curs + i] - x;
-    ldel[i] = x - T.knots[c.curs - (i + 1)];
-  }
-  while (outer--)
-    for (apt = 0, lpt = outer, rpt = 0, inner = outer + 1; inner--; lpt--, rpt++, apt++)
-      a[apt] = (a[apt + 1] * ldel[lpt] + a[apt] * rdel[rpt]) / (rdel[rpt] + ldel[lpt]);
-  return a[0];
-}
-
-// SplineBasis::eval (splines.cpp:98-118): all ncoef basis values (or derivatives) at x
-MSIM_HD void spline_eval(const GsmTerm &T, double x, int ders, double val[GSM_MAX_COEF]) {
-  for (int i = 0; i < T.ncoef; i++) val[i] = 0.0;
-  SplineCursor c = spline_set_cursor(T, x);
-  int io = c.curs - 4;
-  if (io < 0 || io > T.nknots) return;
-  if (ders > 0) {
-    for (int i = 0; i < 4; i++) {
-      double a[4] = {0.0, 0.0, 0.0, 0.0};
-      a[i] = 1.0;
-      val[i + io] = spline_slow_evaluate(T, c, x, ders, a);
-    }
-  } else {
-    double b[4];
-    spline_basis_funcs(T, c.curs, x, b);
-    for (int i = 0; i < 4; i++) val[i + io] = b[i];
-  }
-}
-
-// bs::eval for x inside the boundary knots (splines.cpp:163-165): drop the first column unless intercept
-MSIM_HD void bs_eval_inside(const GsmTerm &T, double x, int ders, double v[GSM_MAX_COEF]) {
-  double val[GSM_MAX_COEF];
-  spline_eval(T, x, ders, val);
-  for (int i = 0; i < T.df; i++) v[i] = val[i + 1 - T.intercept];
-}
-
-// ns::eval(x, 0) . gamma   (splines.cpp:204-219 and gsm.cpp:19)
-MSIM_HD double ns_dot_gamma(const GsmTerm &T, double x) {
-  double s = 0.0;
-  if (x < T.b0) {
-    for (int r = 0; r < T.n_ns; r++) s += (T.tl0[r] + (x - T.b0) * T.tl1[r]) * T.gamma[r];
-  } else if (x > T.b1) {
-    for (int r = 0; r < T.n_ns; r++) s += (T.tr0[r] + (x - T.b1) * T.tr1[r]) * T.gamma[r];
-  } else {
-    double v[GSM_MAX_COEF];
-    bs_eval_inside(T, x, 0, v);
-    for (int r = 0; r < T.n_ns; r++) {
-      double e = 0.0;
-      for (int j = 0; j < T.df; j++) e += T.q[r][j] * v[j];  // q_matrix * bs::eval
-      s += e * T.gamma[r];
-    }
-  }
-  return s;
+  return true;
 }
 
 // ---- gsm ------------------------------------------------------------------
 
-MSIM_HD double gsm_link(double S) { return log(-log(S)); }          // PH, gsm.cpp:8-10
-MSIM_HD double gsm_linkinv(double eta) { return exp(-exp(eta)); }   // gsm.cpp:11-13
+MSIM_HD double gsm_link(double S) { return fm_log(-fm_log(S)); }    // PH, gsm.cpp:8-10 (exp / log: fastmath.cuh)
+MSIM_HD double gsm_linkinv(double eta) { return fm_exp(-fm_exp(eta)); }   // gsm.cpp:11-13
 
 MSIM_HD double gsm_eta(const GsmModel &M, int index, double y, bool baseline0) {  // gsm.cpp:15-28
   double eta = baseline0 ? M.etap0[index] : M.etap[index];
@@ -306,29 +308,6 @@ MSIM_HD double gsm_randU0(const GsmModel &M, double u, int index, double scale) 
   f.target0 = gsm_link(u * gsm_linkinv(gsm_eta(M, index, y0, true)) / gsm_linkinv(gsm_eta(M, index, y0, false)));
   double root = zeroin2(ymin, ymax, f, 1.0e-8, 100);
   return M.log_time ? exp(root) : root;
-}
-
-// ns::ns (splines.cpp:194-203): the linear-extrapolation vectors, from bs::eval and its first derivative at the
-// boundary knots.  Host only (model set-up).
-inline void gsm_term_finish(GsmTerm &T) {
-  T.df = T.intercept + 3 + T.n_interior;
-  T.nknots = T.n_interior + 8;
-  T.ncoef = T.nknots - 4;
-  double v0[GSM_MAX_COEF], v1[GSM_MAX_COEF];
-  for (int side = 0; side < 2; side++) {
-    double xb = side ? T.b1 : T.b0;
-    bs_eval_inside(T, xb, 0, v0);
-    bs_eval_inside(T, xb, 1, v1);
-    for (int r = 0; r < T.n_ns; r++) {
-      double e0 = 0, e1 = 0;
-      for (int j = 0; j < T.df; j++) {
-        e0 += T.q[r][j] * v0[j];
-        e1 += T.q[r][j] * v1[j];
-      }
-      (side ? T.tr0 : T.tl0)[r] = e0;
-      (side ? T.tr1 : T.tl1)[r] = e1;
-    }
-  }
 }
 
 }  // namespace msim

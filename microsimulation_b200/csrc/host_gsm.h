@@ -32,28 +32,25 @@ int gsm_upload(const msim_gsm *m) {
     GsmTerm &T = M.terms[i];
     if (t.n_knots < 1 || t.n_knots > GSM_MAX_INTERIOR || !t.gamma || !t.knots || !t.q_const || !t.x)
       return fail(MSIM_ERR_ARG, "gsm term: 1..12 interior knots and non-null vectors are required");
-    T.n_interior = t.n_knots;
-    T.intercept = t.intercept != 0;
-    T.cure = t.cure;
-    T.b0 = t.Boundary_knots[0];
-    T.b1 = t.Boundary_knots[1];
-    T.df = T.intercept + 3 + T.n_interior;
-    T.nknots = T.n_interior + 8;
-    T.ncoef = T.nknots - 4;
-    for (int k = 0; k < 4; k++) {
-      T.knots[k] = T.b0;
-      T.knots[T.nknots - k - 1] = T.b1;
-    }
-    for (int k = 0; k < T.n_interior; k++) T.knots[k + 4] = t.knots[k];
     // q_matrix = q_const, transposed if it has fewer columns than rows (splines.cpp:197-198)
+    const int df = (t.intercept != 0) + 3 + t.n_knots;
     const bool tr = t.q_cols < t.q_rows;
     const int rows = tr ? t.q_cols : t.q_rows, cols = tr ? t.q_rows : t.q_cols;
-    if (rows != t.n_gamma || cols != T.df || rows > GSM_MAX_NS) return fail(MSIM_ERR_ARG, "gsm term: q_const does not match gamma / knots");
-    T.n_ns = rows;
+    if (rows != t.n_gamma || cols != df || rows > GSM_MAX_NS) return fail(MSIM_ERR_ARG, "gsm term: q_const does not match gamma / knots");
+    std::vector<double> q((size_t)rows * cols);
     for (int r = 0; r < rows; r++)
-      for (int c = 0; c < cols; c++) T.q[r][c] = tr ? t.q_const[c * t.q_cols + r] : t.q_const[r * t.q_cols + c];
-    for (int r = 0; r < rows; r++) T.gamma[r] = t.gamma[r];
-    gsm_term_finish(T);
+      for (int c = 0; c < cols; c++) q[(size_t)r * cols + c] = tr ? t.q_const[c * t.q_cols + r] : t.q_const[r * t.q_cols + c];
+    GsmTermSpec spec;
+    spec.n_interior = t.n_knots;
+    spec.intercept = t.intercept != 0;
+    spec.n_ns = rows;
+    spec.b0 = t.Boundary_knots[0];
+    spec.b1 = t.Boundary_knots[1];
+    spec.interior = t.knots;
+    spec.q = q.data();
+    spec.gamma = t.gamma;
+    // the term as polynomials per knot interval, projection and coefficients folded in (gsm.cuh)
+    if (!gsm_term_build(T, spec)) return fail(MSIM_ERR_ARG, "gsm term: interior knots must ascend strictly inside the boundary knots");
     memcpy(&data[(2 + (size_t)i) * ni], t.x, sizeof(double) * ni);
   }
   if ((rc = ensure(g.gsm_data, sizeof(double) * data.size()))) return rc;

@@ -774,26 +774,15 @@ int emu_gsm(const msim_gsm *m, int mode, int64_t n, const double *u, const doubl
   for (int i = 0; i < m->n_terms; i++) {
     const msim_gsm_term &t = m->terms[i];
     GsmTerm &T = M.terms[i];
-    T.n_interior = t.n_knots;
-    T.intercept = t.intercept != 0;
-    T.cure = t.cure;
-    T.b0 = t.Boundary_knots[0];
-    T.b1 = t.Boundary_knots[1];
-    T.df = T.intercept + 3 + T.n_interior;
-    T.nknots = T.n_interior + 8;
-    T.ncoef = T.nknots - 4;
-    for (int k = 0; k < 4; k++) {
-      T.knots[k] = T.b0;
-      T.knots[T.nknots - k - 1] = T.b1;
-    }
-    for (int k = 0; k < T.n_interior; k++) T.knots[k + 4] = t.knots[k];
+    const int df = (t.intercept != 0) + 3 + t.n_knots;
     const bool tr = t.q_cols < t.q_rows;
     const int rows = tr ? t.q_cols : t.q_rows, cols = tr ? t.q_rows : t.q_cols;
-    T.n_ns = rows;
+    if (cols != df) return -3;
+    std::vector<double> q((size_t)rows * cols);
     for (int r = 0; r < rows; r++)
-      for (int c = 0; c < cols; c++) T.q[r][c] = tr ? t.q_const[c * t.q_cols + r] : t.q_const[r * t.q_cols + c];
-    for (int r = 0; r < rows; r++) T.gamma[r] = t.gamma[r];
-    gsm_term_finish(T);
+      for (int c = 0; c < cols; c++) q[(size_t)r * cols + c] = tr ? t.q_const[c * t.q_cols + r] : t.q_const[r * t.q_cols + c];
+    GsmTermSpec spec = {t.n_knots, t.intercept != 0, rows, t.Boundary_knots[0], t.Boundary_knots[1], t.knots, q.data(), t.gamma};
+    if (!gsm_term_build(T, spec)) return -3;
     M.x[i] = t.x;
   }
   for (int64_t i = 0; i < n; i++) {

@@ -501,8 +501,9 @@ def test_cost_report_add_vs_oracle(msim, oracle, rate, start_age, part):
     rng = np.random.RandomState(7)
     n = 50000
     state = rng.randint(0, 5, n).astype(np.int32)
-    time = np.round(rng.uniform(0, 110, n), 3)
-    time[:100] = np.arange(100)           # exactly on partition points
+    # (times below the partition's first point have no bin in the reference: lower_bound() returns end(), :1270)
+    time = np.round(rng.uniform(part[0], 110, n), 3)
+    time[:100] = part[0] + part[2] * np.arange(100) % (part[1] - part[0])   # exactly on partition points
     cost = np.round(rng.uniform(0, 2e4, n), 2)
     cost[100:120] = 0.0
     got, cur = api.cost_report(state, time, cost, rate, start_age, part, n_state=8)

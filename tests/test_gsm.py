@@ -74,7 +74,10 @@ def _emu_call(emu, model, mode, u, tentry=None, index=None, scale=10.0):
 
 @pytest.mark.parametrize("intercept", [0, 1])
 def test_device_functions_on_host_vs_oracle(oracle, emu, intercept):
-    """gsm.cuh compiled for the host against the restated reference: same statements, same libm -> same roots."""
+    """gsm.cuh compiled for the host against the restated reference: the term expanded into per-interval cubics on the
+    host (gsm_term_build) against the reference's basis + projection evaluation — eta to rounding, roots to the
+    solver's tolerance (Brent stops within 1e-8 on the log-time scale; a last-bit difference in a function value can
+    end a search one step earlier or later)."""
     model, _, _, B = make_model(oracle, intercept=intercept)
     m = model.cstruct()
     rs = np.random.RandomState(11)
@@ -82,12 +85,14 @@ def test_device_functions_on_host_vs_oracle(oracle, emu, intercept):
     u = rs.uniform(1e-6, 1 - 1e-6, n)
     index = rs.randint(0, 3, n).astype(np.int32)
     y = rs.uniform(B[0] - 2, B[1] + 2, n)
-    np.testing.assert_allclose(_emu_call(emu, model, 2, y, index=index), oracle.gsm_eta(m, y, index), rtol=1e-13, atol=1e-13)
-    np.testing.assert_allclose(_emu_call(emu, model, 0, u, index=index), oracle.gsm_randU(m, u, index=index), rtol=1e-10)
+    y = np.r_[y, B, B[0] - 1e-9, B[1] + 1e-9, np.asarray(model.terms[0]["knots"], dtype=float)]  # at and around every breakpoint
+    index_y = np.r_[index, np.zeros(len(y) - n, dtype=np.int32)].astype(np.int32)
+    np.testing.assert_allclose(_emu_call(emu, model, 2, y, index=index_y), oracle.gsm_eta(m, y, index_y), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(np.log(_emu_call(emu, model, 0, u, index=index)), np.log(oracle.gsm_randU(m, u, index=index)), atol=2e-8)
     te = rs.uniform(0.2, 10, n)
-    np.testing.assert_allclose(_emu_call(emu, model, 0, u, tentry=te, index=index),
-                               oracle.gsm_randU(m, u, tentry=te, index=index), rtol=1e-10)
-    np.testing.assert_allclose(_emu_call(emu, model, 1, u, index=index), oracle.gsm_randU0(m, u, index=index), rtol=1e-10)
+    np.testing.assert_allclose(np.log(_emu_call(emu, model, 0, u, tentry=te, index=index)),
+                               np.log(oracle.gsm_randU(m, u, tentry=te, index=index)), atol=2e-8)
+    np.testing.assert_allclose(np.log(_emu_call(emu, model, 1, u, index=index)), np.log(oracle.gsm_randU0(m, u, index=index)), atol=2e-8)
 
 
 @pytest.mark.gpu
@@ -103,7 +108,6 @@ def test_gsm_on_gpu_vs_oracle(msim, oracle):
     # Brent stops within tol = 1e-8 of the root on the log-time scale; device libm may end a step earlier or later
     t_gpu, t_ref = model.randU(u, index=index), oracle.gsm_randU(m, u, index=index)
     np.testing.assert_allclose(np.log(t_gpu), np.log(t_ref), atol=2e-8)
-    assert (t_gpu == t_ref).mean() > 0.5
     te = rs.uniform(0.2, 10, n)
     np.testing.assert_allclose(np.log(model.randU(u, tentry=te, index=index)), np.log(oracle.gsm_randU(m, u, tentry=te, index=index)),
                                atol=2e-8)
