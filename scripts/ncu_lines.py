@@ -1,7 +1,13 @@
 #!/usr/bin/env python
 """Per-source-line instruction counts for one kernel of an .ncu-rep.
 
-  python scripts/ncu_lines.py REP KERNEL_SUBSTRING [TOP_N] [LIB.so]
+  python scripts/ncu_lines.py REP KERNEL_SUBSTRING [TOP_N] [LIB.so] [MANGLED_SUBSTRING]
+
+KERNEL_SUBSTRING selects the launch in the report (demangled name); MANGLED_SUBSTRING (e.g. ILj255E for the <255>
+instantiation; default: KERNEL_SUBSTRING) selects the ONE function section of the cubin whose line table is used — with
+several instantiations of a template in the library a loose match joins the counts with the wrong function's lines.
+An instruction is attributed to the innermost frame of its inline chain that lies in this repository's sources (CUDA's
+own headers — shuffle and atomic wrappers — are skipped), so intrinsics count for the line that calls them.
 
 ncu's SASS page gives executed warp instructions / thread instructions / stall samples per instruction;
 nvdisasm --print-line-info-inline on the cubin of the SAME build gives file:line per instruction (needs
@@ -10,7 +16,8 @@ nvdisasm --print-line-info-inline on the cubin of the SAME build gives file:line
 import csv, os, re, subprocess, sys, tempfile
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-lib = sys.argv[4] if len(sys.argv) > 4 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "microsimulation_b200", "libmsim_b200.so")
+mangled = sys.argv[5] if len(sys.argv) > 5 else kern
+lib = sys.argv[4] if len(sys.argv) > 4 and sys.argv[4] else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "microsimulation_b200", "libmsim_b200.so")
 
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
@@ -38,19 +45,27 @@ tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
 cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "--print-line-info-inline", cubin], capture_output=True, text=True).stdout
-lines, infn, where, in_chain = {}, False, None, False
+OURS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "microsimulation_b200", "csrc")
+lines, infn, where, in_chain, matched = {}, False, None, False, []
 for ln in dis.splitlines():
     m = re.match(r"\s*\.section\s+\.text\.(\S+),", ln)
     if m:
-        infn = kern in m.group(1)
+        infn = mangled in m.group(1)
+        if infn:
+            matched.append(m.group(1))
         where, in_chain = None, False
         continue
     if not infn:
         continue
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)(.*)', ln)
     if m:
-        if not in_chain:  # a run of //## lines is one inline chain, innermost location first
-            where = (m.group(1).split("/")[-1], int(m.group(2)))
+        # a run of //## lines is one inline chain, innermost location first: take the innermost frame in our sources
+        here = (m.group(1).split("/")[-1], int(m.group(2)))
+        ours = os.path.exists(os.path.join(OURS, here[0]))
+        if not in_chain:
+            where, where_ours = here, ours
+        elif not where_ours and ours:
+            where, where_ours = here, True
         in_chain = True
         continue
     in_chain = False
@@ -58,6 +73,8 @@ for ln in dis.splitlines():
     if m:
         lines[int(m.group(1), 16)] = where
 
+if len(set(matched)) != 1:
+    sys.exit("the mangled substring %r matches %d function sections: %s" % (mangled, len(set(matched)), sorted(set(matched))[:6]))
 agg, tot, tots = {}, 0.0, 0.0
 for d in recs:
     off = int(d["Address"], 16) - base
