@@ -115,7 +115,17 @@ static SEXP mt_seed_var(void) {
   return s;
 }
 static void mt_in(void) { check(msim_mt_set_state((const uint32_t *)(INTEGER(mt_seed_var()) + 1))); }
-static void mt_out(void) { check(msim_mt_get_state((uint32_t *)(INTEGER(mt_seed_var()) + 1))); }
+/* PutRNGstate(): a FRESH .Random.seed is installed (the old vector may be shared, e.g. after s <- .Random.seed, and
+ * must not change under its other owners).  The state is fetched by the caller first, so that nothing of the library's
+ * is allocated when an error is raised. */
+static void mt_store(const uint32_t st[625]) {
+  SEXP old = mt_seed_var();
+  SEXP s = PROTECT(Rf_allocVector(INTSXP, 626));
+  INTEGER(s)[0] = INTEGER(old)[0];
+  memcpy(INTEGER(s) + 1, st, 625 * sizeof(uint32_t));
+  Rf_defineVar(Rf_install(".Random.seed"), s, R_GlobalEnv);
+  UNPROTECT(1);
+}
 
 SEXP callPersonSimulation(SEXP inseed, SEXP parms) {
   if (TYPEOF(inseed) != INTSXP || Rf_xlength(inseed) < 6) Rf_error("microsimulation: inseed must be six integers");
@@ -136,8 +146,12 @@ SEXP callSimplePerson(SEXP parms) {
   ensure_device();
   mt_in();
   msim_table t;
+  uint32_t st[625];
   check(msim_callSimplePerson(n, &t));
-  mt_out();
+  const int rc = msim_mt_get_state(st);
+  if (rc) msim_table_free(&t); /* before the R error unwinds past it */
+  check(rc);
+  mt_store(st);
   SEXP out = PROTECT(table_to_list(&t, 0));
   msim_table_free(&t);
   UNPROTECT(1);
@@ -149,8 +163,12 @@ SEXP callSimplePerson2(SEXP parms) {
   ensure_device();
   mt_in();
   msim_report r;
+  uint32_t st[625];
   check(msim_callSimplePerson2(n, &r));
-  mt_out();
+  const int rc = msim_mt_get_state(st);
+  if (rc) msim_report_free(&r);
+  check(rc);
+  mt_store(st);
   return report_to_list(&r);
 }
 
@@ -160,8 +178,12 @@ SEXP callIllnessDeath(SEXP parms) {
   ensure_device();
   mt_in();
   msim_report r;
+  uint32_t st[625];
   check(msim_callIllnessDeath(n, cure, zsd, &r));
-  mt_out();
+  const int rc = msim_mt_get_state(st);
+  if (rc) msim_report_free(&r);
+  check(rc);
+  mt_store(st);
   return report_to_list(&r);
 }
 

@@ -48,6 +48,28 @@ int sick_launch(SickParams &p, int64_t n, bool substreams, const HostStream &hs,
     CK(cudaGetLastError());
     g.launches += 3;
   } else {
+    // A shard that does not start at person 0 inherits the report's utility and cost from the persons before it
+    // (the reference never resets them between persons): the last set_uc() code of persons [0, first_person), found
+    // by running the code pass backwards from first_person in windows until one holds a non-zero code.
+    int code0 = 0;
+    for (int64_t hi_p = first_person, w = 256; hi_p > 0 && code0 == 0; w *= 16) {
+      const int64_t lo_p = std::max<int64_t>(0, hi_p - w), cnt = hi_p - lo_p;
+      SickParams q = p;
+      q.n = cnt;
+      q.first_person = lo_p;
+      if ((rc = ensure(g.aux, (size_t)cnt))) return rc;
+      q.code_out = (unsigned char *)g.aux.p;
+      const int wgrid = (int)std::max<int64_t>(1, std::min<int64_t>((cnt + BLOCK - 1) / BLOCK, grid));
+      stream_start(hs.Cg.s, lo_p, (int64_t)wgrid * BLOCK, &q.st);
+      sick_code_kernel<ORDERED><<<wgrid, BLOCK, 0, g.stream>>>(q);
+      CK(cudaGetLastError());
+      g.launches++;
+      std::vector<unsigned char> codes((size_t)cnt);
+      CK(cudaMemcpyAsync(codes.data(), g.aux.p, (size_t)cnt, cudaMemcpyDeviceToHost, g.stream));
+      CK(cudaStreamSynchronize(g.stream));
+      for (int64_t k = cnt - 1; k >= 0 && code0 == 0; k--) code0 = codes[(size_t)k];
+      hi_p = lo_p;
+    }
     stream_start(hs.Cg.s, first_person, (int64_t)grid * BLOCK, &p.st);
     sick_code_kernel<ORDERED><<<grid, BLOCK, 0, g.stream>>>(p);
     CK(cudaGetLastError());
@@ -56,7 +78,7 @@ int sick_launch(SickParams &p, int64_t n, bool substreams, const HostStream &hs,
       if ((rc = ensure(g.carry_tiles, tiles))) return rc;
       carry_tile_kernel<<<tiles, 256, 0, g.stream>>>(p.code_out, n, (unsigned char *)g.carry_tiles.p);
       CK(cudaGetLastError());
-      carry_apply_kernel<<<tiles, 256, 0, g.stream>>>(p.code_out, n, 0, (const unsigned char *)g.carry_tiles.p,
+      carry_apply_kernel<<<tiles, 256, 0, g.stream>>>(p.code_out, n, code0, (const unsigned char *)g.carry_tiles.p,
                                                       (unsigned char *)g.code_in.p);
       CK(cudaGetLastError());
       g.launches++;

@@ -554,7 +554,25 @@ void run_sick_sicker(int64_t n, const SickSickerParam *param, bool indivp, bool 
     rlite::set_user_unif_rand(user_unif_rand);
     rng = new Rng();
     rng->set();
-    if (first_person > 0) rng->AdvanceSubstream(0, (int32_t)first_person);
+    // A shard that starts at person first_person > 0 must begin with the utility and cost the persons before it left
+    // in the report (see below): the 256 persons before the shard are simulated first (one of them has set them with
+    // probability 1 - 1e-980), then the tables are emptied and the report's utility and cost kept.
+    const int64_t warm = first_person < 256 ? first_person : 256;
+    if (first_person - warm > 0) rng->AdvanceSubstream(0, (int32_t)(first_person - warm));
+    if (warm > 0) {
+      Report scratch((int)warm, true);
+      scratch.setPartition(0.0, 31.0, param->partitionBy);
+      scratch.setDiscountRate(param->discountRate);
+      SickSicker before(param, &scratch);
+      for (int64_t i = 0; i < warm; i++) {
+        rng->nextSubstream();
+        Sim::create_process(&before);
+        Sim::run_simulation();
+        Sim::clear();
+      }
+      report.setUtility(scratch.utility);
+      report.setCost(scratch.cost);
+    }
   }
   // NB the reference never resets utility/cost between persons: the values
   // set by the previous person's last transition carry into the next

@@ -36,6 +36,7 @@ const char *R_CHAR(SEXP x);
 #define CHAR(x) R_CHAR(x)
 SEXP Rf_install(const char *name);
 SEXP Rf_findVar(SEXP symbol, SEXP env);
+void Rf_defineVar(SEXP symbol, SEXP value, SEXP env);
 SEXP Rf_setAttrib(SEXP x, SEXP name, SEXP value);
 SEXP Rf_getAttrib(SEXP x, SEXP name);
 int Rf_asInteger(SEXP x);

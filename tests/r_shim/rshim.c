@@ -148,6 +148,10 @@ SEXP Rf_findVar(SEXP symbol, SEXP env) {
   SEXP v = attr_get(env, symbol);
   return v ? v : R_UnboundValue;
 }
+void Rf_defineVar(SEXP symbol, SEXP value, SEXP env) {
+  if (env != R_GlobalEnv) Rf_error("shim: only the global environment exists");
+  attr_set(env, symbol, value);
+}
 SEXP Rf_setAttrib(SEXP x, SEXP name, SEXP value) {
   if (x == R_NilValue) Rf_error("shim: attempt to set an attribute on NULL");
   if (name == R_NamesSymbol && (value->type != STRSXP || value->n != x->n)) Rf_error("shim: 'names' must be a character vector of the object's length");

@@ -521,6 +521,33 @@ def test_cost_report_add_vs_oracle(msim, oracle, rate, start_age, part):
         api.cost_report(np.array([9], dtype=np.int32), [1.0], [1.0], n_state=8)
 
 
+def test_sick_sicker_shards_add_up_to_the_single_run(msim):
+    """first_person is the sharding knob of the substream regime (include/msim.h): the report's utility and cost
+    carry over from one person to the next in the reference (README.org:252-281), so a shard starts with what the
+    persons BEFORE it left — two shards must give exactly the single run's per-person values and, added, its tables."""
+    import microsimulation_b200.api as api
+    par = api.sick_sicker_param(True)
+    n, cut = 40000, 17123
+    api.set_user_random_seed(12345)
+    whole = api.callSim(n, par, substreams=True, first_person=0)
+    api.set_user_random_seed(12345)
+    a = api.callSim(cut, par, substreams=True, first_person=0)
+    api.set_user_random_seed(12345)
+    b = api.callSim(n - cut, par, substreams=True, first_person=cut)
+    for col in ("utilities", "costs"):
+        assert np.array_equal(np.r_[a["indiv"][col], b["indiv"][col]], whole["indiv"][col]), col
+    for tb, val in (("pt", "pt"), ("ut", "utility"), ("costs", "cost"), ("events", "number"), ("prev", "number")):
+        keys = [k for k in whole[tb] if k != val]
+        acc = {}
+        for part in (a, b):
+            for i in range(len(part[tb][val])):
+                kt = tuple(part[tb][k][i] for k in keys)
+                acc[kt] = acc.get(kt, 0.0) + part[tb][val][i]
+        got = np.array([acc[tuple(whole[tb][k][i] for k in keys)] for i in range(len(whole[tb][val]))])
+        assert len(acc) == len(whole[tb][val]), tb
+        np.testing.assert_allclose(got, whole[tb][val], rtol=1e-12, err_msg=tb)
+
+
 @pytest.mark.parametrize("substreams", [False, True])
 def test_sick_sicker_event_queues_agree(msim, oracle, substreams):
     """Default (small ordered array, cancelled actions removed), heap.h's binary heap with lingering cancelled entries,
