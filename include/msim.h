@@ -250,9 +250,26 @@ int msim_gsm_eta(const msim_gsm *model, int64_t n, const double *y, const int32_
 #define MSIM_OUT_ROWLOG 1u   /* life-history rows */
 #define MSIM_OUT_REPORT 2u   /* EventReport attached to every handled event */
 #define MSIM_OUT_COUNTS 4u   /* per-kind event counts + sum of end times */
+#define MSIM_OUT_INDIV 8u    /* with MSIM_OUT_REPORT: every individual's discounted total (EventReport::individualReset) */
 
-/* Dense report geometry (states x events x age bins over the partition
- * {0,1,..,100,1e6} used by every built model). */
+/* The EventReport attached to person-r runs (and to plugin models): what its constructor and setPartition take
+ * (inst/include/microsimulation.h:873-904).
+ *   setPartition(start, finish, delta, maxTime): points start, start+delta, ... <= finish (by repeated addition, as the
+ *     reference builds them), then maxTime; at most 127 points
+ *   startReportAge: an individual's discounted total (addBrief / individualReset, :905-932) counts from this age
+ *   outputUtilities = 0: wrap() has no "ut" table
+ * NULL restores the default: the built models' partition {0, 1, ..., 100, 1e6} (illness-death.cpp:81-85),
+ * startReportAge 0, utilities on.  Times below `start` have no bin in the reference (lower_bound returns end());
+ * here they are booked to the first bin. */
+typedef struct msim_report_options {
+  double start, finish, delta, max_time;
+  double start_report_age;
+  int32_t output_utilities;
+} msim_report_options;
+int msim_set_report_options(const msim_report_options *opt);
+
+/* Dense report geometry (states x events x age bins; the partition {0,1,..,100,1e6} of every built model unless
+ * msim_set_report_options chose another). */
 #define MSIM_N_COUNTS 9 /* per-kind event counts [0..7] and sum(endTime) [8] */
 
 typedef struct msim_dense_dims {
@@ -295,6 +312,11 @@ int msim_timer_stop(float *ms);
 /* Copy results of the last run to the host. */
 int msim_person_fetch_rowlog(msim_table *out);
 int msim_person_fetch_counts(double counts[9]);
+/* After a run with MSIM_OUT_REPORT | MSIM_OUT_INDIV: out[i] = individual i's discounted total at individualReset
+ * (wrap_indiv(); NaN = NA_REAL where the individual's last event came before startReportAge), and means[0..6] = what
+ * wrap_means() tabulates (the reference's Means class, :468-496): n, mean, var, sd, se, sum, sumsq over the
+ * individuals that count, summed in person order in long double as the reference does.  Either pointer may be NULL. */
+int msim_person_fetch_indiv(double *out, int64_t n, double means[7]);
 /* Accumulator vector (e.g. after an all-reduce done by the caller on the
  * device buffer) -> sparse report tables in the reference's layout.  Pure host
  * code: needs no device. */

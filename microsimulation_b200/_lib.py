@@ -6,7 +6,7 @@ import numpy as np
 
 from . import build as _build
 
-MSIM_OUT_ROWLOG, MSIM_OUT_REPORT, MSIM_OUT_COUNTS = 1, 2, 4
+MSIM_OUT_ROWLOG, MSIM_OUT_REPORT, MSIM_OUT_COUNTS, MSIM_OUT_INDIV = 1, 2, 4, 8
 
 ERRORS = {-1: "MSIM_ERR_NO_DEVICE", -2: "MSIM_ERR_CUDA", -3: "MSIM_ERR_ARG", -4: "MSIM_ERR_HEAP", -5: "MSIM_ERR_SEED",
           -6: "MSIM_ERR_STREAM", -7: "MSIM_ERR_STATE", -8: "MSIM_ERR_MODEL"}
@@ -59,6 +59,11 @@ class DenseDims(C.Structure):
     _fields_ = [("n_state", C.c_int32), ("n_event", C.c_int32), ("n_bin", C.c_int32), ("n_doubles", C.c_int64)]
 
 
+class ReportOptions(C.Structure):
+    _fields_ = [("start", C.c_double), ("finish", C.c_double), ("delta", C.c_double), ("max_time", C.c_double),
+                ("start_report_age", C.c_double), ("output_utilities", C.c_int32)]
+
+
 class PersonShard(C.Structure):
     _fields_ = [("seed", C.c_double * 6), ("first_person", C.c_int64), ("n", C.c_int64), ("outputs", C.c_uint32),
                 ("discount_rate", C.c_double)]
@@ -72,7 +77,7 @@ class PersonDeviceResult(C.Structure):
 # every symbol include/msim.h declares (tests check that the library exports them all)
 SYMBOLS = [
     "msim_table_free", "msim_report_free", "msim_last_error", "msim_version", "msim_init", "msim_shutdown",
-    "msim_launch_count", "msim_set_stream", "msim_set_person_schedule", "msim_set_mt_parallel", "msim_set_rowlog_plan", "msim_r_create_current_stream", "msim_r_remove_current_stream",
+    "msim_launch_count", "msim_set_stream", "msim_set_person_schedule", "msim_set_mt_parallel", "msim_set_rowlog_plan", "msim_set_report_options", "msim_person_fetch_indiv", "msim_r_create_current_stream", "msim_r_remove_current_stream",
     "msim_r_set_user_random_seed", "msim_r_get_user_random_seed", "msim_r_next_rng_substream",
     "msim_r_rng_advance_substream", "msim_next_rng_stream", "msim_user_unif_rand", "msim_mt_set_state", "msim_mt_get_state", "msim_mt_set_seed",
     "msim_callPersonSimulation", "msim_callSimplePerson", "msim_callSimplePerson2", "msim_callIllnessDeath",

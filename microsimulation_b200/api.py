@@ -11,8 +11,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (MSIM_OUT_COUNTS, MSIM_OUT_REPORT, MSIM_OUT_ROWLOG, Calibration, DenseDims, PersonDeviceResult,
-                   PersonShard, Report, Table, check, load)
+from ._lib import (MSIM_OUT_COUNTS, MSIM_OUT_INDIV, MSIM_OUT_REPORT, MSIM_OUT_ROWLOG, Calibration, DenseDims,
+                   PersonDeviceResult, PersonShard, Report, ReportOptions, Table, check, load)
 
 _stream_created = False
 
@@ -414,8 +414,33 @@ def dense_to_report(dense, dims, discount_rate=0.0):
     return d
 
 
-def person_report(seed, first_person, n, discount_rate=0.0):
-    """Single-GPU person-r run with the EventReport attached; returns (report tables, counts)."""
-    res = person_run_device(seed, first_person, n, MSIM_OUT_REPORT | MSIM_OUT_COUNTS, discount_rate)
+def set_report_options(start=None, finish=100.0, delta=1.0, max_time=1.0e100, start_report_age=0.0, output_utilities=True):
+    """The EventReport attached to person-r (and plugin) runs: setPartition(start, finish, delta, maxTime), the
+    constructor's startReportAge and outputUtilities (microsimulation.h:873-904).  No arguments: the default (the built
+    models' partition {0, 1, ..., 100, 1e6}, startReportAge 0, utilities on)."""
+    if start is None:
+        check(load().msim_set_report_options(None))
+        return
+    o = ReportOptions(float(start), float(finish), float(delta), float(max_time), float(start_report_age), int(bool(output_utilities)))
+    check(load().msim_set_report_options(C.byref(o)))
+
+
+def person_fetch_indiv(n):
+    """wrap_indiv() and wrap_means() after a run with MSIM_OUT_REPORT | MSIM_OUT_INDIV: (vector of n totals, NaN = NA;
+    dict n / mean / var / sd / se / sum / sumsq)."""
+    out = np.empty(int(n))
+    means = (C.c_double * 7)()
+    check(load().msim_person_fetch_indiv(out.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(int(n)), means))
+    return out, dict(zip(("n", "mean", "var", "sd", "se", "sum", "sumsq"), means[:]))
+
+
+def person_report(seed, first_person, n, discount_rate=0.0, indiv=False):
+    """Single-GPU person-r run with the EventReport attached; returns (report tables, counts) and, with indiv, the
+    individuals' discounted totals and their means as well."""
+    outs = MSIM_OUT_REPORT | MSIM_OUT_COUNTS | (MSIM_OUT_INDIV if indiv else 0)
+    res = person_run_device(seed, first_person, n, outs, discount_rate)
     dense = dense_fetch(res.dims.n_doubles)
-    return dense_to_report(dense, res.dims, discount_rate), person_fetch_counts()
+    rep, counts = dense_to_report(dense, res.dims, discount_rate), person_fetch_counts()
+    if indiv:
+        return (rep, counts) + person_fetch_indiv(n)
+    return rep, counts

@@ -98,6 +98,20 @@ int msim_set_rowlog_plan(double rows_per_person, double extra_rows_per_person) {
   return MSIM_OK;
 }
 
+int msim_set_report_options(const msim_report_options *opt) {
+  if (!opt) {
+    g.have_report_opts = false;
+    return MSIM_OK;
+  }
+  ReportGeom G;
+  if (!make_report_geom_partition(&G, 1, 1, opt->start, opt->finish, opt->delta, opt->max_time, 0.0, opt->start_report_age, opt->output_utilities))
+    return fail(MSIM_ERR_ARG, "report options: the partition must ascend (delta > 0, finish >= start, maxTime > finish) and hold at most 127 points");
+  if (!(opt->start_report_age >= 0)) return fail(MSIM_ERR_ARG, "report options: startReportAge must be >= 0");
+  g.report_opts = *opt;
+  g.have_report_opts = true;
+  return MSIM_OK;
+}
+
 int msim_set_mt_parallel(int on) {
   g.mt_parallel = on != 0;
   return (on && g.inited && !g.d_mt_table) ? 1 : MSIM_OK;  // 1: asked for, but mt_jump.bin was not found
@@ -590,6 +604,35 @@ int msim_person_fetch_counts(double counts[9]) {
   if (!counts) return fail(MSIM_ERR_ARG, "null argument");
   if (!g.have_last) return fail(MSIM_ERR_STATE, "no run yet");
   CK(cudaMemcpy(counts, (const double *)g.dense.p + g.last_cells, sizeof(double) * N_COUNTS, cudaMemcpyDeviceToHost));
+  return MSIM_OK;
+}
+
+int msim_person_fetch_indiv(double *out, int64_t n, double means[7]) {
+  if (!g.have_last || !g.last_staged || (g.last_outputs & (OUT_REPORT | OUT_INDIV)) != (OUT_REPORT | OUT_INDIV))
+    return fail(MSIM_ERR_STATE, "the last run kept no individual totals (MSIM_OUT_REPORT | MSIM_OUT_INDIV)");
+  if (n != g.last_n) return fail(MSIM_ERR_ARG, "size mismatch");
+  std::vector<double> h((size_t)std::max<int64_t>(n, 1));
+  if (n > 0) CK(cudaMemcpy(h.data(), g.indiv.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+  if (out && n > 0) memcpy(out, h.data(), sizeof(double) * (size_t)n);
+  if (means) {  // Means::operator+= in person order (microsimulation.h:476-481)
+    long double sum = 0, sumsq = 0;
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < n; i++)
+      if (h[(size_t)i] == h[(size_t)i]) {
+        cnt++;
+        sum += (long double)h[(size_t)i];
+        sumsq += (long double)h[(size_t)i] * (long double)h[(size_t)i];
+      }
+    const double mean = (double)(sum / cnt);
+    const double var = (double)((long double)cnt / (cnt - 1) * (sumsq / cnt - (long double)mean * mean));
+    means[0] = (double)cnt;
+    means[1] = mean;
+    means[2] = var;
+    means[3] = sqrt(var);
+    means[4] = sqrt(var) / sqrt((double)cnt);
+    means[5] = (double)sum;
+    means[6] = (double)sumsq;
+  }
   return MSIM_OK;
 }
 

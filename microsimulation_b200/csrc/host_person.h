@@ -49,9 +49,10 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
   memset(&p, 0, sizeof p);
   p.first_person = sh->first_person;
   p.n = sh->n;
-  p.outputs = sh->outputs & 7u;
+  p.outputs = sh->outputs & 15u;
+  if ((p.outputs & OUT_INDIV) && !(p.outputs & OUT_REPORT)) return fail(MSIM_ERR_ARG, "MSIM_OUT_INDIV needs MSIM_OUT_REPORT");
   p.consts = person_r::make_consts();
-  p.geom = ages_geom(person_r::N_STATE, person_r::N_EVENT, sh->discount_rate);
+  if ((rc = person_geom(person_r::N_STATE, person_r::N_EVENT, sh->discount_rate, &p.geom))) return rc;
   if (!make_report_compact(p.geom, &person_r::REACHABLE_PAIRS[0][0], person_r::N_REACHABLE_PAIRS, &p.compact))
     return fail(MSIM_ERR_ARG, "report geometry too large for the block tables");
   size_t smem = sizeof(WarpQueues) * SWARPS;
@@ -124,6 +125,10 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
     p.ov_cap = (int)ov_cap;
   }
   g.last_ov_cap = ov_cap;
+  if (p.outputs & OUT_INDIV) {
+    if ((rc = ensure(g.indiv, sizeof(double) * (size_t)std::max<int64_t>(sh->n, 1)))) return rc;
+    p.indiv = (double *)g.indiv.p;
+  }
   if (p.outputs & OUT_REPORT) {
     // per-block slices of the FP sums (pt, ut): zeroed by their blocks, added up by the launch itself
     const size_t bytes = sizeof(double) * (size_t)grid * staged_slice_doubles(p.geom, p.compact);
@@ -171,9 +176,10 @@ int person_enqueue(const msim_person_shard *sh, int64_t capacity_override, int64
   memset(&p, 0, sizeof p);
   p.first_person = sh->first_person;
   p.n = sh->n;
+  if (sh->outputs & OUT_INDIV) return fail(MSIM_ERR_ARG, "individual totals (MSIM_OUT_INDIV) are produced by the staged schedule only");
   p.outputs = sh->outputs & 7u;
   p.consts = person_r::make_consts();
-  p.geom = ages_geom(person_r::N_STATE, person_r::N_EVENT, sh->discount_rate);
+  if ((rc = person_geom(person_r::N_STATE, person_r::N_EVENT, sh->discount_rate, &p.geom))) return rc;
   uint32_t state[6];
   seed_to_u32(sh->seed, state);
   int grid;

@@ -57,6 +57,8 @@ struct Ctx {
   int64_t want_capacity = 0;
   int64_t last_n = 0, last_first = 0;
   int last_max_rows = 0;
+  msim_report_options report_opts;   // msim_set_report_options: the EventReport attached to person-r (and plugin) runs
+  bool have_report_opts = false;
   int last_calib_sets = 0;  // parameter sets of the last calibration run (rows of calib_out)
   int last_cells = 0;  // dense report cells of the last run (0 when no report was requested)
   bool have_last = false;
@@ -239,8 +241,24 @@ inline void host_free(double *p) {
   }
 }
 
+// The geometry of the EventReport attached to a run: the built models' partition {0, 1, ..., 100, 1e6}
+// (illness-death.cpp:81-85) unless msim_set_report_options chose another.
+inline int person_geom(int n_state, int n_event, double discount_rate, ReportGeom *out) {
+  if (!g.have_report_opts) {
+    *out = ages_geom(n_state, n_event, discount_rate);
+    return MSIM_OK;
+  }
+  const msim_report_options &o = g.report_opts;
+  if (!make_report_geom_partition(out, n_state, n_event, o.start, o.finish, o.delta, o.max_time, discount_rate, o.start_report_age,
+                                  o.output_utilities))
+    return fail(MSIM_ERR_ARG, "report options: the partition must ascend (delta > 0, finish >= start, maxTime > finish) and hold at most 127 points");
+  return MSIM_OK;
+}
+
 inline ReportGeom geom_from_dims(const msim_dense_dims *dims, double discount_rate) {
-  return ages_geom(dims->n_state, dims->n_event, discount_rate);
+  ReportGeom G;
+  if (person_geom(dims->n_state, dims->n_event, discount_rate, &G) != MSIM_OK) G = ages_geom(dims->n_state, dims->n_event, discount_rate);
+  return G;
 }
 
 // `small` buffer layout (8-byte cells): [9] n_rows (u64), [10] error (int), [11] end_word (i64), [12] overflow rows (u64)

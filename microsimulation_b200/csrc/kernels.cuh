@@ -36,7 +36,7 @@ namespace msim {
 
 constexpr int BLOCK = 256;
 constexpr int WARPS = BLOCK / 32;
-constexpr unsigned OUT_ROWLOG = 1u, OUT_REPORT = 2u, OUT_COUNTS = 4u;
+constexpr unsigned OUT_ROWLOG = 1u, OUT_REPORT = 2u, OUT_COUNTS = 4u, OUT_INDIV = 8u;
 constexpr int N_COUNTS = 9;  // up to 8 per-kind counts + sum(endTime)
 
 // ---- small device helpers ------------------------------------------------

@@ -149,6 +149,7 @@ struct StagedParams {
   double *slices;  // gridDim.x slices of 2 * compact.n_states * n_bin doubles (pt, ut); every block zeroes its own
   unsigned *fold_sync;  // [groups + 1] arrival counters of the fold, zero before the first launch, left zero by every launch
   double *counts;  // N_COUNTS doubles
+  double *indiv;   // [n] every individual's discounted total at individualReset (outputs & 8), NaN below startReportAge
   int *error;
   // row log, first pass
   double *first_end;           // [n] end time of each person's first row
@@ -249,9 +250,11 @@ struct StagedEnvT {
   unsigned first_tag;
   WarpRows *wq;
   int lane;
+  double current;  // EventReport::current: the individual's discounted total so far (outputs & 8)
   __device__ __forceinline__ void begin_person() {
     report_cursor_start(*geom, cursor);
     nrows = 0;
+    current = 0.0;
   }
   __device__ __forceinline__ void row(double, double start, double end, int state, int kind) {
     if (out() & 4u) {
@@ -275,7 +278,11 @@ struct StagedEnvT {
     }
   }
   __device__ __forceinline__ void report(int state, int kind, double lhs, double rhs) {
-    if (out() & 2u) acc.add(report_cells(*geom, cursor, state, kind, lhs, rhs), geom->discount_rate != 0.0);
+    if (out() & 2u) {
+      const ReportCells c = report_cells(*geom, cursor, state, kind, lhs, rhs);
+      acc.add(c, geom->discount_rate != 0.0);
+      if (out() & 8u) current += report_brief(*geom, c, lhs, rhs);  // addBrief, microsimulation.h:929-932
+    }
   }
 };
 
@@ -288,6 +295,10 @@ __device__ __forceinline__ void staged_finish(const StagedParams &p, StagedEnv &
     p.first_end[idx] = env.first_end;
     p.first_tag[idx] = (unsigned short)(env.first_tag | ((unsigned)extra << 8) | (env.nrows > 0 ? 0x8000u : 0u));
   }
+  // EventReport::individualReset (microsimulation.h:905-916) at the end of the person's simulation: now() is the
+  // time of its last event (the cursor's), the total counts only if that is past startReportAge (else NA_REAL)
+  if ((env.out() & 10u) == 10u)
+    p.indiv[idx] = (env.cursor.t >= env.geom->start_report_age) ? env.current : __longlong_as_double(0x7ff8000000000000ll);
 }
 
 // a lane appends its person's further rows to the region of the person's chunk

@@ -51,6 +51,11 @@ struct ReportGeom {
   double part_last;
   int unit;  // 1: partition {0, 1, 2, ..., n_bin-2, part_last}: a bin index is just the integer part
   int bin0;  // the bin of time 0, where every person's first interval starts (cProcess::startTime)
+  // EventReport(discountRate, outputUtilities, size, startReportAge, indiv) (microsimulation.h:873-877): every
+  // individual's discounted total counts from startReportAge on (addBrief, :929-932); sra_gain = exp(alpha * sra)
+  double start_report_age, sra_gain;
+  int output_utilities;
+  double part[REPORT_MAX_BINS];  // the partition points (setPartition), ascending; entries >= n_bin repeat the last
   double discount_rate, alpha, inv_alpha;  // alpha = log(1 + discount_rate), inv_alpha = 1/alpha (host libm)
   // offsets (in doubles) into the dense vector; FP sums first, then counters
   int off_pt, off_ut, off_dstart, off_noedge, off_events, total;
@@ -83,13 +88,47 @@ inline ReportGeom make_report_geom(int n_state, int n_event, int n_bin, double s
     double p = (i >= n_bin - 1) ? last : start + i * delta;
     g.edge_decay[i] = (discount_rate != 0.0) ? fm_exp(-p * g.alpha) : 1.0;  // the function the events use (report_decay)
   }
+  for (int i = 0; i < REPORT_MAX_BINS; i++) g.part[i] = (i >= n_bin - 1) ? last : start + i * delta;
   g.bin0 = 0;
-  while (g.bin0 + 1 < n_bin && ((g.bin0 + 1 >= n_bin - 1) ? last : start + (g.bin0 + 1) * delta) <= 0.0) g.bin0++;
+  while (g.bin0 + 1 < n_bin && g.part[g.bin0 + 1] <= 0.0) g.bin0++;
+  g.start_report_age = 0.0;
+  g.sra_gain = 1.0;
+  g.output_utilities = 1;
   return g;
 }
 
+// EventReport::setPartition(start, finish, delta, maxTime) (microsimulation.h:879-884): the points by REPEATED
+// addition, as the reference builds them (start + i*delta can differ in the last bit), then maxTime; plus the
+// constructor's startReportAge and outputUtilities.  Returns false if the partition does not fit the tables.
+inline bool make_report_geom_partition(ReportGeom *out, int n_state, int n_event, double start, double finish, double delta,
+                                       double max_time, double discount_rate, double start_report_age, int output_utilities) {
+  if (!(delta > 0) || !(finish >= start) || !(max_time > finish)) return false;
+  double pts[REPORT_MAX_BINS];
+  int n = 0;
+  for (double t = start; t <= finish; t += delta) {
+    if (n >= REPORT_MAX_BINS - 1) return false;
+    pts[n++] = t;
+  }
+  pts[n++] = max_time;
+  ReportGeom g = make_report_geom(n_state, n_event, n, start, delta, max_time, discount_rate);
+  bool unit = (start == 0.0 && delta == 1.0);
+  for (int i = 0; i < REPORT_MAX_BINS; i++) {
+    g.part[i] = pts[i < n ? i : n - 1];
+    g.edge_decay[i] = (discount_rate != 0.0) ? fm_exp(-g.part[i] * g.alpha) : 1.0;
+  }
+  g.unit = unit ? 1 : 0;
+  g.bin0 = 0;
+  while (g.bin0 + 1 < n && g.part[g.bin0 + 1] <= 0.0) g.bin0++;
+  g.start_report_age = start_report_age;
+  g.sra_gain = (discount_rate != 0.0) ? fm_exp(start_report_age * g.alpha) : 1.0;
+  g.output_utilities = output_utilities ? 1 : 0;
+  *out = g;
+  return true;
+}
+
 MSIM_HD double report_part(const ReportGeom &g, int i) {
-  return (i >= g.n_bin - 1) ? g.part_last : g.part_start + i * g.part_delta;
+  if (g.unit) return (i >= g.n_bin - 1) ? g.part_last : (double)i;  // {0, 1, ..., n_bin-2, last}
+  return g.part[i];
 }
 
 // index of the largest partition point <= x (set<greater>::lower_bound, :937-938)
@@ -101,8 +140,8 @@ MSIM_HD int report_bin(const ReportGeom &g, double x) {
   }
   double y = (x - g.part_start) * g.part_inv_delta;
   int i = (y > 0.0) ? ((y < (double)(nb - 2)) ? (int)y : nb - 2) : 0;
-  while (i + 1 < nb && report_part(g, i + 1) <= x) i++;
-  while (i > 0 && report_part(g, i) > x) i--;
+  while (i + 1 < nb && g.part[i + 1] <= x) i++;
+  while (i > 0 && g.part[i] > x) i--;
   return i;
 }
 
@@ -185,6 +224,7 @@ MSIM_HD void report_cursor_start(const ReportGeom &g, ReportCursor &cur) {
 struct ReportCells {
   int state, event, bin_hi, bin_f0;  // the same cells by coordinates, for accumulators with their own layout
   int i_events, i_dstart;  // counters to increment
+  double e_lhs, e_rhs;     // exp(-alpha * lhs), exp(-alpha * rhs) (1 without discounting): for addBrief
   bool noedge;             // also increment noedge[s][hi]
   int row_hi, row_lo;      // state*n_bin + bin of the partial overlaps; row_lo < 0: none
   double pt_hi, ut_hi, pt_lo, ut_lo;
@@ -209,6 +249,8 @@ MSIM_HD ReportCells report_cells(const ReportGeom &g, ReportCursor &cur, int sta
   cur.e = erhs;
   cur.bin = hi;
   cur.valid = true;
+  c.e_lhs = elhs;
+  c.e_rhs = erhs;
 
   const int row = state * nb;
   const double plo = report_part(g, lo);
@@ -243,6 +285,19 @@ MSIM_HD ReportCells report_cells(const ReportGeom &g, ReportCursor &cur, int sta
   if (disc) c.ut_hi = report_discounted_e(g, phi, rhs, g.edge_decay[hi], erhs);
   c.noedge = !(phi < rhs);
   return c;
+}
+
+// EventReport::addBrief (microsimulation.h:929-932): what the interval [lhs, rhs] adds to the individual's running
+// discounted total, which counts from startReportAge on: discountedUtilities(max(lhs - sra, 0), rhs - sra) with
+// utility 1.  exp(-alpha (t - sra)) = exp(-alpha t) exp(alpha sra): the interval's own exponentials are reused.
+MSIM_HD double report_brief(const ReportGeom &g, const ReportCells &c, double lhs, double rhs) {
+  const double sra = g.start_report_age;
+  if (!(rhs >= sra)) return 0.0;
+  const double a = (lhs > sra) ? lhs - sra : 0.0, b = rhs - sra;
+  if (g.discount_rate == 0.0) return b - a;
+  if (a == b) return 0.0;
+  const double ea = (lhs > sra) ? c.e_lhs * g.sra_gain : 1.0;
+  return g.inv_alpha * (ea - c.e_rhs * g.sra_gain);
 }
 
 // Acc supplies addf(index, double) for FP sums, addi(index, int) for counters

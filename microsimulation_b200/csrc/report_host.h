@@ -111,6 +111,7 @@ inline void dense_to_report_impl(const double *d, const ReportGeom &G, msim_repo
         }
     }
   }
+  if (!G.output_utilities) ut.clear();  // EventReport(..., outputUtilities = false): wrap() has no "ut" (microsimulation.h:981-985)
   table_from_rows(pt, 3, PT_COLS, &out->pt);
   table_from_rows(ut, 3, UT_COLS, &out->ut);
   table_from_rows(ev, 4, EV_COLS, &out->events);

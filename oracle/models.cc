@@ -119,7 +119,8 @@ void Person::handleMessage(const cMessage *msg) {
 // persons' substream jumps are done one by one, exactly as the loop would)
 // and optional EventReport attachment (BASELINE config 4).
 void run_person_r(const double seed_in[6], int64_t first_person, int64_t n, bool keep_rows, RowLog *log,
-                  double counts[9], ReportTables *report, double discount_rate) {
+                  double counts[9], ReportTables *report, double discount_rate, const PersonReportOptions *opt,
+                  double *indiv, double means[7]) {
   using namespace person_r;
   double seed[6];
   for (int i = 0; i < 6; i++) seed[i] = seed_in[i];
@@ -129,13 +130,18 @@ void run_person_r(const double seed_in[6], int64_t first_person, int64_t n, bool
   g_log = log;
   g_keep_rows = keep_rows;
   memset(g_counts, 0, sizeof g_counts);
-  Report rep(discount_rate);
+  Report rep(discount_rate, opt ? opt->output_utilities != 0 : true, opt ? opt->start_report_age : 0.0);
   if (report) {
-    std::vector<double> ages;
-    for (int a = 0; a <= 100; a++) ages.push_back(a);
-    ages.push_back(1.0e+6);
     rep.clear();
-    rep.setPartition(ages);
+    if (opt) {  // EventReport::setPartition(start, finish, delta, maxTime)
+      rep.setPartition(opt->start, opt->finish, opt->delta, opt->max_time);
+    } else {
+      std::vector<double> ages;
+      for (int a = 0; a <= 100; a++) ages.push_back(a);
+      ages.push_back(1.0e+6);
+      rep.setPartition(ages);
+    }
+    if (indiv) rep.setIndivN((int)n);
     g_report = &rep;
   } else {
     g_report = 0;
@@ -154,12 +160,20 @@ void run_person_r(const double seed_in[6], int64_t first_person, int64_t n, bool
     person = Person((int)i);
     Sim::create_process(&person);
     Sim::run_simulation();
+    if (g_report) g_report->individualReset();  // at the end of the individual, while now() is its last event's time
     Sim::clear();
   }
   delete rng["NH"];
   delete rng["S"];
   if (counts) memcpy(counts, g_counts, sizeof g_counts);
   if (report) flatten(rep, report);
+  if (report && indiv)
+    for (int64_t i = 0; i < n; i++) indiv[i] = rep._vector[(size_t)i];
+  if (report && means) {
+    Means &m = rep.mean_utilities;
+    means[0] = m.n(); means[1] = m.mean(); means[2] = m.var(); means[3] = m.sd(); means[4] = m.sd() / sqrt((double)m.n());
+    means[5] = m.sum(); means[6] = m.sumsq();
+  }
   g_report = 0;
 }
 

@@ -91,8 +91,13 @@ void flatten(const Rep &r, ReportTables *out) {
   flatten3(r._prev, out->prev, out->n_prev);
 }
 
-void run_person_r(const double seed[6], int64_t first_person, int64_t n, bool keep_rows, RowLog *log,
-                  double counts[9], ReportTables *report, double discount_rate);
+struct PersonReportOptions {  // include/msim.h msim_report_options
+  double start, finish, delta, max_time, start_report_age;
+  int32_t output_utilities;
+};
+void run_person_r(const double seed_in[6], int64_t first_person, int64_t n, bool keep_rows, RowLog *log,
+                  double counts[9], ReportTables *report, double discount_rate, const PersonReportOptions *opt = 0,
+                  double *indiv = 0, double means[7] = 0);
 void run_calibration(int64_t first_person, int64_t n, const double par[6], msim_calibration *out);
 void run_illness_death(int64_t n, double cure, double zsd, ReportTables *out);
 void run_simple_person(int64_t n, RowLog *log);

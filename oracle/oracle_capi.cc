@@ -189,6 +189,21 @@ int oracle_person_run(const msim_person_shard *sh, msim_table *rowlog, double co
   return 0;
 }
 
+// the same with the report's options (msim_report_options), every individual's discounted total and their means
+int oracle_person_run_options(const msim_person_shard *sh, const msim_report_options *opt, double counts[9], msim_report *report,
+                              double *indiv, double means[7]) {
+  RowLog log;
+  ReportTables rt;
+  PersonReportOptions o;
+  if (opt) {
+    o.start = opt->start; o.finish = opt->finish; o.delta = opt->delta; o.max_time = opt->max_time;
+    o.start_report_age = opt->start_report_age; o.output_utilities = opt->output_utilities;
+  }
+  run_person_r(sh->seed, sh->first_person, sh->n, false, &log, counts, &rt, sh->discount_rate, opt ? &o : 0, indiv, means);
+  fill_report(rt, report);
+  return 0;
+}
+
 int oracle_callSimplePerson(int32_t n, msim_table *out) {
   RowLog log;
   run_simple_person(n, &log);

@@ -192,6 +192,26 @@ class Oracle:
             self.lib.oracle_report_free(C.byref(r))
         return out
 
+    def person_run_options(self, seed, first_person, n, discount_rate, start, finish, delta, max_time=1.0e100,
+                           start_report_age=0.0, output_utilities=True):
+        """person-r with an EventReport built from setPartition(start, finish, delta, maxTime), startReportAge and
+        outputUtilities, individualReset after every person: (report tables, counts, wrap_indiv, wrap_means)."""
+        class Opt(C.Structure):
+            _fields_ = [("start", C.c_double), ("finish", C.c_double), ("delta", C.c_double), ("max_time", C.c_double),
+                        ("start_report_age", C.c_double), ("output_utilities", C.c_int32)]
+        sh = PersonShard((C.c_double * 6)(*[float(x) for x in _seed6(seed)]), first_person, n, 0, discount_rate)
+        o = Opt(start, finish, delta, max_time, start_report_age, int(bool(output_utilities)))
+        r = Report()
+        counts = (C.c_double * 9)()
+        indiv = np.empty(max(n, 1))
+        means = (C.c_double * 7)()
+        rc = self.lib.oracle_person_run_options(C.byref(sh), C.byref(o), counts, C.byref(r),
+                                                indiv.ctypes.data_as(C.POINTER(C.c_double)), means)
+        assert rc == 0
+        rep = r.to_dict()
+        self.lib.oracle_report_free(C.byref(r))
+        return rep, np.array(counts[:]), indiv[:n], dict(zip(("n", "mean", "var", "sd", "se", "sum", "sumsq"), means[:]))
+
     def callSimplePerson(self, n=10, seed=12345):
         self.set_seed(seed)
         return self._table_call(self.lib.oracle_callSimplePerson, C.c_int32(n))

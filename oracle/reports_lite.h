@@ -49,6 +49,28 @@ struct KeyHash {
   }
 };
 
+// microsimulation.h:468-496
+class Means {
+ public:
+  Means() : _n(0), _sum(0.0), _sumsq(0.0) {}
+  double mean() { return _sum / _n; }
+  double var() { return (long double)_n / (_n - 1) * (_sumsq / _n - mean() * mean()); }
+  int n() { return _n; }
+  double sum() { return _sum; }
+  double sumsq() { return _sumsq; }
+  double sd() { return sqrt(var()); }
+  Means *operator+=(const double value) {
+    _n++;
+    _sum += (long double)value;
+    _sumsq += (long double)value * (long double)value;
+    return this;
+  }
+
+ private:
+  int _n;
+  long double _sum, _sumsq;
+};
+
 template <class State, class Event, class Time = double, class Utility = double>
 class EventReport {
  public:
@@ -56,10 +78,22 @@ class EventReport {
   typedef typename Partition::iterator Iterator;
   typedef std::pair<State, Time> Pair;
   typedef std::tuple<State, Event, Time> Triple;
-  EventReport(Utility discountRate = 0.0, bool outputUtilities = true, Time startReportAge = Time(0))
+  EventReport(Utility discountRate = 0.0, bool outputUtilities = true, Time startReportAge = Time(0), int size = 1,
+              bool indiv = false)
       : discountRate(discountRate), current(0), outputUtilities(outputUtilities),
-        startReportAge(startReportAge) {
+        startReportAge(startReportAge), id(0), indiv(indiv) {
+    _vector.resize(size);
     setPartition(startReportAge);
+  }
+  void setIndivN(const int n) {  // microsimulation.h:889-892
+    _vector.resize(n);
+    indiv = true;
+  }
+  void individualReset() {  // microsimulation.h:905-916
+    if (now() >= startReportAge) mean_utilities += double(current);
+    if (indiv && id < int(_vector.size())) _vector[id] = (now() >= startReportAge) ? double(current) : NAN;  // NA_REAL
+    current = Utility(0);
+    id++;
   }
   void setPartition(const std::vector<Time> v) {
     for (size_t i = 0; i < v.size(); i++) _partition.insert(v[i]);
@@ -126,6 +160,10 @@ class EventReport {
   std::unordered_map<Pair, Time, KeyHash> _pt;
   std::unordered_map<Triple, int, KeyHash> _events;
   Time startReportAge;
+  std::vector<Utility> _vector;
+  Means mean_utilities;
+  int id;
+  bool indiv;
 };
 
 template <class State, class Event = short, class Time = double, class Utility = double, class Cost = double>

@@ -709,6 +709,24 @@ int emu_sick_sicker(int64_t n, const double par17[17], int indivp, int substream
     end_word = pos;
   }
   int carry = 0;
+  if (substreams && first_person > 0) {  // a shard inherits the last code of the persons before it (host_summary.h)
+    for (int64_t hi_p = first_person, wdw = 256; hi_p > 0 && carry == 0; wdw *= 16) {
+      const int64_t lo_p = std::max<int64_t>(0, hi_p - wdw);
+      StreamStart st2;
+      make_start(seed, lo_p + 1, 1, &st2);
+      Mrg32k3a b2;
+      memcpy(b2.s, st2.base, sizeof b2.s);
+      for (int64_t i = lo_p; i < hi_p; i++) {
+        HostNullEnv<MrgSource> env;
+        env.src.g = b2;
+        sick_sicker::SickSicker<HostNullEnv<MrgSource> > person(env, P, 0);
+        person.run();
+        if (env.code) carry = env.code;
+        b2.jump(mrg_substream_jump());
+      }
+      hi_p = lo_p;
+    }
+  }
   for (int64_t i = 0; i < n; i++) {
     code_in[i] = (unsigned char)carry;
     if (code_out[i]) carry = code_out[i];

@@ -9,7 +9,7 @@ bit-exact; FP64 report sums within 1e-9 relative; event TIMES within a few ulp
 import numpy as np
 import pytest
 
-from conftest import assert_report_close, assert_rowlog_close
+from conftest import assert_report_close, assert_rowlog_close, assert_table_close
 
 pytestmark = pytest.mark.gpu
 
@@ -651,6 +651,51 @@ def test_gpu_against_the_reference_linked_oracle(msim, oracle_ref):
             assert np.array_equal(g[k], r[k]), k
     par = api.sick_sicker_param(True)
     _summary_equal(api.callSim(3000, par), oracle_ref.sick_sicker(3000, par))
+
+
+@pytest.mark.parametrize("start,finish,delta,max_time,sra,rate,out_ut", [
+    (0.0, 100.0, 5.0, 1.0e100, 50.0, 0.03, True),      # 0..100 by 5, startReportAge 50
+    (0.0, 100.0, 1.0, 1.0e100, 0.0, 0.03, True),       # the unit partition through the general entry (maxTime 1e100)
+    (0.0, 90.0, 0.1 * 7, 1.0e6, 20.0, 0.05, True),     # points by repeated addition of an inexact delta
+    (0.0, 100.0, 10.0, 1.0e100, 65.0, 0.0, False),     # no discounting, outputUtilities = false
+])
+def test_person_report_options_vs_oracle(msim, oracle, start, finish, delta, max_time, sra, rate, out_ut):
+    """EventReport's surface beyond the built models' fixed partition (microsimulation.h:873-932): setPartition(start,
+    finish, delta, maxTime), startReportAge, outputUtilities, and the per-individual discounted totals of addBrief /
+    individualReset with their Means — the GPU against the oracle's EventReport, cell by cell and person by person."""
+    import microsimulation_b200.api as api
+    n = 60000
+    api.set_report_options(start, finish, delta, max_time, sra, out_ut)
+    try:
+        rep, counts, indiv, means = api.person_report(12345, 77, n, rate, indiv=True)
+    finally:
+        api.set_report_options()
+    ref, rcounts, rindiv, rmeans = oracle.person_run_options(12345, 77, n, rate, start, finish, delta, max_time, sra, out_ut)
+    assert np.array_equal(counts[:8], rcounts[:8])
+    for tb in ("pt", "events", "prev") + (("ut",) if out_ut else ()):
+        assert_table_close(rep[tb], ref[tb], 1e-9)
+    if not out_ut:
+        assert len(rep["ut"]["utility"]) == 0
+    assert np.array_equal(np.isnan(indiv), np.isnan(rindiv))     # NA exactly where the last event came before startReportAge
+    assert 0 < np.isnan(indiv).sum() < n or sra == 0.0
+    ok = ~np.isnan(indiv)
+    np.testing.assert_allclose(indiv[ok], rindiv[ok], rtol=1e-11, atol=1e-12)
+    assert means["n"] == rmeans["n"] == ok.sum()
+    for k in ("mean", "var", "sd", "se", "sum", "sumsq"):
+        np.testing.assert_allclose(means[k], rmeans[k], rtol=1e-10, err_msg=k)
+    # the default is restored: the built models' partition again
+    again, _ = api.person_report(12345, 77, 2000, 0.03)
+    assert again["pt"]["age"].max() in (1.0e6, 100.0) and len(set(again["pt"]["age"])) > 50
+
+
+def test_report_options_are_validated(msim):
+    import microsimulation_b200.api as api
+    for bad in ((0.0, 100.0, 0.0), (0.0, -1.0, 1.0), (0.0, 100.0, 0.5)):   # delta 0; finish < start; 201 points
+        with pytest.raises(msim.MsimError):
+            api.set_report_options(*bad)
+    api.set_report_options()
+    with pytest.raises(msim.MsimError):   # individual totals need the report
+        api.person_run_device(12345, 0, 100, 4 | 8, 0.03)
 
 
 def test_person_1e7_rows_and_report_against_the_reference_on_all_cores(msim):
