@@ -121,7 +121,16 @@ constexpr int QCAP = 64;        // a queue holds < 32 entries between pushes, < 
 constexpr int XROWS = 4;        // rows a person may log beyond its first (person_r::MAX_ROWS - 1)
 constexpr int ROW_CHUNK = 1024;  // persons per block of the row-log passes
 constexpr int ROW_OV_MIN = 64;    // smallest region for a chunk's further rows, whatever the plan says
-constexpr int ROW_WINDOW = 2048;  // rows a block of the final pass stages at a time (a chunk holds 1262 on average)
+#ifndef MSIM_ROW_WINDOW
+#define MSIM_ROW_WINDOW 1536
+#endif
+#ifndef MSIM_ROW_MINB
+#define MSIM_ROW_MINB 6
+#endif
+// rows a block of the final pass stages at a time (a chunk holds 1262 on average).  1536 rows and 6 blocks per SM (40
+// registers) measured best: 5.06 ms per 1e8 persons for the whole row-log step against 5.29 (2048 rows, 55 registers),
+// 5.14 (2048, 5 blocks), 5.10 (1280, 7), 5.13 (1024, 8)  [gpurun_out/variants, round 2]
+constexpr int ROW_WINDOW = MSIM_ROW_WINDOW;
 
 struct alignas(16) WarpQueues {
   uint32_t q1_s[6][QCAP];
@@ -631,7 +640,7 @@ __global__ void __launch_bounds__(1024) rowpass_scan_kernel(RowPassParams p) {
 
 // One block per chunk: every person's row offset by a block scan of the row counts, first rows and further
 // rows placed in shared memory in final order, then streamed out (all global accesses coalesced).
-__global__ void __launch_bounds__(256) rowpass_final_kernel(RowPassParams p) {
+__global__ void __launch_bounds__(256, MSIM_ROW_MINB) rowpass_final_kernel(RowPassParams p) {
   __shared__ unsigned short s_tag[ROW_CHUNK];
   __shared__ unsigned short s_off[ROW_CHUNK];
   __shared__ double s_end[ROW_WINDOW], s_start[ROW_WINDOW];

@@ -12,6 +12,8 @@
 // pass in the stream regime), carry_tile_kernel / carry_apply_kernel turn that into the code each
 // person starts with, and only then does sick_kernel run the persons.
 #pragma once
+#include <new>
+
 #include "kernels.cuh"
 #include "summary.cuh"
 
@@ -42,26 +44,53 @@ struct SickParams {
   int *tie;  // set if two pending actions of a person compared equal (ORDERED only)
 };
 
+// Lives of this model differ widely in length (1 to ~40 events), so with 32 persons side by side a warp waits for its
+// longest life: 8 of 32 lanes busy (profiles/r01c_secondary_kernels.md).  Here every lane walks ITS OWN list of persons
+// (lane l of the grid takes persons l, l + threads, l + 2 threads, ...: the same persons as before, so its substream
+// state still advances by one fixed jump per person) at its own pace: every pass of the loop is ONE event on every
+// lane that has a person, and lanes whose person has ended start their next one together, once SICK_REFILL_MIN of
+// them wait (or nothing else is running), so that the start-up code — substream jump, init() — does not run for
+// one or two lanes at a time.
+#ifndef MSIM_SICK_REFILL
+#define MSIM_SICK_REFILL 8
+#endif
+constexpr int SICK_REFILL_MIN = MSIM_SICK_REFILL;
+
 // first pass, substream regime: each person's last set_uc() code
 template <bool ORDERED>
 __global__ void __launch_bounds__(BLOCK) sick_code_kernel(SickParams p) {
   typedef NullEnv<MrgSource> Env;
+  typedef sick_sicker::SickSicker<Env, ORDERED> Person;
   Mrg32k3a sub = thread_start_state(p.st, blockIdx.x * BLOCK + threadIdx.x);
   const int64_t stride = (int64_t)gridDim.x * BLOCK;
-  for (int64_t i0 = (int64_t)blockIdx.x * BLOCK + (threadIdx.x & ~31); i0 < p.n; i0 += stride) {
-    const int64_t i = i0 + (threadIdx.x & 31);
-    __syncwarp();  // every pass starts with the warp together (kernels.cuh, calib_kernel)
-    if (i < p.n) {
-      Env env;
+  int64_t next = (int64_t)blockIdx.x * BLOCK + threadIdx.x, cur = 0;
+  bool have = false;
+  Env env;
+  Person person(env, p.par, 0);
+  for (;;) {
+    __syncwarp();
+    const bool want = !have && next < p.n;
+    const unsigned wm = __ballot_sync(0xffffffffu, want), hm = __ballot_sync(0xffffffffu, have);
+    if ((wm | hm) == 0) break;
+    if (want && (__popc(wm) >= SICK_REFILL_MIN || hm == 0)) {
+      cur = next;
+      next += stride;
+      env.code = 0;
       env.src.g = sub;
-      sick_sicker::SickSicker<Env, ORDERED> person(env, p.par, 0);
-      person.run();
-      p.code_out[i] = (unsigned char)env.code;
-      if (person.error_) atomicCAS(p.error, 0, person.error_);
-      if (ORDERED && person.actions.tie) *p.tie = 1;
+      sub.jump(p.st.stride);
+      new (&person) Person(env, p.par, 0);
+      person.begin();
+      have = true;
     }
     __syncwarp();
-    sub.jump(p.st.stride);
+    if (have) {
+      have = person.alive() && person.step();
+      if (!have) {
+        p.code_out[cur] = (unsigned char)env.code;
+        if (person.error_) atomicCAS(p.error, 0, person.error_);
+        if (ORDERED && person.actions.tie) *p.tie = 1;
+      }
+    }
   }
 }
 
@@ -195,38 +224,51 @@ __global__ void __launch_bounds__(BLOCK) sick_kernel(SickParams p) {
   const int64_t stride = (int64_t)gridDim.x * BLOCK;
   int err = 0;
   double all_u = 0.0, all_c = 0.0;
-  for (int64_t i0 = (int64_t)blockIdx.x * BLOCK + (threadIdx.x & ~31); i0 < p.n; i0 += stride) {
-    const int64_t i = i0 + (threadIdx.x & 31);
-    __syncwarp();  // every pass starts with the warp together (kernels.cuh, calib_kernel)
-    if (i >= p.n) {
-      if constexpr (!STREAM) sub.jump(p.st.stride);
-      continue;
+  // every lane walks its own list of persons, one event per pass (see sick_code_kernel)
+  typedef sick_sicker::SickSicker<Env, ORDERED> Person;
+  int64_t next = (int64_t)blockIdx.x * BLOCK + threadIdx.x, cur = 0;
+  bool have = false;
+  Person person(env, p.par, 0);
+  for (;;) {
+    __syncwarp();
+    const bool want = !have && next < p.n;
+    const unsigned wm = __ballot_sync(0xffffffffu, want), hm = __ballot_sync(0xffffffffu, have);
+    if ((wm | hm) == 0) break;
+    if (want && (__popc(wm) >= SICK_REFILL_MIN || hm == 0)) {
+      cur = next;
+      next += stride;
+      if constexpr (STREAM) {
+        env.src.w = p.mt_words;
+        env.src.pos = p.starts[cur];
+        env.src.end = p.mt_end;
+        env.src.overrun = 0;
+      } else {
+        env.src.g = sub;
+        sub.jump(p.st.stride);
+      }
+      sick_sicker::uc_of_code(p.par, p.code_in[cur], &env.u, &env.c);
+      env.tot_u = env.tot_c = 0.0;
+      new (&person) Person(env, p.par, p.first_person + cur);
+      person.begin();
+      have = true;
     }
-    if constexpr (STREAM) {
-      env.src.w = p.mt_words;
-      env.src.pos = p.starts[i];
-      env.src.end = p.mt_end;
-      env.src.overrun = 0;
-    } else {
-      env.src.g = sub;
-    }
-    sick_sicker::uc_of_code(p.par, p.code_in[i], &env.u, &env.c);
-    env.tot_u = env.tot_c = 0.0;
-    sick_sicker::SickSicker<Env, ORDERED> person(env, p.par, p.first_person + i);
-    person.run();
-    if (person.error_) err = person.error_;
-    if (ORDERED && person.actions.tie) *p.tie = 1;
-    if constexpr (STREAM) {
-      if (env.src.overrun) err = -6;
-    } else {
-      sub.jump(p.st.stride);
-    }
-    if (p.indivp) {
-      p.indiv[2 * i] = env.tot_u;
-      p.indiv[2 * i + 1] = env.tot_c;
-    } else {
-      all_u += env.tot_u;
-      all_c += env.tot_c;
+    __syncwarp();
+    if (have) {
+      have = person.alive() && person.step();
+      if (!have) {
+        if (person.error_) err = person.error_;
+        if (ORDERED && person.actions.tie) *p.tie = 1;
+        if constexpr (STREAM) {
+          if (env.src.overrun) err = -6;
+        }
+        if (p.indivp) {
+          p.indiv[2 * cur] = env.tot_u;
+          p.indiv[2 * cur + 1] = env.tot_c;
+        } else {
+          all_u += env.tot_u;
+          all_c += env.tot_c;
+        }
+      }
     }
   }
   if (!p.indivp) {

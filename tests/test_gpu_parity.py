@@ -656,7 +656,7 @@ def test_gpu_against_the_reference_linked_oracle(msim, oracle_ref):
 @pytest.mark.parametrize("start,finish,delta,max_time,sra,rate,out_ut", [
     (0.0, 100.0, 5.0, 1.0e100, 50.0, 0.03, True),      # 0..100 by 5, startReportAge 50
     (0.0, 100.0, 1.0, 1.0e100, 0.0, 0.03, True),       # the unit partition through the general entry (maxTime 1e100)
-    (0.0, 90.0, 0.1 * 7, 1.0e6, 20.0, 0.05, True),     # points by repeated addition of an inexact delta
+    (0.0, 90.0, 0.1 * 9, 1.0e6, 20.0, 0.05, True),     # points by repeated addition of an inexact delta
     (0.0, 100.0, 10.0, 1.0e100, 65.0, 0.0, False),     # no discounting, outputUtilities = false
 ])
 def test_person_report_options_vs_oracle(msim, oracle, start, finish, delta, max_time, sra, rate, out_ut):
