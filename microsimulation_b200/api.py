@@ -54,7 +54,7 @@ def set_person_schedule(which):
     """0 / "staged" (default) or 1 / "generic": which GPU schedule runs person-r, and whether the calibration model
     keeps its pending actions in an ordered array (0) or the binary heap (1).  Same results either way.  2 / "repeat"
     is 0 with the repeat paths forced (tests)."""
-    which = {"staged": 0, "generic": 1, "repeat": 2, "three_pass_rowlog": 3}.get(which, which)
+    which = {"staged": 0, "generic": 1, "repeat": 2}.get(which, which)
     check(load().msim_set_person_schedule(C.c_int(int(which))))
 
 

@@ -58,7 +58,7 @@ void msim_shutdown(void) {
   DevBuf *bufs[] = {&g.rowlog, &g.prov_start, &g.prov_end, &g.prov_meta, &g.tile_count, &g.partial, &g.dense, &g.small, &g.mt_words, &g.len, &g.starts, &g.chain_exit,
                     &g.chain_count, &g.chain_entry, &g.chain_base, &g.chain_gexit, &g.chain_gcount, &g.chain_gentry, &g.chain_gbase, &g.calib_out, &g.calib_partial, &g.calib_par, &g.uniforms,
                     &g.first_end, &g.first_tag, &g.ov_fill, &g.ov_tag, &g.ov_start, &g.ov_end,
-                    &g.aux, &g.code_in, &g.code_out, &g.sgeom, &g.indiv, &g.gsm_model, &g.gsm_data, &g.gsm_in, &g.gsm_out, &g.slices, &g.fold_sync, &g.carry_tiles, &g.scan_state};
+                    &g.aux, &g.code_in, &g.code_out, &g.sgeom, &g.indiv, &g.gsm_model, &g.gsm_data, &g.gsm_in, &g.gsm_out, &g.slices, &g.fold_sync, &g.carry_tiles};
   if (g.d_mt_table) cudaFree(g.d_mt_table);
   g.d_mt_table = nullptr;
   g.mt_table_polys = 0;
@@ -118,10 +118,8 @@ int msim_set_mt_parallel(int on) {
 }
 
 int msim_set_person_schedule(int which) {
-  if (which < 0 || which > 3)
-    return fail(MSIM_ERR_ARG, "schedule must be 0 (staged), 1 (generic), 2 (test: 0 with the repeat paths forced) or 3 (test: 0 with the row log's three-launch passes)");
-  g.rowpass_three = which == 3;
-  g.person_kernel = which == 3 ? 0 : which;
+  if (which < 0 || which > 2) return fail(MSIM_ERR_ARG, "schedule must be 0 (staged), 1 (generic) or 2 (test: 0 with the repeat paths forced)");
+  g.person_kernel = which;
   return MSIM_OK;
 }
 

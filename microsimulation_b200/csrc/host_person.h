@@ -29,26 +29,14 @@ int staged_rowpasses(int64_t n, int64_t first_person, int64_t capacity, bool cou
   r.rowlog = (double *)g.rowlog.p;
   r.capacity = capacity;
   if (r.n_chunks == 0) return MSIM_OK;
-  (void)count_first;
-  // one launch: chunks are handed out by ticket, their row offsets come from a chained scan inside the kernel
-  // (person_staged.cuh, rowpass_fused_kernel); the scan cells and the ticket are zeroed by one memset
-  const size_t state_bytes = sizeof(unsigned long long) * (size_t)(r.n_chunks + 1);
-  int rc;
-  if ((rc = ensure(g.scan_state, state_bytes))) return rc;
-  CK(cudaMemsetAsync(g.scan_state.p, 0, state_bytes, g.stream));
-  r.scan_state = (unsigned long long *)g.scan_state.p + 1;
-  r.ticket = (unsigned *)g.scan_state.p;
-  if (g.rowpass_three) {  // the three-launch form (tests compare the two)
+  if (count_first) {
     rowpass_count_kernel<<<(unsigned)r.n_chunks, 256, 0, g.stream>>>(r);
     CK(cudaGetLastError());
     rowpass_scan_kernel<<<1, 1024, 0, g.stream>>>(r);
     CK(cudaGetLastError());
-    rowpass_final_kernel<<<(unsigned)r.n_chunks, 256, 0, g.stream>>>(r);
-    CK(cudaGetLastError());
-    g.launches += 3;
-    return MSIM_OK;
+    g.launches += 2;
   }
-  rowpass_fused_kernel<<<(unsigned)r.n_chunks, 256, 0, g.stream>>>(r);
+  rowpass_final_kernel<<<(unsigned)r.n_chunks, 256, 0, g.stream>>>(r);
   CK(cudaGetLastError());
   g.launches++;
   return MSIM_OK;

@@ -43,10 +43,9 @@ struct Ctx {
   bool mt_parallel = true;         // msim_set_mt_parallel: tests switch the jump-ahead path off to compare
   DevBuf rowlog, prov_start, prov_end, prov_meta, tile_count, partial, dense, small, mt_words, len, starts, chain_exit, chain_count, chain_entry, chain_base, chain_gexit, chain_gcount, chain_gentry, chain_gbase, calib_out, calib_partial,
       calib_par, uniforms, first_end, first_tag, ov_fill, ov_tag, ov_start, ov_end, aux, code_in, code_out, sgeom,
-      indiv, gsm_model, gsm_data, gsm_in, gsm_out, slices, fold_sync, carry_tiles, scan_state;
+      indiv, gsm_model, gsm_data, gsm_in, gsm_out, slices, fold_sync, carry_tiles;
   int person_kernel = 0;  // 0 = staged schedule (person_staged.cuh), 1 = generic cohort kernel
   bool last_staged = false;
-  bool rowpass_three = false;  // msim_set_person_schedule(3): the row log's three-launch form (tests)
   double plan_rows = 1.25, plan_extra_rows = 0.26;  // row-log buffer planning (msim_set_rowlog_plan)
   int64_t last_ov_cap = 0, last_ov_rows = 0;
   HostRngState rng;

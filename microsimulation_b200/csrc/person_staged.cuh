@@ -580,11 +580,6 @@ struct RowPassParams {
   int ov_cap;
   int64_t n, first_person;
   unsigned long long *chunk_rows;  // per-chunk totals, then (in place) exclusive offsets
-  // single-pass form (rowpass_fused_kernel): chunk c's cell of the chained scan — bits 62-63: 0 nothing yet, 1 the
-  // chunk's own total, 2 the total of chunks 0..c; bits 0-61 the value — and the ticket counter that hands out chunks
-  // in the order blocks start (a block only ever waits for chunks that were handed out before its own)
-  unsigned long long *scan_state;
-  unsigned *ticket;
   unsigned long long *n_rows;
   unsigned long long *max_fill;    // largest ov_fill seen (tells the host whether ov_cap was enough)
   int64_t n_chunks;
@@ -723,123 +718,11 @@ __global__ void __launch_bounds__(256, MSIM_ROW_MINB) rowpass_final_kernel(RowPa
   }
 }
 
-// The three row-log passes in ONE launch: a block takes the next chunk (ticket), counts its rows, publishes the
-// count, finds the rows before it by looking back over the chunks handed out earlier (chained scan with decoupled
-// look-back: a warp reads 32 predecessors at a time until it meets one that already knows its inclusive total), and
-// then places and streams its rows exactly as rowpass_final_kernel does.  Saves reading the tags twice and the
-// one-block scan between two launches (0.35 of 5.06 ms per 1e8 persons).
-__global__ void __launch_bounds__(256, MSIM_ROW_MINB) rowpass_fused_kernel(RowPassParams p) {
-  __shared__ unsigned short s_tag[ROW_CHUNK];
-  __shared__ unsigned short s_off[ROW_CHUNK];
-  __shared__ double s_end[ROW_WINDOW], s_start[ROW_WINDOW];
-  __shared__ unsigned s_meta[ROW_WINDOW];
-  __shared__ unsigned s_w[8];
-  __shared__ unsigned s_chunk;
-  __shared__ unsigned long long s_base;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_chunk = atomicAdd(p.ticket, 1u);
-  __syncthreads();
-  const int64_t c = s_chunk, lo = c * ROW_CHUNK;
-  constexpr int PER = ROW_CHUNK / 256;
-  constexpr unsigned long long VAL = (1ull << 62) - 1;
-  // ---- row offsets: thread t owns persons [PER*t, PER*t + PER)
-  unsigned cnt[PER], v = 0;
-#pragma unroll
-  for (int k = 0; k < PER; k++) {
-    const int64_t i = lo + tid * PER + k;
-    const unsigned short tag = (i < p.n) ? p.first_tag[i] : (unsigned short)0;
-    s_tag[tid * PER + k] = tag;
-    cnt[k] = tag_rows(tag);
-    v += cnt[k];
-  }
-  unsigned incl = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) s_w[warp] = incl;
-  __syncthreads();
-  unsigned run = incl - v, total = 0;
-  for (int w = 0; w < 8; w++) {
-    if (w < warp) run += s_w[w];
-    total += s_w[w];
-  }
-#pragma unroll
-  for (int k = 0; k < PER; k++) {
-    s_off[tid * PER + k] = (unsigned short)run;
-    run += cnt[k];
-  }
-  // ---- the rows before this chunk
-  if (warp == 0) {
-    volatile unsigned long long *st = p.scan_state;
-    if (lane == 0) {
-      st[c] = ((c == 0 ? 2ull : 1ull) << 62) | (unsigned long long)total;
-      atomicMax(p.max_fill, (unsigned long long)p.ov_fill[c]);
-    }
-    unsigned long long before = 0;
-    for (int64_t hi = c - 1; hi >= 0;) {  // predecessors hi, hi-1, ..., hi-31
-      const int64_t q = hi - lane;
-      unsigned long long cell = 0;
-      do {
-        cell = (q >= 0) ? st[q] : (2ull << 62);  // (before chunk 0: an inclusive total of 0)
-      } while (__any_sync(0xffffffffu, (cell >> 62) == 0));
-      const unsigned incl_mask = __ballot_sync(0xffffffffu, (cell >> 62) == 2);
-      const int stop = incl_mask ? __ffs(incl_mask) - 1 : 32;  // the nearest predecessor with an inclusive total
-      unsigned long long part = (lane <= stop && lane < 32) ? (cell & VAL) : 0ull;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      before += part;
-      if (incl_mask) break;
-      hi -= 32;
-    }
-    if (lane == 0) {
-      __threadfence();
-      if (c > 0) st[c] = (2ull << 62) | (before + total);
-      s_base = before;
-      if (c == p.n_chunks - 1) *p.n_rows = before + total;
-    }
-  }
-  __syncthreads();
-  const unsigned long long base = s_base;
-  unsigned m = p.ov_fill[c];
-  if (m > (unsigned)p.ov_cap) m = (unsigned)p.ov_cap;
-  const size_t ov0 = (size_t)c * p.ov_cap;
-  for (unsigned w0 = 0; w0 < total; w0 += ROW_WINDOW) {
-    for (int i = tid; i < ROW_CHUNK; i += 256) {
-      const unsigned short tag = s_tag[i];
-      const unsigned o = (unsigned)s_off[i] - w0;
-      if ((tag & 0x8000u) && o < (unsigned)ROW_WINDOW) {  // (unsigned wrap-around rejects rows before the window)
-        s_end[o] = p.first_end[lo + i];
-        s_start[o] = 0.0;  // a person's first interval starts at startTime = 0 (microsimulation.h:430)
-        s_meta[o] = ((unsigned)i << 16) | (((unsigned)tag >> 4) & 0xfu) << 8 | ((unsigned)tag & 0xfu);
-      }
-    }
-    for (unsigned e = tid; e < m; e += 256) {
-      const unsigned tag = p.ov_tag[ov0 + e];
-      const unsigned o = (unsigned)s_off[tag >> 16] + ((tag >> 12) & 0xfu) - w0;
-      if (o < (unsigned)ROW_WINDOW) {
-        s_end[o] = p.ov_end[ov0 + e];
-        s_start[o] = p.ov_start[ov0 + e];
-        s_meta[o] = (tag & 0xffff0000u) | (tag & 0xfffu);
-      }
-    }
-    __syncthreads();
-    const unsigned nw = (total - w0 < (unsigned)ROW_WINDOW) ? total - w0 : (unsigned)ROW_WINDOW;
-    for (unsigned r = tid; r < nw; r += 256) {
-      const unsigned long long g = base + w0 + r;
-      if (g < (unsigned long long)p.capacity) {
-        const unsigned mt = s_meta[r];
-        p.rowlog[0 * p.capacity + g] = s_end[r];
-        p.rowlog[1 * p.capacity + g] = (double)(mt & 0xffu);
-        p.rowlog[2 * p.capacity + g] = (double)(p.first_person + lo + (mt >> 16));
-        p.rowlog[3 * p.capacity + g] = s_start[r];
-        p.rowlog[4 * p.capacity + g] = (double)((mt >> 8) & 0xfu);
-      }
-    }
-    __syncthreads();
-  }
-}
+// Tried and dropped (round 2): the three passes in ONE launch — chunks handed out by ticket, each chunk's row offset
+// from a chained scan with decoupled look-back inside the kernel.  It saves reading the tags twice and the one-block
+// scan between two launches, but measured 5.21 ms per 1e8 persons for the whole row-log step against 5.06 for the
+// three launches: the look-back's L2 round trips sit in front of every block's bandwidth-bound part, and count + scan
+// together only cost 0.35 ms.
 
 #endif  // __CUDACC__
 

@@ -202,23 +202,6 @@ def test_person_rowlog_undersized_plan_is_recovered(msim, oracle, sched):
     assert_rowlog_close(g, r, TIME_RTOL)
 
 
-def test_rowlog_single_pass_equals_three_launch_passes(msim):
-    """The row log's final columns from the one-launch form (chunks by ticket, chained scan with look-back inside the
-    kernel) and from the three launches count / scan / place: bit for bit, at a size with 9766 chunks and at one
-    with a single partial chunk."""
-    import microsimulation_b200.api as api
-    for n in (10 ** 7, 700, 1025):
-        api.set_person_schedule(3)
-        try:
-            a = msim.callPersonSimulation(n)
-        finally:
-            api.set_person_schedule("staged")
-        b = msim.callPersonSimulation(n)
-        assert len(a["id"]) == len(b["id"]) > 0
-        for k in a:
-            assert np.array_equal(a[k], b[k]), (n, k)
-
-
 # ------------------------------------------------------------------ sequential-stream models (configs 1-2)
 
 @pytest.mark.parametrize("n", [0, 1, 10, 2049, 100000])
