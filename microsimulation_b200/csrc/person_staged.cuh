@@ -288,7 +288,9 @@ struct StagedEnvT {
   }
   __device__ __forceinline__ void report(int state, int kind, double lhs, double rhs) {
     if (out() & 2u) {
-      const ReportCells c = report_cells(*geom, cursor, state, kind, lhs, rhs);
+      // a person's first interval (lhs = startTime = 0) on a partition point: the short form of the same cells
+      const ReportCells c = (lhs == 0.0 && geom->first_on_edge) ? report_cells_first(*geom, cursor, state, kind, rhs)
+                                                                : report_cells(*geom, cursor, state, kind, lhs, rhs);
       acc.add(c, geom->discount_rate != 0.0);
       if (out() & 8u) current += report_brief(*geom, c, lhs, rhs);  // addBrief, microsimulation.h:929-932
     }
@@ -610,16 +612,24 @@ __global__ void __launch_bounds__(256) rowpass_count_kernel(RowPassParams p) {
   }
 }
 
-// one block: exclusive scan of the chunk totals in place; total row count out
+// one block: exclusive scan of the chunk totals in place; total row count out.  Eight consecutive chunks per thread
+// and pass (8192 per pass: 12 passes for 1e8 persons instead of 96 — the pass count is what this one block's time is made of)
 __global__ void __launch_bounds__(1024) rowpass_scan_kernel(RowPassParams p) {
   __shared__ unsigned long long s_w[32];
   __shared__ unsigned long long s_carry;
+  constexpr int PER = 8;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_carry = 0;
   __syncthreads();
-  for (int64_t c0 = 0; c0 < p.n_chunks; c0 += 1024) {
-    int64_t c = c0 + tid;
-    unsigned long long v = (c < p.n_chunks) ? p.chunk_rows[c] : 0, incl = v;
+  for (int64_t c0 = 0; c0 < p.n_chunks; c0 += 1024 * PER) {
+    const int64_t c = c0 + (int64_t)tid * PER;
+    unsigned long long x[PER], v = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      x[k] = (c + k < p.n_chunks) ? p.chunk_rows[c + k] : 0;
+      v += x[k];
+    }
+    unsigned long long incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -629,8 +639,13 @@ __global__ void __launch_bounds__(1024) rowpass_scan_kernel(RowPassParams p) {
     __syncthreads();
     unsigned long long woff = 0;
     for (int w = 0; w < warp; w++) woff += s_w[w];
-    unsigned long long carry = s_carry;
-    if (c < p.n_chunks) p.chunk_rows[c] = carry + woff + incl - v;
+    const unsigned long long carry = s_carry;
+    unsigned long long run = carry + woff + incl - v;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      if (c + k < p.n_chunks) p.chunk_rows[c + k] = run;
+      run += x[k];
+    }
     __syncthreads();
     if (tid == 1023) s_carry = carry + woff + incl;
     __syncthreads();
