@@ -55,7 +55,6 @@ struct ReportGeom {
   // individual's discounted total counts from startReportAge on (addBrief, :929-932); sra_gain = exp(alpha * sra)
   double start_report_age, sra_gain;
   int output_utilities;
-  int first_on_edge;  // 1 if time 0 is itself a partition point (part[bin0] == 0): a first interval then starts on an edge
   double part[REPORT_MAX_BINS];  // the partition points (setPartition), ascending; entries >= n_bin repeat the last
   double discount_rate, alpha, inv_alpha;  // alpha = log(1 + discount_rate), inv_alpha = 1/alpha (host libm)
   // offsets (in doubles) into the dense vector; FP sums first, then counters
@@ -92,7 +91,6 @@ inline ReportGeom make_report_geom(int n_state, int n_event, int n_bin, double s
   for (int i = 0; i < REPORT_MAX_BINS; i++) g.part[i] = (i >= n_bin - 1) ? last : start + i * delta;
   g.bin0 = 0;
   while (g.bin0 + 1 < n_bin && g.part[g.bin0 + 1] <= 0.0) g.bin0++;
-  g.first_on_edge = g.part[g.bin0] == 0.0;
   g.start_report_age = 0.0;
   g.sra_gain = 1.0;
   g.output_utilities = 1;
@@ -121,7 +119,6 @@ inline bool make_report_geom_partition(ReportGeom *out, int n_state, int n_event
   g.unit = unit ? 1 : 0;
   g.bin0 = 0;
   while (g.bin0 + 1 < n && g.part[g.bin0 + 1] <= 0.0) g.bin0++;
-  g.first_on_edge = g.part[g.bin0] == 0.0;
   g.start_report_age = start_report_age;
   g.sra_gain = (discount_rate != 0.0) ? fm_exp(start_report_age * g.alpha) : 1.0;
   g.output_utilities = output_utilities ? 1 : 0;
@@ -286,39 +283,6 @@ MSIM_HD ReportCells report_cells(const ReportGeom &g, ReportCursor &cur, int sta
   const double phi = report_part(g, hi);
   c.pt_hi = rhs - phi;
   if (disc) c.ut_hi = report_discounted_e(g, phi, rhs, g.edge_decay[hi], erhs);
-  c.noedge = !(phi < rhs);
-  return c;
-}
-
-// report_cells for a person's FIRST interval when it starts on a partition point (lhs = startTime = 0 = part[bin0],
-// g.first_on_edge): no left partial overlap, no left exponential, the first completely covered bin is bin0 — the same
-// cells report_cells computes for that case, without the work of finding that out.  Every person has a first
-// interval and four in five have no other, so this is the common path (person_staged.cuh).
-MSIM_HD ReportCells report_cells_first(const ReportGeom &g, ReportCursor &cur, int state, int event, double rhs) {
-  const int nb = g.n_bin;
-  const bool disc = g.discount_rate != 0.0;
-  ReportCells c;
-  const int lo = g.bin0, hi = report_bin(g, rhs);
-  const double erhs = disc ? report_decay(g, rhs) : 1.0;
-  cur.t = rhs;
-  cur.e = erhs;
-  cur.bin = hi;
-  cur.valid = true;
-  c.e_lhs = 1.0;
-  c.e_rhs = erhs;
-  const int row = state * nb;
-  const double phi = report_part(g, hi);  // (= 0 = lhs when hi == bin0)
-  c.state = state;
-  c.event = event;
-  c.bin_hi = hi;
-  c.bin_f0 = lo;
-  c.i_events = g.off_events + (state * g.n_event + event) * nb + hi;
-  c.i_dstart = g.off_dstart + row + lo;
-  c.row_hi = row + hi;
-  c.row_lo = -1;
-  c.pt_lo = c.ut_lo = 0.0;
-  c.pt_hi = rhs - phi;
-  c.ut_hi = disc ? report_discounted_e(g, phi, rhs, g.edge_decay[hi], erhs) : 0.0;
   c.noedge = !(phi < rhs);
   return c;
 }
