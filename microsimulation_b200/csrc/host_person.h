@@ -59,23 +59,25 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
   if (p.outputs & OUT_ROWLOG) smem += sizeof(WarpRows) * SWARPS;
   if (p.outputs & OUT_REPORT) smem += staged_counter_bytes(p.geom, p.compact);  // the counters; FP sums go to per-block global slices
   typedef void (*StagedKernel)(const StagedParams);
-  // kernels specialised for the output combinations without a report; the general one with (person_staged.cuh)
-  static const StagedKernel kernels[8] = {person_staged_kernel<0>, person_staged_kernel<1>, person_staged_kernel<OUT_RUNTIME>,
-                                          person_staged_kernel<OUT_RUNTIME>, person_staged_kernel<4>, person_staged_kernel<5>,
-                                          person_staged_kernel<OUT_RUNTIME>, person_staged_kernel<OUT_RUNTIME>};
-  const StagedKernel kernel = kernels[p.outputs & 7u];
+  // one instantiation per combination of outputs (person_staged.cuh); the general one, which reads the outputs at
+  // run time, only where individual totals are kept
+  static const StagedKernel kernels[8] = {person_staged_kernel<0>, person_staged_kernel<1>, person_staged_kernel<2>,
+                                          person_staged_kernel<3>, person_staged_kernel<4>, person_staged_kernel<5>,
+                                          person_staged_kernel<6>, person_staged_kernel<7>};
+  const StagedKernel kernel = (p.outputs & OUT_INDIV) ? person_staged_kernel<OUT_RUNTIME> : kernels[p.outputs & 7u];
   // blocks per SM for this (kernel, shared memory) pair: asked once, the answer does not change
-  static size_t occ_smem[8] = {0};
-  static int occ_per_sm[8] = {0};
-  int per_sm = occ_per_sm[p.outputs & 7u];
-  if (per_sm == 0 || occ_smem[p.outputs & 7u] != smem) {
+  static size_t occ_smem[9] = {0};
+  static int occ_per_sm[9] = {0};
+  const unsigned slot = (p.outputs & OUT_INDIV) ? 8u : (p.outputs & 7u);
+  int per_sm = occ_per_sm[slot];
+  if (per_sm == 0 || occ_smem[slot] != smem) {
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // as much of the SM's memory as shared memory as there is: the kernel reads no global data worth caching
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SBLOCK, smem));
     if (per_sm < 1) return fail(MSIM_ERR_CUDA, "staged kernel does not fit on an SM");
-    occ_per_sm[p.outputs & 7u] = per_sm;
-    occ_smem[p.outputs & 7u] = smem;
+    occ_per_sm[slot] = per_sm;
+    occ_smem[slot] = smem;
   }
   const int64_t tiles = (sh->n + 31) / 32;
   int64_t gmax = (int64_t)per_sm * g.sm_count;

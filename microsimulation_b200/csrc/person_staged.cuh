@@ -110,7 +110,7 @@ MSIM_DEV void run_life(Env &env, const Consts &K, int64_t id, const Life &life, 
 #ifdef __CUDACC__
 
 #ifndef MSIM_SBLOCK
-#define MSIM_SBLOCK 256
+#define MSIM_SBLOCK 320
 #endif
 #ifndef MSIM_SMINB
 #define MSIM_SMINB 2
@@ -291,7 +291,12 @@ struct StagedEnvT {
       // (a short form of the cells for a person's first interval — no left partial, no left exponential — was tried
       // here: 5.99 against 5.56 ms per 1e8 persons; the second copy of the cell code costs more in instruction
       // fetch and scheduling than the arithmetic it skips)
+#ifdef MSIM_FIRST_SHORT
+      const ReportCells c = (lhs == 0.0 && geom->part[geom->bin0] == 0.0) ? report_cells_first(*geom, cursor, state, kind, rhs)
+                                                                           : report_cells(*geom, cursor, state, kind, lhs, rhs);
+#else
       const ReportCells c = report_cells(*geom, cursor, state, kind, lhs, rhs);
+#endif
       acc.add(c, geom->discount_rate != 0.0);
       if (out() & 8u) current += report_brief(*geom, c, lhs, rhs);  // addBrief, microsimulation.h:929-932
     }
