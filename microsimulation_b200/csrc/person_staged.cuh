@@ -234,11 +234,17 @@ struct StagedAcc {
   }
 };
 
-// OUT = the MSIM_OUT_* combination when it is known at compile time (each such combination is its own kernel),
-// or OUT_RUNTIME: read from the parameters.  Which is faster is a matter of what the compiler makes of it
-// (measured on 1e8 persons): without a report the specialised kernels win (counts 3.97 vs 4.30 ms, row log 5.92
-// vs 6.15 ms); with one the general kernel does (6.2 vs 9.6 ms — the specialised one runs the substream jump and
-// the draws in fragments of a few lanes).
+// OUT = the MSIM_OUT_* combination when it is known at compile time (each combination is its own kernel), or
+// OUT_RUNTIME: read from the parameters (used where individual totals are kept).  Which is faster is a matter of what
+// the compiler makes of it.  Round 1 (1e8 persons): without a report the specialised kernels won (counts 3.97 vs 4.30
+// ms, row log 5.92 vs 6.15), with one the general kernel did (6.2 vs 9.6 ms — the specialised one ran the substream
+// jump and the draws in fragments of a few lanes).  Round 2, after the arithmetic was rewritten (mrg32k3a.cuh,
+// fastmath.cuh) and the block tables shrunk: the specialised report kernel wins too (5.35 vs 5.56 ms at 256 threads,
+// 103 registers), and at 92 registers it fits 320-thread blocks — 20 warps per SM, 5 per scheduler — without spills:
+// 4.77 ms.  Block sizes, all kernels specialised, counts / report + counts / row log in ms per 1e8 persons:
+// 256 x 2: 3.25 / 5.31 / 5.03; 288 x 2: 3.45 / 5.34 / 5.20; 320 x 2: 3.11 / 4.79 / 4.84; 352 x 2: 3.26 / 5.25 / 5.21;
+// 384 x 2 (80 registers, spills): 2.99 / 4.92 / 4.90.  (Warps per SM that are not a multiple of 4 leave the four
+// schedulers unevenly loaded.)
 constexpr unsigned OUT_RUNTIME = 0xffu;
 template <unsigned OUT>
 struct StagedEnvT {
@@ -289,14 +295,9 @@ struct StagedEnvT {
   __device__ __forceinline__ void report(int state, int kind, double lhs, double rhs) {
     if (out() & 2u) {
       // (a short form of the cells for a person's first interval — no left partial, no left exponential — was tried
-      // here: 5.99 against 5.56 ms per 1e8 persons; the second copy of the cell code costs more in instruction
-      // fetch and scheduling than the arithmetic it skips)
-#ifdef MSIM_FIRST_SHORT
-      const ReportCells c = (lhs == 0.0 && geom->part[geom->bin0] == 0.0) ? report_cells_first(*geom, cursor, state, kind, rhs)
-                                                                           : report_cells(*geom, cursor, state, kind, lhs, rhs);
-#else
+      // here, twice: 5.99 against 5.56 ms per 1e8 persons with the run-time-flag kernel, 4.93 against 4.77 with this
+      // one; the second copy of the cell code costs more in instruction fetch and scheduling than the arithmetic it skips)
       const ReportCells c = report_cells(*geom, cursor, state, kind, lhs, rhs);
-#endif
       acc.add(c, geom->discount_rate != 0.0);
       if (out() & 8u) current += report_brief(*geom, c, lhs, rhs);  // addBrief, microsimulation.h:929-932
     }

@@ -287,41 +287,6 @@ MSIM_HD ReportCells report_cells(const ReportGeom &g, ReportCursor &cur, int sta
   return c;
 }
 
-#ifdef MSIM_FIRST_SHORT
-// report_cells for a person's FIRST interval when it starts on a partition point (lhs = startTime = 0 = part[bin0],
-// true): no left partial overlap, no left exponential, the first completely covered bin is bin0 — the same
-// cells report_cells computes for that case, without the work of finding that out.  Every person has a first
-// interval and four in five have no other, so this is the common path (person_staged.cuh).
-MSIM_HD ReportCells report_cells_first(const ReportGeom &g, ReportCursor &cur, int state, int event, double rhs) {
-  const int nb = g.n_bin;
-  const bool disc = g.discount_rate != 0.0;
-  ReportCells c;
-  const int lo = g.bin0, hi = report_bin(g, rhs);
-  const double erhs = disc ? report_decay(g, rhs) : 1.0;
-  cur.t = rhs;
-  cur.e = erhs;
-  cur.bin = hi;
-  cur.valid = true;
-  c.e_lhs = 1.0;
-  c.e_rhs = erhs;
-  const int row = state * nb;
-  const double phi = report_part(g, hi);  // (= 0 = lhs when hi == bin0)
-  c.state = state;
-  c.event = event;
-  c.bin_hi = hi;
-  c.bin_f0 = lo;
-  c.i_events = g.off_events + (state * g.n_event + event) * nb + hi;
-  c.i_dstart = g.off_dstart + row + lo;
-  c.row_hi = row + hi;
-  c.row_lo = -1;
-  c.pt_lo = c.ut_lo = 0.0;
-  c.pt_hi = rhs - phi;
-  c.ut_hi = disc ? report_discounted_e(g, phi, rhs, g.edge_decay[hi], erhs) : 0.0;
-  c.noedge = !(phi < rhs);
-  return c;
-}
-
-#endif
 // EventReport::addBrief (microsimulation.h:929-932): what the interval [lhs, rhs] adds to the individual's running
 // discounted total, which counts from startReportAge on: discountedUtilities(max(lhs - sra, 0), rhs - sra) with
 // utility 1.  exp(-alpha (t - sra)) = exp(-alpha t) exp(alpha sra): the interval's own exponentials are reused.

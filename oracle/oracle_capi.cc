@@ -15,6 +15,7 @@
 #include "gsm_lite.h"
 #include "lookups_lite.h"
 #include "reports_lite.h"
+#include "../examples/plugins/screening_skeleton.h"
 
 using namespace orc;
 
@@ -366,6 +367,137 @@ int oracle_cost_report(double rate, double start_age, double p_start, double p_f
     out_rows[3 * k + 2] = it->second;
   }
   return (int)k;
+}
+
+// ---- the screening-model skeleton (examples/plugins/screening_skeleton.h): Rpexp + Table + NumericInterpolate + gsm +
+// EventReport in one model, restated on the oracle's building blocks.  Person i draws from substream
+// first_person + i + 1 of a stream made from the package seed.
+namespace scr {
+using namespace ssim;
+// R::rnormPos (src/microsimulation.cc:103-107): a normal draw conditioned on being non-negative, by rejection
+static double rnormPos(double mean, double sd) {
+  double x;
+  while ((x = R::rnorm(mean, sd)) < 0.0) {
+  }
+  return x;
+}
+struct Model {
+  const screening_inputs *in;
+  orc::Rpexp *mortality;
+  orc::Table *biopsy;
+  orc::NumericInterpolate *sensitivity, *survival;
+  orc::gsm *sojourn;
+  EventReport<short, short> *report;
+};
+class Person : public cProcess {
+ public:
+  Model *M;
+  int state, grade;
+  bool dx, screen_dx;
+  double age_o, beta0, beta1, beta2, eps, age_dx;
+  Person(Model *m) : M(m) {}
+  void init() {
+    const screening_inputs &p = *M->in;
+    state = SCR_Healthy;
+    dx = screen_dx = false;
+    age_dx = 0.0;
+    age_o = 35.0 + sqrt(-2.0 * log(R::runif(0.0, 1.0)) / p.g0);
+    grade = (R::runif(0.0, 1.0) < 0.006 * (age_o - 35.0)) ? 1 : 0;
+    beta0 = R::rnorm(p.mubeta0, p.sebeta0);
+    beta1 = rnormPos(p.mubeta1, p.sebeta1);
+    beta2 = rnormPos(p.mubeta2[grade], p.sebeta2[grade]);
+    eps = R::rnorm(0.0, p.tau2);
+    scheduleAt(M->mortality->rand(R::runif(0.0, 1.0)), SCR_toOtherDeath);
+    scheduleAt(age_o, SCR_toLocalised);
+    if (p.screen > 0) scheduleAt(50.0, SCR_toScreen);
+  }
+  void handleMessage(const cMessage *msg) {
+    const screening_inputs &p = *M->in;
+    M->report->add((short)state, msg->kind, previous(), now());
+    switch (msg->kind) {
+      case SCR_toOtherDeath:
+      case SCR_toCancerDeath:
+        Sim::stop_simulation();
+        break;
+      case SCR_toLocalised:
+        state = SCR_Localised;
+        scheduleAt(now() + M->sojourn->randU(R::runif(0.0, 1.0), 0.0, grade), SCR_toClinicalDiagnosis);
+        break;
+      case SCR_toScreen: {
+        const double psa = exp(std::min(log(20.0), beta0 + beta1 * (now() - 35.0) + beta2 * std::max(0.0, now() - age_o) + eps));
+        if (psa >= p.psa_threshold) {
+          std::vector<double> key(2);
+          key[0] = psa;
+          key[1] = now();
+          if (R::runif(0.0, 1.0) < p.compliance * (*M->biopsy)(key)) scheduleAt(now(), SCR_toBiopsy);
+        }
+        if (now() + p.screen <= 70.0) scheduleAt(now() + p.screen, SCR_toScreen);
+        break;
+      }
+      case SCR_toBiopsy:
+        if (state == SCR_Localised && R::runif(0.0, 1.0) < (*M->sensitivity)(p.cohort + now())) scheduleAt(now(), SCR_toScreenDiagnosis);
+        break;
+      case SCR_toClinicalDiagnosis:
+      case SCR_toScreenDiagnosis:
+        if (!dx) {
+          dx = true;
+          screen_dx = msg->kind == SCR_toScreenDiagnosis;
+          age_dx = now();
+          state = SCR_Diagnosed;
+          RemoveKind(SCR_toScreen);
+          RemoveKind(SCR_toBiopsy);
+          RemoveKind(SCR_toClinicalDiagnosis);
+          RemoveKind(SCR_toScreenDiagnosis);
+          const double u = R::runif(0.0, 1.0);
+          if (u >= p.surv_value[p.n_surv - 1]) scheduleAt(now() + M->survival->invert_decreasing(u), SCR_toCancerDeath);
+        }
+        break;
+      default:
+        break;
+    }
+  }
+};
+}  // namespace scr
+
+int oracle_screening_skeleton(const screening_inputs *in, int64_t first_person, int64_t n, double discount_rate, msim_report *report,
+                              double *values) {
+  using namespace scr;
+  orc::Rpexp mortality(in->mort_rate, in->mort_age, in->n_mort);
+  orc::Table biopsy(2);
+  for (int i = 0; i < in->n_biopsy; i++) {
+    std::vector<double> key(in->biopsy_rows + 3 * i, in->biopsy_rows + 3 * i + 2);
+    biopsy.insert(key, in->biopsy_rows[3 * i + 2]);
+  }
+  orc::NumericInterpolate sensitivity(in->sens_year, in->sens_value, in->n_sens), survival(in->surv_time, in->surv_value, in->n_surv);
+  orc::gsm sojourn = make_gsm(in->gsm);
+  ssim::EventReport<short, short> rep(discount_rate);
+  std::vector<double> ages;
+  for (int a = 0; a <= 100; a++) ages.push_back(a);
+  ages.push_back(1.0e+6);
+  rep.clear();
+  rep.setPartition(ages);
+  Model M = {in, &mortality, &biopsy, &sensitivity, &survival, &sojourn, &rep};
+  rlite::RNGkind(rlite::USER_UNIF);
+  rlite::set_user_unif_rand(ssim::user_unif_rand);
+  ssim::Rng *rng = new ssim::Rng();
+  rng->set();
+  if (first_person > 0) rng->AdvanceSubstream(0, (int32_t)first_person);
+  Person person(&M);
+  for (int64_t i = 0; i < n; i++) {
+    rng->nextSubstream();
+    ssim::Sim::create_process(&person);
+    ssim::Sim::run_simulation();
+    values[SCR_N_VALUES * i + 0] = ssim::now();
+    values[SCR_N_VALUES * i + 1] = person.age_dx;
+    values[SCR_N_VALUES * i + 2] = person.screen_dx ? 1.0 : 0.0;
+    values[SCR_N_VALUES * i + 3] = person.grade;
+    ssim::Sim::clear();
+  }
+  delete rng;
+  ReportTables rt;
+  flatten(rep, &rt);
+  fill_report(rt, report);
+  return 0;
 }
 
 // ---- survival-time utilities and lookup tables (lookups_lite.h); modes as in include/msim.h
