@@ -273,6 +273,18 @@ class Oracle:
         self.lib.oracle_report_free(C.byref(r))
         return d
 
+    def screening_skeleton(self, inputs, n, first_person=0, discount_rate=0.0):
+        """The screening-model skeleton (examples/plugins/screening_skeleton.h) on the oracle's building blocks:
+        (report tables, values n x 4: age at death, age at diagnosis, screen-detected, grade)."""
+        r = Report()
+        values = np.zeros((max(n, 1), 4))
+        rc = self.lib.oracle_screening_skeleton(C.byref(inputs), C.c_int64(first_person), C.c_int64(n), C.c_double(discount_rate),
+                                                C.byref(r), values.ctypes.data_as(C.POINTER(C.c_double)))
+        assert rc == 0
+        d = r.to_dict()
+        self.lib.oracle_report_free(C.byref(r))
+        return d, values[:n]
+
     # ---- generalised survival model (gsm_lite); `model` is a ctypes msim_gsm (include/msim.h), passed by reference
     def _gsm(self, fn, model, u, extra, index, scale):
         u = np.ascontiguousarray(u, dtype=np.float64)
