@@ -84,3 +84,23 @@ def test_port_matches_committed_fixtures(oracle, golden):
     c = oracle.callCalibrationPerson(12345, 20000)
     for k, v in c.items():
         assert np.array_equal(v, golden["calib_seed12345_n20000_" + k])
+
+
+def test_reference_engine_cannot_hold_two_processes(tmp_path):
+    """SURVEY 8(f) 4 (multi-process simulations, cProcess::send): the reference's current engine cannot run them — the
+    second create_process compares two A_Init actions whose events are null (src/ssim.cc:60-62, 108-113) and
+    dereferences null.  So there is no reference behaviour to be in parity with; DESIGN.md section 8."""
+    import subprocess
+    from oracle import pyoracle
+    if not os.path.isdir(pyoracle.REF_ROOT):
+        pytest.skip("the reference tree is not on this machine")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "two")
+    r = subprocess.run(["g++", "-O0", "-std=gnu++17", "-Wno-deprecated", "-I" + os.path.join(root, "oracle", "shim"),
+                        "-I" + os.path.join(pyoracle.REF_ROOT, "inst", "include"), "-o", exe,
+                        os.path.join(root, "tests", "manual", "probe_two_processes.cc"),
+                        os.path.join(pyoracle.REF_ROOT, "src", "ssim.cc")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert "one created" in run.stdout and "two created" not in run.stdout
+    assert run.returncode != 0   # killed by SIGSEGV
