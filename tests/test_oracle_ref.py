@@ -90,6 +90,7 @@ def test_reference_engine_cannot_hold_two_processes(tmp_path):
     """SURVEY 8(f) 4 (multi-process simulations, cProcess::send): the reference's current engine cannot run them — the
     second create_process compares two A_Init actions whose events are null (src/ssim.cc:60-62, 108-113) and
     dereferences null.  So there is no reference behaviour to be in parity with; DESIGN.md section 8."""
+    import os
     import subprocess
     from oracle import pyoracle
     if not os.path.isdir(pyoracle.REF_ROOT):
