@@ -93,8 +93,13 @@ int64_t msim_launch_count(void);
  * through, the kernel every other model uses).  The calibration and Sick-Sicker
  * models keep their pending actions in an ordered array under 0 (a run in which
  * two pending actions compared equal is repeated with the heap) and in heap.h's
- * binary heap under 1.  Same results either way; the switch exists so tests can
- * check exactly that.  2 = 0 with the repeat taken unconditionally (tests). */
+ * binary heap under 1.  The calibration sweep under 0 computes every person's
+ * draws once for all parameter sets and needs no event queue
+ * (csrc/calib_shared.cuh; sweeps it cannot run, and runs in which two event
+ * times of a person were equal, go through the event queue); 3 = as 0, but
+ * the calibration sweep always goes through the event queue (ordered array).
+ * Same results either way; the switch exists so tests can check exactly
+ * that.  2 = 0 with the repeat taken unconditionally (tests). */
 int msim_set_person_schedule(int which);
 /* R's Mersenne-Twister stream is generated in parallel segments started by jump-ahead when the table of jump
  * polynomials (mt_jump.bin, next to the library; written at build time) is present and the stream is long; 0

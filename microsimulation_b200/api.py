@@ -51,10 +51,12 @@ def set_stream(cuda_stream=None):
 
 
 def set_person_schedule(which):
-    """0 / "staged" (default) or 1 / "generic": which GPU schedule runs person-r, and whether the calibration model
-    keeps its pending actions in an ordered array (0) or the binary heap (1).  Same results either way.  2 / "repeat"
-    is 0 with the repeat paths forced (tests)."""
-    which = {"staged": 0, "generic": 1, "repeat": 2}.get(which, which)
+    """0 / "staged" (default) or 1 / "generic": which GPU schedule runs person-r, and how the calibration and Sick-Sicker
+    models keep their pending actions: 0 = the calibration sweep computes each person's draws once for all parameter
+    sets and needs no queue (csrc/calib_shared.cuh), Sick-Sicker uses an ordered array; 1 = the binary heap;
+    3 / "queue" = as 0, but the calibration sweep goes through the event loop with an ordered array.  Same results
+    either way.  2 / "repeat" is 0 with the repeat paths forced (tests)."""
+    which = {"staged": 0, "generic": 1, "repeat": 2, "queue": 3}.get(which, which)
     check(load().msim_set_person_schedule(C.c_int(int(which))))
 
 

@@ -1,0 +1,280 @@
+// Calibration sweep (BASELINE configs[4], R/calibSim.R:10-40) with the random draws SHARED between parameter sets.
+//
+// Every parameter set of a sweep is simulated from the same substreams (common random numbers: callCalibrationSimulation
+// re-seeds with one seed for all sets, R/calibSim.R:12-14, calibperson-r.cc:180-193).  The model (calibperson-r.cc:95-171)
+// takes its draws in an order that does not depend on the parameters:
+//
+//   init():         runif (diseasepot), norm_rand (lam1), exp_rand (time to precursor), runif (Gumbel time of death)
+//   toPrecursor:    exp_rand (dwell time to pre-clinical)         — only if diseasepot and the person is still alive
+//   toPreClinical:  norm_rand (dwell time to clinical)            — only after toPrecursor's draw
+//
+// (rnorm(mu, sigma) = mu + sigma * norm_rand() and rexp(scale) = scale * exp_rand(): the parameters scale the draws, they
+// do not change how many uniforms are taken — except rnorm with sigma == 0, which draws nothing; the host sends sweeps
+// with such a set to the event-queue kernels.)  So person i's six variates are the same numbers in every set, and a
+// block computes them ONCE per person (phase 1: one person per thread, full warps) and then runs all its parameter
+// sets over them (phase 2: one SET per thread, the person's variates read from shared memory by broadcast).
+//
+// Phase 2 needs no event queue either.  The model's events are one chain — toPrecursor -> toPreClinical -> toClinical,
+// each scheduled by its predecessor's handler — racing one toDeath and crossing a fixed ladder of Count events at
+// 10, 20, .., 100.  With all event times distinct, Sim::run_simulation's pop order IS the order of the times, so the
+// stage at every Count and the clinical time at death follow from comparisons of t1 <= t2 <= t3 with tD and the
+// ladder (straight_life below).  Where two of those times are EQUAL the pop order is heap.h's business (it depends
+// on the heap's shape): such a person raises the tie flag and the host repeats the sweep with the binary-heap kernel
+// (calib_kernel<false>), exactly as the ordered-array kernel does.  Times are computed with the engine's own
+// roundings (scheduleAt: clock + (t - clock), microsimulation.h:347 + ssim.cc:97).
+//
+// Occupancy is kept as histograms of c1 <= c2 <= c3 <= nC — the number of Count events a person sees before each
+// transition and before death (nC does not depend on the parameters) — in per-thread columns of shared memory (no
+// atomics), turned into the report's occupancy[stage][decade] when the block ends:
+//   DiseaseFree[k] = #(k < c1), Precursor[k] = #(c1 <= k < c2), PreClinical[k] = #(c2 <= k < c3), Clinical[k] = #(c3 <= k < nC).
+// Most persons never leave Precursor, so c2 and c3 are stored as differences from nC.
+//
+// Same output vector as calib_kernel (kernels.cuh): [set][48].
+#pragma once
+#include "models.cuh"
+#ifdef __CUDACC__
+#include "kernels.cuh"
+#endif
+
+namespace msim {
+namespace calib {
+
+// what one person takes from its substream, in stream order (tD: the Gumbel time of death, already transformed)
+struct Draws {
+  double u0, z1, e1, tD, e2, z2;
+};
+
+template <class Src>
+MSIM_DEV Draws draw_person(Src &src) {
+  RMath<Src> R(&src);
+  Draws d;
+  d.u0 = R.runif(0, 1);
+  d.z1 = R.norm_rand();
+  d.e1 = R.exp_rand();
+  const double x = R.runif(0, 1);
+  d.tD = 65 - 15 * fm_log(-fm_log(x));  // calibperson-r.cc:105-106
+  d.e2 = R.exp_rand();
+  d.z2 = R.norm_rand();
+  return d;
+}
+
+// number of Count events (at 10, 20, .., 100) strictly before time t >= 0; *tie is set if t coincides with one
+MSIM_HD int counts_before(double t, bool *tie) {
+  const double tc = t < 105.0 ? t : 105.0;
+  int a = (int)(tc * 0.1);  // floor(t / 10) give or take one; 10 * a is exact, so the two steps below settle it
+  if (a > 0 && !((double)(10 * a) < t)) a--;
+  if (a < 10 && (double)(10 * (a + 1)) < t) a++;
+  if (a < 10 && (double)(10 * (a + 1)) == t) *tie = true;
+  return a;
+}
+
+struct SetPar {
+  double Lam1, sigm1, p2, lam2, mu3, sd3;  // sd3 = tau3 * mu3, the sigma handed to rnorm (calibperson-r.cc:150)
+};
+
+// Sweeps the straight-line form can run: every draw is taken in every set (no rnorm with sigma == 0) and no event
+// is scheduled in the past (lam2 >= 0); anything else goes through the event queue.
+inline bool straight_ok(const double par[6]) {
+  for (int k = 0; k < 6; k++)
+    if (!(par[k] - par[k] == 0.0)) return false;  // NaN or infinite
+  return par[1] != 0.0 && par[5] * par[4] != 0.0 && par[3] >= 0.0;
+}
+
+// One person under one parameter set.  c1, c2, c3: Count events seen before toPrecursor / toPreClinical / toClinical
+// (capped at nC, the number seen before death); clin: clinTime as the toDeath handler leaves it (calibperson-r.cc:120).
+MSIM_HD void straight_life(const Draws &d, int nC, const SetPar &P, int *c1, int *c2, int *c3, double *clin, bool *tie) {
+  const double lam1 = fm_exp(P.Lam1 + P.sigm1 * d.z1);
+  const double t1 = lam1 * d.e1;  // scheduled from time 0: 0 + (t1 - 0) == t1
+  if (t1 == d.tD) *tie = true;
+  const int m1 = counts_before(t1, tie);
+  *c1 = m1 < nC ? m1 : nC;
+  *c2 = nC;
+  *c3 = nC;
+  *clin = d.tD;
+  if (d.u0 < P.p2 && t1 < d.tD) {
+    const double dwell = t1 + P.lam2 * d.e2;
+    const double t2 = t1 + (dwell - t1);
+    if (t2 == d.tD) *tie = true;
+    const int m2 = counts_before(t2, tie);
+    *c2 = m2 < nC ? m2 : nC;
+    if (t2 < d.tD) {
+      const double dwell3 = t2 + fm_exp(P.mu3 + P.sd3 * d.z2);
+      const double t3 = t2 + (dwell3 - t2);
+      if (t3 == d.tD) *tie = true;
+      const int m3 = counts_before(t3, tie);
+      *c3 = m3 < nC ? m3 : nC;
+      if (t3 < d.tD) *clin = t3;
+    }
+  }
+}
+
+}  // namespace calib
+
+#ifdef __CUDACC__
+
+constexpr int CS_BINS = 11;  // c in 0..10
+
+struct CalibSharedParams {
+  StreamStart st;  // stride = M^(gridDim.x*BLOCK)
+  int64_t n;
+  const double *runpar;  // [n_sets][6]
+  double *out;           // [n_sets][48], as calib_kernel's
+  int set0;              // first parameter set of this launch
+  int n_here;            // sets of this launch; blockIdx.y covers sets [set0 + y*spb, set0 + min((y+1)*spb, n_here))
+  int spb;               // sets per block (<= BLOCK)
+  int *tie;
+  double *partial;       // [n_here][gridDim.x][4]
+};
+
+// dynamic shared memory: 6 x BLOCK doubles (draws; reused for the TimeAtRisk reduction), BLOCK ints (nC),
+// 3 x CS_BINS x BLOCK ints (histograms, one column per thread)
+constexpr size_t CS_SMEM = sizeof(double) * 6 * BLOCK + sizeof(int) * BLOCK + sizeof(int) * 3 * CS_BINS * BLOCK;
+
+__global__ void __launch_bounds__(BLOCK) calib_shared_kernel(CalibSharedParams p) {
+  extern __shared__ __align__(16) unsigned char cs_raw[];
+  double *s_d = reinterpret_cast<double *>(cs_raw);  // [6][BLOCK]
+  int *s_nC = reinterpret_cast<int *>(s_d + 6 * BLOCK);
+  int *s_h = s_nC + BLOCK;  // [3][CS_BINS][BLOCK]
+  __shared__ int s_histN[CS_BINS];
+  __shared__ int s_tie;
+  const int tid = threadIdx.x;
+  const int set_first = blockIdx.y * p.spb;
+  const int n_sets_blk = min(p.spb, p.n_here - set_first);  // >= 1
+  const int G = BLOCK / n_sets_blk;                         // person groups
+  const bool active = tid < G * n_sets_blk;
+  const int s = tid % n_sets_blk, g = tid / n_sets_blk;
+  for (int k = tid; k < 3 * CS_BINS * BLOCK; k += BLOCK) s_h[k] = 0;
+  if (tid < CS_BINS) s_histN[tid] = 0;
+  if (tid == 0) s_tie = 0;
+
+  calib::SetPar P;
+  {
+    const double *rp = p.runpar + 6 * (size_t)(p.set0 + set_first + (active ? s : 0));
+    P.Lam1 = rp[0];
+    P.sigm1 = rp[1];
+    P.p2 = rp[2];
+    P.lam2 = rp[3];
+    P.mu3 = rp[4];
+    P.sd3 = rp[5] * rp[4];
+  }
+  double tar0 = 0.0, tar1 = 0.0, tar2 = 0.0, tar3 = 0.0, cmax = -1.0;
+  bool tie = false;
+  int *h1 = s_h + tid, *d2 = s_h + CS_BINS * BLOCK + tid, *d3 = s_h + 2 * CS_BINS * BLOCK + tid;
+
+  MrgSource src;
+  Mrg32k3a sub = thread_start_state(p.st, blockIdx.x * BLOCK + tid);
+  const int64_t stride = (int64_t)gridDim.x * BLOCK;
+  for (int64_t base = (int64_t)blockIdx.x * BLOCK; base < p.n; base += stride) {
+    __syncthreads();  // the previous tile has been read (and the zeroing above is done)
+    // ---- phase 1: this thread's person
+    {
+      const int64_t idx = base + tid;
+      double tD = -1.0;
+      if (idx < p.n) {
+        src.g = sub;
+        const calib::Draws d = calib::draw_person(src);
+        bool t0 = false;
+        const int nC = calib::counts_before(d.tD, &t0);
+        if (t0) tie = true;
+        s_d[0 * BLOCK + tid] = d.u0;
+        s_d[1 * BLOCK + tid] = d.z1;
+        s_d[2 * BLOCK + tid] = d.e1;
+        s_d[4 * BLOCK + tid] = d.e2;
+        s_d[5 * BLOCK + tid] = d.z2;
+        s_nC[tid] = nC;
+        atomicAdd(&s_histN[nC], 1);
+        tD = d.tD;
+      }
+      s_d[3 * BLOCK + tid] = tD;
+      sub.jump(p.st.stride);
+    }
+    __syncthreads();
+    // ---- phase 2: this thread's parameter set over the tile's persons (every G-th, from g)
+    if (active) {
+      for (int j = g; j < BLOCK; j += G) {
+        calib::Draws d;
+        d.tD = s_d[3 * BLOCK + j];
+        if (d.tD < 0.0) break;  // past the last person (persons of a tile are in index order)
+        d.u0 = s_d[0 * BLOCK + j];
+        d.z1 = s_d[1 * BLOCK + j];
+        d.e1 = s_d[2 * BLOCK + j];
+        d.e2 = s_d[4 * BLOCK + j];
+        d.z2 = s_d[5 * BLOCK + j];
+        const int nC = s_nC[j];
+        int c1, c2, c3;
+        double c;
+        calib::straight_life(d, nC, P, &c1, &c2, &c3, &c, &tie);
+        h1[c1 * BLOCK] += 1;
+        if (c2 != nC) {
+          d2[c2 * BLOCK] += 1;
+          d2[nC * BLOCK] -= 1;
+        }
+        if (c3 != nC) {
+          d3[c3 * BLOCK] += 1;
+          d3[nC * BLOCK] -= 1;
+        }
+        // TimeAtRisk, calibperson-r.cc:124-135
+        tar0 += fmin(20.0, c);
+        if (!(c < 20.0)) {
+          tar1 += fmin(40.0, c);
+          if (!(c < 40.0)) {
+            tar2 += fmin(60.0, c);
+            if (!(c < 60.0)) tar3 += fmin(80.0, c);
+          }
+        }
+        cmax = fmax(cmax, c);
+      }
+    }
+  }
+  if (tie) s_tie = 1;
+  __syncthreads();
+
+  // ---- the block's results.  TimeAtRisk first (the draws' area is free now): [BLOCK][5] = four sums and cmax
+  double *s_t = s_d;
+  s_t[tid * 5 + 0] = tar0;
+  s_t[tid * 5 + 1] = tar1;
+  s_t[tid * 5 + 2] = tar2;
+  s_t[tid * 5 + 3] = tar3;
+  s_t[tid * 5 + 4] = active ? cmax : -1.0;
+  __syncthreads();
+  if (tid < n_sets_blk) {
+    const int set_local = set_first + tid;  // within this launch
+    double *out = p.out + 48 * (size_t)(p.set0 + set_local);
+    // histograms: sum the groups' columns, then cumulate
+    int F1 = 0, D2 = 0, D3 = 0, FN = 0, N = 0;
+    for (int b = 0; b < CS_BINS; b++) N += s_histN[b];
+    for (int k = 0; k < 10; k++) {
+      int a1 = 0, a2 = 0, a3 = 0;
+      for (int gg = 0; gg < G; gg++) {
+        const int col = gg * n_sets_blk + tid;
+        a1 += s_h[k * BLOCK + col];
+        a2 += s_h[(CS_BINS + k) * BLOCK + col];
+        a3 += s_h[(2 * CS_BINS + k) * BLOCK + col];
+      }
+      F1 += a1;  // #(c1 <= k)
+      D2 += a2;  // #(c2 <= k) - #(nC <= k)
+      D3 += a3;
+      FN += s_histN[k];
+      const int occ[4] = {N - F1, F1 - (FN + D2), D2 - D3, D3};  // F2 = FN + D2, F3 = FN + D3; Clinical = F3 - FN
+      for (int st = 0; st < 4; st++)
+        if (occ[st]) atomicAdd(&out[st * 10 + k], (double)occ[st]);
+    }
+    double t[4] = {0.0, 0.0, 0.0, 0.0}, cm = -1.0;
+    for (int gg = 0; gg < G; gg++) {  // fixed order: the sums do not depend on timing
+      const int col = gg * n_sets_blk + tid;
+      for (int k = 0; k < 4; k++) t[k] += s_t[col * 5 + k];
+      cm = fmax(cm, s_t[col * 5 + 4]);
+    }
+    double *q = p.partial + ((size_t)set_local * gridDim.x + blockIdx.x) * 4;
+    for (int k = 0; k < 4; k++) q[k] = t[k];
+    if (cm >= 0.0) {
+      const int reached = 1 + (cm >= 20.0) + (cm >= 40.0) + (cm >= 60.0);
+      for (int k = 0; k < reached; k++) atomicAdd(&out[44 + k], 1.0);
+    }
+  }
+  if (tid == 0 && s_tie) *p.tie = 1;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace msim

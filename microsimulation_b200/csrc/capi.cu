@@ -20,6 +20,7 @@
 #include "host_person.h"
 #include "host_runtime.h"
 #include "host_summary.h"
+#include "calib_shared.cuh"
 #include "microbench.cuh"
 
 using namespace msim;
@@ -118,7 +119,8 @@ int msim_set_mt_parallel(int on) {
 }
 
 int msim_set_person_schedule(int which) {
-  if (which < 0 || which > 2) return fail(MSIM_ERR_ARG, "schedule must be 0 (staged), 1 (generic) or 2 (test: 0 with the repeat paths forced)");
+  if (which < 0 || which > 3)
+    return fail(MSIM_ERR_ARG, "schedule must be 0 (default), 1 (generic / binary heap), 2 (test: 0 with the repeat paths forced) or 3 (as 0, calibration through the event queue)");
   g.person_kernel = which;
   return MSIM_OK;
 }
@@ -281,46 +283,81 @@ static int calibration_run(const double seed[6], int64_t first_person, int64_t n
   if ((rc = ensure(g.calib_out, sizeof(double) * 48 * n_sets))) return rc;
   if ((rc = ensure(g.small, 16 * sizeof(double)))) return rc;
   CK(cudaMemcpyAsync(g.calib_par.p, runpar, sizeof(double) * 6 * n_sets, cudaMemcpyHostToDevice, g.stream));
-  CalibParams p;
-  memset(&p, 0, sizeof p);
-  int64_t tiles = (n + BLOCK - 1) / BLOCK;
-  // enough blocks per set to fill the GPU even for few sets, no more than the work
-  int64_t want = std::max<int64_t>(1, ((int64_t)g.sm_count * 8 + std::max(n_here, 1) - 1) / std::max(n_here, 1));
-  int grid_x = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, tiles), 2048));
   uint32_t state[6];
   seed_to_u32(seed, state);
-  stream_start(state, first_person, (int64_t)grid_x * BLOCK, &p.st);
-  p.n = n;
-  p.n_sets = n_sets;
-  p.set0 = set_lo;
-  p.runpar = (const double *)g.calib_par.p;
-  p.out = (double *)g.calib_out.p;
-  p.error = small_view().error;
-  p.tie = (int *)((double *)g.small.p + 13);
-  if ((rc = ensure(g.calib_partial, sizeof(double) * 4 * (size_t)grid_x * std::max(n_here, 1)))) return rc;
-  p.partial = (double *)g.calib_partial.p;
+  int *tie_flag = (int *)((double *)g.small.p + 13);
   g.last_calib_sets = n_sets;
-  // Schedule 0 keeps the pending actions in an ordered array (engine.cuh, OrderedEvents), which pops in the heap's
-  // order unless two pending actions compare equal; a run that saw such a pair is repeated with the binary heap
-  // (schedule 1).  Schedule 2 (tests) takes the repeat path unconditionally.
-  for (int attempt = g.person_kernel == 1 ? 1 : 0; attempt < 2; attempt++) {
+  const int64_t tiles = (n + BLOCK - 1) / BLOCK;
+  // Three kernels, same results.  SHARED (calib_shared.cuh): the persons' draws are computed once and every parameter
+  // set runs over them, without an event queue; ORDERED / HEAP (calib_kernel): every (person, set) pair through
+  // the event loop, pending actions in an ordered array / in heap.h's binary heap.  SHARED and ORDERED are exact
+  // unless two of a person's event times are equal, which they report; such a sweep is repeated with HEAP.
+  // Schedule 0: SHARED where the parameters allow it (calib::straight_ok), else ORDERED; 3: ORDERED; 1: HEAP;
+  // 2 (tests): as 0 with the repeat taken unconditionally.
+  enum { K_SHARED, K_ORDERED, K_HEAP };
+  bool straight = n_here > 0;
+  for (int s = set_lo; s < set_hi; s++) straight = straight && calib::straight_ok(runpar + 6 * (size_t)s);
+  const int first = g.person_kernel == 1 ? K_HEAP : (g.person_kernel == 3 || !straight) ? K_ORDERED : K_SHARED;
+  for (int kind = first;;) {
     CK(cudaMemsetAsync(g.calib_out.p, 0, sizeof(double) * 48 * n_sets, g.stream));
     CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
     CK(cudaEventRecord(g.ev0, g.stream));
     if (n > 0 && n_here > 0) {
-      if (attempt == 0) calib_kernel<true><<<dim3(grid_x, n_here), BLOCK, 0, g.stream>>>(p);
-      else calib_kernel<false><<<dim3(grid_x, n_here), BLOCK, 0, g.stream>>>(p);
+      int grid_x;
+      if (kind == K_SHARED) {
+        // a block = up to BLOCK parameter sets x a share of the person tiles; 4 blocks fit an SM (shared memory)
+        const int n_chunks = (n_here + BLOCK - 1) / BLOCK;
+        CalibSharedParams p;
+        memset(&p, 0, sizeof p);
+        grid_x = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, std::max(1, g.sm_count * 4 / n_chunks)));
+        stream_start(state, first_person, (int64_t)grid_x * BLOCK, &p.st);
+        p.n = n;
+        p.runpar = (const double *)g.calib_par.p;
+        p.out = (double *)g.calib_out.p;
+        p.set0 = set_lo;
+        p.n_here = n_here;
+        p.spb = (n_here + n_chunks - 1) / n_chunks;
+        p.tie = tie_flag;
+        if ((rc = ensure(g.calib_partial, sizeof(double) * 4 * (size_t)grid_x * n_here))) return rc;
+        p.partial = (double *)g.calib_partial.p;
+        static bool attr_set = false;
+        if (!attr_set) {
+          CK(cudaFuncSetAttribute(calib_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM));
+          attr_set = true;
+        }
+        calib_shared_kernel<<<dim3(grid_x, n_chunks), BLOCK, CS_SMEM, g.stream>>>(p);
+      } else {
+        CalibParams p;
+        memset(&p, 0, sizeof p);
+        // enough blocks per set to fill the GPU even for few sets, no more than the work
+        const int64_t want = std::max<int64_t>(1, ((int64_t)g.sm_count * 8 + n_here - 1) / n_here);
+        grid_x = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, tiles), 2048));
+        stream_start(state, first_person, (int64_t)grid_x * BLOCK, &p.st);
+        p.n = n;
+        p.n_sets = n_sets;
+        p.set0 = set_lo;
+        p.runpar = (const double *)g.calib_par.p;
+        p.out = (double *)g.calib_out.p;
+        p.error = small_view().error;
+        p.tie = tie_flag;
+        if ((rc = ensure(g.calib_partial, sizeof(double) * 4 * (size_t)grid_x * n_here))) return rc;
+        p.partial = (double *)g.calib_partial.p;
+        if (kind == K_ORDERED) calib_kernel<true><<<dim3(grid_x, n_here), BLOCK, 0, g.stream>>>(p);
+        else calib_kernel<false><<<dim3(grid_x, n_here), BLOCK, 0, g.stream>>>(p);
+      }
       CK(cudaGetLastError());
-      calib_fold_kernel<<<n_here, 32, 0, g.stream>>>(p.partial, grid_x, set_lo, p.out);
+      calib_fold_kernel<<<n_here, 32, 0, g.stream>>>((const double *)g.calib_partial.p, grid_x, set_lo, (double *)g.calib_out.p);
       CK(cudaGetLastError());
       g.launches += 2;
     }
     CK(cudaEventRecord(g.ev1, g.stream));
     g.timing_pending = true;
     if ((rc = finish_run(nullptr))) return rc;
+    if (kind == K_HEAP) break;
     int tie = 0;
-    CK(cudaMemcpy(&tie, p.tie, sizeof tie, cudaMemcpyDeviceToHost));
-    if (attempt == 0 && !tie && g.person_kernel != 2) break;
+    CK(cudaMemcpy(&tie, tie_flag, sizeof tie, cudaMemcpyDeviceToHost));
+    if (!tie && g.person_kernel != 2) break;
+    kind = K_HEAP;
   }
   return MSIM_OK;
 }

@@ -19,6 +19,7 @@
 #include "../../microsimulation_b200/csrc/host_state.h"
 #include "../../microsimulation_b200/csrc/fastmath.cuh"
 #include "../../microsimulation_b200/csrc/models.cuh"
+#include "../../microsimulation_b200/csrc/calib_shared.cuh"
 #include "../../microsimulation_b200/csrc/person_staged.cuh"
 #include "../../microsimulation_b200/csrc/report.cuh"
 #include "../../microsimulation_b200/csrc/report_host.h"
@@ -575,6 +576,66 @@ int emu_calibration_ordered(const double seed[6], int64_t first_person, int64_t 
                             msim_calibration *out, int *tie_out) {
   *tie_out = 0;
   return emu_calibration_t<true>(seed, first_person, n, runpar, grid, out, tie_out);
+}
+
+// The calibration sweep's straight-line form (calib_shared.cuh): every person's draws once, then every parameter set
+// over them by comparisons of the event times.  runpar = [n_sets][6], out = [n_sets]; *tie_out as above.  With
+// force_tD > 0 every person's time of death is replaced by that value (tests: event times that coincide).
+int emu_calibration_shared(const double seed[6], int64_t first_person, int64_t n, int n_sets, const double *runpar, int grid,
+                           msim_calibration *out, int *tie_out, double force_tD) {
+  *tie_out = 0;
+  StreamStart st;
+  make_start(seed, first_person + 1, grid, &st);
+  std::vector<Mrg32k3a> subs((size_t)n);
+  for (int blk = 0; blk < grid; blk++)
+    for (int tid = 0; tid < BLOCK; tid++) {
+      Mrg32k3a sub = thread_start_state(st, blk * BLOCK + tid);
+      for (int64_t idx = (int64_t)blk * BLOCK + tid; idx < n; idx += (int64_t)grid * BLOCK) {
+        subs[idx] = sub;
+        sub.jump(st.stride);
+      }
+    }
+  std::vector<calib::Draws> draws((size_t)n);
+  std::vector<int> nC((size_t)n);
+  bool tie = false;
+  for (int64_t i = 0; i < n; i++) {
+    MrgSource src;
+    src.g = subs[i];
+    draws[i] = calib::draw_person(src);
+    if (force_tD > 0) draws[i].tD = force_tD;
+    nC[i] = calib::counts_before(draws[i].tD, &tie);
+  }
+  for (int s = 0; s < n_sets; s++) {
+    const double *rp = runpar + 6 * s;
+    if (!calib::straight_ok(rp)) return -7;
+    const calib::SetPar P = {rp[0], rp[1], rp[2], rp[3], rp[4], rp[5] * rp[4]};
+    msim_calibration *o = out + s;
+    memset(o, 0, sizeof *o);
+    for (int64_t i = 0; i < n; i++) {
+      int c1, c2, c3;
+      double clin;
+      calib::straight_life(draws[i], nC[i], P, &c1, &c2, &c3, &clin, &tie);
+      for (int k = 0; k < nC[i]; k++) o->occupancy[(k < c1 ? 0 : k < c2 ? 1 : k < c3 ? 2 : 3) * 10 + k] += 1;
+      calib::time_at_risk_terms(clin, [o](int j, double v) {
+        o->time_at_risk[j] += v;
+        if (j + 1 > o->n_time_at_risk) o->n_time_at_risk = j + 1;
+      });
+    }
+    for (int stg = 0; stg < 4; stg++) {
+      double tot = 0;
+      for (int k = 0; k < 10; k++) tot += o->occupancy[stg * 10 + k];
+      o->present[stg] = tot > 0;
+    }
+  }
+  *tie_out = tie;
+  return 0;
+}
+
+int emu_counts_before(double t, int *tie_out) {
+  bool tie = false;
+  const int c = calib::counts_before(t, &tie);
+  *tie_out = tie;
+  return c;
 }
 
 // OrderedEvents against EventHeap on a random schedule/pop(/cancel) sequence (engine.cuh).  Times are drawn from

@@ -324,26 +324,60 @@ def test_calibration_sweep_vs_oracle(msim, oracle):
                 assert np.array_equal(a[k], b[k]), k
 
 
+def test_calibration_sweep_shared_draws_vs_oracle(msim, oracle):
+    """The default sweep kernel (calib_shared.cuh: a person's draws once for all parameter sets, no event queue) against
+    the oracle's event loop: 6 sets (several persons per set and block), 40 (a ragged block), 300 (two set chunks)."""
+    rs = np.random.RandomState(8)
+    base = np.array([4, 0.5, 0.3, 10, 3, 0.5])
+    for n_sets, n, first in ((6, 40000, 1000), (40, 6000, 0), (300, 1500, 77)):
+        pars = base * (1 + 0.6 * (rs.rand(n_sets, 6) - 0.5))
+        before = msim.launch_count()
+        g = msim.calibration_sweep(12345, pars, n, first_person=first)
+        assert msim.launch_count() - before == 2   # one sweep kernel + the TimeAtRisk fold: no repeat
+        r = oracle.calibration_sweep(12345, first, n, pars)
+        seen = set()
+        for a, b in zip(g, r):
+            assert set(a) == set(b)
+            seen |= set(b)
+            for k in b:
+                if k == "TimeAtRisk":
+                    np.testing.assert_allclose(a[k], b[k], rtol=1e-12)
+                else:
+                    assert np.array_equal(a[k], b[k]), (n_sets, k)
+        assert "Clinical" in seen
+
+
 def test_calibration_event_queues_agree_bit_for_bit(msim):
-    """Ordered array (default), binary heap, and the repeat path (ordered, then the heap again): identical tables,
-    TimeAtRisk included (each thread adds the same persons in the same order)."""
+    """Shared draws without a queue (default), ordered array, binary heap, and the repeat path (default, then the heap
+    again): identical integer tables; TimeAtRisk bit-identical between the event-loop kernels (each thread adds the
+    same persons in the same order) and to 1e-12 against the shared-draws kernel, which adds in another order."""
     rs = np.random.RandomState(11)
     pars = np.array([4, 0.5, 0.05, 10, 3, 0.5]) * (1 + 0.4 * (rs.rand(16, 6) - 0.5))
     runs = {}
     try:
-        for sched in ("staged", "generic", "repeat"):
+        for sched in ("staged", "queue", "generic", "repeat"):
             msim.set_person_schedule(sched)
+            before = msim.launch_count()
             runs[sched] = msim.calibration_sweep(12345, pars, 100000, first_person=77)
-            runs[sched + "_launches"] = msim.launch_count()
+            runs[sched + "_launches"] = msim.launch_count() - before
     finally:
         msim.set_person_schedule("staged")
-    assert runs["repeat_launches"] - runs["generic_launches"] == 4   # the ordered attempt and the heap repeat (+ folds)
-    assert runs["generic_launches"] - runs["staged_launches"] == 2
-    for other in ("generic", "repeat"):
+    assert runs["repeat_launches"] == 4   # the first attempt and the heap repeat (+ folds)
+    assert runs["generic_launches"] == runs["staged_launches"] == runs["queue_launches"] == 2
+    for other in ("queue", "generic", "repeat"):
         for a, b in zip(runs["staged"], runs[other]):
             assert set(a) == set(b)
             for k in a:
-                assert np.array_equal(a[k], b[k]), (other, k)
+                if k == "TimeAtRisk":
+                    np.testing.assert_allclose(a[k], b[k], rtol=1e-12)
+                else:
+                    assert np.array_equal(a[k], b[k]), (other, k)
+    for a, b in zip(runs["queue"], runs["generic"]):
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+    for a, b in zip(runs["generic"], runs["repeat"]):
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k   # the repeat path ends with the heap kernel's result
     again = msim.calibration_sweep(12345, pars, 100000, first_person=77)
     for a, b in zip(runs["staged"], again):
         for k in a:

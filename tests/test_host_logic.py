@@ -314,6 +314,67 @@ def test_emulated_calibration_ordered_queue(oracle, emu):
             assert np.array_equal(a[k], b[k]), k
 
 
+def test_count_ladder_position_is_exact(emu):
+    """calib_shared.cuh counts_before: how many Count events (10, 20, .., 100) lie strictly before t — by an estimate and
+    two exact corrections; checked against the ten comparisons at and one ulp either side of every rung."""
+    emu.emu_counts_before.restype = C.c_int
+    tie = C.c_int(0)
+    rng = np.random.default_rng(5)
+    ts = [0.0, 5e-324, 1e-300, 9.999999999999998, 1e3, 1e300, np.inf]
+    for j in range(1, 12):
+        t = float(10 * j)
+        ts += [t, np.nextafter(t, 0.0), np.nextafter(t, np.inf), np.nextafter(np.nextafter(t, 0.0), 0.0)]
+    ts += list(rng.uniform(0.0, 130.0, 20000)) + list(10.0 * rng.integers(1, 11, 2000) * (1.0 + rng.integers(-3, 4, 2000) * 2.0 ** -52))
+    for t in ts:
+        got = emu.emu_counts_before(C.c_double(t), C.byref(tie))
+        assert got == sum(10.0 * j < t for j in range(1, 11)), t
+        assert tie.value == int(any(10.0 * j == t for j in range(1, 11))), t
+
+
+def test_emulated_calibration_with_shared_draws(oracle, emu):
+    """The sweep's straight-line form (calib_shared.cuh: a person's draws once for all parameter sets, the stages from
+    comparisons of the event times) gives the event loop's tables — integer cells exactly — and flags coinciding times."""
+    seed = (C.c_double * 6)(*[10.0] * 6)
+    sets = [(4, 0.5, 0.05, 10, 3, 0.5), (3, 0.8, 0.6, 4, 1, 0.9), (2.5, 1.2, 0.9, 0.5, 0.5, 2.0), (5, 0.3, 0.2, 30, 4, 0.1),
+            (3.5, 0.7, 1.0, 0.0, 2, 0.3), (4, 0.5, 0.5, 10, -1, 0.5)]
+    flat = (C.c_double * (6 * len(sets)))(*[v for s in sets for v in s])
+    tie = C.c_int(0)
+    for first, n in ((0, 3000), (12345, 2500)):
+        got = (Calibration * len(sets))()
+        assert emu.emu_calibration_shared(seed, C.c_int64(first), C.c_int64(n), len(sets), flat, C.c_int(2), got, C.byref(tie),
+                                          C.c_double(0.0)) == 0
+        assert tie.value == 0
+        progressed = 0
+        for k, par in enumerate(sets):
+            ref = Calibration()
+            assert emu.emu_calibration(seed, C.c_int64(first), C.c_int64(n), (C.c_double * 6)(*par), C.c_int(2), C.byref(ref)) == 0
+            a, b = got[k].to_dict(), ref.to_dict()
+            assert set(a) == set(b), (k, set(a), set(b))
+            for key in b:
+                if key == "TimeAtRisk":
+                    np.testing.assert_allclose(a[key], b[key], rtol=1e-14)
+                else:
+                    assert np.array_equal(a[key], b[key]), (k, key)
+            progressed += int("Clinical" in b)
+        assert progressed >= 3  # the chain was walked to its end under several sets
+    # and against the oracle (the reference's engine restated) for one of them
+    ref = oracle.calibration_sweep(10, 12345, 2500, [list(sets[1])])[0]
+    a = got[1].to_dict()
+    for key in ref:
+        if key == "TimeAtRisk":
+            np.testing.assert_allclose(a[key], ref[key], rtol=1e-13)
+        else:
+            assert np.array_equal(a[key], ref[key]), key
+    # a death on a Count rung is a pair of equal times: flagged (the device then repeats the sweep with the heap)
+    assert emu.emu_calibration_shared(seed, C.c_int64(0), C.c_int64(10), 1, flat, C.c_int(1), got, C.byref(tie), C.c_double(70.0)) == 0
+    assert tie.value == 1
+    # sets the straight-line form must not take: rnorm with sigma == 0 draws nothing, a negative rate schedules in the past
+    for bad in ((4, 0.0, 0.05, 10, 3, 0.5), (4, 0.5, 0.05, 10, 3, 0.0), (4, 0.5, 0.05, 10, 0.0, 0.5), (4, 0.5, 0.05, -1, 3, 0.5),
+                (np.nan, 0.5, 0.05, 10, 3, 0.5), (4, 0.5, 0.05, np.inf, 3, 0.5)):
+        assert emu.emu_calibration_shared(seed, C.c_int64(0), C.c_int64(10), 1, (C.c_double * 6)(*bad), C.c_int(1), got,
+                                          C.byref(tie), C.c_double(0.0)) == -7
+
+
 @pytest.mark.parametrize("n,trt,indivp,substreams,by", [(5, 0, 1, 0, 1.0), (1000, 0, 1, 0, 1.0), (1000, 1, 1, 0, 1.0),
                                                         (700, 1, 0, 0, 1.0), (800, 0, 1, 1, 1.0), (0, 0, 1, 0, 1.0),
                                                         (600, 0, 1, 0, 0.5), (600, 1, 1, 0, 2.5)])
