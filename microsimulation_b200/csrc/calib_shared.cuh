@@ -58,13 +58,22 @@ MSIM_DEV Draws draw_person(Src &src) {
   return d;
 }
 
+// the Count ladder with a rung below every time and one above: RUNGS[a] < t <= RUNGS[a + 1] brackets t >= 0
+#ifdef __CUDACC__
+__constant__
+#else
+static
+#endif
+    const double MSIM_CALIB_RUNGS[12] = {-1.0, 10.0, 20.0, 30.0, 40.0, 50.0, 60.0, 70.0, 80.0, 90.0, 100.0, 1e300};
+
 // number of Count events (at 10, 20, .., 100) strictly before time t >= 0; *tie is set if t coincides with one
-MSIM_HD int counts_before(double t, bool *tie) {
-  const double tc = t < 105.0 ? t : 105.0;
-  int a = (int)(tc * 0.1);  // floor(t / 10) give or take one; 10 * a is exact, so the two steps below settle it
-  if (a > 0 && !((double)(10 * a) < t)) a--;
-  if (a < 10 && (double)(10 * (a + 1)) < t) a++;
-  if (a < 10 && (double)(10 * (a + 1)) == t) *tie = true;
+MSIM_DEV int counts_before(double t, bool *tie) {
+  const double tc = fmin(t, 105.0);
+  int a = (int)(tc * 0.1);  // floor(t / 10) give or take one: one exact comparison either side settles it
+  if (a < 0) a = 0;
+  const double lo = MSIM_CALIB_RUNGS[a], hi = MSIM_CALIB_RUNGS[a + 1];
+  if (tc == lo || tc == hi) *tie = true;
+  a += (int)(tc > hi) - (int)(tc <= lo);
   return a;
 }
 
@@ -82,7 +91,7 @@ inline bool straight_ok(const double par[6]) {
 
 // One person under one parameter set.  c1, c2, c3: Count events seen before toPrecursor / toPreClinical / toClinical
 // (capped at nC, the number seen before death); clin: clinTime as the toDeath handler leaves it (calibperson-r.cc:120).
-MSIM_HD void straight_life(const Draws &d, int nC, const SetPar &P, int *c1, int *c2, int *c3, double *clin, bool *tie) {
+MSIM_DEV void straight_life(const Draws &d, int nC, const SetPar &P, int *c1, int *c2, int *c3, double *clin, bool *tie) {
   const double lam1 = fm_exp(P.Lam1 + P.sigm1 * d.z1);
   const double t1 = lam1 * d.e1;  // scheduled from time 0: 0 + (t1 - 0) == t1
   if (t1 == d.tD) *tie = true;
@@ -130,13 +139,28 @@ struct CalibSharedParams {
 // 3 x CS_BINS x BLOCK ints (histograms, one column per thread)
 constexpr size_t CS_SMEM = sizeof(double) * 6 * BLOCK + sizeof(int) * BLOCK + sizeof(int) * 3 * CS_BINS * BLOCK;
 
-__global__ void __launch_bounds__(BLOCK) calib_shared_kernel(CalibSharedParams p) {
+// a counter in a column of shared memory that only this thread touches: one instruction, no read-back
+__device__ __forceinline__ void cs_bump(int *ptr, int v) {
+  asm volatile("red.shared.add.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(ptr)), "r"(v) : "memory");
+}
+
+// TimeAtRisk (calibperson-r.cc:124-135): term k of a person with clinical time c, and whether it is added at all
+__device__ __forceinline__ double cs_term(int k, double c) {
+  return k == 0 ? fmin(20.0, c) : (c >= 20.0 * k ? fmin(20.0 * (k + 1), c) : 0.0);
+}
+
+#ifndef MSIM_CS_MINB
+#define MSIM_CS_MINB 3
+#endif
+__global__ void __launch_bounds__(BLOCK, MSIM_CS_MINB) calib_shared_kernel(CalibSharedParams p) {
   extern __shared__ __align__(16) unsigned char cs_raw[];
   double *s_d = reinterpret_cast<double *>(cs_raw);  // [6][BLOCK]
   int *s_nC = reinterpret_cast<int *>(s_d + 6 * BLOCK);
   int *s_h = s_nC + BLOCK;  // [3][CS_BINS][BLOCK]
   __shared__ int s_histN[CS_BINS];
   __shared__ int s_tie;
+  __shared__ double s_base[4];  // TimeAtRisk of the block's persons had nobody become clinical (no parameter in it)
+  __shared__ int s_reach[3];    // persons of the block that die at or after 20, 40, 60
   const int tid = threadIdx.x;
   const int set_first = blockIdx.y * p.spb;
   const int n_sets_blk = min(p.spb, p.n_here - set_first);  // >= 1
@@ -145,6 +169,7 @@ __global__ void __launch_bounds__(BLOCK) calib_shared_kernel(CalibSharedParams p
   const int s = tid % n_sets_blk, g = tid / n_sets_blk;
   for (int k = tid; k < 3 * CS_BINS * BLOCK; k += BLOCK) s_h[k] = 0;
   if (tid < CS_BINS) s_histN[tid] = 0;
+  if (tid < 3) s_reach[tid] = 0;
   if (tid == 0) s_tie = 0;
 
   calib::SetPar P;
@@ -157,7 +182,11 @@ __global__ void __launch_bounds__(BLOCK) calib_shared_kernel(CalibSharedParams p
     P.mu3 = rp[4];
     P.sd3 = rp[5] * rp[4];
   }
-  double tar0 = 0.0, tar1 = 0.0, tar2 = 0.0, tar3 = 0.0, cmax = -1.0;
+  // phase 1's sums (this thread's persons, whatever the parameters) and phase 2's corrections (this thread's set:
+  // persons who became clinical before they died leave the risk set at t3 instead of tD)
+  double base0 = 0.0, base1 = 0.0, base2 = 0.0, base3 = 0.0;
+  double dev0 = 0.0, dev1 = 0.0, dev2 = 0.0, dev3 = 0.0;
+  int drop20 = 0, drop40 = 0, drop60 = 0;
   bool tie = false;
   int *h1 = s_h + tid, *d2 = s_h + CS_BINS * BLOCK + tid, *d3 = s_h + 2 * CS_BINS * BLOCK + tid;
 
@@ -184,6 +213,11 @@ __global__ void __launch_bounds__(BLOCK) calib_shared_kernel(CalibSharedParams p
         s_nC[tid] = nC;
         atomicAdd(&s_histN[nC], 1);
         tD = d.tD;
+        base0 += cs_term(0, tD);
+        base1 += cs_term(1, tD);
+        base2 += cs_term(2, tD);
+        base3 += cs_term(3, tD);
+        if (tD >= 20.0) atomicAdd(&s_reach[tD >= 60.0 ? 2 : tD >= 40.0 ? 1 : 0], 1);
       }
       s_d[3 * BLOCK + tid] = tD;
       sub.jump(p.st.stride);
@@ -192,50 +226,73 @@ __global__ void __launch_bounds__(BLOCK) calib_shared_kernel(CalibSharedParams p
     // ---- phase 2: this thread's parameter set over the tile's persons (every G-th, from g)
     if (active) {
       for (int j = g; j < BLOCK; j += G) {
-        calib::Draws d;
-        d.tD = s_d[3 * BLOCK + j];
-        if (d.tD < 0.0) break;  // past the last person (persons of a tile are in index order)
-        d.u0 = s_d[0 * BLOCK + j];
-        d.z1 = s_d[1 * BLOCK + j];
-        d.e1 = s_d[2 * BLOCK + j];
-        d.e2 = s_d[4 * BLOCK + j];
-        d.z2 = s_d[5 * BLOCK + j];
+        const double tD = s_d[3 * BLOCK + j];
+        if (tD < 0.0) break;  // past the last person (persons of a tile are in index order)
+        const double u0 = s_d[0 * BLOCK + j], z1 = s_d[1 * BLOCK + j], e1 = s_d[2 * BLOCK + j];
         const int nC = s_nC[j];
-        int c1, c2, c3;
-        double c;
-        calib::straight_life(d, nC, P, &c1, &c2, &c3, &c, &tie);
-        h1[c1 * BLOCK] += 1;
-        if (c2 != nC) {
-          d2[c2 * BLOCK] += 1;
-          d2[nC * BLOCK] -= 1;
-        }
-        if (c3 != nC) {
-          d3[c3 * BLOCK] += 1;
-          d3[nC * BLOCK] -= 1;
-        }
-        // TimeAtRisk, calibperson-r.cc:124-135
-        tar0 += fmin(20.0, c);
-        if (!(c < 20.0)) {
-          tar1 += fmin(40.0, c);
-          if (!(c < 40.0)) {
-            tar2 += fmin(60.0, c);
-            if (!(c < 60.0)) tar3 += fmin(80.0, c);
+        // calib::straight_life, with the branch for persons who go on to pre-clinical disease written out so that the
+        // other draws are only read there
+        const double t1 = fm_exp(P.Lam1 + P.sigm1 * z1) * e1;
+        if (t1 == tD) tie = true;
+        cs_bump(h1 + min(calib::counts_before(t1, &tie), nC) * BLOCK, 1);
+        if (u0 < P.p2 && t1 < tD) {
+          const double dwell = t1 + P.lam2 * s_d[4 * BLOCK + j];
+          const double t2 = t1 + (dwell - t1);
+          if (t2 == tD) tie = true;
+          const int c2 = min(calib::counts_before(t2, &tie), nC);
+          int c3 = nC;
+          if (t2 < tD) {
+            const double dwell3 = t2 + fm_exp(P.mu3 + P.sd3 * s_d[5 * BLOCK + j]);
+            const double t3 = t2 + (dwell3 - t2);
+            if (t3 == tD) tie = true;
+            c3 = min(calib::counts_before(t3, &tie), nC);
+            if (t3 < tD) {  // clinical before death: clinTime = t3
+              dev0 += cs_term(0, t3) - cs_term(0, tD);
+              dev1 += cs_term(1, t3) - cs_term(1, tD);
+              dev2 += cs_term(2, t3) - cs_term(2, tD);
+              dev3 += cs_term(3, t3) - cs_term(3, tD);
+              drop20 += (int)(tD >= 20.0) - (int)(t3 >= 20.0);
+              drop40 += (int)(tD >= 40.0) - (int)(t3 >= 40.0);
+              drop60 += (int)(tD >= 60.0) - (int)(t3 >= 60.0);
+            }
+          }
+          if (c2 != nC) {
+            cs_bump(d2 + c2 * BLOCK, 1);
+            cs_bump(d2 + nC * BLOCK, -1);
+          }
+          if (c3 != nC) {
+            cs_bump(d3 + c3 * BLOCK, 1);
+            cs_bump(d3 + nC * BLOCK, -1);
           }
         }
-        cmax = fmax(cmax, c);
       }
     }
   }
   if (tie) s_tie = 1;
   __syncthreads();
 
-  // ---- the block's results.  TimeAtRisk first (the draws' area is free now): [BLOCK][5] = four sums and cmax
+  // ---- the block's results.  TimeAtRisk first (the draws' area is free now): [BLOCK][4] phase-1 sums, then
+  // [BLOCK][4] phase-2 corrections; both are added in thread order, so the sums do not depend on timing
   double *s_t = s_d;
-  s_t[tid * 5 + 0] = tar0;
-  s_t[tid * 5 + 1] = tar1;
-  s_t[tid * 5 + 2] = tar2;
-  s_t[tid * 5 + 3] = tar3;
-  s_t[tid * 5 + 4] = active ? cmax : -1.0;
+  s_t[tid * 4 + 0] = base0;
+  s_t[tid * 4 + 1] = base1;
+  s_t[tid * 4 + 2] = base2;
+  s_t[tid * 4 + 3] = base3;
+  __syncthreads();
+  if (tid < 4) {
+    double t = 0.0;
+    for (int k = 0; k < BLOCK; k++) t += s_t[k * 4 + tid];
+    s_base[tid] = t;
+  }
+  __syncthreads();
+  s_t[tid * 4 + 0] = dev0;
+  s_t[tid * 4 + 1] = dev1;
+  s_t[tid * 4 + 2] = dev2;
+  s_t[tid * 4 + 3] = dev3;
+  int *s_drop = reinterpret_cast<int *>(s_t + 4 * BLOCK);  // [BLOCK][3]
+  s_drop[tid * 3 + 0] = drop20;
+  s_drop[tid * 3 + 1] = drop40;
+  s_drop[tid * 3 + 2] = drop60;
   __syncthreads();
   if (tid < n_sets_blk) {
     const int set_local = set_first + tid;  // within this launch
@@ -259,18 +316,19 @@ __global__ void __launch_bounds__(BLOCK) calib_shared_kernel(CalibSharedParams p
       for (int st = 0; st < 4; st++)
         if (occ[st]) atomicAdd(&out[st * 10 + k], (double)occ[st]);
     }
-    double t[4] = {0.0, 0.0, 0.0, 0.0}, cm = -1.0;
-    for (int gg = 0; gg < G; gg++) {  // fixed order: the sums do not depend on timing
+    double t[4] = {0.0, 0.0, 0.0, 0.0};
+    int drop[3] = {0, 0, 0};
+    for (int gg = 0; gg < G; gg++) {
       const int col = gg * n_sets_blk + tid;
-      for (int k = 0; k < 4; k++) t[k] += s_t[col * 5 + k];
-      cm = fmax(cm, s_t[col * 5 + 4]);
+      for (int k = 0; k < 4; k++) t[k] += s_t[col * 4 + k];
+      for (int k = 0; k < 3; k++) drop[k] += s_drop[col * 3 + k];
     }
     double *q = p.partial + ((size_t)set_local * gridDim.x + blockIdx.x) * 4;
-    for (int k = 0; k < 4; k++) q[k] = t[k];
-    if (cm >= 0.0) {
-      const int reached = 1 + (cm >= 20.0) + (cm >= 40.0) + (cm >= 60.0);
-      for (int k = 0; k < reached; k++) atomicAdd(&out[44 + k], 1.0);
-    }
+    for (int k = 0; k < 4; k++) q[k] = s_base[k] + t[k];
+    // the list has as many entries as the largest index any person reached: persons with clinTime >= 20, 40, 60
+    const int at60 = s_reach[2] - drop[2], at40 = s_reach[2] + s_reach[1] - drop[1], at20 = s_reach[2] + s_reach[1] + s_reach[0] - drop[0];
+    const int reached = N > 0 ? 1 + (at20 > 0) + (at40 > 0) + (at60 > 0) : 0;
+    for (int k = 0; k < reached; k++) atomicAdd(&out[44 + k], 1.0);
   }
   if (tid == 0 && s_tie) *p.tie = 1;
 }

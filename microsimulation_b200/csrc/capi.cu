@@ -309,7 +309,16 @@ static int calibration_run(const double seed[6], int64_t first_person, int64_t n
         const int n_chunks = (n_here + BLOCK - 1) / BLOCK;
         CalibSharedParams p;
         memset(&p, 0, sizeof p);
-        grid_x = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, std::max(1, g.sm_count * 4 / n_chunks)));
+        static int per_sm = 0;
+        if (!per_sm) {
+          CK(cudaFuncSetAttribute(calib_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM));
+          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, calib_shared_kernel, BLOCK, CS_SMEM));
+          if (per_sm < 1) per_sm = 1;
+        }
+        // one wave of resident blocks, every block the same number of person tiles (give or take one)
+        const int64_t slots = std::max<int64_t>(1, (int64_t)g.sm_count * per_sm / n_chunks);
+        const int64_t tiles_per_block = (tiles + slots - 1) / slots;
+        grid_x = (int)std::max<int64_t>(1, (tiles + tiles_per_block - 1) / tiles_per_block);
         stream_start(state, first_person, (int64_t)grid_x * BLOCK, &p.st);
         p.n = n;
         p.runpar = (const double *)g.calib_par.p;
@@ -320,11 +329,6 @@ static int calibration_run(const double seed[6], int64_t first_person, int64_t n
         p.tie = tie_flag;
         if ((rc = ensure(g.calib_partial, sizeof(double) * 4 * (size_t)grid_x * n_here))) return rc;
         p.partial = (double *)g.calib_partial.p;
-        static bool attr_set = false;
-        if (!attr_set) {
-          CK(cudaFuncSetAttribute(calib_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM));
-          attr_set = true;
-        }
         calib_shared_kernel<<<dim3(grid_x, n_chunks), BLOCK, CS_SMEM, g.stream>>>(p);
       } else {
         CalibParams p;
