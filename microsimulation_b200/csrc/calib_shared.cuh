@@ -64,16 +64,22 @@ __constant__
 #else
 static
 #endif
-    const double MSIM_CALIB_RUNGS[12] = {-1.0, 10.0, 20.0, 30.0, 40.0, 50.0, 60.0, 70.0, 80.0, 90.0, 100.0, 1e300};
+    const double MSIM_CALIB_RUNGS[12] = {-1.0, 10.0, 20.0, 30.0, 40.0, 50.0, 60.0, 70.0, 80.0, 90.0, 100.0, INFINITY};
 
-// number of Count events (at 10, 20, .., 100) strictly before time t >= 0; *tie is set if t coincides with one
+// number of Count events (at 10, 20, .., 100) strictly before time t >= 0; *tie is set if t coincides with one (or
+// is infinite, which no event time of a valid sweep is)
 MSIM_DEV int counts_before(double t, bool *tie) {
-  const double tc = fmin(t, 105.0);
-  int a = (int)(tc * 0.1);  // floor(t / 10) give or take one: one exact comparison either side settles it
-  if (a < 0) a = 0;
-  const double lo = MSIM_CALIB_RUNGS[a], hi = MSIM_CALIB_RUNGS[a + 1];
-  if (tc == lo || tc == hi) *tie = true;
-  a += (int)(tc > hi) - (int)(tc <= lo);
+  // floor(t / 10) give or take one, within 0..10
+#ifdef __CUDA_ARCH__
+  int a = __double2int_rz(t * 0.1);  // saturates; NaN gives 0
+  a = a < 0 ? 0 : (a > 10 ? 10 : a);
+#else
+  const double q = t * 0.1;
+  int a = q >= 10.0 ? 10 : (q > 0.0 ? (int)q : 0);
+#endif
+  const double lo = MSIM_CALIB_RUNGS[a], hi = MSIM_CALIB_RUNGS[a + 1];  // one exact comparison either side settles it
+  *tie = *tie | (t == lo) | (t == hi);
+  a += (int)(t > hi) - (int)(t <= lo);
   return a;
 }
 
@@ -135,13 +141,14 @@ struct CalibSharedParams {
   double *partial;       // [n_here][gridDim.x][4]
 };
 
-// dynamic shared memory: 6 x BLOCK doubles (draws; reused for the TimeAtRisk reduction), BLOCK ints (nC),
-// 3 x CS_BINS x BLOCK ints (histograms, one column per thread)
-constexpr size_t CS_SMEM = sizeof(double) * 6 * BLOCK + sizeof(int) * BLOCK + sizeof(int) * 3 * CS_BINS * BLOCK;
+// dynamic shared memory: 6 x BLOCK doubles (draws), 8 x BLOCK doubles (TimeAtRisk: every thread's phase-1 sums and
+// phase-2 corrections, kept here rather than in registers for the whole run), BLOCK ints (nC), 3 x BLOCK ints
+// (persons leaving the risk set early), 3 x CS_BINS x BLOCK ints (histograms, one column per thread)
+constexpr size_t CS_SMEM = sizeof(double) * 14 * BLOCK + sizeof(int) * 4 * BLOCK + sizeof(int) * 3 * CS_BINS * BLOCK;
 
 // a counter in a column of shared memory that only this thread touches: one instruction, no read-back
-__device__ __forceinline__ void cs_bump(int *ptr, int v) {
-  asm volatile("red.shared.add.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(ptr)), "r"(v) : "memory");
+__device__ __forceinline__ void cs_bump(unsigned shared_addr, int v) {
+  asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(shared_addr), "r"(v) : "memory");
 }
 
 // TimeAtRisk (calibperson-r.cc:124-135): term k of a person with clinical time c, and whether it is added at all
@@ -155,11 +162,14 @@ __device__ __forceinline__ double cs_term(int k, double c) {
 __global__ void __launch_bounds__(BLOCK, MSIM_CS_MINB) calib_shared_kernel(CalibSharedParams p) {
   extern __shared__ __align__(16) unsigned char cs_raw[];
   double *s_d = reinterpret_cast<double *>(cs_raw);  // [6][BLOCK]
-  int *s_nC = reinterpret_cast<int *>(s_d + 6 * BLOCK);
-  int *s_h = s_nC + BLOCK;  // [3][CS_BINS][BLOCK]
+  double *s_base = s_d + 6 * BLOCK;                  // [4][BLOCK]
+  double *s_dev = s_base + 4 * BLOCK;                // [4][BLOCK]
+  int *s_nC = reinterpret_cast<int *>(s_dev + 4 * BLOCK);
+  int *s_drop = s_nC + BLOCK;   // [3][BLOCK]
+  int *s_h = s_drop + 3 * BLOCK;  // [3][CS_BINS][BLOCK]
   __shared__ int s_histN[CS_BINS];
   __shared__ int s_tie;
-  __shared__ double s_base[4];  // TimeAtRisk of the block's persons had nobody become clinical (no parameter in it)
+  __shared__ double s_base_sum[4];  // TimeAtRisk of the block's persons had nobody become clinical (no parameter in it)
   __shared__ int s_reach[3];    // persons of the block that die at or after 20, 40, 60
   const int tid = threadIdx.x;
   const int set_first = blockIdx.y * p.spb;
@@ -168,6 +178,8 @@ __global__ void __launch_bounds__(BLOCK, MSIM_CS_MINB) calib_shared_kernel(Calib
   const bool active = tid < G * n_sets_blk;
   const int s = tid % n_sets_blk, g = tid / n_sets_blk;
   for (int k = tid; k < 3 * CS_BINS * BLOCK; k += BLOCK) s_h[k] = 0;
+  for (int k = 0; k < 8; k++) s_base[k * BLOCK + tid] = 0.0;  // s_base and s_dev
+  for (int k = 0; k < 3; k++) s_drop[k * BLOCK + tid] = 0;
   if (tid < CS_BINS) s_histN[tid] = 0;
   if (tid < 3) s_reach[tid] = 0;
   if (tid == 0) s_tie = 0;
@@ -182,13 +194,13 @@ __global__ void __launch_bounds__(BLOCK, MSIM_CS_MINB) calib_shared_kernel(Calib
     P.mu3 = rp[4];
     P.sd3 = rp[5] * rp[4];
   }
-  // phase 1's sums (this thread's persons, whatever the parameters) and phase 2's corrections (this thread's set:
-  // persons who became clinical before they died leave the risk set at t3 instead of tD)
-  double base0 = 0.0, base1 = 0.0, base2 = 0.0, base3 = 0.0;
-  double dev0 = 0.0, dev1 = 0.0, dev2 = 0.0, dev3 = 0.0;
-  int drop20 = 0, drop40 = 0, drop60 = 0;
+  // TimeAtRisk: phase 1 adds every person's terms as if nobody became clinical (no parameter in them: s_base, this
+  // thread's persons); phase 2 corrects for the persons of this thread's set who did, and so leave the risk set at t3
+  // instead of tD (s_dev, s_drop)
   bool tie = false;
-  int *h1 = s_h + tid, *d2 = s_h + CS_BINS * BLOCK + tid, *d3 = s_h + 2 * CS_BINS * BLOCK + tid;
+  // this thread's histogram columns, as shared-window addresses; bin b of a column is b * BLOCK ints on
+  const unsigned h1 = (unsigned)__cvta_generic_to_shared(s_h + tid), d2 = h1 + 4u * CS_BINS * BLOCK, d3 = d2 + 4u * CS_BINS * BLOCK;
+  constexpr unsigned BIN = 4u * BLOCK;
 
   MrgSource src;
   Mrg32k3a sub = thread_start_state(p.st, blockIdx.x * BLOCK + tid);
@@ -213,10 +225,8 @@ __global__ void __launch_bounds__(BLOCK, MSIM_CS_MINB) calib_shared_kernel(Calib
         s_nC[tid] = nC;
         atomicAdd(&s_histN[nC], 1);
         tD = d.tD;
-        base0 += cs_term(0, tD);
-        base1 += cs_term(1, tD);
-        base2 += cs_term(2, tD);
-        base3 += cs_term(3, tD);
+#pragma unroll
+        for (int k = 0; k < 4; k++) s_base[k * BLOCK + tid] += cs_term(k, tD);
         if (tD >= 20.0) atomicAdd(&s_reach[tD >= 60.0 ? 2 : tD >= 40.0 ? 1 : 0], 1);
       }
       s_d[3 * BLOCK + tid] = tD;
@@ -232,9 +242,9 @@ __global__ void __launch_bounds__(BLOCK, MSIM_CS_MINB) calib_shared_kernel(Calib
         const int nC = s_nC[j];
         // calib::straight_life, with the branch for persons who go on to pre-clinical disease written out so that the
         // other draws are only read there
-        const double t1 = fm_exp(P.Lam1 + P.sigm1 * z1) * e1;
-        if (t1 == tD) tie = true;
-        cs_bump(h1 + min(calib::counts_before(t1, &tie), nC) * BLOCK, 1);
+        const double t1 = fm_exp_bank(P.Lam1 + P.sigm1 * z1) * e1;
+        tie = tie | (t1 == tD);
+        cs_bump(h1 + (unsigned)min(calib::counts_before(t1, &tie), nC) * BIN, 1);
         if (u0 < P.p2 && t1 < tD) {
           const double dwell = t1 + P.lam2 * s_d[4 * BLOCK + j];
           const double t2 = t1 + (dwell - t1);
@@ -242,27 +252,24 @@ __global__ void __launch_bounds__(BLOCK, MSIM_CS_MINB) calib_shared_kernel(Calib
           const int c2 = min(calib::counts_before(t2, &tie), nC);
           int c3 = nC;
           if (t2 < tD) {
-            const double dwell3 = t2 + fm_exp(P.mu3 + P.sd3 * s_d[5 * BLOCK + j]);
+            const double dwell3 = t2 + fm_exp_bank(P.mu3 + P.sd3 * s_d[5 * BLOCK + j]);
             const double t3 = t2 + (dwell3 - t2);
             if (t3 == tD) tie = true;
             c3 = min(calib::counts_before(t3, &tie), nC);
             if (t3 < tD) {  // clinical before death: clinTime = t3
-              dev0 += cs_term(0, t3) - cs_term(0, tD);
-              dev1 += cs_term(1, t3) - cs_term(1, tD);
-              dev2 += cs_term(2, t3) - cs_term(2, tD);
-              dev3 += cs_term(3, t3) - cs_term(3, tD);
-              drop20 += (int)(tD >= 20.0) - (int)(t3 >= 20.0);
-              drop40 += (int)(tD >= 40.0) - (int)(t3 >= 40.0);
-              drop60 += (int)(tD >= 60.0) - (int)(t3 >= 60.0);
+#pragma unroll
+              for (int k = 0; k < 4; k++) s_dev[k * BLOCK + tid] += cs_term(k, t3) - cs_term(k, tD);
+#pragma unroll
+              for (int k = 0; k < 3; k++) s_drop[k * BLOCK + tid] += (int)(tD >= 20.0 * (k + 1)) - (int)(t3 >= 20.0 * (k + 1));
             }
           }
           if (c2 != nC) {
-            cs_bump(d2 + c2 * BLOCK, 1);
-            cs_bump(d2 + nC * BLOCK, -1);
+            cs_bump(d2 + (unsigned)c2 * BIN, 1);
+            cs_bump(d2 + (unsigned)nC * BIN, -1);
           }
           if (c3 != nC) {
-            cs_bump(d3 + c3 * BLOCK, 1);
-            cs_bump(d3 + nC * BLOCK, -1);
+            cs_bump(d3 + (unsigned)c3 * BIN, 1);
+            cs_bump(d3 + (unsigned)nC * BIN, -1);
           }
         }
       }
@@ -271,28 +278,12 @@ __global__ void __launch_bounds__(BLOCK, MSIM_CS_MINB) calib_shared_kernel(Calib
   if (tie) s_tie = 1;
   __syncthreads();
 
-  // ---- the block's results.  TimeAtRisk first (the draws' area is free now): [BLOCK][4] phase-1 sums, then
-  // [BLOCK][4] phase-2 corrections; both are added in thread order, so the sums do not depend on timing
-  double *s_t = s_d;
-  s_t[tid * 4 + 0] = base0;
-  s_t[tid * 4 + 1] = base1;
-  s_t[tid * 4 + 2] = base2;
-  s_t[tid * 4 + 3] = base3;
-  __syncthreads();
+  // ---- the block's results.  The phase-1 sums are added in thread order, so the result does not depend on timing
   if (tid < 4) {
     double t = 0.0;
-    for (int k = 0; k < BLOCK; k++) t += s_t[k * 4 + tid];
-    s_base[tid] = t;
+    for (int k = 0; k < BLOCK; k++) t += s_base[tid * BLOCK + k];
+    s_base_sum[tid] = t;
   }
-  __syncthreads();
-  s_t[tid * 4 + 0] = dev0;
-  s_t[tid * 4 + 1] = dev1;
-  s_t[tid * 4 + 2] = dev2;
-  s_t[tid * 4 + 3] = dev3;
-  int *s_drop = reinterpret_cast<int *>(s_t + 4 * BLOCK);  // [BLOCK][3]
-  s_drop[tid * 3 + 0] = drop20;
-  s_drop[tid * 3 + 1] = drop40;
-  s_drop[tid * 3 + 2] = drop60;
   __syncthreads();
   if (tid < n_sets_blk) {
     const int set_local = set_first + tid;  // within this launch
@@ -320,11 +311,11 @@ __global__ void __launch_bounds__(BLOCK, MSIM_CS_MINB) calib_shared_kernel(Calib
     int drop[3] = {0, 0, 0};
     for (int gg = 0; gg < G; gg++) {
       const int col = gg * n_sets_blk + tid;
-      for (int k = 0; k < 4; k++) t[k] += s_t[col * 4 + k];
-      for (int k = 0; k < 3; k++) drop[k] += s_drop[col * 3 + k];
+      for (int k = 0; k < 4; k++) t[k] += s_dev[k * BLOCK + col];
+      for (int k = 0; k < 3; k++) drop[k] += s_drop[k * BLOCK + col];
     }
     double *q = p.partial + ((size_t)set_local * gridDim.x + blockIdx.x) * 4;
-    for (int k = 0; k < 4; k++) q[k] = s_base[k] + t[k];
+    for (int k = 0; k < 4; k++) q[k] = s_base_sum[k] + t[k];
     // the list has as many entries as the largest index any person reached: persons with clinTime >= 20, 40, 60
     const int at60 = s_reach[2] - drop[2], at40 = s_reach[2] + s_reach[1] - drop[1], at20 = s_reach[2] + s_reach[1] + s_reach[0] - drop[0];
     const int reached = N > 0 ? 1 + (at20 > 0) + (at40 > 0) + (at60 > 0) : 0;
