@@ -319,6 +319,15 @@ def measure_calib(args, steps, rank, world, with_cpu):
     def sweep(unpack):
         return D.calibration_sweep_sharded(SEED, pars, CALIB_PERSONS, unpack=unpack)
 
+    # the same sweep through the event loop (every (person, set) pair simulated on its own: ordered event array),
+    # which is what the default kernel — draws shared between the sets, no queue — replaces; reported beside it
+    api.set_person_schedule("queue")
+    try:
+        for _ in range(2):
+            sweep(False)
+        event_loop_ms = api.last_kernel_ms()
+    finally:
+        api.set_person_schedule("staged")
     for _ in range(2):
         sweep(False)
     kernel_ms = api.last_kernel_ms()
@@ -342,7 +351,8 @@ def measure_calib(args, steps, rank, world, with_cpu):
     e2e_ms = (time.perf_counter() - t0) * 1e3
     gs, gp = D.calibration_grid(world, N_SETS)
     out = {"workload": workload_name("calib"), "value": N_SETS * CALIB_PERSONS / (ms * 1e-3), "unit": "person-simulations/s",
-           "ms_per_step": ms, "kernel_ms_rank0": kernel_ms, "scaling": "strong", "gpu_launches": int(launches),
+           "ms_per_step": ms, "kernel_ms_rank0": kernel_ms, "kernel": "calib_shared_kernel (csrc/calib_shared.cuh)",
+           "event_loop_kernel_ms_rank0": event_loop_ms, "scaling": "strong", "gpu_launches": int(launches),
            "split": {"set_groups": gs, "person_groups": gp},
            "e2e": {"value": N_SETS * CALIB_PERSONS / (e2e_ms * 1e-3), "unit": "person-simulations/s", "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": N_SETS * 48, "d2h_bytes_per_step": N_SETS * 48 * 8},

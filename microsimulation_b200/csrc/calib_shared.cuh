@@ -67,8 +67,9 @@ static
     const double MSIM_CALIB_RUNGS[12] = {-1.0, 10.0, 20.0, 30.0, 40.0, 50.0, 60.0, 70.0, 80.0, 90.0, 100.0, INFINITY};
 
 // number of Count events (at 10, 20, .., 100) strictly before time t >= 0; *tie is set if t coincides with one (or
-// is infinite, which no event time of a valid sweep is)
-MSIM_DEV int counts_before(double t, bool *tie) {
+// is infinite, which no event time of a valid sweep is).  `rungs`: MSIM_CALIB_RUNGS or a copy of it (the kernel keeps
+// one in shared memory: lanes look up different rungs, which the constant cache would serve one address at a time)
+MSIM_DEV int counts_before(double t, const double *rungs, bool *tie) {
   // floor(t / 10) give or take one, within 0..10
 #ifdef __CUDA_ARCH__
   int a = __double2int_rz(t * 0.1);  // saturates; NaN gives 0
@@ -77,7 +78,7 @@ MSIM_DEV int counts_before(double t, bool *tie) {
   const double q = t * 0.1;
   int a = q >= 10.0 ? 10 : (q > 0.0 ? (int)q : 0);
 #endif
-  const double lo = MSIM_CALIB_RUNGS[a], hi = MSIM_CALIB_RUNGS[a + 1];  // one exact comparison either side settles it
+  const double lo = rungs[a], hi = rungs[a + 1];  // one exact comparison either side settles it
   *tie = *tie | (t == lo) | (t == hi);
   a += (int)(t > hi) - (int)(t <= lo);
   return a;
@@ -101,7 +102,7 @@ MSIM_DEV void straight_life(const Draws &d, int nC, const SetPar &P, int *c1, in
   const double lam1 = fm_exp(P.Lam1 + P.sigm1 * d.z1);
   const double t1 = lam1 * d.e1;  // scheduled from time 0: 0 + (t1 - 0) == t1
   if (t1 == d.tD) *tie = true;
-  const int m1 = counts_before(t1, tie);
+  const int m1 = counts_before(t1, MSIM_CALIB_RUNGS, tie);
   *c1 = m1 < nC ? m1 : nC;
   *c2 = nC;
   *c3 = nC;
@@ -110,13 +111,13 @@ MSIM_DEV void straight_life(const Draws &d, int nC, const SetPar &P, int *c1, in
     const double dwell = t1 + P.lam2 * d.e2;
     const double t2 = t1 + (dwell - t1);
     if (t2 == d.tD) *tie = true;
-    const int m2 = counts_before(t2, tie);
+    const int m2 = counts_before(t2, MSIM_CALIB_RUNGS, tie);
     *c2 = m2 < nC ? m2 : nC;
     if (t2 < d.tD) {
       const double dwell3 = t2 + fm_exp(P.mu3 + P.sd3 * d.z2);
       const double t3 = t2 + (dwell3 - t2);
       if (t3 == d.tD) *tie = true;
-      const int m3 = counts_before(t3, tie);
+      const int m3 = counts_before(t3, MSIM_CALIB_RUNGS, tie);
       *c3 = m3 < nC ? m3 : nC;
       if (t3 < d.tD) *clin = t3;
     }
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(BLOCK, MSIM_CS_MINB) calib_shared_kernel(Calib
   int *s_drop = s_nC + BLOCK;   // [3][BLOCK]
   int *s_h = s_drop + 3 * BLOCK;  // [3][CS_BINS][BLOCK]
   __shared__ int s_histN[CS_BINS];
+  __shared__ double s_rungs[12];
   __shared__ int s_tie;
   __shared__ double s_base_sum[4];  // TimeAtRisk of the block's persons had nobody become clinical (no parameter in it)
   __shared__ int s_reach[3];    // persons of the block that die at or after 20, 40, 60
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(BLOCK, MSIM_CS_MINB) calib_shared_kernel(Calib
   for (int k = 0; k < 8; k++) s_base[k * BLOCK + tid] = 0.0;  // s_base and s_dev
   for (int k = 0; k < 3; k++) s_drop[k * BLOCK + tid] = 0;
   if (tid < CS_BINS) s_histN[tid] = 0;
+  if (tid < 12) s_rungs[tid] = calib::MSIM_CALIB_RUNGS[tid];
   if (tid < 3) s_reach[tid] = 0;
   if (tid == 0) s_tie = 0;
 
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(BLOCK, MSIM_CS_MINB) calib_shared_kernel(Calib
         src.g = sub;
         const calib::Draws d = calib::draw_person(src);
         bool t0 = false;
-        const int nC = calib::counts_before(d.tD, &t0);
+        const int nC = calib::counts_before(d.tD, s_rungs, &t0);
         if (t0) tie = true;
         s_d[0 * BLOCK + tid] = d.u0;
         s_d[1 * BLOCK + tid] = d.z1;
@@ -244,18 +247,18 @@ __global__ void __launch_bounds__(BLOCK, MSIM_CS_MINB) calib_shared_kernel(Calib
         // other draws are only read there
         const double t1 = fm_exp_bank(P.Lam1 + P.sigm1 * z1) * e1;
         tie = tie | (t1 == tD);
-        cs_bump(h1 + (unsigned)min(calib::counts_before(t1, &tie), nC) * BIN, 1);
+        cs_bump(h1 + (unsigned)min(calib::counts_before(t1, s_rungs, &tie), nC) * BIN, 1);
         if (u0 < P.p2 && t1 < tD) {
           const double dwell = t1 + P.lam2 * s_d[4 * BLOCK + j];
           const double t2 = t1 + (dwell - t1);
           if (t2 == tD) tie = true;
-          const int c2 = min(calib::counts_before(t2, &tie), nC);
+          const int c2 = min(calib::counts_before(t2, s_rungs, &tie), nC);
           int c3 = nC;
           if (t2 < tD) {
             const double dwell3 = t2 + fm_exp_bank(P.mu3 + P.sd3 * s_d[5 * BLOCK + j]);
             const double t3 = t2 + (dwell3 - t2);
             if (t3 == tD) tie = true;
-            c3 = min(calib::counts_before(t3, &tie), nC);
+            c3 = min(calib::counts_before(t3, s_rungs, &tie), nC);
             if (t3 < tD) {  // clinical before death: clinTime = t3
 #pragma unroll
               for (int k = 0; k < 4; k++) s_dev[k * BLOCK + tid] += cs_term(k, t3) - cs_term(k, tD);

@@ -118,8 +118,8 @@ inline int finish_run(int64_t *n_rows_out) {
     CK(cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1));
     g.timing_pending = false;
   }
-  double small[16];
-  CK(cudaMemcpy(small, g.small.p, sizeof small, cudaMemcpyDeviceToHost));
+  double *small = g.last_small;  // kept: callers read their own flags from it (e.g. the calibration sweep's tie flag)
+  CK(cudaMemcpy(small, g.small.p, sizeof g.last_small, cudaMemcpyDeviceToHost));
   int err = *(int *)(small + 10);
   unsigned long long nr = *(unsigned long long *)(small + 9);
   g.last_n_rows = (int64_t)nr;
@@ -341,8 +341,8 @@ inline int stream_offsets_attempt(int64_t n, const typename Traits::Consts &cons
   CK(cudaGetLastError());
   g.launches += 4;
   CK(cudaStreamSynchronize(g.stream));
-  double small[16];
-  CK(cudaMemcpy(small, g.small.p, sizeof small, cudaMemcpyDeviceToHost));
+  double *small = g.last_small;  // kept: callers read their own flags from it (e.g. the calibration sweep's tie flag)
+  CK(cudaMemcpy(small, g.small.p, sizeof g.last_small, cudaMemcpyDeviceToHost));
   const int64_t end_word = *(int64_t *)(small + 11);
   const int err = *(int *)(small + 10);
   if (end_word == 0 || err == MSIM_ERR_STREAM) {  // person n-1 was never reached

@@ -44,6 +44,7 @@ struct Ctx {
   DevBuf rowlog, prov_start, prov_end, prov_meta, tile_count, partial, dense, small, mt_words, len, starts, chain_exit, chain_count, chain_entry, chain_base, chain_gexit, chain_gcount, chain_gentry, chain_gbase, calib_out, calib_partial,
       calib_par, uniforms, first_end, first_tag, ov_fill, ov_tag, ov_start, ov_end, aux, code_in, code_out, sgeom,
       indiv, gsm_model, gsm_data, gsm_in, gsm_out, slices, fold_sync, carry_tiles;
+  double last_small[16] = {0};  // the flag block as finish_run read it last
   int person_kernel = 0;  // 0 = staged schedule (person_staged.cuh), 1 = generic cohort kernel
   bool last_staged = false;
   double plan_rows = 1.25, plan_extra_rows = 0.26;  // row-log buffer planning (msim_set_rowlog_plan)

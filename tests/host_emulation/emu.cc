@@ -603,7 +603,7 @@ int emu_calibration_shared(const double seed[6], int64_t first_person, int64_t n
     src.g = subs[i];
     draws[i] = calib::draw_person(src);
     if (force_tD > 0) draws[i].tD = force_tD;
-    nC[i] = calib::counts_before(draws[i].tD, &tie);
+    nC[i] = calib::counts_before(draws[i].tD, calib::MSIM_CALIB_RUNGS, &tie);
   }
   for (int s = 0; s < n_sets; s++) {
     const double *rp = runpar + 6 * s;
@@ -633,7 +633,7 @@ int emu_calibration_shared(const double seed[6], int64_t first_person, int64_t n
 
 int emu_counts_before(double t, int *tie_out) {
   bool tie = false;
-  const int c = calib::counts_before(t, &tie);
+  const int c = calib::counts_before(t, calib::MSIM_CALIB_RUNGS, &tie);
   *tie_out = tie;
   return c;
 }
