@@ -188,14 +188,21 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------- our arm
 
+PEER_MERGE = False  # the merge across ranks happens inside the simulation launch (microsimulation_b200.distributed.enable_peer_merge)
+
+
 def merge_check(P, first, outputs, rate, world):
-    """One step with the merge taken apart: every rank's accumulator vector is gathered BEFORE the all-reduce, and
-    the all-reduced vector must equal their sum (integer cells exactly: counters are integer-valued doubles; FP
-    sums to 1e-12) and account for every person exactly once (each dies once: toDeath or toPCDeath)."""
+    """One step with the merge taken apart: every rank's accumulator vector is gathered BEFORE any merge, and the
+    merged vector must equal their sum (integer cells exactly: counters are integer-valued doubles; FP sums to 1e-12)
+    and account for every person exactly once (each dies once: toDeath or toPCDeath).  Checked for the NCCL
+    all-reduce and, where it is in use, for the merge inside the launch — which must also leave the SAME bits on
+    every rank (it adds in rank order)."""
     import torch
     import torch.distributed as dist
     import microsimulation_b200.api as api
     from microsimulation_b200.distributed import _CudaBuffer
+    if PEER_MERGE:
+        api.peer_merge(False)
     res = api.person_run_device(SEED, first, P, outputs, rate)
     ptr, n = api.dense_device_ptr()
     t = torch.as_tensor(_CudaBuffer(ptr, n), device="cuda")
@@ -205,13 +212,30 @@ def merge_check(P, first, outputs, rate, world):
     dist.all_reduce(t)
     total = torch.stack(parts).sum(0)
     n_fp = 2 * res.dims.n_state * res.dims.n_bin if n > 9 else 0  # pt and ut cells lead the vector (csrc/report.cuh)
-    ints_equal = bool(torch.equal(t[n_fp:-1], total[n_fp:-1]))
-    fp = torch.cat([t[:n_fp], t[-1:]]), torch.cat([total[:n_fp], total[-1:]])
-    fp_diff = float(((fp[0] - fp[1]).abs() / fp[1].abs().clamp_min(1e-300)).max()) if fp[0].numel() else 0.0
-    deaths = float(t[-9] + t[-8])
-    return {"allreduced_equals_sum_of_ranks_int_cells": ints_equal, "fp_cells_max_rel_diff": fp_diff,
-            "deaths_equal_persons": deaths == float(world) * P, "persons": world * P, "ranks": world,
-            "ok": ints_equal and fp_diff <= 1e-12 and deaths == float(world) * P}
+
+    def against_total(v):
+        ints_equal = bool(torch.equal(v[n_fp:-1], total[n_fp:-1]))
+        fp = torch.cat([v[:n_fp], v[-1:]]), torch.cat([total[:n_fp], total[-1:]])
+        fp_diff = float(((fp[0] - fp[1]).abs() / fp[1].abs().clamp_min(1e-300)).max()) if fp[0].numel() else 0.0
+        return ints_equal, fp_diff, float(v[-9] + v[-8])
+
+    ints_equal, fp_diff, deaths = against_total(t)
+    out = {"allreduced_equals_sum_of_ranks_int_cells": ints_equal, "fp_cells_max_rel_diff": fp_diff,
+           "deaths_equal_persons": deaths == float(world) * P, "persons": world * P, "ranks": world,
+           "ok": ints_equal and fp_diff <= 1e-12 and deaths == float(world) * P}
+    if PEER_MERGE:
+        api.peer_merge(True)
+        api.person_run_device(SEED, first, P, outputs, rate)
+        ptr, n = api.dense_device_ptr()
+        v = torch.as_tensor(_CudaBuffer(ptr, n), device="cuda").clone()
+        i2, f2, d2 = against_total(v)
+        every = [torch.empty_like(v) for _ in range(world)]
+        dist.all_gather(every, v)
+        same_bits = all(bool(torch.equal(e.view(torch.int64), v.view(torch.int64))) for e in every)
+        out["in_launch_merge"] = {"equals_sum_of_ranks_int_cells": i2, "fp_cells_max_rel_diff": f2, "deaths_equal_persons": d2 == float(world) * P,
+                                  "identical_bits_on_all_ranks": same_bits}
+        out["ok"] = out["ok"] and i2 and f2 <= 1e-12 and d2 == float(world) * P and same_bits
+    return out
 
 
 def measure(args, workload, steps, P, rank, local, world, clocks_wanted, with_e2e=True):
@@ -231,7 +255,7 @@ def measure(args, workload, steps, P, rank, local, world, clocks_wanted, with_e2
         torch.cuda.synchronize()
 
     def merge():
-        if world > 1 and report_mode:  # the single collective: accumulator vector (report cells + counts)
+        if world > 1 and report_mode and not PEER_MERGE:  # the single collective: accumulator vector (report cells + counts)
             from microsimulation_b200.distributed import _CudaBuffer
             ptr, n = api.dense_device_ptr()
             dist.all_reduce(torch.as_tensor(_CudaBuffer(ptr, n), device="cuda"))
@@ -449,6 +473,10 @@ def run_ours(args):
     import microsimulation_b200.api as api
     m.init(local)
     api.set_stream(torch.cuda.current_stream().cuda_stream)  # kernels and the all-reduce on ONE stream
+    global PEER_MERGE
+    if world > 1 and not args.nccl_merge:
+        from microsimulation_b200 import distributed as D
+        PEER_MERGE = D.enable_peer_merge()  # report runs are merged inside their launch (NVLink peer memory)
     P = args.persons
     few = max(3, min(args.steps, 5))
     if args.workload == "calib":
@@ -469,6 +497,18 @@ def run_ours(args):
     strong = None
     if world > 1 and not args.no_strong and TOTAL_STRONG % world == 0:
         strong = measure(args, args.workload, args.steps, TOTAL_STRONG // world, rank, local, world, False)
+        if PEER_MERGE and args.workload == "report":
+            # the same steps with the merge as a separate NCCL all-reduce after every launch, for comparison
+            import microsimulation_b200.api as api_
+            api_.peer_merge(False)
+            PEER_MERGE = False
+            try:
+                strong["nccl_ms_per_step"] = measure(args, args.workload, few, TOTAL_STRONG // world, rank, local, world, False)["ms_per_step"]
+            finally:
+                api_.peer_merge(True)
+                PEER_MERGE = True
+    if PEER_MERGE:
+        api.peer_merge(False)  # what follows runs on rank 0 alone (CPU baseline checks) or does not involve person-r
     calib = None
     if not args.no_calib:
         calib = measure_calib(args, 3, rank, world, with_cpu=not args.no_cpu_baseline)
@@ -507,8 +547,10 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.workload) + "; %d persons per GPU per step" % P,
                        "seed": "12345x6", "persons_per_gpu": P, "rows_per_step_rank0": main["rows"],
-                       "merge": "one NCCL all-reduce(sum, f64) of the accumulator vector per step" if report_mode and world > 1
-                                else ("none (one GPU)" if world == 1 else "none: row logs stay sharded"),
+                       "merge": (("inside the simulation launch: the block that finishes the fold exchanges the accumulator vector with "
+                                  "the other ranks over NVLink peer memory and adds them in rank order" if PEER_MERGE else
+                                  "one NCCL all-reduce(sum, f64) of the accumulator vector per step") if report_mode and world > 1
+                                 else ("none (one GPU)" if world == 1 else "none: row logs stay sharded")),
                        "l2": ("no input: each person is generated from (seed, index); outputs are KB-sized tables, nothing to flush"
                               if report_mode else
                               "no input reuse; each step writes a %.1f GB row log (>> 126 MB L2)" % (main["rows"] * 40 / 1e9))},
@@ -523,7 +565,10 @@ def run_ours(args):
         line["strong"] = {"persons_total": TOTAL_STRONG, "persons_per_gpu": strong["persons_per_gpu"], "value": strong["value"],
                           "unit": UNIT, "ms_per_step": strong["ms_per_step"], "kernel_ms_rank0": strong["kernel_ms"], "e2e": strong["e2e"],
                           "gpu_launches": strong["launches"], "merge_check": strong.get("merge_check"),
-                          "note": "BASELINE.json's metric: 1e8 persons in total over the ranks; per step = kernel + one all-reduce"}
+                          "nccl_ms_per_step": strong.get("nccl_ms_per_step"),
+                          "note": "BASELINE.json's metric: 1e8 persons in total over the ranks; per step = one launch that simulates and "
+                                  "merges (nccl_ms_per_step: the same with the merge as a separate NCCL all-reduce)" if PEER_MERGE else
+                                  "BASELINE.json's metric: 1e8 persons in total over the ranks; per step = kernel + one all-reduce"}
     if other:
         line["other_workload"] = {"workload": workload_name(other_name), "value": other["value"], "unit": UNIT,
                                   "ms_per_step": other["ms_per_step"], "e2e": other["e2e"], "gpu_launches": other["launches"],
@@ -570,6 +615,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="persons per host process for the CPU legs (0: 1e6 report / 5e6 rowlog / 2.5e5 calib)")
     ap.add_argument("--no-other-workload", action="store_true", help="measure only the chosen workload")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    ap.add_argument("--nccl-merge", action="store_true", help="merge with an NCCL all-reduce after every launch instead of inside the launch")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (1e8 persons in total) at N > 1")
     ap.add_argument("--no-calib", action="store_true", help="skip the calibration-sweep leg")
     args = ap.parse_args()

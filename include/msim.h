@@ -37,6 +37,7 @@ extern "C" {
 #define MSIM_ERR_STREAM (-6)      /* sequential-stream model drew more uniforms per person than planned for */
 #define MSIM_ERR_STATE (-7)       /* call order error (e.g. no current stream) */
 #define MSIM_ERR_MODEL (-8)       /* a model reported a (state, event) pair outside the set it declared reachable */
+#define MSIM_ERR_PEER (-9)        /* in-launch merge across GPUs: a rank did not deliver its vector in time */
 
 /* ---- tables --------------------------------------------------------- */
 
@@ -84,6 +85,31 @@ void msim_shutdown(void);
  * caller's NCCL all-reduce runs on, so that the merge needs no host
  * synchronisation), use_own = 1 returns to the library's own. */
 int msim_set_stream(void *cuda_stream, int use_own);
+/* Merging a sharded person-r run across the GPUs of ONE node inside the
+ * simulation launch (csrc/person_staged.cuh, staged_peer_merge; replaces the
+ * all-reduce a caller would otherwise enqueue after every step — SURVEY.md
+ * 8(e), "one all-reduce of the accumulator vector").  One process per GPU:
+ *   msim_peer_export(world, handle)          allocate this rank's mailbox, get
+ *                                            its CUDA IPC handle (64 bytes);
+ *   (exchange the handles, e.g. torch.distributed.all_gather_object)
+ *   msim_peer_import(rank, world, handles)   map the other ranks' mailboxes
+ *                                            (handles: world x 64 bytes, in
+ *                                            rank order), then a host barrier;
+ *   msim_peer_merge(1)                       from now on every person-r run
+ *                                            with MSIM_OUT_REPORT leaves the SUM
+ *                                            over all ranks in its dense vector
+ *                                            (msim_dense_device_ptr), added in
+ *                                            rank order: bit-identical on all
+ *                                            ranks.  Every rank must make the
+ *                                            same sequence of such runs; a rank
+ *                                            that stays away for 4 s makes the
+ *                                            others fail with MSIM_ERR_PEER.
+ *   msim_peer_merge(0) / msim_peer_close()   stop merging / release. */
+#define MSIM_PEER_HANDLE_BYTES 64
+int msim_peer_export(int32_t world, void *handle_out);
+int msim_peer_import(int32_t rank, int32_t world, const void *handles);
+int msim_peer_merge(int on);
+int msim_peer_close(void);
 /* Number of kernels this library has launched since it was loaded. */
 int64_t msim_launch_count(void);
 

@@ -406,6 +406,35 @@ def dense_device_ptr():
     return C.cast(p, C.c_void_p).value, n.value
 
 
+# ---- merge across the GPUs of a node inside the person-r launch (include/msim.h, msim_peer_*)
+
+PEER_HANDLE_BYTES = 64
+
+
+def peer_export(world):
+    """This rank's mailbox: returns its CUDA IPC handle (bytes) for the other ranks."""
+    h = (C.c_ubyte * PEER_HANDLE_BYTES)()
+    check(load().msim_peer_export(C.c_int32(int(world)), h))
+    return bytes(h)
+
+
+def peer_import(rank, world, handles):
+    """`handles`: every rank's peer_export(), in rank order."""
+    blob = b"".join(handles)
+    if len(blob) != PEER_HANDLE_BYTES * int(world):
+        raise ValueError("one %d-byte handle per rank" % PEER_HANDLE_BYTES)
+    buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+    check(load().msim_peer_import(C.c_int32(int(rank)), C.c_int32(int(world)), buf))
+
+
+def peer_merge(on=True):
+    check(load().msim_peer_merge(C.c_int(1 if on else 0)))
+
+
+def peer_close():
+    check(load().msim_peer_close())
+
+
 def dense_to_report(dense, dims, discount_rate=0.0):
     dense = np.ascontiguousarray(dense, dtype=np.float64)
     r = Report()

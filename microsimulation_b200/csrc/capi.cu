@@ -60,6 +60,7 @@ void msim_shutdown(void) {
                     &g.chain_count, &g.chain_entry, &g.chain_base, &g.chain_gexit, &g.chain_gcount, &g.chain_gentry, &g.chain_gbase, &g.calib_out, &g.calib_partial, &g.calib_par, &g.uniforms,
                     &g.first_end, &g.first_tag, &g.ov_fill, &g.ov_tag, &g.ov_start, &g.ov_end,
                     &g.aux, &g.code_in, &g.code_out, &g.sgeom, &g.indiv, &g.gsm_model, &g.gsm_data, &g.gsm_in, &g.gsm_out, &g.slices, &g.fold_sync, &g.carry_tiles};
+  peer_close();
   if (g.d_mt_table) cudaFree(g.d_mt_table);
   g.d_mt_table = nullptr;
   g.mt_table_polys = 0;
@@ -117,6 +118,15 @@ int msim_set_mt_parallel(int on) {
   g.mt_parallel = on != 0;
   return (on && g.inited && !g.d_mt_table) ? 1 : MSIM_OK;  // 1: asked for, but mt_jump.bin was not found
 }
+
+int msim_peer_export(int32_t world, void *handle_out) { return peer_export(world, handle_out); }
+int msim_peer_import(int32_t rank, int32_t world, const void *handles) { return peer_import(rank, world, handles); }
+int msim_peer_merge(int on) {
+  if (on && (!g.peers.local || !g.peers.mapped[g.peers.rank])) return fail(MSIM_ERR_STATE, "peer merge: msim_peer_export and msim_peer_import first");
+  g.peers.on = on != 0;
+  return MSIM_OK;
+}
+int msim_peer_close(void) { return peer_close(); }
 
 int msim_set_person_schedule(int which) {
   if (which < 0 || which > 3)

@@ -128,6 +128,7 @@ inline int finish_run(int64_t *n_rows_out) {
   if (err == MSIM_ERR_HEAP) return fail(MSIM_ERR_HEAP, "a person scheduled more pending events / rows than the device capacity");
   if (err == MSIM_ERR_STREAM) return fail(MSIM_ERR_STREAM, "a person drew more uniforms than the sequential-stream plan allows");
   if (err == MSIM_ERR_MODEL) return fail(MSIM_ERR_MODEL, "a model reported a (state, event) pair outside the set it declared reachable");
+  if (err == MSIM_ERR_PEER) return fail(MSIM_ERR_PEER, "peer merge: another rank did not deliver its result vector in time");
   if (err) return fail(err, "device-side error");
   return MSIM_OK;
 }

@@ -42,6 +42,54 @@ int staged_rowpasses(int64_t n, int64_t first_person, int64_t capacity, bool cou
   return MSIM_OK;
 }
 
+// ---- mailboxes for the in-launch merge across GPUs (person_staged.cuh, staged_peer_merge)
+constexpr int PEER_CAP = 16384;  // doubles per slot (person-r's report + counts: 9810)
+
+inline size_t peer_mailbox_bytes(int world) { return sizeof(double) * 2 * (size_t)world * PEER_CAP + sizeof(unsigned) * 2 * (size_t)world + 256; }
+
+int peer_close() {
+  for (int r = 0; r < 8; r++) {
+    if (g.peers.mapped[r] && g.peers.mapped[r] != g.peers.local) cudaIpcCloseMemHandle(g.peers.mapped[r]);
+    g.peers.mapped[r] = nullptr;
+  }
+  if (g.peers.local) cudaFree(g.peers.local);
+  g.peers = Ctx::Peers();
+  return MSIM_OK;
+}
+
+int peer_export(int world, void *handle_out) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  if (world < 1 || world > PEER_MAX || !handle_out) return fail(MSIM_ERR_ARG, "peer merge: 1 to 8 ranks on one node");
+  peer_close();
+  CK(cudaMalloc(&g.peers.local, peer_mailbox_bytes(world)));
+  CK(cudaMemset(g.peers.local, 0, peer_mailbox_bytes(world)));
+  CK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, g.peers.local));
+  static_assert(sizeof h == MSIM_PEER_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out, &h, sizeof h);
+  g.peers.world = world;
+  return MSIM_OK;
+}
+
+int peer_import(int rank, int world, const void *handles) {
+  if (!g.peers.local || world != g.peers.world) return fail(MSIM_ERR_STATE, "peer merge: msim_peer_export first, with the same number of ranks");
+  if (rank < 0 || rank >= world || !handles) return fail(MSIM_ERR_ARG, "peer merge: bad rank");
+  for (int r = 0; r < world; r++) {
+    if (r == rank) {
+      g.peers.mapped[r] = g.peers.local;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + (size_t)r * MSIM_PEER_HANDLE_BYTES, sizeof h);
+    CK(cudaIpcOpenMemHandle(&g.peers.mapped[r], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  g.peers.rank = rank;
+  g.peers.epoch = 0;
+  return MSIM_OK;
+}
+
 int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t ov_cap_override) {
   int rc;
   if (sh->n >= (int64_t)4294967296ll) return fail(MSIM_ERR_ARG, "a shard holds at most 2^32 - 1 persons");
@@ -142,6 +190,22 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
       CK(cudaMemsetAsync(g.fold_sync.p, 0, g.fold_sync.bytes, g.stream));
     }
     p.fold_sync = (unsigned *)g.fold_sync.p;
+  }
+  if (g.peers.on && g.peers.world > 1 && (p.outputs & OUT_REPORT)) {
+    // the launch also merges the dense vector with the other ranks' (person_staged.cuh, staged_peer_merge): every
+    // rank must make the same sequence of such calls
+    if (p.n == 0) return fail(MSIM_ERR_ARG, "peer merge: every rank needs at least one person");
+    if (cells + N_COUNTS > PEER_CAP) return fail(MSIM_ERR_ARG, "peer merge: report too large for the mailbox");
+    const size_t flags_at = sizeof(double) * 2 * (size_t)g.peers.world * PEER_CAP;
+    for (int r = 0; r < g.peers.world; r++) {
+      p.peer_mail[r] = (double *)g.peers.mapped[r];
+      p.peer_flag[r] = (unsigned *)((char *)g.peers.mapped[r] + flags_at);
+    }
+    p.peer_rank = g.peers.rank;
+    p.peer_world = g.peers.world;
+    p.peer_cap = PEER_CAP;
+    p.peer_total = cells + N_COUNTS;
+    p.peer_epoch = ++g.peers.epoch;
   }
   CK(cudaEventRecord(g.ev0, g.stream));
   if (p.n > 0) {

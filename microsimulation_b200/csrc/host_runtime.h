@@ -45,6 +45,14 @@ struct Ctx {
       calib_par, uniforms, first_end, first_tag, ov_fill, ov_tag, ov_start, ov_end, aux, code_in, code_out, sgeom,
       indiv, gsm_model, gsm_data, gsm_in, gsm_out, slices, fold_sync, carry_tiles;
   double last_small[16] = {0};  // the flag block as finish_run read it last
+  // merge across the GPUs of a node inside the person-r launch (msim_peer_*, person_staged.cuh)
+  struct Peers {
+    int rank = 0, world = 0;
+    bool on = false;
+    void *local = nullptr;           // this rank's mailbox (cudaMalloc)
+    void *mapped[8] = {nullptr};     // every rank's mailbox in this process's address space (own = local)
+    unsigned epoch = 0;
+  } peers;
   int person_kernel = 0;  // 0 = staged schedule (person_staged.cuh), 1 = generic cohort kernel
   bool last_staged = false;
   double plan_rows = 1.25, plan_extra_rows = 0.26;  // row-log buffer planning (msim_set_rowlog_plan)

@@ -146,6 +146,7 @@ struct alignas(16) WarpRows {
   uint32_t x_meta[XROWS][32];
 };
 constexpr int FOLD_GROUP = 16;  // blocks whose report slices are added by the last of them to finish
+constexpr int PEER_MAX = 8;     // GPUs of one node that merge their result vectors inside the launch
 
 struct StagedParams {
   StreamStart st;  // stride = M^(gridDim.x*SBLOCK)
@@ -168,6 +169,12 @@ struct StagedParams {
   double *ov_start, *ov_end;
   unsigned *ov_fill;           // [chunks] entries appended to each chunk's region (may exceed ov_cap: then the run is repeated)
   int ov_cap;
+  // merge of the dense vector across the GPUs of a node INSIDE this launch (msim_peer_*, below): every rank's mailbox
+  // as mapped into this process (NVLink peer memory), peer_world <= 1 = no merge
+  double *peer_mail[PEER_MAX];    // [2][peer_world][peer_cap] doubles
+  unsigned *peer_flag[PEER_MAX];  // [2][peer_world] epochs
+  int peer_rank, peer_world, peer_cap, peer_total;
+  unsigned peer_epoch;
 };
 
 // Report accumulators of a block.  Counters: tables in shared memory laid out by the model's reachable states and
@@ -341,6 +348,66 @@ inline size_t staged_counter_bytes(const ReportGeom &g, const ReportCompact &cm)
   return sizeof(int) * (size_t)(2 * cm.n_states + cm.n_pairs) * g.n_bin;
 }
 inline int staged_slice_doubles(const ReportGeom &g, const ReportCompact &cm) { return 2 * cm.n_states * g.n_bin; }
+
+// ---- all-reduce of the dense vector over NVLink peer memory, by the block that finished the fold ------------------
+// Every rank owns a mailbox (cudaMalloc + CUDA IPC, mapped into every other rank's process) with one slot per source
+// rank and epoch parity.  The last block of rank r: (1) stores its vector into slot r of every peer's mailbox and, after
+// a system-scope fence, the launch's epoch into the matching flag; (2) waits until every peer's flag in its OWN mailbox
+// shows the epoch; (3) adds the vectors in rank order into `dense` — the same order on every rank, so all ranks
+// hold bit-identical sums.  One step of a sharded run is then ONE launch (no NCCL kernel, no second launch): what the
+// strong-scaling run (1e8 persons over 8 GPUs, 0.6 ms per step) needs.  Slots alternate with the epoch's parity: a
+// rank can only be one launch ahead of a peer (it needs that peer's vector to finish its own launch), so the slot it
+// writes for launch e + 1 is never the one the peer may still be reading for launch e.  A peer that does not show up
+// within PEER_TIMEOUT_NS raises MSIM_ERR_PEER instead of hanging the GPU.
+constexpr unsigned long long PEER_TIMEOUT_NS = 4000000000ull;
+constexpr int ERR_PEER = -9;  // MSIM_ERR_PEER
+
+__device__ __forceinline__ unsigned peer_ld_acquire(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void peer_st_release(unsigned *p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long peer_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __noinline__ void staged_peer_merge(const StagedParams &p) {
+  const int tid = threadIdx.x, W = p.peer_world, me = p.peer_rank;
+  const size_t par = (size_t)(p.peer_epoch & 1u) * (size_t)W;
+  __threadfence();
+  __syncthreads();  // this block's own stores to `dense` (the fold) are visible to all its threads
+  for (int k = tid; k < p.peer_total; k += SBLOCK) {
+    const double v = __ldcg(&p.dense[k]);
+    for (int r = 0; r < W; r++)
+      if (r != me) p.peer_mail[r][(par + me) * (size_t)p.peer_cap + k] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < W && tid != me) {
+    peer_st_release(&p.peer_flag[tid][par + me], p.peer_epoch);
+    const unsigned *mine = &p.peer_flag[me][par + tid];
+    const unsigned long long t0 = peer_now_ns();
+    while (peer_ld_acquire(mine) != p.peer_epoch) {
+      if (peer_now_ns() - t0 > PEER_TIMEOUT_NS) {
+        atomicCAS(p.error, 0, ERR_PEER);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  const double *box = p.peer_mail[me];
+  for (int k = tid; k < p.peer_total; k += SBLOCK) {
+    const double own = __ldcg(&p.dense[k]);
+    double t = 0.0;
+    for (int r = 0; r < W; r++) t += (r == me) ? own : __ldcg(&box[(par + r) * (size_t)p.peer_cap + k]);
+    p.dense[k] = t;
+  }
+}
 
 template <unsigned OUT>
 __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const __grid_constant__ StagedParams p) {
@@ -576,6 +643,7 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
     p.dense[(tb == 0 ? p.geom.off_pt : p.geom.off_ut) + (int)s_cm.slot_state[slot] * nb + b] = t;
   }
   if (tid == 0) p.fold_sync[n_groups] = 0;
+  if (p.peer_world > 1) staged_peer_merge(p);
 }
 
 // ---- row log passes -----------------------------------------------------------

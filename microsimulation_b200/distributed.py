@@ -55,6 +55,57 @@ def _gpu_compute(seed, first, count, outputs, discount_rate):
     return t, res.dims, res.n_rows
 
 
+_peer_group_ready = False
+
+
+def enable_peer_merge(group=None):
+    """Sets up the merge INSIDE the person-r launch (csrc/person_staged.cuh, staged_peer_merge): every rank allocates a
+    mailbox, the CUDA IPC handles go round once (all_gather_object), every rank maps the others' mailboxes over
+    NVLink.  After this, person-r runs with a report leave the sum over all ranks in their dense vector — no
+    all-reduce to enqueue.  One node, at most 8 ranks, one process per GPU; returns False (and changes nothing) where
+    that does not hold or peer memory cannot be mapped."""
+    global _peer_group_ready
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        return False
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world < 2 or world > 8:
+        return False
+    ok = True
+    handle = b""
+    try:
+        handle = api.peer_export(world)
+    except RuntimeError:
+        ok = False
+    handles = [None] * world
+    dist.all_gather_object(handles, handle if ok else None, group=group)
+    if any(h is None for h in handles):
+        ok = False
+    if ok:
+        try:
+            api.peer_import(rank, world, handles)
+        except RuntimeError:
+            ok = False
+    flags = [None] * world
+    dist.all_gather_object(flags, ok, group=group)  # also the barrier: every mailbox is zeroed and mapped from here on
+    if not all(flags):
+        try:
+            api.peer_close()
+        except RuntimeError:
+            pass
+        return False
+    api.peer_merge(True)
+    _peer_group_ready = True
+    return True
+
+
+def disable_peer_merge():
+    global _peer_group_ready
+    if _peer_group_ready:
+        api.peer_merge(False)
+    _peer_group_ready = False
+
+
 def person_simulation_sharded(n, seed=(12345,) * 6, outputs=MSIM_OUT_REPORT | MSIM_OUT_COUNTS, discount_rate=0.0,
                               first_person=0, group=None, compute=None):
     """callPersonSimulation over all ranks of `group`.
@@ -68,7 +119,8 @@ def person_simulation_sharded(n, seed=(12345,) * 6, outputs=MSIM_OUT_REPORT | MS
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     first, count = shard_range(n, rank, world)
     acc, dims, n_rows = (compute or _gpu_compute)(seed, first_person + first, count, outputs, discount_rate)
-    if world > 1:
+    merged_in_launch = _peer_group_ready and compute is None and bool(outputs & MSIM_OUT_REPORT)
+    if world > 1 and not merged_in_launch:
         dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)  # the single collective
     host = acc.detach().cpu().numpy()
     counts = host[-9:].copy()

@@ -16,6 +16,34 @@ m.init(local)
 api.set_stream(torch.cuda.current_stream().cuda_stream)
 n = 3_000_001
 rep, counts, rows = person_simulation_sharded(n, discount_rate=0.03)
+# the same with the merge inside the launch (NVLink peer memory) instead of the NCCL all-reduce: same tables, the same
+# bits on every rank, many launches in a row (mailbox slots alternate), ragged shards
+from microsimulation_b200 import distributed as D
+if D.enable_peer_merge():
+    for n2 in (n, 1000 * world + 3, n, 5 * world, n):
+        rep2, counts2, _ = person_simulation_sharded(n2, discount_rate=0.03)
+    assert np.array_equal(counts2[:8], counts[:8]), (counts2, counts)
+    for tb in ("events", "prev"):
+        for k in rep[tb]:
+            assert np.array_equal(rep2[tb][k], rep[tb][k]), (tb, k)
+    for tb, k in (("pt", "pt"), ("ut", "utility")):
+        np.testing.assert_allclose(rep2[tb][k], rep[tb][k], rtol=1e-12)
+    ptr, nd = api.dense_device_ptr()
+    mine = torch.as_tensor(D._CudaBuffer(ptr, nd), device="cuda").clone()
+    every = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine)
+    assert all(torch.equal(e.view(torch.int64), mine.view(torch.int64)) for e in every)
+    for _ in range(200):  # back to back, asynchronously: a rank may run one launch ahead of its peers
+        api.person_enqueue(12345, rank * 1000, 1000, api.MSIM_OUT_REPORT | api.MSIM_OUT_COUNTS, 0.03)
+    api.sync()
+    ptr, nd = api.dense_device_ptr()
+    v = torch.as_tensor(D._CudaBuffer(ptr, nd), device="cuda").clone()
+    assert float(v[-9] + v[-8]) == 1000.0 * world, float(v[-9] + v[-8])
+    D.disable_peer_merge()
+    if rank == 0:
+        print("in-launch merge ok: world %d" % world)
+elif rank == 0:
+    print("in-launch merge NOT available on this box (peer memory could not be mapped)")
 pars = np.tile(np.array([4, 0.5, 0.05, 10, 3, 0.5]), (8, 1)) * (1 + 0.2 * (np.random.RandomState(1).rand(8, 6) - 0.5))
 cal = calibration_sweep_sharded(12345, pars, 200_001)
 if rank == 0:
