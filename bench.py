@@ -202,7 +202,8 @@ def merge_check(P, first, outputs, rate, world):
     import microsimulation_b200.api as api
     from microsimulation_b200.distributed import _CudaBuffer
     if PEER_MERGE:
-        api.peer_merge(False)
+        api.peer_flush()
+        api.peer_merge(0)
     res = api.person_run_device(SEED, first, P, outputs, rate)
     ptr, n = api.dense_device_ptr()
     t = torch.as_tensor(_CudaBuffer(ptr, n), device="cuda")
@@ -224,17 +225,26 @@ def merge_check(P, first, outputs, rate, world):
            "deaths_equal_persons": deaths == float(world) * P, "persons": world * P, "ranks": world,
            "ok": ints_equal and fp_diff <= 1e-12 and deaths == float(world) * P}
     if PEER_MERGE:
-        api.peer_merge(True)
-        api.person_run_device(SEED, first, P, outputs, rate)
-        ptr, n = api.dense_device_ptr()
+        api.peer_merge(2)
+        api.person_enqueue(SEED, first, P, outputs, rate)  # two steps: the first one's sum is formed inside the second launch,
+        api.person_enqueue(SEED, first, P, outputs, rate)  # the second one's by the flush
+        api.sync()
+        ptr, n = api.peer_result_ptr()
+        first_step = torch.as_tensor(_CudaBuffer(ptr, n), device="cuda").clone()
+        api.peer_flush()
+        api.sync()
         v = torch.as_tensor(_CudaBuffer(ptr, n), device="cuda").clone()
         i2, f2, d2 = against_total(v)
         every = [torch.empty_like(v) for _ in range(world)]
         dist.all_gather(every, v)
         same_bits = all(bool(torch.equal(e.view(torch.int64), v.view(torch.int64))) for e in every)
+        # the two steps are the same simulation: same bits, except the last cell (sum of end times: added across blocks
+        # by atomics, in whatever order they arrive)
+        same_steps = bool(torch.equal(first_step[:-1].view(torch.int64), v[:-1].view(torch.int64))) and \
+            abs(float(first_step[-1]) - float(v[-1])) <= 1e-12 * abs(float(v[-1]))
         out["in_launch_merge"] = {"equals_sum_of_ranks_int_cells": i2, "fp_cells_max_rel_diff": f2, "deaths_equal_persons": d2 == float(world) * P,
-                                  "identical_bits_on_all_ranks": same_bits}
-        out["ok"] = out["ok"] and i2 and f2 <= 1e-12 and d2 == float(world) * P and same_bits
+                                  "identical_bits_on_all_ranks": same_bits, "sum_formed_in_next_launch_equals_flushed_sum": same_steps}
+        out["ok"] = out["ok"] and i2 and f2 <= 1e-12 and d2 == float(world) * P and same_bits and same_steps
     return out
 
 
@@ -260,10 +270,17 @@ def measure(args, workload, steps, P, rank, local, world, clocks_wanted, with_e2
             ptr, n = api.dense_device_ptr()
             dist.all_reduce(torch.as_tensor(_CudaBuffer(ptr, n), device="cuda"))
 
+    def finish():
+        # with the merge inside the launches, a launch adds up what the ranks sent in the launch before it (nobody waits
+        # for a slower rank): the last step of a sequence needs one small launch more
+        if world > 1 and report_mode and PEER_MERGE:
+            api.peer_flush()
+
     # ---- warm-up (>= 3 steps)
     for _ in range(max(args.warmup, 3)):
         api.person_run_device(SEED, first, P, outputs, rate)
         merge()
+    finish()
     rows = api.person_run_device(SEED, first, P, outputs, rate).n_rows
     kernel_ms_one = api.last_kernel_ms()  # CUDA events around this workload's kernels, one step
 
@@ -280,6 +297,7 @@ def measure(args, workload, steps, P, rank, local, world, clocks_wanted, with_e2
     for _ in range(steps):
         api.person_enqueue(SEED, first, P, outputs, rate)
         merge()
+    finish()
     ev1.record()
     barrier()
     api.sync()
@@ -304,7 +322,13 @@ def measure(args, workload, steps, P, rank, local, world, clocks_wanted, with_e2
         res = api.person_run_device(SEED, first, P, outputs, rate)
         if report_mode:
             merge()
-            dense = api.dense_fetch(res.dims.n_doubles)   # D2H of the accumulators
+            finish()
+            if world > 1 and PEER_MERGE:
+                from microsimulation_b200.distributed import _CudaBuffer
+                ptr, nd = api.peer_result_ptr()
+                dense = torch.as_tensor(_CudaBuffer(ptr, nd), device="cuda").cpu().numpy()  # D2H of the merged accumulators
+            else:
+                dense = api.dense_fetch(res.dims.n_doubles)   # D2H of the accumulators
             api.dense_to_report(dense, res.dims, rate)     # the reference's sparse tables (host)
             return dense.nbytes
         d, tab = api.person_fetch_rowlog(copy=False)       # D2H of every row into page-locked host memory
@@ -476,7 +500,7 @@ def run_ours(args):
     global PEER_MERGE
     if world > 1 and not args.nccl_merge:
         from microsimulation_b200 import distributed as D
-        PEER_MERGE = D.enable_peer_merge()  # report runs are merged inside their launch (NVLink peer memory)
+        PEER_MERGE = D.enable_peer_merge(mode=2)  # report runs are merged inside the launches (NVLink peer memory)
     P = args.persons
     few = max(3, min(args.steps, 5))
     if args.workload == "calib":
@@ -499,16 +523,17 @@ def run_ours(args):
         strong = measure(args, args.workload, args.steps, TOTAL_STRONG // world, rank, local, world, False)
         if PEER_MERGE and args.workload == "report":
             # the same steps with the merge as a separate NCCL all-reduce after every launch, for comparison
-            import microsimulation_b200.api as api_
-            api_.peer_merge(False)
+            api.peer_flush()
+            api.peer_merge(0)
             PEER_MERGE = False
             try:
                 strong["nccl_ms_per_step"] = measure(args, args.workload, few, TOTAL_STRONG // world, rank, local, world, False)["ms_per_step"]
             finally:
-                api_.peer_merge(True)
+                api.peer_merge(2)
                 PEER_MERGE = True
     if PEER_MERGE:
-        api.peer_merge(False)  # what follows runs on rank 0 alone (CPU baseline checks) or does not involve person-r
+        api.peer_flush()
+        api.peer_merge(0)  # what follows runs on rank 0 alone (CPU baseline checks) or does not involve person-r
     calib = None
     if not args.no_calib:
         calib = measure_calib(args, 3, rank, world, with_cpu=not args.no_cpu_baseline)
@@ -547,8 +572,9 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.workload) + "; %d persons per GPU per step" % P,
                        "seed": "12345x6", "persons_per_gpu": P, "rows_per_step_rank0": main["rows"],
-                       "merge": (("inside the simulation launch: the block that finishes the fold exchanges the accumulator vector with "
-                                  "the other ranks over NVLink peer memory and adds them in rank order" if PEER_MERGE else
+                       "merge": (("inside the simulation launches: the block that finishes the fold sends the accumulator vector to the other "
+                                  "ranks over NVLink peer memory; the next launch (or, after the last step, one small launch) adds the "
+                                  "ranks' vectors in rank order" if PEER_MERGE else
                                   "one NCCL all-reduce(sum, f64) of the accumulator vector per step") if report_mode and world > 1
                                  else ("none (one GPU)" if world == 1 else "none: row logs stay sharded")),
                        "l2": ("no input: each person is generated from (seed, index); outputs are KB-sized tables, nothing to flush"

@@ -104,11 +104,23 @@ int msim_set_stream(void *cuda_stream, int use_own);
  *                                            same sequence of such runs; a rank
  *                                            that stays away for 4 s makes the
  *                                            others fail with MSIM_ERR_PEER.
+ *   msim_peer_merge(2)                       the same, one launch later: run k
+ *                                            adds up what the ranks sent in run
+ *                                            k - 1 (nobody waits for a slower
+ *                                            rank) and leaves it in the vector
+ *                                            msim_peer_result_ptr names; the
+ *                                            dense vector keeps this rank's own
+ *                                            sums.  msim_peer_flush() adds up
+ *                                            the last run's (one small launch)
+ *                                            — after it the vector holds the
+ *                                            latest run's merged result.
  *   msim_peer_merge(0) / msim_peer_close()   stop merging / release. */
 #define MSIM_PEER_HANDLE_BYTES 64
 int msim_peer_export(int32_t world, void *handle_out);
 int msim_peer_import(int32_t rank, int32_t world, const void *handles);
-int msim_peer_merge(int on);
+int msim_peer_merge(int mode);
+int msim_peer_flush(void);
+int msim_peer_result_ptr(double **d_vector, int64_t *n_doubles);
 int msim_peer_close(void);
 /* Number of kernels this library has launched since it was loaded. */
 int64_t msim_launch_count(void);

@@ -427,8 +427,21 @@ def peer_import(rank, world, handles):
     check(load().msim_peer_import(C.c_int32(int(rank)), C.c_int32(int(world)), buf))
 
 
-def peer_merge(on=True):
-    check(load().msim_peer_merge(C.c_int(1 if on else 0)))
+def peer_merge(mode=1):
+    """0 / False: off; 1 / True: every report run ends with the sum over all ranks in its dense vector; 2: the sum of
+    run k is formed during run k + 1 (nobody waits for a slower rank) or by peer_flush(), in peer_result_ptr()'s vector."""
+    check(load().msim_peer_merge(C.c_int(int(mode))))
+
+
+def peer_flush():
+    check(load().msim_peer_flush())
+
+
+def peer_result_ptr():
+    p = C.POINTER(C.c_double)()
+    n = C.c_int64()
+    check(load().msim_peer_result_ptr(C.byref(p), C.byref(n)))
+    return C.cast(p, C.c_void_p).value, n.value
 
 
 def peer_close():

@@ -121,9 +121,19 @@ int msim_set_mt_parallel(int on) {
 
 int msim_peer_export(int32_t world, void *handle_out) { return peer_export(world, handle_out); }
 int msim_peer_import(int32_t rank, int32_t world, const void *handles) { return peer_import(rank, world, handles); }
-int msim_peer_merge(int on) {
-  if (on && (!g.peers.local || !g.peers.mapped[g.peers.rank])) return fail(MSIM_ERR_STATE, "peer merge: msim_peer_export and msim_peer_import first");
-  g.peers.on = on != 0;
+int msim_peer_merge(int mode) {
+  if (mode < 0 || mode > 2) return fail(MSIM_ERR_ARG, "peer merge: mode 0 (off), 1 (merged when the launch ends) or 2 (merged one launch later)");
+  if (mode && (!g.peers.local || !g.peers.mapped[g.peers.rank])) return fail(MSIM_ERR_STATE, "peer merge: msim_peer_export and msim_peer_import first");
+  if (g.peers.mode == 2 && mode != 2 && g.peers.epoch != g.peers.collected) return fail(MSIM_ERR_STATE, "peer merge: msim_peer_flush first");
+  g.peers.mode = mode;
+  return MSIM_OK;
+}
+int msim_peer_flush(void) { return peer_flush(); }
+int msim_peer_result_ptr(double **d_vector, int64_t *n_doubles) {
+  if (!d_vector || !n_doubles) return fail(MSIM_ERR_ARG, "null argument");
+  if (g.peers.mode != 2 || !g.peers.out) return fail(MSIM_ERR_STATE, "peer merge: no run in mode 2 yet");
+  *d_vector = g.peers.out;
+  *n_doubles = g.peers.out_doubles;
   return MSIM_OK;
 }
 int msim_peer_close(void) { return peer_close(); }

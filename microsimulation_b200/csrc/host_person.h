@@ -43,9 +43,9 @@ int staged_rowpasses(int64_t n, int64_t first_person, int64_t capacity, bool cou
 }
 
 // ---- mailboxes for the in-launch merge across GPUs (person_staged.cuh, staged_peer_merge)
-constexpr int PEER_CAP = 16384;  // doubles per slot (person-r's report + counts: 9810)
+constexpr int PEER_CAP = 8192;  // values per slot, 16 bytes each (person-r's reachable report cells + counts: 2763)
 
-inline size_t peer_mailbox_bytes(int world) { return sizeof(double) * 2 * (size_t)world * PEER_CAP + sizeof(unsigned) * 2 * (size_t)world + 256; }
+inline size_t peer_mailbox_bytes(int world) { return 16 * 2 * (size_t)world * PEER_CAP; }
 
 int peer_close() {
   for (int r = 0; r < 8; r++) {
@@ -53,6 +53,7 @@ int peer_close() {
     g.peers.mapped[r] = nullptr;
   }
   if (g.peers.local) cudaFree(g.peers.local);
+  if (g.peers.out) cudaFree(g.peers.out);
   g.peers = Ctx::Peers();
   return MSIM_OK;
 }
@@ -87,6 +88,21 @@ int peer_import(int rank, int world, const void *handles) {
   }
   g.peers.rank = rank;
   g.peers.epoch = 0;
+  return MSIM_OK;
+}
+
+// mode 2: the vectors of the last launch, which no later launch has added up yet
+int peer_flush() {
+  if (g.peers.mode != 2 || g.peers.world < 2 || g.peers.epoch == g.peers.collected) return MSIM_OK;
+  PeerCollectParams q;
+  memset(&q, 0, sizeof q);
+  q.peer = g.peers_last;
+  q.peer.epoch = g.peers.epoch;
+  q.error = small_view().error;
+  peer_collect_kernel<<<1, 256, 0, g.stream>>>(q);
+  CK(cudaGetLastError());
+  g.launches++;
+  g.peers.collected = g.peers.epoch;
   return MSIM_OK;
 }
 
@@ -184,28 +200,50 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
     const size_t bytes = sizeof(double) * (size_t)grid * staged_slice_doubles(p.geom, p.compact);
     if ((rc = ensure(g.slices, bytes))) return rc;
     p.slices = (double *)g.slices.p;
-    const size_t sync_bytes = sizeof(unsigned) * (size_t)((grid + FOLD_GROUP - 1) / FOLD_GROUP + 1);
+    const size_t sync_bytes = sizeof(unsigned) * (size_t)((grid + FOLD_GROUP - 1) / FOLD_GROUP + 2);
     if (g.fold_sync.bytes < sync_bytes || !g.fold_sync.p) {  // arrival counters: zero once, every launch leaves them zero
       if ((rc = ensure(g.fold_sync, sync_bytes))) return rc;
       CK(cudaMemsetAsync(g.fold_sync.p, 0, g.fold_sync.bytes, g.stream));
     }
     p.fold_sync = (unsigned *)g.fold_sync.p;
   }
-  if (g.peers.on && g.peers.world > 1 && (p.outputs & OUT_REPORT)) {
+  if (g.peers.mode && g.peers.world > 1 && (p.outputs & OUT_REPORT)) {
     // the launch also merges the dense vector with the other ranks' (person_staged.cuh, staged_peer_merge): every
     // rank must make the same sequence of such calls
     if (p.n == 0) return fail(MSIM_ERR_ARG, "peer merge: every rank needs at least one person");
-    if (cells + N_COUNTS > PEER_CAP) return fail(MSIM_ERR_ARG, "peer merge: report too large for the mailbox");
-    const size_t flags_at = sizeof(double) * 2 * (size_t)g.peers.world * PEER_CAP;
-    for (int r = 0; r < g.peers.world; r++) {
-      p.peer_mail[r] = (double *)g.peers.mapped[r];
-      p.peer_flag[r] = (unsigned *)((char *)g.peers.mapped[r] + flags_at);
+    const int n_compact = (4 * p.compact.n_states + p.compact.n_pairs) * p.geom.n_bin + N_COUNTS;  // person_staged.cuh, peer_cell
+    if (n_compact > PEER_CAP) return fail(MSIM_ERR_ARG, "peer merge: report too large for the mailbox");
+    if (g.peers.mode == 2 && g.peers.out_doubles != cells + N_COUNTS) {
+      if (g.peers.epoch != g.peers.collected) return fail(MSIM_ERR_STATE, "peer merge: msim_peer_flush before a run with another report geometry");
+      if (g.peers.out) cudaFree(g.peers.out);
+      g.peers.out = nullptr;
+      CK(cudaMalloc((void **)&g.peers.out, sizeof(double) * (cells + N_COUNTS)));
+      CK(cudaMemsetAsync(g.peers.out, 0, sizeof(double) * (cells + N_COUNTS), g.stream));  // cells the model cannot reach stay 0
+      g.peers.out_doubles = cells + N_COUNTS;
     }
-    p.peer_rank = g.peers.rank;
-    p.peer_world = g.peers.world;
-    p.peer_cap = PEER_CAP;
-    p.peer_total = cells + N_COUNTS;
-    p.peer_epoch = ++g.peers.epoch;
+    {  // which cell of dense each entry of the travelling vector is (person_staged.cuh, peer_cell_of)
+      std::vector<int> map((size_t)n_compact);
+      for (int c = 0; c < n_compact; c++) map[c] = peer_cell_of(p.geom, p.compact, c);
+      if (map != g.peers_map) {
+        if (g.peers.epoch != g.peers.collected) return fail(MSIM_ERR_STATE, "peer merge: msim_peer_flush before a run with another report geometry");
+        if ((rc = ensure(g.peers_map_dev, sizeof(int) * map.size()))) return rc;
+        CK(cudaMemcpyAsync(g.peers_map_dev.p, map.data(), sizeof(int) * map.size(), cudaMemcpyHostToDevice, g.stream));
+        CK(cudaStreamSynchronize(g.stream));  // `map` is pageable host memory
+        g.peers_map = map;
+      }
+      p.peer.cell = (const int *)g.peers_map_dev.p;
+    }
+    for (int r = 0; r < g.peers.world; r++) p.peer.mail[r] = (unsigned long long *)g.peers.mapped[r];
+    p.peer.rank = g.peers.rank;
+    p.peer.world = g.peers.world;
+    p.peer.cap = PEER_CAP;
+    p.peer.total = n_compact;
+    p.peer.mode = g.peers.mode;
+    p.peer.out = g.peers.out;
+    p.peer.epoch = ++g.peers.epoch;
+    if (g.peers.mode == 2) g.peers.collected = p.peer.epoch - 1;  // this launch adds up the previous one's vectors
+    else g.peers.collected = p.peer.epoch;
+    g.peers_last = p.peer;
   }
   CK(cudaEventRecord(g.ev0, g.stream));
   if (p.n > 0) {

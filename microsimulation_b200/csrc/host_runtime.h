@@ -48,11 +48,17 @@ struct Ctx {
   // merge across the GPUs of a node inside the person-r launch (msim_peer_*, person_staged.cuh)
   struct Peers {
     int rank = 0, world = 0;
-    bool on = false;
+    int mode = 0;                    // 0 off, 1 merged when the launch ends, 2 merged one launch later (msim_peer_merge)
     void *local = nullptr;           // this rank's mailbox (cudaMalloc)
     void *mapped[8] = {nullptr};     // every rank's mailbox in this process's address space (own = local)
-    unsigned epoch = 0;
-  } peers;
+    unsigned epoch = 0;              // launches that sent a vector
+    unsigned collected = 0;          // mode 2: the last epoch added up into `out`
+    double *out = nullptr;           // mode 2: the merged vector (dense layout)
+    int out_doubles = 0;
+    } peers;
+  PeerParams peers_last;        // as the last merging launch got them (msim_peer_flush)
+  std::vector<int> peers_map;   // entry of the travelling vector -> cell of dense, as uploaded to peers_map_dev
+  DevBuf peers_map_dev;
   int person_kernel = 0;  // 0 = staged schedule (person_staged.cuh), 1 = generic cohort kernel
   bool last_staged = false;
   double plan_rows = 1.25, plan_extra_rows = 0.26;  // row-log buffer planning (msim_set_rowlog_plan)

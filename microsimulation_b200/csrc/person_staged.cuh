@@ -146,7 +146,19 @@ struct alignas(16) WarpRows {
   uint32_t x_meta[XROWS][32];
 };
 constexpr int FOLD_GROUP = 16;  // blocks whose report slices are added by the last of them to finish
-constexpr int PEER_MAX = 8;     // GPUs of one node that merge their result vectors inside the launch
+
+constexpr int PEER_MAX = 8;  // GPUs of one node that merge their result vectors inside the launch
+// Merge of a sharded run's result vector across the GPUs of one node (msim_peer_*; device side further down): every
+// rank's mailbox as mapped into this process (NVLink peer memory).
+struct PeerParams {
+  unsigned long long *mail[PEER_MAX];  // [2][world][cap] pairs of words (payload 32 bits | epoch << 32)
+  int rank, world, cap, total;         // total: reachable cells + counts (peer_cell)
+  unsigned epoch;                      // of this launch: 1, 2, ...
+  int mode;                            // 1: this launch's vectors are exchanged and added before it ends (-> dense);
+                                       // 2: this launch adds the PREVIOUS launch's vectors (-> out) and sends its own
+  double *out;                         // mode 2: the merged vector, in dense's layout
+  const int *cell;                     // [total] entry of the vector that travels -> cell of dense (peer_cell_of, host)
+};
 
 struct StagedParams {
   StreamStart st;  // stride = M^(gridDim.x*SBLOCK)
@@ -157,7 +169,7 @@ struct StagedParams {
   ReportCompact compact;  // the rows of the report this model can reach (block tables are laid out by these)
   double *dense;   // dense report accumulators in global memory (zeroed before launch)
   double *slices;  // gridDim.x slices of 2 * compact.n_states * n_bin doubles (pt, ut); every block zeroes its own
-  unsigned *fold_sync;  // [groups + 1] arrival counters of the fold, zero before the first launch, left zero by every launch
+  unsigned *fold_sync;  // [groups + 2] arrival counters of the fold (+ one for the peer merge), zero before the first launch, left zero by every launch
   double *counts;  // N_COUNTS doubles
   double *indiv;   // [n] every individual's discounted total at individualReset (outputs & 8), NaN below startReportAge
   int *error;
@@ -169,12 +181,7 @@ struct StagedParams {
   double *ov_start, *ov_end;
   unsigned *ov_fill;           // [chunks] entries appended to each chunk's region (may exceed ov_cap: then the run is repeated)
   int ov_cap;
-  // merge of the dense vector across the GPUs of a node INSIDE this launch (msim_peer_*, below): every rank's mailbox
-  // as mapped into this process (NVLink peer memory), peer_world <= 1 = no merge
-  double *peer_mail[PEER_MAX];    // [2][peer_world][peer_cap] doubles
-  unsigned *peer_flag[PEER_MAX];  // [2][peer_world] epochs
-  int peer_rank, peer_world, peer_cap, peer_total;
-  unsigned peer_epoch;
+  PeerParams peer;  // merge of the dense vector across the GPUs of a node INSIDE this launch (below); world <= 1 = none
 };
 
 // Report accumulators of a block.  Counters: tables in shared memory laid out by the model's reachable states and
@@ -351,24 +358,30 @@ inline int staged_slice_doubles(const ReportGeom &g, const ReportCompact &cm) { 
 
 // ---- all-reduce of the dense vector over NVLink peer memory, by the block that finished the fold ------------------
 // Every rank owns a mailbox (cudaMalloc + CUDA IPC, mapped into every other rank's process) with one slot per source
-// rank and epoch parity.  The last block of rank r: (1) stores its vector into slot r of every peer's mailbox and, after
-// a system-scope fence, the launch's epoch into the matching flag; (2) waits until every peer's flag in its OWN mailbox
-// shows the epoch; (3) adds the vectors in rank order into `dense` — the same order on every rank, so all ranks
-// hold bit-identical sums.  One step of a sharded run is then ONE launch (no NCCL kernel, no second launch): what the
-// strong-scaling run (1e8 persons over 8 GPUs, 0.6 ms per step) needs.  Slots alternate with the epoch's parity: a
-// rank can only be one launch ahead of a peer (it needs that peer's vector to finish its own launch), so the slot it
-// writes for launch e + 1 is never the one the peer may still be reading for launch e.  A peer that does not show up
+// rank and epoch parity.  SEND: the last block of rank r stores its vector into slot r of every rank's mailbox (its
+// own included).  COLLECT: it reads all ranks' vectors of one epoch from its OWN mailbox and adds them in rank order —
+// the same order on every rank, so all ranks hold bit-identical sums.  No flags and no fences: every 8-byte word that
+// travels carries 32 bits of payload and the 32-bit epoch (a double = two such words, one 16-byte store), an 8-byte
+// store arrives whole, and the reader polls each word until it shows the epoch — the latency of ONE store across
+// NVLink instead of store, fence (a round trip), flag, fence.
+//   mode 1: send(e), collect(e) -> dense.  The launch ends with the merged vector in place; it waits for the slowest
+//           rank (as an all-reduce after the launch would).
+//   mode 2: collect(e - 1) -> out, send(e).  A launch adds up what the ranks sent a whole launch ago, so nobody waits
+//           and the ranks' launches need not end together; the result of launch e is complete after launch e + 1, or
+//           after peer_collect_kernel (msim_peer_flush) at the end of a sequence.
+// Either way a step of a sharded run is ONE launch (no NCCL kernel): what the strong-scaling run (1e8 persons over
+// 8 GPUs, 0.65 ms per step) needs.  Slots alternate with the epoch's parity, and a rank sends epoch e only after it has
+// collected e - 1 (mode 2) or e (mode 1) from every peer — which those peers sent after they were done with the slot's
+// previous content — so a slot is never overwritten while its owner may still read it.  A peer that does not show up
 // within PEER_TIMEOUT_NS raises MSIM_ERR_PEER instead of hanging the GPU.
 constexpr unsigned long long PEER_TIMEOUT_NS = 4000000000ull;
 constexpr int ERR_PEER = -9;  // MSIM_ERR_PEER
 
-__device__ __forceinline__ unsigned peer_ld_acquire(const unsigned *p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ void peer_store_pair(unsigned long long *p, unsigned long long w0, unsigned long long w1) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
 }
-__device__ __forceinline__ void peer_st_release(unsigned *p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void peer_load_pair(const unsigned long long *p, unsigned long long &w0, unsigned long long &w1) {
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
 }
 __device__ __forceinline__ unsigned long long peer_now_ns() {
   unsigned long long t;
@@ -376,37 +389,104 @@ __device__ __forceinline__ unsigned long long peer_now_ns() {
   return t;
 }
 
-__device__ __noinline__ void staged_peer_merge(const StagedParams &p) {
-  const int tid = threadIdx.x, W = p.peer_world, me = p.peer_rank;
-  const size_t par = (size_t)(p.peer_epoch & 1u) * (size_t)W;
-  __threadfence();
-  __syncthreads();  // this block's own stores to `dense` (the fold) are visible to all its threads
-  for (int k = tid; k < p.peer_total; k += SBLOCK) {
-    const double v = __ldcg(&p.dense[k]);
-    for (int r = 0; r < W; r++)
-      if (r != me) p.peer_mail[r][(par + me) * (size_t)p.peer_cap + k] = v;
+// What travels is the vector WITHOUT the cells the model cannot reach (ReportCompact: person-r uses 4 of 8 states and
+// 11 of 64 (state, event) pairs — 2 763 of 9 810 doubles): entry c of the compact vector is cell q.cell[c] of `dense`
+// (a table the host fills with peer_cell_of: one block does the whole exchange, index arithmetic would be in its way).
+inline int peer_cell_of(const ReportGeom &g, const ReportCompact &cm, int c) {
+  const int nb = g.n_bin, n_sb = cm.n_states * nb;
+  if (c < 4 * n_sb) {
+    const int t = c / n_sb, r = c - t * n_sb, slot = r / nb, b = r - slot * nb;
+    const int off = t == 0 ? g.off_pt : t == 1 ? g.off_ut : t == 2 ? g.off_dstart : g.off_noedge;
+    return off + (int)cm.slot_state[slot] * nb + b;
   }
-  __threadfence_system();
-  __syncthreads();
-  if (tid < W && tid != me) {
-    peer_st_release(&p.peer_flag[tid][par + me], p.peer_epoch);
-    const unsigned *mine = &p.peer_flag[me][par + tid];
-    const unsigned long long t0 = peer_now_ns();
-    while (peer_ld_acquire(mine) != p.peer_epoch) {
-      if (peer_now_ns() - t0 > PEER_TIMEOUT_NS) {
-        atomicCAS(p.error, 0, ERR_PEER);
-        break;
-      }
+  c -= 4 * n_sb;
+  if (c < cm.n_pairs * nb) {
+    const int ps = c / nb, b = c - ps * nb;
+    return g.off_events + ((int)cm.pair_state[ps] * g.n_event + (int)cm.pair_event[ps]) * nb + b;
+  }
+  return g.total + (c - cm.n_pairs * nb);  // the counts follow the report's cells
+}
+
+// this rank's vector (from `dense`) into slot `rank` of every mailbox, tagged with `epoch`
+template <int THREADS>
+__device__ __forceinline__ void peer_send(const PeerParams &q, const double *dense, unsigned epoch) {
+  const size_t slot = ((size_t)(epoch & 1u) * q.world + q.rank) * (size_t)q.cap;
+  const unsigned long long ep = (unsigned long long)epoch << 32;
+  for (int c0 = threadIdx.x; c0 < q.total; c0 += 4 * THREADS) {  // four entries' values requested together, then sent
+    double v[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int c = c0 + i * THREADS;
+      v[i] = c < q.total ? __ldcg(&dense[__ldg(&q.cell[c])]) : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int c = c0 + i * THREADS;
+      if (c >= q.total) break;
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(v[i]);
+      const unsigned long long w0 = (bits & 0xffffffffull) | ep, w1 = (bits >> 32) | ep;
+      for (int r = 0; r < q.world; r++) peer_store_pair(q.mail[r] + 2 * (slot + c), w0, w1);
     }
   }
-  __syncthreads();
-  const double *box = p.peer_mail[me];
-  for (int k = tid; k < p.peer_total; k += SBLOCK) {
-    const double own = __ldcg(&p.dense[k]);
+}
+
+// all ranks' vectors of `epoch`, from this rank's mailbox, added in rank order into dst (dense's layout)
+template <int THREADS>
+__device__ __forceinline__ void peer_collect(const PeerParams &q, double *dst, unsigned epoch, int *error) {
+  const unsigned long long *box = q.mail[q.rank] + 2 * ((size_t)(epoch & 1u) * q.world) * (size_t)q.cap;
+  const unsigned long long ep = (unsigned long long)epoch << 32;
+  const unsigned long long t0 = peer_now_ns();
+  bool late = false;
+  for (int c = threadIdx.x; c < q.total; c += THREADS) {
+    const int cell = __ldg(&q.cell[c]);
+    // all ranks' words for this entry are requested before the first is looked at (one memory latency, not `world`)
+    unsigned long long w0[PEER_MAX], w1[PEER_MAX];
+#pragma unroll
+    for (int r = 0; r < PEER_MAX; r++)
+      if (r < q.world) peer_load_pair(box + 2 * ((size_t)r * q.cap + c), w0[r], w1[r]);
     double t = 0.0;
-    for (int r = 0; r < W; r++) t += (r == me) ? own : __ldcg(&box[(par + r) * (size_t)p.peer_cap + k]);
-    p.dense[k] = t;
+#pragma unroll
+    for (int r = 0; r < PEER_MAX; r++) {
+      if (r >= q.world) break;
+      unsigned spins = 0;
+      while ((w0[r] & 0xffffffff00000000ull) != ep || (w1[r] & 0xffffffff00000000ull) != ep) {
+        if (late || ((++spins & 0xfffu) == 0 && peer_now_ns() - t0 > PEER_TIMEOUT_NS)) {
+          late = true;
+          break;
+        }
+        peer_load_pair(box + 2 * ((size_t)r * q.cap + c), w0[r], w1[r]);
+      }
+      t += __longlong_as_double((long long)((w0[r] & 0xffffffffull) | (w1[r] << 32)));
+    }
+    dst[cell] = t;
   }
+  if (late) atomicCAS(error, 0, ERR_PEER);
+}
+
+// by the block that finished the fold: dense is complete
+__device__ __noinline__ void staged_peer_merge(const StagedParams &p) {
+  __threadfence();
+  __syncthreads();  // this block's own stores to `dense` (the fold) are visible to all its threads
+  peer_send<SBLOCK>(p.peer, p.dense, p.peer.epoch);
+  if (p.peer.mode == 1) {
+    __syncthreads();  // dense is overwritten below: every thread has read what it sends
+    peer_collect<SBLOCK>(p.peer, p.dense, p.peer.epoch, p.error);
+  }
+}
+
+// mode 2, by the FIRST block of the launch to finish its persons: the previous launch's vectors, while the other blocks
+// are still at work (it does not need this launch's results, so it is kept off the launch's critical path)
+__device__ __noinline__ void staged_peer_collect_previous(const StagedParams &p) {
+  peer_collect<SBLOCK>(p.peer, p.peer.out, p.peer.epoch - 1, p.error);
+}
+
+// the last launch's vectors, for a sequence of mode-2 launches (msim_peer_flush)
+struct PeerCollectParams {
+  PeerParams peer;
+  int *error;
+};
+__global__ void __launch_bounds__(256) peer_collect_kernel(const __grid_constant__ PeerCollectParams p) {
+  peer_collect<256>(p.peer, p.peer.out, p.peer.epoch, p.error);
 }
 
 template <unsigned OUT>
@@ -616,6 +696,12 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
   const int n_groups = (gridDim.x + FOLD_GROUP - 1) / FOLD_GROUP;
   const int group = blockIdx.x / FOLD_GROUP, g0 = group * FOLD_GROUP;
   const int g_size = min(FOLD_GROUP, (int)gridDim.x - g0);
+  if (p.peer.world > 1 && p.peer.mode == 2 && p.peer.epoch > 1) {
+    if (tid == 0) s_last = (atomicAdd(&p.fold_sync[n_groups + 1], 1u) == 0u);  // the first to get here
+    __syncthreads();
+    if (s_last) staged_peer_collect_previous(p);
+    __syncthreads();
+  }
   __threadfence();  // this thread's REDs are performed before the arrival below is visible
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(&p.fold_sync[group], 1u) == (unsigned)(g_size - 1));
@@ -642,8 +728,8 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
     const int tb = k / n_sb_d, r = k - tb * n_sb, slot = r / nb_d, b = r - slot * nb;
     p.dense[(tb == 0 ? p.geom.off_pt : p.geom.off_ut) + (int)s_cm.slot_state[slot] * nb + b] = t;
   }
-  if (tid == 0) p.fold_sync[n_groups] = 0;
-  if (p.peer_world > 1) staged_peer_merge(p);
+  if (tid == 0) p.fold_sync[n_groups] = p.fold_sync[n_groups + 1] = 0;
+  if (p.peer.world > 1) staged_peer_merge(p);
 }
 
 // ---- row log passes -----------------------------------------------------------

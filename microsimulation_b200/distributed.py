@@ -58,12 +58,13 @@ def _gpu_compute(seed, first, count, outputs, discount_rate):
 _peer_group_ready = False
 
 
-def enable_peer_merge(group=None):
+def enable_peer_merge(group=None, mode=1):
     """Sets up the merge INSIDE the person-r launch (csrc/person_staged.cuh, staged_peer_merge): every rank allocates a
     mailbox, the CUDA IPC handles go round once (all_gather_object), every rank maps the others' mailboxes over
     NVLink.  After this, person-r runs with a report leave the sum over all ranks in their dense vector — no
-    all-reduce to enqueue.  One node, at most 8 ranks, one process per GPU; returns False (and changes nothing) where
-    that does not hold or peer memory cannot be mapped."""
+    all-reduce to enqueue.  mode 2: the sum of run k is formed during run k + 1 or by api.peer_flush(), and is read from
+    api.peer_result_ptr() (api.peer_merge switches between the modes afterwards).  One node, at most 8 ranks, one
+    process per GPU; returns False (and changes nothing) where that does not hold or peer memory cannot be mapped."""
     global _peer_group_ready
     import torch.distributed as dist
     if not dist.is_initialized():
@@ -94,7 +95,7 @@ def enable_peer_merge(group=None):
         except RuntimeError:
             pass
         return False
-    api.peer_merge(True)
+    api.peer_merge(mode)
     _peer_group_ready = True
     return True
 
@@ -102,7 +103,8 @@ def enable_peer_merge(group=None):
 def disable_peer_merge():
     global _peer_group_ready
     if _peer_group_ready:
-        api.peer_merge(False)
+        api.peer_flush()
+        api.peer_merge(0)
     _peer_group_ready = False
 
 

@@ -39,9 +39,46 @@ if D.enable_peer_merge():
     ptr, nd = api.dense_device_ptr()
     v = torch.as_tensor(D._CudaBuffer(ptr, nd), device="cuda").clone()
     assert float(v[-9] + v[-8]) == 1000.0 * world, float(v[-9] + v[-8])
+    # mode 2: run k adds up what the ranks sent in run k - 1; a flush adds up the last run's
+    api.peer_merge(2)
+    sizes = [5000 + 17 * world, 300 * world, 40_001, 2 * world]
+    want = []
+    for n2 in sizes:  # what every run's merged vector must be, from the NCCL path
+        api.peer_merge(0)
+        first, count = D.shard_range(n2, rank, world)
+        api.person_run_device(12345, first, count, api.MSIM_OUT_REPORT | api.MSIM_OUT_COUNTS, 0.03)
+        ptr, nd = api.dense_device_ptr()
+        t = torch.as_tensor(D._CudaBuffer(ptr, nd), device="cuda").clone()
+        dist.all_reduce(t)
+        want.append(t)
+    api.peer_merge(2)
+    for k, n2 in enumerate(sizes):
+        first, count = D.shard_range(n2, rank, world)
+        api.person_enqueue(12345, first, count, api.MSIM_OUT_REPORT | api.MSIM_OUT_COUNTS, 0.03)
+        api.sync()
+        if k > 0:  # the previous run's sum is in place now
+            ptr, nd = api.peer_result_ptr()
+            got = torch.as_tensor(D._CudaBuffer(ptr, nd), device="cuda")
+            assert torch.equal(got[-9:-1], want[k - 1][-9:-1]), (k, got[-9:], want[k - 1][-9:])
+            assert torch.allclose(got, want[k - 1], rtol=1e-12, atol=0)
+    api.peer_flush()
+    api.sync()
+    ptr, nd = api.peer_result_ptr()
+    got = torch.as_tensor(D._CudaBuffer(ptr, nd), device="cuda").clone()
+    assert torch.equal(got[-9:-1], want[-1][-9:-1]) and torch.allclose(got, want[-1], rtol=1e-12, atol=0)
+    every = [torch.empty_like(got) for _ in range(world)]
+    dist.all_gather(every, got)
+    assert all(torch.equal(e.view(torch.int64), got.view(torch.int64)) for e in every)
+    for _ in range(300):  # back to back: ranks drift apart by up to a launch, slots must not be overwritten early
+        api.person_enqueue(12345, rank * 1000, 1000 + 50 * rank, api.MSIM_OUT_REPORT | api.MSIM_OUT_COUNTS, 0.03)
+    api.peer_flush()
+    api.sync()
+    ptr, nd = api.peer_result_ptr()
+    v = torch.as_tensor(D._CudaBuffer(ptr, nd), device="cuda").clone()
+    assert float(v[-9] + v[-8]) == 1000.0 * world + 50.0 * sum(range(world)), float(v[-9] + v[-8])
     D.disable_peer_merge()
     if rank == 0:
-        print("in-launch merge ok: world %d" % world)
+        print("in-launch merge ok (both modes): world %d" % world)
 elif rank == 0:
     print("in-launch merge NOT available on this box (peer memory could not be mapped)")
 pars = np.tile(np.array([4, 0.5, 0.05, 10, 3, 0.5]), (8, 1)) * (1 + 0.2 * (np.random.RandomState(1).rand(8, 6) - 0.5))
