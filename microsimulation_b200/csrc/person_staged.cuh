@@ -125,11 +125,14 @@ constexpr int ROW_OV_MIN = 64;    // smallest region for a chunk's further rows,
 #define MSIM_ROW_WINDOW 1536
 #endif
 #ifndef MSIM_ROW_MINB
-#define MSIM_ROW_MINB 6
+#define MSIM_ROW_MINB 4
 #endif
-// rows a block of the final pass stages at a time (a chunk holds 1262 on average).  1536 rows and 6 blocks per SM (40
-// registers) measured best: 5.06 ms per 1e8 persons for the whole row-log step against 5.29 (2048 rows, 55 registers),
-// 5.14 (2048, 5 blocks), 5.10 (1280, 7), 5.13 (1024, 8)  [gpurun_out/variants, round 2]
+// rows a block of the final pass stages at a time (a chunk holds 1262 on average), and blocks per SM.  With one load
+// per thread in flight at a time (round 2's first form) 1536 rows and 6 blocks per SM (40 registers) measured best:
+// 5.06 ms per 1e8 persons for the whole row-log step against 5.29 (2048 rows, 55 registers), 5.14 (2048, 5 blocks),
+// 5.10 (1280, 7), 5.13 (1024, 8).  With everything a thread needs requested up front (the kernel as it is now) the
+// registers matter more than the sixth block: 4 blocks (64 registers) or 5 (48, spilling 36 bytes) 4.73 ms, 6 blocks
+// (40 registers, spilling) 4.84  [gpurun_out/variants, round 2]
 constexpr int ROW_WINDOW = MSIM_ROW_WINDOW;
 
 struct alignas(16) WarpQueues {
@@ -815,9 +818,10 @@ __global__ void __launch_bounds__(1024) rowpass_scan_kernel(RowPassParams p) {
 }
 
 // One block per chunk: every person's row offset by a block scan of the row counts, first rows and further
-// rows placed in shared memory in final order, then streamed out (all global accesses coalesced).
+// rows placed in shared memory in final order, then streamed out (all global accesses coalesced).  The pass is
+// bandwidth-bound and its warps wait for loads, so everything a thread needs from global memory is requested up front:
+// its four persons' tags and first end times before the scan, its further row (tag, start, end) before the placing.
 __global__ void __launch_bounds__(256, MSIM_ROW_MINB) rowpass_final_kernel(RowPassParams p) {
-  __shared__ unsigned short s_tag[ROW_CHUNK];
   __shared__ unsigned short s_off[ROW_CHUNK];
   __shared__ double s_end[ROW_WINDOW], s_start[ROW_WINDOW];
   __shared__ unsigned s_meta[ROW_WINDOW];
@@ -825,14 +829,52 @@ __global__ void __launch_bounds__(256, MSIM_ROW_MINB) rowpass_final_kernel(RowPa
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t c = blockIdx.x, lo = c * ROW_CHUNK;
   constexpr int PER = ROW_CHUNK / 256;
-  // ---- row offsets: thread t owns persons [PER*t, PER*t + PER)
+  static_assert(PER == 4, "a thread owns four consecutive persons: one 8-byte load of tags, two 16-byte loads of end times");
+  // ---- thread t owns persons [PER*t, PER*t + PER): tags, first end times, and (below) the scan of their row counts
+  const int64_t i0 = lo + (int64_t)tid * PER;
+  unsigned short tag[PER];
+  double fe[PER];
+  if (i0 + PER <= p.n) {
+    const uint2 t2 = *reinterpret_cast<const uint2 *>(p.first_tag + i0);  // i0 is a multiple of 4: 8-byte aligned
+    tag[0] = (unsigned short)(t2.x & 0xffffu);
+    tag[1] = (unsigned short)(t2.x >> 16);
+    tag[2] = (unsigned short)(t2.y & 0xffffu);
+    tag[3] = (unsigned short)(t2.y >> 16);
+    const double2 a = *reinterpret_cast<const double2 *>(p.first_end + i0), b = *reinterpret_cast<const double2 *>(p.first_end + i0 + 2);
+    fe[0] = a.x;
+    fe[1] = a.y;
+    fe[2] = b.x;
+    fe[3] = b.y;
+  } else {
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      tag[k] = (i0 + k < p.n) ? p.first_tag[i0 + k] : (unsigned short)0;
+      fe[k] = (i0 + k < p.n) ? p.first_end[i0 + k] : 0.0;
+    }
+  }
+  // this thread's further rows (entries of the chunk's region: as many as the chunk appended, at most ov_cap)
+  unsigned m = p.ov_fill[c];
+  if (m > (unsigned)p.ov_cap) m = (unsigned)p.ov_cap;
+  const size_t ov0 = (size_t)c * p.ov_cap;
+  const unsigned long long base = p.chunk_rows[c];
+  constexpr int OV_PER = 2;  // entries per thread requested up front (512 per block; a region holds 522 at the default plan)
+  unsigned otag[OV_PER];
+  double oend[OV_PER], ostart[OV_PER];
+#pragma unroll
+  for (int k = 0; k < OV_PER; k++) {
+    const unsigned e = tid + 256u * k;
+    otag[k] = 0;
+    oend[k] = ostart[k] = 0.0;
+    if (e < m) {
+      otag[k] = p.ov_tag[ov0 + e];
+      oend[k] = p.ov_end[ov0 + e];
+      ostart[k] = p.ov_start[ov0 + e];
+    }
+  }
   unsigned cnt[PER], v = 0;
 #pragma unroll
   for (int k = 0; k < PER; k++) {
-    const int64_t i = lo + tid * PER + k;
-    const unsigned short tag = (i < p.n) ? p.first_tag[i] : (unsigned short)0;
-    s_tag[tid * PER + k] = tag;
-    cnt[k] = tag_rows(tag);
+    cnt[k] = tag_rows(tag[k]);
     v += cnt[k];
   }
   unsigned incl = v;
@@ -848,33 +890,42 @@ __global__ void __launch_bounds__(256, MSIM_ROW_MINB) rowpass_final_kernel(RowPa
     if (w < warp) run += s_w[w];
     total += s_w[w];
   }
+  unsigned off[PER];
 #pragma unroll
   for (int k = 0; k < PER; k++) {
+    off[k] = run;
     s_off[tid * PER + k] = (unsigned short)run;
     run += cnt[k];
   }
   __syncthreads();
-  const unsigned long long base = p.chunk_rows[c];
-  unsigned m = p.ov_fill[c];
-  if (m > (unsigned)p.ov_cap) m = (unsigned)p.ov_cap;
-  const size_t ov0 = (size_t)c * p.ov_cap;
   for (unsigned w0 = 0; w0 < total; w0 += ROW_WINDOW) {
-    for (int i = tid; i < ROW_CHUNK; i += 256) {
-      const unsigned short tag = s_tag[i];
-      const unsigned o = (unsigned)s_off[i] - w0;
-      if ((tag & 0x8000u) && o < (unsigned)ROW_WINDOW) {  // (unsigned wrap-around rejects rows before the window)
-        s_end[o] = p.first_end[lo + i];
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      const unsigned o = off[k] - w0;
+      if ((tag[k] & 0x8000u) && o < (unsigned)ROW_WINDOW) {  // (unsigned wrap-around rejects rows before the window)
+        s_end[o] = fe[k];
         s_start[o] = 0.0;  // a person's first interval starts at startTime = 0 (microsimulation.h:430)
-        s_meta[o] = ((unsigned)i << 16) | (((unsigned)tag >> 4) & 0xfu) << 8 | ((unsigned)tag & 0xfu);
+        s_meta[o] = ((unsigned)(tid * PER + k) << 16) | (((unsigned)tag[k] >> 4) & 0xfu) << 8 | ((unsigned)tag[k] & 0xfu);
       }
     }
-    for (unsigned e = tid; e < m; e += 256) {
-      const unsigned tag = p.ov_tag[ov0 + e];
-      const unsigned o = (unsigned)s_off[tag >> 16] + ((tag >> 12) & 0xfu) - w0;
+#pragma unroll
+    for (int k = 0; k < OV_PER; k++) {
+      if (tid + 256u * k < m) {
+        const unsigned o = (unsigned)s_off[otag[k] >> 16] + ((otag[k] >> 12) & 0xfu) - w0;
+        if (o < (unsigned)ROW_WINDOW) {
+          s_end[o] = oend[k];
+          s_start[o] = ostart[k];
+          s_meta[o] = (otag[k] & 0xffff0000u) | (otag[k] & 0xfffu);
+        }
+      }
+    }
+    for (unsigned e = tid + 256u * OV_PER; e < m; e += 256) {  // regions planned larger than 512 entries
+      const unsigned t = p.ov_tag[ov0 + e];
+      const unsigned o = (unsigned)s_off[t >> 16] + ((t >> 12) & 0xfu) - w0;
       if (o < (unsigned)ROW_WINDOW) {
         s_end[o] = p.ov_end[ov0 + e];
         s_start[o] = p.ov_start[ov0 + e];
-        s_meta[o] = (tag & 0xffff0000u) | (tag & 0xfffu);
+        s_meta[o] = (t & 0xffff0000u) | (t & 0xfffu);
       }
     }
     __syncthreads();
