@@ -14,6 +14,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --c
 echo "ncu launches rc=$?"
 timeout 900 bash scripts/gpu_prof.sh 6 staged_report 1e8 1
 timeout 900 bash scripts/gpu_prof.sh 1 staged_rowlog 1e8 5
+python scripts/prof_calib.py 256 1e6 > gpurun_out/plain_calib.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:calib_shared -s 1 -c 1 -f -o gpurun_out/prof_calib_shared python scripts/prof_calib.py 256 1e6 > gpurun_out/ncu_calib.log 2>&1
+echo "ncu calib rc=$?"
+python scripts/calib_timing.py > gpurun_out/calib_timing.log 2>&1; cat gpurun_out/calib_timing.log
 python scripts/inst_floor.py run > gpurun_out/inst_floor_plain.log 2>&1 && \
 timeout 600 ncu --metrics smsp__inst_executed.sum,smsp__thread_inst_executed.sum --clock-control none -k regex:microbench --csv \
     --log-file gpurun_out/inst_floor.csv python scripts/inst_floor.py run > gpurun_out/inst_floor_ncu.log 2>&1

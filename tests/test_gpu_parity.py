@@ -776,3 +776,39 @@ def test_kernels_were_launched(msim):
     before = msim.launch_count()
     msim.callPersonSimulation(1000)
     assert msim.launch_count() > before
+
+
+def test_peer_merge_entries_on_one_gpu(msim):
+    """msim_peer_*: the merge across GPUs inside the launch (the multi-GPU behaviour itself is checked by
+    scripts/multi_gpu_check.py under torchrun and by bench.py's merge_check at N > 1).  On one GPU: call order is
+    checked, and a world of one rank changes nothing."""
+    import microsimulation_b200.api as api
+    from microsimulation_b200._lib import load
+    api.peer_close()
+    with pytest.raises(RuntimeError):
+        api.peer_merge(1)                      # no mailbox yet
+    with pytest.raises(RuntimeError):
+        api.peer_export(9)                     # at most 8 ranks
+    with pytest.raises(RuntimeError):
+        api.peer_import(0, 1, [b"\0" * 64])    # export first
+    rep0, counts0 = msim.person_report(12345, 100, 30000, 0.03)
+    h = api.peer_export(1)
+    assert len(h) == 64
+    with pytest.raises(ValueError):
+        api.peer_import(0, 1, [h, h])
+    api.peer_import(0, 1, [h])
+    with pytest.raises(RuntimeError):
+        api.peer_merge(3)
+    try:
+        for mode in (1, 2):
+            api.peer_merge(mode)
+            rep, counts = msim.person_report(12345, 100, 30000, 0.03)
+            api.peer_flush()
+            assert np.array_equal(counts[:8], counts0[:8])
+            for tb in ("events", "prev"):
+                for k in rep0[tb]:
+                    assert np.array_equal(rep[tb][k], rep0[tb][k])
+    finally:
+        api.peer_merge(0)
+        api.peer_close()
+    assert load().msim_peer_flush() == 0
