@@ -128,11 +128,17 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
   static const StagedKernel kernels[8] = {person_staged_kernel<0>, person_staged_kernel<1>, person_staged_kernel<2>,
                                           person_staged_kernel<3>, person_staged_kernel<4>, person_staged_kernel<5>,
                                           person_staged_kernel<6>, person_staged_kernel<7>};
-  const StagedKernel kernel = (p.outputs & OUT_INDIV) ? person_staged_kernel<OUT_RUNTIME> : kernels[p.outputs & 7u];
+  // with the merge across GPUs in the launch's tail (msim_peer_merge): instantiations of their own
+  static const StagedKernel peer_kernels[4] = {person_staged_kernel<2, true>, person_staged_kernel<3, true>,
+                                               person_staged_kernel<6, true>, person_staged_kernel<7, true>};
+  const bool with_peers = g.peers.mode && g.peers.world > 1 && (p.outputs & OUT_REPORT);
+  if (with_peers && (p.outputs & OUT_INDIV)) return fail(MSIM_ERR_ARG, "peer merge: not with MSIM_OUT_INDIV (individual totals stay on their rank)");
+  const StagedKernel kernel = with_peers ? peer_kernels[((p.outputs & 4u) >> 1) | (p.outputs & 1u)]
+                              : (p.outputs & OUT_INDIV) ? person_staged_kernel<OUT_RUNTIME> : kernels[p.outputs & 7u];
   // blocks per SM for this (kernel, shared memory) pair: asked once, the answer does not change
-  static size_t occ_smem[9] = {0};
-  static int occ_per_sm[9] = {0};
-  const unsigned slot = (p.outputs & OUT_INDIV) ? 8u : (p.outputs & 7u);
+  static size_t occ_smem[13] = {0};
+  static int occ_per_sm[13] = {0};
+  const unsigned slot = with_peers ? 9u + (((p.outputs & 4u) >> 1) | (p.outputs & 1u)) : (p.outputs & OUT_INDIV) ? 8u : (p.outputs & 7u);
   int per_sm = occ_per_sm[slot];
   if (per_sm == 0 || occ_smem[slot] != smem) {
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -207,7 +213,7 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
     }
     p.fold_sync = (unsigned *)g.fold_sync.p;
   }
-  if (g.peers.mode && g.peers.world > 1 && (p.outputs & OUT_REPORT)) {
+  if (with_peers) {
     // the launch also merges the dense vector with the other ranks' (person_staged.cuh, staged_peer_merge): every
     // rank must make the same sequence of such calls
     if (p.n == 0) return fail(MSIM_ERR_ARG, "peer merge: every rank needs at least one person");
