@@ -101,7 +101,13 @@ struct Mrg32k3a {
     // (p1 - p2) or (p1 - p2 + m1): an integer in [1, m1], exact in double
     uint32_t d = p1 - p2;
     if (p1 <= p2) d += MRG_M1;
+#ifdef __CUDA_ARCH__
+    // d as a double without an integer conversion: 2^52 + d is the bit pattern (0x43300000, d); the multiply-add
+    // (2^52 + d) * norm - 2^52 * norm is exact before its one rounding, so this is RN(d * norm), the reference's value
+    return __fma_rn(__hiloint2double(0x43300000, (int)d), MRG_NORM, -(4503599627370496.0 * MRG_NORM));
+#else
     return (double)d * MRG_NORM;
+#endif
   }
 
   // state <- J * state (MatVecModM on both components)
