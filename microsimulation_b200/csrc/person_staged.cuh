@@ -755,6 +755,12 @@ struct RowPassParams {
   int64_t capacity;
 };
 
+// an integer below 2^52 as a double, exactly, without the conversion instruction (three per row otherwise, on a pipe
+// that is a few lanes wide): 2^52 + v has v as its mantissa bits
+__device__ __forceinline__ double row_u52_to_double(unsigned long long v) {
+  return __longlong_as_double((long long)(0x4330000000000000ull | v)) - 4503599627370496.0;
+}
+
 __device__ __forceinline__ int tag_rows(unsigned short t) { return (t & 0x8000u) ? 1 + ((t >> 8) & 7) : 0; }
 
 // rows per chunk of ROW_CHUNK persons; largest overflow fill
@@ -937,10 +943,10 @@ __global__ void __launch_bounds__(256, MSIM_ROW_MINB) rowpass_final_kernel(RowPa
       if (g < (unsigned long long)p.capacity) {
         const unsigned mt = s_meta[r];
         p.rowlog[0 * p.capacity + g] = s_end[r];
-        p.rowlog[1 * p.capacity + g] = (double)(mt & 0xffu);
-        p.rowlog[2 * p.capacity + g] = (double)(p.first_person + lo + (mt >> 16));
+        p.rowlog[1 * p.capacity + g] = row_u52_to_double(mt & 0xffu);
+        p.rowlog[2 * p.capacity + g] = row_u52_to_double((unsigned long long)(p.first_person + lo + (mt >> 16)));
         p.rowlog[3 * p.capacity + g] = s_start[r];
-        p.rowlog[4 * p.capacity + g] = (double)((mt >> 8) & 0xfu);
+        p.rowlog[4 * p.capacity + g] = row_u52_to_double((mt >> 8) & 0xfu);
       }
     }
     __syncthreads();
