@@ -28,6 +28,15 @@ static
                                    0.9999999924734159, 0.9999999995283275, 0.9999999999728814, 0.9999999999985598,
                                    0.9999999999999289, 0.9999999999999968, 0.9999999999999999, 1.0000000000000000};
 
+// exp_rand's first loop adds ln 2 once per doubling of u: MSIM_EXP_A[k] = ln 2 + ln 2 + ... (k times, rounded at every
+// addition as the loop does: from k = 25 on that is not k * ln 2)
+#ifdef __CUDACC__
+__constant__
+#else
+static
+#endif
+    const double MSIM_EXP_A[64] = {0.0, 0.6931471805599453, 1.3862943611198906, 2.0794415416798357, 2.772588722239781, 3.4657359027997265, 4.1588830833596715, 4.852030263919617, 5.545177444479562, 6.238324625039508, 6.931471805599453, 7.6246189861593985, 8.317766166719343, 9.010913347279288, 9.704060527839234, 10.39720770839918, 11.090354888959125, 11.78350206951907, 12.476649250079015, 13.16979643063896, 13.862943611198906, 14.556090791758852, 15.249237972318797, 15.942385152878742, 16.635532333438686, 17.32867951399863, 18.021826694558573, 18.714973875118517, 19.40812105567846, 20.101268236238404, 20.794415416798348, 21.48756259735829, 22.180709777918235, 22.87385695847818, 23.567004139038122, 24.260151319598066, 24.95329850015801, 25.646445680717953, 26.339592861277897, 27.03274004183784, 27.725887222397784, 28.419034402957728, 29.11218158351767, 29.805328764077615, 30.49847594463756, 31.191623125197502, 31.884770305757446, 32.57791748631739, 33.271064666877336, 33.964211847437284, 34.65735902799723, 35.35050620855718, 36.043653389117125, 36.73680056967707, 37.42994775023702, 38.12309493079697, 38.816242111356914, 39.50938929191686, 40.20253647247681, 40.895683653036755, 41.5888308335967, 42.28197801415665, 42.9751251947166, 43.668272375276544};
+
 // the `R::` namespace as seen from a model: R.runif(a,b), R.rweibull(...), ...
 template <class Src>
 struct RMath {
@@ -52,14 +61,17 @@ struct RMath {
   MSIM_DEV double exp_rand() {
     const double q0 = 0.6931471805599453;  // MSIM_EXP_Q[0] = ln 2
     const double *q = MSIM_EXP_Q;
-    double a = 0.;
     double u = unif_rand();
     while (u <= 0. || u >= 1.) u = unif_rand();
-    for (;;) {
-      u += u;
-      if (u > 1.) break;
-      a += q0;
-    }
+    // R's loop — for (;;) { u += u; if (u > 1.) break; a += q0; } — doubles u until it exceeds 1 and adds ln 2 for every
+    // doubling but the last.  Doubling is exact, so the number of doublings j follows from u's exponent (u = m 2^e,
+    // 1 <= m < 2, e < 0: j = -e, one more if m = 1), the doubled u is u with j added to its exponent field, and a is
+    // the (j - 1)-fold sum from the table.  (As a loop a warp runs as many passes as its unluckiest lane needs.)
+    const int64_t ub = fm_bits(u);
+    const int j = 1023 - (int)(ub >> 52) + ((ub & 0x000fffffffffffffll) == 0 ? 1 : 0);
+    double a = MSIM_EXP_A[j - 1 < 63 ? j - 1 : 63];
+    for (int k = 63; k < j - 1; k++) a += q0;  // u < 2^-64: no generator here produces it (u must be a normal number)
+    u = fm_from_bits(ub + ((int64_t)j << 52));
     u -= 1.;
     if (u <= q0) return a + u;
     int i = 0;

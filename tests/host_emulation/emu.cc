@@ -631,6 +631,47 @@ int emu_calibration_shared(const double seed[6], int64_t first_person, int64_t n
   return 0;
 }
 
+// exp_rand (rmath.cuh) fed with the given uniforms, against R's algorithm as R writes it (Ahrens & Dieter 1972,
+// nmath/sexp.c: the doubling loop).  Returns the number of results that differ in any bit.
+struct ListSource {
+  const double *u;
+  int64_t pos;
+  double unif_rand() { return u[pos++]; }
+};
+int64_t emu_exp_rand_selftest(const double *u, int64_t n, int draws_each) {
+  int64_t bad = 0;
+  for (int64_t i = 0; i < n; i++) {
+    ListSource s1{u + i * draws_each, 0}, s2{u + i * draws_each, 0};
+    RMath<ListSource> R(&s1);
+    const double got = R.exp_rand();
+    // R's own form
+    const double *q = MSIM_EXP_Q;
+    double a = 0., x = s2.unif_rand();
+    while (x <= 0. || x >= 1.) x = s2.unif_rand();
+    for (;;) {
+      x += x;
+      if (x > 1.) break;
+      a += q[0];
+    }
+    x -= 1.;
+    double want;
+    if (x <= q[0]) {
+      want = a + x;
+    } else {
+      int k = 0;
+      double ustar = s2.unif_rand(), umin = ustar;
+      do {
+        ustar = s2.unif_rand();
+        if (umin > ustar) umin = ustar;
+        k++;
+      } while (x > q[k]);
+      want = a + umin * q[0];
+    }
+    if (memcmp(&got, &want, 8) != 0 || s1.pos != s2.pos) bad++;
+  }
+  return bad;
+}
+
 int emu_counts_before(double t, int *tie_out) {
   bool tie = false;
   const int c = calib::counts_before(t, calib::MSIM_CALIB_RUNGS, &tie);

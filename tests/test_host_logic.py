@@ -314,6 +314,28 @@ def test_emulated_calibration_ordered_queue(oracle, emu):
             assert np.array_equal(a[k], b[k]), k
 
 
+def test_exp_rand_without_its_doubling_loop_is_bit_exact(emu):
+    """rmath.cuh exp_rand: the number of doublings from u's exponent and the sum of ln 2's from a table of repeated
+    additions, against R's loop — every exponent down to 2^-70, exact powers of two, values next to them, 2e5 random
+    uniforms and the smallest values the generators produce; same result bits, same number of uniforms taken."""
+    emu.emu_exp_rand_selftest.restype = C.c_int64
+    rng = np.random.default_rng(11)
+    first = []
+    for e in range(1, 71):
+        p = 2.0 ** -e
+        first += [p, np.nextafter(p, 1.0), np.nextafter(p, 0.0), p * 1.5, p * 1.9999999]
+    first += [2.328306549295727688e-10, 2.328306437080797e-10, 1.0 - 2.3283064365386963e-10, 0.5, 0.75, 0.9999999999]
+    first += list(rng.random(200000)) + list(rng.random(20000) * 2.0 ** -rng.integers(1, 40, 20000))
+    first = np.array(first)
+    draws = 24   # the first uniform, then up to 17 more in the second loop (q[16] = 1 ends it)
+    u = rng.random((first.size, draws))
+    u[:, 0] = first
+    assert ((u > 0) & (u < 1)).all()
+    u = np.ascontiguousarray(u)
+    bad = emu.emu_exp_rand_selftest(u.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(first.size), C.c_int(draws))
+    assert bad == 0
+
+
 def test_count_ladder_position_is_exact(emu):
     """calib_shared.cuh counts_before: how many Count events (10, 20, .., 100) lie strictly before t — by an estimate and
     two exact corrections; checked against the ten comparisons at and one ulp either side of every rung."""
