@@ -149,6 +149,14 @@ int msim_set_mt_parallel(int on);
  * (default 0.26).  A run that needs more is repeated with the exact sizes, so
  * the plan only affects speed and memory, never results. */
 int msim_set_rowlog_plan(double rows_per_person, double extra_rows_per_person);
+/* Staged person-r schedule, scheduling only (results never depend on it): with two
+ * thread blocks per SM, the share of the persons the blocks that arrive first on
+ * their SMs simulate.  The warp schedulers favour those blocks; by default
+ * (share <= 0) the library moves the share, from the finishing times of earlier
+ * launches, to where both halves of the grid end together.  0.40 <= share <= 0.65
+ * fixes it.  msim_last_wave_share: what the last launch used (0: it was not split). */
+int msim_set_wave_share(double share);
+int msim_last_wave_share(double *share);
 
 /* ---- RNG state (replaces the .C table, src/init.c:11-30) ------------- */
 

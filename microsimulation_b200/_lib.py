@@ -77,7 +77,7 @@ class PersonDeviceResult(C.Structure):
 # every symbol include/msim.h declares (tests check that the library exports them all)
 SYMBOLS = [
     "msim_table_free", "msim_report_free", "msim_last_error", "msim_version", "msim_init", "msim_shutdown",
-    "msim_launch_count", "msim_set_stream", "msim_peer_export", "msim_peer_import", "msim_peer_merge", "msim_peer_flush", "msim_peer_result_ptr", "msim_peer_close", "msim_set_person_schedule", "msim_set_mt_parallel", "msim_set_rowlog_plan", "msim_set_report_options", "msim_person_fetch_indiv", "msim_r_create_current_stream", "msim_r_remove_current_stream",
+    "msim_launch_count", "msim_set_stream", "msim_peer_export", "msim_peer_import", "msim_peer_merge", "msim_peer_flush", "msim_peer_result_ptr", "msim_peer_close", "msim_set_person_schedule", "msim_set_mt_parallel", "msim_set_rowlog_plan", "msim_set_wave_share", "msim_last_wave_share", "msim_set_report_options", "msim_person_fetch_indiv", "msim_r_create_current_stream", "msim_r_remove_current_stream",
     "msim_r_set_user_random_seed", "msim_r_get_user_random_seed", "msim_r_next_rng_substream",
     "msim_r_rng_advance_substream", "msim_next_rng_stream", "msim_user_unif_rand", "msim_mt_set_state", "msim_mt_get_state", "msim_mt_set_seed",
     "msim_callPersonSimulation", "msim_callSimplePerson", "msim_callSimplePerson2", "msim_callIllnessDeath",
@@ -123,6 +123,8 @@ def load():
                                    C.POINTER(C.c_int32), dp, dp, C.POINTER(Table), dp]
     L.msim_set_stream.argtypes = [C.c_void_p, C.c_int]
     L.msim_set_rowlog_plan.argtypes = [C.c_double, C.c_double]
+    L.msim_set_wave_share.argtypes = [C.c_double]
+    L.msim_last_wave_share.argtypes = [C.POINTER(C.c_double)]
     L.msim_dense_to_report.argtypes = [C.POINTER(C.c_double), C.POINTER(DenseDims), C.c_double, C.POINTER(Report)]
     _lib = L
     return L

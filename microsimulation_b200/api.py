@@ -69,6 +69,18 @@ def set_rowlog_plan(rows_per_person=1.25, extra_rows_per_person=0.26):
     check(load().msim_set_rowlog_plan(rows_per_person, extra_rows_per_person))
 
 
+def set_wave_share(share=0.0):
+    """Staged person-r schedule: the first wave of blocks' share of the persons (0: adapted from the finishing times
+    of earlier launches, the default).  Scheduling only."""
+    check(load().msim_set_wave_share(share))
+
+
+def last_wave_share():
+    v = C.c_double(0.0)
+    check(load().msim_last_wave_share(C.byref(v)))
+    return v.value
+
+
 # ---- RNG utilities (R/rcpp_hello_world.R:104-152)
 
 def set_user_random_seed(seed):

@@ -100,6 +100,20 @@ int msim_set_rowlog_plan(double rows_per_person, double extra_rows_per_person) {
   return MSIM_OK;
 }
 
+int msim_set_wave_share(double share) {
+  if (share > 0 && !(share >= 0.40 && share <= 0.65)) return fail(MSIM_ERR_ARG, "wave share: 0.40 to 0.65, or <= 0 to adapt");
+  g.wave_share_fixed = share > 0 ? share : 0;
+  if (!(share > 0))
+    for (double &f : g.wave_share) f = 0.5;
+  return MSIM_OK;
+}
+
+int msim_last_wave_share(double *share) {
+  if (!share) return fail(MSIM_ERR_ARG, "null pointer");
+  *share = g.have_last && g.last_staged ? g.last_wave_share : 0.0;
+  return MSIM_OK;
+}
+
 int msim_set_report_options(const msim_report_options *opt) {
   if (!opt) {
     g.have_report_opts = false;

@@ -158,11 +158,33 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
   if (sh->n / ((int64_t)grid * SBLOCK) >= 32000) return fail(MSIM_ERR_ARG, "shard too large for this device: split it");
   uint32_t state[6];
   seed_to_u32(sh->seed, state);
-  stream_start(state, sh->first_person, (int64_t)grid * SBLOCK, &p.st);
+  // Two blocks per SM: the blocks that arrive first on their SMs (the first sm_count of the grid) are favoured by the
+  // warp schedulers, so they get the larger share of the tiles — as much larger as makes both waves of blocks finish
+  // together (wave_feedback below; person_staged.cuh).  Results do not depend on the share.
+  const int64_t tiles_per_warp = tiles / ((int64_t)grid * SWARPS);
+  const bool two_waves = per_sm == 2 && grid == 2 * g.sm_count && tiles_per_warp >= WAVE_MIN_TILES;
+  p.wave_blocks = two_waves ? g.sm_count : grid;
+  p.wave_split = tiles;
+  g.last_wave_slot = -1;
+  g.last_wave_share = 0;
+  if (two_waves) {
+    const double share = g.wave_share_fixed > 0 ? g.wave_share_fixed : g.wave_share[slot];
+    p.wave_split = std::min<int64_t>(tiles, std::max<int64_t>(0, (int64_t)(share * (double)tiles + 0.5)));
+    Mrg32k3a b;
+    memcpy(b.s, state, sizeof b.s);
+    b.jump(mrg_jump_pow(mrg_substream_jump(), (uint64_t)sh->first_person + 1 + 32ull * (uint64_t)p.wave_split));
+    memcpy(p.base_b, b.s, sizeof b.s);
+    g.last_wave_slot = (int)slot;
+    g.last_wave_share = (double)p.wave_split / (double)tiles;
+    g.last_wave_adapt = g.wave_share_fixed <= 0 && tiles_per_warp >= WAVE_ADAPT_TILES;
+  }
+  stream_start(state, sh->first_person, (int64_t)p.wave_blocks * SBLOCK, &p.st);
   if ((rc = ensure(g.small, 16 * sizeof(double)))) return rc;
   CK(cudaMemsetAsync(g.small.p, 0, 16 * sizeof(double), g.stream));
   SmallView sv = small_view();
   p.error = sv.error;
+  p.wave_clock = two_waves ? sv.wave_clock : nullptr;
+  p.wave_sync = sv.wave_sync;
   const int cells = (p.outputs & OUT_REPORT) ? p.geom.total : 0;
   if ((rc = ensure(g.dense, sizeof(double) * (cells + N_COUNTS)))) return rc;
   CK(cudaMemsetAsync(g.dense.p, 0, sizeof(double) * (cells + N_COUNTS), g.stream));

@@ -60,6 +60,12 @@ struct Ctx {
   std::vector<int> peers_map;   // entry of the travelling vector -> cell of dense, as uploaded to peers_map_dev
   DevBuf peers_map_dev;
   int person_kernel = 0;  // 0 = staged schedule (person_staged.cuh), 1 = generic cohort kernel
+  // share of the tiles the first wave of blocks takes, per kernel instantiation of the staged schedule (host_person.h)
+  double wave_share[13] = {0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5};
+  double wave_share_fixed = 0;  // msim_set_wave_share: > 0 switches the adaptation off
+  int last_wave_slot = -1;      // of the last staged launch (-1: one wave)
+  double last_wave_share = 0;
+  bool last_wave_adapt = false;
   bool last_staged = false;
   double plan_rows = 1.25, plan_extra_rows = 0.26;  // row-log buffer planning (msim_set_rowlog_plan)
   int64_t last_ov_cap = 0, last_ov_rows = 0;
@@ -278,6 +284,8 @@ inline ReportGeom geom_from_dims(const msim_dense_dims *dims, double discount_ra
 
 // `small` buffer layout (8-byte cells): [9] n_rows (u64), [10] error (int), [11] end_word (i64), [12] overflow rows (u64)
 struct SmallView {
+  unsigned long long *wave_clock;  // [3] (person_staged.cuh, StagedParams::wave_clock)
+  unsigned *wave_sync;             // [2] (StagedParams::wave_sync)
   unsigned long long *n_rows;
   int *error;
   int64_t *end_word;
@@ -286,6 +294,8 @@ struct SmallView {
 inline SmallView small_view() {
   SmallView v;
   double *b = (double *)g.small.p;
+  v.wave_clock = (unsigned long long *)b;
+  v.wave_sync = (unsigned *)(b + 3);
   v.n_rows = (unsigned long long *)(b + 9);
   v.error = (int *)(b + 10);
   v.end_word = (int64_t *)(b + 11);

@@ -164,7 +164,15 @@ struct PeerParams {
 };
 
 struct StagedParams {
-  StreamStart st;  // stride = M^(gridDim.x*SBLOCK)
+  StreamStart st;  // stride = M^(wave_blocks*SBLOCK)
+  // Two WAVES of wave_blocks blocks each when the grid is two blocks per SM: the blocks that are the first on their
+  // SMs take the tiles [0, wave_split), the others [wave_split, tiles); base_b = substream state of the person that
+  // tile wave_split starts with.  One wave (wave_blocks = gridDim.x, wave_split = tiles) otherwise.  Why: see the kernel.
+  int wave_blocks;
+  int64_t wave_split;
+  uint32_t base_b[6];
+  unsigned long long *wave_clock;  // [3]: ~(first block's start), wave 0's end, wave 1's end (globaltimer ns; max); null: one wave
+  unsigned *wave_sync;             // [2] blocks that joined each wave; zero before the launch
   int64_t first_person, n;
   unsigned outputs;
   person_r::Consts consts;
@@ -494,6 +502,18 @@ __global__ void __launch_bounds__(256) peer_collect_kernel(const __grid_constant
 
 // PEER: with the merge across GPUs (above) in the launch's tail.  A separate instantiation: compiled into the one kernel,
 // the two calls cost runs that do not merge 0.4% (4.83 against 4.81 ms per 1e8 persons: another register allocation).
+#ifdef MSIM_TRACE
+// development aid (scripts/trace_run.py, build with -DMSIM_TRACE): where a launch's time goes.  Every block leaves time
+// stamps in global memory; the block that ends the fold prints, per stamp, the earliest and latest block (ns after the
+// first block's entry) — one printf at the very end, so the stamps themselves are not disturbed.
+__device__ unsigned long long g_trace[1024][4];
+__device__ unsigned long long g_trace_warp[1024][32];  // when each warp of the block had no persons left
+__device__ unsigned g_trace_sm[1024];
+#define MSIM_STAMP(k) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_trace[blockIdx.x][k] = peer_now_ns(); } while (0)
+#else
+#define MSIM_STAMP(k) do { } while (0)
+#endif
+
 template <unsigned OUT, bool PEER = false>
 __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const __grid_constant__ StagedParams p) {
   typedef StagedEnvT<OUT> StagedEnv;
@@ -520,11 +540,37 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
   __shared__ ReportCompact s_cm;
   __shared__ int s_error;
   __shared__ int s_last;
+  __shared__ long long s_tile_end;
+  __shared__ int s_wave[2];  // this block's wave and its place in it
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  MSIM_STAMP(0);
   const unsigned lt_mask = (1u << lane) - 1u;
   WarpQueues &Q = queues[warp];
   if (tid < 8) s_kind[tid] = 0;
   if (tid == 0) s_error = 0;
+  if (tid == 0) {
+    // Which wave, and which of its blocks, this block is.  The favoured block of an SM is the one in the SM's lower
+    // warp slots (%warpid of its first warp 0, 1 or 3 against 10, 11 or 9 on every SM of a B200: scripts/trace_run.py);
+    // the block index does not tell (the block scheduler hands 6 of the first 148 blocks to SMs that have one), nor
+    // does the order in which the two arrive at a counter (they start within 0.4 us of one another).  A wave that is
+    // full — a GPU shared with another kernel, so that an SM sees its blocks one after the other — sends the block to
+    // the other one: every place in every wave is taken exactly once whatever the slots are.
+    int wave = 0;
+    unsigned rank = blockIdx.x;
+    if (p.wave_clock) {
+      unsigned wid;
+      asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+      wave = wid >= (unsigned)(SWARPS * 3 / 5) ? 1 : 0;
+      rank = atomicAdd(&p.wave_sync[wave], 1u);
+      if (rank >= (unsigned)p.wave_blocks) {
+        wave ^= 1;
+        rank = atomicAdd(&p.wave_sync[wave], 1u);
+      }
+    }
+    s_wave[0] = wave;
+    s_wave[1] = (int)rank;
+    s_tile_end = wave ? (long long)((p.n + 31) / 32) : (long long)p.wave_split;
+  }
   for (int k = tid; k < (int)(sizeof(ReportGeom) / 4); k += SBLOCK)
     reinterpret_cast<int *>(&s_geom)[k] = reinterpret_cast<const int *>(&p.geom)[k];
   for (int k = tid; k < (int)(sizeof(ReportCompact) / 4); k += SBLOCK)
@@ -558,17 +604,34 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
   env.lane = lane;
   const person_r::Consts &K = p.consts;
 
-  Mrg32k3a sub = thread_start_state(p.st, blockIdx.x * SBLOCK + tid);
-  const int64_t n_tiles = (p.n + 31) / 32;
-  const int64_t gw = (int64_t)blockIdx.x * SWARPS + warp, GW = (int64_t)gridDim.x * SWARPS;
+  // The two blocks of an SM do not advance alike: the schedulers favour the warps of the block that arrived first, and
+  // with equal shares that block was done at 3.97 ms of a 4.5 ms launch while its neighbour ran the last 0.45 ms with
+  // half the SM's warps (1e8 persons, scripts/trace_run.py).  So the first wave of blocks gets the larger share of the
+  // tiles (wave_split; the host sets it from the waves' finishing times of earlier launches, wave_clock), each wave
+  // dealing its range of tiles to its warps in turn.  (Handing tiles out by ticket from a counter per SM instead evens
+  // the blocks out as well, but costs more than it gains: profiles/experiments/r02_tiles_by_ticket.md.)
+  const bool wave_b = s_wave[0] != 0;
+  const unsigned w_thread = (unsigned)s_wave[1] * SBLOCK + (unsigned)tid;
+  Mrg32k3a sub;
+  {
+    StreamStart st = p.st;
+    if (wave_b)
+      for (int k = 0; k < 6; k++) st.base[k] = p.base_b[k];
+    sub = thread_start_state(st, w_thread);
+  }
+  // (the end of the wave's range of tiles is read from shared memory in every pass of the loop: held in registers it
+  // takes the kernel to its register limit, with spills)
+  const int64_t tile_first = (wave_b ? p.wave_split : 0) + (w_thread >> 5), GW = (int64_t)p.wave_blocks * SWARPS;
+  if (tid == 0 && p.wave_clock) atomicMax(&p.wave_clock[0], ~peer_now_ns());
   int c1 = 0, c2 = 0;  // queue fills (warp-uniform)
 
   // Each pass of the loop runs ONE stage on up to 32 persons and then, in one place for all stages, the events
   // of the persons that became ready in it: new persons while there are tiles (stage A), parked persons
   // whenever a full warp of them waits (B1: onset times; B2: lives with onset before death), and whatever is
   // left once the tiles are used up.
-  for (int64_t tile = gw;;) {
-    const bool last = tile >= n_tiles;
+  MSIM_STAMP(1);
+  for (int64_t tile = tile_first;;) {
+    const bool last = tile >= *(volatile long long *)&s_tile_end;
     bool ready = false, park1 = false, park2 = false;
     person_r::Life life;
     person_r::ParkedOnset po;
@@ -648,6 +711,19 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
     __syncwarp();
   }
 
+  MSIM_STAMP(2);
+#ifdef MSIM_TRACE
+  if (lane == 0 && blockIdx.x < 1024) {
+    g_trace_warp[blockIdx.x][warp] = peer_now_ns();
+    if (warp == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      unsigned wid;
+      asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+      g_trace_sm[blockIdx.x] = smid | ((unsigned)s_wave[0] << 16) | (wid << 20);
+    }
+  }
+#endif
   env.acc.flush();
   if (err) atomicCAS(&s_error, 0, err);
   if (outs & 4u) {
@@ -666,6 +742,7 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
     if (lane == 0) s_sum[warp] = v;
   }
   __syncthreads();
+  if (tid == 0 && p.wave_clock) atomicMax(&p.wave_clock[1 + s_wave[0]], peer_now_ns());  // the block's persons are done
   // the block's counters -> the dense vector (cell by cell through the compact layout); with a report the per-kind
   // event counts are the column sums of the event table
   for (int k = tid; k < n_i; k += SBLOCK) {
@@ -693,6 +770,7 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
     }
   }
   if (tid == 0 && s_error) atomicCAS(p.error, 0, s_error);
+  MSIM_STAMP(3);
   if (!rep) return;
 
   // ---- the FP sums: slices -> dense, inside this launch.  The last block of a group to arrive adds the group's
@@ -734,6 +812,30 @@ __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const
     p.dense[(tb == 0 ? p.geom.off_pt : p.geom.off_ut) + (int)s_cm.slot_state[slot] * nb + b] = t;
   }
   if (tid == 0) p.fold_sync[n_groups] = p.fold_sync[n_groups + 1] = 0;
+#ifdef MSIM_TRACE
+  if (tid == 0) {
+    const unsigned long long now = peer_now_ns();
+    const int nblk = min((int)gridDim.x, 1024);
+    unsigned long long lo[4], hi[4];
+    for (int k = 0; k < 4; k++) lo[k] = ~0ull, hi[k] = 0;
+    for (int b = 0; b < nblk; b++)
+      for (int k = 0; k < 4; k++) {
+        const unsigned long long t = *(volatile unsigned long long *)&g_trace[b][k];
+        lo[k] = t < lo[k] ? t : lo[k];
+        hi[k] = t > hi[k] ? t : hi[k];
+      }
+    const unsigned long long t0 = lo[0];
+    printf("trace n %lld entry %llu..%llu loop %llu..%llu drained %llu..%llu flushed %llu..%llu folded %llu (ns)\n", (long long)p.n,
+           lo[0] - t0, hi[0] - t0, lo[1] - t0, hi[1] - t0, lo[2] - t0, hi[2] - t0, lo[3] - t0, hi[3] - t0, now - t0);
+    if (p.n == 100000000)  // the full table once: block, SM, start of the loop, every warp's end, counters flushed (us)
+      for (int b = 0; b < nblk; b++) {
+        printf("tb %d sm %u wave %u loop %.1f warps", b, *(volatile unsigned *)&g_trace_sm[b] & 0xffffu, (*(volatile unsigned *)&g_trace_sm[b] >> 16 & 1u) + 100 * (*(volatile unsigned *)&g_trace_sm[b] >> 20),
+               (double)(g_trace[b][1] - t0) * 1e-3);
+        for (int w = 0; w < SWARPS; w++) printf(" %.0f", (double)(*(volatile unsigned long long *)&g_trace_warp[b][w] - t0) * 1e-3);
+        printf(" flushed %.0f\n", (double)(g_trace[b][3] - t0) * 1e-3);
+      }
+  }
+#endif
   if (PEER && p.peer.world > 1) staged_peer_merge(p);
 }
 

@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 os.environ["MSIM_B200_LIB"] = os.path.join(ROOT, "build", "variants", "libmsim_trace.so")
 import microsimulation_b200 as m, microsimulation_b200.api as api
 m.init(0)
-for n in (1000, 12500000, 100000000):
+for n in (1000, 12500000, 100000000, 100000000, 100000000):
     for rep in range(2):
         api.person_run_device(12345, 0, n, 6, 0.03)
         print("n=%d rep=%d kernel_ms %.4f" % (n, rep, api.last_kernel_ms()), flush=True)

@@ -35,7 +35,7 @@ calls = {
  "msim_dense_device_ptr#p": "(None, buf)", "msim_dense_fetch#n": "(None, C.c_int64(9))",
  "msim_r_rng_advance_substream#n": "(buf, None)", "msim_r_rng_advance_substream#seed": "(None, ibuf)",
  "msim_set_report_options": "(None,)", "msim_person_fetch_indiv": "(None, C.c_int64(5), None)",
- "msim_microbench": "(2, C.c_int64(256), 1, None)",
+ "msim_microbench": "(2, C.c_int64(256), 1, None)", "msim_last_wave_share": "(None,)",
  "msim_table_free": "(None,)", "msim_report_free": "(None,)", "msim_set_stream": "(None, 0)",
 }
 if __name__ == "__main__" and len(sys.argv) > 1:

@@ -172,6 +172,35 @@ def test_person_schedules_agree_bit_for_bit(msim):
     _schedules_equal(out["generic"], out["staged"])
 
 
+def test_person_wave_share_never_changes_results(msim):
+    """Two blocks per SM: the favoured block's share of the persons (msim_set_wave_share; adapted from the waves'
+    finishing times by default) moves persons between blocks, nothing else: rows, counts and integer tables are
+    identical at the smallest, the largest and the adapted share, and equal to the generic schedule's."""
+    import microsimulation_b200.api as api
+    n, out = 2 * 10 ** 6 + 77, {}
+    api.set_person_schedule("generic")
+    api.person_run_device(12345, 5, n, 1 | 4)
+    ref = (api.person_fetch_rowlog(), api.person_fetch_counts(), msim.person_report(12345, 5, n, 0.03)[0])
+    api.set_person_schedule("staged")
+    try:
+        for share in (0.40, 0.65, 0.0, 0.0):  # adapted: the second run uses what the first one's clocks said
+            api.set_wave_share(share) if share else None
+            api.person_run_device(12345, 5, n, 1 | 4)
+            used = api.last_wave_share()
+            assert (abs(used - share) < 1e-3) if share else (0.40 <= used <= 0.65), (share, used)
+            got = (api.person_fetch_rowlog(), api.person_fetch_counts(), msim.person_report(12345, 5, n, 0.03)[0])
+            _schedules_equal(ref, got)
+            if share == 0.65:
+                api.set_wave_share(0.0)
+        # a launch too small for two waves is not split
+        api.person_run_device(12345, 0, 1000, 4)
+        assert api.last_wave_share() == 0.0
+        with pytest.raises(msim.MsimError):
+            api.set_wave_share(0.9)
+    finally:
+        api.set_wave_share(0.0)
+
+
 def _schedules_equal(x, y):
     (ra, ca, pa), (rb, cb, pb) = x, y
     for k in ra:
