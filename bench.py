@@ -393,16 +393,21 @@ def measure_calib(args, steps, rank, world, with_cpu):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
     launches = m.launch_count() - launches0
+    lists = sweep(True)  # + D2H of the 98 KB vector and the per-set lists; the first call sets up the host side
+    e2e_steps = max(1, min(steps, args.e2e_steps))
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
-    lists = sweep(True)  # + D2H of the 98 KB vector and the per-set lists
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    for _ in range(e2e_steps):
+        lists = sweep(True)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     gs, gp = D.calibration_grid(world, N_SETS)
     out = {"workload": workload_name("calib"), "value": N_SETS * CALIB_PERSONS / (ms * 1e-3), "unit": "person-simulations/s",
            "ms_per_step": ms, "kernel_ms_rank0": kernel_ms, "kernel": "calib_shared_kernel (csrc/calib_shared.cuh)",
            "event_loop_kernel_ms_rank0": event_loop_ms, "scaling": "strong", "gpu_launches": int(launches),
            "split": {"set_groups": gs, "person_groups": gp},
            "e2e": {"value": N_SETS * CALIB_PERSONS / (e2e_ms * 1e-3), "unit": "person-simulations/s", "ms_per_step": e2e_ms,
-                   "h2d_bytes_per_step": N_SETS * 48, "d2h_bytes_per_step": N_SETS * 48 * 8},
+                   "steps": e2e_steps, "h2d_bytes_per_step": N_SETS * 48, "d2h_bytes_per_step": N_SETS * 48 * 8},
            "persons_counted_per_set": float(np.sum([lists[0].get(k, np.zeros(10))[0] for k in ("DiseaseFree", "Precursor", "PreClinical", "Clinical")]))}
     if with_cpu and rank == 0:
         from oracle import parallel
@@ -636,7 +641,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--persons", type=int, default=10 ** 8, help="persons per GPU per step (the weak-scaling headline)")
     ap.add_argument("--workload", default="report", choices=["rowlog", "report", "calib"])
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-sample", type=int, default=0, help="persons per host process for the CPU legs (0: 1e6 report / 5e6 rowlog / 2.5e5 calib)")
     ap.add_argument("--no-other-workload", action="store_true", help="measure only the chosen workload")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline leg (profiling runs)")
