@@ -451,3 +451,18 @@ def test_emulated_cost_report(oracle, emu, rate, start_age):
     assert a.shape == b.shape and np.array_equal(a[:, :2], b[:, :2])
     np.testing.assert_allclose(a[:, 2], b[:, 2], rtol=1e-13)
     assert abs(ca - cb) <= 1e-12 * abs(cb)
+
+
+def test_wave_share_is_validated_without_a_device():
+    """msim_set_wave_share (scheduling of the staged person-r kernel): 0 = adapt, 0.40..0.65 = fixed, anything else is an
+    argument error; no launch has happened, so there is no share to report."""
+    import microsimulation_b200 as m
+    import microsimulation_b200.api as api
+    for ok in (0.0, -1.0, 0.40, 0.5, 0.65):
+        api.set_wave_share(ok)
+    for bad in (0.2, 0.39, 0.66, 1.0):
+        with pytest.raises(m.MsimError) as e:
+            api.set_wave_share(bad)
+        assert e.value.code == -3, bad  # MSIM_ERR_ARG
+    api.set_wave_share(0.0)
+    assert api.last_wave_share() == 0.0
