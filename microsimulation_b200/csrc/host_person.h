@@ -131,14 +131,23 @@ int person_enqueue_staged(const msim_person_shard *sh, int64_t capacity, int64_t
   // with the merge across GPUs in the launch's tail (msim_peer_merge): instantiations of their own
   static const StagedKernel peer_kernels[4] = {person_staged_kernel<2, true>, person_staged_kernel<3, true>,
                                                person_staged_kernel<6, true>, person_staged_kernel<7, true>};
+  // with a report on the built models' partition {0, 1, ..., 100, 1e6} (the default): instantiations without the
+  // search for other partitions in their code
+  static const StagedKernel unit_kernels[4] = {person_staged_kernel<2, false, true>, person_staged_kernel<3, false, true>,
+                                               person_staged_kernel<6, false, true>, person_staged_kernel<7, false, true>};
+  static const StagedKernel unit_peer_kernels[4] = {person_staged_kernel<2, true, true>, person_staged_kernel<3, true, true>,
+                                                    person_staged_kernel<6, true, true>, person_staged_kernel<7, true, true>};
   const bool with_peers = g.peers.mode && g.peers.world > 1 && (p.outputs & OUT_REPORT);
   if (with_peers && (p.outputs & OUT_INDIV)) return fail(MSIM_ERR_ARG, "peer merge: not with MSIM_OUT_INDIV (individual totals stay on their rank)");
-  const StagedKernel kernel = with_peers ? peer_kernels[((p.outputs & 4u) >> 1) | (p.outputs & 1u)]
-                              : (p.outputs & OUT_INDIV) ? person_staged_kernel<OUT_RUNTIME> : kernels[p.outputs & 7u];
+  const bool unit = (p.outputs & OUT_REPORT) && !(p.outputs & OUT_INDIV) && p.geom.unit;
+  const unsigned rep_idx = ((p.outputs & 4u) >> 1) | (p.outputs & 1u);  // among the four combinations with a report
+  const StagedKernel kernel = with_peers ? (unit ? unit_peer_kernels : peer_kernels)[rep_idx]
+                              : (p.outputs & OUT_INDIV) ? person_staged_kernel<OUT_RUNTIME>
+                              : unit ? unit_kernels[rep_idx] : kernels[p.outputs & 7u];
   // blocks per SM for this (kernel, shared memory) pair: asked once, the answer does not change
-  static size_t occ_smem[13] = {0};
-  static int occ_per_sm[13] = {0};
-  const unsigned slot = with_peers ? 9u + (((p.outputs & 4u) >> 1) | (p.outputs & 1u)) : (p.outputs & OUT_INDIV) ? 8u : (p.outputs & 7u);
+  static size_t occ_smem[STAGED_KERNELS] = {0};
+  static int occ_per_sm[STAGED_KERNELS] = {0};
+  const unsigned slot = (with_peers ? 9u + rep_idx : (p.outputs & OUT_INDIV) ? 8u : (p.outputs & 7u)) + (unit ? 13u : 0u);
   int per_sm = occ_per_sm[slot];
   if (per_sm == 0 || occ_smem[slot] != smem) {
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

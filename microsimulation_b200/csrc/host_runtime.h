@@ -31,6 +31,8 @@ struct DevBuf {
   size_t bytes = 0;
 };
 
+constexpr int STAGED_KERNELS = 26;  // instantiations of person_staged_kernel the host chooses from (host_person.h)
+
 struct Ctx {
   bool inited = false;
   int device = 0;
@@ -61,7 +63,8 @@ struct Ctx {
   DevBuf peers_map_dev;
   int person_kernel = 0;  // 0 = staged schedule (person_staged.cuh), 1 = generic cohort kernel
   // share of the tiles the first wave of blocks takes, per kernel instantiation of the staged schedule (host_person.h)
-  double wave_share[13] = {0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5};
+  double wave_share[STAGED_KERNELS];  // (0.5 each to begin with: Ctx())
+  Ctx() { for (double &f : wave_share) f = 0.5; }
   double wave_share_fixed = 0;  // msim_set_wave_share: > 0 switches the adaptation off
   int last_wave_slot = -1;      // of the last staged launch (-1: one wave)
   double last_wave_share = 0;

@@ -271,7 +271,8 @@ struct StagedAcc {
 // 384 x 2 (80 registers, spills): 2.99 / 4.92 / 4.90.  (Warps per SM that are not a multiple of 4 leave the four
 // schedulers unevenly loaded.)
 constexpr unsigned OUT_RUNTIME = 0xffu;
-template <unsigned OUT>
+// UNIT: instantiated for the built models' partition {0, 1, ..., 100, 1e6} (ReportGeom::unit; report_cells<true>)
+template <unsigned OUT, bool UNIT = false>
 struct StagedEnvT {
   typedef MrgSource Src;
   Src src;
@@ -322,7 +323,11 @@ struct StagedEnvT {
       // (a short form of the cells for a person's first interval — no left partial, no left exponential — was tried
       // here, twice: 5.99 against 5.56 ms per 1e8 persons with the run-time-flag kernel, 4.93 against 4.77 with this
       // one; the second copy of the cell code costs more in instruction fetch and scheduling than the arithmetic it skips)
-      const ReportCells c = report_cells(*geom, cursor, state, kind, lhs, rhs);
+      if (UNIT && !(cursor.valid && cursor.t == lhs)) {  // person-r reports from previous() to now(): every interval starts where the last one ended
+        *acc.err = MSIM_ERR_MODEL_DEV;
+        return;
+      }
+      const ReportCells c = report_cells<UNIT>(*geom, cursor, state, kind, lhs, rhs);
       acc.add(c, geom->discount_rate != 0.0);
       if (out() & 8u) current += report_brief(*geom, c, lhs, rhs);  // addBrief, microsimulation.h:929-932
     }
@@ -514,9 +519,9 @@ __device__ unsigned g_trace_sm[1024];
 #define MSIM_STAMP(k) do { } while (0)
 #endif
 
-template <unsigned OUT, bool PEER = false>
+template <unsigned OUT, bool PEER = false, bool UNIT = false>
 __global__ void __launch_bounds__(SBLOCK, MSIM_SMINB) person_staged_kernel(const __grid_constant__ StagedParams p) {
-  typedef StagedEnvT<OUT> StagedEnv;
+  typedef StagedEnvT<OUT, UNIT> StagedEnv;
   const unsigned outs = (OUT == OUT_RUNTIME) ? p.outputs : OUT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // shared layout: [per-warp queues | per-warp row staging (row log) | report counters]

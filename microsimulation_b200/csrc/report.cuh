@@ -135,13 +135,17 @@ MSIM_HD double report_part(const ReportGeom &g, int i) { return g.part[i]; }
 
 // (The (int)x below stays a conversion instruction: x + 1.5 * 2^52, the low word and a comparison — floor without the
 // conversion — measured slower, 4.63 against 4.61 ms per 1e8 persons; the conversions of constants did pay: nb2, part[].)
-// index of the largest partition point <= x (set<greater>::lower_bound, :937-938)
+// index of the largest partition point <= x (set<greater>::lower_bound, :937-938).  UNIT: the caller knows that
+// g.unit is set (a kernel instantiated for the built models' partition: the general search, never executed there, is
+// then not in its code at all — 230 instructions of the person-r kernel's loop, 2% of its time).
+template <bool UNIT = false>
 MSIM_HD int report_bin(const ReportGeom &g, double x) {
   const int nb = g.n_bin;
-  if (g.unit) {  // every built model's partition {0, 1, ..., 100, 1e6}: exact without a search
+  if (UNIT || g.unit) {  // every built model's partition {0, 1, ..., 100, 1e6}: exact without a search
     if (x >= g.part_last) return nb - 1;
     return (x > 0.0) ? ((x < g.nb2) ? (int)x : nb - 2) : 0;
   }
+  if (UNIT) return 0;  // (not reached)
   double y = (x - g.part_start) * g.part_inv_delta;
   int i = (y > 0.0) ? ((y < g.nb2) ? (int)y : nb - 2) : 0;
   while (i + 1 < nb && g.part[i + 1] <= x) i++;
@@ -234,20 +238,24 @@ struct ReportCells {
   double pt_hi, ut_hi, pt_lo, ut_lo;
 };
 
+// UNIT: instantiated for the built models' partition (report_bin), by a caller that has made sure the interval starts
+// where the process's previous one ended (cur.valid && cur.t == lhs: true of every interval of a model that reports
+// from previous() to now()), so that the left end's bin search and exponential are not in its code either.
+template <bool UNIT = false>
 MSIM_HD ReportCells report_cells(const ReportGeom &g, ReportCursor &cur, int state, int event, double lhs, double rhs) {
   const int nb = g.n_bin;
   const bool disc = g.discount_rate != 0.0;  // rate 0: ut == pt, filled in at finalisation
   ReportCells c;
   int lo;
   double elhs = 1.0;
-  if (cur.valid && cur.t == lhs) {
+  if (UNIT || (cur.valid && cur.t == lhs)) {
     lo = cur.bin;
     elhs = cur.e;
   } else {
-    lo = report_bin(g, lhs);
+    lo = report_bin<UNIT>(g, lhs);
     if (disc) elhs = report_decay(g, lhs);
   }
-  const int hi = report_bin(g, rhs);
+  const int hi = report_bin<UNIT>(g, rhs);
   const double erhs = disc ? report_decay(g, rhs) : 1.0;
   cur.t = rhs;
   cur.e = erhs;

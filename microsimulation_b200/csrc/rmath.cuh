@@ -70,7 +70,11 @@ struct RMath {
     const int64_t ub = fm_bits(u);
     const int j = 1023 - (int)(ub >> 52) + ((ub & 0x000fffffffffffffll) == 0 ? 1 : 0);
     double a = MSIM_EXP_A[j - 1 < 63 ? j - 1 : 63];
-    for (int k = 63; k < j - 1; k++) a += q0;  // u < 2^-64: no generator here produces it (u must be a normal number)
+    // u < 2^-64: no generator here produces it (RngStream's and R's uniforms stay above 2^-33), so the loop is kept as a
+    // loop: unrolled, as the compiler has it otherwise, it sat — 78 instructions, never executed — in the middle of
+    // the person-r kernel's loop
+#pragma unroll 1
+    for (int k = 63; k < j - 1; k++) a += q0;
     u = fm_from_bits(ub + ((int64_t)j << 52));
     u -= 1.;
     if (u <= q0) return a + u;
