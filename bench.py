@@ -308,7 +308,8 @@ def measure(args, workload, steps, P, rank, local, world, clocks_wanted, with_e2
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     step_ms = float(t[0])
     out = {"value": world * P / (step_ms * 1e-3), "ms_per_step": step_ms, "rows": int(rows), "kernel_ms": kernel_ms_one,
-           "launches": int(launches), "clocks": clocks, "persons_per_gpu": P}
+           "launches": int(launches), "clocks": clocks, "persons_per_gpu": P,
+           "wave_share": api.last_wave_share()}  # rank 0's: the favoured blocks' share of the persons in the timed launches
     if world > 1 and report_mode:
         out["merge_check"] = merge_check(P, first, outputs, rate, world)
     if not with_e2e:
@@ -576,6 +577,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.workload) + "; %d persons per GPU per step" % P,
                        "seed": "12345x6", "persons_per_gpu": P, "rows_per_step_rank0": main["rows"],
+                       "wave_share_rank0": main["wave_share"],
                        "merge": (("inside the simulation launches: the block that finishes the fold sends the accumulator vector to the other "
                                   "ranks over NVLink peer memory; the next launch (or, after the last step, one small launch) adds the "
                                   "ranks' vectors in rank order" if PEER_MERGE else
