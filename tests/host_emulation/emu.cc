@@ -423,11 +423,21 @@ int emu_person_run(const msim_person_shard *sh, int grid, msim_table *rowlog, do
 // The staged schedule of person_staged.cuh, one warp at a time, lanes in order:
 // the same stage functions and the same queue discipline (push by lane order,
 // pop the top <= 32 entries) as person_staged_kernel.
-int emu_person_run_staged(const msim_person_shard *sh, int grid, msim_table *rowlog, double counts[9], msim_report *report) {
+// share > 0: the kernel's two waves of blocks (grid must be even): the first grid / 2 blocks deal the tiles
+// [0, split) to their warps in turn, the others [split, tiles), each wave from the substream state of its range's first
+// person (host_person.h, person_enqueue_staged; person_staged.cuh "waves").  share <= 0: one wave.
+int emu_person_run_staged_waves(const msim_person_shard *sh, int grid, double share, msim_table *rowlog, double counts[9],
+                                msim_report *report) {
   if (!mrg_seed_ok(sh->seed)) return MSIM_ERR_SEED;
   const int SB = 128, SW = 4;
-  StreamStart st;
-  make_start(sh->seed, sh->first_person + 1, grid, &st, SB);
+  const bool two = share > 0;
+  if (two && (grid % 2)) return MSIM_ERR_ARG;
+  const int wave_blocks = two ? grid / 2 : grid;
+  const int64_t all_tiles = (sh->n + 31) / 32;
+  const int64_t split = two ? std::min<int64_t>(all_tiles, (int64_t)(share * (double)all_tiles + 0.5)) : all_tiles;
+  StreamStart st, st_b;
+  make_start(sh->seed, sh->first_person + 1, wave_blocks, &st, SB);
+  make_start(sh->seed, sh->first_person + 1 + 32 * split, wave_blocks, &st_b, SB);
   person_r::Consts K = person_r::make_consts();
   ReportGeom geom = ages_geom(person_r::N_STATE, person_r::N_EVENT, sh->discount_rate);
   std::vector<double> dense(geom.total, 0.0);
@@ -440,7 +450,7 @@ int emu_person_run_staged(const msim_person_shard *sh, int grid, msim_table *row
   env.acc.d = dense.data();
   double cnt[9] = {0};
   env.counts = cnt;
-  const int64_t n_tiles = (sh->n + 31) / 32, GW = (int64_t)grid * SW;
+  const int64_t GW = (int64_t)wave_blocks * SW;
   struct E1 {
     person_r::ParkedOnset p;
     int64_t idx;
@@ -450,12 +460,16 @@ int emu_person_run_staged(const msim_person_shard *sh, int grid, msim_table *row
     int64_t idx;
   };
   int err = 0;
-  for (int64_t gw = 0; gw < GW; gw++) {
+  for (int64_t gw_all = 0; gw_all < (two ? 2 : 1) * GW; gw_all++) {
+    const bool wave_b = gw_all >= GW;
+    const int64_t gw = wave_b ? gw_all - GW : gw_all;
+    const StreamStart &stw = wave_b ? st_b : st;
+    const int64_t n_tiles = wave_b ? all_tiles : split;  // end of the wave's range
     Mrg32k3a sub[32];
-    for (int lane = 0; lane < 32; lane++) sub[lane] = thread_start_state(st, (unsigned)(gw * 32 + lane));
+    for (int lane = 0; lane < 32; lane++) sub[lane] = thread_start_state(stw, (unsigned)(gw * 32 + lane));
     std::vector<E1> q1;
     std::vector<E2> q2;
-    for (int64_t tile = gw;;) {
+    for (int64_t tile = (wave_b ? split : 0) + gw;;) {
       const bool last = tile >= n_tiles;
       std::vector<E2> ready;
       if (q2.size() >= 32 || (last && q1.empty() && !q2.empty())) {
@@ -503,6 +517,10 @@ int emu_person_run_staged(const msim_person_shard *sh, int grid, msim_table *row
   }
   if (report) dense_to_report_impl(dense.data(), geom, report);
   return 0;
+}
+
+int emu_person_run_staged(const msim_person_shard *sh, int grid, msim_table *rowlog, double counts[9], msim_report *report) {
+  return emu_person_run_staged_waves(sh, grid, 0.0, rowlog, counts, report);
 }
 
 // the accumulator vector a shard contributes to the all-reduce: dense report cells, then the 9 counts

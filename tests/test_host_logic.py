@@ -203,6 +203,26 @@ def test_emulated_person_r_staged_schedule(oracle, emu, first, n, grid):
     emu.emu_report_free(C.byref(r))
 
 
+@pytest.mark.parametrize("first,n,grid,share", [(0, 20000, 4, 0.55), (12345, 5000, 40, 0.40), (7, 255, 2, 0.65),
+                                                (0, 100000, 8, 0.5), (3, 40, 2, 0.6), (0, 33, 2, 0.5)])
+def test_emulated_person_r_two_waves(oracle, emu, first, n, grid, share):
+    """The staged kernel's two waves of blocks (the favoured blocks take the tiles [0, split), the others the rest, each
+    wave from the substream state of its range's first person): every person still gets its own substream and is
+    simulated once, whatever the share."""
+    seed = (C.c_double * 6)(*[12345.0] * 6)
+    sh = PersonShard(seed, first, n, 7, 0.03)
+    t, r, cnt = Table(), Report(), (C.c_double * 9)()
+    assert emu.emu_person_run_staged_waves(C.byref(sh), C.c_int(grid), C.c_double(share), C.byref(t), cnt, C.byref(r)) == 0
+    e, er = t.to_dict(), r.to_dict()
+    ref = oracle.person_run(12345, first, n, rowlog=True, report=True, discount_rate=0.03)
+    assert_rowlog_close(e, ref["rowlog"], 4e-15)
+    assert np.array_equal(np.array(cnt[:8]), ref["counts"][:8])
+    assert_report_close(er, ref["report"], rtol=1e-10)
+    emu.emu_table_free(C.byref(t))
+    emu.emu_report_free(C.byref(r))
+    assert emu.emu_person_run_staged_waves(C.byref(sh), C.c_int(3), C.c_double(0.5), C.byref(t), cnt, C.byref(r)) == -3  # odd grid
+
+
 @pytest.mark.parametrize("n", [0, 1, 10, 700, 5000, 60000])
 def test_emulated_sequential_stream_models(oracle, emu, n):
     """Per-position draw counts + chunked chain resolution == the reference's person-after-person consumption."""
