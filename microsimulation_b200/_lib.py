@@ -23,16 +23,16 @@ class Table(C.Structure):
                 ("data", C.POINTER(C.c_double))]
 
     def to_dict(self, copy=True):
-        out = {}
-        for j in range(self.ncol):
-            name = self.colnames[j].decode()
-            if self.nrow:
-                base = C.addressof(self.data.contents) + 8 * j * self.nrow
-                col = np.ctypeslib.as_array((C.c_double * self.nrow).from_address(base))
-                out[name] = col.copy() if copy else col
-            else:
-                out[name] = np.zeros(0)
-        return out
+        # one view of the whole column-major table, then a row of it per column (a ctypes array per column costs more
+        # than the copy itself for the report's small tables)
+        n, k = int(self.nrow), int(self.ncol)
+        names = [self.colnames[j].decode() for j in range(k)]
+        if not n:
+            return {name: np.zeros(0) for name in names}
+        whole = np.ctypeslib.as_array((C.c_double * (n * k)).from_address(C.addressof(self.data.contents))).reshape(k, n)
+        if copy:
+            whole = whole.copy()
+        return {name: whole[j] for j, name in enumerate(names)}
 
 
 class Report(C.Structure):
